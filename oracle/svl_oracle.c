@@ -1,0 +1,894 @@
+/*
+ * svl_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE (see svl_oracle.h).
+ *
+ * CPU restatement of SeismoVLAB/SVL's explicit hot path.  Citations are
+ * relative to /root/reference/02-Run_Process/.  Compile with
+ * -ffp-contract=off so that no FMA contraction changes the rounding relative
+ * to the reference's plain C++ arithmetic.
+ */
+#include "svl_oracle.h"
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* 04-Elements/11-Integration/GaussQuadrature.cpp:311-316, 733-742:
+ * 15-digit literal, weights 1, x fastest.                                      */
+#define GP 0.577350269189626
+
+static const double HX[8] = {-1, 1, 1, -1, -1, 1, 1, -1};   /* lin3DHexa8.cpp:791-798 */
+static const double HY[8] = {-1, -1, 1, 1, -1, -1, 1, 1};
+static const double HZ[8] = {-1, -1, -1, -1, 1, 1, 1, 1};
+static const double QX[4] = {-1, 1, 1, -1};                  /* lin2DQuad4.cpp:673-676 */
+static const double QY[4] = {-1, -1, 1, 1};
+
+/* ------------------------------------------------------------------------ */
+/* materials                                                                 */
+/* ------------------------------------------------------------------------ */
+/* 02-Materials/01-Linear/Elastic3DLinear.cpp:18-27 */
+void svlo_elastic3d_C(double E, double nu, double C[36]) {
+    double c1 = E * (1.0 - nu) / (1.0 - 2.0 * nu) / (1.0 + nu);
+    double c2 = E * nu / (1.0 - 2.0 * nu) / (1.0 + nu);
+    double c3 = E / (2.0 * (1.0 + nu));
+    memset(C, 0, 36 * sizeof(double));
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) C[6 * i + j] = (i == j) ? c1 : c2;
+    C[21] = C[28] = C[35] = c3;
+}
+/* 02-Materials/01-Linear/Elastic2DPlaneStrain.cpp:18-26 */
+void svlo_planestrain_C(double E, double nu, double C[9]) {
+    double c1 = E * (1.0 - nu) / (1.0 - 2.0 * nu) / (1.0 + nu);
+    double c2 = E * nu / (1.0 - 2.0 * nu) / (1.0 + nu);
+    double c3 = E / (2.0 * (1.0 + nu));
+    double t[9] = {c1, c2, 0, c2, c1, 0, 0, 0, c3};
+    memcpy(C, t, sizeof t);
+}
+
+/* 02-Materials/02-NonLinear/Plastic3DJ2.cpp:206-259 (UpdateState cond==1) and
+ * :163-170 (CommitState).  state = eps_p(6) | backstress(6) | alpha.          */
+void svlo_j2_update(const double par[6], const double e_in[6], double st[13], double sig[6]) {
+    const double K = par[0], G = par[1], H = par[3], beta = par[4], Sy = par[5];
+    double e[6] = {e_in[0], e_in[1], e_in[2], 0.5 * e_in[3], 0.5 * e_in[4], 0.5 * e_in[5]};
+    double tr = e[0] + e[1] + e[2];
+    double one[6] = {1, 1, 1, 0, 0, 0};
+    double s_tr[6], xi[6];
+    for (int i = 0; i < 6; i++) {
+        double dev = e[i] - 1.0 / 3.0 * tr * one[i];
+        s_tr[i] = 2.0 * G * (dev - st[i]);
+        xi[i] = s_tr[i] - st[6 + i];
+    }
+    double nrm = sqrt(xi[0] * xi[0] + xi[1] * xi[1] + xi[2] * xi[2] +
+                      2.0 * (xi[3] * xi[3] + xi[4] * xi[4] + xi[5] * xi[5]));   /* :326-329 */
+    double f = nrm - sqrt(2.0 / 3.0) * (Sy + st[12] * beta * H);
+    if (f <= 0) {
+        for (int i = 0; i < 6; i++) sig[i] = K * tr * one[i] + s_tr[i];
+    } else {
+        double dg = f / (2.0 * G + 2.0 / 3.0 * H);
+        st[12] += sqrt(2.0 / 3.0) * dg;
+        for (int i = 0; i < 6; i++) {
+            double n = xi[i] / nrm;
+            st[6 + i] += 2.0 / 3.0 * (1.0 - beta) * H * dg * n;
+            st[i] += dg * n;
+            sig[i] = K * tr * one[i] + s_tr[i] - 2.0 * G * dg * n;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------ */
+/* hex8 kinematics: lin3DHexa8.cpp:755-785 (J), :810-853 (B)                 */
+/* ------------------------------------------------------------------------ */
+static void hex8_dN_local(double r, double s, double t, double dN[8][3], double N[8]) {
+    for (int i = 0; i < 8; i++) {
+        double a = 1.0 + HX[i] * r, b = 1.0 + HY[i] * s, c = 1.0 + HZ[i] * t;
+        dN[i][0] = 1.0 / 8.0 * HX[i] * b * c;
+        dN[i][1] = 1.0 / 8.0 * HY[i] * a * c;
+        dN[i][2] = 1.0 / 8.0 * HZ[i] * a * b;
+        if (N) N[i] = 1.0 / 8.0 * a * b * c;
+    }
+}
+static double inv3(const double J[9], double Ji[9]) {
+    double c00 = J[4] * J[8] - J[5] * J[7], c01 = J[5] * J[6] - J[3] * J[8], c02 = J[3] * J[7] - J[4] * J[6];
+    double det = J[0] * c00 + J[1] * c01 + J[2] * c02;
+    double id = 1.0 / det;
+    Ji[0] = c00 * id; Ji[1] = (J[2] * J[7] - J[1] * J[8]) * id; Ji[2] = (J[1] * J[5] - J[2] * J[4]) * id;
+    Ji[3] = c01 * id; Ji[4] = (J[0] * J[8] - J[2] * J[6]) * id; Ji[5] = (J[2] * J[3] - J[0] * J[5]) * id;
+    Ji[6] = c02 * id; Ji[7] = (J[1] * J[6] - J[0] * J[7]) * id; Ji[8] = (J[0] * J[4] - J[1] * J[3]) * id;
+    return det;
+}
+/* dNdx[i][b] = d N_i / d x_b at (r,s,t); returns |det J|; N optional           */
+static double hex8_grad(const double *X, double r, double s, double t, double dNdx[8][3], double N[8]) {
+    double dN[8][3], J[9] = {0}, Ji[9];
+    hex8_dN_local(r, s, t, dN, N);
+    for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) {
+            double v = 0;
+            for (int i = 0; i < 8; i++) v += dN[i][a] * X[3 * i + b];
+            J[3 * a + b] = v;
+        }
+    double det = inv3(J, Ji);
+    for (int i = 0; i < 8; i++)
+        for (int b = 0; b < 3; b++)
+            dNdx[i][b] = Ji[3 * b + 2] * dN[i][2] + Ji[3 * b + 1] * dN[i][1] + Ji[3 * b + 0] * dN[i][0];
+    return fabs(det);
+}
+static void hex8_gp(int g, double *r, double *s, double *t) {
+    *r = (g & 1) ? GP : -GP; *s = (g & 2) ? GP : -GP; *t = (g & 4) ? GP : -GP;
+}
+/* strain Voigt [11,22,33,12,23,13] engineering shear: lin3DHexa8.cpp:845-850, :721-741 */
+void svlo_hex8_strain(const double *X, const double *U, double eps[8][6]) {
+    for (int g = 0; g < 8; g++) {
+        double r, s, t, d[8][3];
+        hex8_gp(g, &r, &s, &t);
+        hex8_grad(X, r, s, t, d, NULL);
+        double e[6] = {0};
+        for (int i = 0; i < 8; i++) {
+            const double *u = U + 3 * i;
+            e[0] += d[i][0] * u[0];
+            e[1] += d[i][1] * u[1];
+            e[2] += d[i][2] * u[2];
+            e[3] += d[i][1] * u[0] + d[i][0] * u[1];
+            e[4] += d[i][2] * u[1] + d[i][1] * u[2];
+            e[5] += d[i][2] * u[0] + d[i][0] * u[2];
+        }
+        memcpy(eps[g], e, sizeof e);
+    }
+}
+/* f = sum_gp w |J| B^T sigma : lin3DHexa8.cpp:382-412 */
+void svlo_hex8_force(const double *X, const double sig[8][6], double f[24]) {
+    memset(f, 0, 24 * sizeof(double));
+    for (int g = 0; g < 8; g++) {
+        double r, s, t, d[8][3];
+        hex8_gp(g, &r, &s, &t);
+        double wd = 1.0 * hex8_grad(X, r, s, t, d, NULL);
+        const double *sg = sig[g];
+        for (int i = 0; i < 8; i++) {
+            f[3 * i + 0] += wd * (d[i][0] * sg[0] + d[i][1] * sg[3] + d[i][2] * sg[5]);
+            f[3 * i + 1] += wd * (d[i][1] * sg[1] + d[i][0] * sg[3] + d[i][2] * sg[4]);
+            f[3 * i + 2] += wd * (d[i][2] * sg[2] + d[i][1] * sg[4] + d[i][0] * sg[5]);
+        }
+    }
+}
+/* lin3DHexa8.cpp:242-285: consistent mass then optional row-sum lumping        */
+void svlo_hex8_mass(const double *X, double rho, int lumped, double M[576]) {
+    memset(M, 0, 576 * sizeof(double));
+    for (int g = 0; g < 8; g++) {
+        double r, s, t, d[8][3], N[8];
+        hex8_gp(g, &r, &s, &t);
+        double wd = 1.0 * rho * hex8_grad(X, r, s, t, d, N);
+        for (int i = 0; i < 8; i++)
+            for (int j = 0; j < 8; j++)
+                for (int c = 0; c < 3; c++) M[(3 * i + c) * 24 + 3 * j + c] += wd * N[i] * N[j];
+    }
+    if (lumped)
+        for (int i = 0; i < 24; i++)
+            for (int j = 0; j < 24; j++)
+                if (i != j) { M[i * 24 + i] += M[i * 24 + j]; M[i * 24 + j] = 0.0; }
+}
+static void hex8_B(const double d[8][3], double B[6][24]) {
+    memset(B, 0, 6 * 24 * sizeof(double));
+    for (int i = 0; i < 8; i++) {
+        B[0][3 * i] = d[i][0]; B[1][3 * i + 1] = d[i][1]; B[2][3 * i + 2] = d[i][2];
+        B[3][3 * i] = d[i][1]; B[3][3 * i + 1] = d[i][0];
+        B[4][3 * i + 1] = d[i][2]; B[4][3 * i + 2] = d[i][1];
+        B[5][3 * i] = d[i][2]; B[5][3 * i + 2] = d[i][0];
+    }
+}
+/* lin3DHexa8.cpp:288-318 */
+void svlo_hex8_stiffness(const double *X, const double C[36], double K[576]) {
+    memset(K, 0, 576 * sizeof(double));
+    for (int g = 0; g < 8; g++) {
+        double r, s, t, d[8][3], B[6][24], CB[6][24];
+        hex8_gp(g, &r, &s, &t);
+        double wd = 1.0 * hex8_grad(X, r, s, t, d, NULL);
+        hex8_B(d, B);
+        for (int a = 0; a < 6; a++)
+            for (int j = 0; j < 24; j++) {
+                double v = 0;
+                for (int b = 0; b < 6; b++) v += C[6 * a + b] * B[b][j];
+                CB[a][j] = v;
+            }
+        for (int i = 0; i < 24; i++)
+            for (int j = 0; j < 24; j++) {
+                double v = 0;
+                for (int a = 0; a < 6; a++) v += B[a][i] * CB[a][j];
+                K[i * 24 + j] += wd * v;
+            }
+    }
+}
+
+/* ------------------------------------------------------------------------ */
+/* quad4 kinematics: lin2DQuad4.cpp:648-711                                  */
+/* ------------------------------------------------------------------------ */
+static double quad4_grad(const double *X, double r, double s, double dNdx[4][2], double N[4]) {
+    double dN[4][2], J[4] = {0};
+    for (int i = 0; i < 4; i++) {
+        dN[i][0] = 1.0 / 4.0 * QX[i] * (1.0 + QY[i] * s);
+        dN[i][1] = 1.0 / 4.0 * QY[i] * (1.0 + QX[i] * r);
+        if (N) N[i] = 1.0 / 4.0 * (1.0 + QX[i] * r) * (1.0 + QY[i] * s);
+    }
+    for (int a = 0; a < 2; a++)
+        for (int b = 0; b < 2; b++) {
+            double v = 0;
+            for (int i = 0; i < 4; i++) v += dN[i][a] * X[2 * i + b];
+            J[2 * a + b] = v;
+        }
+    double det = J[0] * J[3] - J[1] * J[2];
+    double Ji[4] = {J[3] / det, -J[1] / det, -J[2] / det, J[0] / det};
+    for (int i = 0; i < 4; i++)
+        for (int b = 0; b < 2; b++) dNdx[i][b] = Ji[2 * b + 1] * dN[i][1] + Ji[2 * b + 0] * dN[i][0];
+    return fabs(det);
+}
+static void quad4_gp(int g, double *r, double *s) { *r = (g & 1) ? GP : -GP; *s = (g & 2) ? GP : -GP; }
+/* Voigt [11,22,12]: lin2DQuad4.cpp:705-708 */
+void svlo_quad4_strain(const double *X, const double *U, double eps[4][3]) {
+    for (int g = 0; g < 4; g++) {
+        double r, s, d[4][2];
+        quad4_gp(g, &r, &s);
+        quad4_grad(X, r, s, d, NULL);
+        double e[3] = {0};
+        for (int i = 0; i < 4; i++) {
+            e[0] += d[i][0] * U[2 * i];
+            e[1] += d[i][1] * U[2 * i + 1];
+            e[2] += d[i][1] * U[2 * i] + d[i][0] * U[2 * i + 1];
+        }
+        memcpy(eps[g], e, sizeof e);
+    }
+}
+/* lin2DQuad4.cpp:383-412 */
+void svlo_quad4_force(const double *X, double th, const double sig[4][3], double f[8]) {
+    memset(f, 0, 8 * sizeof(double));
+    for (int g = 0; g < 4; g++) {
+        double r, s, d[4][2];
+        quad4_gp(g, &r, &s);
+        double wd = 1.0 * th * quad4_grad(X, r, s, d, NULL);
+        for (int i = 0; i < 4; i++) {
+            f[2 * i + 0] += wd * (d[i][0] * sig[g][0] + d[i][1] * sig[g][2]);
+            f[2 * i + 1] += wd * (d[i][1] * sig[g][1] + d[i][0] * sig[g][2]);
+        }
+    }
+}
+/* lin2DQuad4.cpp:243-286 */
+void svlo_quad4_mass(const double *X, double th, double rho, int lumped, double M[64]) {
+    memset(M, 0, 64 * sizeof(double));
+    for (int g = 0; g < 4; g++) {
+        double r, s, d[4][2], N[4];
+        quad4_gp(g, &r, &s);
+        double wd = 1.0 * rho * th * quad4_grad(X, r, s, d, N);
+        for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 4; j++)
+                for (int c = 0; c < 2; c++) M[(2 * i + c) * 8 + 2 * j + c] += wd * N[i] * N[j];
+    }
+    if (lumped)
+        for (int i = 0; i < 8; i++)
+            for (int j = 0; j < 8; j++)
+                if (i != j) { M[i * 8 + i] += M[i * 8 + j]; M[i * 8 + j] = 0.0; }
+}
+/* lin2DQuad4.cpp:289-319 */
+void svlo_quad4_stiffness(const double *X, double th, const double C[9], double K[64]) {
+    memset(K, 0, 64 * sizeof(double));
+    for (int g = 0; g < 4; g++) {
+        double r, s, d[4][2], B[3][8] = {{0}}, CB[3][8];
+        quad4_gp(g, &r, &s);
+        double wd = 1.0 * th * quad4_grad(X, r, s, d, NULL);
+        for (int i = 0; i < 4; i++) {
+            B[0][2 * i] = d[i][0]; B[1][2 * i + 1] = d[i][1];
+            B[2][2 * i] = d[i][1]; B[2][2 * i + 1] = d[i][0];
+        }
+        for (int a = 0; a < 3; a++)
+            for (int j = 0; j < 8; j++) {
+                double v = 0;
+                for (int b = 0; b < 3; b++) v += C[3 * a + b] * B[b][j];
+                CB[a][j] = v;
+            }
+        for (int i = 0; i < 8; i++)
+            for (int j = 0; j < 8; j++) {
+                double v = 0;
+                for (int a = 0; a < 3; a++) v += B[a][i] * CB[a][j];
+                K[i * 8 + j] += wd * v;
+            }
+    }
+}
+
+/* ------------------------------------------------------------------------ */
+/* PML matrices: PML3DHexa8.cpp:214-285 (M), 430-568 (C), 288-427 (K),        */
+/* 572-713 (G), 952-996 (stretching);  PML2DQuad4.cpp:233-292, 296-377,       */
+/* 380-464, 655-691.                                                          */
+/* ------------------------------------------------------------------------ */
+void svlo_pml3d_matrices(const double *X, double E, double nu, double rho, const double p[9],
+                         double *M, double *C, double *K, double *G) {
+    const int n = 72;
+    double *out[4] = {M, C, K, G};
+    for (int q = 0; q < 4; q++) if (out[q]) memset(out[q], 0, n * n * sizeof(double));
+    const double mp = p[0], L = p[1], R = p[2], x0[3] = {p[3], p[4], p[5]}, np[3] = {p[6], p[7], p[8]};
+    const double mu = E / (2.0 * (1.0 + nu));                 /* Elastic3DLinear::GetShearModulus */
+    const double lambda = E * nu / (1.0 + nu) / (1.0 - 2.0 * nu);
+    for (int g = 0; g < 8; g++) {
+        double r, s, t, d[8][3], N[8];
+        hex8_gp(g, &r, &s, &t);
+        double D = hex8_grad(X, r, s, t, d, N);
+        double xg[3] = {0, 0, 0};
+        for (int i = 0; i < 8; i++) for (int c = 0; c < 3; c++) xg[c] += N[i] * X[3 * i + c];
+        double Vp = sqrt((lambda + 2.0 * mu) / rho);
+        double bp = L / 10.0;
+        double a0 = (mp + 1.0) * bp / 2.0 / L * log(1.0 / R);
+        double b0 = (mp + 1.0) * Vp / 2.0 / L * log(1.0 / R);
+        double al[3], be[3];
+        for (int c = 0; c < 3; c++) {
+            double pw = pow((xg[c] - x0[c]) * np[c] / L, mp);
+            al[c] = 1.0 + a0 * pw;
+            be[c] = b0 * pw;
+        }
+        const double ax = al[0], ay = al[1], az = al[2], bx = be[0], by = be[1], bz = be[2];
+        /* chi and phi_{x,y,z} for M, C, K, G */
+        double chi[4] = {ax * ay * az, ax * ay * bz + ax * by * az + bx * ay * az,
+                         ax * by * bz + bx * by * az + bx * ay * bz, bx * by * bz};
+        double phi[4][3] = {{0, 0, 0},
+                            {ay * az, ax * az, ax * ay},
+                            {ay * bz + az * by, ax * bz + az * bx, ax * by + ay * bx},
+                            {by * bz, bx * bz, bx * by}};
+        for (int q = 0; q < 4; q++) {
+            double *A = out[q];
+            if (!A) continue;
+            double ch = chi[q];
+            double d1 = -ch * (lambda + mu) / mu / (3.0 * lambda + 2.0 * mu);
+            double d2 = -ch / mu;
+            double o1 = ch * lambda / 2.0 / mu / (3.0 * lambda + 2.0 * mu);
+            for (int j = 0; j < 8; j++)
+                for (int k = 0; k < 8; k++) {
+                    double S = N[j] * N[k] * 1.0 * D;
+                    double *B = A + (9 * j) * n + 9 * k;
+#define AT(a, b) B[(a) * n + (b)]
+                    AT(0, 0) += rho * ch * S; AT(1, 1) += rho * ch * S; AT(2, 2) += rho * ch * S;
+                    AT(3, 3) += d1 * S; AT(4, 4) += d1 * S; AT(5, 5) += d1 * S;
+                    AT(6, 6) += d2 * S; AT(7, 7) += d2 * S; AT(8, 8) += d2 * S;
+                    AT(3, 4) += o1 * S; AT(3, 5) += o1 * S; AT(4, 5) += o1 * S;
+                    AT(4, 3) += o1 * S; AT(5, 3) += o1 * S; AT(5, 4) += o1 * S;
+                    if (q > 0) {
+                        double wD = 1.0 * D;
+                        double gxj = d[j][0] * N[k] * phi[q][0] * wD, gyj = d[j][1] * N[k] * phi[q][1] * wD,
+                               gzj = d[j][2] * N[k] * phi[q][2] * wD;
+                        double gxk = d[k][0] * N[j] * phi[q][0] * wD, gyk = d[k][1] * N[j] * phi[q][1] * wD,
+                               gzk = d[k][2] * N[j] * phi[q][2] * wD;
+                        AT(0, 3) += gxj; AT(0, 6) += gyj; AT(0, 8) += gzj;
+                        AT(1, 4) += gyj; AT(1, 6) += gxj; AT(1, 7) += gzj;
+                        AT(2, 5) += gzj; AT(2, 8) += gxj; AT(2, 7) += gyj;
+                        AT(3, 0) += gxk; AT(6, 0) += gyk; AT(8, 0) += gzk;
+                        AT(4, 1) += gyk; AT(6, 1) += gxk; AT(7, 1) += gzk;
+                        AT(5, 2) += gzk; AT(8, 2) += gxk; AT(7, 2) += gyk;
+                    }
+#undef AT
+                }
+        }
+    }
+}
+
+void svlo_pml2d_matrices(const double *X, double E, double nu, double rho, const double p[8],
+                         double *M, double *C, double *K) {
+    const int n = 20;
+    double *out[3] = {M, C, K};
+    for (int q = 0; q < 3; q++) if (out[q]) memset(out[q], 0, n * n * sizeof(double));
+    const double th = p[0], mp = p[1], L = p[2], R = p[3], x0[2] = {p[4], p[5]}, np[2] = {p[6], p[7]};
+    const double mu = E / (2.0 * (1.0 + nu));
+    const double lambda = E * nu / (1.0 + nu) / (1.0 - 2.0 * nu);
+    for (int g = 0; g < 4; g++) {
+        double r, s, d[4][2], N[4];
+        quad4_gp(g, &r, &s);
+        double D = quad4_grad(X, r, s, d, N);
+        double xg[2] = {0, 0};
+        for (int i = 0; i < 4; i++) for (int c = 0; c < 2; c++) xg[c] += N[i] * X[2 * i + c];
+        double Vp = sqrt((lambda + 2.0 * mu) / rho);
+        double bp = L / 10.0;
+        double a0 = (mp + 1.0) * bp / 2.0 / L * log(1.0 / R);
+        double b0 = (mp + 1.0) * Vp / 2.0 / L * log(1.0 / R);
+        double al[2], be[2];
+        for (int c = 0; c < 2; c++) {
+            double pw = pow((xg[c] - x0[c]) * np[c] / L, mp);
+            al[c] = 1.0 + a0 * pw;
+            be[c] = b0 * pw;
+        }
+        const double ax = al[0], ay = al[1], bx = be[0], by = be[1];
+        double chi[3] = {ax * ay, ax * by + ay * bx, bx * by};
+        double phx[3] = {0, ay, by}, phy[3] = {0, ax, bx};
+        for (int q = 0; q < 3; q++) {
+            double *A = out[q];
+            if (!A) continue;
+            double ch = chi[q];
+            double d1 = -ch * (lambda + 2.0 * mu) / 4.0 / mu / (lambda + mu);
+            double d2 = -ch / mu;
+            double o1 = ch * lambda / 4.0 / mu / (lambda + mu);
+            for (int j = 0; j < 4; j++)
+                for (int k = 0; k < 4; k++) {
+                    double S = N[j] * N[k] * th * 1.0 * D;
+                    double *B = A + (5 * j) * n + 5 * k;
+#define AT(a, b) B[(a) * n + (b)]
+                    AT(0, 0) += rho * ch * S; AT(1, 1) += rho * ch * S;
+                    AT(2, 2) += d1 * S; AT(3, 3) += d1 * S; AT(4, 4) += d2 * S;
+                    AT(2, 3) += o1 * S; AT(3, 2) += o1 * S;
+                    if (q > 0) {
+                        double w = th * 1.0 * D;
+                        AT(0, 2) += phx[q] * d[j][0] * N[k] * w; AT(2, 0) += phx[q] * d[k][0] * N[j] * w;
+                        AT(0, 4) += phy[q] * d[j][1] * N[k] * w; AT(4, 0) += phy[q] * d[k][1] * N[j] * w;
+                        AT(1, 3) += phy[q] * d[j][1] * N[k] * w; AT(3, 1) += phy[q] * d[k][1] * N[j] * w;
+                        AT(1, 4) += phx[q] * d[j][0] * N[k] * w; AT(4, 1) += phx[q] * d[k][0] * N[j] * w;
+                    }
+#undef AT
+                }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------ */
+/* DRM element forces: lin3DHexa8.cpp:660-718, lin2DQuad4.cpp:564-614         */
+/* ------------------------------------------------------------------------ */
+void svlo_hex8_drm_force(const double *X, const double C[36], double rho, int lumped,
+                         const uint8_t ext[8], const double Uo[24], const double Vo[24],
+                         const double Ao[24], double f[24]) {
+    double M[576], K[576];
+    (void)Vo;                                     /* FREE damping: C_e = 0 */
+    svlo_hex8_mass(X, rho, lumped, M);
+    svlo_hex8_stiffness(X, C, K);
+    for (int i = 0; i < 24; i++) {
+        double v = 0;
+        for (int j = 0; j < 24; j++) {
+            if (ext[i / 3] == ext[j / 3]) continue;
+            v += M[i * 24 + j] * Ao[j];
+        }
+        double w = 0;
+        for (int j = 0; j < 24; j++) {
+            if (ext[i / 3] == ext[j / 3]) continue;
+            w += K[i * 24 + j] * Uo[j];
+        }
+        f[i] = v + w;
+    }
+}
+void svlo_quad4_drm_force(const double *X, double th, const double C[9], double rho, int lumped,
+                          const uint8_t ext[4], const double Uo[8], const double Vo[8],
+                          const double Ao[8], double f[8]) {
+    double M[64], K[64];
+    (void)Vo;
+    svlo_quad4_mass(X, th, rho, lumped, M);
+    svlo_quad4_stiffness(X, th, C, K);
+    for (int i = 0; i < 8; i++) {
+        double v = 0, w = 0;
+        for (int j = 0; j < 8; j++) {
+            if (ext[i / 2] == ext[j / 2]) continue;
+            v += M[i * 8 + j] * Ao[j];
+        }
+        for (int j = 0; j < 8; j++) {
+            if (ext[i / 2] == ext[j / 2]) continue;
+            w += K[i * 8 + j] * Uo[j];
+        }
+        f[i] = v + w;
+    }
+}
+
+/* ------------------------------------------------------------------------ */
+/* analysis level                                                            */
+/* ------------------------------------------------------------------------ */
+typedef struct { int i, j; double v; } trip;
+static int trip_cmp(const void *a, const void *b) {
+    const trip *x = (const trip *)a, *y = (const trip *)b;
+    if (x->i != y->i) return x->i < y->i ? -1 : 1;
+    if (x->j != y->j) return x->j < y->j ? -1 : 1;
+    return 0;
+}
+typedef struct { int n, cap; trip *t; } tlist;
+static void tl_push(tlist *l, int i, int j, double v) {
+    if (l->n == l->cap) { l->cap = l->cap ? 2 * l->cap : 1024; l->t = (trip *)realloc(l->t, l->cap * sizeof(trip)); }
+    l->t[l->n].i = i; l->t[l->n].j = j; l->t[l->n].v = v; l->n++;
+}
+/* COO -> CSR with duplicate summation (Eigen setFromTriplets semantics)        */
+typedef struct { int n; int *ptr, *col; double *val; } csr;
+static csr tl_to_csr(tlist *l, int n) {
+    csr A; A.n = n;
+    qsort(l->t, l->n, sizeof(trip), trip_cmp);
+    int m = 0;
+    for (int k = 0; k < l->n; k++) {
+        if (m > 0 && l->t[m - 1].i == l->t[k].i && l->t[m - 1].j == l->t[k].j) l->t[m - 1].v += l->t[k].v;
+        else l->t[m++] = l->t[k];
+    }
+    A.ptr = (int *)calloc(n + 1, sizeof(int)); A.col = (int *)malloc((m + 1) * sizeof(int));
+    A.val = (double *)malloc((m + 1) * sizeof(double));
+    for (int k = 0; k < m; k++) A.ptr[l->t[k].i + 1]++;
+    for (int i = 0; i < n; i++) A.ptr[i + 1] += A.ptr[i];
+    for (int k = 0; k < m; k++) { A.col[k] = l->t[k].j; A.val[k] = l->t[k].v; }
+    return A;
+}
+static void csr_free(csr *A) { free(A->ptr); free(A->col); free(A->val); }
+
+static int elem_nn(int kind) { return (kind == SVLO_LIN3DHEXA8 || kind == SVLO_PML3DHEXA8) ? 8 : 4; }
+static int elem_is_pml(int kind) { return kind == SVLO_PML3DHEXA8 || kind == SVLO_PML2DQUAD4; }
+
+typedef struct {
+    int nd;                /* element dofs                                         */
+    int dofs[72];          /* total dofs (Element::GetTotalDegreeOfFreedom)        */
+    double X[24];
+    double *Kpml;          /* PML: nd*nd stiffness                                 */
+    double sig[8][6];      /* stored Gauss-point stress (solid)                    */
+    double st[8][13];      /* J2 state                                             */
+} elem_rt;
+
+static void elem_setup(const svlo_model *m, int e, elem_rt *rt) {
+    int kind = m->elem_kind[e], nn = elem_nn(kind);
+    rt->nd = 0; rt->Kpml = NULL;
+    memset(rt->sig, 0, sizeof rt->sig); memset(rt->st, 0, sizeof rt->st);
+    for (int i = 0; i < nn; i++) {
+        int nd = m->elem_conn[8 * e + i];
+        for (int c = 0; c < m->ndim; c++) rt->X[m->ndim * i + c] = m->coords[m->ndim * nd + c];
+        /* lin3DHexa8.cpp:129-147 / PML3DHexa8.cpp GetTotalDegreeOfFreedom        */
+        for (int p = m->node_ptr[nd]; p < m->node_ptr[nd + 1]; p++) rt->dofs[rt->nd++] = m->totaldof[p];
+    }
+}
+
+/* element mass/damping matrices -> triplets with |m_ij| > mtol filter
+ * (Assembler.cpp:660-697, 116-158)                                             */
+static void elem_MC(const svlo_model *m, int e, const elem_rt *rt, double *Me, double *Ce) {
+    int kind = m->elem_kind[e];
+    const double *mp = m->mat_par + 8 * m->elem_mat[e];
+    const double *at = m->elem_attr + 10 * e;
+    int nd = rt->nd;
+    memset(Ce, 0, nd * nd * sizeof(double));
+    if (kind == SVLO_LIN3DHEXA8) {
+        svlo_hex8_mass(rt->X, mp[2], m->lumped, Me);
+    } else if (kind == SVLO_LIN2DQUAD4) {
+        svlo_quad4_mass(rt->X, at[0], mp[2], m->lumped, Me);
+    } else if (kind == SVLO_PML3DHEXA8) {
+        svlo_pml3d_matrices(rt->X, mp[0], mp[1], mp[2], at, Me, Ce, NULL, NULL);
+    } else {
+        svlo_pml2d_matrices(rt->X, mp[0], mp[1], mp[2], at, Me, Ce, NULL);
+    }
+    if (!elem_is_pml(kind)) {
+        /* Rayleigh: C_e = am*M_e + ak*K0_e  (lin3DHexa8.cpp:354-366)            */
+        double am = m->elem_am ? m->elem_am[e] : 0.0, ak = m->elem_ak ? m->elem_ak[e] : 0.0;
+        if (am != 0.0 || ak != 0.0) {
+            double K0[576], Cm[36];
+            int mk = m->mat_kind[m->elem_mat[e]];
+            if (kind == SVLO_LIN3DHEXA8) {
+                if (mk == SVLO_ELASTIC3DLINEAR) svlo_elastic3d_C(mp[0], mp[1], Cm);
+                else { /* Plastic3DJ2 initial tangent K*D + 2G(I - D/3): Plastic3DJ2.cpp:148-160 */
+                    memset(Cm, 0, sizeof Cm);
+                    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++)
+                        Cm[6 * i + j] = mp[0] + 2.0 * mp[1] * ((i == j ? 1.0 : 0.0) - 1.0 / 3.0);
+                    Cm[21] = Cm[28] = Cm[35] = 2.0 * mp[1] * 0.5;
+                }
+                svlo_hex8_stiffness(rt->X, Cm, K0);
+            } else {
+                svlo_planestrain_C(mp[0], mp[1], Cm);
+                svlo_quad4_stiffness(rt->X, at[0], Cm, K0);
+            }
+            for (int i = 0; i < nd * nd; i++) Ce[i] += am * Me[i] + ak * K0[i];
+        }
+    }
+}
+
+/* dense LDL^T without pivoting (EigenSolver.hpp:88 SimplicialLDLT semantics)   */
+static int ldlt_factor(double *A, int n) {
+    for (int j = 0; j < n; j++) {
+        double d = A[j * n + j];
+        for (int k = 0; k < j; k++) d -= A[j * n + k] * A[j * n + k] * A[k * n + k];
+        if (d == 0.0 || d != d) return 1;
+        A[j * n + j] = d;
+        for (int i = j + 1; i < n; i++) {
+            double v = A[i * n + j];
+            for (int k = 0; k < j; k++) v -= A[i * n + k] * A[j * n + k] * A[k * n + k];
+            A[i * n + j] = v / d;
+        }
+    }
+    return 0;
+}
+static void ldlt_solve(const double *A, int n, double *b) {
+    for (int i = 0; i < n; i++) { double v = b[i]; for (int k = 0; k < i; k++) v -= A[i * n + k] * b[k]; b[i] = v; }
+    for (int i = 0; i < n; i++) b[i] /= A[i * n + i];
+    for (int i = n - 1; i >= 0; i--) { double v = b[i]; for (int k = i + 1; k < n; k++) v -= A[k * n + i] * b[k]; b[i] = v; }
+}
+
+/* Mesh::GetTotalToFreeMatrix (06-Mesh/Mesh.cpp:328-381) as a CSR over total dofs */
+static csr build_T(const svlo_model *m) {
+    tlist l = {0, 0, NULL};
+    for (int nd = 0; nd < m->n_nodes; nd++)
+        for (int p = m->node_ptr[nd]; p < m->node_ptr[nd + 1]; p++) {
+            int fr = m->freedof[p], to = m->totaldof[p];
+            if (fr > -1) tl_push(&l, to, fr, 1.0);
+            if (fr < -1)
+                for (int c = 0; c < m->n_cons; c++)
+                    if (m->cons_tag[c] == fr)
+                        for (int q = m->cons_ptr[c]; q < m->cons_ptr[c + 1]; q++)
+                            tl_push(&l, m->cons_slave[c], m->cons_master[q], m->cons_factor[q]);
+        }
+    csr T = tl_to_csr(&l, m->n_total);
+    free(l.t);
+    return T;
+}
+
+static void material_update(const svlo_model *m, int e, elem_rt *rt, const double *Utot) {
+    int kind = m->elem_kind[e], mk = m->mat_kind[m->elem_mat[e]];
+    const double *mp = m->mat_par + 8 * m->elem_mat[e];
+    double ue[24];
+    for (int i = 0; i < rt->nd; i++) ue[i] = Utot[rt->dofs[i]];
+    if (kind == SVLO_LIN3DHEXA8) {
+        double eps[8][6];
+        svlo_hex8_strain(rt->X, ue, eps);
+        if (mk == SVLO_ELASTIC3DLINEAR) {
+            double C[36];
+            svlo_elastic3d_C(mp[0], mp[1], C);
+            for (int g = 0; g < 8; g++)
+                for (int a = 0; a < 6; a++) {
+                    double v = 0;
+                    for (int b = 0; b < 6; b++) v += C[6 * a + b] * eps[g][b];
+                    rt->sig[g][a] = v;
+                }
+        } else {
+            for (int g = 0; g < 8; g++) svlo_j2_update(mp, eps[g], rt->st[g], rt->sig[g]);
+        }
+    } else if (kind == SVLO_LIN2DQUAD4) {
+        double eps[4][3], C[9];
+        svlo_quad4_strain(rt->X, ue, eps);
+        svlo_planestrain_C(mp[0], mp[1], C);
+        for (int g = 0; g < 4; g++)
+            for (int a = 0; a < 3; a++) {
+                double v = 0;
+                for (int b = 0; b < 3; b++) v += C[3 * a + b] * eps[g][b];
+                rt->sig[g][a] = v;
+            }
+    }
+}
+
+static void elem_fint(const svlo_model *m, int e, const elem_rt *rt, const double *U, double *fe) {
+    int kind = m->elem_kind[e];
+    if (kind == SVLO_LIN3DHEXA8) svlo_hex8_force(rt->X, rt->sig, fe);
+    else if (kind == SVLO_LIN2DQUAD4) {
+        double s3[4][3];
+        for (int g = 0; g < 4; g++) for (int a = 0; a < 3; a++) s3[g][a] = rt->sig[g][a];
+        svlo_quad4_force(rt->X, m->elem_attr[10 * e], s3, fe);
+    } else {
+        /* PML: f = K_e u_e, PML3DHexa8.cpp:716-743, PML2DQuad4.cpp:474-494       */
+        int nd = rt->nd;
+        for (int i = 0; i < nd; i++) {
+            double v = 0;
+            for (int j = 0; j < nd; j++) v += rt->Kpml[i * nd + j] * U[rt->dofs[j]];
+            fe[i] = v;
+        }
+    }
+}
+
+int svlo_mass_diagonal(const svlo_model *m, double *Md) {
+    memset(Md, 0, m->n_total * sizeof(double));
+    int off = 0;
+    for (int q = 0; q < m->n_mass; q++) {
+        int nd = m->mass_node[q];
+        for (int p = m->node_ptr[nd]; p < m->node_ptr[nd + 1]; p++, off++)
+            if (fabs(m->mass_val[off]) > m->mtol) Md[m->totaldof[p]] += m->mass_val[off];
+    }
+    double *Me = (double *)malloc(72 * 72 * sizeof(double)), *Ce = (double *)malloc(72 * 72 * sizeof(double));
+    for (int e = 0; e < m->n_elem; e++) {
+        elem_rt rt; elem_setup(m, e, &rt);
+        elem_MC(m, e, &rt, Me, Ce);
+        for (int i = 0; i < rt.nd; i++)
+            if (fabs(Me[i * rt.nd + i]) > m->mtol) Md[rt.dofs[i]] += Me[i * rt.nd + i];
+    }
+    free(Me); free(Ce);
+    return 0;
+}
+
+int svlo_internal_force(const svlo_model *m, const double *U, double *F) {
+    memset(F, 0, m->n_total * sizeof(double));
+    for (int e = 0; e < m->n_elem; e++) {
+        elem_rt rt; elem_setup(m, e, &rt);
+        double fe[72];
+        double *Kp = NULL;
+        if (elem_is_pml(m->elem_kind[e])) {
+            const double *mp = m->mat_par + 8 * m->elem_mat[e];
+            Kp = (double *)malloc(rt.nd * rt.nd * sizeof(double));
+            if (m->elem_kind[e] == SVLO_PML3DHEXA8) svlo_pml3d_matrices(rt.X, mp[0], mp[1], mp[2], m->elem_attr + 10 * e, NULL, NULL, Kp, NULL);
+            else svlo_pml2d_matrices(rt.X, mp[0], mp[1], mp[2], m->elem_attr + 10 * e, NULL, NULL, Kp);
+            rt.Kpml = Kp;
+        } else material_update(m, e, &rt, U);
+        elem_fint(m, e, &rt, U, fe);
+        for (int i = 0; i < rt.nd; i++)
+            if (fabs(fe[i]) > m->ftol) F[rt.dofs[i]] += fe[i];
+        free(Kp);
+    }
+    return 0;
+}
+
+int svlo_run_central_difference(const svlo_model *m, int nt, int field, int n_rec,
+                                const int32_t *rec_dofs, double *out, double *Ufinal, int nthreads) {
+    const int nT = m->n_total, nF = m->n_free, nE = m->n_elem;
+    const double dt = m->dt;
+    int rc = 0;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+    (void)nthreads;
+#endif
+    elem_rt *rt = (elem_rt *)malloc((size_t)nE * sizeof(elem_rt));
+    double *U = (double *)calloc(nT, sizeof(double)), *V = (double *)calloc(nT, sizeof(double)),
+           *A = (double *)calloc(nT, sizeof(double)), *Up = (double *)calloc(nT, sizeof(double));
+    double *Fint = (double *)calloc(nT, sizeof(double)), *Fext = (double *)calloc(nT, sizeof(double)),
+           *Ftmp = (double *)calloc(nT, sizeof(double)), *rhs = (double *)calloc(nT, sizeof(double)),
+           *dUt = (double *)calloc(nT, sizeof(double)), *Utr = (double *)calloc(nT, sizeof(double));
+    double *Feff = (double *)calloc(nF + 1, sizeof(double)), *dU = (double *)calloc(nF + 1, sizeof(double));
+    double *fe_all = (double *)malloc((size_t)nE * 72 * sizeof(double));
+    if (m->U0) memcpy(U, m->U0, nT * sizeof(double));
+    if (m->V0) memcpy(V, m->V0, nT * sizeof(double));
+    if (m->A0) memcpy(A, m->A0, nT * sizeof(double));
+    /* CentralDifference::Initialize :61 */
+    for (int i = 0; i < nT; i++) Up[i] = U[i] - dt * V[i] + dt * dt / 2.0 * A[i];
+
+    /* M, C in total space (Assembler.cpp:47-67, 116-158) */
+    tlist lM = {0, 0, NULL}, lC = {0, 0, NULL};
+    {
+        int off = 0;
+        for (int q = 0; q < m->n_mass; q++) {
+            int nd = m->mass_node[q];
+            for (int p = m->node_ptr[nd]; p < m->node_ptr[nd + 1]; p++, off++)
+                if (fabs(m->mass_val[off]) > m->mtol) tl_push(&lM, m->totaldof[p], m->totaldof[p], m->mass_val[off]);
+        }
+        double *Me = (double *)malloc(72 * 72 * sizeof(double)), *Ce = (double *)malloc(72 * 72 * sizeof(double));
+        for (int e = 0; e < nE; e++) {
+            elem_setup(m, e, &rt[e]);
+            elem_MC(m, e, &rt[e], Me, Ce);
+            int nd = rt[e].nd;
+            for (int j = 0; j < nd; j++)
+                for (int i = 0; i < nd; i++) {
+                    if (fabs(Me[i * nd + j]) > m->mtol) tl_push(&lM, rt[e].dofs[i], rt[e].dofs[j], Me[i * nd + j]);
+                    if (fabs(Ce[i * nd + j]) > m->mtol) tl_push(&lC, rt[e].dofs[i], rt[e].dofs[j], Ce[i * nd + j]);
+                }
+            if (elem_is_pml(m->elem_kind[e])) {
+                const double *mp = m->mat_par + 8 * m->elem_mat[e];
+                rt[e].Kpml = (double *)malloc(nd * nd * sizeof(double));
+                if (m->elem_kind[e] == SVLO_PML3DHEXA8) svlo_pml3d_matrices(rt[e].X, mp[0], mp[1], mp[2], m->elem_attr + 10 * e, NULL, NULL, rt[e].Kpml, NULL);
+                else svlo_pml2d_matrices(rt[e].X, mp[0], mp[1], mp[2], m->elem_attr + 10 * e, NULL, NULL, rt[e].Kpml);
+            }
+        }
+        free(Me); free(Ce);
+    }
+    /* Keff = M/dt^2 + C/2dt (:70) and Kminus = M/dt^2 - C/2dt (:217) */
+    tlist lKp = {0, 0, NULL}, lKm = {0, 0, NULL};
+    for (int k = 0; k < lM.n; k++) {
+        tl_push(&lKp, lM.t[k].i, lM.t[k].j, 1.0 / dt / dt * lM.t[k].v);
+        tl_push(&lKm, lM.t[k].i, lM.t[k].j, 1.0 / dt / dt * lM.t[k].v);
+    }
+    for (int k = 0; k < lC.n; k++) {
+        tl_push(&lKp, lC.t[k].i, lC.t[k].j, 1.0 / 2.0 / dt * lC.t[k].v);
+        tl_push(&lKm, lC.t[k].i, lC.t[k].j, -(1.0 / 2.0 / dt * lC.t[k].v));
+    }
+    csr Kp = tl_to_csr(&lKp, nT), Km = tl_to_csr(&lKm, nT);
+    csr T = build_T(m);
+    /* Keff_free = T' Keff T (:224-231) */
+    tlist lF = {0, 0, NULL};
+    for (int i = 0; i < nT; i++)
+        for (int p = Kp.ptr[i]; p < Kp.ptr[i + 1]; p++) {
+            int j = Kp.col[p];
+            for (int a = T.ptr[i]; a < T.ptr[i + 1]; a++)
+                for (int b = T.ptr[j]; b < T.ptr[j + 1]; b++)
+                    tl_push(&lF, T.col[a], T.col[b], T.val[a] * T.val[b] * Kp.val[p]);
+        }
+    csr Kf = tl_to_csr(&lF, nF);
+    /* split free dofs into diagonal rows and a coupled block */
+    int *cidx = (int *)malloc((nF + 1) * sizeof(int));
+    int nc = 0;
+    double *Kdiag = (double *)calloc(nF + 1, sizeof(double));
+    for (int i = 0; i < nF; i++) {
+        int coupled = 0;
+        for (int p = Kf.ptr[i]; p < Kf.ptr[i + 1]; p++) {
+            if (Kf.col[p] == i) Kdiag[i] = Kf.val[p];
+            else if (Kf.val[p] != 0.0) coupled = 1;
+        }
+        cidx[i] = coupled ? nc++ : -1;
+    }
+    double *Kc = NULL, *bc = NULL;
+    if (nc > 0) {
+        Kc = (double *)calloc((size_t)nc * nc, sizeof(double));
+        bc = (double *)calloc(nc, sizeof(double));
+        for (int i = 0; i < nF; i++) {
+            if (cidx[i] < 0) continue;
+            for (int p = Kf.ptr[i]; p < Kf.ptr[i + 1]; p++)
+                if (cidx[Kf.col[p]] >= 0) Kc[(size_t)cidx[i] * nc + cidx[Kf.col[p]]] = Kf.val[p];
+        }
+        if (ldlt_factor(Kc, nc)) { rc = 2; goto done; }
+    }
+
+    for (int k = 1; k < nt; k++) {            /* DynamicAnalysis.cpp:36 */
+        /* --- Fint: Assembler.cpp:239-269 (ascending element order, ftol filter) */
+#pragma omp parallel for schedule(static)
+        for (int e = 0; e < nE; e++) elem_fint(m, e, &rt[e], U, fe_all + (size_t)72 * e);
+        memset(Fint, 0, nT * sizeof(double));
+        for (int e = 0; e < nE; e++) {
+            const double *fe = fe_all + (size_t)72 * e;
+            for (int i = 0; i < rt[e].nd; i++)
+                if (fabs(fe[i]) > m->ftol) Fint[rt[e].dofs[i]] += fe[i];
+        }
+        /* --- Fext: Assembler.cpp:290-489 */
+        memset(Fext, 0, nT * sizeof(double));
+        for (int l = 0; l < m->n_pload; l++) {
+            memset(Ftmp, 0, nT * sizeof(double));
+            int ntl = m->pl_nt[l];
+            double amp = (ntl == 1) ? m->pl_series[m->pl_sptr[l]] : m->pl_series[m->pl_sptr[l] + k];
+            for (int q = m->pl_ptr[l]; q < m->pl_ptr[l + 1]; q++) {
+                int nd = m->pl_nodes[q], c = 0;
+                for (int p = m->node_ptr[nd]; p < m->node_ptr[nd + 1] && c < 3; p++, c++)
+                    if (c < m->ndim) Ftmp[m->totaldof[p]] = amp * m->pl_dir[3 * l + c];   /* assign: :330,347 */
+            }
+            for (int i = 0; i < nT; i++) Fext[i] += m->pl_factor[l] * Ftmp[i];
+        }
+        if (m->n_drm_elem > 0) {
+            memset(Ftmp, 0, nT * sizeof(double));
+            int nf = 3 * m->ndim;
+            for (int q = 0; q < m->n_drm_elem; q++) {
+                int e = m->drm_elem[q], nn = elem_nn(m->elem_kind[e]), nd = m->ndim;
+                double Uo[24], Vo[24], Ao[24], f[24];
+                uint8_t ext[8];
+                for (int i = 0; i < nn; i++) {
+                    int node = m->elem_conn[8 * e + i], li = -1;
+                    for (int z = 0; z < m->n_drm_node; z++) if (m->drm_node[z] == node) { li = z; break; }
+                    ext[i] = (li >= 0) ? m->drm_ext[li] : 0;
+                    for (int c = 0; c < nd; c++) {
+                        double sgn = (li >= 0 && m->drm_ext[li]) ? -1.00 : 1.0;   /* Driver.hpp:1714-1716 */
+                        const double *row = (li >= 0) ? m->drm_field + ((size_t)li * m->drm_nt + k) * nf : NULL;
+                        Uo[nd * i + c] = row ? sgn * row[c] : 0.0;
+                        Vo[nd * i + c] = row ? sgn * row[nd + c] : 0.0;
+                        Ao[nd * i + c] = row ? sgn * row[2 * nd + c] : 0.0;
+                    }
+                }
+                const double *mp = m->mat_par + 8 * m->elem_mat[e];
+                if (m->elem_kind[e] == SVLO_LIN3DHEXA8) {
+                    double C[36]; svlo_elastic3d_C(mp[0], mp[1], C);
+                    svlo_hex8_drm_force(rt[e].X, C, mp[2], m->lumped, ext, Uo, Vo, Ao, f);
+                } else {
+                    double C[9]; svlo_planestrain_C(mp[0], mp[1], C);
+                    svlo_quad4_drm_force(rt[e].X, m->elem_attr[10 * e], C, mp[2], m->lumped, ext, Uo, Vo, Ao, f);
+                }
+                for (int i = 0; i < rt[e].nd; i++) Ftmp[rt[e].dofs[i]] += f[i];
+            }
+            for (int i = 0; i < nT; i++) Fext[i] += m->drm_factor * Ftmp[i];
+        }
+        /* --- Feff = T'(Fext - Fint + Kminus (U-Up)) : CentralDifference.cpp:217-220 */
+        for (int i = 0; i < nT; i++) Ftmp[i] = U[i] - Up[i];
+        for (int i = 0; i < nT; i++) {
+            double v = 0;
+            for (int p = Km.ptr[i]; p < Km.ptr[i + 1]; p++) v += Km.val[p] * Ftmp[Km.col[p]];
+            rhs[i] = Fext[i] - Fint[i] + v;
+        }
+        memset(Feff, 0, nF * sizeof(double));
+        for (int i = 0; i < nT; i++)
+            for (int a = T.ptr[i]; a < T.ptr[i + 1]; a++) Feff[T.col[a]] += T.val[a] * rhs[i];
+        /* --- solve (EigenSolver.cpp:19-60) */
+        for (int i = 0; i < nF; i++)
+            if (cidx[i] < 0) dU[i] = Feff[i] / Kdiag[i]; else bc[cidx[i]] = Feff[i];
+        if (nc > 0) {
+            ldlt_solve(Kc, nc, bc);
+            for (int i = 0; i < nF; i++) if (cidx[i] >= 0) dU[i] = bc[cidx[i]];
+        }
+        /* --- dU_total = T dU ; UpdateStatesIncrements: Algorithm.cpp:18-56 */
+        for (int i = 0; i < nT; i++) {
+            double v = 0;
+            for (int a = T.ptr[i]; a < T.ptr[i + 1]; a++) v += T.val[a] * dU[T.col[a]];
+            dUt[i] = v;
+            Utr[i] = U[i] + v;
+        }
+#pragma omp parallel for schedule(static)
+        for (int e = 0; e < nE; e++) material_update(m, e, &rt[e], Utr);
+        /* --- CentralDifference.cpp:138-148 */
+        for (int i = 0; i < nT; i++) {
+            V[i] = 1.0 / 2.0 / dt * (U[i] + dUt[i] - Up[i]);
+            A[i] = 1.0 / dt / dt * (dUt[i] - U[i] + Up[i]);
+            Up[i] = U[i];
+            U[i] += dUt[i];
+        }
+        for (int i = 0; i < nT; i++) if (U[i] != U[i]) rc = 3;
+        const double *src = field == 0 ? U : field == 1 ? V : A;
+        for (int q = 0; q < n_rec; q++) out[(size_t)(k - 1) * n_rec + q] = src[rec_dofs[q]];
+    }
+    if (Ufinal) memcpy(Ufinal, U, nT * sizeof(double));
+done:
+    for (int e = 0; e < nE; e++) free(rt[e].Kpml);
+    free(rt); free(U); free(V); free(A); free(Up); free(Fint); free(Fext); free(Ftmp); free(rhs);
+    free(dUt); free(Utr); free(Feff); free(dU); free(fe_all); free(lM.t); free(lC.t); free(lKp.t);
+    free(lKm.t); free(lF.t); csr_free(&Kp); csr_free(&Km); csr_free(&T); csr_free(&Kf);
+    free(cidx); free(Kdiag); free(Kc); free(bc);
+    return rc;
+}

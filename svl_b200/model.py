@@ -1,0 +1,373 @@
+"""Host-side model container, synthetic structured generators and the writer of the
+reference's per-rank JSON partition files.
+
+This mirrors what the reference's pre-processor produces (01-Pre_Process):
+  * node / element numbering of ``makeDomainVolume`` / ``makeDomainArea``
+    (Method/Builder.py:134-141, 167-183, 244-417),
+  * the ``PlainScheme`` total/free DOF numbering (Core/Numberer.py:185-233),
+  * the per-rank JSON schema consumed by Driver.hpp:1981-2046.
+
+A ``Model`` is plain numpy data; ``svl_b200.capi.upload`` turns it into a device
+model through the C ABI (include/svlgpu.h), ``tests/oracle_lib.py`` turns the same
+object into the oracle's input, and ``write_reference_json`` into the files the
+reference executable reads.  Nothing here computes physics.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+
+LIN3DHEXA8, LIN2DQUAD4, PML3DHEXA8, PML2DQUAD4 = 1, 2, 3, 4
+ELASTIC3DLINEAR, ELASTIC2DPLANESTRAIN, PLASTIC3DJ2, PLASTICPLANESTRAINJ2 = 1, 2, 3, 4
+
+ELEM_NAME = {LIN3DHEXA8: "LIN3DHEXA8", LIN2DQUAD4: "LIN2DQUAD4", PML3DHEXA8: "PML3DHEXA8",
+             PML2DQUAD4: "PML2DQUAD4"}
+MAT_NAME = {ELASTIC3DLINEAR: "ELASTIC3DLINEAR", ELASTIC2DPLANESTRAIN: "ELASTIC2DPLANESTRAIN",
+            PLASTIC3DJ2: "PLASTIC3DJ2", PLASTICPLANESTRAINJ2: "PLASTICPLANESTRAINJ2"}
+MAT_KEYS = {ELASTIC3DLINEAR: ["E", "nu", "rho"], ELASTIC2DPLANESTRAIN: ["E", "nu", "rho"],
+            PLASTIC3DJ2: ["K", "G", "rho", "h", "beta", "Sy"],
+            PLASTICPLANESTRAINJ2: ["K", "G", "rho", "h", "beta", "Sy"]}
+
+
+@dataclass
+class PointLoad:
+    nodes: np.ndarray          # node indices (0-based)
+    dir: np.ndarray            # ndim direction
+    series: np.ndarray         # nt amplitudes (len 1 = constant)
+    factor: float = 1.0
+
+
+@dataclass
+class DRMLoad:
+    elems: np.ndarray          # element indices
+    nodes: np.ndarray          # node indices
+    exterior: np.ndarray       # uint8 per node
+    field: Optional[np.ndarray] = None   # [nnodes, nt, 3*ndim]  (u, v, a) as in .drm files
+    planewave: Optional[dict] = None     # analytic alternative, see capi
+    factor: float = 1.0
+
+
+@dataclass
+class Model:
+    ndim: int
+    lumped: bool = True
+    coords: np.ndarray = None            # [n, ndim]
+    node_ndof: np.ndarray = None         # [n]
+    freedof: List[np.ndarray] = None     # per node list, -1 = restrained, >=0 placeholder
+    materials: List[tuple] = field(default_factory=list)        # (kind, [params])
+    elem_kind: np.ndarray = None         # [ne]
+    elem_conn: np.ndarray = None         # [ne, 8] (quads: first 4)
+    elem_mat: np.ndarray = None          # [ne]
+    elem_attr: np.ndarray = None         # [ne, 10]
+    elem_am: Optional[np.ndarray] = None
+    elem_ak: Optional[np.ndarray] = None
+    constraints: List[tuple] = field(default_factory=list)      # (tag, slave_total, [master_free], [factor])
+    masses: List[tuple] = field(default_factory=list)           # (node, [mass per dof])
+    point_loads: List[PointLoad] = field(default_factory=list)
+    drm: Optional[DRMLoad] = None
+    blocks: List[tuple] = field(default_factory=list)           # (node0, nx, ny, nz) lattice hints
+    dt: float = 0.0
+    nt: int = 0
+    rec_nodes: np.ndarray = None
+
+    # ---- derived numbering (PlainScheme) -------------------------------------
+    def number_dofs(self):
+        n = len(self.node_ndof)
+        self.node_ptr = np.zeros(n + 1, dtype=np.int32)
+        np.cumsum(self.node_ndof, out=self.node_ptr[1:])
+        self.n_total = int(self.node_ptr[-1])
+        self.totaldof = np.arange(self.n_total, dtype=np.int32)
+        fd = np.concatenate(self.freedof).astype(np.int32) if isinstance(self.freedof, list) \
+            else np.asarray(self.freedof, dtype=np.int32)
+        free = fd.copy()
+        is_free = fd > -1
+        free[is_free] = np.arange(int(is_free.sum()), dtype=np.int32)
+        self.freedof_flat = free
+        self.n_free = int(is_free.sum())
+        return self
+
+    @property
+    def n_nodes(self):
+        return len(self.node_ndof)
+
+    @property
+    def n_elem(self):
+        return len(self.elem_kind)
+
+    def node_dofs(self, node):
+        return self.totaldof[self.node_ptr[node]:self.node_ptr[node + 1]]
+
+    def rec_dofs(self):
+        return np.concatenate([self.node_dofs(n) for n in self.rec_nodes]).astype(np.int32)
+
+
+# -------------------------------------------------------------------------------
+# generators
+# -------------------------------------------------------------------------------
+def box_nodes(ne, P0, P1, P2, P3):
+    """Builder.py:134-141: tag = 1 + i + (nx+1) j + (nx+1)(ny+1) k, coords P0 + i DX + j DY + k DZ."""
+    nx, ny, nz = ne
+    P0, P1, P2, P3 = (np.asarray(p, dtype=np.float64) for p in (P0, P1, P2, P3))
+    DX, DY, DZ = (P1 - P0) / nx, (P2 - P0) / ny, (P3 - P0) / nz
+    k, j, i = np.meshgrid(np.arange(nz + 1), np.arange(ny + 1), np.arange(nx + 1), indexing="ij")
+    i, j, k = i.ravel(), j.ravel(), k.ravel()
+    # same operation order as the reference: ((P0 + i*DX) + j*DY) + k*DZ
+    return ((P0[None, :] + i[:, None] * DX[None, :]) + j[:, None] * DY[None, :]) + k[:, None] * DZ[None, :]
+
+
+def box_hex8_conn(ne, node0=0):
+    """Builder.py:167-183 (0-based): [n1..n8] in VTK hexahedron order."""
+    nx, ny, nz = ne
+    k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    i, j, k = i.ravel(), j.ravel(), k.ravel()
+    sx, sy = nx + 1, (nx + 1) * (ny + 1)
+    n1 = sy * k + j * sx + i
+    conn = np.stack([n1, n1 + 1, n1 + sx + 1, n1 + sx, n1 + sy, n1 + sy + 1, n1 + sy + sx + 1, n1 + sy + sx],
+                    axis=1)
+    return (conn + node0).astype(np.int32)
+
+
+def area_nodes(ne, P0, P1, P2):
+    nx, ny = ne
+    P0, P1, P2 = (np.asarray(p, dtype=np.float64) for p in (P0, P1, P2))
+    DX, DY = (P1 - P0) / nx, (P2 - P0) / ny
+    j, i = np.meshgrid(np.arange(ny + 1), np.arange(nx + 1), indexing="ij")
+    i, j = i.ravel(), j.ravel()
+    return (P0[None, :] + i[:, None] * DX[None, :]) + j[:, None] * DY[None, :]
+
+
+def area_quad4_conn(ne, node0=0):
+    """Builder.py:244-417 makeDomainArea QUAD4: [n1, n2, n3, n4] counter-clockwise."""
+    nx, ny = ne
+    j, i = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    i, j = i.ravel(), j.ravel()
+    sx = nx + 1
+    n1 = j * sx + i
+    conn = np.stack([n1, n1 + 1, n1 + sx + 1, n1 + sx], axis=1)
+    return (conn + node0).astype(np.int32)
+
+
+def ricker(nt, dt, f0, t0):
+    """Ricker pulse (1-2b) exp(-b), b = (pi f0 (t-t0))^2  (PlaneWave.py:222-223)."""
+    t = np.arange(nt) * dt
+    b = (math.pi * f0 * (t - t0)) ** 2
+    return (1.0 - 2.0 * b) * np.exp(-b)
+
+
+def make_box_model(ne, h=1.0, mat=(ELASTIC3DLINEAR, [1.3e7, 0.3, 2000.0]), fix="bottom",
+                   dt=None, nt=0, load_node=None, load_dir=(0.0, 0.0, 1.0e4), series=None,
+                   rec_nodes=None, jitter=0.0, seed=20260117, layers=None) -> Model:
+    """Config-1-like soil box: nx*ny*nz lin3DHexa8 on [0,nx h]x[0,ny h]x[0,nz h], bottom fixed,
+    lumped mass, vertical point load on the top-centre node.  `layers`: optional list of
+    (material tuple) assigned per element layer in z (cyclic)."""
+    nx, ny, nz = ne
+    X = box_nodes(ne, [0, 0, 0], [nx * h, 0, 0], [0, ny * h, 0], [0, 0, nz * h])
+    if jitter:
+        rng = np.random.default_rng(seed)
+        X = X + jitter * h * rng.uniform(-1.0, 1.0, X.shape)
+    n = X.shape[0]
+    m = Model(ndim=3)
+    m.coords = X
+    m.node_ndof = np.full(n, 3, dtype=np.int32)
+    fd = np.zeros((n, 3), dtype=np.int32)
+    NX, NY = nx + 1, ny + 1
+    if fix == "bottom":
+        fd[: NX * NY, :] = -1
+    m.freedof = fd.reshape(-1)
+    mats = [mat] if layers is None else list(layers)
+    m.materials = mats
+    conn = box_hex8_conn(ne)
+    m.elem_conn = conn
+    m.elem_kind = np.full(len(conn), LIN3DHEXA8, dtype=np.int32)
+    if layers is None:
+        m.elem_mat = np.zeros(len(conn), dtype=np.int32)
+    else:
+        kz = np.arange(len(conn)) // (nx * ny)
+        m.elem_mat = (kz % len(mats)).astype(np.int32)
+    m.elem_attr = np.zeros((len(conn), 10))
+    m.blocks = [(0, NX, NY, nz + 1)] if not jitter else []
+    if dt is None:
+        E, nu, rho = mats[0][1][:3] if mats[0][0] == ELASTIC3DLINEAR else (None, None, None)
+        if E is None:
+            K, G, rho = mats[0][1][0], mats[0][1][1], mats[0][1][2]
+            vp = math.sqrt((K + 4.0 * G / 3.0) / rho)
+        else:
+            lam = E * nu / ((1 + nu) * (1 - 2 * nu)); mu = E / (2 * (1 + nu))
+            vp = math.sqrt((lam + 2 * mu) / rho)
+        dt = 0.5 * h / vp
+    m.dt, m.nt = dt, nt
+    if load_node is None:
+        load_node = (nx // 2) + NX * (ny // 2) + NX * NY * nz
+    if series is None and nt > 0:
+        f0 = 1.0 / (20.0 * dt)
+        series = ricker(nt, dt, f0, 1.2 / f0)
+    if series is not None:
+        m.point_loads = [PointLoad(np.array([load_node], dtype=np.int32), np.asarray(load_dir, float),
+                                   np.asarray(series, float))]
+    m.rec_nodes = np.asarray(rec_nodes if rec_nodes is not None else [load_node], dtype=np.int32)
+    return m.number_dofs()
+
+
+def make_area_model(ne, h=1.0, th=1.0, mat=(ELASTIC2DPLANESTRAIN, [1.3e7, 0.3, 2000.0]), fix="bottom",
+                    dt=None, nt=0, load_node=None, load_dir=(0.0, 1.0e4), series=None,
+                    rec_nodes=None, jitter=0.0, seed=20260117) -> Model:
+    nx, ny = ne
+    X = area_nodes(ne, [0, 0], [nx * h, 0], [0, ny * h])
+    if jitter:
+        rng = np.random.default_rng(seed)
+        X = X + jitter * h * rng.uniform(-1.0, 1.0, X.shape)
+    n = X.shape[0]
+    m = Model(ndim=2)
+    m.coords = X
+    m.node_ndof = np.full(n, 2, dtype=np.int32)
+    fd = np.zeros((n, 2), dtype=np.int32)
+    if fix == "bottom":
+        fd[: nx + 1, :] = -1
+    m.freedof = fd.reshape(-1)
+    m.materials = [mat]
+    conn4 = area_quad4_conn(ne)
+    conn = np.zeros((len(conn4), 8), dtype=np.int32)
+    conn[:, :4] = conn4
+    m.elem_conn = conn
+    m.elem_kind = np.full(len(conn), LIN2DQUAD4, dtype=np.int32)
+    m.elem_mat = np.zeros(len(conn), dtype=np.int32)
+    m.elem_attr = np.zeros((len(conn), 10))
+    m.elem_attr[:, 0] = th
+    m.blocks = [(0, nx + 1, ny + 1, 1)] if not jitter else []
+    if dt is None:
+        E, nu, rho = mat[1][:3]
+        lam = E * nu / ((1 + nu) * (1 - 2 * nu)); mu = E / (2 * (1 + nu))
+        dt = 0.5 * h / math.sqrt((lam + 2 * mu) / rho)
+    m.dt, m.nt = dt, nt
+    if load_node is None:
+        load_node = (nx // 2) + (nx + 1) * ny
+    if series is None and nt > 0:
+        f0 = 1.0 / (20.0 * dt)
+        series = ricker(nt, dt, f0, 1.2 / f0)
+    if series is not None:
+        m.point_loads = [PointLoad(np.array([load_node], dtype=np.int32), np.asarray(load_dir, float),
+                                   np.asarray(series, float))]
+    m.rec_nodes = np.asarray(rec_nodes if rec_nodes is not None else [load_node], dtype=np.int32)
+    return m.number_dofs()
+
+
+# -------------------------------------------------------------------------------
+# reference JSON writer (Core/SeismoVLAB.py:49-298, Outputs.py:29-51)
+# -------------------------------------------------------------------------------
+def write_reference_json(m: Model, directory: str, name: str = "Model", combo: str = "Run",
+                         resp=("disp",), integrator: str = "CENTRALDIFFERENCE", ndps: int = 16) -> str:
+    """Writes <directory>/Partition/<name>.1.0.json (+ load / .drm text files) in the schema the
+    reference executable reads.  Tags are index+1.  Returns the partition directory."""
+    part = os.path.join(directory, "Partition")
+    os.makedirs(part, exist_ok=True)
+    # the reference's recorders write into <dir>/../Solution/<combo>/ and expect it to exist
+    os.makedirs(os.path.join(directory, "Solution", combo), exist_ok=True)
+    J: Dict[str, dict] = {}
+    J["Global"] = {"ndim": m.ndim, "ntotal": m.n_total, "nfree": m.n_free, "update": "RESTARTABLE",
+                   "massform": "LUMPED" if m.lumped else "CONSISTENT"}
+    J["Materials"] = {}
+    for i, (kind, par) in enumerate(m.materials):
+        J["Materials"][str(i + 1)] = {"name": MAT_NAME[kind],
+                                      "attributes": dict(zip(MAT_KEYS[kind], [float(p) for p in par]))}
+    J["Nodes"] = {}
+    for i in range(m.n_nodes):
+        a, b = m.node_ptr[i], m.node_ptr[i + 1]
+        J["Nodes"][str(i + 1)] = {"ndof": int(m.node_ndof[i]),
+                                  "freedof": [int(v) for v in m.freedof_flat[a:b]],
+                                  "totaldof": [int(v) for v in m.totaldof[a:b]],
+                                  "coords": [float(v) for v in m.coords[i]]}
+    if m.masses:
+        J["Masses"] = {str(n + 1): {"ndof": len(v), "mass": [float(x) for x in v]} for n, v in m.masses}
+    if m.constraints:
+        J["Constraints"] = {str(t): {"stag": int(s), "mtag": [int(x) for x in mt], "factor": [float(x) for x in f]}
+                            for t, s, mt, f in m.constraints}
+    J["Elements"] = {}
+    for e in range(m.n_elem):
+        kind = int(m.elem_kind[e])
+        nn = 8 if kind in (LIN3DHEXA8, PML3DHEXA8) else 4
+        at = m.elem_attr[e]
+        attr = {"material": int(m.elem_mat[e]) + 1, "rule": "GAUSS", "np": nn}
+        if kind == LIN2DQUAD4:
+            attr["th"] = float(at[0])
+        elif kind == PML3DHEXA8:
+            attr.update({"n": float(at[0]), "L": float(at[1]), "R": float(at[2]),
+                         "x0": [float(v) for v in at[3:6]], "npml": [float(v) for v in at[6:9]]})
+        elif kind == PML2DQUAD4:
+            attr.update({"th": float(at[0]), "n": float(at[1]), "L": float(at[2]), "R": float(at[3]),
+                         "x0": [float(v) for v in at[4:6]], "npml": [float(v) for v in at[6:8]]})
+        J["Elements"][str(e + 1)] = {"name": ELEM_NAME[kind],
+                                     "conn": [int(v) + 1 for v in m.elem_conn[e, :nn]], "attributes": attr}
+    # dampings: FREE on everything unless Rayleigh given (SeismoVLAB.py:704-707)
+    if m.elem_am is not None and (np.any(m.elem_am != 0) or np.any(m.elem_ak != 0)):
+        groups: Dict[tuple, list] = {}
+        for e in range(m.n_elem):
+            groups.setdefault((float(m.elem_am[e]), float(m.elem_ak[e])), []).append(e + 1)
+        J["Dampings"] = {}
+        for i, ((am, ak), lst) in enumerate(groups.items()):
+            if am == 0.0 and ak == 0.0:
+                J["Dampings"][str(i + 1)] = {"name": "FREE", "attributes": {"list": lst}}
+            else:
+                J["Dampings"][str(i + 1)] = {"name": "RAYLEIGH", "attributes": {"am": am, "ak": ak, "list": lst}}
+    else:
+        J["Dampings"] = {"1": {"name": "FREE", "attributes": {"list": list(range(1, m.n_elem + 1))}}}
+    J["Loads"] = {}
+    tag = 0
+    for pl in m.point_loads:
+        tag += 1
+        if len(pl.series) == 1:
+            J["Loads"][str(tag)] = {"name": "POINTLOAD", "attributes": {
+                "name": "CONSTANT", "type": "CONCENTRATED", "mag": float(pl.series[0]),
+                "dir": [float(v) for v in pl.dir], "list": [int(v) + 1 for v in pl.nodes]}}
+        else:
+            fn = os.path.join(part, f"{name}_load{tag}.txt")
+            with open(fn, "w") as f:
+                f.write(f"{len(pl.series)}\n" + "\n".join(repr(float(v)) for v in pl.series) + "\n")
+            J["Loads"][str(tag)] = {"name": "POINTLOAD", "attributes": {
+                "name": "TIMESERIES", "type": "CONCENTRATED", "file": fn,
+                "dir": [float(v) for v in pl.dir], "list": [int(v) + 1 for v in pl.nodes]}}
+    factors = [float(pl.factor) for pl in m.point_loads]
+    if m.drm is not None and m.drm.field is not None:
+        tag += 1
+        d = m.drm
+        drmdir = os.path.join(part, "DRM")
+        os.makedirs(drmdir, exist_ok=True)
+        for li, node in enumerate(d.nodes):
+            with open(os.path.join(drmdir, f"{name}-{tag}.{int(node) + 1}.drm"), "w") as f:
+                fld = d.field[li]
+                f.write(f"{fld.shape[0]} {fld.shape[1]} {int(d.exterior[li])}\n")
+                for row in fld:
+                    f.write(" ".join(repr(float(v)) for v in row) + "\n")
+        J["Loads"][str(tag)] = {"name": "ELEMENTLOAD", "attributes": {
+            "name": "TIMESERIES", "type": "GENERALWAVE",
+            "file": os.path.join(drmdir, f"{name}-{tag}.$.drm"),
+            "list": [int(v) + 1 for v in d.elems]}}
+        factors.append(float(d.factor))
+    J["Combinations"] = {"1": {"name": combo, "attributes": {
+        "folder": combo, "load": list(range(1, tag + 1)), "factor": factors}}}
+    J["Recorders"] = {}
+    for i, r in enumerate(resp):
+        J["Recorders"][str(i + 1)] = {"name": "NODE", "file": f"{r}.0.out", "ndps": ndps, "resp": r,
+                                      "list": [int(v) + 1 for v in m.rec_nodes], "nsamp": 1}
+    J["Simulations"] = {"combo": 1, "attributes": {
+        "analysis": {"name": "DYNAMIC", "nt": int(m.nt)},
+        "algorithm": {"name": "LINEAR", "nstep": 1},
+        "integrator": {"name": integrator, "dt": float(m.dt), "ktol": 1e-12, "mtol": 1e-12, "ftol": 1e-12},
+        "solver": {"name": "EIGEN", "update": 1}}}
+    with open(os.path.join(part, f"{name}.1.0.json"), "w") as f:
+        json.dump(J, f, indent=4)
+    return part
+
+
+def read_node_recorder(path: str) -> np.ndarray:
+    """NODE recorder text file (Recorder.cpp:73-105, 239-269) -> [nrows, ncols] array."""
+    with open(path) as f:
+        first = f.readline().split()
+        nn = int(first[0])
+        for _ in range(nn):
+            f.readline()
+        return np.loadtxt(f, ndmin=2)
