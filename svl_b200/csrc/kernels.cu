@@ -1,0 +1,821 @@
+// kernels.cu -- sm_100a FP64 kernels of the explicit step (see DESIGN.md for the data layout).
+//
+//   k_stencil3<NW>   block-stencil force + CentralDifference update for lattice blocks of
+//                    lin3DHexa8/Elastic3DLinear (node-class pre-summed 27 x 3x3 rows of K)
+//   k_stencil2       same for lin2DQuad4/Elastic2DPlaneStrain lattices (9 x 2x2)
+//   k_gen_hex8/quad4 Gauss-point element force (elastic or J2 return map), one thread per
+//                    Gauss point, warp-shuffle reduce-scatter of B^T sigma to the 8 (4) nodes
+//   k_gen_nodes      atomic-free node gather (ascending element order) + update
+//   k_nodal_loads    point loads,  k_drm  DRM effective forces,  k_record  NODE recorder rows
+//
+// Reference semantics reproduced: CentralDifference.cpp:123-152,205-221 (update),
+// Assembler.cpp:239-269 (scatter order), lin3DHexa8.cpp:86-107,382-412 (element force).
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include "model.h"
+#include "elem_math.h"
+
+namespace svl {
+
+#define CUDA_OK(x)                                                                          \
+    do {                                                                                    \
+        cudaError_t e_ = (x);                                                               \
+        if (e_ != cudaSuccess) {                                                            \
+            set_error(std::string(#x) + ": " + cudaGetErrorString(e_));                     \
+            return 1;                                                                       \
+        }                                                                                   \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// cp.async helpers (LDGSTS; 8-byte granules because a lattice row starts on an 8 B boundary)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, bool valid) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int sz = valid ? 8 : 0;                       // src-size 0 => zero fill
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// ------------------------------------------------------------------------------------------
+// 3-D block stencil
+// ------------------------------------------------------------------------------------------
+struct Blk3 {
+    const double *U;      // U_n      (internal dof array)
+    const double *Up;     // U_{n-1}
+    double *Un;           // U_{n+1}  (mode 0)  or  F_int (mode 1)
+    const uint8_t *cls;   // [nx*ny*nz]
+    const double *tbl;    // [ncls][276]
+    long long dof0;       // internal dof of lattice node (0,0,0)
+    int ncls, nx, ny, nz;
+    int tiles_x, tiles_y, kz;
+    int mode;
+};
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 1) k_stencil3(const Blk3 p) {
+    constexpr int R = 4;                 // lattice rows (y) per thread
+    constexpr int TY = NW * R;           // tile rows
+    constexpr int TYH = TY + 2;          // + halo
+    constexpr int ROWP = 36;             // 34 columns (+halo) padded to a 16 B multiple
+    constexpr int PLANE = 3 * TYH * ROWP;
+    constexpr int ROWD = 102;            // doubles per tile row in global memory (34 nodes x 3)
+    extern __shared__ __align__(16) double sm[];
+    double *tbl = sm;
+    double *pl = sm + ((p.ncls * kTbl3Stride + 1) & ~1);
+
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int item = blockIdx.x;
+    const int txi = item % p.tiles_x; item /= p.tiles_x;
+    const int tyi = item % p.tiles_y; item /= p.tiles_y;
+    const int i0 = txi * 32, j0 = tyi * TY;
+    const int k0 = item * p.kz, k1 = min(k0 + p.kz, p.nz);
+    const int gi = i0 + lane, gjb = j0 + w * R;
+
+    for (int t = threadIdx.x; t < p.ncls * kTbl3Stride; t += NW * 32) tbl[t] = p.tbl[t];
+
+    auto load_plane = [&](int k, double *buf) {
+        const bool kin = (k >= 0) && (k < p.nz);
+        for (int t = threadIdx.x; t < TYH * ROWD; t += NW * 32) {
+            const int row = t / ROWD, d = t - row * ROWD;
+            const int ii = d / 3, c = d - 3 * ii;
+            const int x = i0 - 1 + ii, y = j0 - 1 + row;
+            const bool ok = kin && (x >= 0) && (x < p.nx) && (y >= 0) && (y < p.ny);
+            const double *src = ok ? p.U + p.dof0 + 3ll * (x + (long long)p.nx * (y + (long long)p.ny * k)) + c : p.U;
+            cp_async8(buf + (c * TYH + row) * ROWP + ii, src, ok);
+        }
+    };
+
+    double acc[3][R][3];
+    double ucen[R][3];
+    int cl[3][R];
+#pragma unroll
+    for (int s = 0; s < 3; s++)
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            cl[s][r] = 0;
+#pragma unroll
+            for (int a = 0; a < 3; a++) acc[s][r][a] = 0.0;
+        }
+#pragma unroll
+    for (int r = 0; r < R; r++)
+#pragma unroll
+        for (int a = 0; a < 3; a++) ucen[r][a] = 0.0;
+
+    auto node_cls = [&](int r, int k) -> int {
+        const int y = gjb + r;
+        if (gi >= p.nx || y >= p.ny || k < k0 || k >= k1) return 0;
+        return p.cls[gi + (long long)p.nx * (y + (long long)p.ny * k)];
+    };
+    // classes of output planes kk-1 (slot 0), kk (slot 1), kk+1 (slot 2) for kk = k0-1
+#pragma unroll
+    for (int r = 0; r < R; r++) cl[2][r] = node_cls(r, k0);
+
+    load_plane(k0 - 1, pl);
+    cp_async_commit();
+
+    int idx = 0;
+    for (int kk = k0 - 1; kk <= k1; kk++, idx++) {
+        double *buf = pl + (idx % 3) * PLANE;
+        if (kk + 1 <= k1) load_plane(kk + 1, pl + ((idx + 1) % 3) * PLANE);
+        cp_async_commit();
+        // U_{n-1} of the nodes completed in this iteration (plane kk-1)
+        double upv[R][3];
+        const bool fin = (kk - 1 >= k0);
+        if (fin && p.mode == 0) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (cl[0][r]) {
+                    const double *q = p.Up + p.dof0 + 3ll * (gi + (long long)p.nx * (gjb + r + (long long)p.ny * (kk - 1)));
+                    upv[r][0] = q[0]; upv[r][1] = q[1]; upv[r][2] = q[2];
+                }
+            }
+        }
+        cp_async_wait<1>();
+        __syncthreads();
+
+        const bool any = (cl[0][0] | cl[0][1] | cl[0][2] | cl[0][3] | cl[1][0] | cl[1][1] | cl[1][2] | cl[1][3] |
+                          cl[2][0] | cl[2][1] | cl[2][2] | cl[2][3]) != 0;
+        const bool uni = (cl[0][0] == cl[0][1]) && (cl[0][0] == cl[0][2]) && (cl[0][0] == cl[0][3]) &&
+                         (cl[1][0] == cl[1][1]) && (cl[1][0] == cl[1][2]) && (cl[1][0] == cl[1][3]) &&
+                         (cl[2][0] == cl[2][1]) && (cl[2][0] == cl[2][2]) && (cl[2][0] == cl[2][3]);
+        if (any) {
+            if (uni) {
+                const double *t0 = tbl + cl[0][0] * kTbl3Stride;
+                const double *t1 = tbl + cl[1][0] * kTbl3Stride;
+                const double *t2 = tbl + cl[2][0] * kTbl3Stride;
+                for (int di = 0; di < 3; di++) {
+                    for (int b = 0; b < 3; b++) {
+                        const double *ub = buf + (b * TYH + w * R) * ROWP + lane + di;
+                        double u[R + 2];
+#pragma unroll
+                        for (int q = 0; q < R + 2; q++) u[q] = ub[q * ROWP];
+                        const int off = (di * 3 + b) * 30;
+#pragma unroll
+                        for (int dj = 0; dj < 3; dj++) {
+                            // slot s accumulates plane-offset dk = 1 - s (coefficient sub-block s)
+                            const double2 *c0 = reinterpret_cast<const double2 *>(t0 + off + dj * 10);
+                            const double2 *c1 = reinterpret_cast<const double2 *>(t1 + off + dj * 10);
+                            const double2 *c2 = reinterpret_cast<const double2 *>(t2 + off + dj * 10);
+                            const double2 a01 = c0[0], a2x = c0[1];          // slot 0: entries 0,1,2
+                            const double2 bx0 = c1[1], b12 = c1[2];          // slot 1: entries 3,4,5
+                            const double2 g01 = c2[3], g2x = c2[4];          // slot 2: entries 6,7,8
+#pragma unroll
+                            for (int r = 0; r < R; r++) {
+                                const double uv = u[r + dj];
+                                acc[0][r][0] = fma(a01.x, uv, acc[0][r][0]);
+                                acc[0][r][1] = fma(a01.y, uv, acc[0][r][1]);
+                                acc[0][r][2] = fma(a2x.x, uv, acc[0][r][2]);
+                                acc[1][r][0] = fma(bx0.y, uv, acc[1][r][0]);
+                                acc[1][r][1] = fma(b12.x, uv, acc[1][r][1]);
+                                acc[1][r][2] = fma(b12.y, uv, acc[1][r][2]);
+                                acc[2][r][0] = fma(g01.x, uv, acc[2][r][0]);
+                                acc[2][r][1] = fma(g01.y, uv, acc[2][r][1]);
+                                acc[2][r][2] = fma(g2x.x, uv, acc[2][r][2]);
+                            }
+                        }
+                    }
+                }
+            } else {
+                // rows of this thread belong to different node classes (lattice faces / edges)
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    if ((cl[0][r] | cl[1][r] | cl[2][r]) == 0) continue;
+                    const double *t0 = tbl + cl[0][r] * kTbl3Stride;
+                    const double *t1 = tbl + cl[1][r] * kTbl3Stride;
+                    const double *t2 = tbl + cl[2][r] * kTbl3Stride;
+                    for (int di = 0; di < 3; di++) {
+                        for (int b = 0; b < 3; b++) {
+                            const double *ub = buf + (b * TYH + w * R + r) * ROWP + lane + di;
+                            const int off = (di * 3 + b) * 30;
+#pragma unroll
+                            for (int dj = 0; dj < 3; dj++) {
+                                const double uv = ub[dj * ROWP];
+                                const double *c0 = t0 + off + dj * 10, *c1 = t1 + off + dj * 10, *c2 = t2 + off + dj * 10;
+                                acc[0][r][0] = fma(c0[0], uv, acc[0][r][0]);
+                                acc[0][r][1] = fma(c0[1], uv, acc[0][r][1]);
+                                acc[0][r][2] = fma(c0[2], uv, acc[0][r][2]);
+                                acc[1][r][0] = fma(c1[3], uv, acc[1][r][0]);
+                                acc[1][r][1] = fma(c1[4], uv, acc[1][r][1]);
+                                acc[1][r][2] = fma(c1[5], uv, acc[1][r][2]);
+                                acc[2][r][0] = fma(c2[6], uv, acc[2][r][0]);
+                                acc[2][r][1] = fma(c2[7], uv, acc[2][r][1]);
+                                acc[2][r][2] = fma(c2[8], uv, acc[2][r][2]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // ---- nodes of plane kk-1 are complete: CentralDifference update (CentralDifference.cpp:138-148)
+        if (fin) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int c = cl[0][r];
+                if (c) {
+                    const long long d0 = p.dof0 + 3ll * (gi + (long long)p.nx * (gjb + r + (long long)p.ny * (kk - 1)));
+                    if (p.mode == 0) {
+                        const double *tc = tbl + c * kTbl3Stride + 270;
+#pragma unroll
+                        for (int a = 0; a < 3; a++) {
+                            const double un = ucen[r][a];
+                            const double du = (tc[3 + a] * (un - upv[r][a]) - acc[0][r][a]) * tc[a];
+                            p.Un[d0 + a] = un + du;
+                        }
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < 3; a++) p.Un[d0 + a] = acc[0][r][a];
+                    }
+                }
+            }
+        }
+        // ---- rotate: plane kk becomes "previous"
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                acc[0][r][a] = acc[1][r][a];
+                acc[1][r][a] = acc[2][r][a];
+                acc[2][r][a] = 0.0;
+                ucen[r][a] = buf[(a * TYH + w * R + r + 1) * ROWP + lane + 1];
+            }
+            cl[0][r] = cl[1][r];
+            cl[1][r] = cl[2][r];
+            cl[2][r] = node_cls(r, kk + 2);
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------
+// 2-D block stencil (quad4 lattices): one thread per node, neighbours through L1/L2
+// ------------------------------------------------------------------------------------------
+struct Blk2 {
+    const double *U, *Up;
+    double *Un;
+    const uint8_t *cls;
+    const double *tbl;     // [ncls][40]: 9 neighbours x (2x2) + kinv[2] + km[2]
+    long long dof0;
+    int ncls, nx, ny, mode;
+};
+
+__global__ void __launch_bounds__(256) k_stencil2(const Blk2 p) {
+    extern __shared__ __align__(16) double sm[];
+    for (int t = threadIdx.x; t < p.ncls * kTbl2Stride; t += blockDim.x) sm[t] = p.tbl[t];
+    __syncthreads();
+    const int i = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (i >= p.nx || j >= p.ny) return;
+    const int c = p.cls[i + (long long)p.nx * j];
+    if (!c) return;
+    const double *t = sm + c * kTbl2Stride;
+    const double2 *U2 = reinterpret_cast<const double2 *>(p.U + p.dof0);
+    double f0 = 0.0, f1 = 0.0;
+    double2 uc = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int dj = -1; dj <= 1; dj++)
+#pragma unroll
+        for (int di = -1; di <= 1; di++) {
+            const int x = i + di, y = j + dj;
+            double2 u = make_double2(0.0, 0.0);
+            if (x >= 0 && x < p.nx && y >= 0 && y < p.ny) u = U2[x + (long long)p.nx * y];
+            if (di == 0 && dj == 0) uc = u;
+            const double *k = t + ((dj + 1) * 3 + (di + 1)) * 4;
+            f0 = fma(k[0], u.x, f0); f0 = fma(k[1], u.y, f0);
+            f1 = fma(k[2], u.x, f1); f1 = fma(k[3], u.y, f1);
+        }
+    const long long n = i + (long long)p.nx * j;
+    double2 *out = reinterpret_cast<double2 *>(p.Un + p.dof0) + n;
+    if (p.mode == 0) {
+        const double2 up = reinterpret_cast<const double2 *>(p.Up + p.dof0)[n];
+        double2 r;
+        r.x = uc.x + (t[38] * (uc.x - up.x) - f0) * t[36];
+        r.y = uc.y + (t[39] * (uc.y - up.y) - f1) * t[37];
+        *out = r;
+    } else {
+        *out = make_double2(f0, f1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// generic Gauss-point element force: one thread per Gauss point
+// ------------------------------------------------------------------------------------------
+struct GenArgs {
+    int n;                     // elements in the set
+    const int32_t *conn;       // [n][npe]
+    const int32_t *mat;        // [n]
+    const double *th;          // [n] (quad)
+    const int32_t *matkind;    // per material
+    const double *matpar;      // [nmat][8]
+    const double *coords;      // [nnodes][ndim]
+    const int32_t *node_ptr;   // internal dof0 per node
+    const double *U;
+    double *fe;                // [n][npe][ndofn]
+    double *state;             // [13][n*ngp] or null
+    double *gp;                // [2][ncomp][n*ngp] strain|stress or null
+    int commit;                // 1: store the updated J2 state
+};
+
+__device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+__global__ void __launch_bounds__(128) k_gen_hex8(const GenArgs a) {
+    __shared__ double sx[4][4][8][6];            // [warp][elem in warp][node][X(3) U(3)]
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int el = lane >> 3, g = lane & 7;
+    int e = tid >> 3;
+    const bool act = e < a.n;
+    if (!act) e = a.n - 1;
+    {
+        const int node = a.conn[(long long)e * 8 + g];
+        const double *x = a.coords + 3ll * node;
+        const double *u = a.U + a.node_ptr[node];
+        double *s = sx[w][el][g];
+        s[0] = x[0]; s[1] = x[1]; s[2] = x[2]; s[3] = u[0]; s[4] = u[1]; s[5] = u[2];
+    }
+    __syncwarp();
+    double X[8][3], Ue[8][3];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const double *s = sx[w][el][i];
+        X[i][0] = s[0]; X[i][1] = s[1]; X[i][2] = s[2];
+        Ue[i][0] = s[3]; Ue[i][1] = s[4]; Ue[i][2] = s[5];
+    }
+    double d[8][3];
+    const double wd = hex8_grad(X, g, d, nullptr);        // weight 1 * |det J|
+    double ep[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 8; i++) {                         // eps = B u  (lin3DHexa8.cpp:721-741,845-850)
+        ep[0] = fma(d[i][0], Ue[i][0], ep[0]);
+        ep[1] = fma(d[i][1], Ue[i][1], ep[1]);
+        ep[2] = fma(d[i][2], Ue[i][2], ep[2]);
+        ep[3] += d[i][1] * Ue[i][0] + d[i][0] * Ue[i][1];
+        ep[4] += d[i][2] * Ue[i][1] + d[i][1] * Ue[i][2];
+        ep[5] += d[i][2] * Ue[i][0] + d[i][0] * Ue[i][2];
+    }
+    const int mi = a.mat[e];
+    const double *mp = a.matpar + 8 * mi;
+    double sg[6];
+    const long long ngp = 8ll * a.n, q = 8ll * e + g;
+    if (a.matkind[mi] == SVLGPU_PLASTIC3DJ2) {
+        J2Par jp = {mp[0], mp[1], mp[3], mp[4], mp[5]};
+        double st[13];
+#pragma unroll
+        for (int i = 0; i < 13; i++) st[i] = a.state[i * ngp + q];
+        j2_return_map(jp, ep, st, sg);
+        if (a.commit && act) {
+#pragma unroll
+            for (int i = 0; i < 13; i++) a.state[i * ngp + q] = st[i];
+        }
+    } else {
+        iso_stress3(iso_from_E_nu(mp[0], mp[1]), ep, sg);
+    }
+    if (a.gp && act) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) { a.gp[i * ngp + q] = ep[i]; a.gp[(6 + i) * ngp + q] = sg[i]; }
+    }
+    // f_gp = w |J| B^T sigma  (lin3DHexa8.cpp:408), then reduce-scatter over the 8 Gauss points:
+    // after the three exchanges lane g holds the 3 force components of node g.
+    double f[8][3];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        f[i][0] = wd * (d[i][0] * sg[0] + d[i][1] * sg[3] + d[i][2] * sg[5]);
+        f[i][1] = wd * (d[i][1] * sg[1] + d[i][0] * sg[3] + d[i][2] * sg[4]);
+        f[i][2] = wd * (d[i][2] * sg[2] + d[i][1] * sg[4] + d[i][0] * sg[5]);
+    }
+    double h4[4][3], h2[2][3], h1[3];
+    const bool b4 = g & 4, b2 = g & 2, b1 = g & 1;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double keep = b4 ? f[4 + i][c] : f[i][c];
+            const double send = b4 ? f[i][c] : f[4 + i][c];
+            h4[i][c] = keep + shfl_xor_d(send, 4);
+        }
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double keep = b2 ? h4[2 + i][c] : h4[i][c];
+            const double send = b2 ? h4[i][c] : h4[2 + i][c];
+            h2[i][c] = keep + shfl_xor_d(send, 2);
+        }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const double keep = b1 ? h2[1][c] : h2[0][c];
+        const double send = b1 ? h2[0][c] : h2[1][c];
+        h1[c] = keep + shfl_xor_d(send, 1);
+    }
+    if (act) {
+        double *o = a.fe + 3ll * q;
+        o[0] = h1[0]; o[1] = h1[1]; o[2] = h1[2];
+    }
+}
+
+__global__ void __launch_bounds__(128) k_gen_quad4(const GenArgs a) {
+    __shared__ double sx[4][8][4][4];            // [warp][elem in warp][node][X(2) U(2)]
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int el = lane >> 2, g = lane & 3;
+    int e = tid >> 2;
+    const bool act = e < a.n;
+    if (!act) e = a.n - 1;
+    {
+        const int node = a.conn[(long long)e * 4 + g];
+        const double *x = a.coords + 2ll * node;
+        const double *u = a.U + a.node_ptr[node];
+        double *s = sx[w][el][g];
+        s[0] = x[0]; s[1] = x[1]; s[2] = u[0]; s[3] = u[1];
+    }
+    __syncwarp();
+    double X[4][2], Ue[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const double *s = sx[w][el][i];
+        X[i][0] = s[0]; X[i][1] = s[1]; Ue[i][0] = s[2]; Ue[i][1] = s[3];
+    }
+    double d[4][2];
+    const double wd = a.th[e] * quad4_grad(X, g, d, nullptr);
+    double ep[3] = {0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {                // lin2DQuad4.cpp:705-708
+        ep[0] = fma(d[i][0], Ue[i][0], ep[0]);
+        ep[1] = fma(d[i][1], Ue[i][1], ep[1]);
+        ep[2] += d[i][1] * Ue[i][0] + d[i][0] * Ue[i][1];
+    }
+    const int mi = a.mat[e];
+    const double *mp = a.matpar + 8 * mi;
+    double sg[3];
+    iso_stress2(iso_from_E_nu(mp[0], mp[1]), ep, sg);
+    const long long ngp = 4ll * a.n, q = 4ll * e + g;
+    if (a.gp && act) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) { a.gp[i * ngp + q] = ep[i]; a.gp[(3 + i) * ngp + q] = sg[i]; }
+    }
+    double f[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        f[i][0] = wd * (d[i][0] * sg[0] + d[i][1] * sg[2]);
+        f[i][1] = wd * (d[i][1] * sg[1] + d[i][0] * sg[2]);
+    }
+    double h2[2][2], h1[2];
+    const bool b2 = g & 2, b1 = g & 1;
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const double keep = b2 ? f[2 + i][c] : f[i][c];
+            const double send = b2 ? f[i][c] : f[2 + i][c];
+            h2[i][c] = keep + shfl_xor_d(send, 2);
+        }
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        const double keep = b1 ? h2[1][c] : h2[0][c];
+        const double send = b1 ? h2[0][c] : h2[1][c];
+        h1[c] = keep + shfl_xor_d(send, 1);
+    }
+    if (act) {
+        double *o = a.fe + 2ll * q;
+        o[0] = h1[0]; o[1] = h1[1];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// generic nodes: gather element contributions in ascending element order, then update
+// ------------------------------------------------------------------------------------------
+struct GNodeArgs {
+    int n;
+    const int32_t *dof0, *ndof, *ptr;
+    const long long *slot;
+    const double *fe;
+    const double *U, *Up, *kinv, *km;
+    double *Un;
+    int mode;
+};
+__global__ void __launch_bounds__(256) k_gen_nodes(const GNodeArgs a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n) return;
+    const int d0 = a.dof0[t], nd = a.ndof[t];
+    double F[9];
+#pragma unroll
+    for (int c = 0; c < 9; c++) F[c] = 0.0;
+    for (int q = a.ptr[t]; q < a.ptr[t + 1]; q++) {
+        const double *f = a.fe + a.slot[q];
+#pragma unroll
+        for (int c = 0; c < 9; c++)
+            if (c < nd) F[c] += f[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 9; c++)
+        if (c < nd) {
+            if (a.mode == 0) {
+                const double un = a.U[d0 + c];
+                const double du = (a.km[d0 + c] * (un - a.Up[d0 + c]) - F[c]) * a.kinv[d0 + c];
+                a.Un[d0 + c] = un + du;
+            } else {
+                a.Un[d0 + c] = F[c];
+            }
+        }
+}
+
+// ------------------------------------------------------------------------------------------
+// nodal loads (Assembler.cpp:316-350 point loads): U_{n+1}[d] += kinv[d] * sum_l coef_l amp_l(k)
+// ------------------------------------------------------------------------------------------
+struct PLArgs {
+    int n;                        // loaded dofs
+    const int32_t *dof, *ptr;     // CSR over loaded dofs
+    const int32_t *load;          // load index of each entry
+    const double *coef;           // factor * dir
+    const double *series;         // concatenated amplitude series
+    const int32_t *soff, *snt;    // per load
+    const double *amp;            // per-load amplitude of this step (host-fed) or null
+    const double *kinv;
+    double *Un;
+    int k;
+};
+__global__ void k_nodal_loads(const PLArgs a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n) return;
+    double F = 0.0;
+    for (int q = a.ptr[t]; q < a.ptr[t + 1]; q++) {
+        const int l = a.load[q];
+        double amp;
+        if (a.amp) amp = a.amp[l];
+        else amp = (a.snt[l] == 1) ? a.series[a.soff[l]] : ((a.k < a.snt[l]) ? a.series[a.soff[l] + a.k] : 0.0);
+        F += a.coef[q] * amp;
+    }
+    const int d = a.dof[t];
+    a.Un[d] += a.kinv[d] * F;
+}
+
+// ------------------------------------------------------------------------------------------
+// DRM effective forces (lin3DHexa8.cpp:660-718): per DRM node, sum of pre-assembled
+// boundary<->exterior stiffness blocks times the (sign-flipped for exterior) incident field.
+// ------------------------------------------------------------------------------------------
+struct DrmArgs {
+    int n, ndim, nt, nf, k, analytic;
+    const int32_t *dof0, *ptr, *col;
+    const uint8_t *ext;
+    const double *blk;            // [entries][ndim*ndim]
+    const double *field;          // [n][nt][nf]
+    const double *xyz;            // [n][ndim]
+    double dir[3], pol[3], xref[3], c, f0, t0, amp, factor, dt;
+    const double *kinv;
+    double *Un;
+};
+__device__ __forceinline__ double ricker_disp(double tau, double f0) {
+    // Ricker displacement pulse (1 - 2b) e^{-b}, b = (pi f0 tau)^2  (PlaneWave.py:222-223)
+    const double b = (M_PI * f0 * tau) * (M_PI * f0 * tau);
+    return (1.0 - 2.0 * b) * exp(-b);
+}
+__global__ void k_drm(const DrmArgs a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n) return;
+    double F[3] = {0, 0, 0};
+    for (int q = a.ptr[t]; q < a.ptr[t + 1]; q++) {
+        const int cn = a.col[q];
+        double u[3] = {0, 0, 0};
+        if (a.analytic) {
+            double s = 0.0;
+            for (int c = 0; c < a.ndim; c++) s += (a.xyz[(long long)cn * a.ndim + c] - a.xref[c]) * a.dir[c];
+            const double val = a.amp * ricker_disp(a.k * a.dt - a.t0 - s / a.c, a.f0);
+            for (int c = 0; c < a.ndim; c++) u[c] = val * a.pol[c];
+        } else {
+            const double *row = a.field + ((long long)cn * a.nt + a.k) * a.nf;
+            for (int c = 0; c < a.ndim; c++) u[c] = row[c];
+        }
+        const double sgn = a.ext[cn] ? -1.0 : 1.0;          // Driver.hpp:1714-1716
+        const double *B = a.blk + (long long)q * a.ndim * a.ndim;
+        for (int r = 0; r < a.ndim; r++)
+            for (int c = 0; c < a.ndim; c++) F[r] += B[r * a.ndim + c] * (sgn * u[c]);
+    }
+    const int d0 = a.dof0[t];
+    for (int r = 0; r < a.ndim; r++) a.Un[d0 + r] += a.kinv[d0 + r] * (a.factor * F[r]);
+}
+
+// ------------------------------------------------------------------------------------------
+// NODE recorder row (Recorder.cpp:239-269); V, A as in CentralDifference.cpp:141-144
+// ------------------------------------------------------------------------------------------
+__global__ void k_record(int n, const int32_t *dofs, const double *Un, const double *U, const double *Up,
+                         double dt, int field, double *row) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int d = dofs[t];
+    const double un = Un[d], u = U[d], up = Up[d];
+    double v;
+    if (field == SVLGPU_DISP) v = un;
+    else if (field == SVLGPU_VEL) v = 1.0 / 2.0 / dt * (un - up);
+    else v = 1.0 / dt / dt * ((un - u) - u + up);
+    row[t] = v;
+}
+
+__global__ void k_gather(int n, const int32_t *dofs, const int32_t *int_of_total, const double *Un,
+                         const double *U, const double *Up, double dt, int field, double *out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int d = int_of_total[dofs ? dofs[t] : t];
+    // state after the last step: Un = U_{n+1} (current), U = U_n, Up = U_{n-1}
+    const double un = Un[d], u = U[d], up = Up[d];
+    double v;
+    if (field == SVLGPU_DISP) v = un;
+    else if (field == SVLGPU_VEL) v = 1.0 / 2.0 / dt * (un - up);
+    else v = 1.0 / dt / dt * ((un - u) - u + up);
+    out[t] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// host drivers
+// ------------------------------------------------------------------------------------------
+static void timer_begin(svlgpu_model *m, int which) {
+    if (!m->kernel_timing) return;
+    KernelTimer &t = m->timers[which];
+    if (!t.e0) { cudaEventCreate(&t.e0); cudaEventCreate(&t.e1); }
+    if (t.pending) {
+        float ms = 0;
+        cudaEventSynchronize(t.e1);
+        cudaEventElapsedTime(&ms, t.e0, t.e1);
+        t.total_ms += ms; t.pending = false;
+    }
+    cudaEventRecord(t.e0, m->stream);
+}
+static void timer_end(svlgpu_model *m, int which) {
+    if (!m->kernel_timing) return;
+    KernelTimer &t = m->timers[which];
+    cudaEventRecord(t.e1, m->stream);
+    t.pending = true;
+    t.launches++;
+}
+void timer_flush(svlgpu_model *m) {
+    for (int i = 0; i < 5; i++) {
+        KernelTimer &t = m->timers[i];
+        if (t.pending) {
+            float ms = 0;
+            cudaEventSynchronize(t.e1);
+            cudaEventElapsedTime(&ms, t.e0, t.e1);
+            t.total_ms += ms; t.pending = false;
+        }
+    }
+}
+
+static int stencil_nw() {
+    static int nw = 0;
+    if (!nw) {
+        const char *s = getenv("SVLGPU_STENCIL_NW");
+        nw = s ? atoi(s) : 8;
+        if (nw != 4 && nw != 8) nw = 8;
+    }
+    return nw;
+}
+size_t stencil3_smem(int ncls, int nw) {
+    const size_t tbl = ((size_t)ncls * kTbl3Stride + 1) & ~(size_t)1;
+    return (tbl + 3ull * 3 * (nw * 4 + 2) * 36) * sizeof(double);
+}
+
+static int launch_force_update(svlgpu_model *m, const double *U, const double *Up, double *Un, int mode, int commit) {
+    // 1. generic Gauss-point elements
+    for (auto &gs : m->gsets) {
+        if (!gs.n) continue;
+        GenArgs a;
+        a.n = gs.n; a.conn = gs.d_conn; a.mat = gs.d_mat; a.th = gs.d_th; a.matkind = m->d_matkind;
+        a.matpar = m->d_matpar; a.coords = m->d_coords; a.node_ptr = m->d_node_ptr; a.U = U;
+        a.fe = gs.d_fe; a.state = gs.d_state; a.gp = gs.d_gp; a.commit = commit;
+        timer_begin(m, 1);
+        if (gs.kind == SVLGPU_LIN3DHEXA8) {
+            const long long thr = 8ll * gs.n;
+            k_gen_hex8<<<(unsigned)((thr + 127) / 128), 128, 0, m->stream>>>(a);
+        } else {
+            const long long thr = 4ll * gs.n;
+            k_gen_quad4<<<(unsigned)((thr + 127) / 128), 128, 0, m->stream>>>(a);
+        }
+        timer_end(m, 1);
+        m->total_launches++;
+    }
+    // 2. lattice blocks
+    for (auto &b : m->blocks) {
+        if (!b.n_stencil_nodes) continue;
+        timer_begin(m, 0);
+        if (b.ndim == 3) {
+            Blk3 p;
+            p.U = U; p.Up = Up; p.Un = Un; p.cls = b.d_cls; p.tbl = b.d_tbl; p.dof0 = b.dof0;
+            p.ncls = b.ncls; p.nx = b.nx; p.ny = b.ny; p.nz = b.nz;
+            p.tiles_x = b.tiles_x; p.tiles_y = b.tiles_y; p.kz = b.kz; p.mode = mode;
+            const unsigned grid = (unsigned)(b.tiles_x * b.tiles_y * b.zchunks);
+            if (b.nw == 4) k_stencil3<4><<<grid, 128, stencil3_smem(b.ncls, 4), m->stream>>>(p);
+            else k_stencil3<8><<<grid, 256, stencil3_smem(b.ncls, 8), m->stream>>>(p);
+        } else {
+            Blk2 p;
+            p.U = U; p.Up = Up; p.Un = Un; p.cls = b.d_cls; p.tbl = b.d_tbl; p.dof0 = b.dof0;
+            p.ncls = b.ncls; p.nx = b.nx; p.ny = b.ny; p.mode = mode;
+            dim3 grid((b.nx + 63) / 64, (b.ny + 3) / 4);
+            k_stencil2<<<grid, 256, (size_t)b.ncls * kTbl2Stride * sizeof(double), m->stream>>>(p);
+        }
+        timer_end(m, 0);
+        m->total_launches++;
+    }
+    // 3. generic nodes
+    if (m->n_gnodes) {
+        GNodeArgs a;
+        a.n = m->n_gnodes; a.dof0 = m->d_gn_dof0; a.ndof = m->d_gn_ndof; a.ptr = m->d_gn_ptr;
+        a.slot = (const long long *)m->d_gn_slot; a.fe = m->d_fe_arena; a.U = U; a.Up = Up;
+        a.kinv = m->d_kinv; a.km = m->d_km; a.Un = Un; a.mode = mode;
+        timer_begin(m, 2);
+        k_gen_nodes<<<(m->n_gnodes + 255) / 256, 256, 0, m->stream>>>(a);
+        timer_end(m, 2);
+        m->total_launches++;
+    }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+void record_rows(svlgpu_model *m) {
+    for (auto &r : m->recorders) {
+        if (r.rows >= r.max_rows || !r.width) continue;
+        k_record<<<(r.width + 127) / 128, 128, 0, m->stream>>>(r.width, r.d_dofs, m->d_U[m->next], m->d_U[m->cur],
+                                                                 m->d_U[m->prev], m->dt, r.field,
+                                                                 r.d_rows + (size_t)r.rows * r.width);
+        r.rows++;
+        m->total_launches++;
+    }
+}
+
+int run_steps(svlgpu_model *m, int k0, int k1, const double *dev_amp) {
+    const int64_t before = m->total_launches;
+    for (int k = k0; k < k1; k++) {
+        const double *U = m->d_U[m->cur], *Up = m->d_U[m->prev];
+        double *Un = m->d_U[m->next];
+        if (launch_force_update(m, U, Up, Un, 0, 1)) return 1;
+        if (m->n_pl_dofs) {
+            PLArgs a;
+            a.n = m->n_pl_dofs; a.dof = m->d_pl_dof; a.ptr = m->d_pl_ptr; a.load = m->d_pl_load;
+            a.coef = m->d_pl_coef; a.series = m->d_pl_series; a.soff = m->d_pl_soff; a.snt = m->d_pl_nt;
+            a.amp = dev_amp; a.kinv = m->d_kinv; a.Un = Un; a.k = k;
+            timer_begin(m, 3);
+            k_nodal_loads<<<(a.n + 127) / 128, 128, 0, m->stream>>>(a);
+            timer_end(m, 3);
+            m->total_launches++;
+        }
+        for (auto &d : m->drm_dev) {
+            DrmArgs a;
+            a.n = d.n_nodes; a.ndim = m->ndim; a.nt = d.nt; a.nf = d.nf; a.k = k; a.analytic = d.analytic;
+            a.dof0 = d.d_node_dof0; a.ptr = d.d_row_ptr; a.col = d.d_col_node; a.ext = d.d_ext;
+            a.blk = d.d_blk; a.field = d.d_field; a.xyz = d.d_xyz;
+            for (int c = 0; c < 3; c++) { a.dir[c] = d.dir[c]; a.pol[c] = d.pol[c]; a.xref[c] = d.xref[c]; }
+            a.c = d.c; a.f0 = d.f0; a.t0 = d.t0; a.amp = d.amp; a.factor = d.factor; a.dt = m->dt;
+            a.kinv = m->d_kinv; a.Un = Un;
+            if (!d.analytic && k >= d.nt) continue;
+            k_drm<<<(a.n + 127) / 128, 128, 0, m->stream>>>(a);
+            m->total_launches++;
+        }
+        record_rows(m);
+        // rotate: U_{n-1} <- U_n <- U_{n+1}
+        const int old_prev = m->prev;
+        m->prev = m->cur; m->cur = m->next; m->next = old_prev;
+        m->steps_done++;
+    }
+    CUDA_OK(cudaGetLastError());
+    if (k1 > k0) m->launches_per_step = (m->total_launches - before) / (k1 - k0);
+    return 0;
+}
+
+// Assembler::ComputeInternalForceVector for the current displacement state
+int compute_internal_force(svlgpu_model *m, double *F_host) {
+    double *tmp = m->d_U[m->next];
+    CUDA_OK(cudaMemsetAsync(tmp, 0, sizeof(double) * m->n_int, m->stream));
+    if (launch_force_update(m, m->d_U[m->cur], m->d_U[m->prev], tmp, 1, 0)) return 1;
+    std::vector<double> h(m->n_int);
+    CUDA_OK(cudaMemcpyAsync(h.data(), tmp, sizeof(double) * m->n_int, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_OK(cudaStreamSynchronize(m->stream));
+    for (int t = 0; t < m->n_total; t++) F_host[t] = h[m->int_of_total[t]];
+    return 0;
+}
+
+int gather_state(svlgpu_model *m, int field, const int32_t *dofs, int n, double *out) {
+    int32_t *d_dofs = nullptr;
+    double *d_out = nullptr;
+    if (dofs) {
+        CUDA_OK(cudaMalloc(&d_dofs, sizeof(int32_t) * n));
+        CUDA_OK(cudaMemcpyAsync(d_dofs, dofs, sizeof(int32_t) * n, cudaMemcpyHostToDevice, m->stream));
+    }
+    CUDA_OK(cudaMalloc(&d_out, sizeof(double) * n));
+    // after a step the newest state sits in `cur`; U_n in `prev`, U_{n-1} in `next`
+    k_gather<<<(n + 255) / 256, 256, 0, m->stream>>>(n, d_dofs, m->d_int_of_total, m->d_U[m->cur], m->d_U[m->prev],
+                                                      m->d_U[m->next], m->dt, m->steps_done ? field : SVLGPU_DISP, d_out);
+    CUDA_OK(cudaMemcpyAsync(out, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_OK(cudaStreamSynchronize(m->stream));
+    cudaFree(d_dofs); cudaFree(d_out);
+    return 0;
+}
+
+int configure_kernels() {
+    CUDA_OK(cudaFuncSetAttribute(k_stencil3<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(k_stencil3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(k_stencil2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    return 0;
+}
+int default_stencil_nw() { return stencil_nw(); }
+
+}  // namespace svl

@@ -1,0 +1,167 @@
+// model.h -- host-side model (what the C ABI builder calls fill in) and the device plan.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <utility>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../include/svlgpu.h"
+
+namespace svl {
+
+struct Material { int kind; double p[8]; };
+
+struct PointLoad {
+    std::vector<int32_t> nodes;
+    double dir[3];
+    std::vector<double> series;      // size 1 = constant
+    double factor;
+};
+
+struct DrmLoad {
+    std::vector<int32_t> elems, nodes;
+    std::vector<uint8_t> ext;
+    int nt = 0;
+    std::vector<double> field;       // [nnodes][nt][3*ndim], empty when analytic
+    bool analytic = false;
+    double dir[3], pol[3], xref[3], c = 0, f0 = 0, t0 = 0, amp = 0;
+    double factor = 1.0;
+};
+
+struct Recorder {
+    int field = 0;
+    std::vector<int32_t> nodes;
+    int max_rows = 0;
+    int32_t *d_dofs = nullptr;       // internal dof ids, `width` entries
+    double *d_rows = nullptr;        // [max_rows][width]
+    int width = 0, rows = 0;
+};
+
+struct BlockHint { int node0, nx, ny, nz; };
+
+// One verified lattice block advanced by the block-stencil kernel.
+struct Block {
+    int node0 = 0, nx = 0, ny = 0, nz = 0;   // node lattice dims
+    int ndim = 3;                    // 3 (hex8) or 2 (quad4, nz == 1)
+    long long dof0 = 0;              // internal dof of lattice node 0
+    int ncls = 0;                    // node classes incl. class 0 (= not handled here)
+    uint8_t *d_cls = nullptr;        // [nx*ny*nz] class per node
+    double *d_tbl = nullptr;         // [ncls][stride]
+    int64_t n_stencil_nodes = 0;
+    int tiles_x = 0, tiles_y = 0, zchunks = 0, kz = 0, nw = 8;   // launch geometry
+};
+
+// per-class coefficient table strides (doubles)
+constexpr int kTbl3Stride = 276;     // 27 x (9 coefficients + 1 pad) + kinv[3] + km[3]
+constexpr int kTbl2Stride = 40;      // 9 x (2x2) + kinv[2] + km[2]
+
+struct KernelTimer {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    double total_ms = 0.0;
+    int64_t launches = 0;
+    bool pending = false;
+};
+
+struct GenericSet {                  // Gauss-point path: elements of one kind
+    int kind = 0, n = 0, npe = 8, ndofn = 3, ngp = 8;
+    int32_t *d_conn = nullptr;       // [n][npe] node ids
+    int32_t *d_mat = nullptr;        // [n] material index
+    double *d_th = nullptr;          // [n] thickness (quad)
+    double *d_fe = nullptr;          // [n][npe][ndofn] (inside the fe arena)
+    double *d_state = nullptr;       // [13][n*ngp] J2 state (only when the set has J2 elements)
+    double *d_gp = nullptr;          // [2*ncomp][n*ngp] strain | stress at Gauss points
+    std::vector<int32_t> elems;      // global element ids
+    bool has_j2 = false;
+};
+
+struct DrmDev {
+    int n_nodes = 0, nt = 0, nf = 0;
+    int32_t *d_node_dof0 = nullptr;  // internal dof0 of each DRM node
+    uint8_t *d_ext = nullptr;
+    double *d_field = nullptr;       // [nnodes][nt][nf]
+    int32_t *d_row_ptr = nullptr;    // CSR over DRM nodes
+    int32_t *d_col_node = nullptr;   // local DRM node index of the column node
+    double *d_blk = nullptr;         // [entries][ndim*ndim] K block (row node <- col node)
+    double *d_xyz = nullptr;         // node coordinates (analytic mode)
+    bool analytic = false;
+    double dir[3], pol[3], xref[3], c = 0, f0 = 0, t0 = 0, amp = 0, factor = 1;
+};
+
+}  // namespace svl
+
+struct svlgpu_model {
+    // ---- builder state (host) ----
+    int ndim = 3, lumped = 1;
+    int n_nodes = 0, n_total = 0, n_free = 0;
+    std::vector<int32_t> node_ndof, node_ptr, totaldof, freedof;
+    std::vector<double> coords;
+    std::vector<std::pair<int32_t, std::vector<double>>> masses;
+    struct Constraint { int tag, slave; std::vector<int32_t> master; std::vector<double> factor; };
+    std::vector<Constraint> constraints;
+    std::vector<svl::Material> materials;
+    std::vector<int32_t> elem_kind, elem_conn /*8 per elem*/, elem_mat;
+    std::vector<double> elem_attr /*10 per elem*/, elem_am;
+    std::vector<svl::PointLoad> ploads;
+    std::vector<svl::DrmLoad> drms;
+    std::vector<svl::Recorder> recorders;
+    std::vector<svl::BlockHint> hints;
+    std::vector<double> U0, V0, A0;
+
+    // ---- plan / device state ----
+    bool finalized = false;
+    int device = 0;
+    double dt = 0.0;
+    cudaStream_t stream = nullptr;
+    int64_t device_bytes = 0;
+    std::vector<void *> allocs;
+
+    int n_int = 0;                                  // internal dofs (= sum of node ndof)
+    std::vector<int32_t> int_of_total;              // total dof -> internal dof (= node_ptr[node] + c)
+    int32_t *d_int_of_total = nullptr, *d_node_ptr = nullptr;
+    double *d_U[3] = {nullptr, nullptr, nullptr};   // rotating buffers
+    int cur = 0, prev = 1, next = 2;
+    double *d_kinv = nullptr, *d_km = nullptr;      // per internal dof: 1/Keff, Kminus (0 if not free)
+    std::vector<double> h_mass;                     // lumped mass per internal dof
+
+    std::vector<svl::Block> blocks;
+    std::vector<svl::GenericSet> gsets;
+    double *d_coords = nullptr;                     // [n_nodes][ndim]
+    double *d_matpar = nullptr;                     // [n_mat][8]
+    int32_t *d_matkind = nullptr;
+    int n_gnodes = 0;
+    int32_t *d_gn_dof0 = nullptr, *d_gn_ndof = nullptr, *d_gn_ptr = nullptr;
+    int64_t *d_gn_slot = nullptr;                   // offsets (in doubles) into the fe arena
+    double *d_fe_arena = nullptr;
+
+    // nodal loads: CSR over loaded dofs
+    int n_ploads = 0, n_pl_dofs = 0;
+    int32_t *d_pl_dof = nullptr, *d_pl_ptr = nullptr, *d_pl_load = nullptr;
+    double *d_pl_coef = nullptr, *d_pl_series = nullptr;
+    int32_t *d_pl_soff = nullptr, *d_pl_nt = nullptr;
+    double *d_pl_amp = nullptr;                     // per-load amplitude of the current step (host-fed)
+    double *h_pl_amp = nullptr, *h_row = nullptr;   // pinned staging
+    int h_row_len = 0;
+
+    std::vector<svl::DrmDev> drm_dev;
+
+    // counters / timing
+    int64_t total_launches = 0, launches_per_step = 0;
+    int64_t n_block_nodes = 0, n_generic_elements = 0, n_elem_classes = 0, n_node_classes = 0;
+    bool kernel_timing = false;
+    svl::KernelTimer timers[5];
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_step_ms = 0.0;
+    int steps_done = 0;
+};
+
+namespace svl {
+void set_error(const std::string &s);
+int plan_and_upload(svlgpu_model *m);                                       // planner.cu
+int run_steps(svlgpu_model *m, int k0, int k1, const double *dev_amp);      // kernels.cu
+int compute_internal_force(svlgpu_model *m, double *F_host);
+int gather_state(svlgpu_model *m, int field, const int32_t *dofs, int n, double *out);
+void timer_flush(svlgpu_model *m);
+int configure_kernels();
+int default_stencil_nw();
+size_t stencil3_smem(int ncls, int nw);
+}  // namespace svl

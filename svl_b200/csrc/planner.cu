@@ -1,0 +1,565 @@
+// planner.cu -- turns the host model into the device plan:
+//   * element classes (congruent geometry + material -> one K_e / lumped-mass table),
+//   * lumped M, C and the CentralDifference coefficients 1/Keff, Kminus per dof
+//     (CentralDifference.cpp:35-71,217; Assembler.cpp:47-67,116-158,622-697),
+//   * verified lattice blocks -> node classes -> pre-summed stencil tables,
+//   * the generic Gauss-point element sets and the atomic-free node gather lists,
+//   * nodal load / DRM / recorder tables.
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <unordered_map>
+#include "model.h"
+#include "elem_math.h"
+
+namespace svl {
+
+#define CUDA_OK(x)                                                                          \
+    do {                                                                                    \
+        cudaError_t e_ = (x);                                                               \
+        if (e_ != cudaSuccess) {                                                            \
+            set_error(std::string(#x) + ": " + cudaGetErrorString(e_));                     \
+            return 1;                                                                       \
+        }                                                                                   \
+    } while (0)
+
+template <typename T> static T *dalloc(svlgpu_model *m, size_t n) {
+    T *p = nullptr;
+    if (n == 0) n = 1;
+    if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) return nullptr;
+    m->allocs.push_back(p);
+    m->device_bytes += (int64_t)(n * sizeof(T));
+    return p;
+}
+template <typename T> static T *dupload(svlgpu_model *m, const T *h, size_t n) {
+    T *p = dalloc<T>(m, n);
+    if (p && n) cudaMemcpy(p, h, n * sizeof(T), cudaMemcpyHostToDevice);
+    return p;
+}
+template <typename T> static T *dupload(svlgpu_model *m, const std::vector<T> &v) {
+    return dupload<T>(m, v.data(), v.size());
+}
+
+static inline uint64_t mix(uint64_t h, uint64_t v) {
+    h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+    return h * 0xff51afd7ed558ccdull;
+}
+
+struct ElemClass {
+    int kind, mat;
+    bool linear;                 // has a constant K_e
+    int rep;                     // representative element
+    std::vector<double> Ke;      // (npe*ndim)^2 row-major, empty if !linear
+    double mnode[8];             // lumped nodal mass of each local node
+};
+
+static int kind_npe(int k) { return (k == SVLGPU_LIN3DHEXA8 || k == SVLGPU_PML3DHEXA8) ? 8 : 4; }
+static const int kHexPos[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+static const int kQuadPos[4][2] = {{0, 0}, {1, 0}, {1, 1}, {0, 1}};
+
+int plan_and_upload(svlgpu_model *m) {
+    const int nd = m->ndim;
+    const int nE = (int)m->elem_kind.size();
+    const int nN = m->n_nodes;
+    const double dt = m->dt;
+    if (cudaSetDevice(m->device) != cudaSuccess) { set_error("no usable CUDA device (there is no CPU fallback)"); return 1; }
+    CUDA_OK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    if (configure_kernels()) return 1;
+    CUDA_OK(cudaEventCreate(&m->ev0));
+    CUDA_OK(cudaEventCreate(&m->ev1));
+
+    // ---- A. dof maps --------------------------------------------------------------------
+    m->n_int = m->node_ptr[nN];
+    m->int_of_total.assign(m->n_total, -1);
+    for (int q = 0; q < m->n_int; q++) {
+        const int t = m->totaldof[q];
+        if (t < 0 || t >= m->n_total || m->int_of_total[t] != -1) { set_error("total dof numbering is not a permutation"); return 1; }
+        m->int_of_total[t] = q;
+    }
+    if (!m->constraints.empty()) { set_error("constraints are not supported by the device path yet"); return 1; }
+    for (int e = 0; e < nE; e++) {
+        const int k = m->elem_kind[e];
+        if (k == SVLGPU_PML3DHEXA8 || k == SVLGPU_PML2DQUAD4) { set_error("PML elements are not supported by the device path yet"); return 1; }
+        if (!m->lumped) { set_error("consistent mass makes Keff non-diagonal: not supported by the explicit device path"); return 1; }
+        const int mk = m->materials[m->elem_mat[e]].kind;
+        const bool ok = (k == SVLGPU_LIN3DHEXA8 && (mk == SVLGPU_ELASTIC3DLINEAR || mk == SVLGPU_PLASTIC3DJ2)) ||
+                        (k == SVLGPU_LIN2DQUAD4 && mk == SVLGPU_ELASTIC2DPLANESTRAIN);
+        if (!ok) { set_error("unsupported element/material combination"); return 1; }
+    }
+
+    // ---- B. element classes ---------------------------------------------------------------
+    const char *tol_s = getenv("SVLGPU_CLASS_TOL");
+    const double class_tol = tol_s ? atof(tol_s) : 1e-11;
+    std::vector<int32_t> elem_cls(nE);
+    std::vector<ElemClass> classes;
+    {
+        std::unordered_map<uint64_t, std::vector<int>> table;     // hash -> class ids
+        std::vector<std::vector<int64_t>> keys;
+        std::vector<int64_t> key;
+        for (int e = 0; e < nE; e++) {
+            const int kind = m->elem_kind[e], npe = kind_npe(kind);
+            const int32_t *cn = &m->elem_conn[8ll * e];
+            const double *x0 = &m->coords[(size_t)nd * cn[0]], *x1 = &m->coords[(size_t)nd * cn[1]];
+            double h = 0;
+            for (int c = 0; c < nd; c++) h += (x1[c] - x0[c]) * (x1[c] - x0[c]);
+            h = std::sqrt(h);
+            const double inv = 1.0 / (class_tol * (h > 0 ? h : 1.0));
+            key.clear();
+            key.push_back(kind); key.push_back(m->elem_mat[e]);
+            for (int i = 1; i < npe; i++) {
+                const double *xi = &m->coords[(size_t)nd * cn[i]];
+                for (int c = 0; c < nd; c++) key.push_back(llround((xi[c] - x0[c]) * inv));
+            }
+            key.push_back(llround(h / (class_tol * 1e3)));        // absolute size (coarser: relative coords carry the shape)
+            if (kind == SVLGPU_LIN2DQUAD4) { int64_t b; std::memcpy(&b, &m->elem_attr[10ll * e], 8); key.push_back(b); }
+            uint64_t hsh = 1469598103934665603ull;
+            for (int64_t v : key) hsh = mix(hsh, (uint64_t)v);
+            auto &bucket = table[hsh];
+            int found = -1;
+            for (int c : bucket) if (keys[c] == key) { found = c; break; }
+            if (found < 0) {
+                found = (int)classes.size();
+                bucket.push_back(found);
+                keys.push_back(key);
+                ElemClass ec;
+                ec.kind = kind; ec.mat = m->elem_mat[e]; ec.rep = e;
+                const Material &mat = m->materials[ec.mat];
+                ec.linear = (mat.kind == SVLGPU_ELASTIC3DLINEAR || mat.kind == SVLGPU_ELASTIC2DPLANESTRAIN);
+                const double rho = mat.p[2];
+                if (kind == SVLGPU_LIN3DHEXA8) {
+                    double X[8][3], mm[8][8];
+                    for (int i = 0; i < 8; i++) for (int c = 0; c < 3; c++) X[i][c] = m->coords[3ll * cn[i] + c];
+                    hex8_mass_nodes(X, rho, mm);
+                    for (int i = 0; i < 8; i++) { double s = mm[i][i]; for (int j = 0; j < 8; j++) if (j != i) s += mm[i][j]; ec.mnode[i] = s; }
+                    if (ec.linear) { ec.Ke.resize(576); hex8_stiffness(X, iso_from_E_nu(mat.p[0], mat.p[1]), ec.Ke.data()); }
+                } else {
+                    double X[4][2], mm[4][4];
+                    const double th = m->elem_attr[10ll * e];
+                    for (int i = 0; i < 4; i++) for (int c = 0; c < 2; c++) X[i][c] = m->coords[2ll * cn[i] + c];
+                    quad4_mass_nodes(X, th, rho, mm);
+                    for (int i = 0; i < 4; i++) { double s = mm[i][i]; for (int j = 0; j < 4; j++) if (j != i) s += mm[i][j]; ec.mnode[i] = s; }
+                    if (ec.linear) { ec.Ke.resize(64); quad4_stiffness(X, th, iso_from_E_nu(mat.p[0], mat.p[1]), ec.Ke.data()); }
+                }
+                classes.push_back(std::move(ec));
+            }
+            elem_cls[e] = found;
+        }
+    }
+    m->n_elem_classes = (int64_t)classes.size();
+
+    // ---- C. lumped mass, damping, CentralDifference coefficients ---------------------------
+    const double mtol = 1e-12;                       // Driver.hpp:1804 default, Assembler.cpp:647,687
+    std::vector<double> mass(m->n_int, 0.0), cdiag(m->n_int, 0.0);
+    for (auto &pm : m->masses) {
+        const int node = pm.first;
+        for (int c = 0; c < m->node_ndof[node]; c++)
+            if (std::fabs(pm.second[c]) > mtol) mass[m->node_ptr[node] + c] += pm.second[c];
+    }
+    std::vector<int32_t> inc_count(nN, 0);
+    for (int e = 0; e < nE; e++) {
+        const ElemClass &ec = classes[elem_cls[e]];
+        const int npe = kind_npe(ec.kind);
+        const double am = m->elem_am.empty() ? 0.0 : m->elem_am[e];
+        for (int l = 0; l < npe; l++) {
+            const int node = m->elem_conn[8ll * e + l];
+            inc_count[node]++;
+            if (m->node_ndof[node] < nd) { set_error("element node has fewer dofs than the element needs"); return 1; }
+            if (std::fabs(ec.mnode[l]) > mtol)
+                for (int c = 0; c < nd; c++) {
+                    mass[m->node_ptr[node] + c] += ec.mnode[l];
+                    cdiag[m->node_ptr[node] + c] += am * ec.mnode[l];
+                }
+        }
+    }
+    m->h_mass = mass;
+    std::vector<double> kinv(m->n_int, 0.0), km(m->n_int, 0.0);
+    for (int q = 0; q < m->n_int; q++) {
+        if (m->freedof[q] < 0) continue;             // restrained: dU = 0 (Mesh.cpp:354-357)
+        const double keff = 1.0 / dt / dt * mass[q] + 1.0 / 2.0 / dt * cdiag[q];
+        if (!(keff > 0.0)) { set_error("free dof without mass: Keff is singular (EigenSolver.cpp:52-55)"); return 1; }
+        kinv[q] = 1.0 / keff;
+        km[q] = 1.0 / dt / dt * mass[q] - 1.0 / 2.0 / dt * cdiag[q];
+    }
+    m->d_kinv = dupload(m, kinv);
+    m->d_km = dupload(m, km);
+
+    // ---- D. lattice blocks -> node classes ------------------------------------------------
+    std::vector<uint8_t> node_done(nN, 0);           // 1 = advanced by a block-stencil kernel
+    const int nw = default_stencil_nw();
+    for (const BlockHint &h : m->hints) {
+        const bool is3 = (nd == 3);
+        if (h.nx < 2 || h.ny < 2 || (is3 && h.nz < 2) || h.node0 < 0) continue;
+        const int NX = h.nx, NY = h.ny, NZ = is3 ? h.nz : 1;
+        const long long nbn = (long long)NX * NY * NZ;
+        if (h.node0 + nbn > nN) continue;
+        bool ok = true;
+        for (long long q = 0; q < nbn && ok; q++) ok = (m->node_ndof[h.node0 + q] == nd) && !node_done[h.node0 + q];
+        if (!ok) continue;
+        const int CX = NX - 1, CY = NY - 1, CZ = is3 ? NZ - 1 : 1;
+        std::vector<int32_t> cell(1ll * CX * CY * CZ, -1);
+        const int want_kind = is3 ? SVLGPU_LIN3DHEXA8 : SVLGPU_LIN2DQUAD4;
+        const int npe = is3 ? 8 : 4;
+        for (int e = 0; e < nE; e++) {
+            if (m->elem_kind[e] != want_kind) continue;
+            const int32_t *cn = &m->elem_conn[8ll * e];
+            const long long l0 = (long long)cn[0] - h.node0;
+            if (l0 < 0 || l0 >= nbn) continue;
+            const int i = (int)(l0 % NX), j = (int)((l0 / NX) % NY), k = (int)(l0 / ((long long)NX * NY));
+            if (i >= CX || j >= CY || (is3 && k >= CZ)) continue;
+            bool match = true;
+            for (int l = 0; l < npe && match; l++) {
+                const long long want = is3 ? l0 + kHexPos[l][0] + (long long)NX * (kHexPos[l][1] + (long long)NY * kHexPos[l][2])
+                                           : l0 + kQuadPos[l][0] + (long long)NX * kQuadPos[l][1];
+                match = ((long long)cn[l] - h.node0 == want);
+            }
+            if (!match) continue;
+            int32_t &slot = cell[i + (long long)CX * (j + (long long)CY * k)];
+            slot = (slot == -1) ? e : -2;
+        }
+        // signature of every lattice node
+        const int noct = is3 ? 8 : 4;
+        struct Sig { int32_t oc[8]; double kv[3], kmv[3]; };
+        auto sig_hash = [&](const Sig &s) {
+            uint64_t hh = 7;
+            for (int o = 0; o < 8; o++) hh = mix(hh, (uint64_t)(uint32_t)s.oc[o]);
+            for (int c = 0; c < 3; c++) { uint64_t b; std::memcpy(&b, &s.kv[c], 8); hh = mix(hh, b); std::memcpy(&b, &s.kmv[c], 8); hh = mix(hh, b); }
+            return hh;
+        };
+        std::unordered_map<uint64_t, std::vector<int>> smap;
+        std::vector<Sig> sigs;
+        std::vector<long long> pop;
+        std::vector<std::array<int32_t, 8>> rep_elems;
+        std::vector<int32_t> ncls_of(nbn, -1);
+        for (long long q = 0; q < nbn; q++) {
+            const int i = (int)(q % NX), j = (int)((q / NX) % NY), k = (int)(q / ((long long)NX * NY));
+            Sig s;
+            std::array<int32_t, 8> el;
+            for (int o = 0; o < 8; o++) { s.oc[o] = -1; el[o] = -1; }
+            int cnt = 0;
+            bool bad = false;
+            for (int o = 0; o < noct; o++) {
+                const int ci = i - 1 + (o & 1), cj = j - 1 + ((o >> 1) & 1), ck = is3 ? k - 1 + ((o >> 2) & 1) : 0;
+                if (ci < 0 || ci >= CX || cj < 0 || cj >= CY || ck < 0 || ck >= CZ) continue;
+                const int32_t e = cell[ci + (long long)CX * (cj + (long long)CY * ck)];
+                if (e == -1) continue;
+                if (e == -2 || !classes[elem_cls[e]].linear) { bad = true; break; }
+                s.oc[o] = elem_cls[e]; el[o] = e; cnt++;
+            }
+            const int node = h.node0 + (int)q;
+            if (bad || cnt == 0 || cnt != inc_count[node]) continue;
+            for (int c = 0; c < 3; c++) {
+                s.kv[c] = (c < nd) ? kinv[m->node_ptr[node] + c] : 0.0;
+                s.kmv[c] = (c < nd) ? km[m->node_ptr[node] + c] : 0.0;
+            }
+            const uint64_t hh = sig_hash(s);
+            auto &bucket = smap[hh];
+            int found = -1;
+            for (int c : bucket) if (std::memcmp(&sigs[c], &s, sizeof(Sig)) == 0) { found = c; break; }
+            if (found < 0) {
+                found = (int)sigs.size();
+                bucket.push_back(found); sigs.push_back(s); pop.push_back(0); rep_elems.push_back(el);
+            }
+            pop[found]++;
+            ncls_of[q] = found;
+        }
+        if (sigs.empty()) continue;
+        // keep the most populous classes that fit in shared memory / uint8
+        const int stride = is3 ? kTbl3Stride : kTbl2Stride;
+        int cap = 255;
+        if (is3) {
+            const long long budget = 227 * 1024 - (long long)stencil3_smem(0, nw) - 1024;
+            cap = (int)std::min<long long>(255, budget / (stride * 8) - 1);
+        }
+        std::vector<int> order(sigs.size());
+        for (size_t c = 0; c < order.size(); c++) order[c] = (int)c;
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return pop[a] != pop[b] ? pop[a] > pop[b] : a < b; });
+        std::vector<int> newid(sigs.size(), 0);
+        int ncls = 1;
+        for (int c : order) { if (ncls - 1 >= cap) break; newid[c] = ncls++; }
+        std::vector<double> tbl((size_t)ncls * stride, 0.0);
+        for (size_t c = 0; c < sigs.size(); c++) {
+            if (!newid[c]) continue;
+            double *T = &tbl[(size_t)newid[c] * stride];
+            // octants in ascending element id = the reference's assembly order (Assembler.cpp:251)
+            int oo[8], no = 0;
+            for (int o = 0; o < noct; o++) if (rep_elems[c][o] >= 0) oo[no++] = o;
+            std::sort(oo, oo + no, [&](int a, int b) { return rep_elems[c][a] < rep_elems[c][b]; });
+            for (int z = 0; z < no; z++) {
+                const int o = oo[z];
+                const ElemClass &ec = classes[sigs[c].oc[o]];
+                // this node sits at position p = 1 - octant bit inside that element
+                const int px = 1 - (o & 1), py = 1 - ((o >> 1) & 1), pz = is3 ? 1 - ((o >> 2) & 1) : 0;
+                int l = -1;
+                for (int q = 0; q < npe; q++) {
+                    if (is3 ? (kHexPos[q][0] == px && kHexPos[q][1] == py && kHexPos[q][2] == pz)
+                            : (kQuadPos[q][0] == px && kQuadPos[q][1] == py)) l = q;
+                }
+                const int ned = npe * nd;
+                for (int l2 = 0; l2 < npe; l2++) {
+                    const int dx = (is3 ? kHexPos[l2][0] : kQuadPos[l2][0]) - px;
+                    const int dy = (is3 ? kHexPos[l2][1] : kQuadPos[l2][1]) - py;
+                    const int dz = is3 ? kHexPos[l2][2] - pz : 0;
+                    for (int a = 0; a < nd; a++)
+                        for (int b = 0; b < nd; b++) {
+                            const double v = ec.Ke[(size_t)(nd * l + a) * ned + nd * l2 + b];
+                            if (is3) {
+                                // entry (di,b,dj)[s][a] with s = 1 - dz  (see k_stencil3)
+                                const int di = dx + 1, dj = dy + 1, s = 1 - dz;
+                                T[((di * 3 + b) * 3 + dj) * 10 + s * 3 + a] += v;
+                            } else {
+                                T[((dy + 1) * 3 + (dx + 1)) * 4 + a * 2 + b] += v;
+                            }
+                        }
+                }
+            }
+            for (int cc = 0; cc < nd; cc++) {
+                T[(is3 ? 270 : 36) + cc] = sigs[c].kv[cc];
+                T[(is3 ? 273 : 38) + cc] = sigs[c].kmv[cc];
+            }
+        }
+        std::vector<uint8_t> cls(nbn, 0);
+        long long nst = 0;
+        for (long long q = 0; q < nbn; q++) {
+            if (ncls_of[q] >= 0 && newid[ncls_of[q]]) { cls[q] = (uint8_t)newid[ncls_of[q]]; node_done[h.node0 + q] = 1; nst++; }
+        }
+        if (!nst) continue;
+        Block b;
+        b.node0 = h.node0; b.nx = NX; b.ny = NY; b.nz = NZ; b.ndim = nd; b.dof0 = m->node_ptr[h.node0];
+        b.ncls = ncls; b.n_stencil_nodes = nst; b.nw = nw;
+        b.d_cls = dupload(m, cls);
+        b.d_tbl = dupload(m, tbl);
+        if (is3) {
+            const int TY = nw * 4;
+            b.tiles_x = (NX + 31) / 32; b.tiles_y = (NY + TY - 1) / TY;
+            const char *kzs = getenv("SVLGPU_STENCIL_KZ");
+            int kz = kzs ? atoi(kzs) : 0;
+            if (kz <= 0) {
+                // enough work items for >= 4 waves of 148 SMs, but keep the 2 halo planes <= ~10 %
+                const long long tiles = (long long)b.tiles_x * b.tiles_y;
+                long long want = (4 * 148 + tiles - 1) / tiles;
+                kz = (int)std::max<long long>(1, (NZ + want - 1) / want);
+                kz = std::max(kz, std::min(NZ, 16));
+            }
+            b.kz = std::min(kz, NZ); b.zchunks = (NZ + b.kz - 1) / b.kz;
+        }
+        m->n_block_nodes += nst;
+        m->n_node_classes += ncls - 1;
+        m->blocks.push_back(b);
+    }
+
+    // ---- E. generic Gauss-point sets + node gather lists -----------------------------------
+    std::vector<int32_t> gset_of(nE, -1), gidx(nE, -1);
+    {
+        GenericSet gh, gq;
+        gh.kind = SVLGPU_LIN3DHEXA8; gh.npe = 8; gh.ndofn = 3; gh.ngp = 8;
+        gq.kind = SVLGPU_LIN2DQUAD4; gq.npe = 4; gq.ndofn = 2; gq.ngp = 4;
+        for (int e = 0; e < nE; e++) {
+            const int npe = kind_npe(m->elem_kind[e]);
+            bool generic = false;
+            for (int l = 0; l < npe && !generic; l++) generic = !node_done[m->elem_conn[8ll * e + l]];
+            if (!generic) continue;
+            GenericSet &g = (m->elem_kind[e] == SVLGPU_LIN3DHEXA8) ? gh : gq;
+            gidx[e] = (int)g.elems.size();
+            g.elems.push_back(e);
+            gset_of[e] = (m->elem_kind[e] == SVLGPU_LIN3DHEXA8) ? 0 : 1;
+            if (m->materials[m->elem_mat[e]].kind == SVLGPU_PLASTIC3DJ2) g.has_j2 = true;
+        }
+        m->gsets.push_back(gh);
+        m->gsets.push_back(gq);
+    }
+    long long arena = 0;
+    std::vector<long long> gbase(m->gsets.size(), 0);
+    for (size_t s = 0; s < m->gsets.size(); s++) {
+        GenericSet &g = m->gsets[s];
+        g.n = (int)g.elems.size();
+        gbase[s] = arena;
+        arena += (long long)g.n * g.npe * g.ndofn;
+        m->n_generic_elements += g.n;
+    }
+    m->d_fe_arena = dalloc<double>(m, (size_t)arena);
+    if (!m->d_fe_arena) { set_error("out of device memory (fe arena)"); return 1; }
+    CUDA_OK(cudaMemset(m->d_fe_arena, 0, sizeof(double) * (size_t)std::max<long long>(arena, 1)));
+    const bool want_gp = getenv("SVLGPU_KEEP_GAUSS") != nullptr;
+    for (size_t s = 0; s < m->gsets.size(); s++) {
+        GenericSet &g = m->gsets[s];
+        if (!g.n) continue;
+        std::vector<int32_t> conn((size_t)g.n * g.npe), mat(g.n);
+        std::vector<double> th(g.n, 1.0);
+        for (int q = 0; q < g.n; q++) {
+            const int e = g.elems[q];
+            for (int l = 0; l < g.npe; l++) conn[(size_t)q * g.npe + l] = m->elem_conn[8ll * e + l];
+            mat[q] = m->elem_mat[e];
+            th[q] = m->elem_attr[10ll * e];
+        }
+        g.d_conn = dupload(m, conn); g.d_mat = dupload(m, mat); g.d_th = dupload(m, th);
+        g.d_fe = m->d_fe_arena + gbase[s];
+        if (g.has_j2) {
+            g.d_state = dalloc<double>(m, 13ull * g.n * g.ngp);
+            if (!g.d_state) { set_error("out of device memory (J2 state)"); return 1; }
+            CUDA_OK(cudaMemset(g.d_state, 0, sizeof(double) * 13ull * g.n * g.ngp));
+        }
+        if (want_gp || g.has_j2) {
+            const int ncomp = (g.kind == SVLGPU_LIN3DHEXA8) ? 6 : 3;
+            g.d_gp = want_gp ? dalloc<double>(m, 2ull * ncomp * g.n * g.ngp) : nullptr;
+            if (g.d_gp) CUDA_OK(cudaMemset(g.d_gp, 0, sizeof(double) * 2ull * ncomp * g.n * g.ngp));
+        }
+    }
+    {
+        // generic nodes and their incidences in ascending element order
+        std::vector<int32_t> gn_of(nN, -1), dof0, ndofv, ptr;
+        for (int n = 0; n < nN; n++)
+            if (!node_done[n]) { gn_of[n] = (int)dof0.size(); dof0.push_back(m->node_ptr[n]); ndofv.push_back(m->node_ndof[n]); }
+        const int ng = (int)dof0.size();
+        ptr.assign(ng + 1, 0);
+        for (int e = 0; e < nE; e++) {
+            if (gset_of[e] < 0) continue;
+            const int npe = kind_npe(m->elem_kind[e]);
+            for (int l = 0; l < npe; l++) { const int g = gn_of[m->elem_conn[8ll * e + l]]; if (g >= 0) ptr[g + 1]++; }
+        }
+        for (int g = 0; g < ng; g++) ptr[g + 1] += ptr[g];
+        std::vector<int64_t> slot(ptr[ng]);
+        std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
+        for (int e = 0; e < nE; e++) {
+            if (gset_of[e] < 0) continue;
+            const GenericSet &gs = m->gsets[gset_of[e]];
+            for (int l = 0; l < gs.npe; l++) {
+                const int g = gn_of[m->elem_conn[8ll * e + l]];
+                if (g >= 0) slot[fill[g]++] = gbase[gset_of[e]] + ((long long)gidx[e] * gs.npe + l) * gs.ndofn;
+            }
+        }
+        m->n_gnodes = ng;
+        m->d_gn_dof0 = dupload(m, dof0); m->d_gn_ndof = dupload(m, ndofv); m->d_gn_ptr = dupload(m, ptr);
+        m->d_gn_slot = dupload(m, slot);
+    }
+    m->d_coords = dupload(m, m->coords);
+    m->d_node_ptr = dupload(m, m->node_ptr);
+    m->d_int_of_total = dupload(m, m->int_of_total);
+    {
+        std::vector<double> mp(8 * m->materials.size() + 8, 0.0);
+        std::vector<int32_t> mk(m->materials.size() + 1, 0);
+        for (size_t i = 0; i < m->materials.size(); i++) { mk[i] = m->materials[i].kind; for (int c = 0; c < 8; c++) mp[8 * i + c] = m->materials[i].p[c]; }
+        m->d_matpar = dupload(m, mp); m->d_matkind = dupload(m, mk);
+    }
+
+    // ---- F. nodal loads ------------------------------------------------------------------
+    {
+        std::map<int32_t, std::vector<std::pair<int32_t, double>>> by_dof;
+        std::vector<double> series;
+        std::vector<int32_t> soff, snt;
+        for (size_t l = 0; l < m->ploads.size(); l++) {
+            const PointLoad &pl = m->ploads[l];
+            soff.push_back((int32_t)series.size()); snt.push_back((int32_t)pl.series.size());
+            series.insert(series.end(), pl.series.begin(), pl.series.end());
+            std::map<int32_t, double> seen;              // "assign" semantics inside one load: Assembler.cpp:330,347
+            for (int node : pl.nodes)
+                for (int c = 0; c < nd && c < m->node_ndof[node]; c++) seen[m->node_ptr[node] + c] = pl.factor * pl.dir[c];
+            for (auto &kv : seen) by_dof[kv.first].push_back({(int32_t)l, kv.second});
+        }
+        std::vector<int32_t> dof, ptr(1, 0), load;
+        std::vector<double> coef;
+        for (auto &kv : by_dof) {
+            dof.push_back(kv.first);
+            for (auto &lc : kv.second) { load.push_back(lc.first); coef.push_back(lc.second); }
+            ptr.push_back((int32_t)load.size());
+        }
+        m->n_ploads = (int)m->ploads.size();
+        m->n_pl_dofs = (int)dof.size();
+        m->d_pl_dof = dupload(m, dof); m->d_pl_ptr = dupload(m, ptr); m->d_pl_load = dupload(m, load);
+        m->d_pl_coef = dupload(m, coef); m->d_pl_series = dupload(m, series);
+        m->d_pl_soff = dupload(m, soff); m->d_pl_nt = dupload(m, snt);
+        m->d_pl_amp = dalloc<double>(m, m->n_ploads + 1);
+        CUDA_OK(cudaMallocHost(&m->h_pl_amp, sizeof(double) * (m->n_ploads + 1)));
+    }
+    // ---- F2. DRM loads: pre-assembled boundary<->exterior stiffness blocks -----------------
+    for (const DrmLoad &dl : m->drms) {
+        DrmDev dd;
+        const int nn = (int)dl.nodes.size();
+        std::unordered_map<int32_t, int32_t> local;
+        for (int i = 0; i < nn; i++) local[dl.nodes[i]] = i;
+        std::map<std::pair<int32_t, int32_t>, std::array<double, 9>> blocks;
+        for (int e : dl.elems) {
+            const ElemClass &ec = classes[elem_cls[e]];
+            if (!ec.linear) { set_error("DRM element with a non-linear material"); return 1; }
+            const int npe = kind_npe(ec.kind), ned = npe * nd;
+            int li[8];
+            for (int l = 0; l < npe; l++) {
+                auto it = local.find(m->elem_conn[8ll * e + l]);
+                if (it == local.end()) { set_error("DRM element node without a DRM field"); return 1; }
+                li[l] = it->second;
+            }
+            for (int r = 0; r < npe; r++)
+                for (int c = 0; c < npe; c++) {
+                    if (dl.ext[li[r]] == dl.ext[li[c]]) continue;       // lin3DHexa8.cpp:704-712
+                    auto &B = blocks[{li[r], li[c]}];
+                    for (int a = 0; a < nd; a++)
+                        for (int b = 0; b < nd; b++) B[a * nd + b] += ec.Ke[(size_t)(nd * r + a) * ned + nd * c + b];
+                }
+        }
+        std::vector<int32_t> rows, ptr(1, 0), col, dof0;
+        std::vector<double> blk;
+        int last = -1;
+        for (auto &kv : blocks) {
+            if (kv.first.first != last) {
+                if (last >= 0) ptr.push_back((int32_t)col.size());
+                last = kv.first.first; rows.push_back(last); dof0.push_back(m->node_ptr[dl.nodes[last]]);
+            }
+            col.push_back(kv.first.second);
+            for (int q = 0; q < nd * nd; q++) blk.push_back(kv.second[q]);
+        }
+        if (last >= 0) ptr.push_back((int32_t)col.size());
+        dd.n_nodes = (int)rows.size(); dd.nt = dl.nt; dd.nf = 3 * nd;
+        dd.d_node_dof0 = dupload(m, dof0); dd.d_row_ptr = dupload(m, ptr); dd.d_col_node = dupload(m, col);
+        dd.d_blk = dupload(m, blk); dd.d_ext = dupload(m, dl.ext);
+        dd.analytic = dl.analytic; dd.factor = dl.factor;
+        if (dl.analytic) {
+            std::vector<double> xyz((size_t)nn * nd);
+            for (int i = 0; i < nn; i++) for (int c = 0; c < nd; c++) xyz[(size_t)i * nd + c] = m->coords[(size_t)nd * dl.nodes[i] + c];
+            dd.d_xyz = dupload(m, xyz);
+            for (int c = 0; c < 3; c++) { dd.dir[c] = dl.dir[c]; dd.pol[c] = dl.pol[c]; dd.xref[c] = dl.xref[c]; }
+            dd.c = dl.c; dd.f0 = dl.f0; dd.t0 = dl.t0; dd.amp = dl.amp;
+        } else {
+            dd.d_field = dupload(m, dl.field);
+        }
+        m->drm_dev.push_back(dd);
+    }
+
+    // ---- G. recorders -------------------------------------------------------------------
+    int maxw = 1;
+    for (Recorder &r : m->recorders) {
+        std::vector<int32_t> dofs;
+        for (int node : r.nodes) for (int c = 0; c < m->node_ndof[node]; c++) dofs.push_back(m->node_ptr[node] + c);
+        r.width = (int)dofs.size(); r.rows = 0;
+        r.d_dofs = dupload(m, dofs);
+        r.d_rows = dalloc<double>(m, (size_t)r.width * std::max(1, r.max_rows));
+        maxw = std::max(maxw, r.width);
+    }
+    CUDA_OK(cudaMallocHost(&m->h_row, sizeof(double) * maxw));
+    m->h_row_len = maxw;
+
+    // ---- H. state ------------------------------------------------------------------------
+    {
+        std::vector<double> U(m->n_int, 0.0), Up(m->n_int, 0.0);
+        for (int t = 0; t < m->n_total; t++) {
+            const int q = m->int_of_total[t];
+            const double u = m->U0.empty() ? 0.0 : m->U0[t], v = m->V0.empty() ? 0.0 : m->V0[t], a = m->A0.empty() ? 0.0 : m->A0[t];
+            U[q] = u;
+            Up[q] = u - dt * v + dt * dt / 2.0 * a;          // CentralDifference.cpp:61
+        }
+        for (int b = 0; b < 3; b++) {
+            m->d_U[b] = dalloc<double>(m, m->n_int);
+            if (!m->d_U[b]) { set_error("out of device memory (state)"); return 1; }
+        }
+        m->cur = 0; m->prev = 1; m->next = 2;
+        CUDA_OK(cudaMemcpy(m->d_U[0], U.data(), sizeof(double) * m->n_int, cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(m->d_U[1], Up.data(), sizeof(double) * m->n_int, cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemset(m->d_U[2], 0, sizeof(double) * m->n_int));
+    }
+    CUDA_OK(cudaDeviceSynchronize());
+    m->finalized = true;
+    return 0;
+}
+
+}  // namespace svl
