@@ -17,7 +17,12 @@ TOL_PLASTIC = 1e-8
 
 
 def rel_err(a, b):
-    scale = np.abs(b).max(axis=0)
+    """max over recorded dofs of max_t|a-b| / max_t|b|.  Dofs whose whole
+    history stays below 1e-3 of the global peak are normalised by that floor instead: they are
+    zero by symmetry or ahead of the wave front, both codes only hold ~1e-19 rounding noise
+    there (and the reference's |f| <= ftol = 1e-12 assembly filter, Assembler.cpp:262, which
+    the device path does not apply, decides which precursors exist at all)."""
+    scale = np.maximum(np.abs(b).max(axis=0), 1e-3 * np.abs(b).max())
     scale[scale == 0] = 1.0
     return (np.abs(a - b).max(axis=0) / scale).max()
 
