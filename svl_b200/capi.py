@@ -136,7 +136,7 @@ class DeviceModel:
             npe = 8 if kind in (1, 3) else 4
             conn = A(m.elem_conn[start:end, :npe], np.int32)
             nattr = {1: 0, 2: 1, 3: 9, 4: 8}[kind]
-            attrs = A(m.elem_attr[start:end, :nattr], np.float64) if nattr else None
+            attrs = A(m.elem_attr[start:end, :nattr], np.float64) if nattr else None  # hex8: none
             if self.L.svlgpu_add_elements(self.h, kind, end - start, _i(conn), _i(A(m.elem_mat[start:end], np.int32)),
                                           _d(attrs), nattr) < 0:
                 raise SvlError(self._err())

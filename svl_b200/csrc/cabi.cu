@@ -121,7 +121,7 @@ int svlgpu_add_elements(svlgpu_model *m, int kind, int n, const int32_t *conn, c
         m->elem_kind.resize(first + n, kind);
         m->elem_conn.resize(8ull * (first + n), 0);
         m->elem_mat.resize(first + n);
-        m->elem_attr.resize(10ull * (first + n), 0.0);
+        if (nattr > 0 || kind == SVLGPU_LIN2DQUAD4 || !m->elem_attr.empty()) m->elem_attr.resize(10ull * (first + n), 0.0);
         for (int e = 0; e < n; e++) {
             for (int l = 0; l < npe; l++) {
                 const int nd = conn[(size_t)e * npe + l];

@@ -100,7 +100,8 @@ struct svlgpu_model {
     std::vector<Constraint> constraints;
     std::vector<svl::Material> materials;
     std::vector<int32_t> elem_kind, elem_conn /*8 per elem*/, elem_mat;
-    std::vector<double> elem_attr /*10 per elem*/, elem_am;
+    std::vector<double> elem_attr /*10 per elem, allocated only once an element carries attributes*/, elem_am;
+    double attr(long long e, int a) const { return elem_attr.empty() ? 0.0 : elem_attr[10 * e + a]; }
     std::vector<svl::PointLoad> ploads;
     std::vector<svl::DrmLoad> drms;
     std::vector<svl::Recorder> recorders;

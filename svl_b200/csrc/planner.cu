@@ -114,7 +114,7 @@ int plan_and_upload(svlgpu_model *m) {
                 for (int c = 0; c < nd; c++) key.push_back(llround((xi[c] - x0[c]) * inv));
             }
             key.push_back(llround(h / (class_tol * 1e3)));        // absolute size (coarser: relative coords carry the shape)
-            if (kind == SVLGPU_LIN2DQUAD4) { int64_t b; std::memcpy(&b, &m->elem_attr[10ll * e], 8); key.push_back(b); }
+            if (kind == SVLGPU_LIN2DQUAD4) { int64_t b; const double thk = m->attr(e, 0); std::memcpy(&b, &thk, 8); key.push_back(b); }
             uint64_t hsh = 1469598103934665603ull;
             for (int64_t v : key) hsh = mix(hsh, (uint64_t)v);
             auto &bucket = table[hsh];
@@ -137,7 +137,7 @@ int plan_and_upload(svlgpu_model *m) {
                     if (ec.linear) { ec.Ke.resize(576); hex8_stiffness(X, iso_from_E_nu(mat.p[0], mat.p[1]), ec.Ke.data()); }
                 } else {
                     double X[4][2], mm[4][4];
-                    const double th = m->elem_attr[10ll * e];
+                    const double th = m->attr(e, 0);
                     for (int i = 0; i < 4; i++) for (int c = 0; c < 2; c++) X[i][c] = m->coords[2ll * cn[i] + c];
                     quad4_mass_nodes(X, th, rho, mm);
                     for (int i = 0; i < 4; i++) { double s = mm[i][i]; for (int j = 0; j < 4; j++) if (j != i) s += mm[i][j]; ec.mnode[i] = s; }
@@ -392,7 +392,7 @@ int plan_and_upload(svlgpu_model *m) {
             const int e = g.elems[q];
             for (int l = 0; l < g.npe; l++) conn[(size_t)q * g.npe + l] = m->elem_conn[8ll * e + l];
             mat[q] = m->elem_mat[e];
-            th[q] = m->elem_attr[10ll * e];
+            th[q] = m->attr(e, 0);
         }
         g.d_conn = dupload(m, conn); g.d_mat = dupload(m, mat); g.d_th = dupload(m, th);
         g.d_fe = m->d_fe_arena + gbase[s];

@@ -189,7 +189,7 @@ def make_box_model(ne, h=1.0, mat=(ELASTIC3DLINEAR, [1.3e7, 0.3, 2000.0]), fix="
     else:
         kz = np.arange(len(conn)) // (nx * ny)
         m.elem_mat = (kz % len(mats)).astype(np.int32)
-    m.elem_attr = np.zeros((len(conn), 10))
+    m.elem_attr = None                      # lin3DHexa8 carries no attributes
     m.blocks = [(0, NX, NY, nz + 1)] if not jitter else []
     if dt is None:
         E, nu, rho = mats[0][1][:3] if mats[0][0] == ELASTIC3DLINEAR else (None, None, None)
@@ -290,7 +290,7 @@ def write_reference_json(m: Model, directory: str, name: str = "Model", combo: s
     for e in range(m.n_elem):
         kind = int(m.elem_kind[e])
         nn = 8 if kind in (LIN3DHEXA8, PML3DHEXA8) else 4
-        at = m.elem_attr[e]
+        at = m.elem_attr[e] if m.elem_attr is not None else np.zeros(10)
         attr = {"material": int(m.elem_mat[e]) + 1, "rule": "GAUSS", "np": nn}
         if kind == LIN2DQUAD4:
             attr["th"] = float(at[0])
@@ -371,3 +371,49 @@ def read_node_recorder(path: str) -> np.ndarray:
         for _ in range(nn):
             f.readline()
         return np.loadtxt(f, ndmin=2)
+
+
+# -------------------------------------------------------------------------------
+# DRM (Method/Builder.py:1010-1073 setDRMDomain; Core/PlaneWave.py:272-318 file layout)
+# -------------------------------------------------------------------------------
+def ricker_uva(tau, f0):
+    """Ricker displacement pulse and its first two time derivatives."""
+    w = math.pi * f0
+    b = (w * tau) ** 2
+    e = np.exp(-b)
+    u = (1.0 - 2.0 * b) * e
+    v = (-6.0 * w * w * tau + 4.0 * w ** 4 * tau ** 3) * e
+    a = (-6.0 * w * w + 24.0 * w ** 4 * tau ** 2 - 8.0 * w ** 6 * tau ** 4) * e
+    return u, v, a
+
+
+def add_drm_box(m: Model, x0, xl, planewave: dict, tabulate_nt: int = 0, factor: float = 1.0) -> Model:
+    """DRM element layer = elements cut by the box |x - x0| <= xl (setDRMDomain); nodes inside the
+    box are 'interior/boundary' (cond 0), outside 'exterior' (cond 1).  planewave = {dir, pol, xref,
+    c, f0, t0, amp}: u(x,t) = amp pol ricker(t - t0 - (x - xref).dir / c).  tabulate_nt > 0 also
+    tabulates the [nnodes, nt, 3 ndim] field exactly as the reference's .drm files hold it."""
+    X = m.coords
+    x0 = np.asarray(x0, float); xl = np.asarray(xl, float)
+    inside = np.all(np.abs(X - x0[None, :]) <= xl[None, :], axis=1)
+    npe = 8 if m.ndim == 3 else 4
+    cnt = inside[m.elem_conn[:, :npe]].sum(axis=1)
+    elems = np.nonzero((cnt > 0) & (cnt < npe))[0].astype(np.int32)
+    nodes = np.unique(m.elem_conn[elems, :npe]).astype(np.int32)
+    ext = (~inside[nodes]).astype(np.uint8)
+    d = DRMLoad(elems=elems, nodes=nodes, exterior=ext, planewave=dict(planewave), factor=factor)
+    if tabulate_nt:
+        pw = planewave
+        dirv = np.asarray(pw["dir"], float); pol = np.asarray(pw["pol"], float); xr = np.asarray(pw["xref"], float)
+        t = np.arange(tabulate_nt) * m.dt
+        s = ((X[nodes] - xr[None, :]) @ dirv) / pw["c"]
+        tau = t[None, :] - pw["t0"] - s[:, None]
+        u, v, a = ricker_uva(tau, pw["f0"])
+        nd = m.ndim
+        fld = np.zeros((len(nodes), tabulate_nt, 3 * nd))
+        for c in range(nd):
+            fld[:, :, c] = pw["amp"] * pol[c] * u
+            fld[:, :, nd + c] = pw["amp"] * pol[c] * v
+            fld[:, :, 2 * nd + c] = pw["amp"] * pol[c] * a
+        d.field = fld
+    m.drm = d
+    return m

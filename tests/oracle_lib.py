@@ -199,7 +199,7 @@ class Oracle:
         s.mat_kind = _i(A([k for k, _ in m.materials], np.int32)); s.mat_par = _d(A(mp, np.float64))
         s.n_elem = m.n_elem
         s.elem_kind = _i(A(m.elem_kind, np.int32)); s.elem_conn = _i(A(m.elem_conn, np.int32))
-        s.elem_mat = _i(A(m.elem_mat, np.int32)); s.elem_attr = _d(A(m.elem_attr, np.float64))
+        s.elem_mat = _i(A(m.elem_mat, np.int32)); s.elem_attr = _d(A(m.elem_attr if m.elem_attr is not None else np.zeros((m.n_elem, 10)), np.float64))
         if m.elem_am is not None:
             s.elem_am = _d(A(m.elem_am, np.float64)); s.elem_ak = _d(A(m.elem_ak, np.float64))
         npl = len(m.point_loads)

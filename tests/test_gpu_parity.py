@@ -157,3 +157,36 @@ def test_step_host_roundtrip(oracle):
     for k in range(1, m.nt):
         d.step_host(k, [m.point_loads[0].series[k]], rec=0, row=row)
         assert np.abs(row - ref[k - 1]).max() <= TOL_LINEAR * np.abs(ref).max()
+
+
+def drm_model(ne=(8, 8, 6), nt=60, tabulate=True):
+    m = M.make_box_model(ne, 1.0, nt=nt, series=None, fix=None)
+    m.point_loads = []
+    nx, ny, nz = ne
+    vs = math.sqrt(1.3e7 / (2 * 1.3) / 2000.0)
+    pw = dict(dir=[0.0, 0.0, 1.0], pol=[1.0, 0.0, 0.0], xref=[0.0, 0.0, 0.0], c=vs, f0=1.0 / (25 * m.dt),
+              t0=30 * m.dt, amp=1e-3)
+    # box whose faces cut the 2nd element layer from the sides / bottom; open at the top
+    M.add_drm_box(m, x0=[nx / 2, ny / 2, nz], xl=[nx / 2 - 1.5, ny / 2 - 1.5, nz - 1.5], planewave=pw,
+                  tabulate_nt=nt if tabulate else 0)
+    m.rec_nodes = np.array([0, m.n_nodes // 2, m.n_nodes - 1, int(m.drm.nodes[3])], dtype=np.int32)
+    return m
+
+
+def test_drm_tabulated_field(oracle):
+    m = drm_model()
+    assert len(m.drm.elems) > 0 and m.drm.exterior.sum() > 0
+    ref, _ = oracle.run(m)
+    assert np.abs(ref).max() > 1e-5
+    out = _device(m).run()[0]
+    assert rel_err(out, ref) < TOL_LINEAR
+    m.blocks = []
+    assert rel_err(_device(m).run()[0], ref) < TOL_LINEAR
+
+
+def test_drm_analytic_planewave_matches_tabulated(oracle):
+    m = drm_model()
+    ref, _ = oracle.run(m)
+    m.drm.field = None                       # device evaluates the Ricker plane wave itself
+    out = _device(m).run()[0]
+    assert rel_err(out, ref) < 1e-9
