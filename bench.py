@@ -209,7 +209,7 @@ def main():
     # ---- roofline of the dominant kernel: per-launch CUDA-event durations (separate pass)
     d.set_kernel_timing(True)
     d.step(k, k + min(K, 20), True); k += min(K, 20)
-    kt = {w: d.kernel_time(w) for w in range(4)}
+    kt = {w: d.kernel_time(w) for w in range(6)}
     d.set_kernel_timing(False)
     peak, peak_src = measured_peaks()
     st_ms, st_n = kt[0]
@@ -258,7 +258,8 @@ def main():
                        "node_classes": c["n_node_classes"], "model_build_s": t_model, "plan_upload_s": t_plan,
                        "wall_s_timed_region": wall},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
-            "kernel_ms": {"stencil": kt[0][0], "gauss_elements": kt[1][0], "gather_nodes": kt[2][0], "loads": kt[3][0]},
+            "kernel_ms": {"stencil_dom": kt[0][0], "stencil_shell_gather": kt[4][0], "gauss_elements": kt[1][0],
+                          "gather_nodes": kt[2][0], "point_loads": kt[3][0], "drm": kt[5][0]},
             "cpu_baseline": cb}
     if rank == 0:
         print(json.dumps(line))

@@ -187,8 +187,8 @@ int svlgpu_get_counters(svlgpu_model *m, svlgpu_counters *out);
  * the launching stream so that bench.py can report the roofline live.          */
 int svlgpu_set_kernel_timing(svlgpu_model *m, int on);
 /* average duration (ms) and launch count of kernel `which` since last reset:
- * 0 = block stencil, 1 = generic element force, 2 = generic node update,
- * 3 = nodal loads, 4 = recorder.  reset!=0 clears after reading.               */
+ * 0 = block stencil (dominant class), 1 = Gauss-point element force, 2 = generic node update,
+ * 3 = point loads, 4 = block stencil (shell gather), 5 = DRM.  reset!=0 clears after reading.              */
 int svlgpu_kernel_time(svlgpu_model *m, int which, double *avg_ms, int64_t *launches, int reset);
 
 /* raw device pointers for zero-copy interop (torch.from_blob / NCCL plumbing):

@@ -36,6 +36,7 @@ svlgpu_model *svlgpu_create(int ndim, int lumped) {
 
 void svlgpu_destroy(svlgpu_model *m) {
     if (!m) return;
+    forget_const_owner(m);
     if (m->finalized || m->stream) {
         cudaSetDevice(m->device);
         if (m->stream) cudaStreamSynchronize(m->stream);
@@ -393,7 +394,7 @@ int svlgpu_set_kernel_timing(svlgpu_model *m, int on) {
     return 0;
 }
 int svlgpu_kernel_time(svlgpu_model *m, int which, double *avg_ms, int64_t *launches, int reset) {
-    REQUIRE(m && which >= 0 && which < 5, "kernel_time: bad arguments");
+    REQUIRE(m && which >= 0 && which < 6, "kernel_time: bad arguments");
     timer_flush(m);
     KernelTimer &t = m->timers[which];
     if (avg_ms) *avg_ms = t.launches ? t.total_ms / t.launches : 0.0;

@@ -41,41 +41,62 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
 }
 
 // ------------------------------------------------------------------------------------------
-// 3-D block stencil
+// 3-D block stencil, dominant node class.
+//
+// A lattice block has one (or a few) node classes that cover almost all nodes (the interior of
+// a homogeneous region).  Their 27 x 3x3 pre-summed coefficient rows live in __constant__
+// memory and are used as constant-bank operands of the DFMAs: no register, no LSU traffic.
+// The kernel computes every node of its box as if it belonged to the dominant class and stores
+// only those that do; the thin shells of other classes are done by k_stencil3_gather.
+//
+// Work decomposition: CTA = 32 (x) x NW*R (y) nodes, marching over kz planes.  Plane kk of U_n
+// is staged in shared memory by cp.async (3-deep ring); each thread owns R consecutive rows and
+// scatters plane kk into the accumulators of output planes kk-1, kk, kk+1 (slots 0,1,2), so
+// every U value is read from shared memory once per (di,b) and each output node is finished
+// when its upper neighbour plane has been consumed.
 // ------------------------------------------------------------------------------------------
-struct Blk3 {
+constexpr int kDomSlots = 4;
+__constant__ double cK[kDomSlots][kTbl3Stride];
+
+struct Dom3 {
     const double *U;      // U_n      (internal dof array)
     const double *Up;     // U_{n-1}
     double *Un;           // U_{n+1}  (mode 0)  or  F_int (mode 1)
     const uint8_t *cls;   // [nx*ny*nz]
-    const double *tbl;    // [ncls][276]
     long long dof0;       // internal dof of lattice node (0,0,0)
-    int ncls, nx, ny, nz;
+    int nx, ny, nz;
+    int bi0, bj0, bk0, bk1;   // box origin and z end (exclusive) of the nodes of this class
     int tiles_x, tiles_y, kz;
+    int dom;              // class id to store
     int mode;
 };
 
-template <int NW>
-__global__ void __launch_bounds__(NW * 32, 1) k_stencil3(const Blk3 p) {
-    constexpr int R = 4;                 // lattice rows (y) per thread
+// structural zero of the stencil of a rectangular cell with isotropic material: the a != b
+// block entry vanishes unless the neighbour offset is non-zero along both axes a and b
+__host__ __device__ constexpr bool stencil_nz(int di, int b, int dj, int s, int a) {
+    if (a == b) return true;
+    const int d0 = di - 1, d1 = dj - 1, d2 = 1 - s;
+    const int da = (a == 0) ? d0 : (a == 1) ? d1 : d2;
+    const int db = (b == 0) ? d0 : (b == 1) ? d1 : d2;
+    return da != 0 && db != 0;
+}
+
+template <int NW, int R, int SLOT, bool ORTHO>
+__global__ void __launch_bounds__(NW * 32, (NW <= 4) ? 3 : 1) k_stencil3_dom(const Dom3 p) {
     constexpr int TY = NW * R;           // tile rows
     constexpr int TYH = TY + 2;          // + halo
     constexpr int ROWP = 36;             // 34 columns (+halo) padded to a 16 B multiple
     constexpr int PLANE = 3 * TYH * ROWP;
     constexpr int ROWD = 102;            // doubles per tile row in global memory (34 nodes x 3)
-    extern __shared__ __align__(16) double sm[];
-    double *tbl = sm;
-    double *pl = sm + ((p.ncls * kTbl3Stride + 1) & ~1);
+    extern __shared__ __align__(16) double pl[];
 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int item = blockIdx.x;
     const int txi = item % p.tiles_x; item /= p.tiles_x;
     const int tyi = item % p.tiles_y; item /= p.tiles_y;
-    const int i0 = txi * 32, j0 = tyi * TY;
-    const int k0 = item * p.kz, k1 = min(k0 + p.kz, p.nz);
+    const int i0 = p.bi0 + txi * 32, j0 = p.bj0 + tyi * TY;
+    const int k0 = p.bk0 + item * p.kz, k1 = min(k0 + p.kz, p.bk1);
     const int gi = i0 + lane, gjb = j0 + w * R;
-
-    for (int t = threadIdx.x; t < p.ncls * kTbl3Stride; t += NW * 32) tbl[t] = p.tbl[t];
 
     auto load_plane = [&](int k, double *buf) {
         const bool kin = (k >= 0) && (k < p.nz);
@@ -89,145 +110,87 @@ __global__ void __launch_bounds__(NW * 32, 1) k_stencil3(const Blk3 p) {
         }
     };
 
+    double *ups = pl + 3 * PLANE + (w * 32 + lane) * (R * 3);   // this thread's U_{n-1} slots
+
     double acc[3][R][3];
-    double ucen[R][3];
-    int cl[3][R];
+    double ucen[R][3];               // U_n of this thread's nodes on the previous plane
 #pragma unroll
     for (int s = 0; s < 3; s++)
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            cl[s][r] = 0;
+        for (int r = 0; r < R; r++)
 #pragma unroll
-            for (int a = 0; a < 3; a++) acc[s][r][a] = 0.0;
-        }
-#pragma unroll
-    for (int r = 0; r < R; r++)
-#pragma unroll
-        for (int a = 0; a < 3; a++) ucen[r][a] = 0.0;
+            for (int a = 0; a < 3; a++) { acc[s][r][a] = 0.0; ucen[r][a] = 0.0; }
 
-    auto node_cls = [&](int r, int k) -> int {
-        const int y = gjb + r;
-        if (gi >= p.nx || y >= p.ny || k < k0 || k >= k1) return 0;
-        return p.cls[gi + (long long)p.nx * (y + (long long)p.ny * k)];
+    // class of this thread's nodes, fetched one plane ahead of its use
+    auto my_cls = [&](int r, int k) -> bool {
+        if (gi >= p.nx || gjb + r >= p.ny || k < k0 || k >= k1) return false;
+        return p.cls[gi + (long long)p.nx * (gjb + r + (long long)p.ny * k)] == p.dom;
     };
-    // classes of output planes kk-1 (slot 0), kk (slot 1), kk+1 (slot 2) for kk = k0-1
+    bool mine[R], mine_nx[R];
 #pragma unroll
-    for (int r = 0; r < R; r++) cl[2][r] = node_cls(r, k0);
+    for (int r = 0; r < R; r++) { mine[r] = false; mine_nx[r] = false; }   // planes k0-2, k0-1: not ours
 
     load_plane(k0 - 1, pl);
     cp_async_commit();
 
     int idx = 0;
     for (int kk = k0 - 1; kk <= k1; kk++, idx++) {
-        double *buf = pl + (idx % 3) * PLANE;
+        const double *buf = pl + (idx % 3) * PLANE;
         if (kk + 1 <= k1) load_plane(kk + 1, pl + ((idx + 1) % 3) * PLANE);
-        cp_async_commit();
-        // U_{n-1} of the nodes completed in this iteration (plane kk-1)
-        double upv[R][3];
-        const bool fin = (kk - 1 >= k0);
-        if (fin && p.mode == 0) {
+        // U_{n-1} of the nodes finished at the end of this iteration (plane kk-1): own slots only,
+        // so cp.async.wait_group alone orders them (no barrier needed)
+        if (p.mode == 0) {
 #pragma unroll
-            for (int r = 0; r < R; r++) {
-                if (cl[0][r]) {
+            for (int r = 0; r < R; r++)
+                if (mine[r]) {
                     const double *q = p.Up + p.dof0 + 3ll * (gi + (long long)p.nx * (gjb + r + (long long)p.ny * (kk - 1)));
-                    upv[r][0] = q[0]; upv[r][1] = q[1]; upv[r][2] = q[2];
+                    cp_async8(ups + 3 * r + 0, q + 0, true);
+                    cp_async8(ups + 3 * r + 1, q + 1, true);
+                    cp_async8(ups + 3 * r + 2, q + 2, true);
                 }
-            }
         }
+        cp_async_commit();
+        bool mine_n2[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) mine_n2[r] = my_cls(r, kk + 1);
         cp_async_wait<1>();
         __syncthreads();
 
-        const bool any = (cl[0][0] | cl[0][1] | cl[0][2] | cl[0][3] | cl[1][0] | cl[1][1] | cl[1][2] | cl[1][3] |
-                          cl[2][0] | cl[2][1] | cl[2][2] | cl[2][3]) != 0;
-        const bool uni = (cl[0][0] == cl[0][1]) && (cl[0][0] == cl[0][2]) && (cl[0][0] == cl[0][3]) &&
-                         (cl[1][0] == cl[1][1]) && (cl[1][0] == cl[1][2]) && (cl[1][0] == cl[1][3]) &&
-                         (cl[2][0] == cl[2][1]) && (cl[2][0] == cl[2][2]) && (cl[2][0] == cl[2][3]);
-        if (any) {
-            if (uni) {
-                const double *t0 = tbl + cl[0][0] * kTbl3Stride;
-                const double *t1 = tbl + cl[1][0] * kTbl3Stride;
-                const double *t2 = tbl + cl[2][0] * kTbl3Stride;
-                for (int di = 0; di < 3; di++) {
-                    for (int b = 0; b < 3; b++) {
-                        const double *ub = buf + (b * TYH + w * R) * ROWP + lane + di;
-                        double u[R + 2];
 #pragma unroll
-                        for (int q = 0; q < R + 2; q++) u[q] = ub[q * ROWP];
-                        const int off = (di * 3 + b) * 30;
+        for (int di = 0; di < 3; di++) {
 #pragma unroll
-                        for (int dj = 0; dj < 3; dj++) {
-                            // slot s accumulates plane-offset dk = 1 - s (coefficient sub-block s)
-                            const double2 *c0 = reinterpret_cast<const double2 *>(t0 + off + dj * 10);
-                            const double2 *c1 = reinterpret_cast<const double2 *>(t1 + off + dj * 10);
-                            const double2 *c2 = reinterpret_cast<const double2 *>(t2 + off + dj * 10);
-                            const double2 a01 = c0[0], a2x = c0[1];          // slot 0: entries 0,1,2
-                            const double2 bx0 = c1[1], b12 = c1[2];          // slot 1: entries 3,4,5
-                            const double2 g01 = c2[3], g2x = c2[4];          // slot 2: entries 6,7,8
+            for (int b = 0; b < 3; b++) {
+                const double *ub = buf + (b * TYH + w * R) * ROWP + lane + di;
+                double u[R + 2];
 #pragma unroll
-                            for (int r = 0; r < R; r++) {
-                                const double uv = u[r + dj];
-                                acc[0][r][0] = fma(a01.x, uv, acc[0][r][0]);
-                                acc[0][r][1] = fma(a01.y, uv, acc[0][r][1]);
-                                acc[0][r][2] = fma(a2x.x, uv, acc[0][r][2]);
-                                acc[1][r][0] = fma(bx0.y, uv, acc[1][r][0]);
-                                acc[1][r][1] = fma(b12.x, uv, acc[1][r][1]);
-                                acc[1][r][2] = fma(b12.y, uv, acc[1][r][2]);
-                                acc[2][r][0] = fma(g01.x, uv, acc[2][r][0]);
-                                acc[2][r][1] = fma(g01.y, uv, acc[2][r][1]);
-                                acc[2][r][2] = fma(g2x.x, uv, acc[2][r][2]);
-                            }
+                for (int q = 0; q < R + 2; q++) u[q] = ub[q * ROWP];
+#pragma unroll
+                for (int dj = 0; dj < 3; dj++)
+#pragma unroll
+                    for (int s = 0; s < 3; s++)
+#pragma unroll
+                        for (int a = 0; a < 3; a++) {
+                            if (ORTHO && !stencil_nz(di, b, dj, s, a)) continue;
+                            const double c = cK[SLOT][((di * 3 + b) * 3 + dj) * 10 + s * 3 + a];
+#pragma unroll
+                            for (int r = 0; r < R; r++) acc[s][r][a] = fma(c, u[r + dj], acc[s][r][a]);
                         }
-                    }
-                }
-            } else {
-                // rows of this thread belong to different node classes (lattice faces / edges)
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    if ((cl[0][r] | cl[1][r] | cl[2][r]) == 0) continue;
-                    const double *t0 = tbl + cl[0][r] * kTbl3Stride;
-                    const double *t1 = tbl + cl[1][r] * kTbl3Stride;
-                    const double *t2 = tbl + cl[2][r] * kTbl3Stride;
-                    for (int di = 0; di < 3; di++) {
-                        for (int b = 0; b < 3; b++) {
-                            const double *ub = buf + (b * TYH + w * R + r) * ROWP + lane + di;
-                            const int off = (di * 3 + b) * 30;
-#pragma unroll
-                            for (int dj = 0; dj < 3; dj++) {
-                                const double uv = ub[dj * ROWP];
-                                const double *c0 = t0 + off + dj * 10, *c1 = t1 + off + dj * 10, *c2 = t2 + off + dj * 10;
-                                acc[0][r][0] = fma(c0[0], uv, acc[0][r][0]);
-                                acc[0][r][1] = fma(c0[1], uv, acc[0][r][1]);
-                                acc[0][r][2] = fma(c0[2], uv, acc[0][r][2]);
-                                acc[1][r][0] = fma(c1[3], uv, acc[1][r][0]);
-                                acc[1][r][1] = fma(c1[4], uv, acc[1][r][1]);
-                                acc[1][r][2] = fma(c1[5], uv, acc[1][r][2]);
-                                acc[2][r][0] = fma(c2[6], uv, acc[2][r][0]);
-                                acc[2][r][1] = fma(c2[7], uv, acc[2][r][1]);
-                                acc[2][r][2] = fma(c2[8], uv, acc[2][r][2]);
-                            }
-                        }
-                    }
-                }
             }
         }
         // ---- nodes of plane kk-1 are complete: CentralDifference update (CentralDifference.cpp:138-148)
-        if (fin) {
+        cp_async_wait<0>();
 #pragma unroll
-            for (int r = 0; r < R; r++) {
-                const int c = cl[0][r];
-                if (c) {
-                    const long long d0 = p.dof0 + 3ll * (gi + (long long)p.nx * (gjb + r + (long long)p.ny * (kk - 1)));
+        for (int r = 0; r < R; r++) {
+            if (mine[r]) {
+                const long long d0 = p.dof0 + 3ll * (gi + (long long)p.nx * (gjb + r + (long long)p.ny * (kk - 1)));
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
                     if (p.mode == 0) {
-                        const double *tc = tbl + c * kTbl3Stride + 270;
-#pragma unroll
-                        for (int a = 0; a < 3; a++) {
-                            const double un = ucen[r][a];
-                            const double du = (tc[3 + a] * (un - upv[r][a]) - acc[0][r][a]) * tc[a];
-                            p.Un[d0 + a] = un + du;
-                        }
+                        const double un = ucen[r][a];
+                        const double du = (cK[SLOT][273 + a] * (un - ups[3 * r + a]) - acc[0][r][a]) * cK[SLOT][270 + a];
+                        p.Un[d0 + a] = un + du;
                     } else {
-#pragma unroll
-                        for (int a = 0; a < 3; a++) p.Un[d0 + a] = acc[0][r][a];
+                        p.Un[d0 + a] = acc[0][r][a];
                     }
                 }
             }
@@ -240,14 +203,68 @@ __global__ void __launch_bounds__(NW * 32, 1) k_stencil3(const Blk3 p) {
                 acc[0][r][a] = acc[1][r][a];
                 acc[1][r][a] = acc[2][r][a];
                 acc[2][r][a] = 0.0;
+                // plane kk stays in the ring until the prefetch of iteration kk+2, i.e. past the next barrier
                 ucen[r][a] = buf[(a * TYH + w * R + r + 1) * ROWP + lane + 1];
             }
-            cl[0][r] = cl[1][r];
-            cl[1][r] = cl[2][r];
-            cl[2][r] = node_cls(r, kk + 2);
+            mine[r] = mine_nx[r];
+            mine_nx[r] = mine_n2[r];
         }
     }
-    cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------
+// 3-D block stencil, remaining node classes (faces / edges / corners / material interfaces):
+// one thread per listed node, coefficients from the per-class table (warp-uniform -> L1
+// broadcast because the list is sorted by class), neighbours through L1/L2.
+// ------------------------------------------------------------------------------------------
+struct Gat3 {
+    const double *U, *Up;
+    double *Un;
+    const uint8_t *cls;
+    const double *tbl;      // [ncls][276]
+    const int32_t *list;    // lattice-local node ids, sorted by class
+    long long dof0;
+    int n, nx, ny, nz, mode;
+};
+__global__ void __launch_bounds__(128) k_stencil3_gather(const Gat3 p) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.n) return;
+    const int q = p.list[t];
+    const int i = q % p.nx, j = (q / p.nx) % p.ny, k = q / (p.nx * p.ny);
+    const double *T = p.tbl + (size_t)p.cls[q] * kTbl3Stride;
+    double F[3] = {0.0, 0.0, 0.0};
+    for (int s = 0; s < 3; s++) {
+        const int z = k + 1 - s;                  // slot s <-> neighbour plane offset dk = 1 - s
+        if (z < 0 || z >= p.nz) continue;
+        for (int dj = 0; dj < 3; dj++) {
+            const int y = j + dj - 1;
+            if (y < 0 || y >= p.ny) continue;
+#pragma unroll
+            for (int di = 0; di < 3; di++) {
+                const int x = i + di - 1;
+                if (x < 0 || x >= p.nx) continue;
+                const double *u = p.U + p.dof0 + 3ll * (x + (long long)p.nx * (y + (long long)p.ny * z));
+#pragma unroll
+                for (int b = 0; b < 3; b++) {
+                    const double ub = u[b];
+                    const double *c = T + ((di * 3 + b) * 3 + dj) * 10 + s * 3;
+                    F[0] = fma(c[0], ub, F[0]);
+                    F[1] = fma(c[1], ub, F[1]);
+                    F[2] = fma(c[2], ub, F[2]);
+                }
+            }
+        }
+    }
+    const long long d0 = p.dof0 + 3ll * q;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        if (p.mode == 0) {
+            const double un = p.U[d0 + a];
+            p.Un[d0 + a] = un + (T[273 + a] * (un - p.Up[d0 + a]) - F[a]) * T[270 + a];
+        } else {
+            p.Un[d0 + a] = F[a];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -557,12 +574,13 @@ __global__ void k_nodal_loads(const PLArgs a) {
 // boundary<->exterior stiffness blocks times the (sign-flipped for exterior) incident field.
 // ------------------------------------------------------------------------------------------
 struct DrmArgs {
-    int n, ndim, nt, nf, k, analytic;
-    const int32_t *dof0, *ptr, *col;
+    int n, nn, ndim, nt, nf, k, analytic;
+    const int32_t *dof0, *ptr, *col, *bid;
     const uint8_t *ext;
-    const double *blk;            // [entries][ndim*ndim]
-    const double *field;          // [n][nt][nf]
-    const double *xyz;            // [n][ndim]
+    const double *dict;           // unique K blocks [nblk][ndim*ndim]
+    const double *field;          // [nn][nt][nf]
+    const double *xyz;            // [nn][ndim]
+    double *uo;                   // [nn][ndim] incident displacement of this step (sign-flipped if exterior)
     double dir[3], pol[3], xref[3], c, f0, t0, amp, factor, dt;
     const double *kinv;
     double *Un;
@@ -572,29 +590,35 @@ __device__ __forceinline__ double ricker_disp(double tau, double f0) {
     const double b = (M_PI * f0 * tau) * (M_PI * f0 * tau);
     return (1.0 - 2.0 * b) * exp(-b);
 }
+// incident field of step k at every DRM node (Node::GetDomainReductionMotion, Node.cpp:222-225;
+// exterior rows negated as in Driver.hpp:1714-1716)
+__global__ void k_drm_field(const DrmArgs a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.nn) return;
+    const double sgn = a.ext[t] ? -1.0 : 1.0;
+    if (a.analytic) {
+        double s = 0.0;
+        for (int c = 0; c < a.ndim; c++) s += (a.xyz[(long long)t * a.ndim + c] - a.xref[c]) * a.dir[c];
+        const double val = a.amp * ricker_disp(a.k * a.dt - a.t0 - s / a.c, a.f0);
+        for (int c = 0; c < a.ndim; c++) a.uo[(long long)t * a.ndim + c] = sgn * (val * a.pol[c]);
+    } else {
+        const double *row = a.field + ((long long)t * a.nt + a.k) * a.nf;
+        for (int c = 0; c < a.ndim; c++) a.uo[(long long)t * a.ndim + c] = sgn * row[c];
+    }
+}
 __global__ void k_drm(const DrmArgs a) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.n) return;
     double F[3] = {0, 0, 0};
+    const int nd = a.ndim;
     for (int q = a.ptr[t]; q < a.ptr[t + 1]; q++) {
-        const int cn = a.col[q];
-        double u[3] = {0, 0, 0};
-        if (a.analytic) {
-            double s = 0.0;
-            for (int c = 0; c < a.ndim; c++) s += (a.xyz[(long long)cn * a.ndim + c] - a.xref[c]) * a.dir[c];
-            const double val = a.amp * ricker_disp(a.k * a.dt - a.t0 - s / a.c, a.f0);
-            for (int c = 0; c < a.ndim; c++) u[c] = val * a.pol[c];
-        } else {
-            const double *row = a.field + ((long long)cn * a.nt + a.k) * a.nf;
-            for (int c = 0; c < a.ndim; c++) u[c] = row[c];
-        }
-        const double sgn = a.ext[cn] ? -1.0 : 1.0;          // Driver.hpp:1714-1716
-        const double *B = a.blk + (long long)q * a.ndim * a.ndim;
-        for (int r = 0; r < a.ndim; r++)
-            for (int c = 0; c < a.ndim; c++) F[r] += B[r * a.ndim + c] * (sgn * u[c]);
+        const double *u = a.uo + (long long)a.col[q] * nd;
+        const double *B = a.dict + (long long)a.bid[q] * nd * nd;
+        for (int r = 0; r < nd; r++)
+            for (int c = 0; c < nd; c++) F[r] += B[r * nd + c] * u[c];
     }
     const int d0 = a.dof0[t];
-    for (int r = 0; r < a.ndim; r++) a.Un[d0 + r] += a.kinv[d0 + r] * (a.factor * F[r]);
+    for (int r = 0; r < nd; r++) a.Un[d0 + r] += a.kinv[d0 + r] * (a.factor * F[r]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -650,7 +674,7 @@ static void timer_end(svlgpu_model *m, int which) {
     t.launches++;
 }
 void timer_flush(svlgpu_model *m) {
-    for (int i = 0; i < 5; i++) {
+    for (int i = 0; i < 6; i++) {
         KernelTimer &t = m->timers[i];
         if (t.pending) {
             float ms = 0;
@@ -661,18 +685,35 @@ void timer_flush(svlgpu_model *m) {
     }
 }
 
-static int stencil_nw() {
-    static int nw = 0;
-    if (!nw) {
-        const char *s = getenv("SVLGPU_STENCIL_NW");
-        nw = s ? atoi(s) : 8;
-        if (nw != 4 && nw != 8) nw = 8;
-    }
-    return nw;
+size_t stencil3_smem(int nw, int r) { return (3ull * 3 * (nw * r + 2) * 36 + (size_t)nw * 32 * r * 3) * sizeof(double); }
+
+static svlgpu_model *g_const_owner = nullptr;
+static int upload_dom_tables(svlgpu_model *m) {
+    if (g_const_owner == m) return 0;
+    CUDA_OK(cudaDeviceSynchronize());          // another model's kernels may still read the tables
+    for (auto &b : m->blocks)
+        for (auto &d : b.doms)
+            CUDA_OK(cudaMemcpyToSymbolAsync(cK, d.tbl, sizeof(double) * kTbl3Stride, sizeof(double) * kTbl3Stride * d.slot,
+                                            cudaMemcpyHostToDevice, m->stream));
+    g_const_owner = m;
+    return 0;
 }
-size_t stencil3_smem(int ncls, int nw) {
-    const size_t tbl = ((size_t)ncls * kTbl3Stride + 1) & ~(size_t)1;
-    return (tbl + 3ull * 3 * (nw * 4 + 2) * 36) * sizeof(double);
+void forget_const_owner(svlgpu_model *m) { if (g_const_owner == m) g_const_owner = nullptr; }
+
+template <int NW, int R, int SLOT>
+static void launch_dom_so(const Dom3 &p, bool ortho, unsigned grid, cudaStream_t st) {
+    const size_t sm = stencil3_smem(NW, R);
+    if (ortho) k_stencil3_dom<NW, R, SLOT, true><<<grid, NW * 32, sm, st>>>(p);
+    else k_stencil3_dom<NW, R, SLOT, false><<<grid, NW * 32, sm, st>>>(p);
+}
+template <int NW, int R>
+static void launch_dom(const Dom3 &p, int slot, bool ortho, unsigned grid, cudaStream_t st) {
+    switch (slot) {
+    case 0: launch_dom_so<NW, R, 0>(p, ortho, grid, st); break;
+    case 1: launch_dom_so<NW, R, 1>(p, ortho, grid, st); break;
+    case 2: launch_dom_so<NW, R, 2>(p, ortho, grid, st); break;
+    default: launch_dom_so<NW, R, 3>(p, ortho, grid, st); break;
+    }
 }
 
 static int launch_force_update(svlgpu_model *m, const double *U, const double *Up, double *Un, int mode, int commit) {
@@ -695,26 +736,41 @@ static int launch_force_update(svlgpu_model *m, const double *U, const double *U
         m->total_launches++;
     }
     // 2. lattice blocks
+    if (upload_dom_tables(m)) return 1;
     for (auto &b : m->blocks) {
         if (!b.n_stencil_nodes) continue;
-        timer_begin(m, 0);
         if (b.ndim == 3) {
-            Blk3 p;
-            p.U = U; p.Up = Up; p.Un = Un; p.cls = b.d_cls; p.tbl = b.d_tbl; p.dof0 = b.dof0;
-            p.ncls = b.ncls; p.nx = b.nx; p.ny = b.ny; p.nz = b.nz;
-            p.tiles_x = b.tiles_x; p.tiles_y = b.tiles_y; p.kz = b.kz; p.mode = mode;
-            const unsigned grid = (unsigned)(b.tiles_x * b.tiles_y * b.zchunks);
-            if (b.nw == 4) k_stencil3<4><<<grid, 128, stencil3_smem(b.ncls, 4), m->stream>>>(p);
-            else k_stencil3<8><<<grid, 256, stencil3_smem(b.ncls, 8), m->stream>>>(p);
+            for (auto &d : b.doms) {
+                Dom3 p;
+                p.U = U; p.Up = Up; p.Un = Un; p.cls = b.d_cls; p.dof0 = b.dof0;
+                p.nx = b.nx; p.ny = b.ny; p.nz = b.nz;
+                p.bi0 = d.bi0; p.bj0 = d.bj0; p.bk0 = d.bk0; p.bk1 = d.bk1;
+                p.tiles_x = d.tiles_x; p.tiles_y = d.tiles_y; p.kz = d.kz; p.dom = d.cls; p.mode = mode;
+                const unsigned grid = (unsigned)(d.tiles_x * d.tiles_y * d.zchunks);
+                timer_begin(m, 0);
+                launch_dom<kDomNW, kDomR>(p, d.slot, d.ortho, grid, m->stream);
+                timer_end(m, 0);
+                m->total_launches++;
+            }
+            if (b.n_glist) {
+                Gat3 p;
+                p.U = U; p.Up = Up; p.Un = Un; p.cls = b.d_cls; p.tbl = b.d_tbl; p.list = b.d_glist;
+                p.dof0 = b.dof0; p.n = b.n_glist; p.nx = b.nx; p.ny = b.ny; p.nz = b.nz; p.mode = mode;
+                timer_begin(m, 4);
+                k_stencil3_gather<<<(b.n_glist + 127) / 128, 128, 0, m->stream>>>(p);
+                timer_end(m, 4);
+                m->total_launches++;
+            }
         } else {
             Blk2 p;
             p.U = U; p.Up = Up; p.Un = Un; p.cls = b.d_cls; p.tbl = b.d_tbl; p.dof0 = b.dof0;
             p.ncls = b.ncls; p.nx = b.nx; p.ny = b.ny; p.mode = mode;
             dim3 grid((b.nx + 63) / 64, (b.ny + 3) / 4);
+            timer_begin(m, 0);
             k_stencil2<<<grid, 256, (size_t)b.ncls * kTbl2Stride * sizeof(double), m->stream>>>(p);
+            timer_end(m, 0);
+            m->total_launches++;
         }
-        timer_end(m, 0);
-        m->total_launches++;
     }
     // 3. generic nodes
     if (m->n_gnodes) {
@@ -759,16 +815,19 @@ int run_steps(svlgpu_model *m, int k0, int k1, const double *dev_amp) {
             m->total_launches++;
         }
         for (auto &d : m->drm_dev) {
+            if (!d.analytic && k >= d.nt) continue;
             DrmArgs a;
-            a.n = d.n_nodes; a.ndim = m->ndim; a.nt = d.nt; a.nf = d.nf; a.k = k; a.analytic = d.analytic;
-            a.dof0 = d.d_node_dof0; a.ptr = d.d_row_ptr; a.col = d.d_col_node; a.ext = d.d_ext;
-            a.blk = d.d_blk; a.field = d.d_field; a.xyz = d.d_xyz;
+            a.n = d.n_nodes; a.nn = d.n_all; a.ndim = m->ndim; a.nt = d.nt; a.nf = d.nf; a.k = k; a.analytic = d.analytic;
+            a.dof0 = d.d_node_dof0; a.ptr = d.d_row_ptr; a.col = d.d_col_node; a.bid = d.d_blk_id; a.ext = d.d_ext;
+            a.dict = d.d_blk; a.field = d.d_field; a.xyz = d.d_xyz; a.uo = d.d_uo;
             for (int c = 0; c < 3; c++) { a.dir[c] = d.dir[c]; a.pol[c] = d.pol[c]; a.xref[c] = d.xref[c]; }
             a.c = d.c; a.f0 = d.f0; a.t0 = d.t0; a.amp = d.amp; a.factor = d.factor; a.dt = m->dt;
             a.kinv = m->d_kinv; a.Un = Un;
-            if (!d.analytic && k >= d.nt) continue;
+            timer_begin(m, 5);
+            k_drm_field<<<(a.nn + 127) / 128, 128, 0, m->stream>>>(a);
             k_drm<<<(a.n + 127) / 128, 128, 0, m->stream>>>(a);
-            m->total_launches++;
+            timer_end(m, 5);
+            m->total_launches += 2;
         }
         record_rows(m);
         // rotate: U_{n-1} <- U_n <- U_{n+1}
@@ -810,12 +869,16 @@ int gather_state(svlgpu_model *m, int field, const int32_t *dofs, int n, double 
     return 0;
 }
 
+template <int SLOT> static int cfg_slot() {
+    CUDA_OK(cudaFuncSetAttribute(k_stencil3_dom<kDomNW, kDomR, SLOT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stencil3_smem(kDomNW, kDomR)));
+    CUDA_OK(cudaFuncSetAttribute(k_stencil3_dom<kDomNW, kDomR, SLOT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stencil3_smem(kDomNW, kDomR)));
+    return 0;
+}
 int configure_kernels() {
-    CUDA_OK(cudaFuncSetAttribute(k_stencil3<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(k_stencil3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (cfg_slot<0>() || cfg_slot<1>() || cfg_slot<2>() || cfg_slot<3>()) return 1;
     CUDA_OK(cudaFuncSetAttribute(k_stencil2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     return 0;
 }
-int default_stencil_nw() { return stencil_nw(); }
+bool stencil_entry_nonzero(int di, int b, int dj, int s, int a) { return stencil_nz(di, b, dj, s, a); }
 
 }  // namespace svl

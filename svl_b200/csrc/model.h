@@ -48,8 +48,21 @@ struct Block {
     uint8_t *d_cls = nullptr;        // [nx*ny*nz] class per node
     double *d_tbl = nullptr;         // [ncls][stride]
     int64_t n_stencil_nodes = 0;
-    int tiles_x = 0, tiles_y = 0, zchunks = 0, kz = 0, nw = 8;   // launch geometry
+    // 3-D: dominant classes (constant-bank coefficient kernel) + list of the remaining stencil nodes
+    struct Dom {
+        int cls = 0, slot = 0;
+        bool ortho = false;
+        int bi0 = 0, bj0 = 0, bk0 = 0, bk1 = 0;      // box of the nodes of this class
+        int tiles_x = 0, tiles_y = 0, zchunks = 0, kz = 0;
+        double tbl[276];
+        int64_t nodes = 0;
+    };
+    std::vector<Dom> doms;
+    int32_t *d_glist = nullptr;
+    int n_glist = 0;
 };
+constexpr int kDomNW = 4;            // warps per CTA of k_stencil3_dom
+constexpr int kDomR = 4;             // lattice rows per thread
 
 // per-class coefficient table strides (doubles)
 constexpr int kTbl3Stride = 276;     // 27 x (9 coefficients + 1 pad) + kinv[3] + km[3]
@@ -75,13 +88,15 @@ struct GenericSet {                  // Gauss-point path: elements of one kind
 };
 
 struct DrmDev {
-    int n_nodes = 0, nt = 0, nf = 0;
-    int32_t *d_node_dof0 = nullptr;  // internal dof0 of each DRM node
+    int n_nodes = 0, n_all = 0, nt = 0, nf = 0;   // rows with entries / all DRM nodes
+    int32_t *d_node_dof0 = nullptr;  // internal dof0 of each row node
     uint8_t *d_ext = nullptr;
     double *d_field = nullptr;       // [nnodes][nt][nf]
     int32_t *d_row_ptr = nullptr;    // CSR over DRM nodes
     int32_t *d_col_node = nullptr;   // local DRM node index of the column node
-    double *d_blk = nullptr;         // [entries][ndim*ndim] K block (row node <- col node)
+    int32_t *d_blk_id = nullptr;     // per entry: index into the dictionary of unique K blocks
+    double *d_blk = nullptr;         // [nblk][ndim*ndim] unique K blocks (row node <- col node)
+    double *d_uo = nullptr;          // [n_all][ndim] incident displacement of the current step
     double *d_xyz = nullptr;         // node coordinates (analytic mode)
     bool analytic = false;
     double dir[3], pol[3], xref[3], c = 0, f0 = 0, t0 = 0, amp = 0, factor = 1;
@@ -149,7 +164,7 @@ struct svlgpu_model {
     int64_t total_launches = 0, launches_per_step = 0;
     int64_t n_block_nodes = 0, n_generic_elements = 0, n_elem_classes = 0, n_node_classes = 0;
     bool kernel_timing = false;
-    svl::KernelTimer timers[5];
+    svl::KernelTimer timers[6];
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_step_ms = 0.0;
     int steps_done = 0;
@@ -163,6 +178,7 @@ int compute_internal_force(svlgpu_model *m, double *F_host);
 int gather_state(svlgpu_model *m, int field, const int32_t *dofs, int n, double *out);
 void timer_flush(svlgpu_model *m);
 int configure_kernels();
-int default_stencil_nw();
-size_t stencil3_smem(int ncls, int nw);
+size_t stencil3_smem(int nw, int r);
+bool stencil_entry_nonzero(int di, int b, int dj, int s, int a);
+void forget_const_owner(svlgpu_model *m);
 }  // namespace svl

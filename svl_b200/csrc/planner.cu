@@ -188,7 +188,6 @@ int plan_and_upload(svlgpu_model *m) {
 
     // ---- D. lattice blocks -> node classes ------------------------------------------------
     std::vector<uint8_t> node_done(nN, 0);           // 1 = advanced by a block-stencil kernel
-    const int nw = default_stencil_nw();
     for (const BlockHint &h : m->hints) {
         const bool is3 = (nd == 3);
         if (h.nx < 2 || h.ny < 2 || (is3 && h.nz < 2) || h.node0 < 0) continue;
@@ -268,11 +267,7 @@ int plan_and_upload(svlgpu_model *m) {
         if (sigs.empty()) continue;
         // keep the most populous classes that fit in shared memory / uint8
         const int stride = is3 ? kTbl3Stride : kTbl2Stride;
-        int cap = 255;
-        if (is3) {
-            const long long budget = 227 * 1024 - (long long)stencil3_smem(0, nw) - 1024;
-            cap = (int)std::min<long long>(255, budget / (stride * 8) - 1);
-        }
+        const int cap = 255;                          // uint8 class ids
         std::vector<int> order(sigs.size());
         for (size_t c = 0; c < order.size(); c++) order[c] = (int)c;
         std::sort(order.begin(), order.end(), [&](int a, int b) { return pop[a] != pop[b] ? pop[a] > pop[b] : a < b; });
@@ -328,22 +323,59 @@ int plan_and_upload(svlgpu_model *m) {
         if (!nst) continue;
         Block b;
         b.node0 = h.node0; b.nx = NX; b.ny = NY; b.nz = NZ; b.ndim = nd; b.dof0 = m->node_ptr[h.node0];
-        b.ncls = ncls; b.n_stencil_nodes = nst; b.nw = nw;
+        b.ncls = ncls; b.n_stencil_nodes = nst;
         b.d_cls = dupload(m, cls);
         b.d_tbl = dupload(m, tbl);
         if (is3) {
-            const int TY = nw * 4;
-            b.tiles_x = (NX + 31) / 32; b.tiles_y = (NY + TY - 1) / TY;
+            // dominant classes -> constant-bank kernel over their bounding box; the rest -> gather list
+            std::vector<long long> cpop(ncls, 0);
+            for (long long q = 0; q < nbn; q++) cpop[cls[q]]++;
+            std::vector<int> cand;
+            for (int c = 1; c < ncls; c++) if (cpop[c] >= std::max<long long>(2048, nbn / 50)) cand.push_back(c);
+            std::sort(cand.begin(), cand.end(), [&](int a, int c2) { return cpop[a] > cpop[c2]; });
+            if (cand.size() > 4) cand.resize(4);
+            std::vector<uint8_t> is_dom(ncls, 0);
             const char *kzs = getenv("SVLGPU_STENCIL_KZ");
-            int kz = kzs ? atoi(kzs) : 0;
-            if (kz <= 0) {
-                // enough work items for >= 4 waves of 148 SMs, but keep the 2 halo planes <= ~10 %
-                const long long tiles = (long long)b.tiles_x * b.tiles_y;
-                long long want = (4 * 148 + tiles - 1) / tiles;
-                kz = (int)std::max<long long>(1, (NZ + want - 1) / want);
-                kz = std::max(kz, std::min(NZ, 16));
+            for (size_t z = 0; z < cand.size(); z++) {
+                const int c = cand[z];
+                Block::Dom d;
+                d.cls = c; d.slot = (int)z; d.nodes = cpop[c];
+                std::memcpy(d.tbl, &tbl[(size_t)c * stride], sizeof(double) * stride);
+                double mx = 0;
+                for (int q = 0; q < 270; q++) mx = std::max(mx, std::fabs(d.tbl[q]));
+                d.ortho = true;
+                for (int di = 0; di < 3; di++) for (int bb = 0; bb < 3; bb++) for (int dj = 0; dj < 3; dj++)
+                    for (int s = 0; s < 3; s++) for (int a = 0; a < 3; a++)
+                        if (!stencil_entry_nonzero(di, bb, dj, s, a) &&
+                            std::fabs(d.tbl[((di * 3 + bb) * 3 + dj) * 10 + s * 3 + a]) > 1e-13 * mx) d.ortho = false;
+                if (getenv("SVLGPU_NO_ORTHO")) d.ortho = false;
+                int lo[3] = {NX, NY, NZ}, hi[3] = {-1, -1, -1};
+                for (long long q = 0; q < nbn; q++) {
+                    if (cls[q] != c) continue;
+                    const int ijk[3] = {(int)(q % NX), (int)((q / NX) % NY), (int)(q / ((long long)NX * NY))};
+                    for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], ijk[a]); hi[a] = std::max(hi[a], ijk[a]); }
+                }
+                d.bi0 = lo[0]; d.bj0 = lo[1]; d.bk0 = lo[2]; d.bk1 = hi[2] + 1;
+                const int TY = kDomNW * kDomR;
+                d.tiles_x = (hi[0] - lo[0] + 1 + 31) / 32; d.tiles_y = (hi[1] - lo[1] + 1 + TY - 1) / TY;
+                const int nzb = d.bk1 - d.bk0;
+                int kz = kzs ? atoi(kzs) : 0;
+                if (kz <= 0) {
+                    // >= ~6 waves of 148 SMs x 3 CTAs, but keep the 2 halo planes per chunk <= ~8 %
+                    const long long tiles = (long long)d.tiles_x * d.tiles_y;
+                    const long long want = std::max<long long>(1, (6 * 444 + tiles - 1) / tiles);
+                    kz = (int)std::max<long long>(24, (nzb + want - 1) / want);
+                }
+                d.kz = std::min(kz, nzb); d.zchunks = (nzb + d.kz - 1) / d.kz;
+                is_dom[c] = 1;
+                b.doms.push_back(d);
             }
-            b.kz = std::min(kz, NZ); b.zchunks = (NZ + b.kz - 1) / b.kz;
+            // remaining stencil nodes, sorted by class (stable in node order)
+            std::vector<int32_t> glist;
+            for (long long q = 0; q < nbn; q++) if (cls[q] && !is_dom[cls[q]]) glist.push_back((int32_t)q);
+            std::stable_sort(glist.begin(), glist.end(), [&](int32_t a, int32_t c2) { return cls[a] < cls[c2]; });
+            b.n_glist = (int)glist.size();
+            b.d_glist = dupload(m, glist);
         }
         m->n_block_nodes += nst;
         m->n_node_classes += ncls - 1;
@@ -498,8 +530,9 @@ int plan_and_upload(svlgpu_model *m) {
                         for (int b = 0; b < nd; b++) B[a * nd + b] += ec.Ke[(size_t)(nd * r + a) * ned + nd * c + b];
                 }
         }
-        std::vector<int32_t> rows, ptr(1, 0), col, dof0;
-        std::vector<double> blk;
+        std::vector<int32_t> rows, ptr(1, 0), col, dof0, bid;
+        std::vector<double> dict;
+        std::map<std::array<double, 9>, int32_t> uniq;            // K blocks repeat: store each once
         int last = -1;
         for (auto &kv : blocks) {
             if (kv.first.first != last) {
@@ -507,12 +540,18 @@ int plan_and_upload(svlgpu_model *m) {
                 last = kv.first.first; rows.push_back(last); dof0.push_back(m->node_ptr[dl.nodes[last]]);
             }
             col.push_back(kv.first.second);
-            for (int q = 0; q < nd * nd; q++) blk.push_back(kv.second[q]);
+            auto it = uniq.find(kv.second);
+            if (it == uniq.end()) {
+                it = uniq.emplace(kv.second, (int32_t)uniq.size()).first;
+                for (int q = 0; q < nd * nd; q++) dict.push_back(kv.second[q]);
+            }
+            bid.push_back(it->second);
         }
         if (last >= 0) ptr.push_back((int32_t)col.size());
-        dd.n_nodes = (int)rows.size(); dd.nt = dl.nt; dd.nf = 3 * nd;
+        dd.n_nodes = (int)rows.size(); dd.n_all = nn; dd.nt = dl.nt; dd.nf = 3 * nd;
         dd.d_node_dof0 = dupload(m, dof0); dd.d_row_ptr = dupload(m, ptr); dd.d_col_node = dupload(m, col);
-        dd.d_blk = dupload(m, blk); dd.d_ext = dupload(m, dl.ext);
+        dd.d_blk_id = dupload(m, bid); dd.d_blk = dupload(m, dict); dd.d_ext = dupload(m, dl.ext);
+        dd.d_uo = dalloc<double>(m, (size_t)nn * nd);
         dd.analytic = dl.analytic; dd.factor = dl.factor;
         if (dl.analytic) {
             std::vector<double> xyz((size_t)nn * nd);
