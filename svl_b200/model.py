@@ -417,3 +417,176 @@ def add_drm_box(m: Model, x0, xl, planewave: dict, tabulate_nt: int = 0, factor:
         d.field = fld
     m.drm = d
     return m
+
+
+# -------------------------------------------------------------------------------
+# PML layer (Method/Builder.py:804-1008 setPMLattributes / setPMLDomain, :581-667 mergeDomain)
+# -------------------------------------------------------------------------------
+def make_pml_model(ne, npml, h=1.0, soil=None, pml_mat=None, pml_n=2.0, pml_R=1.0e-5, th=1.0,
+                   dt=None, nt=0, load_dir=None, series=None, rec_nodes=None) -> Model:
+    """Soil box (2-D: nx x ny quads, 3-D: nx x ny x nz hexes, free top) wrapped by a `npml`-cell PML
+    layer on its sides and bottom, assembled the way the reference pre-processor does it:
+      * the PML is its own mesh with 5 (2-D) / 9 (3-D) dofs per node; its interface nodes duplicate
+        the soil boundary nodes and are tied to them by EQUAL constraints on the displacement dofs
+        (mergeDomain, Builder.py:653-666); soil nodes / elements are numbered first;
+      * per-element PML attributes x0 / npml from the element centroid (setPMLattributes);
+      * displacement dofs of the outer PML boundary are restrained (B10 / J13 model scripts).
+    Element attrs: 3-D [n, L, R, x0(3), npml(3)], 2-D [th, n, L, R, x0(2), npml(2)]."""
+    nd = len(ne)
+    is3 = nd == 3
+    if soil is None:
+        soil = (ELASTIC3DLINEAR if is3 else ELASTIC2DPLANESTRAIN, [1.3e7, 0.3, 2000.0])
+    if pml_mat is None:
+        pml_mat = (soil[0], list(soil[1]))
+    p = int(npml)
+    L = p * h
+    n_cells = list(ne)
+    top = nd - 1                                   # vertical axis: last one, free surface at its max
+    # ---- soil lattice -------------------------------------------------------------
+    if is3:
+        nx, ny, nz = ne
+        Xs = box_nodes(ne, [0, 0, 0], [nx * h, 0, 0], [0, ny * h, 0], [0, 0, nz * h])
+        conn_s = box_hex8_conn(ne)
+    else:
+        nx, ny = ne
+        Xs = area_nodes(ne, [0, 0], [nx * h, 0], [0, ny * h])
+        conn_s = area_quad4_conn(ne)
+    ns = Xs.shape[0]
+    sdim = [c + 1 for c in n_cells]
+
+    def soil_id(ijk):
+        idx = ijk[0] + sdim[0] * ijk[1]
+        if is3:
+            idx = idx + sdim[0] * sdim[1] * ijk[2]
+        return idx
+
+    # ---- extended lattice: indices lo..hi per axis ----------------------------------
+    lo = [-p] * nd
+    hi = [c + p for c in n_cells]
+    hi[top] = n_cells[top]
+    ext_dim = [hi[a] - lo[a] + 1 for a in range(nd)]
+    grids = np.meshgrid(*[np.arange(lo[a], hi[a] + 1) for a in reversed(range(nd))], indexing="ij")
+    IJK = np.stack([g.ravel() for g in reversed(grids)], axis=1)          # x fastest
+    strictly_in = np.ones(len(IJK), dtype=bool)
+    on_or_in = np.ones(len(IJK), dtype=bool)
+    for a in range(nd):
+        if a == top:
+            strictly_in &= IJK[:, a] > 0
+            on_or_in &= IJK[:, a] >= 0
+        else:
+            strictly_in &= (IJK[:, a] > 0) & (IJK[:, a] < n_cells[a])
+            on_or_in &= (IJK[:, a] >= 0) & (IJK[:, a] <= n_cells[a])
+    is_pml_node = ~strictly_in
+    pml_index = -np.ones(len(IJK), dtype=np.int64)
+    pml_index[is_pml_node] = ns + np.arange(int(is_pml_node.sum()))
+    Xp = IJK[is_pml_node].astype(np.float64) * h
+    npn = Xp.shape[0]
+
+    def ext_id(ijk):
+        idx = (ijk[0] - lo[0]) + ext_dim[0] * (ijk[1] - lo[1])
+        if is3:
+            idx = idx + ext_dim[0] * ext_dim[1] * (ijk[2] - lo[2])
+        return idx
+
+    # ---- PML cells ----------------------------------------------------------------------
+    cgr = np.meshgrid(*[np.arange(lo[a], hi[a]) for a in reversed(range(nd))], indexing="ij")
+    C = np.stack([g.ravel() for g in reversed(cgr)], axis=1)
+    cell_in = np.ones(len(C), dtype=bool)
+    for a in range(nd):
+        if a == top:
+            cell_in &= C[:, a] >= 0
+        else:
+            cell_in &= (C[:, a] >= 0) & (C[:, a] < n_cells[a])
+    Cp = C[~cell_in]
+    offs = kHexPos if is3 else kQuadPos
+    conn_p = np.zeros((len(Cp), 8), dtype=np.int32)
+    for l, o in enumerate(offs):
+        q = Cp + np.asarray(o)[None, :]
+        conn_p[:, l] = pml_index[ext_id(q.T)]
+    assert (conn_p[:, :len(offs)] >= ns).all()
+    # attributes (setPMLattributes): centroid classification against the soil box
+    cen = (Cp + 0.5) * h
+    x0c = np.array([n_cells[a] * h / 2.0 for a in range(nd)]); x0c[top] = n_cells[top] * h
+    xl = np.array([n_cells[a] * h / 2.0 for a in range(nd)]); xl[top] = n_cells[top] * h
+    attr_p = np.zeros((len(Cp), 10))
+    for e in range(len(Cp)):
+        sgn = np.zeros(nd)
+        for a in range(nd):
+            if a == top:
+                sgn[a] = -1.0 if cen[e, a] < x0c[a] - xl[a] else 0.0
+            else:
+                sgn[a] = -1.0 if cen[e, a] < x0c[a] - xl[a] else (1.0 if cen[e, a] > x0c[a] + xl[a] else 0.0)
+        cnt = int(np.count_nonzero(sgn))
+        npv = sgn / math.sqrt(cnt)
+        x0e = x0c + sgn * xl
+        if sgn[top] == 0.0:
+            x0e[top] = x0c[top] - xl[top] / 2.0
+        if is3:
+            attr_p[e, :3] = [pml_n, L, pml_R]; attr_p[e, 3:6] = x0e; attr_p[e, 6:9] = npv
+        else:
+            attr_p[e, :4] = [th, pml_n, L, pml_R]; attr_p[e, 4:6] = x0e; attr_p[e, 6:8] = npv
+
+    # ---- assemble the model ----------------------------------------------------------------
+    m = Model(ndim=nd)
+    m.coords = np.vstack([Xs, Xp])
+    ndof_p = 9 if is3 else 5
+    m.node_ndof = np.concatenate([np.full(ns, nd), np.full(npn, ndof_p)]).astype(np.int32)
+    fd = [np.zeros(nd, dtype=np.int32) for _ in range(ns)] + [np.zeros(ndof_p, dtype=np.int32) for _ in range(npn)]
+    pIJK = IJK[is_pml_node]
+    iface = on_or_in[is_pml_node]
+    outer = np.zeros(npn, dtype=bool)
+    for a in range(nd):
+        outer |= pIJK[:, a] == lo[a]
+        if a != top:
+            outer |= pIJK[:, a] == hi[a]
+    tag = -1
+    cons = []
+    ptr_p = ns * nd + ndof_p * np.arange(npn)
+    for q in range(npn):
+        if outer[q]:
+            fd[ns + q][:nd] = -1
+        elif iface[q]:
+            master = soil_id(pIJK[q])
+            for k in range(nd):
+                tag -= 1
+                fd[ns + q][k] = tag
+                cons.append((tag, int(ptr_p[q] + k), (int(master), k)))
+    m.freedof = fd
+    m.materials = [soil, pml_mat]
+    conn = np.zeros((len(conn_s) + len(conn_p), 8), dtype=np.int32)
+    conn[:len(conn_s), :conn_s.shape[1]] = conn_s
+    conn[len(conn_s):] = conn_p
+    m.elem_conn = conn
+    m.elem_kind = np.concatenate([np.full(len(conn_s), LIN3DHEXA8 if is3 else LIN2DQUAD4),
+                                  np.full(len(conn_p), PML3DHEXA8 if is3 else PML2DQUAD4)]).astype(np.int32)
+    m.elem_mat = np.concatenate([np.zeros(len(conn_s)), np.ones(len(conn_p))]).astype(np.int32)
+    m.elem_attr = np.zeros((len(conn), 10))
+    if not is3:
+        m.elem_attr[:len(conn_s), 0] = th
+    m.elem_attr[len(conn_s):] = attr_p
+    m.blocks = [(0, sdim[0], sdim[1], sdim[2] if is3 else 1)]
+    if dt is None:
+        E, nu, rho = soil[1][:3]
+        lam = E * nu / ((1 + nu) * (1 - 2 * nu)); mu = E / (2 * (1 + nu))
+        dt = 0.5 * h / math.sqrt((lam + 2 * mu) / rho)
+    m.dt, m.nt = dt, nt
+    m.number_dofs()
+    # constraints in the JSON form: slave TOTAL dof <- master FREE dof (SeismoVLAB.py:130-138)
+    m.constraints = [(t, s, [int(m.freedof_flat[m.node_ptr[mn] + k])], [1.0]) for t, s, (mn, k) in cons]
+    ijk_load = [c // 2 for c in n_cells]; ijk_load[top] = n_cells[top]
+    load_node = soil_id(ijk_load)
+    if load_dir is None:
+        load_dir = (0.0, 0.0, 1.0e4) if is3 else (0.0, 1.0e4)
+    if series is None and nt > 0:
+        f0 = 1.0 / (20.0 * dt)
+        series = ricker(nt, dt, f0, 1.2 / f0)
+    if series is not None:
+        m.point_loads = [PointLoad(np.array([load_node], dtype=np.int32), np.asarray(load_dir, float),
+                                   np.asarray(series, float))]
+    m.rec_nodes = np.asarray(rec_nodes if rec_nodes is not None else [load_node], dtype=np.int32)
+    m.n_soil_nodes, m.n_soil_elems = ns, len(conn_s)
+    return m
+
+
+kHexPos = [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]
+kQuadPos = [(0, 0), (1, 0), (1, 1), (0, 1)]

@@ -1,0 +1,126 @@
+"""Named parity cases shared by the golden-vector generator (tests/golden/make_golden.py), the CPU
+tests of the oracle and the GPU parity tests.  Every case is a deterministic svl_b200.model.Model;
+the golden file of a case holds the NODE-recorder history the UNMODIFIED reference executable
+(oracle/_ref/SeismoVLAB.exe) wrote for exactly this model (CentralDifference + Linear + Eigen)."""
+import hashlib
+import math
+
+import numpy as np
+
+from svl_b200 import model as M
+
+SOIL = [1.3e7, 0.3, 2000.0]            # fixture J05
+PMLMAT = [5.0e7, 0.25, 2000.0]         # fixtures J12 / B10
+PML_DT = 0.25 / math.sqrt(1.3e7 * 0.7 / (1.3 * 0.4) / 2000.0)   # 0.25 h / Vp(SOIL), h = 1
+J2 = [2.9e7, 2.0e7, 2000.0, 1.0e7, 0.5, 1.0e4]   # fixture F07 (beta 0.5 as in SURVEY App. B.5)
+
+
+def kat444():
+    """SURVEY.md App. B.5 CentralDifference known-answer case."""
+    nt = 51
+    series = np.array([math.sin(2 * math.pi * k / 20) for k in range(nt)])
+    return M.make_box_model((4, 4, 4), 1.0, dt=0.004, nt=nt, load_node=112, load_dir=(2e3, -1e3, 1e4),
+                            series=series, rec_nodes=[62, 112, 124])
+
+
+def hex8_distorted():
+    nt = 41
+    series = np.array([math.sin(2 * math.pi * k / 16) for k in range(nt)])
+    return M.make_box_model((3, 4, 5), 0.8, dt=0.003, nt=nt, load_dir=(1e3, 2e3, -5e3), series=series,
+                            rec_nodes=[30, 77, 119], jitter=0.15)
+
+
+def hex8_layered_rayleigh():
+    mats = [(M.ELASTIC3DLINEAR, SOIL), (M.ELASTIC3DLINEAR, [5.0e7, 0.25, 2200.0])]
+    m = M.make_box_model((4, 3, 6), 1.0, nt=60, layers=mats, rec_nodes=[22, 70, 139])
+    m.elem_am = np.where(m.elem_mat == 0, 0.8, 0.3)
+    m.elem_ak = np.zeros(m.n_elem)
+    return m
+
+
+def quad4_area():
+    return M.make_area_model((8, 6), 0.5, th=0.8, nt=70, rec_nodes=[12, 40, 58])
+
+
+def quad4_distorted():
+    return M.make_area_model((6, 5), 0.5, th=1.3, nt=50, rec_nodes=[10, 27, 41], jitter=0.2)
+
+
+def j2_column():
+    return M.make_box_model((2, 2, 6), 1.0, mat=(M.PLASTIC3DJ2, J2), nt=100, load_dir=(3.0e5, 0.0, 1.0e5),
+                            rec_nodes=[40, 58, 62])
+
+
+def drm_box():
+    nt = 50
+    ne = (6, 6, 5)
+    m = M.make_box_model(ne, 1.0, nt=nt, series=None, fix=None)
+    m.point_loads = []
+    nx, ny, nz = ne
+    vs = math.sqrt(SOIL[0] / (2 * (1 + SOIL[1])) / SOIL[2])
+    pw = dict(dir=[0.0, 0.0, 1.0], pol=[1.0, 0.0, 0.0], xref=[0.0, 0.0, 0.0], c=vs, f0=1.0 / (25 * m.dt),
+              t0=30 * m.dt, amp=1e-3)
+    M.add_drm_box(m, x0=[nx / 2, ny / 2, nz], xl=[nx / 2 - 1.5, ny / 2 - 1.5, nz - 1.5], planewave=pw,
+                  tabulate_nt=nt)
+    m.rec_nodes = np.array([0, m.n_nodes // 2, m.n_nodes - 1, int(m.drm.nodes[3])], dtype=np.int32)
+    return m
+
+
+def drm_area():
+    nt = 50
+    ne = (8, 6)
+    m = M.make_area_model(ne, 1.0, nt=nt, series=None, fix=None)
+    m.point_loads = []
+    nx, ny = ne
+    vs = math.sqrt(SOIL[0] / (2 * (1 + SOIL[1])) / SOIL[2])
+    pw = dict(dir=[0.0, 1.0], pol=[1.0, 0.0], xref=[0.0, 0.0], c=vs, f0=1.0 / (25 * m.dt), t0=30 * m.dt, amp=1e-3)
+    M.add_drm_box(m, x0=[nx / 2, ny], xl=[nx / 2 - 1.5, ny - 1.5], planewave=pw, tabulate_nt=nt)
+    m.rec_nodes = np.array([0, m.n_nodes // 2, m.n_nodes - 1, int(m.drm.nodes[2])], dtype=np.int32)
+    return m
+
+
+def pml2d():
+    # dt = 0.25 h / Vp: the reference's CentralDifference + PML pair (G term dropped) grows
+    # slowly at the usual 0.5 h / Vp; the parity window stays in the stable regime
+    m = M.make_pml_model((6, 5), 3, 1.0, soil=(M.ELASTIC2DPLANESTRAIN, SOIL), nt=120, dt=PML_DT)
+    ns = m.n_soil_nodes
+    m.rec_nodes = np.array([0, 17, int(m.point_loads[0].nodes[0]), ns + 5, ns + 40], dtype=np.int32)
+    return m
+
+
+def pml3d():
+    m = M.make_pml_model((3, 3, 3), 2, 1.0, soil=(M.ELASTIC3DLINEAR, SOIL), nt=80, dt=PML_DT)
+    ns = m.n_soil_nodes
+    m.rec_nodes = np.array([5, int(m.point_loads[0].nodes[0]), ns + 7, ns + 100], dtype=np.int32)
+    return m
+
+
+CASES = {f.__name__: f for f in (kat444, hex8_distorted, hex8_layered_rayleigh, quad4_area, quad4_distorted,
+                                 j2_column, drm_box, drm_area, pml2d, pml3d)}
+# tolerance of |oracle - reference| and |device - oracle| per case (max_t|d| / max_t|ref| per dof)
+TOL = {name: 1e-10 for name in CASES}
+TOL["j2_column"] = 1e-8        # plastic: looser bound (BASELINE.json north_star), stated in DESIGN.md
+TOL["pml2d"] = 1e-8            # PML: Keff is not diagonal -> iterative block solve, see DESIGN.md
+TOL["pml3d"] = 1e-8
+
+
+def fingerprint(m) -> str:
+    """Hash of the model inputs, stored beside each golden history so that drift of a generator is
+    detected instead of silently comparing different models."""
+    h = hashlib.sha256()
+    for a in (m.coords, m.elem_conn, m.elem_kind, m.elem_mat, m.freedof_flat, m.node_ndof):
+        h.update(np.ascontiguousarray(a).tobytes())
+    h.update(repr((m.dt, m.nt, [(k, list(map(float, p))) for k, p in m.materials])).encode())
+    for pl in m.point_loads:
+        h.update(np.ascontiguousarray(pl.series).tobytes())
+    return h.hexdigest()[:16]
+
+
+def rel_err(a, b):
+    """max over recorded dofs of max_t|a-b| / max_t|b|.  Dofs whose whole history stays
+    below 1e-3 of the global peak are normalised by that floor instead (zero by symmetry / ahead of the
+    wave front: both sides only hold rounding noise there, and the reference's |f| <= ftol assembly filter,
+    Assembler.cpp:262, decides which precursors exist at all)."""
+    scale = np.maximum(np.abs(b).max(axis=0), 1e-3 * np.abs(b).max())
+    scale[scale == 0] = 1.0
+    return (np.abs(a - b).max(axis=0) / scale).max()

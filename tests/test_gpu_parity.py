@@ -190,3 +190,24 @@ def test_drm_analytic_planewave_matches_tabulated(oracle):
     m.drm.field = None                       # device evaluates the Ricker plane wave itself
     out = _device(m).run()[0]
     assert rel_err(out, ref) < 1e-9
+
+
+# ---- device vs the golden histories written by the reference executable (tests/golden/) ----------
+import os
+
+import cases
+
+DEVICE_CASES = [n for n in cases.CASES]
+
+
+@pytest.mark.parametrize("name", DEVICE_CASES)
+def test_device_matches_reference_golden(oracle, name):
+    m = cases.CASES[name]()
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"{name}.npz"))
+    assert str(g["fingerprint"]) == cases.fingerprint(m)
+    d = _device(m)
+    out = d.run()[0]
+    assert d.counters()["total_launches"] > 0
+    assert cases.rel_err(out, g["disp"]) < cases.TOL[name]
+    ref, _ = oracle.run(m)
+    assert cases.rel_err(out, ref) < cases.TOL[name]

@@ -1,0 +1,201 @@
+"""CPU suite (-m "not gpu"): pins the oracle (oracle/svl_oracle.c) against
+  (a) the golden NODE-recorder histories written by the UNMODIFIED reference executable
+      (tests/golden/<case>.npz, generator tests/golden/make_golden.py),
+  (b) element / material vectors produced by the reference's own classes (tests/golden/element_kat.npz),
+  (c) the known answers of SURVEY.md App. B.5,
+and checks the C-ABI library without touching a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cases
+from oracle_lib import RefProbe
+from svl_b200 import model as M
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def gold(name):
+    return np.load(os.path.join(GOLD, f"{name}.npz"))
+
+
+@pytest.fixture(scope="module")
+def kat():
+    return gold("element_kat")
+
+
+# ---- (a) whole-analysis histories --------------------------------------------------------------
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_oracle_history_matches_reference_executable(oracle, name):
+    m = cases.CASES[name]()
+    g = gold(name)
+    assert str(g["fingerprint"]) == cases.fingerprint(m), "case generator drifted: regenerate tests/golden"
+    out, _ = oracle.run(m)
+    assert out.shape == g["disp"].shape
+    assert np.abs(g["disp"]).max() > 0
+    assert cases.rel_err(out, g["disp"]) < cases.TOL[name]
+
+
+def test_oracle_vel_accel_match_reference_executable(oracle):
+    m = cases.kat444()
+    g = gold("kat444")
+    for f, key in ((1, "vel"), (2, "accel")):
+        out, _ = oracle.run(m, field=f)
+        assert cases.rel_err(out, g[key]) < 1e-9
+
+
+def test_survey_b5_central_difference_known_answer(oracle):
+    out, _ = oracle.run(cases.kat444())
+    assert abs(out[0, 3] - 9.888543819998318e-06) < 1e-19
+    assert np.allclose(out[24], [1.305711949530492e-06, -6.528559747652594e-07, -1.540661613904458e-04,
+                                 5.382280138183359e-04, -2.691140069091679e-04, 2.370556193531373e-03,
+                                 1.165693300755441e-04, -1.614276542374741e-04, -2.752663997074770e-05],
+                       rtol=1e-10, atol=1e-18)
+    assert np.allclose(out[49, 3:6], [2.280569168526373e-04, -1.140284584263187e-04, 1.169099120176147e-03],
+                       rtol=1e-10, atol=0)
+
+
+# ---- (b) element / material level -----------------------------------------------------------------
+def test_hex8_element_vectors(oracle, kat):
+    E, nu, rho = cases.SOIL
+    f = oracle.hex8_elastic_force(kat["hex_X"], kat["hex_U"], E, nu)
+    assert np.abs(f - kat["hex_f"]).max() < 1e-12 * np.abs(kat["hex_f"]).max()
+    assert np.abs(oracle.hex8_stiffness(kat["hex_X"], E, nu) - kat["hex_K"]).max() < 1e-12 * np.abs(kat["hex_K"]).max()
+    assert np.abs(oracle.hex8_mass(kat["hex_X"], rho, True) - kat["hex_Mlumped"]).max() < 1e-10
+    assert np.abs(oracle.hex8_mass(kat["hex_X"], rho, False) - kat["hex_Mcons"]).max() < 1e-10
+    cube = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
+    U7 = np.zeros((8, 3)); U7[6] = [1e-3, 2e-3, -1e-3]
+    f7 = oracle.hex8_elastic_force(cube, U7, E, nu)
+    assert np.abs(f7 - kat["hex_unit_f"]).max() < 1e-9
+    # SURVEY App. B.5 literal values (first / last entries) and lumped mass 250
+    assert abs(f7[0] + 1.284722222222221e+03) < 1e-9 and abs(f7[23] - 5.555555555555557e+02) < 1e-9
+    assert np.allclose(np.diag(oracle.hex8_mass(cube, rho, True)), 250.0, rtol=1e-13)
+
+
+def test_quad4_element_vectors(oracle, kat):
+    E, nu, rho = cases.SOIL
+    th = float(kat["quad_th"])
+    f = oracle.quad4_elastic_force(kat["quad_X"], kat["quad_U"], th, E, nu)
+    assert np.abs(f - kat["quad_f"]).max() < 1e-12 * np.abs(kat["quad_f"]).max()
+    assert np.abs(oracle.quad4_stiffness(kat["quad_X"], th, E, nu) - kat["quad_K"]).max() < 1e-12 * np.abs(kat["quad_K"]).max()
+    assert np.abs(oracle.quad4_mass(kat["quad_X"], th, rho, True) - kat["quad_Mlumped"]).max() < 1e-10
+    sq = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], float)
+    U3 = np.zeros((4, 2)); U3[2] = [1e-3, -2e-3]
+    f3 = oracle.quad4_elastic_force(sq, U3, 1.0, E, nu)
+    assert np.allclose(f3, [2.5e3, 4.375e3, 0.0, 9.375e3, 1.25e3, -1.1875e4, -3.75e3, -1.875e3], rtol=1e-12, atol=1e-8)
+
+
+def test_j2_return_map_path(oracle, kat):
+    sig, _ = oracle.j2_path(cases.J2, kat["j2_eps"])
+    assert np.abs(sig - kat["j2_sig"]).max() < 1e-11 * np.abs(kat["j2_sig"]).max()
+    # the path must actually yield, otherwise this only tests elasticity
+    K, G = cases.J2[0], cases.J2[1]
+    e = kat["j2_eps"][-1]
+    tr = e[:3].sum()
+    el = np.concatenate([K * tr + 2 * G * (e[:3] - tr / 3), G * e[3:]])
+    assert np.abs(sig[-1] - el).max() > 1e-3 * np.abs(el).max()
+    # SURVEY App. B.5 two-step known answer
+    s2, _ = oracle.j2_path(cases.J2, [[1e-3, -2e-4, 3e-4, 8e-4, -5e-4, 2e-4], [1.5e-3, -1e-4, 2e-4, -4e-4, -9e-4, 6e-4]])
+    assert np.allclose(s2[0], [3.957938883279864e+04, 2.502896788644333e+04, 3.109164328075804e+04,
+                               4.850140315451767e+03, -3.031337697157354e+03, 1.212535078862942e+03], rtol=1e-12)
+    assert np.allclose(s2[1], [5.493074194109687e+04, 4.211363736707318e+04, 4.215562069182994e+04,
+                               -6.324585637498332e+03, -4.356109137812740e+03, 3.476490645298842e+03], rtol=1e-12)
+
+
+def test_pml_matrices(oracle, kat):
+    E, nu, rho = cases.PMLMAT
+    for tag in ("face", "corner"):
+        got = dict(zip("MCKG", oracle.pml3d(kat[f"pml3_{tag}_X"], E, nu, rho, kat[f"pml3_{tag}_par"])))
+        for k in "MCKG":
+            ref = kat[f"pml3_{tag}_{k}"]
+            scale = max(np.abs(ref).max(), 1e-300)
+            assert np.abs(got[k] - ref).max() <= 1e-12 * scale, (tag, k)
+    got = dict(zip("MCK", oracle.pml2d(kat["pml2_X"], E, nu, rho, kat["pml2_par"])))
+    for k in "MCK":
+        ref = kat[f"pml2_{k}"]
+        assert np.abs(got[k] - ref).max() <= 1e-12 * np.abs(ref).max(), k
+    # SURVEY App. B.5 literal values
+    cube = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
+    Mm, Cc, Kk, Gg = oracle.pml3d(cube, 5e7, 0.25, 2000.0, [2, 10, 1e-5, 0.5, 0.5, 1.0, 0, 0, -1])
+    assert abs(Mm[0, 0] - 7.482028220606291e+01) < 1e-11 and abs(Mm[3, 3] + 7.482028220606293e-10) < 1e-21
+    assert abs(Cc[0, 0] - 1.292470397625685e+02) < 1e-10 and abs(Cc[0, 3] + 5.611521165454719e-02) < 1e-14
+    assert abs(np.linalg.norm(Kk) - 1.155283173875213e+00) < 1e-12 and np.linalg.norm(Gg) == 0.0
+
+
+def test_drm_element_forces(oracle, kat):
+    E, nu, rho = cases.SOIL
+    f = oracle.hex8_drm(kat["hex_X"], E, nu, rho, True, kat["drm_hex_ext"], kat["drm_hex_field"])
+    assert np.abs(f - kat["drm_hex_f"]).max() < 1e-12 * np.abs(kat["drm_hex_f"]).max()
+    f = oracle.quad4_drm(kat["quad_X"], float(kat["quad_th"]), E, nu, rho, True, kat["drm_quad_ext"], kat["drm_quad_field"])
+    assert np.abs(f - kat["drm_quad_f"]).max() < 1e-12 * np.abs(kat["drm_quad_f"]).max()
+
+
+@pytest.mark.skipif(not RefProbe.available(), reason="reference probe only exists in the build container")
+def test_oracle_against_live_reference_classes(oracle):
+    rp = RefProbe()
+    rng = np.random.default_rng(7)
+    cube = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
+    for _ in range(5):
+        X = cube + 0.2 * rng.uniform(-1, 1, (8, 3))
+        U = 1e-3 * rng.uniform(-1, 1, (8, 3))
+        a = oracle.hex8_elastic_force(X, U, *cases.SOIL[:2])
+        b = rp.internal_force(1, X, U, 1, cases.SOIL)
+        assert np.abs(a - b).max() < 1e-12 * np.abs(b).max()
+
+
+# ---- host-side model logic ----------------------------------------------------------------------
+def test_structured_numbering_follows_builder():
+    m = M.make_box_model((1, 1, 3), 1.0)
+    # Builder.py:174-183: a 1x1xk column gives conn [1,2,4,3,5,6,8,7] (1-based)
+    assert list(m.elem_conn[0] + 1) == [1, 2, 4, 3, 5, 6, 8, 7]
+    assert m.n_total == 48 and m.n_free == 36
+
+
+def test_pml_generator_topology():
+    m = M.make_pml_model((4, 3), 2, 1.0)
+    assert m.n_soil_nodes == 20 and (m.elem_kind[:12] == M.LIN2DQUAD4).all() and (m.elem_kind[12:] == M.PML2DQUAD4).all()
+    # every constraint ties a PML displacement dof to the soil dof at the same location
+    for tag, slave, masters, factors in m.constraints:
+        assert tag < -1 and factors == [1.0]
+        node_s = np.searchsorted(m.node_ptr, slave, side="right") - 1
+        free = np.asarray(m.freedof_flat)
+        master_total = int(np.nonzero(free == masters[0])[0][0])
+        node_m = np.searchsorted(m.node_ptr, master_total, side="right") - 1
+        assert node_s >= m.n_soil_nodes > node_m
+        assert np.allclose(m.coords[node_s], m.coords[node_m])
+
+
+# ---- C ABI (no GPU here) --------------------------------------------------------------------------
+def test_cabi_exports_every_declared_symbol():
+    from svl_b200 import capi
+    lib = capi.load_library()
+    hdr = open(os.path.join(os.path.dirname(GOLD), "..", "include", "svlgpu.h")).read()
+    declared = sorted(set(re.findall(r"\b(svlgpu_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 30
+    missing = [n for n in declared if not hasattr(lib, n)]
+    assert not missing, missing
+    assert sorted(capi.EXPORTS) == declared
+
+
+def test_cabi_builder_argument_errors_and_no_cpu_fallback():
+    import ctypes as C
+    from svl_b200 import capi
+    L = capi.load_library()
+    assert not L.svlgpu_create(4, 1)
+    assert b"ndim" in L.svlgpu_last_error()
+    h = L.svlgpu_create(3, 1)
+    assert h
+    assert L.svlgpu_finalize(h, 0.01, 0) != 0           # empty model is refused
+    assert b"empty" in L.svlgpu_last_error()
+    L.svlgpu_destroy(h)
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        m = cases.kat444()
+        with pytest.raises(capi.SvlError, match="no CUDA device|no usable CUDA"):
+            capi.DeviceModel(m)
