@@ -69,23 +69,53 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
-def build_workload(n, nt, rank=0, world=1):
+def build_workload(n, nt, rank=0, world=1, strong=False):
+    """Rank `rank`'s block of the global box: world == 1 -> the whole n^3 mesh; world > 1 -> weak scaling
+    (every rank n^3 elements, global mesh = proc_grid(world) * n) or strong scaling (global n^3 split)."""
     from svl_b200 import model as M
-    ne = (n, n, n)
-    m = M.make_box_model(ne, 1.0, mat=(M.ELASTIC3DLINEAR, MAT), nt=nt, fix="bottom")
-    lam = MAT[0] * MAT[1] / ((1 + MAT[1]) * (1 - 2 * MAT[1])); mu = MAT[0] / (2 * (1 + MAT[1]))
+    from svl_b200 import partition as P
+    grid = P.proc_grid(world)
+    if strong:
+        if any(n % g for g in grid):
+            raise SystemExit(f"--scaling strong needs n divisible by the process grid {grid}")
+        nl = tuple(n // g for g in grid)
+    else:
+        nl = (n, n, n)
+    G = [nl[a] * grid[a] for a in range(3)]                    # global elements per axis
+    if world == 1:
+        m = M.make_box_model(nl, 1.0, mat=(M.ELASTIC3DLINEAR, MAT), nt=nt, fix="bottom")
+        m.halos = {}
+        rpos = (0, 0, 0)
+    else:
+        m = P.local_box(nl, grid, rank, 1.0, mat=(M.ELASTIC3DLINEAR, MAT), nt=nt)
+        rpos = m.grid_pos
+    mu = MAT[0] / (2 * (1 + MAT[1]))
     vs = math.sqrt(mu / MAT[2])
     f0 = vs / (10.0 * 1.0) / 4.0          # >= 10 cells per S wavelength (SURVEY.md 8(d)) with margin
     pw = dict(dir=[0.0, 0.0, 1.0], pol=[1.0, 0.0, 0.0], xref=[0.0, 0.0, 0.0], c=vs, f0=f0, t0=1.2 / f0, amp=1e-3)
-    if n >= 16:
-        M.add_drm_box(m, x0=[n / 2, n / 2, n], xl=[n / 2 - 5.5, n / 2 - 5.5, n - 5.5], planewave=pw)
-    # host-fed Ricker point load at the surface centre (already created by make_box_model)
-    m.point_loads[0].series = 1e4 * M.ricker(nt, m.dt, f0, 1.2 / f0)
-    m.point_loads[0].dir = np.array([0.0, 0.0, 1.0])
-    N1 = n + 1
-    idx = np.linspace(0, N1 - 1, 4).astype(int)
-    rec = [int(i + N1 * j + N1 * N1 * n) for j in idx for i in idx]      # 16 surface nodes
+    if min(G) >= 16:
+        M.add_drm_box(m, x0=[G[0] / 2, G[1] / 2, G[2]], xl=[G[0] / 2 - 5.5, G[1] / 2 - 5.5, G[2] - 5.5], planewave=pw)
+        if len(m.drm.elems) == 0:
+            m.drm = None
+    # host-fed Ricker point load at the centre of the free surface: handed to the lowest rank that holds the node
+    gl = (G[0] // 2, G[1] // 2, G[2])
+    holders = []
+    for r in range(world):
+        rx, ry, rz = r % grid[0], (r // grid[0]) % grid[1], r // (grid[0] * grid[1])
+        if all(rp * nl[a] <= gl[a] <= (rp + 1) * nl[a] for a, rp in enumerate((rx, ry, rz))):
+            holders.append(r)
+    N1 = [c + 1 for c in nl]
+    if rank == holders[0]:
+        li = [gl[a] - rpos[a] * nl[a] for a in range(3)]
+        node = li[0] + N1[0] * li[1] + N1[0] * N1[1] * li[2]
+        m.point_loads = [M.PointLoad(np.array([node], dtype=np.int32), np.array([0.0, 0.0, 1.0]),
+                                     1e4 * M.ricker(nt, m.dt, f0, 1.2 / f0))]
+    else:
+        m.point_loads = []
+    ix = np.linspace(0, N1[0] - 1, 4).astype(int); iy = np.linspace(0, N1[1] - 1, 4).astype(int)
+    rec = [int(i + N1[0] * j + N1[0] * N1[1] * nl[2]) for j in iy for i in ix]      # 16 nodes of the block's top layer
     m.rec_nodes = np.array(rec, dtype=np.int32)
+    m.global_elems_per_axis = G
     return m
 
 
@@ -107,7 +137,7 @@ def cpu_baseline_port(budget_s=12.0):
                       f"with OpenMP over elements on {cores} threads"}
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, emit):
     """Times the UNMODIFIED reference executable (oracle/_ref/SeismoVLAB.exe, built from the reference's
     own sources against oracle/shim) on the host: same element / material / integrator, a bounded
     sample of the mesh.  Falls back to the oracle port when the executable did not travel."""
@@ -122,7 +152,7 @@ def run_reference_arm(args):
                 "config": {"workload": "oracle port (reference executable absent on this box)"},
                 "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "element-updates/s",
                                             "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
     n = args.ref_n
     S = args.ref_steps
@@ -166,45 +196,94 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--n", type=int, default=int(os.environ.get("SVL_BENCH_N", "320")), help="elements per side")
     ap.add_argument("--ref-n", type=int, default=16)
     ap.add_argument("--ref-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = n^3 elements per GPU (default), strong = the n^3 mesh split over the GPUs")
     args = ap.parse_args()
+    # the contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner) go to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
         if rank == 0:
-            run_reference_arm(args)
+            run_reference_arm(args, emit)
         return
 
+    from svl_b200 import capi
     from svl_b200.capi import DeviceModel
     K, W = args.steps, max(args.warmup, 3)
-    nt = 3 * (W + K) + 8
+    nt = 4 * (W + K) + 40
+    dist = None
+    comm = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        comm = (rank, world, bytes(uid.cpu().numpy()))
+
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
     t0 = time.perf_counter()
-    m = build_workload(args.n, nt, rank, world)
+    m = build_workload(args.n, nt, rank, world, strong=(args.scaling == "strong"))
     t_model = time.perf_counter() - t0
     t0 = time.perf_counter()
-    d = DeviceModel(m, device=local_rank, max_rows=nt + 4)
+    d = DeviceModel(m, device=local_rank, max_rows=nt + 4, comm=comm)
     t_plan = time.perf_counter() - t0
     c = d.counters()
+    n_elem_total = int(allsum(m.n_elem))
+    n_dof_total = int(allsum(m.n_total))          # interface dofs counted once per replica
+    amp = m.point_loads[0].series if m.point_loads else None
 
-    # ---- device-resident throughput: K steps in one C-ABI call, CUDA events on the launching stream
+    # ---- device-resident throughput: K steps in one C-ABI call, CUDA events on the launching stream,
+    #      barrier + synchronize on both sides, max over ranks
     k = 1
     d.step(k, k + W, True); k += W
-    sampler = ClockSampler(local_rank); sampler.start()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
     w0 = time.perf_counter()
     d.step(k, k + K, True); k += K
+    barrier()
     wall = time.perf_counter() - w0
-    ms = d.counters()["last_step_ms"]
-    sampler.stop_flag = True; sampler.join(timeout=2)
-    value = m.n_elem * K / (ms * 1e-3)
-    launches = d.counters()["launches_per_step"] * K
+    ms = allmax(d.counters()["last_step_ms"])
+    value = n_elem_total * K / (ms * 1e-3)
+    launches = allsum(d.counters()["launches_per_step"] * K)
 
     # ---- roofline of the dominant kernel: per-launch CUDA-event durations (separate pass)
     d.set_kernel_timing(True)
@@ -215,7 +294,7 @@ def main():
     st_ms, st_n = kt[0]
     ach = HEX8_BYTES * c["n_block_nodes"] / (st_ms * 1e-3) / 1e9 if st_n else None
     own_bytes = 3 * 8 * 3 + 1           # U_n, U_{n-1} reads + U_{n+1} write + 1 class byte per node
-    roof = {"bound": "hbm", "kernel": "k_stencil3 (block-stencil force + CentralDifference update)",
+    roof = {"bound": "hbm", "kernel": "k_stencil3_dom (block-stencil force + CentralDifference update, rank 0)",
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None, "traffic": None,
             "peak_source": peak_src, "avg_launch_ms": st_ms, "launches_timed": st_n,
             "algorithmic_bytes_per_element_update": HEX8_BYTES,
@@ -226,18 +305,22 @@ def main():
 
     # ---- end to end through the per-step C-ABI call with HOST buffers
     row = np.zeros(3 * len(m.rec_nodes))
-    amp = m.point_loads[0].series
     for _ in range(3):
-        d.step_host(k, [amp[k]], rec=0, row=row); k += 1
+        d.step_host(k, [amp[k]] if amp is not None else [], rec=0, row=row); k += 1
+    barrier()
     e0 = time.perf_counter()
     for _ in range(K):
-        d.step_host(k, [amp[k]], rec=0, row=row); k += 1
-    e2e_s = time.perf_counter() - e0
-    e2e = {"value": m.n_elem * K / e2e_s, "unit": "element-updates/s", "h2d_bytes_per_step": 8 * len(m.point_loads),
-           "d2h_bytes_per_step": int(row.nbytes), "ms_per_step": 1e3 * e2e_s / K,
-           "note": "one svlgpu_step_host call per step: pinned H2D of the step's load amplitudes, all kernels, "
-                   "pinned D2H of the recorder row, stream sync; the state vectors stay resident in HBM exactly "
-                   "as the reference keeps U,V,A resident in host RAM between steps"}
+        d.step_host(k, [amp[k]] if amp is not None else [], rec=0, row=row); k += 1
+    barrier()
+    e2e_s = allmax(time.perf_counter() - e0)
+    if rank == 0:
+        sampler.stop_flag = True; sampler.join(timeout=2)
+    e2e = {"value": n_elem_total * K / e2e_s, "unit": "element-updates/s",
+           "h2d_bytes_per_step": int(allsum(8 * len(m.point_loads))),
+           "d2h_bytes_per_step": int(allsum(row.nbytes)), "ms_per_step": 1e3 * e2e_s / K,
+           "note": "one svlgpu_step_host call per step and rank: pinned H2D of the step's load amplitudes, all kernels "
+                   "(+ NCCL interface exchange), pinned D2H of the recorder row, stream sync; the state vectors stay "
+                   "resident in HBM exactly as the reference keeps U,V,A resident in host RAM between steps"}
     if not np.all(np.isfinite(row)):
         raise SystemExit("non-finite response")
 
@@ -245,24 +328,31 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = cpu_baseline_port()
 
+    G = m.global_elems_per_axis
     line = {"metric": "element-updates/sec (FP64 explicit step)", "value": value, "unit": "element-updates/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"3-D elastic half-space, {args.n}^3 lin3DHexa8 + Elastic3DLinear "
-                                   f"({m.n_total} DOF), lumped CentralDifference, DRM SV plane-wave layer "
-                                   f"({0 if m.drm is None else len(m.drm.elems)} DRM elements), 1 point load, 16 "
-                                   f"recorded nodes (BASELINE configs[3]-like, single partition)",
-                       "elements": m.n_elem, "dof": m.n_total, "dt": m.dt,
-                       "l2": "state vectors (3 x %.0f MB) exceed the 126 MB L2" % (m.n_total * 8 / 1e6),
-                       "block_nodes": c["n_block_nodes"], "generic_elements": c["n_generic_elements"],
-                       "node_classes": c["n_node_classes"], "model_build_s": t_model, "plan_upload_s": t_plan,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"3-D elastic half-space, {G[0]}x{G[1]}x{G[2]} lin3DHexa8 + Elastic3DLinear "
+                                   f"({n_dof_total} DOF), lumped CentralDifference, DRM SV plane-wave layer, "
+                                   f"1 host-fed point load, 16 recorded nodes per partition (BASELINE configs[3]-like; "
+                                   f"{world} block partition(s), one per GPU, NCCL interface-force exchange)",
+                       "elements": n_elem_total, "dof": n_dof_total, "dt": m.dt,
+                       "partition_grid": list(__import__("svl_b200.partition", fromlist=["x"]).proc_grid(world)),
+                       "interface_nodes_rank0": int(sum(len(v) for v in m.halos.values())),
+                       "l2": "state vectors (3 x %.0f MB per GPU) exceed the 126 MB L2" % (m.n_total * 8 / 1e6),
+                       "block_nodes_rank0": c["n_block_nodes"], "generic_elements_rank0": c["n_generic_elements"],
+                       "node_classes_rank0": c["n_node_classes"], "model_build_s": t_model, "plan_upload_s": t_plan,
                        "wall_s_timed_region": wall},
-            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
+            "clocks": sampler.summary() if rank == 0 else None, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roof,
             "kernel_ms": {"stencil_dom": kt[0][0], "stencil_shell_gather": kt[4][0], "gauss_elements": kt[1][0],
                           "gather_nodes": kt[2][0], "point_loads": kt[3][0], "drm": kt[5][0]},
             "cpu_baseline": cb}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
+    d.close()
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -196,14 +196,18 @@ int svlgpu_kernel_time(svlgpu_model *m, int which, double *avg_ms, int64_t *laun
 int svlgpu_device_ptr(svlgpu_model *m, int which, void **ptr, int64_t *len);
 
 /* ---- multi-GPU halo (replaces MumpsSolver.cpp:56,161) ----- */
-/* Interface nodes shared with neighbour rank `peer`: both sides must list the
- * same nodes in the same order.  Forces of the listed nodes are summed across
- * ranks each step.  The exchange itself is driven by the host (NCCL through
- * the communicator given to svlgpu_set_comm).                                  */
+/* One process per GPU / partition file.  Interface nodes shared with rank `peer`
+ * (interface nodes are duplicated in every partition that touches them,
+ * 01-Pre_Process/Core/SeismoVLAB.py:354-358): both sides must list the same
+ * nodes in the same order (ascending global tag).  Call before finalize, one
+ * list per peer.  Each step the partial (internal - external) forces of the
+ * listed nodes are exchanged with NCCL send/recv on a second stream, overlapped
+ * with the bulk kernels, and every replica applies the same rank-ordered sum. */
 int svlgpu_add_halo(svlgpu_model *m, int peer, int nnodes, const int32_t *nodes);
-/* comm: ncclComm_t created by the caller (one rank per process).               */
-int svlgpu_set_comm(svlgpu_model *m, void *nccl_comm, int rank, int nranks);
-int svlgpu_nccl_unique_id(void *out128);                 /* ncclGetUniqueId   */
+/* ncclGetUniqueId on rank 0 (128 bytes); the launcher broadcasts it.            */
+int svlgpu_nccl_unique_id(void *out128);
+/* after finalize, on every rank: joins the communicator and replaces the
+ * partial lumped mass / damping of the interface dofs by their global sums.     */
 int svlgpu_comm_init(svlgpu_model *m, const void *id128, int rank, int nranks);
 
 #ifdef __cplusplus

@@ -31,7 +31,7 @@ EXPORTS = [
     "svlgpu_step", "svlgpu_sync", "svlgpu_step_host", "svlgpu_get_state", "svlgpu_internal_force",
     "svlgpu_get_mass_diagonal", "svlgpu_get_gauss", "svlgpu_read_recorder", "svlgpu_recorder_rows",
     "svlgpu_recorder_width", "svlgpu_get_counters", "svlgpu_set_kernel_timing", "svlgpu_kernel_time",
-    "svlgpu_device_ptr", "svlgpu_add_halo", "svlgpu_set_comm", "svlgpu_nccl_unique_id", "svlgpu_comm_init",
+    "svlgpu_device_ptr", "svlgpu_add_halo", "svlgpu_nccl_unique_id", "svlgpu_comm_init",
 ]
 
 
@@ -86,12 +86,24 @@ def load_library():
     L.svlgpu_set_kernel_timing.argtypes = [C.c_void_p, C.c_int]
     L.svlgpu_kernel_time.argtypes = [C.c_void_p, C.c_int, _dp, C.POINTER(C.c_int64), C.c_int]
     L.svlgpu_device_ptr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    L.svlgpu_add_halo.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip]
+    L.svlgpu_nccl_unique_id.argtypes = [C.c_void_p]
+    L.svlgpu_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     _lib = L
     return L
 
 
 class SvlError(RuntimeError):
     pass
+
+
+def nccl_unique_id() -> bytes:
+    """ncclGetUniqueId through the C ABI (rank 0 calls it, the launcher broadcasts the 128 bytes)."""
+    L = load_library()
+    buf = C.create_string_buffer(128)
+    if L.svlgpu_nccl_unique_id(buf):
+        raise SvlError(L.svlgpu_last_error().decode())
+    return buf.raw
 
 
 def _d(a):
@@ -106,7 +118,9 @@ class DeviceModel:
     """One model on one GPU, driven through the C ABI."""
 
     def __init__(self, m: Model, device: int = 0, max_rows: int | None = None, fields=(DISP,),
-                 U0=None, V0=None, A0=None):
+                 U0=None, V0=None, A0=None, comm=None):
+        """comm = (rank, nranks, unique_id_bytes) joins the NCCL communicator after finalize; the
+        model's `.halos` ({peer: local node indices}, svl_b200.partition) are registered before it."""
         self.L = load_library()
         self.m = m
         self.h = self.L.svlgpu_create(m.ndim, int(m.lumped))
@@ -179,8 +193,14 @@ class DeviceModel:
             self._ck(self.L.svlgpu_set_initial_state(self.h, _d(A(U0, np.float64)) if U0 is not None else None,
                                                      _d(A(V0, np.float64)) if V0 is not None else None,
                                                      _d(A(A0, np.float64)) if A0 is not None else None))
+        for peer, nodes in sorted(getattr(m, "halos", {}).items()):
+            self._ck(self.L.svlgpu_add_halo(self.h, int(peer), len(nodes), _i(A(nodes, np.int32))))
         self._ck(self.L.svlgpu_finalize(self.h, float(m.dt), device))
         self._keep = []
+        if comm is not None:
+            rank, nranks, uid = comm
+            buf = C.create_string_buffer(bytes(uid), 128)
+            self._ck(self.L.svlgpu_comm_init(self.h, buf, int(rank), int(nranks)))
 
     # ---- helpers -------------------------------------------------------------------
     def _arr(self, x, dt):

@@ -40,6 +40,7 @@ void svlgpu_destroy(svlgpu_model *m) {
     if (m->finalized || m->stream) {
         cudaSetDevice(m->device);
         if (m->stream) cudaStreamSynchronize(m->stream);
+        halo_destroy(m);
         for (void *p : m->allocs) cudaFree(p);
         if (m->h_pl_amp) cudaFreeHost(m->h_pl_amp);
         if (m->h_row) cudaFreeHost(m->h_row);
@@ -411,9 +412,30 @@ int svlgpu_device_ptr(svlgpu_model *m, int which, void **ptr, int64_t *len) {
     return 0;
 }
 
-int svlgpu_add_halo(svlgpu_model *, int, int, const int32_t *) { set_error("multi-GPU halo: not built yet"); return 1; }
-int svlgpu_set_comm(svlgpu_model *, void *, int, int) { set_error("multi-GPU halo: not built yet"); return 1; }
-int svlgpu_nccl_unique_id(void *) { set_error("multi-GPU halo: not built yet"); return 1; }
-int svlgpu_comm_init(svlgpu_model *, const void *, int, int) { set_error("multi-GPU halo: not built yet"); return 1; }
+int svlgpu_add_halo(svlgpu_model *m, int peer, int nnodes, const int32_t *nodes) {
+    GUARD_BEGIN
+    REQUIRE(m && !m->finalized && peer >= 0 && nnodes > 0 && nodes, "add_halo: bad arguments (call before finalize)");
+    HaloPeer hp;
+    hp.peer = peer;
+    hp.nodes.assign(nodes, nodes + nnodes);
+    for (int n : hp.nodes) REQUIRE(n >= 0 && n < m->n_nodes, "add_halo: node out of range");
+    for (auto &o : m->halo_peers) REQUIRE(o.peer != peer, "add_halo: one list per peer");
+    m->halo_peers.push_back(std::move(hp));
+    return 0;
+    GUARD_END
+}
+int svlgpu_nccl_unique_id(void *out128) {
+    GUARD_BEGIN
+    REQUIRE(out128, "nccl_unique_id: null argument");
+    return halo_unique_id(out128);
+    GUARD_END
+}
+int svlgpu_comm_init(svlgpu_model *m, const void *id128, int rank, int nranks) {
+    GUARD_BEGIN
+    REQUIRE(m && id128 && rank >= 0 && rank < nranks, "comm_init: bad arguments");
+    REQUIRE(!m->halo.active, "comm_init: already initialised");
+    return halo_comm_init(m, id128, rank, nranks);
+    GUARD_END
+}
 
 }  // extern "C"

@@ -225,6 +225,8 @@ struct Gat3 {
     const int32_t *list;    // lattice-local node ids, sorted by class
     long long dof0;
     int n, nx, ny, nz, mode;
+    const int32_t *target;  // halo pass: interface index of each listed node (else null)
+    double *hF;             // halo pass: [n_if][3] partial internal force
 };
 __global__ void __launch_bounds__(128) k_stencil3_gather(const Gat3 p) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -255,6 +257,11 @@ __global__ void __launch_bounds__(128) k_stencil3_gather(const Gat3 p) {
             }
         }
     }
+    if (p.hF) {
+        double *o = p.hF + 3ll * p.target[t];
+        o[0] = F[0]; o[1] = F[1]; o[2] = F[2];
+        return;
+    }
     const long long d0 = p.dof0 + 3ll * q;
 #pragma unroll
     for (int a = 0; a < 3; a++) {
@@ -265,6 +272,37 @@ __global__ void __launch_bounds__(128) k_stencil3_gather(const Gat3 p) {
             p.Un[d0 + a] = F[a];
         }
     }
+}
+
+// halo pass of a 2-D lattice: partial internal force of the listed (interface) nodes
+struct Gat2 {
+    const double *U;
+    const uint8_t *cls;
+    const double *tbl;
+    const int32_t *list, *target;
+    double *hF;
+    long long dof0;
+    int n, nx, ny;
+};
+__global__ void __launch_bounds__(128) k_stencil2_gather(const Gat2 p) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.n) return;
+    const int q = p.list[t];
+    const int i = q % p.nx, j = q / p.nx;
+    const double *T = p.tbl + (size_t)p.cls[q] * kTbl2Stride;
+    const double2 *U2 = reinterpret_cast<const double2 *>(p.U + p.dof0);
+    double f0 = 0.0, f1 = 0.0;
+    for (int dj = -1; dj <= 1; dj++)
+        for (int di = -1; di <= 1; di++) {
+            const int x = i + di, y = j + dj;
+            double2 u = make_double2(0.0, 0.0);
+            if (x >= 0 && x < p.nx && y >= 0 && y < p.ny) u = U2[x + (long long)p.nx * y];
+            const double *k = T + ((dj + 1) * 3 + (di + 1)) * 4;
+            f0 = fma(k[0], u.x, f0); f0 = fma(k[1], u.y, f0);
+            f1 = fma(k[2], u.x, f1); f1 = fma(k[3], u.y, f1);
+        }
+    p.hF[2ll * p.target[t]] = f0;
+    p.hF[2ll * p.target[t] + 1] = f1;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -512,11 +550,14 @@ struct GNodeArgs {
     const double *U, *Up, *kinv, *km;
     double *Un;
     int mode;
+    const int32_t *target;   // halo pass: interface index per listed node (dof0 unused then)
+    double *hF;
+    int hnd;
 };
 __global__ void __launch_bounds__(256) k_gen_nodes(const GNodeArgs a) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.n) return;
-    const int d0 = a.dof0[t], nd = a.ndof[t];
+    const int d0 = a.hF ? 0 : a.dof0[t], nd = a.ndof[t];
     double F[9];
 #pragma unroll
     for (int c = 0; c < 9; c++) F[c] = 0.0;
@@ -525,6 +566,10 @@ __global__ void __launch_bounds__(256) k_gen_nodes(const GNodeArgs a) {
 #pragma unroll
         for (int c = 0; c < 9; c++)
             if (c < nd) F[c] += f[c];
+    }
+    if (a.hF) {
+        for (int c = 0; c < a.hnd; c++) a.hF[(long long)a.target[t] * a.hnd + c] = F[c];
+        return;
     }
 #pragma unroll
     for (int c = 0; c < 9; c++)
@@ -553,6 +598,9 @@ struct PLArgs {
     const double *kinv;
     double *Un;
     int k;
+    const int32_t *target;        // per loaded dof: slot in hF (interface dof) or -1; null without halos
+    double *hF;
+    int phase;                    // 0: interface dofs (hF -= F, before the exchange), 1: all other dofs
 };
 __global__ void k_nodal_loads(const PLArgs a) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -565,6 +613,12 @@ __global__ void k_nodal_loads(const PLArgs a) {
         else amp = (a.snt[l] == 1) ? a.series[a.soff[l]] : ((a.k < a.snt[l]) ? a.series[a.soff[l] + a.k] : 0.0);
         F += a.coef[q] * amp;
     }
+    const int tg = a.target ? a.target[t] : -1;
+    if (a.phase == 0) {
+        if (tg >= 0) a.hF[tg] -= F;
+        return;
+    }
+    if (tg >= 0) return;
     const int d = a.dof[t];
     a.Un[d] += a.kinv[d] * F;
 }
@@ -584,6 +638,9 @@ struct DrmArgs {
     double dir[3], pol[3], xref[3], c, f0, t0, amp, factor, dt;
     const double *kinv;
     double *Un;
+    const int32_t *target;        // per row: first slot in hF (interface node) or -1; null without halos
+    double *hF;
+    int phase;
 };
 __device__ __forceinline__ double ricker_disp(double tau, double f0) {
     // Ricker displacement pulse (1 - 2b) e^{-b}, b = (pi f0 tau)^2  (PlaneWave.py:222-223)
@@ -609,6 +666,8 @@ __global__ void k_drm_field(const DrmArgs a) {
 __global__ void k_drm(const DrmArgs a) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.n) return;
+    const int tg = a.target ? a.target[t] : -1;
+    if ((a.phase == 0) != (tg >= 0)) return;
     double F[3] = {0, 0, 0};
     const int nd = a.ndim;
     for (int q = a.ptr[t]; q < a.ptr[t + 1]; q++) {
@@ -616,6 +675,10 @@ __global__ void k_drm(const DrmArgs a) {
         const double *B = a.dict + (long long)a.bid[q] * nd * nd;
         for (int r = 0; r < nd; r++)
             for (int c = 0; c < nd; c++) F[r] += B[r * nd + c] * u[c];
+    }
+    if (tg >= 0) {
+        for (int r = 0; r < nd; r++) a.hF[tg + r] -= a.factor * F[r];
+        return;
     }
     const int d0 = a.dof0[t];
     for (int r = 0; r < nd; r++) a.Un[d0 + r] += a.kinv[d0 + r] * (a.factor * F[r]);
@@ -716,8 +779,8 @@ static void launch_dom(const Dom3 &p, int slot, bool ortho, unsigned grid, cudaS
     }
 }
 
-static int launch_force_update(svlgpu_model *m, const double *U, const double *Up, double *Un, int mode, int commit) {
-    // 1. generic Gauss-point elements
+// 1. generic Gauss-point elements (element forces into the arena; J2 state update + commit)
+static int launch_generic_elements(svlgpu_model *m, const double *U, int commit) {
     for (auto &gs : m->gsets) {
         if (!gs.n) continue;
         GenArgs a;
@@ -735,7 +798,11 @@ static int launch_force_update(svlgpu_model *m, const double *U, const double *U
         timer_end(m, 1);
         m->total_launches++;
     }
-    // 2. lattice blocks
+    return 0;
+}
+
+// 2. + 3. lattice blocks and generic nodes: force gather + CentralDifference update (mode 0) or force only (mode 1)
+static int launch_node_update(svlgpu_model *m, const double *U, const double *Up, double *Un, int mode) {
     if (upload_dom_tables(m)) return 1;
     for (auto &b : m->blocks) {
         if (!b.n_stencil_nodes) continue;
@@ -756,6 +823,7 @@ static int launch_force_update(svlgpu_model *m, const double *U, const double *U
                 Gat3 p;
                 p.U = U; p.Up = Up; p.Un = Un; p.cls = b.d_cls; p.tbl = b.d_tbl; p.list = b.d_glist;
                 p.dof0 = b.dof0; p.n = b.n_glist; p.nx = b.nx; p.ny = b.ny; p.nz = b.nz; p.mode = mode;
+                p.target = nullptr; p.hF = nullptr;
                 timer_begin(m, 4);
                 k_stencil3_gather<<<(b.n_glist + 127) / 128, 128, 0, m->stream>>>(p);
                 timer_end(m, 4);
@@ -772,17 +840,54 @@ static int launch_force_update(svlgpu_model *m, const double *U, const double *U
             m->total_launches++;
         }
     }
-    // 3. generic nodes
     if (m->n_gnodes) {
         GNodeArgs a;
         a.n = m->n_gnodes; a.dof0 = m->d_gn_dof0; a.ndof = m->d_gn_ndof; a.ptr = m->d_gn_ptr;
         a.slot = (const long long *)m->d_gn_slot; a.fe = m->d_fe_arena; a.U = U; a.Up = Up;
         a.kinv = m->d_kinv; a.km = m->d_km; a.Un = Un; a.mode = mode;
+        a.target = nullptr; a.hF = nullptr; a.hnd = 0;
         timer_begin(m, 2);
         k_gen_nodes<<<(m->n_gnodes + 255) / 256, 256, 0, m->stream>>>(a);
         timer_end(m, 2);
         m->total_launches++;
     }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// partial internal force of the interface nodes -> halo.d_hF (lattice nodes through the class tables,
+// generic nodes through the element-force arena)
+int halo_lattice_force(svlgpu_model *m, const double *U) {
+    HaloDev &h = m->halo;
+    for (auto &l : h.lats) {
+        if (!l.n) continue;
+        const Block &b = m->blocks[l.block];
+        if (b.ndim == 3) {
+            Gat3 p;
+            p.U = U; p.Up = nullptr; p.Un = nullptr; p.cls = b.d_cls; p.tbl = b.d_tbl; p.list = l.d_list;
+            p.dof0 = b.dof0; p.n = l.n; p.nx = b.nx; p.ny = b.ny; p.nz = b.nz; p.mode = 1;
+            p.target = l.d_target; p.hF = h.d_hF;
+            k_stencil3_gather<<<(l.n + 127) / 128, 128, 0, m->stream>>>(p);
+        } else {
+            Gat2 p;
+            p.U = U; p.cls = b.d_cls; p.tbl = b.d_tbl; p.list = l.d_list; p.target = l.d_target; p.hF = h.d_hF;
+            p.dof0 = b.dof0; p.n = l.n; p.nx = b.nx; p.ny = b.ny;
+            k_stencil2_gather<<<(l.n + 127) / 128, 128, 0, m->stream>>>(p);
+        }
+        m->total_launches++;
+    }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int halo_generic_force(svlgpu_model *m) {
+    HaloDev &h = m->halo;
+    if (!h.n_gen) return 0;
+    GNodeArgs a;
+    a.n = h.n_gen; a.dof0 = nullptr; a.ndof = h.d_g_ndof; a.ptr = h.d_g_ptr; a.slot = (const long long *)h.d_g_slot;
+    a.fe = m->d_fe_arena; a.U = nullptr; a.Up = nullptr; a.kinv = nullptr; a.km = nullptr; a.Un = nullptr; a.mode = 1;
+    a.target = h.d_g_target; a.hF = h.d_hF; a.hnd = h.nd;
+    k_gen_nodes<<<(h.n_gen + 255) / 256, 256, 0, m->stream>>>(a);
+    m->total_launches++;
     CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -798,37 +903,59 @@ void record_rows(svlgpu_model *m) {
     }
 }
 
+// external forces of step k (Assembler::ComputeExternalForceVector).  phase 0: contributions to interface
+// dofs, subtracted from the partial force that is about to be exchanged; phase 1: everything else,
+// applied to U_{n+1} directly (the solve is diagonal there).
+static int launch_external(svlgpu_model *m, int k, const double *dev_amp, double *Un, int phase) {
+    const bool halo = m->halo.active;
+    if (phase == 0 && !halo) return 0;
+    if (m->n_pl_dofs) {
+        PLArgs a;
+        a.n = m->n_pl_dofs; a.dof = m->d_pl_dof; a.ptr = m->d_pl_ptr; a.load = m->d_pl_load;
+        a.coef = m->d_pl_coef; a.series = m->d_pl_series; a.soff = m->d_pl_soff; a.snt = m->d_pl_nt;
+        a.amp = dev_amp; a.kinv = m->d_kinv; a.Un = Un; a.k = k;
+        a.target = halo ? m->d_pl_target : nullptr; a.hF = m->halo.d_hF; a.phase = phase;
+        timer_begin(m, 3);
+        k_nodal_loads<<<(a.n + 127) / 128, 128, 0, m->stream>>>(a);
+        timer_end(m, 3);
+        m->total_launches++;
+    }
+    for (auto &d : m->drm_dev) {
+        if (!d.analytic && k >= d.nt) continue;
+        DrmArgs a;
+        a.n = d.n_nodes; a.nn = d.n_all; a.ndim = m->ndim; a.nt = d.nt; a.nf = d.nf; a.k = k; a.analytic = d.analytic;
+        a.dof0 = d.d_node_dof0; a.ptr = d.d_row_ptr; a.col = d.d_col_node; a.bid = d.d_blk_id; a.ext = d.d_ext;
+        a.dict = d.d_blk; a.field = d.d_field; a.xyz = d.d_xyz; a.uo = d.d_uo;
+        for (int c = 0; c < 3; c++) { a.dir[c] = d.dir[c]; a.pol[c] = d.pol[c]; a.xref[c] = d.xref[c]; }
+        a.c = d.c; a.f0 = d.f0; a.t0 = d.t0; a.amp = d.amp; a.factor = d.factor; a.dt = m->dt;
+        a.kinv = m->d_kinv; a.Un = Un;
+        a.target = halo ? d.d_target : nullptr; a.hF = m->halo.d_hF; a.phase = phase;
+        timer_begin(m, 5);
+        if (phase == 0 || !halo) { k_drm_field<<<(a.nn + 127) / 128, 128, 0, m->stream>>>(a); m->total_launches++; }
+        k_drm<<<(a.n + 127) / 128, 128, 0, m->stream>>>(a);
+        timer_end(m, 5);
+        m->total_launches++;
+    }
+    return 0;
+}
+
 int run_steps(svlgpu_model *m, int k0, int k1, const double *dev_amp) {
     const int64_t before = m->total_launches;
+    const bool halo = m->halo.active;
+    if (!m->halo_peers.empty() && !halo) { set_error("step: halos were declared but svlgpu_comm_init was not called"); return 1; }
     for (int k = k0; k < k1; k++) {
         const double *U = m->d_U[m->cur], *Up = m->d_U[m->prev];
         double *Un = m->d_U[m->next];
-        if (launch_force_update(m, U, Up, Un, 0, 1)) return 1;
-        if (m->n_pl_dofs) {
-            PLArgs a;
-            a.n = m->n_pl_dofs; a.dof = m->d_pl_dof; a.ptr = m->d_pl_ptr; a.load = m->d_pl_load;
-            a.coef = m->d_pl_coef; a.series = m->d_pl_series; a.soff = m->d_pl_soff; a.snt = m->d_pl_nt;
-            a.amp = dev_amp; a.kinv = m->d_kinv; a.Un = Un; a.k = k;
-            timer_begin(m, 3);
-            k_nodal_loads<<<(a.n + 127) / 128, 128, 0, m->stream>>>(a);
-            timer_end(m, 3);
-            m->total_launches++;
+        if (launch_generic_elements(m, U, 1)) return 1;
+        if (halo) {
+            // interface partial forces first, so that their exchange overlaps the bulk of the step
+            if (halo_lattice_force(m, U) || halo_generic_force(m)) return 1;
+            if (launch_external(m, k, dev_amp, Un, 0)) return 1;
+            if (halo_exchange_begin(m)) return 1;
         }
-        for (auto &d : m->drm_dev) {
-            if (!d.analytic && k >= d.nt) continue;
-            DrmArgs a;
-            a.n = d.n_nodes; a.nn = d.n_all; a.ndim = m->ndim; a.nt = d.nt; a.nf = d.nf; a.k = k; a.analytic = d.analytic;
-            a.dof0 = d.d_node_dof0; a.ptr = d.d_row_ptr; a.col = d.d_col_node; a.bid = d.d_blk_id; a.ext = d.d_ext;
-            a.dict = d.d_blk; a.field = d.d_field; a.xyz = d.d_xyz; a.uo = d.d_uo;
-            for (int c = 0; c < 3; c++) { a.dir[c] = d.dir[c]; a.pol[c] = d.pol[c]; a.xref[c] = d.xref[c]; }
-            a.c = d.c; a.f0 = d.f0; a.t0 = d.t0; a.amp = d.amp; a.factor = d.factor; a.dt = m->dt;
-            a.kinv = m->d_kinv; a.Un = Un;
-            timer_begin(m, 5);
-            k_drm_field<<<(a.nn + 127) / 128, 128, 0, m->stream>>>(a);
-            k_drm<<<(a.n + 127) / 128, 128, 0, m->stream>>>(a);
-            timer_end(m, 5);
-            m->total_launches += 2;
-        }
+        if (launch_node_update(m, U, Up, Un, 0)) return 1;
+        if (halo && halo_exchange_end(m, U, Up, Un, 0)) return 1;
+        if (launch_external(m, k, dev_amp, Un, 1)) return 1;
         record_rows(m);
         // rotate: U_{n-1} <- U_n <- U_{n+1}
         const int old_prev = m->prev;
@@ -844,7 +971,8 @@ int run_steps(svlgpu_model *m, int k0, int k1, const double *dev_amp) {
 int compute_internal_force(svlgpu_model *m, double *F_host) {
     double *tmp = m->d_U[m->next];
     CUDA_OK(cudaMemsetAsync(tmp, 0, sizeof(double) * m->n_int, m->stream));
-    if (launch_force_update(m, m->d_U[m->cur], m->d_U[m->prev], tmp, 1, 0)) return 1;
+    if (launch_generic_elements(m, m->d_U[m->cur], 0)) return 1;
+    if (launch_node_update(m, m->d_U[m->cur], m->d_U[m->prev], tmp, 1)) return 1;
     std::vector<double> h(m->n_int);
     CUDA_OK(cudaMemcpyAsync(h.data(), tmp, sizeof(double) * m->n_int, cudaMemcpyDeviceToHost, m->stream));
     CUDA_OK(cudaStreamSynchronize(m->stream));

@@ -100,6 +100,33 @@ struct DrmDev {
     double *d_xyz = nullptr;         // node coordinates (analytic mode)
     bool analytic = false;
     double dir[3], pol[3], xref[3], c = 0, f0 = 0, t0 = 0, amp = 0, factor = 1;
+    int32_t *d_target = nullptr;     // per row: first slot in halo.d_hF (interface node) or -1
+};
+
+// Multi-GPU: interface nodes shared with other ranks.  Every rank computes the partial
+// (internal - external) force of its own elements at the interface nodes, exchanges the partials with
+// the ranks sharing each node, and every replica applies the same rank-ordered sum.
+struct HaloPeer { int peer = 0; std::vector<int32_t> nodes; int offset = 0; };
+struct HaloDev {
+    bool active = false;
+    int n_if = 0, nd = 3;              // interface nodes, dofs per node exchanged (= ndim)
+    int n_entries = 0;                 // sum of the peers' node counts
+    int32_t *d_if_dof0 = nullptr;      // [n_if] internal dof0
+    double *d_hF = nullptr;            // [n_if][nd] own partial force
+    int32_t *d_send_map = nullptr;     // [n_entries] interface index of each send entry
+    double *d_send = nullptr, *d_recv = nullptr;   // [n_entries][nd]
+    int32_t *d_fix_ptr = nullptr, *d_fix_src = nullptr;   // per interface node: sources in rank order (-1 = own)
+    // generic (Gauss-point path) interface nodes: subset CSR into the element-force arena
+    int n_gen = 0;
+    int32_t *d_g_ndof = nullptr, *d_g_ptr = nullptr, *d_g_target = nullptr;
+    int64_t *d_g_slot = nullptr;
+    // lattice interface nodes, per block: lattice-local ids + interface index
+    struct Lat { int block = 0, n = 0; int32_t *d_list = nullptr, *d_target = nullptr; };
+    std::vector<Lat> lats;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t e_ready = nullptr, e_done = nullptr;
+    void *comm = nullptr;              // ncclComm_t
+    int rank = 0, nranks = 1;
 };
 
 }  // namespace svl
@@ -137,7 +164,7 @@ struct svlgpu_model {
     double *d_U[3] = {nullptr, nullptr, nullptr};   // rotating buffers
     int cur = 0, prev = 1, next = 2;
     double *d_kinv = nullptr, *d_km = nullptr;      // per internal dof: 1/Keff, Kminus (0 if not free)
-    std::vector<double> h_mass;                     // lumped mass per internal dof
+    std::vector<double> h_mass, h_cdiag;            // lumped mass / damping diagonal per internal dof
 
     std::vector<svl::Block> blocks;
     std::vector<svl::GenericSet> gsets;
@@ -160,6 +187,12 @@ struct svlgpu_model {
 
     std::vector<svl::DrmDev> drm_dev;
 
+    // multi-GPU halo
+    std::vector<svl::HaloPeer> halo_peers;
+    svl::HaloDev halo;
+    std::vector<int32_t> if_of_node;                // node -> interface index or -1 (host, plan time)
+    int32_t *d_pl_target = nullptr;                 // per loaded dof: slot in halo.d_hF or -1
+
     // counters / timing
     int64_t total_launches = 0, launches_per_step = 0;
     int64_t n_block_nodes = 0, n_generic_elements = 0, n_elem_classes = 0, n_node_classes = 0;
@@ -181,4 +214,13 @@ int configure_kernels();
 size_t stencil3_smem(int nw, int r);
 bool stencil_entry_nonzero(int di, int b, int dj, int s, int a);
 void forget_const_owner(svlgpu_model *m);
+// halo.cu
+int halo_plan(svlgpu_model *m);                        // after the node lists are known (planner)
+int halo_comm_init(svlgpu_model *m, const void *id128, int rank, int nranks);
+int halo_unique_id(void *out128);
+int halo_exchange_begin(svlgpu_model *m);              // main stream: hF complete -> comm stream: pack + NCCL
+int halo_exchange_end(svlgpu_model *m, const double *U, const double *Up, double *Un, int mode);
+int halo_lattice_force(svlgpu_model *m, const double *U);   // partial forces of lattice interface nodes -> hF
+int halo_generic_force(svlgpu_model *m);                    // ... of generic interface nodes -> hF
+void halo_destroy(svlgpu_model *m);
 }  // namespace svl

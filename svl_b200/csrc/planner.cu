@@ -174,7 +174,7 @@ int plan_and_upload(svlgpu_model *m) {
                 }
         }
     }
-    m->h_mass = mass;
+    m->h_mass = mass; m->h_cdiag = cdiag;
     std::vector<double> kinv(m->n_int, 0.0), km(m->n_int, 0.0);
     for (int q = 0; q < m->n_int; q++) {
         if (m->freedof[q] < 0) continue;             // restrained: dU = 0 (Mesh.cpp:354-357)
@@ -439,9 +439,11 @@ int plan_and_upload(svlgpu_model *m) {
             if (g.d_gp) CUDA_OK(cudaMemset(g.d_gp, 0, sizeof(double) * 2ull * ncomp * g.n * g.ngp));
         }
     }
+    std::vector<int32_t> gn_of(nN, -1), gn_ptr_h;
+    std::vector<int64_t> gn_slot_h;
     {
         // generic nodes and their incidences in ascending element order
-        std::vector<int32_t> gn_of(nN, -1), dof0, ndofv, ptr;
+        std::vector<int32_t> dof0, ndofv, ptr;
         for (int n = 0; n < nN; n++)
             if (!node_done[n]) { gn_of[n] = (int)dof0.size(); dof0.push_back(m->node_ptr[n]); ndofv.push_back(m->node_ndof[n]); }
         const int ng = (int)dof0.size();
@@ -465,7 +467,74 @@ int plan_and_upload(svlgpu_model *m) {
         m->n_gnodes = ng;
         m->d_gn_dof0 = dupload(m, dof0); m->d_gn_ndof = dupload(m, ndofv); m->d_gn_ptr = dupload(m, ptr);
         m->d_gn_slot = dupload(m, slot);
+        gn_ptr_h = ptr; gn_slot_h = slot;
     }
+    // ---- E2. multi-GPU halo: interface nodes, their force sources, send order ------------------
+    m->if_of_node.assign(nN, -1);
+    if (!m->halo_peers.empty()) {
+        HaloDev &h = m->halo;
+        h.nd = nd;
+        std::vector<int32_t> ifn;
+        for (auto &hp : m->halo_peers) ifn.insert(ifn.end(), hp.nodes.begin(), hp.nodes.end());
+        std::sort(ifn.begin(), ifn.end());
+        ifn.erase(std::unique(ifn.begin(), ifn.end()), ifn.end());
+        h.n_if = (int)ifn.size();
+        std::vector<int32_t> dof0(h.n_if);
+        for (int i = 0; i < h.n_if; i++) {
+            const int n = ifn[i];
+            if (m->node_ndof[n] != nd) { set_error("halo: interface nodes must carry exactly ndim dofs"); return 1; }
+            m->if_of_node[n] = i; dof0[i] = m->node_ptr[n];
+        }
+        h.d_if_dof0 = dupload(m, dof0);
+        h.d_hF = dalloc<double>(m, (size_t)h.n_if * nd);
+        CUDA_OK(cudaMemset(h.d_hF, 0, sizeof(double) * (size_t)std::max(1, h.n_if * nd)));
+        std::vector<int32_t> send_map;
+        for (auto &hp : m->halo_peers) {
+            hp.offset = (int)send_map.size();
+            for (int n : hp.nodes) send_map.push_back(m->if_of_node[n]);
+        }
+        h.n_entries = (int)send_map.size();
+        h.d_send_map = dupload(m, send_map);
+        h.d_send = dalloc<double>(m, (size_t)h.n_entries * nd);
+        h.d_recv = dalloc<double>(m, (size_t)h.n_entries * nd);
+        // force sources
+        std::vector<std::vector<int32_t>> llist(m->blocks.size()), ltgt(m->blocks.size());
+        std::vector<int32_t> g_ndof, g_ptr(1, 0), g_tgt;
+        std::vector<int64_t> g_slot;
+        for (int i = 0; i < h.n_if; i++) {
+            const int n = ifn[i];
+            if (node_done[n]) {
+                for (size_t b = 0; b < m->blocks.size(); b++) {
+                    const Block &B = m->blocks[b];
+                    const long long nbn = (long long)B.nx * B.ny * B.nz;
+                    if (n >= B.node0 && n < B.node0 + nbn) { llist[b].push_back(n - B.node0); ltgt[b].push_back(i); break; }
+                }
+            } else {
+                const int g = gn_of[n];
+                g_ndof.push_back(nd); g_tgt.push_back(i);
+                for (int q = gn_ptr_h[g]; q < gn_ptr_h[g + 1]; q++) g_slot.push_back(gn_slot_h[q]);
+                g_ptr.push_back((int32_t)g_slot.size());
+            }
+        }
+        for (size_t b = 0; b < m->blocks.size(); b++) {
+            if (llist[b].empty()) continue;
+            HaloDev::Lat l;
+            l.block = (int)b; l.n = (int)llist[b].size();
+            l.d_list = dupload(m, llist[b]); l.d_target = dupload(m, ltgt[b]);
+            h.lats.push_back(l);
+        }
+        h.n_gen = (int)g_tgt.size();
+        if (h.n_gen) {
+            h.d_g_ndof = dupload(m, g_ndof); h.d_g_ptr = dupload(m, g_ptr); h.d_g_target = dupload(m, g_tgt);
+            h.d_g_slot = dupload(m, g_slot);
+        }
+    }
+    auto halo_slot_of_dof = [&](int q) -> int32_t {       // internal dof -> slot in hF or -1
+        if (m->halo_peers.empty()) return -1;
+        const int node = (int)(std::upper_bound(m->node_ptr.begin(), m->node_ptr.end(), q) - m->node_ptr.begin()) - 1;
+        const int i = m->if_of_node[node];
+        return i < 0 ? -1 : i * nd + (q - m->node_ptr[node]);
+    };
     m->d_coords = dupload(m, m->coords);
     m->d_node_ptr = dupload(m, m->node_ptr);
     m->d_int_of_total = dupload(m, m->int_of_total);
@@ -499,6 +568,9 @@ int plan_and_upload(svlgpu_model *m) {
         }
         m->n_ploads = (int)m->ploads.size();
         m->n_pl_dofs = (int)dof.size();
+        std::vector<int32_t> tgt(dof.size());
+        for (size_t i = 0; i < dof.size(); i++) tgt[i] = halo_slot_of_dof(dof[i]);
+        m->d_pl_target = dupload(m, tgt);
         m->d_pl_dof = dupload(m, dof); m->d_pl_ptr = dupload(m, ptr); m->d_pl_load = dupload(m, load);
         m->d_pl_coef = dupload(m, coef); m->d_pl_series = dupload(m, series);
         m->d_pl_soff = dupload(m, soff); m->d_pl_nt = dupload(m, snt);
@@ -549,6 +621,11 @@ int plan_and_upload(svlgpu_model *m) {
         }
         if (last >= 0) ptr.push_back((int32_t)col.size());
         dd.n_nodes = (int)rows.size(); dd.n_all = nn; dd.nt = dl.nt; dd.nf = 3 * nd;
+        {
+            std::vector<int32_t> tgt(dof0.size());
+            for (size_t i = 0; i < dof0.size(); i++) tgt[i] = halo_slot_of_dof(dof0[i]);
+            dd.d_target = dupload(m, tgt);
+        }
         dd.d_node_dof0 = dupload(m, dof0); dd.d_row_ptr = dupload(m, ptr); dd.d_col_node = dupload(m, col);
         dd.d_blk_id = dupload(m, bid); dd.d_blk = dupload(m, dict); dd.d_ext = dupload(m, dl.ext);
         dd.d_uo = dalloc<double>(m, (size_t)nn * nd);

@@ -161,12 +161,13 @@ def ricker(nt, dt, f0, t0):
 
 def make_box_model(ne, h=1.0, mat=(ELASTIC3DLINEAR, [1.3e7, 0.3, 2000.0]), fix="bottom",
                    dt=None, nt=0, load_node=None, load_dir=(0.0, 0.0, 1.0e4), series=None,
-                   rec_nodes=None, jitter=0.0, seed=20260117, layers=None) -> Model:
+                   rec_nodes=None, jitter=0.0, seed=20260117, layers=None, origin=(0.0, 0.0, 0.0)) -> Model:
     """Config-1-like soil box: nx*ny*nz lin3DHexa8 on [0,nx h]x[0,ny h]x[0,nz h], bottom fixed,
     lumped mass, vertical point load on the top-centre node.  `layers`: optional list of
     (material tuple) assigned per element layer in z (cyclic)."""
     nx, ny, nz = ne
-    X = box_nodes(ne, [0, 0, 0], [nx * h, 0, 0], [0, ny * h, 0], [0, 0, nz * h])
+    ox, oy, oz = origin
+    X = box_nodes(ne, [ox, oy, oz], [ox + nx * h, oy, oz], [ox, oy + ny * h, oz], [ox, oy, oz + nz * h])
     if jitter:
         rng = np.random.default_rng(seed)
         X = X + jitter * h * rng.uniform(-1.0, 1.0, X.shape)

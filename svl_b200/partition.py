@@ -1,0 +1,179 @@
+"""Element-based domain decomposition, one partition per GPU.
+
+Mirrors what the reference pre-processor does when it writes one JSON file per rank
+(01-Pre_Process/Core/SeismoVLAB.py:300-420, Partition.py:87-201): elements are assigned to
+partitions (METIS `mpmetis` there; a geometric block split for the synthetic structured meshes here, or
+any `epart` array read from a METIS `*.epart` file), interface nodes are duplicated in every partition
+that touches them (:354-358), point loads / nodal masses / recorders are handed to exactly one partition
+(:163-180, :118-122).  The only extra product of this module is the per-neighbour list of shared
+interface nodes that `svlgpu_add_halo` needs (both sides in ascending global node order).
+"""
+from __future__ import annotations
+
+import copy
+from typing import Dict, List
+
+import numpy as np
+
+from .model import DRMLoad, Model, PointLoad, make_box_model, add_drm_box
+
+
+def proc_grid(nparts: int):
+    """(px, py, pz) with px*py*pz = nparts, as cubic as possible, z split first (1,1,2), (1,2,2), (2,2,2)."""
+    g = [1, 1, 1]
+    ax = 2
+    n = nparts
+    f = 2
+    while n > 1:
+        while n % f:
+            f += 1
+        g[ax] *= f
+        n //= f
+        ax = (ax - 1) % 3
+    return tuple(g)
+
+
+def block_epart(ne, pgrid) -> np.ndarray:
+    """Element -> partition for an nx x ny (x nz) box split into pgrid blocks (element order of
+    Builder.py:167-183: x fastest)."""
+    nd = len(ne)
+    idx = np.meshgrid(*[np.arange(n) for n in reversed(ne)], indexing="ij")
+    ijk = [g.ravel() for g in reversed(idx)]
+    part = np.zeros(len(ijk[0]), dtype=np.int32)
+    mult = 1
+    for a in range(nd):
+        pa = np.minimum(ijk[a] * pgrid[a] // ne[a], pgrid[a] - 1)
+        part += (pa * mult).astype(np.int32)
+        mult *= pgrid[a]
+    return part
+
+
+def read_epart(path: str) -> np.ndarray:
+    """METIS `<graph>.epart.<nparts>` file: one partition id per element line (Partition.py:150-201)."""
+    return np.loadtxt(path, dtype=np.int32)
+
+
+def split_model(m: Model, epart: np.ndarray, nparts: int) -> List[Model]:
+    """Global model + element partition -> one sub-model per rank, each carrying
+    `.halos = {peer: local node indices}`, `.global_nodes`, `.global_elems`."""
+    if m.constraints:
+        raise ValueError("constraints (PML interfaces) are not partitioned yet: keep PML models on one GPU")
+    npe_of = lambda k: 8 if k in (1, 3) else 4
+    npe = npe_of(int(m.elem_kind[0]))
+    node_sets = []
+    for r in range(nparts):
+        el = np.nonzero(epart == r)[0]
+        node_sets.append(np.unique(m.elem_conn[el, :npe]))
+    # owner of a node = lowest rank that holds it
+    owner = np.full(m.n_nodes, nparts, dtype=np.int32)
+    for r in reversed(range(nparts)):
+        owner[node_sets[r]] = r
+    fd = np.asarray(m.freedof_flat)
+    subs = []
+    for r in range(nparts):
+        el = np.nonzero(epart == r)[0]
+        gn = node_sets[r]
+        loc = -np.ones(m.n_nodes, dtype=np.int64)
+        loc[gn] = np.arange(len(gn))
+        s = Model(ndim=m.ndim, lumped=m.lumped)
+        s.coords = m.coords[gn]
+        s.node_ndof = m.node_ndof[gn]
+        s.freedof = [np.where(fd[m.node_ptr[n]:m.node_ptr[n + 1]] > -1, 0, -1).astype(np.int32) for n in gn]
+        s.materials = list(m.materials)
+        conn = np.zeros((len(el), 8), dtype=np.int32)
+        conn[:, :npe] = loc[m.elem_conn[el, :npe]]
+        s.elem_conn = conn
+        s.elem_kind = m.elem_kind[el]
+        s.elem_mat = m.elem_mat[el]
+        s.elem_attr = m.elem_attr[el] if m.elem_attr is not None else None
+        s.elem_am = m.elem_am[el] if m.elem_am is not None else None
+        s.elem_ak = m.elem_ak[el] if m.elem_ak is not None else None
+        s.masses = [(int(loc[n]), v) for n, v in m.masses if owner[n] == r]
+        s.point_loads = []
+        for pl in m.point_loads:
+            keep = [int(loc[n]) for n in pl.nodes if owner[n] == r]
+            if keep:
+                s.point_loads.append(PointLoad(np.array(keep, dtype=np.int32), pl.dir.copy(), pl.series.copy(), pl.factor))
+        if m.drm is not None:
+            d = m.drm
+            eloc = -np.ones(m.n_elem, dtype=np.int64)
+            eloc[el] = np.arange(len(el))
+            mine = eloc[d.elems] >= 0
+            if mine.any():
+                de = eloc[d.elems[mine]].astype(np.int32)
+                dn_glob = np.unique(m.elem_conn[d.elems[mine], :npe])
+                pos = np.searchsorted(d.nodes, dn_glob)
+                assert (d.nodes[pos] == dn_glob).all()
+                s.drm = DRMLoad(elems=de, nodes=loc[dn_glob].astype(np.int32), exterior=d.exterior[pos].copy(),
+                                field=None if d.field is None else d.field[pos].copy(),
+                                planewave=copy.deepcopy(d.planewave), factor=d.factor)
+        s.dt, s.nt = m.dt, m.nt
+        rn = [int(loc[n]) for n in (m.rec_nodes if m.rec_nodes is not None else []) if owner[n] == r]
+        s.rec_nodes = np.array(rn, dtype=np.int32)
+        s.rec_global = np.array([int(n) for n in (m.rec_nodes if m.rec_nodes is not None else []) if owner[n] == r],
+                                dtype=np.int32)
+        s.blocks = _sub_lattice_hint(m, gn)
+        s.number_dofs()
+        s.global_nodes, s.global_elems = gn, el
+        s.halos = {}
+        subs.append(s)
+    for r in range(nparts):
+        for q in range(nparts):
+            if q == r:
+                continue
+            shared = np.intersect1d(node_sets[r], node_sets[q], assume_unique=True)
+            if len(shared):
+                subs[r].halos[q] = np.searchsorted(node_sets[r], shared).astype(np.int32)
+    return subs
+
+
+def _sub_lattice_hint(m: Model, gn: np.ndarray):
+    """If the global model is one lattice block and this partition's nodes form a full sub-box of it, the
+    local numbering (ascending global id) is again x-fastest: hint the planner."""
+    if len(m.blocks) != 1:
+        return []
+    n0, NX, NY, NZ = m.blocks[0]
+    q = gn - n0
+    if q.min() < 0 or q.max() >= NX * NY * NZ:
+        return []
+    i, j, k = q % NX, (q // NX) % NY, q // (NX * NY)
+    ni, nj, nk = i.max() - i.min() + 1, j.max() - j.min() + 1, k.max() - k.min() + 1
+    if ni * nj * nk != len(gn):
+        return []
+    return [(0, int(ni), int(nj), int(nk))]
+
+
+# -------------------------------------------------------------------------------
+# direct per-rank construction of a block of a large synthetic box (bench.py): the global model is never
+# materialised; the halo lists follow from the lattice arithmetic
+# -------------------------------------------------------------------------------
+def local_box(n_local, pgrid, rank, h=1.0, **kw) -> Model:
+    """Rank `rank` of a (px*nx) x (py*ny) x (pz*nz) element box split into px x py x pz blocks of
+    n_local = (nx, ny, nz) elements.  Bottom fixed on the lowest layer of ranks only."""
+    px, py, pz = pgrid
+    rx, ry, rz = rank % px, (rank // px) % py, rank // (px * py)
+    nx, ny, nz = n_local
+    origin = (rx * nx * h, ry * ny * h, rz * nz * h)
+    m = make_box_model(n_local, h, fix="bottom" if rz == 0 else None, origin=origin, **kw)
+    NX, NY, NZ = nx + 1, ny + 1, nz + 1
+    i, j, k = np.meshgrid(np.arange(NX), np.arange(NY), np.arange(NZ), indexing="ij")
+    lid = (i + NX * j + NX * NY * k)
+    m.halos = {}
+    for dz in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                if dx == dy == dz == 0:
+                    continue
+                qx, qy, qz = rx + dx, ry + dy, rz + dz
+                if not (0 <= qx < px and 0 <= qy < py and 0 <= qz < pz):
+                    continue
+                sel = [slice(None)] * 3
+                for a, (d, N) in enumerate(((dx, NX), (dy, NY), (dz, NZ))):
+                    if d == -1:
+                        sel[a] = slice(0, 1)
+                    elif d == 1:
+                        sel[a] = slice(N - 1, N)
+                nodes = np.sort(lid[tuple(sel)].ravel()).astype(np.int32)
+                m.halos[qx + px * qy + px * py * qz] = nodes
+    m.grid_pos = (rx, ry, rz)
+    return m

@@ -211,3 +211,21 @@ def test_device_matches_reference_golden(oracle, name):
     assert cases.rel_err(out, g["disp"]) < cases.TOL[name]
     ref, _ = oracle.run(m)
     assert cases.rel_err(out, ref) < cases.TOL[name]
+
+
+def test_multigpu_interface_exchange():
+    """2-rank (or more) run of tests/multigpu_check.py when the box has several GPUs."""
+    import subprocess
+    import sys
+
+    import torch
+    n = min(torch.cuda.device_count(), 8)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = 2 if n < 4 else (4 if n < 8 else 8)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533",
+                        os.path.join(root, "tests", "multigpu_check.py")], capture_output=True, text=True, timeout=900)
+    print(r.stdout[-4000:], r.stderr[-2000:])
+    assert r.returncode == 0

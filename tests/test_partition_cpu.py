@@ -1,0 +1,123 @@
+"""Host-side multi-GPU logic on CPU: the element partitioner and the interface (halo) lists, exercised by two
+`gloo` ranks.  Each rank evaluates the ORACLE's internal force / lumped mass on its own sub-model, the ranks
+exchange the interface partial sums exactly the way libsvlgpu's NCCL exchange does (per-peer lists, ascending
+rank summation), and the result must equal the single-domain oracle."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import cases
+from svl_b200 import partition as P
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, case, q):
+    import torch
+    import torch.distributed as dist
+    from oracle_lib import Oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        m = cases.CASES[case]()
+        ne = {"kat444": (4, 4, 4), "drm_box": (6, 6, 5), "quad4_area": (8, 6), "j2_column": (2, 2, 6)}[case]
+        grid = P.proc_grid(world)[3 - len(ne):] if len(ne) == 3 else (1, world)
+        subs = P.split_model(m, P.block_epart(ne, grid), world)
+        s = subs[rank]
+        o = Oracle()
+        rng = np.random.default_rng(42)
+        Ug = rng.uniform(-1e-3, 1e-3, m.n_total)
+        # local restriction of the global state (node-major dofs on both sides)
+        nd = m.ndim
+        gd = (s.global_nodes[:, None] * nd + np.arange(nd)[None, :]).ravel()
+        out = {}
+        for name, vec in (("F", o.internal_force(s, Ug[gd])), ("M", o.mass_diagonal(s))):
+            vec = vec.copy()
+            part = vec.copy()
+            reqs, recv = [], {}
+            for peer, nodes in sorted(s.halos.items()):
+                dofs = (nodes[:, None] * nd + np.arange(nd)[None, :]).ravel()
+                recv[peer] = (dofs, torch.zeros(len(dofs), dtype=torch.float64))
+                reqs.append(dist.isend(torch.from_numpy(part[dofs].copy()), peer))
+                reqs.append(dist.irecv(recv[peer][1], peer))
+            for r_ in reqs:
+                r_.wait()
+            # ascending-rank summation at the interface dofs
+            if_dofs = np.unique(np.concatenate([d for d, _ in recv.values()])) if recv else np.array([], int)
+            tot = np.zeros(len(if_dofs))
+            for rk in range(world):
+                if rk == rank:
+                    tot += part[if_dofs]
+                elif rk in recv:
+                    d, t = recv[rk]
+                    pos = np.searchsorted(if_dofs, d)
+                    tot[pos] += t.numpy()
+            vec[if_dofs] = tot
+            out[name] = (gd, vec)
+        q.put((rank, out, [len(v) for v in s.halos.values()], s.blocks))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["kat444", "drm_box", "quad4_area"])
+def test_two_rank_interface_sum_matches_single_domain(oracle, case):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, case, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    m = cases.CASES[case]()
+    rng = np.random.default_rng(42)
+    Ug = rng.uniform(-1e-3, 1e-3, m.n_total)
+    Fg, Mg = oracle.internal_force(m, Ug), oracle.mass_diagonal(m)
+    for rank, out, halo_sizes, blocks in res:
+        assert halo_sizes and halo_sizes[0] > 0 and len(blocks) == 1
+        gd, F = out["F"]
+        assert np.abs(F - Fg[gd]).max() <= 1e-12 * np.abs(Fg).max()
+        gd, Mv = out["M"]
+        assert np.abs(Mv - Mg[gd]).max() <= 1e-12 * np.abs(Mg).max()
+
+
+def test_split_hands_loads_and_recorders_to_one_partition():
+    m = cases.drm_box()
+    m.point_loads = cases.kat444().point_loads
+    m.point_loads[0].nodes[:] = 7 * 7 * 3 + 10            # a node on the cut plane of the 2-way z split
+    subs = P.split_model(m, P.block_epart((6, 6, 5), (1, 1, 2)), 2)
+    assert sum(len(s.point_loads) for s in subs) == 1 and len(subs[0].point_loads) == 1
+    assert sorted(np.concatenate([s.rec_global for s in subs])) == sorted(m.rec_nodes)
+    assert sum(len(s.drm.elems) for s in subs) == len(m.drm.elems)
+    # halo lists are mirror images in global numbering
+    a = subs[0].global_nodes[subs[0].halos[1]]
+    b = subs[1].global_nodes[subs[1].halos[0]]
+    assert (a == b).all() and (np.diff(a) > 0).all()
+
+
+def test_local_box_matches_split_of_global_box():
+    from svl_b200 import model as M
+    grid = (2, 2, 2)
+    n = (3, 2, 2)
+    g = M.make_box_model((6, 4, 4), 1.0, nt=4)
+    subs = P.split_model(g, P.block_epart((6, 4, 4), grid), 8)
+    for r in range(8):
+        lb = P.local_box(n, grid, r, nt=4)
+        assert np.allclose(lb.coords, subs[r].coords)
+        assert (lb.elem_conn == subs[r].elem_conn).all()
+        assert sorted(lb.halos) == sorted(subs[r].halos)
+        for peer in lb.halos:
+            assert (lb.halos[peer] == subs[r].halos[peer]).all()
+        assert (np.asarray(lb.freedof_flat) < 0).sum() == (np.asarray(subs[r].freedof_flat) < 0).sum()
