@@ -180,6 +180,9 @@ typedef struct svlgpu_counters {
     int64_t device_bytes;        /* HBM allocated by the handle                    */
     double  last_step_ms;        /* CUDA-event time of the last svlgpu_step call   */
     double  stencil_ms;          /* ... of which block-stencil kernel (if timed)   */
+    int64_t n_pml_elements;      /* PML elements (block solve)       */
+    int64_t n_pml_unknowns;      /* dofs of the non-diagonal block of Keff         */
+    int64_t pml_solves, pml_iterations;   /* BiCGStab solves / iterations so far   */
 } svlgpu_counters;
 int svlgpu_get_counters(svlgpu_model *m, svlgpu_counters *out);
 

@@ -41,6 +41,7 @@ void svlgpu_destroy(svlgpu_model *m) {
         cudaSetDevice(m->device);
         if (m->stream) cudaStreamSynchronize(m->stream);
         halo_destroy(m);
+        pml_destroy(m);
         for (void *p : m->allocs) cudaFree(p);
         if (m->h_pl_amp) cudaFreeHost(m->h_pl_amp);
         if (m->h_row) cudaFreeHost(m->h_row);
@@ -386,6 +387,8 @@ int svlgpu_get_counters(svlgpu_model *m, svlgpu_counters *o) {
     o->total_launches = m->total_launches; o->device_bytes = m->device_bytes;
     o->last_step_ms = m->last_step_ms;
     o->stencil_ms = m->timers[0].launches ? m->timers[0].total_ms / m->timers[0].launches : 0.0;
+    o->n_pml_elements = m->pml.n_elem; o->n_pml_unknowns = m->pml.nc;
+    o->pml_solves = m->pml.solves; o->pml_iterations = m->pml.total_iters;
     return 0;
 }
 

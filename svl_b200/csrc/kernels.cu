@@ -598,9 +598,9 @@ struct PLArgs {
     const double *kinv;
     double *Un;
     int k;
-    const int32_t *target;        // per loaded dof: slot in hF (interface dof) or -1; null without halos
-    double *hF;
-    int phase;                    // 0: interface dofs (hF -= F, before the exchange), 1: all other dofs
+    const int32_t *target;        // per loaded dof: slot in hF (interface dof), -2-c (PML unknown c) or -1
+    double *hF, *bext;
+    int phase;                    // 0: interface / PML dofs (before the exchange / block solve), 1: all other dofs
 };
 __global__ void k_nodal_loads(const PLArgs a) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -616,9 +616,10 @@ __global__ void k_nodal_loads(const PLArgs a) {
     const int tg = a.target ? a.target[t] : -1;
     if (a.phase == 0) {
         if (tg >= 0) a.hF[tg] -= F;
+        else if (tg <= -2) a.bext[-2 - tg] += F;
         return;
     }
-    if (tg >= 0) return;
+    if (tg != -1) return;
     const int d = a.dof[t];
     a.Un[d] += a.kinv[d] * F;
 }
@@ -907,14 +908,14 @@ void record_rows(svlgpu_model *m) {
 // dofs, subtracted from the partial force that is about to be exchanged; phase 1: everything else,
 // applied to U_{n+1} directly (the solve is diagonal there).
 static int launch_external(svlgpu_model *m, int k, const double *dev_amp, double *Un, int phase) {
-    const bool halo = m->halo.active;
+    const bool halo = m->halo.active || m->pml.present;
     if (phase == 0 && !halo) return 0;
     if (m->n_pl_dofs) {
         PLArgs a;
         a.n = m->n_pl_dofs; a.dof = m->d_pl_dof; a.ptr = m->d_pl_ptr; a.load = m->d_pl_load;
         a.coef = m->d_pl_coef; a.series = m->d_pl_series; a.soff = m->d_pl_soff; a.snt = m->d_pl_nt;
         a.amp = dev_amp; a.kinv = m->d_kinv; a.Un = Un; a.k = k;
-        a.target = halo ? m->d_pl_target : nullptr; a.hF = m->halo.d_hF; a.phase = phase;
+        a.target = halo ? m->d_pl_target : nullptr; a.hF = m->halo.d_hF; a.bext = m->pml.d_bext; a.phase = phase;
         timer_begin(m, 3);
         k_nodal_loads<<<(a.n + 127) / 128, 128, 0, m->stream>>>(a);
         timer_end(m, 3);
@@ -941,8 +942,9 @@ static int launch_external(svlgpu_model *m, int k, const double *dev_amp, double
 
 int run_steps(svlgpu_model *m, int k0, int k1, const double *dev_amp) {
     const int64_t before = m->total_launches;
-    const bool halo = m->halo.active;
-    if (!m->halo_peers.empty() && !halo) { set_error("step: halos were declared but svlgpu_comm_init was not called"); return 1; }
+    const bool xchg = !m->halo_peers.empty();                 // interface nodes shared with other ranks
+    const bool halo = m->halo.active || m->pml.present;       // interface nodes exist (peers and / or PML ties)
+    if (xchg && !m->halo.active) { set_error("step: halos were declared but svlgpu_comm_init was not called"); return 1; }
     for (int k = k0; k < k1; k++) {
         const double *U = m->d_U[m->cur], *Up = m->d_U[m->prev];
         double *Un = m->d_U[m->next];
@@ -951,10 +953,11 @@ int run_steps(svlgpu_model *m, int k0, int k1, const double *dev_amp) {
             // interface partial forces first, so that their exchange overlaps the bulk of the step
             if (halo_lattice_force(m, U) || halo_generic_force(m)) return 1;
             if (launch_external(m, k, dev_amp, Un, 0)) return 1;
-            if (halo_exchange_begin(m)) return 1;
+            if (xchg && halo_exchange_begin(m)) return 1;
         }
         if (launch_node_update(m, U, Up, Un, 0)) return 1;
-        if (halo && halo_exchange_end(m, U, Up, Un, 0)) return 1;
+        if (xchg && halo_exchange_end(m, U, Up, Un, 0)) return 1;
+        if (m->pml.present && pml_step(m, U, Up, Un)) return 1;
         if (launch_external(m, k, dev_amp, Un, 1)) return 1;
         record_rows(m);
         // rotate: U_{n-1} <- U_n <- U_{n+1}
@@ -973,6 +976,7 @@ int compute_internal_force(svlgpu_model *m, double *F_host) {
     CUDA_OK(cudaMemsetAsync(tmp, 0, sizeof(double) * m->n_int, m->stream));
     if (launch_generic_elements(m, m->d_U[m->cur], 0)) return 1;
     if (launch_node_update(m, m->d_U[m->cur], m->d_U[m->prev], tmp, 1)) return 1;
+    if (pml_internal_force(m, m->d_U[m->cur], tmp)) return 1;
     std::vector<double> h(m->n_int);
     CUDA_OK(cudaMemcpyAsync(h.data(), tmp, sizeof(double) * m->n_int, cudaMemcpyDeviceToHost, m->stream));
     CUDA_OK(cudaStreamSynchronize(m->stream));

@@ -129,6 +129,38 @@ struct HaloDev {
     int rank = 0, nranks = 1;
 };
 
+// PML block: the dofs of the PML nodes plus the soil dofs they are tied to form the part of
+// Keff = M/dt^2 + C/2dt that is not diagonal; it is solved every step by a matrix-free,
+// Jacobi-scaled BiCGStab (pml.cu).  All element matrices live in per-class tables.
+struct PmlDev {
+    bool present = false;
+    int nde = 72;                    // dofs per element (72 | 20)
+    int n_elem = 0, n_cls = 0, nc = 0;
+    double *d_A = nullptr;           // [n_cls][nde*nde] Keff_e, stored transposed ([col][row])
+    double *d_K = nullptr;           // [n_cls][...] K_e
+    double *d_Km = nullptr;          // [n_cls][...] M/dt^2 - C/2dt
+    int32_t *d_ecls = nullptr;       // [n_elem]
+    int32_t *d_edof = nullptr;       // [n_elem][nde] internal dof of every element dof
+    int32_t *d_ecd = nullptr;        // [n_elem][nde] unknown index (slaves -> their master's) or -1 (restrained)
+    double *d_ye = nullptr;          // [n_elem][nde] element products
+    int32_t *d_c_dof = nullptr;      // [nc] internal dof that carries the unknown
+    int32_t *d_c_ptr = nullptr, *d_c_slot = nullptr;   // gather lists into d_ye, ascending element order
+    int32_t *d_c_hf = nullptr;       // [nc] slot in halo.d_hF for soil (master) dofs, else -1
+    double *d_diag = nullptr;        // [nc] soil diagonal of Keff (0 for pure PML dofs)
+    double *d_kms = nullptr;         // [nc] soil M/dt^2 - C/2dt
+    double *d_w = nullptr;           // [nc] row scaling: sign(diag) / sqrt|diag(Keff)|
+    double *d_sc = nullptr;          // [nc] column scaling 1 / sqrt|diag(Keff)|  (unknown y = x / sc)
+    double *d_x = nullptr, *d_b = nullptr, *d_bext = nullptr, *d_r = nullptr, *d_rh = nullptr, *d_p = nullptr,
+           *d_v = nullptr, *d_s = nullptr, *d_t = nullptr;
+    int n_sc = 0;                    // dofs written back (unknown carriers + slaves)
+    int32_t *d_sc_dof = nullptr, *d_sc_c = nullptr;
+    double *d_part = nullptr;        // reduction partials
+    double *h_scal = nullptr;        // pinned: residual / rhs norms read back by the host
+    double rtol = 1e-14, ftol = 1e-12;   // ftol: Assembler.cpp:262 (Driver.hpp:1806 default)
+    int max_iter = 2000, last_iters = 8;
+    int64_t total_iters = 0, solves = 0;
+};
+
 }  // namespace svl
 
 struct svlgpu_model {
@@ -191,7 +223,8 @@ struct svlgpu_model {
     std::vector<svl::HaloPeer> halo_peers;
     svl::HaloDev halo;
     std::vector<int32_t> if_of_node;                // node -> interface index or -1 (host, plan time)
-    int32_t *d_pl_target = nullptr;                 // per loaded dof: slot in halo.d_hF or -1
+    int32_t *d_pl_target = nullptr;                 // per loaded dof: slot in halo.d_hF, -2-c for PML unknown c, or -1
+    svl::PmlDev pml;
 
     // counters / timing
     int64_t total_launches = 0, launches_per_step = 0;
@@ -223,4 +256,8 @@ int halo_exchange_end(svlgpu_model *m, const double *U, const double *Up, double
 int halo_lattice_force(svlgpu_model *m, const double *U);   // partial forces of lattice interface nodes -> hF
 int halo_generic_force(svlgpu_model *m);                    // ... of generic interface nodes -> hF
 void halo_destroy(svlgpu_model *m);
+// pml.cu
+int pml_step(svlgpu_model *m, const double *U, const double *Up, double *Un);
+int pml_internal_force(svlgpu_model *m, const double *U, double *F);
+void pml_destroy(svlgpu_model *m);
 }  // namespace svl

@@ -14,6 +14,7 @@
 #include <unordered_map>
 #include "model.h"
 #include "elem_math.h"
+#include "pml_math.h"
 
 namespace svl {
 
@@ -60,6 +61,10 @@ static int kind_npe(int k) { return (k == SVLGPU_LIN3DHEXA8 || k == SVLGPU_PML3D
 static const int kHexPos[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
 static const int kQuadPos[4][2] = {{0, 0}, {1, 0}, {1, 1}, {0, 1}};
 
+static int plan_pml(svlgpu_model *m, const std::vector<int32_t> &alias, const std::vector<uint8_t> &node_is_pml,
+                    const std::vector<int32_t> &node_of_dof, const std::vector<double> &kinv,
+                    const std::vector<double> &km, std::vector<int32_t> &cmap);
+
 int plan_and_upload(svlgpu_model *m) {
     const int nd = m->ndim;
     const int nE = (int)m->elem_kind.size();
@@ -79,16 +84,46 @@ int plan_and_upload(svlgpu_model *m) {
         if (t < 0 || t >= m->n_total || m->int_of_total[t] != -1) { set_error("total dof numbering is not a permutation"); return 1; }
         m->int_of_total[t] = q;
     }
-    if (!m->constraints.empty()) { set_error("constraints are not supported by the device path yet"); return 1; }
+    // EQUAL constraints (Constraint.cpp, Mesh.cpp:360-375; the soil-PML ties of Builder.py:653-666): the slave
+    // dof takes the increment of its single master -> index aliasing.  Anything else is refused.
+    std::vector<int32_t> alias(m->n_int), free_to_int(std::max(1, m->n_free), -1);
+    for (int q = 0; q < m->n_int; q++) {
+        alias[q] = q;
+        const int f = m->freedof[q];
+        if (f >= 0) { if (f >= m->n_free) { set_error("free dof id out of range"); return 1; } free_to_int[f] = q; }
+    }
+    for (auto &c : m->constraints) {
+        if (c.master.size() != 1 || c.factor[0] != 1.0) { set_error("only EQUAL constraints (one master, factor 1) are supported on the device path"); return 1; }
+        if (c.slave < 0 || c.slave >= m->n_total || c.master[0] < 0 || c.master[0] >= m->n_free || free_to_int[c.master[0]] < 0) { set_error("constraint refers to an unknown dof"); return 1; }
+        const int qs = m->int_of_total[c.slave];
+        if (m->freedof[qs] != c.tag) { set_error("constraint tag does not match the slave's free-dof entry"); return 1; }
+        alias[qs] = free_to_int[c.master[0]];
+    }
+    for (int q = 0; q < m->n_int; q++)
+        if (m->freedof[q] < -1 && alias[q] == q) { set_error("constrained dof without a constraint"); return 1; }
+    std::vector<uint8_t> node_is_pml(nN, 0);
+    bool has_pml = false;
     for (int e = 0; e < nE; e++) {
         const int k = m->elem_kind[e];
-        if (k == SVLGPU_PML3DHEXA8 || k == SVLGPU_PML2DQUAD4) { set_error("PML elements are not supported by the device path yet"); return 1; }
         if (!m->lumped) { set_error("consistent mass makes Keff non-diagonal: not supported by the explicit device path"); return 1; }
         const int mk = m->materials[m->elem_mat[e]].kind;
+        const bool pml = (k == SVLGPU_PML3DHEXA8 || k == SVLGPU_PML2DQUAD4);
         const bool ok = (k == SVLGPU_LIN3DHEXA8 && (mk == SVLGPU_ELASTIC3DLINEAR || mk == SVLGPU_PLASTIC3DJ2)) ||
-                        (k == SVLGPU_LIN2DQUAD4 && mk == SVLGPU_ELASTIC2DPLANESTRAIN);
+                        (k == SVLGPU_LIN2DQUAD4 && mk == SVLGPU_ELASTIC2DPLANESTRAIN) ||
+                        (k == SVLGPU_PML3DHEXA8 && mk == SVLGPU_ELASTIC3DLINEAR) ||
+                        (k == SVLGPU_PML2DQUAD4 && mk == SVLGPU_ELASTIC2DPLANESTRAIN);
         if (!ok) { set_error("unsupported element/material combination"); return 1; }
+        if (pml) {
+            has_pml = true;
+            const int npe = kind_npe(k), want = (k == SVLGPU_PML3DHEXA8) ? 9 : 5;
+            for (int l = 0; l < npe; l++) {
+                const int node = m->elem_conn[8ll * e + l];
+                if (m->node_ndof[node] != want) { set_error("PML element node must carry 9 (3-D) / 5 (2-D) dofs"); return 1; }
+                node_is_pml[node] = 1;
+            }
+        }
     }
+    if (has_pml && !m->halo_peers.empty()) { set_error("PML models are not partitioned across GPUs yet"); return 1; }
 
     // ---- B. element classes ---------------------------------------------------------------
     const char *tol_s = getenv("SVLGPU_CLASS_TOL");
@@ -101,6 +136,7 @@ int plan_and_upload(svlgpu_model *m) {
         std::vector<int64_t> key;
         for (int e = 0; e < nE; e++) {
             const int kind = m->elem_kind[e], npe = kind_npe(kind);
+            if (kind == SVLGPU_PML3DHEXA8 || kind == SVLGPU_PML2DQUAD4) { elem_cls[e] = -1; continue; }
             const int32_t *cn = &m->elem_conn[8ll * e];
             const double *x0 = &m->coords[(size_t)nd * cn[0]], *x1 = &m->coords[(size_t)nd * cn[1]];
             double h = 0;
@@ -160,6 +196,7 @@ int plan_and_upload(svlgpu_model *m) {
     }
     std::vector<int32_t> inc_count(nN, 0);
     for (int e = 0; e < nE; e++) {
+        if (elem_cls[e] < 0) continue;               // PML: consistent M and C, handled by the block solve
         const ElemClass &ec = classes[elem_cls[e]];
         const int npe = kind_npe(ec.kind);
         const double am = m->elem_am.empty() ? 0.0 : m->elem_am[e];
@@ -176,8 +213,11 @@ int plan_and_upload(svlgpu_model *m) {
     }
     m->h_mass = mass; m->h_cdiag = cdiag;
     std::vector<double> kinv(m->n_int, 0.0), km(m->n_int, 0.0);
+    std::vector<int32_t> node_of_dof(m->n_int);
+    for (int n = 0; n < nN; n++) for (int q = m->node_ptr[n]; q < m->node_ptr[n + 1]; q++) node_of_dof[q] = n;
     for (int q = 0; q < m->n_int; q++) {
-        if (m->freedof[q] < 0) continue;             // restrained: dU = 0 (Mesh.cpp:354-357)
+        if (m->freedof[q] < 0) continue;             // restrained: dU = 0 (Mesh.cpp:354-357); slaves follow their master
+        if (node_is_pml[node_of_dof[q]]) continue;   // advanced by the PML block solve
         const double keff = 1.0 / dt / dt * mass[q] + 1.0 / 2.0 / dt * cdiag[q];
         if (!(keff > 0.0)) { set_error("free dof without mass: Keff is singular (EigenSolver.cpp:52-55)"); return 1; }
         kinv[q] = 1.0 / keff;
@@ -389,6 +429,7 @@ int plan_and_upload(svlgpu_model *m) {
         gh.kind = SVLGPU_LIN3DHEXA8; gh.npe = 8; gh.ndofn = 3; gh.ngp = 8;
         gq.kind = SVLGPU_LIN2DQUAD4; gq.npe = 4; gq.ndofn = 2; gq.ngp = 4;
         for (int e = 0; e < nE; e++) {
+            if (elem_cls[e] < 0) continue;
             const int npe = kind_npe(m->elem_kind[e]);
             bool generic = false;
             for (int l = 0; l < npe && !generic; l++) generic = !node_done[m->elem_conn[8ll * e + l]];
@@ -445,7 +486,7 @@ int plan_and_upload(svlgpu_model *m) {
         // generic nodes and their incidences in ascending element order
         std::vector<int32_t> dof0, ndofv, ptr;
         for (int n = 0; n < nN; n++)
-            if (!node_done[n]) { gn_of[n] = (int)dof0.size(); dof0.push_back(m->node_ptr[n]); ndofv.push_back(m->node_ndof[n]); }
+            if (!node_done[n] && !node_is_pml[n]) { gn_of[n] = (int)dof0.size(); dof0.push_back(m->node_ptr[n]); ndofv.push_back(m->node_ndof[n]); }
         const int ng = (int)dof0.size();
         ptr.assign(ng + 1, 0);
         for (int e = 0; e < nE; e++) {
@@ -471,11 +512,13 @@ int plan_and_upload(svlgpu_model *m) {
     }
     // ---- E2. multi-GPU halo: interface nodes, their force sources, send order ------------------
     m->if_of_node.assign(nN, -1);
-    if (!m->halo_peers.empty()) {
+    if (!m->halo_peers.empty() || !m->constraints.empty()) {
         HaloDev &h = m->halo;
         h.nd = nd;
         std::vector<int32_t> ifn;
         for (auto &hp : m->halo_peers) ifn.insert(ifn.end(), hp.nodes.begin(), hp.nodes.end());
+        // soil nodes tied to PML nodes: their force residual feeds the PML block solve instead of a peer rank
+        for (int q = 0; q < m->n_int; q++) if (alias[q] != q) ifn.push_back(node_of_dof[alias[q]]);
         std::sort(ifn.begin(), ifn.end());
         ifn.erase(std::unique(ifn.begin(), ifn.end()), ifn.end());
         h.n_if = (int)ifn.size();
@@ -529,11 +572,14 @@ int plan_and_upload(svlgpu_model *m) {
             h.d_g_slot = dupload(m, g_slot);
         }
     }
-    auto halo_slot_of_dof = [&](int q) -> int32_t {       // internal dof -> slot in hF or -1
-        if (m->halo_peers.empty()) return -1;
-        const int node = (int)(std::upper_bound(m->node_ptr.begin(), m->node_ptr.end(), q) - m->node_ptr.begin()) - 1;
+    std::vector<int32_t> cmap;                             // internal dof -> PML unknown or -1
+    if (has_pml && plan_pml(m, alias, node_is_pml, node_of_dof, kinv, km, cmap)) return 1;
+    auto halo_slot_of_dof = [&](int q) -> int32_t {       // internal dof -> slot in hF, -2-c (PML unknown c) or -1
+        const int node = node_of_dof[q];
         const int i = m->if_of_node[node];
-        return i < 0 ? -1 : i * nd + (q - m->node_ptr[node]);
+        if (i >= 0) return i * nd + (q - m->node_ptr[node]);
+        if (!cmap.empty() && cmap[q] >= 0) return -2 - cmap[q];
+        return -1;
     };
     m->d_coords = dupload(m, m->coords);
     m->d_node_ptr = dupload(m, m->node_ptr);
@@ -676,6 +722,160 @@ int plan_and_upload(svlgpu_model *m) {
     CUDA_OK(cudaDeviceSynchronize());
     m->finalized = true;
     return 0;
+}
+
+// ---- PML block: class tables of Keff_e, Kminus_e - K_e, Kminus_e; unknown numbering; gather lists
+template <int ND>
+static int plan_pml_nd(svlgpu_model *m, const std::vector<int32_t> &alias, const std::vector<uint8_t> &node_is_pml,
+                       const std::vector<int32_t> &node_of_dof, const std::vector<double> &kinv,
+                       const std::vector<double> &km, std::vector<int32_t> &cmap) {
+    using Lay = PmlLayout<ND>;
+    constexpr int npe = Lay::npe, nn = Lay::ndofn, nde = npe * nn;
+    PmlDev &P = m->pml;
+    const int nE = (int)m->elem_kind.size();
+    const double dt = m->dt, mtol = 1e-12;               // Assembler.cpp:647,687 (Driver.hpp:1804 default)
+    const char *tol_s = getenv("SVLGPU_CLASS_TOL");
+    const double class_tol = tol_s ? atof(tol_s) : 1e-11;
+    // classes
+    std::unordered_map<uint64_t, std::vector<int>> table;
+    std::vector<std::vector<int64_t>> keys;
+    std::vector<int64_t> key;
+    std::vector<int32_t> pe, ecls;                        // PML elements (ascending), class of each
+    std::vector<double> tA, tP, tK;
+    std::vector<double> Mm(nde * nde), Cm(nde * nde), Km(nde * nde);
+    for (int e = 0; e < nE; e++) {
+        const int kind = m->elem_kind[e];
+        if (kind != SVLGPU_PML3DHEXA8 && kind != SVLGPU_PML2DQUAD4) continue;
+        const int32_t *cn = &m->elem_conn[8ll * e];
+        const double *x0 = &m->coords[(size_t)ND * cn[0]], *x1 = &m->coords[(size_t)ND * cn[1]];
+        double h = 0;
+        for (int c = 0; c < ND; c++) h += (x1[c] - x0[c]) * (x1[c] - x0[c]);
+        h = std::sqrt(h);
+        const double inv = 1.0 / (class_tol * (h > 0 ? h : 1.0));
+        const double *at = &m->elem_attr[10ll * e];
+        const double *pp = (ND == 2) ? at + 1 : at;       // n, L, R, x0, npml
+        key.clear();
+        key.push_back(kind); key.push_back(m->elem_mat[e]);
+        for (int i = 1; i < npe; i++) {
+            const double *xi = &m->coords[(size_t)ND * cn[i]];
+            for (int c = 0; c < ND; c++) key.push_back(llround((xi[c] - x0[c]) * inv));
+        }
+        key.push_back(llround(h / (class_tol * 1e3)));
+        for (int a = 0; a < 3; a++) { int64_t b; std::memcpy(&b, &pp[a], 8); key.push_back(b); }
+        if (ND == 2) { int64_t b; std::memcpy(&b, &at[0], 8); key.push_back(b); }
+        for (int c = 0; c < ND; c++) {
+            int64_t b; std::memcpy(&b, &pp[3 + ND + c], 8); key.push_back(b);
+            // only the stretched axes see x0 (the stretch is ((x - x0) n / L)^m)
+            key.push_back(pp[3 + ND + c] != 0.0 ? llround((pp[3 + c] - x0[c]) * inv * 1e-3) : 0);
+        }
+        uint64_t hsh = 1469598103934665603ull;
+        for (int64_t v : key) hsh = mix(hsh, (uint64_t)v);
+        auto &bucket = table[hsh];
+        int found = -1;
+        for (int c : bucket) if (keys[c] == key) { found = c; break; }
+        if (found < 0) {
+            found = (int)keys.size();
+            bucket.push_back(found); keys.push_back(key);
+            const Material &mat = m->materials[m->elem_mat[e]];
+            double X[npe * ND];
+            for (int i = 0; i < npe; i++) for (int c = 0; c < ND; c++) X[ND * i + c] = m->coords[(size_t)ND * cn[i] + c];
+            double *out[4] = {Mm.data(), Cm.data(), Km.data(), nullptr};
+            pml_element_matrices<ND>(X, mat.p[0], mat.p[1], mat.p[2], at, out);
+            const size_t base = tA.size();
+            tA.resize(base + nde * nde); tP.resize(base + nde * nde); tK.resize(base + nde * nde);
+            for (int i = 0; i < nde; i++)
+                for (int j = 0; j < nde; j++) {
+                    const double mm = std::fabs(Mm[i * nde + j]) > mtol ? Mm[i * nde + j] : 0.0;
+                    const double cc = std::fabs(Cm[i * nde + j]) > mtol ? Cm[i * nde + j] : 0.0;
+                    const double kp = 1.0 / dt / dt * mm + 1.0 / 2.0 / dt * cc;
+                    const double kmn = 1.0 / dt / dt * mm - 1.0 / 2.0 / dt * cc;
+                    tA[base + (size_t)j * nde + i] = kp;                      // transposed: [col][row]
+                    tK[base + (size_t)j * nde + i] = kmn;
+                    tP[base + (size_t)j * nde + i] = Km[i * nde + j];
+                }
+        }
+        pe.push_back(e); ecls.push_back(found);
+    }
+    P.present = true; P.nde = nde; P.n_elem = (int)pe.size(); P.n_cls = (int)keys.size();
+    m->n_elem_classes += P.n_cls;
+    // unknowns: free dofs of PML nodes + the soil dofs they are tied to, ascending internal dof
+    cmap.assign(m->n_int, -1);
+    std::vector<uint8_t> carrier(m->n_int, 0);
+    for (int q = 0; q < m->n_int; q++) {
+        if (!node_is_pml[node_of_dof[q]]) continue;
+        if (m->freedof[q] >= 0) carrier[q] = 1;
+        else if (alias[q] != q) carrier[alias[q]] = 1;
+    }
+    std::vector<int32_t> c_dof;
+    for (int q = 0; q < m->n_int; q++) if (carrier[q]) { cmap[q] = (int)c_dof.size(); c_dof.push_back(q); }
+    for (int q = 0; q < m->n_int; q++) if (alias[q] != q) cmap[q] = cmap[alias[q]];
+    P.nc = (int)c_dof.size();
+    std::vector<int32_t> sc_dof, sc_c;
+    for (int q = 0; q < m->n_int; q++)
+        if (cmap[q] >= 0 || node_is_pml[node_of_dof[q]]) { sc_dof.push_back(q); sc_c.push_back(cmap[q]); }
+    P.n_sc = (int)sc_dof.size();
+    // element dof tables + gather lists + diagonal
+    std::vector<int32_t> edof((size_t)P.n_elem * nde), ecd((size_t)P.n_elem * nde), cnt(P.nc + 1, 0);
+    for (int z = 0; z < P.n_elem; z++) {
+        const int32_t *cn = &m->elem_conn[8ll * pe[z]];
+        for (int l = 0; l < npe; l++)
+            for (int k = 0; k < nn; k++) {
+                const int q = m->node_ptr[cn[l]] + k;
+                edof[(size_t)z * nde + l * nn + k] = q;
+                ecd[(size_t)z * nde + l * nn + k] = cmap[q];
+                if (cmap[q] >= 0) cnt[cmap[q] + 1]++;
+            }
+    }
+    for (int c = 0; c < P.nc; c++) cnt[c + 1] += cnt[c];
+    std::vector<int32_t> slot(cnt[P.nc]), fill(cnt.begin(), cnt.end() - 1);
+    std::vector<double> diag(P.nc, 0.0), dsoil(P.nc, 0.0), kms(P.nc, 0.0);
+    std::vector<int32_t> c_hf(P.nc, -1);
+    for (int c = 0; c < P.nc; c++) {
+        const int q = c_dof[c];
+        if (!node_is_pml[node_of_dof[q]]) {
+            dsoil[c] = 1.0 / kinv[q]; kms[c] = km[q];
+            c_hf[c] = m->if_of_node[node_of_dof[q]] * ND + (q - m->node_ptr[node_of_dof[q]]);
+        }
+        diag[c] = dsoil[c];
+    }
+    for (int z = 0; z < P.n_elem; z++)
+        for (int i = 0; i < nde; i++) {
+            const int c = ecd[(size_t)z * nde + i];
+            if (c < 0) continue;
+            slot[fill[c]++] = z * nde + i;
+            diag[c] += tA[(size_t)ecls[z] * nde * nde + (size_t)i * nde + i];
+        }
+    std::vector<double> w(P.nc), scl(P.nc);
+    for (int c = 0; c < P.nc; c++) {
+        if (diag[c] == 0.0) { set_error("PML block: zero diagonal in Keff (EigenSolver.cpp:52-55 would fail too)"); return 1; }
+        scl[c] = 1.0 / std::sqrt(std::fabs(diag[c]));
+        w[c] = diag[c] > 0.0 ? scl[c] : -scl[c];          // stress rows have a negative diagonal
+    }
+    P.d_sc = dupload(m, scl);
+    P.d_A = dupload(m, tA); P.d_K = dupload(m, tP); P.d_Km = dupload(m, tK);
+    P.d_ecls = dupload(m, ecls); P.d_edof = dupload(m, edof); P.d_ecd = dupload(m, ecd);
+    P.d_ye = dalloc<double>(m, (size_t)P.n_elem * nde);
+    P.d_c_dof = dupload(m, c_dof); P.d_c_ptr = dupload(m, cnt); P.d_c_slot = dupload(m, slot); P.d_c_hf = dupload(m, c_hf);
+    P.d_diag = dupload(m, dsoil); P.d_kms = dupload(m, kms); P.d_w = dupload(m, w);
+    P.d_sc_dof = dupload(m, sc_dof); P.d_sc_c = dupload(m, sc_c);
+    double **vecs[] = {&P.d_x, &P.d_b, &P.d_bext, &P.d_r, &P.d_rh, &P.d_p, &P.d_v, &P.d_s, &P.d_t};
+    for (double **v : vecs) {
+        *v = dalloc<double>(m, P.nc);
+        if (!*v) { set_error("out of device memory (PML vectors)"); return 1; }
+        CUDA_OK(cudaMemset(*v, 0, sizeof(double) * std::max(1, P.nc)));
+    }
+    P.d_part = dalloc<double>(m, 8 * 1024);
+    CUDA_OK(cudaMemset(P.d_part, 0, sizeof(double) * 8 * 1024));
+    CUDA_OK(cudaMallocHost(&P.h_scal, sizeof(double) * 8));
+    const char *rt = getenv("SVLGPU_PML_RTOL");
+    if (rt) P.rtol = atof(rt);
+    return 0;
+}
+static int plan_pml(svlgpu_model *m, const std::vector<int32_t> &alias, const std::vector<uint8_t> &node_is_pml,
+                    const std::vector<int32_t> &node_of_dof, const std::vector<double> &kinv,
+                    const std::vector<double> &km, std::vector<int32_t> &cmap) {
+    return m->ndim == 3 ? plan_pml_nd<3>(m, alias, node_is_pml, node_of_dof, kinv, km, cmap)
+                        : plan_pml_nd<2>(m, alias, node_is_pml, node_of_dof, kinv, km, cmap);
 }
 
 }  // namespace svl

@@ -1,0 +1,313 @@
+// pml.cu -- the non-diagonal block of the "explicit" step.
+//
+// PML3DHexa8 / PML2DQuad4 ignore the lumped-mass flag (PML3DHexa8.cpp:214-285, PML2DQuad4.cpp:286-289), so
+// Keff = M/dt^2 + C/2dt couples the dofs of the PML nodes and of the soil nodes tied to them.  The reference factors
+// this sparse symmetric indefinite matrix once (EigenSolver.cpp:19-60, SimplicialLDLT) or runs PETSc BiCGStab to 1e-12
+// and back-substitutes every step; here the block is solved every step, matrix-free, by BiCGStab on the symmetrically
+// scaled, sign-flipped system  (J S Keff S) y = J S b,  x = S y,  S = |diag(Keff)|^-1/2,  J = sign(diag(Keff))  (the stress
+// rows have a negative diagonal; flipping them makes the operator positive real, and the two-sided scaling balances
+// displacement and stress unknowns, which differ by ~10 orders of magnitude).  Element products use per-class tables of Keff_e; the right-hand side
+//   b = T'(Fext - Fint + (M/dt^2 - C/2dt)(U_n - U_{n-1}))        (CentralDifference.cpp:217-220)
+// uses the class tables of K_e and Kminus_e (PML3DHexa8::ComputeInternalForces is K_e u_e, :716-743).
+// Everything is deterministic: gathers run in ascending element order, reductions have a fixed shape.
+#include <algorithm>
+#include <cstring>
+#include "model.h"
+
+namespace svl {
+
+#define CUDA_OK(x)                                                                          \
+    do {                                                                                    \
+        cudaError_t e_ = (x);                                                               \
+        if (e_ != cudaSuccess) {                                                            \
+            set_error(std::string(#x) + ": " + cudaGetErrorString(e_));                     \
+            return 1;                                                                       \
+        }                                                                                   \
+    } while (0)
+
+constexpr int kRedBlocks = 296;      // 2 per SM; every reduction writes kRedBlocks partials
+constexpr int kRedThreads = 256;
+// partial-sum slots
+enum { S_BB = 0, S_RHO = 1, S_RHV = 2, S_TS = 3, S_TT = 4, S_RR0 = 5, S_RR1 = 6, S_NSLOT = 7 };
+
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double sh[kRedThreads / 32];
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x < 32) {
+        r = (threadIdx.x < kRedThreads / 32) ? sh[threadIdx.x] : 0.0;
+        for (int o = 16; o; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+    }
+    __syncthreads();
+    return r;      // valid in thread 0
+}
+// every thread gets the full sum of one slot (fixed order -> identical in all blocks)
+__device__ __forceinline__ double slot_total(const double *part, int slot) {
+    __shared__ double tot;
+    double v = 0.0;
+    if (threadIdx.x < 32) {
+        for (int i = threadIdx.x; i < kRedBlocks; i += 32) v += part[slot * kRedBlocks + i];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) tot = v;
+    }
+    __syncthreads();
+    const double r = tot;
+    __syncthreads();
+    return r;
+}
+
+// ---- element products, one thread per (element, row) -----------------------------------------------------------
+// mode 0: ye = T1 x1                                   (operator application; x1 indexed by unknown, scaled by xs)
+// mode 1: ye = T2 (x1 - x2) - filt(T1 x1)              (right-hand side: T1 = K_e, T2 = Kminus_e, x1 = U_n, x2 = U_{n-1})
+// mode 2: ye = filt(T1 x1)                             (internal force K_e u_e)
+// filt drops components with |f| <= ftol exactly like Assembler::ComputeInternalForceVector (Assembler.cpp:262); the
+// stress rows of the PML are scaled ~1e-10, so unlike in the solids this filter is visible at the 1e-7 level.
+template <int NDE, int EPB>
+__global__ void __launch_bounds__(NDE * EPB) k_pml_elem(int n_elem, int mode, const int32_t *__restrict__ ecls,
+                                                       const int32_t *__restrict__ idx, const double *__restrict__ T1,
+                                                       const double *__restrict__ x1, const double *__restrict__ T2,
+                                                       const double *__restrict__ x2, double *__restrict__ ye,
+                                                       const double *__restrict__ xs, double ftol, const double *part,
+                                                       int rr_slot, double tol2) {
+    __shared__ double sx1[EPB][NDE], sx2[EPB][NDE];
+    if (part && slot_total(part, rr_slot) <= tol2 * slot_total(part, S_BB) + 1e-280) return;   // solver already converged
+    const int le = threadIdx.x / NDE, i = threadIdx.x - le * NDE;
+    const int e = blockIdx.x * EPB + le;
+    const bool act = e < n_elem;
+    if (act) {
+        const int q = idx[(size_t)e * NDE + i];
+        const double a = q >= 0 ? (xs ? x1[q] * xs[q] : x1[q]) : 0.0;
+        sx1[le][i] = a;
+        if (mode == 1) sx2[le][i] = a - x2[q];
+    }
+    __syncthreads();
+    if (!act) return;
+    const size_t base = (size_t)ecls[e] * NDE * NDE + i;
+    double acc = 0.0, acc2 = 0.0;
+    if (mode == 1) {
+#pragma unroll 4
+        for (int j = 0; j < NDE; j++) {
+            acc = fma(T1[base + (size_t)j * NDE], sx1[le][j], acc);
+            acc2 = fma(T2[base + (size_t)j * NDE], sx2[le][j], acc2);
+        }
+        acc = acc2 - (fabs(acc) > ftol ? acc : 0.0);
+    } else {
+#pragma unroll 4
+        for (int j = 0; j < NDE; j++) acc = fma(T1[base + (size_t)j * NDE], sx1[le][j], acc);
+        if (mode == 2 && !(fabs(acc) > ftol)) acc = 0.0;
+    }
+    ye[(size_t)e * NDE + i] = acc;
+}
+
+// ---- right-hand side: b~ = W (bext + gather(ye) + soil part);  partial ||b~||^2 ---------------------------------
+__global__ void __launch_bounds__(kRedThreads) k_pml_rhs(int nc, const int32_t *ptr, const int32_t *slot, const double *ye,
+                                                         const int32_t *c_dof, const int32_t *c_hf, const double *kms,
+                                                         const double *hF, const double *U, const double *Up,
+                                                         double *bext, const double *w, double *b, double *part) {
+    double acc = 0.0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
+        double v = bext[c];
+        bext[c] = 0.0;
+        for (int q = ptr[c]; q < ptr[c + 1]; q++) v += ye[slot[q]];
+        const int hs = c_hf[c];
+        if (hs >= 0) { const int d = c_dof[c]; v += kms[c] * (U[d] - Up[d]) - hF[hs]; }
+        v *= w[c];
+        b[c] = v;
+        acc = fma(v, v, acc);
+    }
+    const double s = block_sum(acc);
+    if (threadIdx.x == 0) part[S_BB * kRedBlocks + blockIdx.x] = s;
+}
+
+// ---- out = W (dsoil * in + gather(ye)); optional dots with up to two vectors -----------------------------------
+// mode 0: r = b - out, rh = r, p = r (initial residual), partial rho = rr = (r,r)
+// mode 1: v = out, partial (rh, v)
+// mode 2: t = out, partials (t, s), (t, t)
+__global__ void __launch_bounds__(kRedThreads) k_pml_gather(int nc, int mode, const int32_t *ptr, const int32_t *slot,
+                                                            const double *ye, const double *dsoil, const double *w,
+                                                            const double *sc, const double *in, double *out, const double *b, double *r,
+                                                            double *rh, double *p, const double *s, double *part,
+                                                            int rr_slot, double tol2) {
+    if (mode != 0 && slot_total(part, rr_slot) <= tol2 * slot_total(part, S_BB) + 1e-280) return;
+    double a0 = 0.0, a1 = 0.0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
+        double v = dsoil[c] * (sc[c] * in[c]);
+        for (int q = ptr[c]; q < ptr[c + 1]; q++) v += ye[slot[q]];
+        v *= w[c];
+        if (mode == 0) {
+            const double rv = b[c] - v;
+            r[c] = rv; rh[c] = rv; p[c] = rv;
+            a0 = fma(rv, rv, a0);
+        } else if (mode == 1) {
+            out[c] = v;
+            a0 = fma(rh[c], v, a0);
+        } else {
+            out[c] = v;
+            a0 = fma(v, s[c], a0);
+            a1 = fma(v, v, a1);
+        }
+    }
+    const double s0 = block_sum(a0);
+    const double s1 = block_sum(a1);
+    if (threadIdx.x == 0) {
+        if (mode == 0) { part[S_RHO * kRedBlocks + blockIdx.x] = s0; part[rr_slot * kRedBlocks + blockIdx.x] = s0; }
+        else if (mode == 1) part[S_RHV * kRedBlocks + blockIdx.x] = s0;
+        else { part[S_TS * kRedBlocks + blockIdx.x] = s0; part[S_TT * kRedBlocks + blockIdx.x] = s1; }
+    }
+}
+
+// scalars carried between kernels: [0] rho of the previous iteration, [1] alpha, [2] omega, [3] rho of this iteration
+// p = r + beta (p - omega v)
+__global__ void __launch_bounds__(kRedThreads) k_bicg_p(int nc, int first, const double *r, double *p, const double *v,
+                                                        double *scal, const double *part, int rr_slot, double tol2) {
+    if (slot_total(part, rr_slot) <= tol2 * slot_total(part, S_BB) + 1e-280) return;
+    const double rho = slot_total(part, S_RHO);
+    if (!first) {
+        const double beta = (rho / scal[0]) * (scal[1] / scal[2]);
+        const double omega = scal[2];
+        for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x)
+            p[c] = r[c] + beta * (p[c] - omega * v[c]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) scal[3] = rho;
+}
+// s = r - alpha v
+__global__ void __launch_bounds__(kRedThreads) k_bicg_s(int nc, const double *r, const double *v, double *s, double *scal,
+                                                        const double *part, int rr_slot, double tol2) {
+    if (slot_total(part, rr_slot) <= tol2 * slot_total(part, S_BB) + 1e-280) return;
+    const double rhv = slot_total(part, S_RHV);
+    const double alpha = scal[3] / rhv;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) s[c] = r[c] - alpha * v[c];
+    if (blockIdx.x == 0 && threadIdx.x == 0) { scal[4] = alpha; }
+}
+// x += alpha p + omega s; r = s - omega t; partial rho_next = (rh, r), rr = (r, r) into the other rr slot
+__global__ void __launch_bounds__(kRedThreads) k_bicg_x(int nc, double *x, const double *p, const double *s, const double *t,
+                                                        double *r, const double *rh, double *scal, double *part,
+                                                        int rr_slot, double tol2) {
+    const bool conv = slot_total(part, rr_slot) <= tol2 * slot_total(part, S_BB) + 1e-280;
+    const int nslot = (rr_slot == S_RR0) ? S_RR1 : S_RR0;
+    if (conv) {
+        // keep the converged flag alive in the slot the next iteration reads
+        if (threadIdx.x == 0) part[nslot * kRedBlocks + blockIdx.x] = part[rr_slot * kRedBlocks + blockIdx.x];
+        return;
+    }
+    const double tt = slot_total(part, S_TT), ts = slot_total(part, S_TS);
+    const double omega = tt > 0.0 ? ts / tt : 0.0;
+    const double alpha = scal[4];
+    double a0 = 0.0, a1 = 0.0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
+        const double sv = s[c];
+        x[c] += alpha * p[c] + omega * sv;
+        const double rv = sv - omega * t[c];
+        r[c] = rv;
+        a0 = fma(rh[c], rv, a0);
+        a1 = fma(rv, rv, a1);
+    }
+    const double s0 = block_sum(a0);
+    const double s1 = block_sum(a1);
+    if (threadIdx.x == 0) {
+        part[S_RHO * kRedBlocks + blockIdx.x] = s0;
+        part[nslot * kRedBlocks + blockIdx.x] = s1;
+        if (blockIdx.x == 0) { scal[0] = scal[3]; scal[1] = alpha; scal[2] = omega; }
+    }
+}
+__global__ void k_pml_norms(const double *part, int rr_slot, double *out) {
+    const double rr = slot_total(part, rr_slot), bb = slot_total(part, S_BB);
+    if (threadIdx.x == 0) { out[0] = rr; out[1] = bb; }
+}
+// U_{n+1} = U_n + T dU on every dof of the block (slaves take their master's increment, Mesh.cpp:360-375)
+__global__ void k_pml_scatter(int n, const int32_t *dof, const int32_t *cix, const double *x, const double *sc,
+                              const double *U, double *Un) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int d = dof[t], c = cix[t];
+    Un[d] = c >= 0 ? U[d] + sc[c] * x[c] : U[d];          // restrained dofs keep their value (Mesh.cpp:354-357)
+}
+__global__ void k_pml_fint_add(int n, const int32_t *edof, const double *ye, double *F) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    atomicAdd(&F[edof[t]], ye[t]);
+}
+
+template <int NDE, int EPB>
+static void launch_elem(svlgpu_model *m, int mode, const int32_t *idx, const double *T1, const double *x1, const double *T2,
+                        const double *x2, const double *xs, const double *part, int rr_slot, double tol2) {
+    PmlDev &P = m->pml;
+    k_pml_elem<NDE, EPB><<<(P.n_elem + EPB - 1) / EPB, NDE * EPB, 0, m->stream>>>(P.n_elem, mode, P.d_ecls, idx, T1, x1, T2, x2,
+                                                                                 P.d_ye, xs, P.ftol, part, rr_slot, tol2);
+    m->total_launches++;
+}
+static void elem_products(svlgpu_model *m, int mode, const int32_t *idx, const double *T1, const double *x1, const double *T2,
+                          const double *x2, const double *xs, const double *part, int rr_slot, double tol2) {
+    if (m->pml.nde == 72) launch_elem<72, 4>(m, mode, idx, T1, x1, T2, x2, xs, part, rr_slot, tol2);
+    else launch_elem<20, 8>(m, mode, idx, T1, x1, T2, x2, xs, part, rr_slot, tol2);
+}
+
+int pml_step(svlgpu_model *m, const double *U, const double *Up, double *Un) {
+    PmlDev &P = m->pml;
+    if (!P.present || !P.nc) return 0;
+    cudaStream_t st = m->stream;
+    const double tol2 = P.rtol * P.rtol;
+    double *scal = P.d_part + S_NSLOT * kRedBlocks;       // 8 carried scalars behind the partial slots
+    // right-hand side
+    elem_products(m, 1, P.d_edof, P.d_K, U, P.d_Km, Up, nullptr, nullptr, 0, 0.0);
+    k_pml_rhs<<<kRedBlocks, kRedThreads, 0, st>>>(P.nc, P.d_c_ptr, P.d_c_slot, P.d_ye, P.d_c_dof, P.d_c_hf, P.d_kms, m->halo.d_hF,
+                                                  U, Up, P.d_bext, P.d_w, P.d_b, P.d_part);
+    // initial residual with the previous increment as the starting guess
+    elem_products(m, 0, P.d_ecd, P.d_A, P.d_x, nullptr, nullptr, P.d_sc, nullptr, 0, 0.0);
+    int rr = S_RR0;
+    k_pml_gather<<<kRedBlocks, kRedThreads, 0, st>>>(P.nc, 0, P.d_c_ptr, P.d_c_slot, P.d_ye, P.d_diag, P.d_w, P.d_sc, P.d_x, nullptr, P.d_b,
+                                                     P.d_r, P.d_rh, P.d_p, nullptr, P.d_part, rr, tol2);
+    m->total_launches += 2;
+    int it = 0;
+    bool done = false;
+    int batch = std::max(2, std::min(P.last_iters, P.max_iter));
+    while (!done) {
+        for (int q = 0; q < batch; q++, it++) {
+            k_bicg_p<<<kRedBlocks, kRedThreads, 0, st>>>(P.nc, it == 0, P.d_r, P.d_p, P.d_v, scal, P.d_part, rr, tol2);
+            elem_products(m, 0, P.d_ecd, P.d_A, P.d_p, nullptr, nullptr, P.d_sc, P.d_part, rr, tol2);
+            k_pml_gather<<<kRedBlocks, kRedThreads, 0, st>>>(P.nc, 1, P.d_c_ptr, P.d_c_slot, P.d_ye, P.d_diag, P.d_w, P.d_sc, P.d_p, P.d_v,
+                                                             nullptr, nullptr, P.d_rh, nullptr, nullptr, P.d_part, rr, tol2);
+            k_bicg_s<<<kRedBlocks, kRedThreads, 0, st>>>(P.nc, P.d_r, P.d_v, P.d_s, scal, P.d_part, rr, tol2);
+            elem_products(m, 0, P.d_ecd, P.d_A, P.d_s, nullptr, nullptr, P.d_sc, P.d_part, rr, tol2);
+            k_pml_gather<<<kRedBlocks, kRedThreads, 0, st>>>(P.nc, 2, P.d_c_ptr, P.d_c_slot, P.d_ye, P.d_diag, P.d_w, P.d_sc, P.d_s, P.d_t,
+                                                             nullptr, nullptr, nullptr, nullptr, P.d_s, P.d_part, rr, tol2);
+            k_bicg_x<<<kRedBlocks, kRedThreads, 0, st>>>(P.nc, P.d_x, P.d_p, P.d_s, P.d_t, P.d_r, P.d_rh, scal, P.d_part, rr, tol2);
+            rr = (rr == S_RR0) ? S_RR1 : S_RR0;
+            m->total_launches += 5;
+        }
+        k_pml_norms<<<1, 32, 0, st>>>(P.d_part, rr, scal + 6);
+        CUDA_OK(cudaMemcpyAsync(P.h_scal, scal + 6, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        const double rrv = P.h_scal[0], bb = P.h_scal[1];
+        if (!(rrv == rrv)) { set_error("PML block solve broke down (NaN residual)"); return 1; }
+        if (rrv <= tol2 * bb + 1e-280) done = true;
+        else if (it >= P.max_iter) { set_error("PML block solve did not converge (LinearSystem::SolveSystem stop)"); return 1; }
+        batch = 2;
+    }
+    P.last_iters = std::max(2, it - 1);
+    P.total_iters += it; P.solves++;
+    k_pml_scatter<<<(P.n_sc + 255) / 256, 256, 0, st>>>(P.n_sc, P.d_sc_dof, P.d_sc_c, P.d_x, P.d_sc, U, Un);
+    m->total_launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// adds the PML part of Assembler::ComputeInternalForceVector (K_e u_e per element) to F (internal dof order)
+int pml_internal_force(svlgpu_model *m, const double *U, double *F) {
+    PmlDev &P = m->pml;
+    if (!P.present) return 0;
+    elem_products(m, 2, P.d_edof, P.d_K, U, nullptr, nullptr, nullptr, nullptr, 0, 0.0);
+    const int n = P.n_elem * P.nde;
+    k_pml_fint_add<<<(n + 255) / 256, 256, 0, m->stream>>>(n, P.d_edof, P.d_ye, F);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+void pml_destroy(svlgpu_model *m) {
+    if (m->pml.h_scal) cudaFreeHost(m->pml.h_scal);
+    m->pml.h_scal = nullptr;
+}
+
+}  // namespace svl

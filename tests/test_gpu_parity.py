@@ -211,6 +211,21 @@ def test_device_matches_reference_golden(oracle, name):
     assert cases.rel_err(out, g["disp"]) < cases.TOL[name]
     ref, _ = oracle.run(m)
     assert cases.rel_err(out, ref) < cases.TOL[name]
+    c = d.counters()
+    if name.startswith("pml"):
+        assert c["n_pml_elements"] > 0 and c["pml_solves"] == m.nt - 1
+        print(f"{name}: {c['n_pml_unknowns']} block unknowns, {c['pml_iterations'] / c['pml_solves']:.1f} BiCGStab iterations/step, "
+              f"err vs reference golden {cases.rel_err(out, g['disp']):.2e}")
+
+
+def test_pml_internal_force(oracle):
+    for name in ("pml2d", "pml3d"):
+        m = cases.CASES[name]()
+        rng = np.random.default_rng(3)
+        U0 = rng.uniform(-1e-3, 1e-3, m.n_total)
+        F = _device(m, U0=U0).internal_force()
+        Fref = oracle.internal_force(m, U0)
+        assert np.abs(F - Fref).max() / np.abs(Fref).max() < 1e-12
 
 
 def test_multigpu_interface_exchange():
