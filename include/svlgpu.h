@@ -93,6 +93,13 @@ int svlgpu_set_rayleigh(svlgpu_model *m, int n, const int32_t *elems, double am,
  * the block-stencil kernel there; a wrong hint is ignored, never trusted.      */
 int svlgpu_hint_structured_block(svlgpu_model *m, int node0, int nx, int ny, int nz);
 
+/* Planner / solver options, before finalize.  name: "lattice_guess" (1: without hints, guess the
+ * makeDomainVolume / makeDomainArea lattice from the connectivity -- verified like a hint; default 1),
+ * "pml_rtol" (relative residual of the PML block solve, default 1e-14), "keep_gauss" (1: keep Gauss-point
+ * strain / stress for svlgpu_get_gauss, default 0), "ftol" (Assembler.cpp:262 filter of the PML element
+ * forces, default 1e-12).                                                        */
+int svlgpu_set_option(svlgpu_model *m, const char *name, double value);
+
 /* ---- loads (replaces Assembler::ComputeExternalForceVector:290-489) ------ */
 
 /* POINTLOAD CONCENTRATED {CONSTANT|TIMESERIES}: Assembler.cpp:316-350,

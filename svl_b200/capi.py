@@ -26,7 +26,7 @@ DISP, VEL, ACCEL = 0, 1, 2
 EXPORTS = [
     "svlgpu_create", "svlgpu_destroy", "svlgpu_last_error", "svlgpu_set_nodes", "svlgpu_add_nodal_mass",
     "svlgpu_add_constraint", "svlgpu_add_material", "svlgpu_add_elements", "svlgpu_set_rayleigh",
-    "svlgpu_hint_structured_block", "svlgpu_add_point_load", "svlgpu_add_drm_load",
+    "svlgpu_hint_structured_block", "svlgpu_set_option", "svlgpu_add_point_load", "svlgpu_add_drm_load",
     "svlgpu_add_drm_planewave", "svlgpu_add_node_recorder", "svlgpu_finalize", "svlgpu_set_initial_state",
     "svlgpu_step", "svlgpu_sync", "svlgpu_step_host", "svlgpu_get_state", "svlgpu_internal_force",
     "svlgpu_get_mass_diagonal", "svlgpu_get_gauss", "svlgpu_read_recorder", "svlgpu_recorder_rows",
@@ -87,6 +87,7 @@ def load_library():
     L.svlgpu_set_kernel_timing.argtypes = [C.c_void_p, C.c_int]
     L.svlgpu_kernel_time.argtypes = [C.c_void_p, C.c_int, _dp, C.POINTER(C.c_int64), C.c_int]
     L.svlgpu_device_ptr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    L.svlgpu_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
     L.svlgpu_add_halo.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip]
     L.svlgpu_nccl_unique_id.argtypes = [C.c_void_p]
     L.svlgpu_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
@@ -119,7 +120,7 @@ class DeviceModel:
     """One model on one GPU, driven through the C ABI."""
 
     def __init__(self, m: Model, device: int = 0, max_rows: int | None = None, fields=(DISP,),
-                 U0=None, V0=None, A0=None, comm=None):
+                 U0=None, V0=None, A0=None, comm=None, options=None):
         """comm = (rank, nranks, unique_id_bytes) joins the NCCL communicator after finalize; the
         model's `.halos` ({peer: local node indices}, svl_b200.partition) are registered before it."""
         self.L = load_library()
@@ -163,6 +164,10 @@ class DeviceModel:
                 idx = A(np.nonzero(m.elem_am == am)[0], np.int32)
                 ak = float(m.elem_ak[idx[0]]) if m.elem_ak is not None else 0.0
                 self._ck(self.L.svlgpu_set_rayleigh(self.h, len(idx), _i(idx), float(am), ak))
+        opts = {"lattice_guess": 0.0} if not m.blocks else {}      # a model without lattice hints asks for the generic path
+        opts.update(options or {})
+        for k, v in opts.items():
+            self._ck(self.L.svlgpu_set_option(self.h, k.encode(), float(v)))
         for (n0, nx, ny, nz) in m.blocks:
             self._ck(self.L.svlgpu_hint_structured_block(self.h, n0, nx, ny, nz))
         for pl in m.point_loads:

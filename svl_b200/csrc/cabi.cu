@@ -153,6 +153,19 @@ int svlgpu_set_rayleigh(svlgpu_model *m, int n, const int32_t *elems, double am,
     GUARD_END
 }
 
+int svlgpu_set_option(svlgpu_model *m, const char *name, double value) {
+    GUARD_BEGIN
+    REQUIRE(m && name && !m->finalized, "set_option: model missing or already finalized");
+    const std::string n(name);
+    if (n == "lattice_guess") m->opt_lattice_guess = value != 0.0;
+    else if (n == "keep_gauss") m->opt_keep_gauss = value != 0.0;
+    else if (n == "pml_rtol") { REQUIRE(value > 0.0 && value < 1.0, "set_option: pml_rtol out of range"); m->pml.rtol = value; }
+    else if (n == "ftol") { REQUIRE(value >= 0.0, "set_option: ftol must be >= 0"); m->pml.ftol = value; }
+    else { set_error("set_option: unknown option " + n); return 1; }
+    return 0;
+    GUARD_END
+}
+
 int svlgpu_hint_structured_block(svlgpu_model *m, int node0, int nx, int ny, int nz) {
     GUARD_BEGIN
     REQUIRE(m && !m->finalized, "hint: model missing or finalized");

@@ -181,6 +181,7 @@ struct svlgpu_model {
     std::vector<svl::Recorder> recorders;
     std::vector<svl::BlockHint> hints;
     std::vector<double> U0, V0, A0;
+    bool opt_lattice_guess = true, opt_keep_gauss = false;
 
     // ---- plan / device state ----
     bool finalized = false;

@@ -227,6 +227,30 @@ int plan_and_upload(svlgpu_model *m) {
     m->d_km = dupload(m, km);
 
     // ---- D. lattice blocks -> node classes ------------------------------------------------
+    // Without a hint (e.g. a model that arrives through the reference's JSON files) guess the lattice of
+    // makeDomainVolume / makeDomainArea (Builder.py:134-183) from the first solid element; like any hint the
+    // guess is verified cell by cell below and silently dropped where it does not hold.
+    if (m->hints.empty() && m->opt_lattice_guess) {
+        for (int e = 0; e < nE; e++) {
+            if (elem_cls[e] < 0) continue;
+            const int32_t *cn = &m->elem_conn[8ll * e];
+            int n0 = nN;
+            for (int e2 = 0; e2 < nE; e2++) if (elem_cls[e2] >= 0) { n0 = std::min(n0, m->elem_conn[8ll * e2]); }
+            int nsolid = 0;
+            while (n0 + nsolid < nN && m->node_ndof[n0 + nsolid] == nd && !node_is_pml[n0 + nsolid]) nsolid++;
+            const int sx = cn[3] - cn[0];
+            if (cn[1] != cn[0] + 1 || sx < 2) break;
+            if (nd == 3) {
+                const int sy = cn[4] - cn[0];
+                if (sy < 2 * sx || sy % sx || nsolid % sy) break;
+                m->hints.push_back({n0, sx, sy / sx, nsolid / sy});
+            } else {
+                if (nsolid % sx) break;
+                m->hints.push_back({n0, sx, nsolid / sx, 1});
+            }
+            break;
+        }
+    }
     std::vector<uint8_t> node_done(nN, 0);           // 1 = advanced by a block-stencil kernel
     for (const BlockHint &h : m->hints) {
         const bool is3 = (nd == 3);
@@ -455,7 +479,7 @@ int plan_and_upload(svlgpu_model *m) {
     m->d_fe_arena = dalloc<double>(m, (size_t)arena);
     if (!m->d_fe_arena) { set_error("out of device memory (fe arena)"); return 1; }
     CUDA_OK(cudaMemset(m->d_fe_arena, 0, sizeof(double) * (size_t)std::max<long long>(arena, 1)));
-    const bool want_gp = getenv("SVLGPU_KEEP_GAUSS") != nullptr;
+    const bool want_gp = m->opt_keep_gauss || getenv("SVLGPU_KEEP_GAUSS") != nullptr;
     for (size_t s = 0; s < m->gsets.size(); s++) {
         GenericSet &g = m->gsets[s];
         if (!g.n) continue;

@@ -1,0 +1,429 @@
+// svl_host.cpp -- the reference's run-time, re-hosted on libsvlgpu (C++17, no third-party dependencies).
+//
+//   SeismoVLAB_gpu.exe -dir <Partition dir> -file '<name>.$.json'
+//
+// keeps the outer boundary of SeismoVLAB.exe verbatim: the same command line
+// (12-Utilities/Utilities.hpp:97-161; '$' -> rank, Driver.hpp:250-276), the same per-rank JSON partition files
+// written by 01-Pre_Process (schema: Driver.hpp:1981-2046), the same time-series / .drm text files
+// (Driver.hpp:1514-1527, 1689-1721) and the same NODE recorder files under <dir>/../Solution/<combo>/
+// (12-Utilities/Recorder.cpp:73-105, 239-269).  Inside, the reference's class surface is kept as thin host
+// classes (Mesh, Node, Element, Material, Load, LoadCombo, Recorder, Assembler, CentralDifference, Linear,
+// DynamicAnalysis) whose hot methods forward to the C ABI of include/svlgpu.h; no physics is computed here.
+// Error convention as in the reference: methods return `true` to stop (Integrator::ComputeNewStep etc.).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <strings.h>
+#include <vector>
+
+#include "../../include/svlgpu.h"
+#include "json.hpp"
+
+using svlhost::JValue;
+
+namespace {
+
+bool ieq(const std::string &a, const char *b) { return strcasecmp(a.c_str(), b) == 0; }
+
+// numeric-tag view of a JSON object, ascending tag (the reference's std::map<unsigned int, ...> order)
+std::vector<std::pair<long, const JValue *>> by_tag(const JValue &o) {
+    std::vector<std::pair<long, const JValue *>> v;
+    for (auto &kv : o.obj) v.push_back({std::strtol(kv.first.c_str(), nullptr, 10), &kv.second});
+    std::sort(v.begin(), v.end(), [](auto &a, auto &b) { return a.first < b.first; });
+    return v;
+}
+
+// ---- Geometry module (01-Node ... 06-Mesh): plain data, the device owns the arithmetic ----------------------
+struct Node {            // 01-Node/Node.cpp:3-21
+    unsigned tag; int index; int ndof;
+    std::vector<int> total, free;
+    std::vector<double> coords;
+};
+struct Material { unsigned tag; int index; int kind; std::vector<double> par; };      // 02-Materials/Material.hpp
+struct Element {         // 04-Elements/Element.hpp:51-249
+    unsigned tag; int index; int kind; std::vector<unsigned> conn; unsigned material; std::vector<double> attr;
+};
+struct Load {            // 05-Loads/Load.cpp
+    unsigned tag; bool drm = false;
+    std::vector<unsigned> nodes, elements;
+    std::vector<double> dir, series;
+    std::string drm_pattern;
+};
+struct LoadCombo { unsigned tag; std::string name, folder; std::vector<unsigned> loads; std::vector<double> factors; };
+struct RecorderSpec { std::string name, file, resp; int precision = 6, nsample = 1; std::vector<unsigned> ids; };
+
+class Mesh {             // 06-Mesh/Mesh.cpp
+  public:
+    int ndim = 3, ntotal = 0, nfree = 0;
+    bool lumped = true;
+    std::map<unsigned, Node> Nodes;
+    std::map<unsigned, Material> Materials;
+    std::map<unsigned, Element> Elements;
+    std::map<unsigned, Load> Loads;
+    std::map<long, std::tuple<int, std::vector<int>, std::vector<double>>> Constraints;   // tag -> slave total, master free, factor
+    std::map<unsigned, std::vector<double>> Masses;
+    std::map<unsigned, std::pair<double, double>> Rayleigh;                               // element tag -> (am, ak)
+};
+
+// ---- Driver (12-Utilities/Driver.hpp UpdateMesh :1981-2046) ------------------------------------------------------------
+bool UpdateMesh(Mesh &mesh, const JValue &J) {
+    const JValue &G = J["Global"];
+    mesh.ndim = G["ndim"].as_int(3);
+    mesh.ntotal = G["ntotal"].as_int();
+    mesh.nfree = G["nfree"].as_int();
+    mesh.lumped = ieq(G["massform"].as_string("LUMPED"), "LUMPED");
+    int idx = 0;
+    for (auto &kv : by_tag(J["Nodes"])) {
+        Node n;
+        n.tag = (unsigned)kv.first; n.index = idx++;
+        n.ndof = (*kv.second)["ndof"].as_int();
+        for (auto &v : (*kv.second)["totaldof"].arr) n.total.push_back(v.as_int());
+        for (auto &v : (*kv.second)["freedof"].arr) n.free.push_back(v.as_int());
+        for (auto &v : (*kv.second)["coords"].arr) n.coords.push_back(v.as_double());
+        mesh.Nodes[n.tag] = n;
+    }
+    idx = 0;
+    for (auto &kv : by_tag(J["Materials"])) {
+        Material m;
+        m.tag = (unsigned)kv.first; m.index = idx++;
+        const std::string name = (*kv.second)["name"].as_string();
+        const JValue &a = (*kv.second)["attributes"];
+        if (ieq(name, "ELASTIC3DLINEAR")) { m.kind = SVLGPU_ELASTIC3DLINEAR; m.par = {a["E"].as_double(), a["nu"].as_double(), a["rho"].as_double()}; }
+        else if (ieq(name, "ELASTIC2DPLANESTRAIN")) { m.kind = SVLGPU_ELASTIC2DPLANESTRAIN; m.par = {a["E"].as_double(), a["nu"].as_double(), a["rho"].as_double()}; }
+        else if (ieq(name, "PLASTIC3DJ2")) { m.kind = SVLGPU_PLASTIC3DJ2; m.par = {a["K"].as_double(), a["G"].as_double(), a["rho"].as_double(), a["h"].as_double(), a["beta"].as_double(), a["Sy"].as_double()}; }
+        else { std::cout << "\x1B[31m ERROR: \x1B[0mmaterial " << name << " is not on the GPU explicit path\n"; return true; }
+        mesh.Materials[m.tag] = m;
+    }
+    for (auto &kv : by_tag(J["Masses"])) {
+        std::vector<double> v;
+        for (auto &x : (*kv.second)["mass"].arr) v.push_back(x.as_double());
+        mesh.Masses[(unsigned)kv.first] = v;
+    }
+    for (auto &kv : J["Constraints"].obj) {
+        const long tag = std::strtol(kv.first.c_str(), nullptr, 10);
+        std::vector<int> mt; std::vector<double> f;
+        for (auto &x : kv.second["mtag"].arr) mt.push_back(x.as_int());
+        for (auto &x : kv.second["factor"].arr) f.push_back(x.as_double());
+        mesh.Constraints[tag] = std::make_tuple(kv.second["stag"].as_int(), mt, f);
+    }
+    idx = 0;
+    for (auto &kv : by_tag(J["Elements"])) {
+        Element e;
+        e.tag = (unsigned)kv.first; e.index = idx++;
+        const std::string name = (*kv.second)["name"].as_string();
+        const JValue &a = (*kv.second)["attributes"];
+        for (auto &v : (*kv.second)["conn"].arr) e.conn.push_back((unsigned)v.as_int());
+        e.material = (unsigned)a["material"].as_int();
+        auto vec = [&](const char *k) { for (auto &x : a[k].arr) e.attr.push_back(x.as_double()); };
+        if (ieq(name, "LIN3DHEXA8")) e.kind = SVLGPU_LIN3DHEXA8;
+        else if (ieq(name, "LIN2DQUAD4")) { e.kind = SVLGPU_LIN2DQUAD4; e.attr = {a["th"].as_double(1.0)}; }
+        else if (ieq(name, "PML3DHEXA8")) { e.kind = SVLGPU_PML3DHEXA8; e.attr = {a["n"].as_double(), a["L"].as_double(), a["R"].as_double()}; vec("x0"); vec("npml"); }
+        else if (ieq(name, "PML2DQUAD4")) { e.kind = SVLGPU_PML2DQUAD4; e.attr = {a["th"].as_double(1.0), a["n"].as_double(), a["L"].as_double(), a["R"].as_double()}; vec("x0"); vec("npml"); }
+        else { std::cout << "\x1B[31m ERROR: \x1B[0melement " << name << " is not on the GPU explicit path\n"; return true; }
+        mesh.Elements[e.tag] = e;
+    }
+    for (auto &kv : by_tag(J["Dampings"])) {
+        const std::string name = (*kv.second)["name"].as_string();
+        const JValue &a = (*kv.second)["attributes"];
+        if (ieq(name, "RAYLEIGH"))
+            for (auto &x : a["list"].arr) mesh.Rayleigh[(unsigned)x.as_int()] = {a["am"].as_double(), a["ak"].as_double()};
+    }
+    for (auto &kv : by_tag(J["Loads"])) {
+        Load l;
+        l.tag = (unsigned)kv.first;
+        const std::string name = (*kv.second)["name"].as_string();
+        const JValue &a = (*kv.second)["attributes"];
+        if (ieq(name, "POINTLOAD")) {
+            if (!ieq(a["type"].as_string(), "CONCENTRATED")) { std::cout << "\x1B[31m ERROR: \x1B[0monly CONCENTRATED point loads are on the GPU explicit path\n"; return true; }
+            for (auto &x : a["list"].arr) l.nodes.push_back((unsigned)x.as_int());
+            for (auto &x : a["dir"].arr) l.dir.push_back(x.as_double());
+            if (ieq(a["name"].as_string(), "CONSTANT")) l.series = {a["mag"].as_double()};
+            else {
+                std::ifstream f(a["file"].as_string());                     // Driver.hpp:1514-1527
+                unsigned nt = 0;
+                if (f.is_open()) { f >> nt; l.series.resize(nt); for (unsigned j = 0; j < nt; j++) f >> l.series[j]; }
+                if (l.series.empty()) { std::cout << "\x1B[31m ERROR: \x1B[0mcannot read load file " << a["file"].as_string() << "\n"; return true; }
+            }
+        } else if (ieq(name, "ELEMENTLOAD") && ieq(a["type"].as_string(), "GENERALWAVE")) {
+            l.drm = true;
+            for (auto &x : a["list"].arr) l.elements.push_back((unsigned)x.as_int());
+            l.drm_pattern = a["file"].as_string();
+        } else { std::cout << "\x1B[31m ERROR: \x1B[0mload " << name << " is not on the GPU explicit path\n"; return true; }
+        mesh.Loads[l.tag] = l;
+    }
+    return false;
+}
+
+// ---- Assembler (07-Assembler/Assembler.cpp): host-vector access to the device passes -------------------------------
+class Assembler {
+  public:
+    explicit Assembler(svlgpu_model *h, int ntotal) : h(h), n(ntotal) {}
+    bool ComputeInternalForceVector(std::vector<double> &F) { F.assign(n, 0.0); return svlgpu_internal_force(h, F.data()) != 0; }   // :239-269
+    bool ComputeMassMatrix(std::vector<double> &Mdiag) { Mdiag.assign(n, 0.0); return svlgpu_get_mass_diagonal(h, Mdiag.data()) != 0; }   // :47-67 (lumped)
+  private:
+    svlgpu_model *h; int n;
+};
+
+// ---- Integrator (10-Integrators/02-CentralDifference/CentralDifference.cpp) -----------------------------------------
+class CentralDifference {
+  public:
+    CentralDifference(Mesh &mesh, double dt) : mesh(mesh), dt(dt) {}
+    ~CentralDifference() { if (h) svlgpu_destroy(h); }
+    svlgpu_model *handle() { return h; }
+
+    // CentralDifference::Initialize (:35-71) + Mesh::Initialize: hands the object graph to the device
+    bool Initialize(const LoadCombo &combo, const std::vector<RecorderSpec> &recs, int nt, int device) {
+        h = svlgpu_create(mesh.ndim, mesh.lumped ? 1 : 0);
+        if (!h) return fail();
+        std::vector<int32_t> ndof, total, freed;
+        std::vector<double> xyz;
+        for (auto &kv : mesh.Nodes) {
+            const Node &n = kv.second;
+            ndof.push_back(n.ndof);
+            total.insert(total.end(), n.total.begin(), n.total.end());
+            freed.insert(freed.end(), n.free.begin(), n.free.end());
+            for (int c = 0; c < mesh.ndim; c++) xyz.push_back(c < (int)n.coords.size() ? n.coords[c] : 0.0);
+        }
+        if (svlgpu_set_nodes(h, (int)ndof.size(), ndof.data(), xyz.data(), total.data(), freed.data(), mesh.ntotal, mesh.nfree)) return fail();
+        for (auto &kv : mesh.Masses) {
+            const int32_t node = mesh.Nodes.at(kv.first).index;
+            if (svlgpu_add_nodal_mass(h, 1, &node, kv.second.data())) return fail();
+        }
+        for (auto &kv : mesh.Constraints) {
+            auto &[stag, mt, f] = kv.second;
+            std::vector<int32_t> m32(mt.begin(), mt.end());
+            if (svlgpu_add_constraint(h, (int)kv.first, stag, (int)m32.size(), m32.data(), f.data())) return fail();
+        }
+        for (auto &kv : mesh.Materials)
+            if (svlgpu_add_material(h, kv.second.kind, kv.second.par.data(), (int)kv.second.par.size()) < 0) return fail();
+        // elements in ascending tag order (Assembler.cpp:251), one call per run of equal kind
+        auto it = mesh.Elements.begin();
+        while (it != mesh.Elements.end()) {
+            const int kind = it->second.kind;
+            const int nattr = (int)it->second.attr.size();
+            std::vector<int32_t> conn, mat;
+            std::vector<double> attr;
+            auto jt = it;
+            for (; jt != mesh.Elements.end() && jt->second.kind == kind; ++jt) {
+                for (unsigned n : jt->second.conn) conn.push_back(mesh.Nodes.at(n).index);
+                mat.push_back(mesh.Materials.at(jt->second.material).index);
+                attr.insert(attr.end(), jt->second.attr.begin(), jt->second.attr.end());
+            }
+            if (svlgpu_add_elements(h, kind, (int)mat.size(), conn.data(), mat.data(), nattr ? attr.data() : nullptr, nattr) < 0) return fail();
+            it = jt;
+        }
+        {   // Rayleigh damping groups (lin3DHexa8.cpp:354-366)
+            std::map<std::pair<double, double>, std::vector<int32_t>> groups;
+            for (auto &kv : mesh.Rayleigh) groups[kv.second].push_back(mesh.Elements.at(kv.first).index);
+            for (auto &g : groups)
+                if (svlgpu_set_rayleigh(h, (int)g.second.size(), g.second.data(), g.first.first, g.first.second)) return fail();
+        }
+        // loads of the active combination (Assembler::ComputeExternalForceVector :290-489)
+        for (size_t q = 0; q < combo.loads.size(); q++) {
+            const Load &l = mesh.Loads.at(combo.loads[q]);
+            const double factor = q < combo.factors.size() ? combo.factors[q] : 1.0;
+            if (!l.drm) {
+                std::vector<int32_t> nodes;
+                for (unsigned n : l.nodes) nodes.push_back(mesh.Nodes.at(n).index);
+                std::vector<double> dir = l.dir;
+                dir.resize(3, 0.0);
+                if (svlgpu_add_point_load(h, (int)nodes.size(), nodes.data(), 3, dir.data(), (int)l.series.size(), l.series.data(), factor)) return fail();
+            } else if (AddDomainReduction(l, factor)) return true;
+        }
+        for (auto &r : recs) {
+            std::vector<int32_t> nodes;
+            for (unsigned id : r.ids) nodes.push_back(mesh.Nodes.at(id).index);
+            const int field = ieq(r.resp, "DISP") ? SVLGPU_DISP : ieq(r.resp, "VEL") ? SVLGPU_VEL : SVLGPU_ACCEL;
+            if (svlgpu_add_node_recorder(h, field, (int)nodes.size(), nodes.data(), nt) < 0) return fail();
+        }
+        if (svlgpu_finalize(h, dt, device)) return fail();
+        return false;
+    }
+
+    // Integrator::ComputeNewStep (:123-152): the whole step (effective force, diagonal / block solve, state update,
+    // CommitState, recorder row) happens on the device
+    bool ComputeNewStep(unsigned k) { return svlgpu_step(h, (int)k, (int)k + 1, 0) != 0 && fail(); }
+    bool ComputeSteps(unsigned k0, unsigned k1) { return svlgpu_step(h, (int)k0, (int)k1, 1) != 0 && fail(); }
+    bool GetDisplacements(std::vector<double> &U) { U.assign(mesh.ntotal, 0.0); return svlgpu_get_state(h, SVLGPU_DISP, nullptr, 0, U.data()) != 0; }
+    bool GetVelocities(std::vector<double> &V) { V.assign(mesh.ntotal, 0.0); return svlgpu_get_state(h, SVLGPU_VEL, nullptr, 0, V.data()) != 0; }
+    bool GetAccelerations(std::vector<double> &A) { A.assign(mesh.ntotal, 0.0); return svlgpu_get_state(h, SVLGPU_ACCEL, nullptr, 0, A.data()) != 0; }
+
+  private:
+    bool fail() { std::cout << "\x1B[31m ERROR: \x1B[0m" << svlgpu_last_error() << "\n"; return true; }
+
+    // ELEMENTLOAD GENERALWAVE: one .drm text file per node, `nt nFields cond` then nt rows (Driver.hpp:1689-1721)
+    bool AddDomainReduction(const Load &l, double factor) {
+        std::map<unsigned, bool> nodes;
+        std::vector<int32_t> elems;
+        for (unsigned e : l.elements) {
+            const Element &el = mesh.Elements.at(e);
+            elems.push_back(el.index);
+            for (unsigned n : el.conn) nodes[n] = true;
+        }
+        std::vector<int32_t> nidx;
+        std::vector<uint8_t> ext;
+        std::vector<double> field;
+        unsigned nt0 = 0;
+        const unsigned nf = 3 * (unsigned)mesh.ndim;
+        for (auto &kv : nodes) {
+            std::string file = l.drm_pattern;
+            const size_t pos = file.find('$');
+            if (pos != std::string::npos) file.replace(pos, 1, std::to_string(kv.first));
+            std::ifstream f(file);
+            if (!f.is_open()) { std::cout << "\x1B[31m ERROR: \x1B[0mcannot read DRM file " << file << "\n"; return true; }
+            unsigned nt = 0, nFields = 0; int cond = 0;
+            f >> nt >> nFields >> cond;
+            if (nFields != nf || (nt0 && nt != nt0)) { std::cout << "\x1B[31m ERROR: \x1B[0minconsistent DRM file " << file << "\n"; return true; }
+            nt0 = nt;
+            const size_t base = field.size();
+            field.resize(base + (size_t)nt * nf);
+            for (size_t i = 0; i < (size_t)nt * nf; i++) f >> field[base + i];
+            nidx.push_back(mesh.Nodes.at(kv.first).index);
+            ext.push_back(cond ? 1 : 0);
+        }
+        if (svlgpu_add_drm_load(h, (int)elems.size(), elems.data(), (int)nidx.size(), nidx.data(), ext.data(), (int)nt0, field.data(), factor)) return fail();
+        return false;
+    }
+
+    Mesh &mesh;
+    double dt;
+    svlgpu_model *h = nullptr;
+};
+
+// ---- Recorder (12-Utilities/Recorder.cpp): NODE files in the reference's text layout -----------------------------------
+class Recorder {
+  public:
+    Recorder(const RecorderSpec &s, int id) : spec(s), id(id) {}
+    void Initialize(const Mesh &mesh, const std::string &dir, const std::string &combo, unsigned nsteps) {     // :57-105
+        out.open(dir + "/../Solution/" + combo + "/" + spec.file);
+        out.precision(spec.precision);
+        out.setf(std::ios::scientific);
+        unsigned ndofs = 0;
+        for (unsigned idn : spec.ids) ndofs += mesh.Nodes.at(idn).ndof;
+        out << spec.ids.size() << " " << ndofs << " " << mesh.ntotal << " " << nsteps << "\n";
+        for (unsigned idn : spec.ids) {
+            const Node &n = mesh.Nodes.at(idn);
+            out << idn << " " << n.ndof;
+            for (int d : n.total) out << " " << d;
+            out << "\n";
+        }
+    }
+    bool WriteResponse(svlgpu_model *h) {                                                                   // :239-269
+        const int rows = svlgpu_recorder_rows(h, id), w = svlgpu_recorder_width(h, id);
+        std::vector<double> buf((size_t)std::max(rows, 0) * std::max(w, 0));
+        if (rows > 0 && svlgpu_read_recorder(h, id, 0, rows, buf.data())) return true;
+        for (int r = 0; r < rows; r++) {
+            for (int c = 0; c < w; c++) out << buf[(size_t)r * w + c] << " ";
+            out << "\n";
+        }
+        return false;
+    }
+    void Finalize() { out.close(); }
+  private:
+    RecorderSpec spec; int id; std::ofstream out;
+};
+
+// ---- Analysis (08-Analysis/02-Dynamic/DynamicAnalysis.cpp:25-64) ----------------------------------------------------------
+class DynamicAnalysis {
+  public:
+    DynamicAnalysis(Mesh &mesh, CentralDifference &integ, std::vector<Recorder> &recs, unsigned nt) : mesh(mesh), integ(integ), recs(recs), nt(nt) {}
+    bool Analyze(const std::string &dir, const LoadCombo &combo) {
+        for (auto &r : recs) r.Initialize(mesh, dir, combo.folder, nt);
+        // k = 1 .. nt-1 (DynamicAnalysis.cpp:36): recorder rows are kept on the device and written at the end
+        bool stop = false;
+        const unsigned chunk = 256;
+        for (unsigned k = 1; k < nt && !stop; k += chunk) {
+            stop = integ.ComputeSteps(k, std::min(nt, k + chunk));
+            std::cout << "\r RUNNING (" << combo.name << ") : " << std::min(100u, 100 * std::min(nt, k + chunk) / std::max(1u, nt - 1)) << "%" << std::flush;
+        }
+        std::cout << "\n";
+        for (auto &r : recs) { stop = r.WriteResponse(integ.handle()) || stop; r.Finalize(); }
+        return stop;
+    }
+  private:
+    Mesh &mesh; CentralDifference &integ; std::vector<Recorder> &recs; unsigned nt;
+};
+
+std::string read_file(const std::string &path) {
+    std::ifstream f(path);
+    if (!f.is_open()) throw std::runtime_error("cannot open " + path);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    return ss.str();
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    std::string dir = ".";
+    std::vector<std::string> files;
+    for (int i = 1; i < argc; i++) {                                     // Utilities.hpp:97-161
+        if (ieq(argv[i], "-dir") && i + 1 < argc) dir = argv[++i];
+        else if (ieq(argv[i], "-file")) { while (i + 1 < argc && argv[i + 1][0] != '-') files.push_back(argv[++i]); }
+    }
+    if (files.empty()) { std::cout << " usage: SeismoVLAB_gpu.exe -dir <Partition dir> -file '<name>.$.json'\n"; return 1; }
+    const char *rk = getenv("RANK"), *lr = getenv("LOCAL_RANK");
+    const int rank = rk ? atoi(rk) : 0, device = lr ? atoi(lr) : 0;
+    try {
+        for (std::string file : files) {                                 // staged analyses run in sequence (Driver.hpp:2058-2100)
+            const size_t pos = file.find('$');
+            if (pos != std::string::npos) file.replace(pos, 1, std::to_string(rank));
+            const std::string text = read_file(dir + "/" + file);
+            const JValue J = svlhost::JParser(text).parse();
+            Mesh mesh;
+            if (UpdateMesh(mesh, J)) return 1;
+            // combination / recorders / simulation (Driver.hpp:1930-1975, 1859-1925, 1748-1856)
+            const JValue &S = J["Simulations"];
+            const unsigned comboTag = (unsigned)S["combo"].as_int(1);
+            const JValue &C = J["Combinations"][std::to_string(comboTag)];
+            LoadCombo combo;
+            combo.tag = comboTag; combo.name = C["name"].as_string("Combo");
+            combo.folder = C["attributes"]["folder"].as_string(combo.name);
+            for (auto &x : C["attributes"]["load"].arr) combo.loads.push_back((unsigned)x.as_int());
+            for (auto &x : C["attributes"]["factor"].arr) combo.factors.push_back(x.as_double());
+            const JValue &A = S["attributes"];
+            if (!ieq(A["analysis"]["name"].as_string(), "DYNAMIC") || !ieq(A["integrator"]["name"].as_string(), "CENTRALDIFFERENCE") ||
+                !ieq(A["algorithm"]["name"].as_string(), "LINEAR")) {
+                std::cout << "\x1B[31m ERROR: \x1B[0monly DYNAMIC + LINEAR + CENTRALDIFFERENCE is on the GPU explicit path\n";
+                return 1;
+            }
+            const unsigned nt = (unsigned)A["analysis"]["nt"].as_int();
+            const double dt = A["integrator"]["dt"].as_double();
+            std::vector<RecorderSpec> specs;
+            for (auto &kv : by_tag(J["Recorders"])) {
+                RecorderSpec r;
+                r.name = (*kv.second)["name"].as_string();
+                if (!ieq(r.name, "NODE")) { std::cout << " WARNING: recorder " << r.name << " is not written by the GPU path\n"; continue; }
+                r.file = (*kv.second)["file"].as_string();
+                r.resp = (*kv.second)["resp"].as_string("disp");
+                if (ieq(r.resp, "REACTION")) { std::cout << " WARNING: REACTION recorder skipped\n"; continue; }
+                r.precision = (*kv.second)["ndps"].as_int(6);
+                r.nsample = (*kv.second)["nsamp"].as_int(1);
+                for (auto &x : (*kv.second)["list"].arr) r.ids.push_back((unsigned)x.as_int());
+                specs.push_back(r);
+            }
+            CentralDifference integrator(mesh, dt);
+            if (integrator.Initialize(combo, specs, (int)nt, device)) return 1;
+            std::vector<Recorder> recorders;
+            for (size_t i = 0; i < specs.size(); i++) recorders.emplace_back(specs[i], (int)i);
+            DynamicAnalysis analysis(mesh, integrator, recorders, nt);
+            if (analysis.Analyze(dir, combo)) { std::cout << "\x1B[31m ERROR: \x1B[0mthe analysis stopped: " << svlgpu_last_error() << "\n"; return 1; }
+            svlgpu_counters c;
+            svlgpu_get_counters(integrator.handle(), &c);
+            std::cout << " elements " << c.n_elements << ", lattice nodes " << c.n_block_nodes << ", Gauss-point elements "
+                      << c.n_generic_elements << ", PML unknowns " << c.n_pml_unknowns << ", kernel launches " << c.total_launches << "\n";
+        }
+    } catch (const std::exception &e) {
+        std::cout << "\x1B[31m ERROR: \x1B[0m" << e.what() << "\n";
+        return 1;
+    }
+    return 0;
+}

@@ -244,3 +244,33 @@ def test_multigpu_interface_exchange():
                         os.path.join(root, "tests", "multigpu_check.py")], capture_output=True, text=True, timeout=900)
     print(r.stdout[-4000:], r.stderr[-2000:])
     assert r.returncode == 0
+
+
+# ---- the reference's command line / file formats on top of the C ABI (svl_b200/host) ----------------------
+@pytest.mark.parametrize("name", ["kat444", "quad4_area", "drm_box", "j2_column", "hex8_layered_rayleigh", "pml2d", "pml3d"])
+def test_host_driver_reads_reference_files_and_writes_reference_recorders(tmp_path, name):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "svl_b200", "SeismoVLAB_gpu.exe")
+    assert os.path.exists(exe), "run __graft_entry__.build() first"
+    m = cases.CASES[name]()
+    g = np.load(os.path.join(root, "tests", "golden", f"{name}.npz"))
+    part = M.write_reference_json(m, str(tmp_path), "Case", "Run", resp=("disp",), ndps=17)
+    r = subprocess.run([exe, "-dir", part, "-file", "Case.1.$.json"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out_file = os.path.join(str(tmp_path), "Solution", "Run", "disp.0.out")
+    head = open(out_file).readline().split()
+    assert int(head[0]) == len(m.rec_nodes) and int(head[2]) == m.n_total and int(head[3]) == m.nt   # Recorder.cpp:92
+    out = M.read_node_recorder(out_file)
+    assert out.shape == g["disp"].shape
+    assert cases.rel_err(out, g["disp"]) < cases.TOL[name]
+    if name == "kat444":
+        assert "lattice nodes 125" in r.stdout          # the planner recognised the makeDomainVolume lattice by itself
+    # when the reference executable travelled to this box, run it on the very same files and compare the text outputs
+    ref_exe = os.path.join(root, "oracle", "_ref", "SeismoVLAB.exe")
+    if os.path.exists(ref_exe):
+        os.rename(out_file, out_file + ".gpu")
+        subprocess.run([ref_exe, "-dir", part, "-file", "Case.1.$.json"], stdout=subprocess.DEVNULL, check=True, timeout=600)
+        ref = M.read_node_recorder(out_file)
+        assert cases.rel_err(out, ref) < cases.TOL[name]
+        assert open(out_file).readline() == open(out_file + ".gpu").readline()        # identical header line
