@@ -53,6 +53,8 @@ struct Block {
         int cls = 0, slot = 0;
         bool ortho = false;
         int bi0 = 0, bj0 = 0, bk0 = 0, bk1 = 0;      // box of the nodes of this class
+        int bi1 = 0, bj1 = 0;
+        bool pure = false;                           // the class fills its box and all 27 neighbours exist -> TMA kernel
         int tiles_x = 0, tiles_y = 0, zchunks = 0, kz = 0;
         double tbl[276];
         int64_t nodes = 0;

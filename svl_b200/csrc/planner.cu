@@ -420,6 +420,10 @@ int plan_and_upload(svlgpu_model *m) {
                     for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], ijk[a]); hi[a] = std::max(hi[a], ijk[a]); }
                 }
                 d.bi0 = lo[0]; d.bj0 = lo[1]; d.bk0 = lo[2]; d.bk1 = hi[2] + 1;
+                d.bi1 = hi[0] + 1; d.bj1 = hi[1] + 1;
+                d.pure = (cpop[c] == (long long)(hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1)) &&
+                         lo[0] >= 1 && lo[1] >= 1 && lo[2] >= 1 && hi[0] <= NX - 2 && hi[1] <= NY - 2 && hi[2] <= NZ - 2 &&
+                         !getenv("SVLGPU_NO_TMA");
                 const int TY = kDomNW * kDomR;
                 d.tiles_x = (hi[0] - lo[0] + 1 + 31) / 32; d.tiles_y = (hi[1] - lo[1] + 1 + TY - 1) / TY;
                 const int nzb = d.bk1 - d.bk0;
@@ -735,7 +739,7 @@ int plan_and_upload(svlgpu_model *m) {
             Up[q] = u - dt * v + dt * dt / 2.0 * a;          // CentralDifference.cpp:61
         }
         for (int b = 0; b < 3; b++) {
-            m->d_U[b] = dalloc<double>(m, m->n_int);
+            m->d_U[b] = dalloc<double>(m, (size_t)m->n_int + 2);     // + slack: bulk copies round rows up to 16 bytes
             if (!m->d_U[b]) { set_error("out of device memory (state)"); return 1; }
         }
         m->cur = 0; m->prev = 1; m->next = 2;

@@ -41,7 +41,7 @@ def main():
         m = cases.CASES[name]()
         if len(ne) == 3:
             grid = P.proc_grid(world)
-            if name == "j2_column":
+            if name == "j2_column" and world <= 6:
                 grid = (1, 1, world)
         else:
             grid = (1, world) if world <= 2 else (2, world // 2)
