@@ -48,6 +48,9 @@ void svlgpu_destroy(svlgpu_model *m) {
         for (auto &t : m->timers) { if (t.e0) cudaEventDestroy(t.e0); if (t.e1) cudaEventDestroy(t.e1); }
         if (m->ev0) cudaEventDestroy(m->ev0);
         if (m->ev1) cudaEventDestroy(m->ev1);
+        for (auto &d : m->drm_dev) for (auto &e : d.ev_ready) if (e) cudaEventDestroy(e);
+        for (auto &st : m->side) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+        for (cudaEvent_t e : {m->ev_fork, m->ev_fork2, m->ev_join}) if (e) cudaEventDestroy(e);
         if (m->stream) cudaStreamDestroy(m->stream);
     }
     delete m;

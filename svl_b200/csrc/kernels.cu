@@ -836,25 +836,32 @@ __global__ void k_drm_field(const DrmArgs a) {
         for (int c = 0; c < a.ndim; c++) a.uo[(long long)t * a.ndim + c] = sgn * row[c];
     }
 }
-__global__ void k_drm(const DrmArgs a) {
+// forces of the DRM rows for one step into a compact buffer F[row][ndim] (one thread per row and component);
+// they depend on the step index only, never on the state, so they are computed one step ahead on a side stream
+__global__ void k_drm(const DrmArgs a, double *F) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.n) return;
-    const int tg = a.target ? a.target[t] : -1;
-    if ((a.phase == 0) != (tg >= 0)) return;
-    double F[3] = {0, 0, 0};
     const int nd = a.ndim;
-    for (int q = a.ptr[t]; q < a.ptr[t + 1]; q++) {
+    if (t >= a.n * nd) return;
+    const int row = t / nd, r = t - row * nd;
+    double f = 0.0;
+    for (int q = a.ptr[row]; q < a.ptr[row + 1]; q++) {
         const double *u = a.uo + (long long)a.col[q] * nd;
-        const double *B = a.dict + (long long)a.bid[q] * nd * nd;
-        for (int r = 0; r < nd; r++)
-            for (int c = 0; c < nd; c++) F[r] += B[r * nd + c] * u[c];
+        const double *B = a.dict + (long long)a.bid[q] * nd * nd + r * nd;
+        for (int c = 0; c < nd; c++) f += B[c] * u[c];
     }
-    if (tg >= 0) {
-        for (int r = 0; r < nd; r++) a.hF[tg + r] -= a.factor * F[r];
-        return;
-    }
-    const int d0 = a.dof0[t];
-    for (int r = 0; r < nd; r++) a.Un[d0 + r] += a.kinv[d0 + r] * (a.factor * F[r]);
+    F[t] = a.factor * f;
+}
+// phase 0: rows on interface nodes (hF -= F, before the exchange); phase 1: all other rows (U_{n+1} += F / Keff)
+__global__ void k_drm_apply(int n, int nd, int phase, const int32_t *dof0, const int32_t *target, const double *F,
+                            const double *kinv, double *Un, double *hF) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * nd) return;
+    const int row = t / nd, r = t - row * nd;
+    const int tg = target ? target[row] : -1;
+    if ((phase == 0) != (tg >= 0)) return;
+    if (tg >= 0) { hF[tg + r] -= F[t]; return; }
+    const int d = dof0[row] + r;
+    Un[d] += kinv[d] * F[t];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -993,6 +1000,11 @@ static int launch_generic_elements(svlgpu_model *m, const double *U, int commit)
 // 2. + 3. lattice blocks and generic nodes: force gather + CentralDifference update (mode 0) or force only (mode 1)
 static int launch_node_update(svlgpu_model *m, const double *U, const double *Up, double *Un, int mode) {
     if (upload_dom_tables(m)) return 1;
+    bool shell_on_side = false;
+    if (m->overlap && !m->kernel_timing) {           // side stream 1 may start once U_n is final
+        CUDA_OK(cudaEventRecord(m->ev_fork, m->stream));
+        CUDA_OK(cudaStreamWaitEvent(m->side[1], m->ev_fork, 0));
+    }
     for (auto &b : m->blocks) {
         if (!b.n_stencil_nodes) continue;
         if (b.ndim == 3) {
@@ -1011,13 +1023,16 @@ static int launch_node_update(svlgpu_model *m, const double *U, const double *Up
                 m->total_launches++;
             }
             if (b.n_glist) {
+                // the shell classes write nodes no other kernel of the step writes: run them beside the bulk kernels
                 Gat3 p;
                 p.U = U; p.Up = Up; p.Un = Un; p.cls = b.d_cls; p.tbl = b.d_tbl; p.list = b.d_glist;
                 p.dof0 = b.dof0; p.n = b.n_glist; p.nx = b.nx; p.ny = b.ny; p.nz = b.nz; p.mode = mode;
                 p.target = nullptr; p.hF = nullptr;
+                cudaStream_t st = (m->overlap && !m->kernel_timing) ? m->side[1] : m->stream;
                 timer_begin(m, 4);
-                k_stencil3_gather<<<(b.n_glist + 127) / 128, 128, 0, m->stream>>>(p);
+                k_stencil3_gather<<<(b.n_glist + 127) / 128, 128, 0, st>>>(p);
                 timer_end(m, 4);
+                if (st != m->stream) shell_on_side = true;
                 m->total_launches++;
             }
         } else {
@@ -1041,6 +1056,10 @@ static int launch_node_update(svlgpu_model *m, const double *U, const double *Up
         k_gen_nodes<<<(m->n_gnodes + 255) / 256, 256, 0, m->stream>>>(a);
         timer_end(m, 2);
         m->total_launches++;
+    }
+    if (shell_on_side) {
+        CUDA_OK(cudaEventRecord(m->ev_join, m->side[1]));
+        CUDA_OK(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
     }
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -1094,6 +1113,34 @@ void record_rows(svlgpu_model *m) {
     }
 }
 
+// incident field + DRM row forces of step k into buffer k & 1, on stream st
+static int drm_compute(svlgpu_model *m, DrmDev &d, int k, cudaStream_t st) {
+    DrmArgs a;
+    a.n = d.n_nodes; a.nn = d.n_all; a.ndim = m->ndim; a.nt = d.nt; a.nf = d.nf; a.k = k; a.analytic = d.analytic;
+    a.dof0 = d.d_node_dof0; a.ptr = d.d_row_ptr; a.col = d.d_col_node; a.bid = d.d_blk_id; a.ext = d.d_ext;
+    a.dict = d.d_blk; a.field = d.d_field; a.xyz = d.d_xyz; a.uo = d.d_uo[k & 1];
+    for (int c = 0; c < 3; c++) { a.dir[c] = d.dir[c]; a.pol[c] = d.pol[c]; a.xref[c] = d.xref[c]; }
+    a.c = d.c; a.f0 = d.f0; a.t0 = d.t0; a.amp = d.amp; a.factor = d.factor; a.dt = m->dt;
+    a.kinv = nullptr; a.Un = nullptr; a.target = nullptr; a.hF = nullptr; a.phase = 0;
+    k_drm_field<<<(a.nn + 127) / 128, 128, 0, st>>>(a);
+    k_drm<<<(a.n * a.ndim + 127) / 128, 128, 0, st>>>(a, d.d_F[k & 1]);
+    d.buf_k[k & 1] = k;
+    m->total_launches += 2;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+// forces of step k + 1 while step k runs (side stream; buffer (k+1)&1 was last read by step k-1)
+static int drm_prefetch(svlgpu_model *m, int knext) {
+    for (auto &d : m->drm_dev) {
+        if (!d.n_nodes || (!d.analytic && knext >= d.nt)) continue;
+        const int b = knext & 1;
+        if (!d.ev_ready[b]) { CUDA_OK(cudaEventCreateWithFlags(&d.ev_ready[0], cudaEventDisableTiming)); CUDA_OK(cudaEventCreateWithFlags(&d.ev_ready[1], cudaEventDisableTiming)); }
+        if (drm_compute(m, d, knext, m->side[0])) return 1;
+        CUDA_OK(cudaEventRecord(d.ev_ready[b], m->side[0]));
+    }
+    return 0;
+}
+
 // external forces of step k (Assembler::ComputeExternalForceVector).  phase 0: contributions to interface
 // dofs, subtracted from the partial force that is about to be exchanged; phase 1: everything else,
 // applied to U_{n+1} directly (the solve is diagonal there).
@@ -1113,17 +1160,14 @@ static int launch_external(svlgpu_model *m, int k, const double *dev_amp, double
     }
     for (auto &d : m->drm_dev) {
         if (!d.analytic && k >= d.nt) continue;
-        DrmArgs a;
-        a.n = d.n_nodes; a.nn = d.n_all; a.ndim = m->ndim; a.nt = d.nt; a.nf = d.nf; a.k = k; a.analytic = d.analytic;
-        a.dof0 = d.d_node_dof0; a.ptr = d.d_row_ptr; a.col = d.d_col_node; a.bid = d.d_blk_id; a.ext = d.d_ext;
-        a.dict = d.d_blk; a.field = d.d_field; a.xyz = d.d_xyz; a.uo = d.d_uo;
-        for (int c = 0; c < 3; c++) { a.dir[c] = d.dir[c]; a.pol[c] = d.pol[c]; a.xref[c] = d.xref[c]; }
-        a.c = d.c; a.f0 = d.f0; a.t0 = d.t0; a.amp = d.amp; a.factor = d.factor; a.dt = m->dt;
-        a.kinv = m->d_kinv; a.Un = Un;
-        a.target = halo ? d.d_target : nullptr; a.hF = m->halo.d_hF; a.phase = phase;
+        if (!d.n_nodes) continue;
+        const int b = k & 1;
         timer_begin(m, 5);
-        if (phase == 0 || !halo) { k_drm_field<<<(a.nn + 127) / 128, 128, 0, m->stream>>>(a); m->total_launches++; }
-        k_drm<<<(a.n + 127) / 128, 128, 0, m->stream>>>(a);
+        if (d.buf_k[b] != k) { if (drm_compute(m, d, k, m->stream)) return 1; }        // not precomputed: do it now
+        else if (d.ev_ready[b]) cudaStreamWaitEvent(m->stream, d.ev_ready[b], 0);
+        k_drm_apply<<<(d.n_nodes * m->ndim + 127) / 128, 128, 0, m->stream>>>(d.n_nodes, m->ndim, phase, d.d_node_dof0,
+                                                                              halo ? d.d_target : nullptr, d.d_F[b], m->d_kinv, Un,
+                                                                              m->halo.d_hF);
         timer_end(m, 5);
         m->total_launches++;
     }
@@ -1138,6 +1182,13 @@ int run_steps(svlgpu_model *m, int k0, int k1, const double *dev_amp) {
     for (int k = k0; k < k1; k++) {
         const double *U = m->d_U[m->cur], *Up = m->d_U[m->prev];
         double *Un = m->d_U[m->next];
+        if (m->overlap && !m->drm_dev.empty() && !m->kernel_timing) {
+            // DRM forces of step k+1 are computed on side stream 0 while this step runs; its buffer was last read
+            // by step k-1, which is complete on the main stream at this point
+            CUDA_OK(cudaEventRecord(m->ev_fork2, m->stream));
+            CUDA_OK(cudaStreamWaitEvent(m->side[0], m->ev_fork2, 0));
+            if (drm_prefetch(m, k + 1)) return 1;
+        }
         if (launch_generic_elements(m, U, 1)) return 1;
         if (halo) {
             // interface partial forces first, so that their exchange overlaps the bulk of the step

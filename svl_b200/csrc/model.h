@@ -98,7 +98,10 @@ struct DrmDev {
     int32_t *d_col_node = nullptr;   // local DRM node index of the column node
     int32_t *d_blk_id = nullptr;     // per entry: index into the dictionary of unique K blocks
     double *d_blk = nullptr;         // [nblk][ndim*ndim] unique K blocks (row node <- col node)
-    double *d_uo = nullptr;          // [n_all][ndim] incident displacement of the current step
+    double *d_uo[2] = {nullptr, nullptr};   // [n_all][ndim] incident displacement of step k in buffer k & 1
+    double *d_F[2] = {nullptr, nullptr};    // [n_nodes][ndim] row forces of step k in buffer k & 1
+    int buf_k[2] = {-1, -1};
+    cudaEvent_t ev_ready[2] = {nullptr, nullptr};
     double *d_xyz = nullptr;         // node coordinates (analytic mode)
     bool analytic = false;
     double dir[3], pol[3], xref[3], c = 0, f0 = 0, t0 = 0, amp = 0, factor = 1;
@@ -190,6 +193,9 @@ struct svlgpu_model {
     int device = 0;
     double dt = 0.0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side[2] = {nullptr, nullptr};       // DRM forces one step ahead / shell classes beside the bulk kernels
+    cudaEvent_t ev_fork = nullptr, ev_fork2 = nullptr, ev_join = nullptr;
+    bool overlap = true;
     int64_t device_bytes = 0;
     std::vector<void *> allocs;
 

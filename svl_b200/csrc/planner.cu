@@ -72,6 +72,12 @@ int plan_and_upload(svlgpu_model *m) {
     const double dt = m->dt;
     if (cudaSetDevice(m->device) != cudaSuccess) { set_error("no usable CUDA device (there is no CPU fallback)"); return 1; }
     CUDA_OK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&m->side[0], cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&m->side[1], cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&m->ev_fork2, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+    m->overlap = getenv("SVLGPU_NO_OVERLAP") == nullptr;
     if (configure_kernels()) return 1;
     CUDA_OK(cudaEventCreate(&m->ev0));
     CUDA_OK(cudaEventCreate(&m->ev1));
@@ -429,10 +435,17 @@ int plan_and_upload(svlgpu_model *m) {
                 const int nzb = d.bk1 - d.bk0;
                 int kz = kzs ? atoi(kzs) : 0;
                 if (kz <= 0) {
-                    // >= ~6 waves of 148 SMs x 3 CTAs, but keep the 2 halo planes per chunk <= ~8 %
                     const long long tiles = (long long)d.tiles_x * d.tiles_y;
-                    const long long want = std::max<long long>(1, (6 * 444 + tiles - 1) / tiles);
-                    kz = (int)std::max<long long>(24, (nzb + want - 1) / want);
+                    const long long slots = 148 * 3;              // resident CTAs of the stencil kernel on a B200
+                    const long long one_wave = slots / tiles;     // z-chunks that still fit a single wave
+                    if (one_wave >= 1 && (nzb + one_wave - 1) / one_wave <= 48) {
+                        // small lattice (e.g. one of 8 partitions of 10^8 DOF): one wave, as many chunks as fit
+                        kz = (int)((nzb + one_wave - 1) / one_wave);
+                    } else {
+                        // many waves: >= ~6 waves of CTAs, but keep the 2 halo planes per chunk <= ~8 %
+                        const long long want = std::max<long long>(1, (6 * slots + tiles - 1) / tiles);
+                        kz = (int)std::max<long long>(24, (nzb + want - 1) / want);
+                    }
                 }
                 d.kz = std::min(kz, nzb); d.zchunks = (nzb + d.kz - 1) / d.kz;
                 is_dom[c] = 1;
@@ -702,7 +715,8 @@ int plan_and_upload(svlgpu_model *m) {
         }
         dd.d_node_dof0 = dupload(m, dof0); dd.d_row_ptr = dupload(m, ptr); dd.d_col_node = dupload(m, col);
         dd.d_blk_id = dupload(m, bid); dd.d_blk = dupload(m, dict); dd.d_ext = dupload(m, dl.ext);
-        dd.d_uo = dalloc<double>(m, (size_t)nn * nd);
+        dd.d_uo[0] = dalloc<double>(m, (size_t)nn * nd); dd.d_uo[1] = dalloc<double>(m, (size_t)nn * nd);
+        dd.d_F[0] = dalloc<double>(m, (size_t)rows.size() * nd + 1); dd.d_F[1] = dalloc<double>(m, (size_t)rows.size() * nd + 1);
         dd.analytic = dl.analytic; dd.factor = dl.factor;
         if (dl.analytic) {
             std::vector<double> xyz((size_t)nn * nd);
