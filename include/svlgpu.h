@@ -95,6 +95,7 @@ int svlgpu_hint_structured_block(svlgpu_model *m, int node0, int nx, int ny, int
 
 /* Planner / solver options, before finalize.  name: "lattice_guess" (1: without hints, guess the
  * makeDomainVolume / makeDomainArea lattice from the connectivity -- verified like a hint; default 1),
+ * "cuda_graph" (1: replay steps from a CUDA graph of 6 consecutive steps; default 0),
  * "pml_rtol" (relative residual of the PML block solve, default 1e-14), "keep_gauss" (1: keep Gauss-point
  * strain / stress for svlgpu_get_gauss, default 0), "ftol" (Assembler.cpp:262 filter of the PML element
  * forces, default 1e-12).                                                        */

@@ -40,6 +40,7 @@ void svlgpu_destroy(svlgpu_model *m) {
     if (m->finalized || m->stream) {
         cudaSetDevice(m->device);
         if (m->stream) cudaStreamSynchronize(m->stream);
+        graph_destroy(m);
         halo_destroy(m);
         pml_destroy(m);
         for (void *p : m->allocs) cudaFree(p);
@@ -162,6 +163,7 @@ int svlgpu_set_option(svlgpu_model *m, const char *name, double value) {
     const std::string n(name);
     if (n == "lattice_guess") m->opt_lattice_guess = value != 0.0;
     else if (n == "keep_gauss") m->opt_keep_gauss = value != 0.0;
+    else if (n == "cuda_graph") m->opt_graph = value != 0.0 ? 1 : 0;
     else if (n == "pml_rtol") { REQUIRE(value > 0.0 && value < 1.0, "set_option: pml_rtol out of range"); m->pml.rtol = value; }
     else if (n == "ftol") { REQUIRE(value >= 0.0, "set_option: ftol must be >= 0"); m->pml.ftol = value; }
     else { set_error("set_option: unknown option " + n); return 1; }

@@ -108,7 +108,8 @@ SVL_HD void iso_stress2(const Iso &m, const double e[3], double s[3]) {
 // J2 radial return with linear mixed hardening: Plastic3DJ2.cpp:206-259 (+ CommitState
 // :163-170: the explicit path commits after every update).  st = eps_p[6] | q[6] | alpha.
 struct J2Par { double K, G, H, beta, Sy; };
-SVL_HD void j2_return_map(const J2Par &p, const double ee[6], double st[13], double sig[6]) {
+// returns true when the step was plastic (the state changed)
+SVL_HD bool j2_return_map(const J2Par &p, const double ee[6], double st[13], double sig[6]) {
     double e[6] = {ee[0], ee[1], ee[2], 0.5 * ee[3], 0.5 * ee[4], 0.5 * ee[5]};
     const double tr = e[0] + e[1] + e[2];
     double str[6], xi[6];
@@ -125,6 +126,7 @@ SVL_HD void j2_return_map(const J2Par &p, const double ee[6], double st[13], dou
     if (f <= 0.0) {
 #pragma unroll
         for (int i = 0; i < 6; i++) sig[i] = ((i < 3) ? kt : 0.0) + str[i];
+        return false;
     } else {
         const double dg = f / (2.0 * p.G + 2.0 / 3.0 * p.H);
         st[12] += sqrt(2.0 / 3.0) * dg;
@@ -135,6 +137,7 @@ SVL_HD void j2_return_map(const J2Par &p, const double ee[6], double st[13], dou
             st[i] += dg * n;
             sig[i] = ((i < 3) ? kt : 0.0) + str[i] - 2.0 * p.G * dg * n;
         }
+        return true;
     }
 }
 

@@ -315,7 +315,9 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4) ? 3 : 1) k_stencil3_tma(con
         bulk_g2s(pl + stage * PLANE + row * kT3Row + dsti, p.U + (g - par), (unsigned)len * 8u, &bar[stage]);
     };
 
-    double *ups = ups_all + (w * 32 + lane) * (R * 3);
+    // U_{n-1} slots of this thread: [slot][thread] so that a warp touches consecutive 8-byte words (conflict free)
+    constexpr int NT = NW * 32;
+    double *ups = ups_all + threadIdx.x;
     double A[3][R][3];
 #pragma unroll
     for (int s = 0; s < 3; s++)
@@ -343,9 +345,9 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4) ? 3 : 1) k_stencil3_tma(con
             for (int r = 0; r < R; r++)
                 if (rowin[r]) {
                     const double *q = p.Up + p.dof0 + 3ll * (gi + (long long)p.nx * (gjb + r + (long long)p.ny * (kk - 1)));
-                    cp_async8(ups + 3 * r + 0, q + 0, true);
-                    cp_async8(ups + 3 * r + 1, q + 1, true);
-                    cp_async8(ups + 3 * r + 2, q + 2, true);
+                    cp_async8(ups + (3 * r + 0) * NT, q + 0, true);
+                    cp_async8(ups + (3 * r + 1) * NT, q + 1, true);
+                    cp_async8(ups + (3 * r + 2) * NT, q + 2, true);
                 }
         }
         cp_async_commit();
@@ -372,7 +374,7 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4) ? 3 : 1) k_stencil3_tma(con
                 for (int a = 0; a < 3; a++) {
                     if (p.mode == 0) {
                         const double un = uc[a];
-                        p.Un[d0 + a] = un + (cK[SLOT][273 + a] * (un - ups[3 * r + a]) - A[J][r][a]) * cK[SLOT][270 + a];
+                        p.Un[d0 + a] = un + (cK[SLOT][273 + a] * (un - ups[(3 * r + a) * NT]) - A[J][r][a]) * cK[SLOT][270 + a];
                     } else {
                         p.Un[d0 + a] = A[J][r][a];
                     }
@@ -544,12 +546,18 @@ struct GenArgs {
     double *state;             // [13][n*ngp] or null
     double *gp;                // [2][ncomp][n*ngp] strain|stress or null
     int commit;                // 1: store the updated J2 state
+    const int32_t *ecls;       // [n] class of each element (TAB kernels)
+    const double *gtab;        // [ncls][ngp][npe*ndim + 1]: shape-function gradients + w|J| per Gauss point
 };
 
 __device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
+// TAB: congruent elements share one table of shape-function gradients and w|J| per Gauss point (what the
+// reference recomputes from the node coordinates 48 + 32 times per element and step);
+// otherwise (distorted meshes: every element its own class) the gradients come from the coordinates.
+template <bool TAB>
 __global__ void __launch_bounds__(128) k_gen_hex8(const GenArgs a) {
-    __shared__ double sx[4][4][8][6];            // [warp][elem in warp][node][X(3) U(3)]
+    __shared__ double sx[4][4][8][TAB ? 3 : 6];  // [warp][elem in warp][node][(X(3)) U(3)]
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int el = lane >> 3, g = lane & 7;
@@ -558,21 +566,39 @@ __global__ void __launch_bounds__(128) k_gen_hex8(const GenArgs a) {
     if (!act) e = a.n - 1;
     {
         const int node = a.conn[(long long)e * 8 + g];
-        const double *x = a.coords + 3ll * node;
         const double *u = a.U + a.node_ptr[node];
         double *s = sx[w][el][g];
-        s[0] = x[0]; s[1] = x[1]; s[2] = x[2]; s[3] = u[0]; s[4] = u[1]; s[5] = u[2];
+        if (!TAB) {
+            const double *x = a.coords + 3ll * node;
+            s[0] = x[0]; s[1] = x[1]; s[2] = x[2]; s[3] = u[0]; s[4] = u[1]; s[5] = u[2];
+        } else {
+            s[0] = u[0]; s[1] = u[1]; s[2] = u[2];
+        }
     }
     __syncwarp();
-    double X[8][3], Ue[8][3];
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const double *s = sx[w][el][i];
-        X[i][0] = s[0]; X[i][1] = s[1]; X[i][2] = s[2];
-        Ue[i][0] = s[3]; Ue[i][1] = s[4]; Ue[i][2] = s[5];
-    }
+    double Ue[8][3];
     double d[8][3];
-    const double wd = hex8_grad(X, g, d, nullptr);        // weight 1 * |det J|
+    double wd;
+    if (!TAB) {
+        double X[8][3];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const double *s = sx[w][el][i];
+            X[i][0] = s[0]; X[i][1] = s[1]; X[i][2] = s[2];
+            Ue[i][0] = s[3]; Ue[i][1] = s[4]; Ue[i][2] = s[5];
+        }
+        wd = hex8_grad(X, g, d, nullptr);                 // weight 1 * |det J|
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const double *s = sx[w][el][i];
+            Ue[i][0] = s[0]; Ue[i][1] = s[1]; Ue[i][2] = s[2];
+        }
+        const double *t = a.gtab + ((size_t)a.ecls[e] * 8 + g) * 25;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { d[i][0] = __ldg(t + 3 * i); d[i][1] = __ldg(t + 3 * i + 1); d[i][2] = __ldg(t + 3 * i + 2); }
+        wd = __ldg(t + 24);
+    }
     double ep[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int i = 0; i < 8; i++) {                         // eps = B u  (lin3DHexa8.cpp:721-741,845-850)
@@ -592,8 +618,8 @@ __global__ void __launch_bounds__(128) k_gen_hex8(const GenArgs a) {
         double st[13];
 #pragma unroll
         for (int i = 0; i < 13; i++) st[i] = a.state[i * ngp + q];
-        j2_return_map(jp, ep, st, sg);
-        if (a.commit && act) {
+        const bool yielded = j2_return_map(jp, ep, st, sg);
+        if (a.commit && act && yielded) {          // an elastic step leaves the state untouched: no write
 #pragma unroll
             for (int i = 0; i < 13; i++) a.state[i * ngp + q] = st[i];
         }
@@ -643,6 +669,86 @@ __global__ void __launch_bounds__(128) k_gen_hex8(const GenArgs a) {
     }
 }
 
+// Class-table variant with a small register footprint (high occupancy hides the conn -> U gather latency):
+// phase 1, lane = Gauss point g: eps = B_g u_e, material update, w|J| sigma_g staged in shared memory;
+// phase 2, lane = node i: f_i = sum_g B_g,i^T (w|J| sigma_g), Gauss points in the reference's order (lin3DHexa8.cpp:397-409).
+__global__ void __launch_bounds__(128, 5) k_gen_hex8_tab(const GenArgs a) {
+    __shared__ double su[4][4][8][3];            // [warp][elem in warp][node][U(3)]
+    __shared__ double ss[4][4][8][6];            // [warp][elem in warp][gp][w|J| sigma(6)]
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int el = lane >> 3, g = lane & 7;
+    int e = tid >> 3;
+    const bool act = e < a.n;
+    if (!act) e = a.n - 1;
+    {
+        const int node = a.conn[(long long)e * 8 + g];
+        const double *u = a.U + a.node_ptr[node];
+        double *s = su[w][el][g];
+        s[0] = u[0]; s[1] = u[1]; s[2] = u[2];
+    }
+    __syncwarp();
+    const double *tab = a.gtab + (size_t)a.ecls[e] * 200;
+    const double *t = tab + g * 25;
+    double ep[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 8; i++) {                         // eps = B u  (lin3DHexa8.cpp:721-741,845-850)
+        const double d0 = __ldg(t + 3 * i), d1 = __ldg(t + 3 * i + 1), d2 = __ldg(t + 3 * i + 2);
+        const double *u = su[w][el][i];
+        const double u0 = u[0], u1 = u[1], u2 = u[2];
+        ep[0] = fma(d0, u0, ep[0]);
+        ep[1] = fma(d1, u1, ep[1]);
+        ep[2] = fma(d2, u2, ep[2]);
+        ep[3] += d1 * u0 + d0 * u1;
+        ep[4] += d2 * u1 + d1 * u2;
+        ep[5] += d2 * u0 + d0 * u2;
+    }
+    const int mi = a.mat[e];
+    const double *mp = a.matpar + 8 * mi;
+    double sg[6];
+    const long long ngp = 8ll * a.n, q = 8ll * e + g;
+    if (a.matkind[mi] == SVLGPU_PLASTIC3DJ2) {
+        J2Par jp = {mp[0], mp[1], mp[3], mp[4], mp[5]};
+        double st[13];
+#pragma unroll
+        for (int i = 0; i < 13; i++) st[i] = a.state[i * ngp + q];
+        const bool yielded = j2_return_map(jp, ep, st, sg);
+        if (a.commit && act && yielded) {          // an elastic step leaves the state untouched: no write
+#pragma unroll
+            for (int i = 0; i < 13; i++) a.state[i * ngp + q] = st[i];
+        }
+    } else {
+        iso_stress3(iso_from_E_nu(mp[0], mp[1]), ep, sg);
+    }
+    if (a.gp && act) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) { a.gp[i * ngp + q] = ep[i]; a.gp[(6 + i) * ngp + q] = sg[i]; }
+    }
+    {
+        const double wd = __ldg(t + 24);
+        double *s = ss[w][el][g];
+#pragma unroll
+        for (int i = 0; i < 6; i++) s[i] = wd * sg[i];
+    }
+    __syncwarp();
+    // phase 2: this lane is node i = g of its element
+    double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+#pragma unroll
+    for (int gp = 0; gp < 8; gp++) {
+        const double *d = tab + gp * 25 + 3 * g;
+        const double d0 = __ldg(d), d1 = __ldg(d + 1), d2 = __ldg(d + 2);
+        const double *s = ss[w][el][gp];
+        f0 += d0 * s[0] + d1 * s[3] + d2 * s[5];
+        f1 += d1 * s[1] + d0 * s[3] + d2 * s[4];
+        f2 += d2 * s[2] + d1 * s[4] + d0 * s[5];
+    }
+    if (act) {
+        double *o = a.fe + 3ll * q;
+        o[0] = f0; o[1] = f1; o[2] = f2;
+    }
+}
+
+template <bool TAB>
 __global__ void __launch_bounds__(128) k_gen_quad4(const GenArgs a) {
     __shared__ double sx[4][8][4][4];            // [warp][elem in warp][node][X(2) U(2)]
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -653,20 +759,28 @@ __global__ void __launch_bounds__(128) k_gen_quad4(const GenArgs a) {
     if (!act) e = a.n - 1;
     {
         const int node = a.conn[(long long)e * 4 + g];
-        const double *x = a.coords + 2ll * node;
         const double *u = a.U + a.node_ptr[node];
         double *s = sx[w][el][g];
-        s[0] = x[0]; s[1] = x[1]; s[2] = u[0]; s[3] = u[1];
+        if (!TAB) { const double *x = a.coords + 2ll * node; s[0] = x[0]; s[1] = x[1]; }
+        s[2] = u[0]; s[3] = u[1];
     }
     __syncwarp();
     double X[4][2], Ue[4][2];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const double *s = sx[w][el][i];
-        X[i][0] = s[0]; X[i][1] = s[1]; Ue[i][0] = s[2]; Ue[i][1] = s[3];
+        if (!TAB) { X[i][0] = s[0]; X[i][1] = s[1]; }
+        Ue[i][0] = s[2]; Ue[i][1] = s[3];
     }
     double d[4][2];
-    const double wd = a.th[e] * quad4_grad(X, g, d, nullptr);
+    double wd;
+    if (!TAB) wd = a.th[e] * quad4_grad(X, g, d, nullptr);
+    else {
+        const double *t = a.gtab + ((size_t)a.ecls[e] * 4 + g) * 9;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { d[i][0] = __ldg(t + 2 * i); d[i][1] = __ldg(t + 2 * i + 1); }
+        wd = __ldg(t + 8);                              // thickness * |det J|
+    }
     double ep[3] = {0, 0, 0};
 #pragma unroll
     for (int i = 0; i < 4; i++) {                // lin2DQuad4.cpp:705-708
@@ -770,6 +884,7 @@ struct PLArgs {
     const double *kinv;
     double *Un;
     int k;
+    const int32_t *kctl;          // device step control {k, recorder row}: overrides k when the step is replayed from a graph
     const int32_t *target;        // per loaded dof: slot in hF (interface dof), -2-c (PML unknown c) or -1
     double *hF, *bext;
     int phase;                    // 0: interface / PML dofs (before the exchange / block solve), 1: all other dofs
@@ -777,12 +892,13 @@ struct PLArgs {
 __global__ void k_nodal_loads(const PLArgs a) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.n) return;
+    const int k = a.kctl ? a.kctl[0] : a.k;
     double F = 0.0;
     for (int q = a.ptr[t]; q < a.ptr[t + 1]; q++) {
         const int l = a.load[q];
         double amp;
         if (a.amp) amp = a.amp[l];
-        else amp = (a.snt[l] == 1) ? a.series[a.soff[l]] : ((a.k < a.snt[l]) ? a.series[a.soff[l] + a.k] : 0.0);
+        else amp = (a.snt[l] == 1) ? a.series[a.soff[l]] : ((k < a.snt[l]) ? a.series[a.soff[l] + k] : 0.0);
         F += a.coef[q] * amp;
     }
     const int tg = a.target ? a.target[t] : -1;
@@ -814,6 +930,8 @@ struct DrmArgs {
     const int32_t *target;        // per row: first slot in hF (interface node) or -1; null without halos
     double *hF;
     int phase;
+    const int32_t *kctl;          // device step control: the field is evaluated for step kctl[0] + koff
+    int koff;
 };
 __device__ __forceinline__ double ricker_disp(double tau, double f0) {
     // Ricker displacement pulse (1 - 2b) e^{-b}, b = (pi f0 tau)^2  (PlaneWave.py:222-223)
@@ -825,14 +943,16 @@ __device__ __forceinline__ double ricker_disp(double tau, double f0) {
 __global__ void k_drm_field(const DrmArgs a) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.nn) return;
+    const int k = a.kctl ? a.kctl[0] + a.koff : a.k;
     const double sgn = a.ext[t] ? -1.0 : 1.0;
     if (a.analytic) {
         double s = 0.0;
         for (int c = 0; c < a.ndim; c++) s += (a.xyz[(long long)t * a.ndim + c] - a.xref[c]) * a.dir[c];
-        const double val = a.amp * ricker_disp(a.k * a.dt - a.t0 - s / a.c, a.f0);
+        const double val = a.amp * ricker_disp(k * a.dt - a.t0 - s / a.c, a.f0);
         for (int c = 0; c < a.ndim; c++) a.uo[(long long)t * a.ndim + c] = sgn * (val * a.pol[c]);
     } else {
-        const double *row = a.field + ((long long)t * a.nt + a.k) * a.nf;
+        if (k >= a.nt) { for (int c = 0; c < a.ndim; c++) a.uo[(long long)t * a.ndim + c] = 0.0; return; }
+        const double *row = a.field + ((long long)t * a.nt + k) * a.nf;
         for (int c = 0; c < a.ndim; c++) a.uo[(long long)t * a.ndim + c] = sgn * row[c];
     }
 }
@@ -868,9 +988,13 @@ __global__ void k_drm_apply(int n, int nd, int phase, const int32_t *dof0, const
 // NODE recorder row (Recorder.cpp:239-269); V, A as in CentralDifference.cpp:141-144
 // ------------------------------------------------------------------------------------------
 __global__ void k_record(int n, const int32_t *dofs, const double *Un, const double *U, const double *Up,
-                         double dt, int field, double *row) {
+                         double dt, int field, double *row, const int32_t *kctl, int max_rows) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
+    if (kctl) {                                   // graph replay: `row` is the recorder base, the row index lives on the device
+        if (kctl[1] >= max_rows) return;
+        row += (size_t)kctl[1] * n;
+    }
     const int d = dofs[t];
     const double un = Un[d], u = U[d], up = Up[d];
     double v;
@@ -893,6 +1017,13 @@ __global__ void k_gather(int n, const int32_t *dofs, const int32_t *int_of_total
     else v = 1.0 / dt / dt * ((un - u) - u + up);
     out[t] = v;
 }
+
+// device step control block {k, recorder row}: advanced at the end of every step so that a captured graph of
+// steps can be replayed without any host-side argument
+__global__ void k_advance(int32_t *kctl) { kctl[0]++; kctl[1]++; }
+// step index of the DRM forces that are about to be computed ahead into buffer b (slot 2 + b): written on the main
+// stream before the side stream forks, so the side-stream kernels never race with k_advance
+__global__ void k_setk(int32_t *kctl, int slot, int off) { kctl[slot] = kctl[0] + off; }
 
 // ------------------------------------------------------------------------------------------
 // host drivers
@@ -983,13 +1114,16 @@ static int launch_generic_elements(svlgpu_model *m, const double *U, int commit)
         a.n = gs.n; a.conn = gs.d_conn; a.mat = gs.d_mat; a.th = gs.d_th; a.matkind = m->d_matkind;
         a.matpar = m->d_matpar; a.coords = m->d_coords; a.node_ptr = m->d_node_ptr; a.U = U;
         a.fe = gs.d_fe; a.state = gs.d_state; a.gp = gs.d_gp; a.commit = commit;
+        a.ecls = gs.d_ecls; a.gtab = gs.d_gtab;
         timer_begin(m, 1);
         if (gs.kind == SVLGPU_LIN3DHEXA8) {
-            const long long thr = 8ll * gs.n;
-            k_gen_hex8<<<(unsigned)((thr + 127) / 128), 128, 0, m->stream>>>(a);
+            const unsigned grid = (unsigned)((8ll * gs.n + 127) / 128);
+            if (gs.d_gtab) k_gen_hex8_tab<<<grid, 128, 0, m->stream>>>(a);
+            else k_gen_hex8<false><<<grid, 128, 0, m->stream>>>(a);
         } else {
-            const long long thr = 4ll * gs.n;
-            k_gen_quad4<<<(unsigned)((thr + 127) / 128), 128, 0, m->stream>>>(a);
+            const unsigned grid = (unsigned)((4ll * gs.n + 127) / 128);
+            if (gs.d_gtab) k_gen_quad4<true><<<grid, 128, 0, m->stream>>>(a);
+            else k_gen_quad4<false><<<grid, 128, 0, m->stream>>>(a);
         }
         timer_end(m, 1);
         m->total_launches++;
@@ -1102,12 +1236,13 @@ int halo_generic_force(svlgpu_model *m) {
     return 0;
 }
 
-void record_rows(svlgpu_model *m) {
+void record_rows(svlgpu_model *m, bool devk) {
     for (auto &r : m->recorders) {
         if (r.rows >= r.max_rows || !r.width) continue;
         k_record<<<(r.width + 127) / 128, 128, 0, m->stream>>>(r.width, r.d_dofs, m->d_U[m->next], m->d_U[m->cur],
                                                                  m->d_U[m->prev], m->dt, r.field,
-                                                                 r.d_rows + (size_t)r.rows * r.width);
+                                                                 devk ? r.d_rows : r.d_rows + (size_t)r.rows * r.width,
+                                                                 devk ? m->d_kctl : nullptr, r.max_rows);
         r.rows++;
         m->total_launches++;
     }
@@ -1122,6 +1257,7 @@ static int drm_compute(svlgpu_model *m, DrmDev &d, int k, cudaStream_t st) {
     for (int c = 0; c < 3; c++) { a.dir[c] = d.dir[c]; a.pol[c] = d.pol[c]; a.xref[c] = d.xref[c]; }
     a.c = d.c; a.f0 = d.f0; a.t0 = d.t0; a.amp = d.amp; a.factor = d.factor; a.dt = m->dt;
     a.kinv = nullptr; a.Un = nullptr; a.target = nullptr; a.hF = nullptr; a.phase = 0;
+    a.kctl = m->graph_capturing ? m->d_kctl + 2 + (k & 1) : nullptr; a.koff = 0;
     k_drm_field<<<(a.nn + 127) / 128, 128, 0, st>>>(a);
     k_drm<<<(a.n * a.ndim + 127) / 128, 128, 0, st>>>(a, d.d_F[k & 1]);
     d.buf_k[k & 1] = k;
@@ -1134,9 +1270,9 @@ static int drm_prefetch(svlgpu_model *m, int knext) {
     for (auto &d : m->drm_dev) {
         if (!d.n_nodes || (!d.analytic && knext >= d.nt)) continue;
         const int b = knext & 1;
-        if (!d.ev_ready[b]) { CUDA_OK(cudaEventCreateWithFlags(&d.ev_ready[0], cudaEventDisableTiming)); CUDA_OK(cudaEventCreateWithFlags(&d.ev_ready[1], cudaEventDisableTiming)); }
         if (drm_compute(m, d, knext, m->side[0])) return 1;
         CUDA_OK(cudaEventRecord(d.ev_ready[b], m->side[0]));
+        d.ev_valid[b] = true;
     }
     return 0;
 }
@@ -1153,6 +1289,7 @@ static int launch_external(svlgpu_model *m, int k, const double *dev_amp, double
         a.coef = m->d_pl_coef; a.series = m->d_pl_series; a.soff = m->d_pl_soff; a.snt = m->d_pl_nt;
         a.amp = dev_amp; a.kinv = m->d_kinv; a.Un = Un; a.k = k;
         a.target = halo ? m->d_pl_target : nullptr; a.hF = m->halo.d_hF; a.bext = m->pml.d_bext; a.phase = phase;
+        a.kctl = m->graph_capturing ? m->d_kctl : nullptr;
         timer_begin(m, 3);
         k_nodal_loads<<<(a.n + 127) / 128, 128, 0, m->stream>>>(a);
         timer_end(m, 3);
@@ -1164,7 +1301,7 @@ static int launch_external(svlgpu_model *m, int k, const double *dev_amp, double
         const int b = k & 1;
         timer_begin(m, 5);
         if (d.buf_k[b] != k) { if (drm_compute(m, d, k, m->stream)) return 1; }        // not precomputed: do it now
-        else if (d.ev_ready[b]) cudaStreamWaitEvent(m->stream, d.ev_ready[b], 0);
+        else if (d.ev_valid[b]) cudaStreamWaitEvent(m->stream, d.ev_ready[b], 0);
         k_drm_apply<<<(d.n_nodes * m->ndim + 127) / 128, 128, 0, m->stream>>>(d.n_nodes, m->ndim, phase, d.d_node_dof0,
                                                                               halo ? d.d_target : nullptr, d.d_F[b], m->d_kinv, Un,
                                                                               m->halo.d_hF);
@@ -1174,37 +1311,114 @@ static int launch_external(svlgpu_model *m, int k, const double *dev_amp, double
     return 0;
 }
 
-int run_steps(svlgpu_model *m, int k0, int k1, const double *dev_amp) {
-    const int64_t before = m->total_launches;
+// one step (DynamicAnalysis.cpp:36-57 loop body) enqueued on the model's streams
+static int step_once(svlgpu_model *m, int k, const double *dev_amp) {
     const bool xchg = !m->halo_peers.empty();                 // interface nodes shared with other ranks
     const bool halo = m->halo.active || m->pml.present;       // interface nodes exist (peers and / or PML ties)
-    if (xchg && !m->halo.active) { set_error("step: halos were declared but svlgpu_comm_init was not called"); return 1; }
-    for (int k = k0; k < k1; k++) {
-        const double *U = m->d_U[m->cur], *Up = m->d_U[m->prev];
-        double *Un = m->d_U[m->next];
-        if (m->overlap && !m->drm_dev.empty() && !m->kernel_timing) {
-            // DRM forces of step k+1 are computed on side stream 0 while this step runs; its buffer was last read
-            // by step k-1, which is complete on the main stream at this point
-            CUDA_OK(cudaEventRecord(m->ev_fork2, m->stream));
-            CUDA_OK(cudaStreamWaitEvent(m->side[0], m->ev_fork2, 0));
-            if (drm_prefetch(m, k + 1)) return 1;
+    const double *U = m->d_U[m->cur], *Up = m->d_U[m->prev];
+    double *Un = m->d_U[m->next];
+    m->k_of_step = k;
+    if (m->overlap && !m->drm_dev.empty() && !m->kernel_timing) {
+        // DRM forces of step k+1 are computed on side stream 0 while this step runs; its buffer was last read
+        // by step k-1, which is complete on the main stream at this point
+        if (m->graph_capturing) { k_setk<<<1, 1, 0, m->stream>>>(m->d_kctl, 2 + ((k + 1) & 1), 1); m->total_launches++; }
+        CUDA_OK(cudaEventRecord(m->ev_fork2, m->stream));
+        CUDA_OK(cudaStreamWaitEvent(m->side[0], m->ev_fork2, 0));
+        if (drm_prefetch(m, k + 1)) return 1;
+    }
+    if (launch_generic_elements(m, U, 1)) return 1;
+    if (halo) {
+        // interface partial forces first, so that their exchange overlaps the bulk of the step
+        if (halo_lattice_force(m, U) || halo_generic_force(m)) return 1;
+        if (launch_external(m, k, dev_amp, Un, 0)) return 1;
+        if (xchg && halo_exchange_begin(m)) return 1;
+    }
+    if (launch_node_update(m, U, Up, Un, 0)) return 1;
+    if (xchg && halo_exchange_end(m, U, Up, Un, 0)) return 1;
+    if (m->pml.present && pml_step(m, U, Up, Un)) return 1;
+    if (launch_external(m, k, dev_amp, Un, 1)) return 1;
+    record_rows(m, m->graph_capturing);
+    k_advance<<<1, 1, 0, m->stream>>>(m->d_kctl);
+    m->total_launches++;
+    // rotate: U_{n-1} <- U_n <- U_{n+1}
+    const int old_prev = m->prev;
+    m->prev = m->cur; m->cur = m->next; m->next = old_prev;
+    m->steps_done++;
+    m->dev_k = k + 1;
+    return 0;
+}
+
+// Steps are replayed from a CUDA graph of kGraphSteps consecutive steps (one period of the 3 rotating state
+// buffers and the 2 DRM buffers): per-step launch latency is what limits small partitions (8 GPUs on 10^8 DOF).
+constexpr int kGraphSteps = 6;
+static bool graph_usable(const svlgpu_model *m, const double *dev_amp) {
+    return m->use_graph && !dev_amp && !m->kernel_timing && !m->pml.present;
+}
+void graph_destroy(svlgpu_model *m) {
+    if (m->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)m->graph_exec);
+    m->graph_exec = nullptr;
+}
+
+int run_steps(svlgpu_model *m, int k0, int k1, const double *dev_amp) {
+    const int64_t before = m->total_launches;
+    if (!m->halo_peers.empty() && !m->halo.active) { set_error("step: halos were declared but svlgpu_comm_init was not called"); return 1; }
+    if (upload_dom_tables(m)) return 1;
+    int k = k0;
+    while (k < k1) {
+        if (m->dev_k != k) {                                  // (re)synchronise the device step control block
+            const int32_t h[2] = {k, m->recorders.empty() ? 0 : m->recorders[0].rows};
+            CUDA_OK(cudaMemcpyAsync(m->d_kctl, h, sizeof(h), cudaMemcpyHostToDevice, m->stream));
+            CUDA_OK(cudaStreamSynchronize(m->stream));
+            m->dev_k = k;
         }
-        if (launch_generic_elements(m, U, 1)) return 1;
-        if (halo) {
-            // interface partial forces first, so that their exchange overlaps the bulk of the step
-            if (halo_lattice_force(m, U) || halo_generic_force(m)) return 1;
-            if (launch_external(m, k, dev_amp, Un, 0)) return 1;
-            if (xchg && halo_exchange_begin(m)) return 1;
+        bool rows_uniform = true;                             // one device row counter serves all recorders
+        for (auto &r : m->recorders) rows_uniform = rows_uniform && r.rows == m->recorders[0].rows && r.rows + kGraphSteps <= r.max_rows;
+        const bool can_graph = graph_usable(m, dev_amp) && rows_uniform && k + kGraphSteps <= k1;
+        if (can_graph && (m->graph_exec ? ((k - m->graph_k0) % kGraphSteps == 0 && m->graph_cur == m->cur) : (k1 - k >= 2 * kGraphSteps))) {
+            // the forces of step k must sit in DRM buffer k & 1, ordered before the graph on the main stream
+            for (auto &d : m->drm_dev) {
+                if (!d.n_nodes) continue;
+                if (d.buf_k[k & 1] != k) { if (drm_compute(m, d, k, m->stream)) return 1; }
+                else if (d.ev_valid[k & 1]) CUDA_OK(cudaStreamWaitEvent(m->stream, d.ev_ready[k & 1], 0));
+                d.ev_valid[0] = d.ev_valid[1] = false;       // from here on main-stream order covers both buffers
+            }
         }
-        if (launch_node_update(m, U, Up, Un, 0)) return 1;
-        if (xchg && halo_exchange_end(m, U, Up, Un, 0)) return 1;
-        if (m->pml.present && pml_step(m, U, Up, Un)) return 1;
-        if (launch_external(m, k, dev_amp, Un, 1)) return 1;
-        record_rows(m);
-        // rotate: U_{n-1} <- U_n <- U_{n+1}
-        const int old_prev = m->prev;
-        m->prev = m->cur; m->cur = m->next; m->next = old_prev;
-        m->steps_done++;
+        if (can_graph && m->graph_exec && (k - m->graph_k0) % kGraphSteps == 0 && m->graph_cur == m->cur) {
+            CUDA_OK(cudaGraphLaunch((cudaGraphExec_t)m->graph_exec, m->stream));
+            for (auto &r : m->recorders) r.rows += kGraphSteps;
+            for (auto &d : m->drm_dev) { d.buf_k[k & 1] = k + kGraphSteps; d.buf_k[(k + 1) & 1] = k + kGraphSteps - 1; d.ev_valid[0] = d.ev_valid[1] = false; }
+            m->steps_done += kGraphSteps; m->dev_k = k + kGraphSteps;
+            m->total_launches += m->graph_launches;
+            k += kGraphSteps;
+            continue;
+        }
+        if (can_graph && !m->graph_exec && k1 - k >= 2 * kGraphSteps) {
+            // capture kGraphSteps steps; the step index and the recorder row come from the device control block
+            const int64_t l0 = m->total_launches;
+            cudaGraph_t graph = nullptr;
+            m->graph_capturing = true;
+            cudaError_t ce = cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal);
+            int rc = ce != cudaSuccess;
+            for (int q = 0; q < kGraphSteps && !rc; q++) rc = step_once(m, k + q, nullptr);
+            if (!rc && m->overlap && !m->drm_dev.empty())     // join the last DRM prefetch into the origin stream
+                for (auto &d : m->drm_dev) if (d.ev_valid[(k + kGraphSteps) & 1]) cudaStreamWaitEvent(m->stream, d.ev_ready[(k + kGraphSteps) & 1], 0);
+            ce = cudaStreamEndCapture(m->stream, &graph);
+            m->graph_capturing = false;
+            if (rc || ce != cudaSuccess || !graph) { set_error(std::string("graph capture failed: ") + cudaGetErrorString(ce)); return 1; }
+            cudaGraphExec_t exec = nullptr;
+            ce = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) { set_error(std::string("graph instantiate failed: ") + cudaGetErrorString(ce)); return 1; }
+            m->graph_exec = exec; m->graph_k0 = k; m->graph_cur = m->cur;      // 6 steps return the rotation to where it began
+            m->graph_launches = m->total_launches - l0;
+            for (auto &d : m->drm_dev) d.ev_valid[0] = d.ev_valid[1] = false;   // events recorded in capture are not waitable outside
+            // the capture advanced the host mirrors as if the steps had run: run them now
+            CUDA_OK(cudaGraphLaunch(exec, m->stream));
+            k += kGraphSteps;
+            continue;
+        }
+        if (step_once(m, k, dev_amp)) return 1;
+        k++;
     }
     CUDA_OK(cudaGetLastError());
     if (k1 > k0) m->launches_per_step = (m->total_launches - before) / (k1 - k0);

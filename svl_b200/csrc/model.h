@@ -85,6 +85,8 @@ struct GenericSet {                  // Gauss-point path: elements of one kind
     double *d_fe = nullptr;          // [n][npe][ndofn] (inside the fe arena)
     double *d_state = nullptr;       // [13][n*ngp] J2 state (only when the set has J2 elements)
     double *d_gp = nullptr;          // [2*ncomp][n*ngp] strain | stress at Gauss points
+    int32_t *d_ecls = nullptr;       // [n] gradient-table class (when few classes cover the set)
+    double *d_gtab = nullptr;        // [ncls][ngp][npe*ndim + 1] shape-function gradients + w|J|
     std::vector<int32_t> elems;      // global element ids
     bool has_j2 = false;
 };
@@ -102,6 +104,7 @@ struct DrmDev {
     double *d_F[2] = {nullptr, nullptr};    // [n_nodes][ndim] row forces of step k in buffer k & 1
     int buf_k[2] = {-1, -1};
     cudaEvent_t ev_ready[2] = {nullptr, nullptr};
+    bool ev_valid[2] = {false, false};      // ev_ready[b] was recorded outside a capture and not yet superseded
     double *d_xyz = nullptr;         // node coordinates (analytic mode)
     bool analytic = false;
     double dir[3], pol[3], xref[3], c = 0, f0 = 0, t0 = 0, amp = 0, factor = 1;
@@ -187,6 +190,7 @@ struct svlgpu_model {
     std::vector<svl::BlockHint> hints;
     std::vector<double> U0, V0, A0;
     bool opt_lattice_guess = true, opt_keep_gauss = false;
+    int opt_graph = -1;                             // -1: environment decides
 
     // ---- plan / device state ----
     bool finalized = false;
@@ -196,6 +200,13 @@ struct svlgpu_model {
     cudaStream_t side[2] = {nullptr, nullptr};       // DRM forces one step ahead / shell classes beside the bulk kernels
     cudaEvent_t ev_fork = nullptr, ev_fork2 = nullptr, ev_join = nullptr;
     bool overlap = true;
+    // CUDA-graph replay of steps
+    int32_t *d_kctl = nullptr;                       // device step control {k, recorder row}
+    int dev_k = -1, k_of_step = 0;
+    bool use_graph = true, graph_capturing = false;
+    void *graph_exec = nullptr;                      // cudaGraphExec_t of kGraphSteps consecutive steps
+    int graph_k0 = 0, graph_cur = 0;
+    int64_t graph_launches = 0;
     int64_t device_bytes = 0;
     std::vector<void *> allocs;
 
@@ -256,6 +267,7 @@ int configure_kernels();
 size_t stencil3_smem(int nw, int r);
 bool stencil_entry_nonzero(int di, int b, int dj, int s, int a);
 void forget_const_owner(svlgpu_model *m);
+void graph_destroy(svlgpu_model *m);
 // halo.cu
 int halo_plan(svlgpu_model *m);                        // after the node lists are known (planner)
 int halo_comm_init(svlgpu_model *m, const void *id128, int rank, int nranks);

@@ -71,6 +71,8 @@ int plan_and_upload(svlgpu_model *m) {
     const int nN = m->n_nodes;
     const double dt = m->dt;
     if (cudaSetDevice(m->device) != cudaSuccess) { set_error("no usable CUDA device (there is no CPU fallback)"); return 1; }
+    // equal stream priorities on purpose: with the bulk kernel prioritised the side-stream kernels only ran in its tail
+    // (measured 0.697 -> 0.78 ms per step at 320^3); interleaved they fill the issue slots the FP64-bound bulk leaves
     CUDA_OK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     CUDA_OK(cudaStreamCreateWithFlags(&m->side[0], cudaStreamNonBlocking));
     CUDA_OK(cudaStreamCreateWithFlags(&m->side[1], cudaStreamNonBlocking));
@@ -78,6 +80,11 @@ int plan_and_upload(svlgpu_model *m) {
     CUDA_OK(cudaEventCreateWithFlags(&m->ev_fork2, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
     m->overlap = getenv("SVLGPU_NO_OVERLAP") == nullptr;
+    // CUDA-graph replay of 6-step periods is built and parity-tested, but measured slower than plain stream launches
+    // once the side streams overlap (0.173 vs 0.130 ms per step at 160^3): off unless asked for
+    m->use_graph = m->opt_graph >= 0 ? m->opt_graph != 0 : getenv("SVLGPU_GRAPH") != nullptr;
+    m->d_kctl = dalloc<int32_t>(m, 8);
+    CUDA_OK(cudaMemset(m->d_kctl, 0, 8 * sizeof(int32_t)));
     if (configure_kernels()) return 1;
     CUDA_OK(cudaEventCreate(&m->ev0));
     CUDA_OK(cudaEventCreate(&m->ev1));
@@ -509,6 +516,38 @@ int plan_and_upload(svlgpu_model *m) {
             th[q] = m->attr(e, 0);
         }
         g.d_conn = dupload(m, conn); g.d_mat = dupload(m, mat); g.d_th = dupload(m, th);
+        {
+            // gradient tables per element class, only when classes repeat (structured / congruent elements)
+            std::vector<int32_t> local(classes.size(), -1), ecl(g.n);
+            std::vector<int> reps;
+            for (int q = 0; q < g.n; q++) {
+                const int c = elem_cls[g.elems[q]];
+                if (local[c] < 0) { local[c] = (int)reps.size(); reps.push_back(g.elems[q]); }
+                ecl[q] = local[c];
+            }
+            if ((long long)reps.size() * 8 <= g.n && !getenv("SVLGPU_NO_GRADTAB")) {
+                const int per = g.npe * nd + 1;
+                std::vector<double> tab((size_t)reps.size() * g.ngp * per);
+                for (size_t c = 0; c < reps.size(); c++) {
+                    const int32_t *cn = &m->elem_conn[8ll * reps[c]];
+                    for (int gp = 0; gp < g.ngp; gp++) {
+                        double *T = &tab[((size_t)c * g.ngp + gp) * per];
+                        if (nd == 3) {
+                            double X[8][3], d[8][3];
+                            for (int i = 0; i < 8; i++) for (int cc = 0; cc < 3; cc++) X[i][cc] = m->coords[3ll * cn[i] + cc];
+                            T[24] = hex8_grad(X, gp, d, nullptr);
+                            for (int i = 0; i < 8; i++) for (int cc = 0; cc < 3; cc++) T[3 * i + cc] = d[i][cc];
+                        } else {
+                            double X[4][2], d[4][2];
+                            for (int i = 0; i < 4; i++) for (int cc = 0; cc < 2; cc++) X[i][cc] = m->coords[2ll * cn[i] + cc];
+                            T[8] = m->attr(reps[c], 0) * quad4_grad(X, gp, d, nullptr);
+                            for (int i = 0; i < 4; i++) for (int cc = 0; cc < 2; cc++) T[2 * i + cc] = d[i][cc];
+                        }
+                    }
+                }
+                g.d_ecls = dupload(m, ecl); g.d_gtab = dupload(m, tab);
+            }
+        }
         g.d_fe = m->d_fe_arena + gbase[s];
         if (g.has_j2) {
             g.d_state = dalloc<double>(m, 13ull * g.n * g.ngp);
@@ -717,6 +756,8 @@ int plan_and_upload(svlgpu_model *m) {
         dd.d_blk_id = dupload(m, bid); dd.d_blk = dupload(m, dict); dd.d_ext = dupload(m, dl.ext);
         dd.d_uo[0] = dalloc<double>(m, (size_t)nn * nd); dd.d_uo[1] = dalloc<double>(m, (size_t)nn * nd);
         dd.d_F[0] = dalloc<double>(m, (size_t)rows.size() * nd + 1); dd.d_F[1] = dalloc<double>(m, (size_t)rows.size() * nd + 1);
+        CUDA_OK(cudaEventCreateWithFlags(&dd.ev_ready[0], cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&dd.ev_ready[1], cudaEventDisableTiming));
         dd.analytic = dl.analytic; dd.factor = dl.factor;
         if (dl.analytic) {
             std::vector<double> xyz((size_t)nn * nd);

@@ -274,3 +274,15 @@ def test_host_driver_reads_reference_files_and_writes_reference_recorders(tmp_pa
         ref = M.read_node_recorder(out_file)
         assert cases.rel_err(out, ref) < cases.TOL[name]
         assert open(out_file).readline() == open(out_file + ".gpu").readline()        # identical header line
+
+
+@pytest.mark.parametrize("name", ["kat444", "drm_box", "quad4_area", "j2_column"])
+def test_cuda_graph_replay_matches(oracle, name):
+    """steps replayed from a CUDA graph (device-resident step index / recorder row) give the same history"""
+    m = cases.CASES[name]()
+    ref, _ = oracle.run(m)
+    d = _device(m, options={"cuda_graph": 1})
+    out = d.run()[0]
+    assert cases.rel_err(out, ref) < cases.TOL[name]
+    plain = _device(m).run()[0]
+    assert np.array_equal(out, plain)
