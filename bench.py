@@ -217,6 +217,16 @@ def run_reference_arm(args, emit):
     emit(line)
 
 
+def ncu_traffic(n):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this very command (profiles/ncu_traffic.json); None when no capture matches."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(f"k_stencil3_tma@n{n}", {}).get("dram_bytes_per_launch")
+    except OSError:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -319,7 +329,8 @@ def main():
     ach = HEX8_BYTES * c["n_block_nodes"] / (st_ms * 1e-3) / 1e9 if st_n else None
     own_bytes = 3 * 8 * 3 + 1           # U_n, U_{n-1} reads + U_{n+1} write + 1 class byte per node
     roof = {"bound": "hbm", "kernel": "k_stencil3_dom (block-stencil force + CentralDifference update, rank 0)",
-            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None, "traffic": None,
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
+            "traffic": ncu_traffic(args.n if world == 1 else None),
             "peak_source": peak_src, "avg_launch_ms": st_ms, "launches_timed": st_n,
             "algorithmic_bytes_per_element_update": HEX8_BYTES,
             "kernel_compulsory_bytes_per_node": own_bytes,
