@@ -387,6 +387,205 @@ __global__ void __launch_bounds__(NW * 32, (NW <= 4) ? 3 : 1) k_stencil3_tma(con
 }
 
 // ------------------------------------------------------------------------------------------
+// 3-D block stencil, dominant node class, v4.  Same arithmetic and tile shape as k_stencil3_tma; what changed is
+// everything around the DFMAs (profiles/r1j: only half of the issued instructions were DFMA, 0.8 barrier stalls per issue):
+//   * no CTA-wide barrier in the plane loop: a stage is handed back to the TMA-issuing lanes through an "empty"
+//     mbarrier (one arrival per warp), so only those lanes ever wait for the slowest warp and the others run ahead
+//     up to the prefetch distance;
+//   * the three accumulator planes rotate by renaming (the loop is unrolled by the period 3) instead of 72 register moves;
+//   * SYM: the interior class of a homogeneous rectangular-cell lattice has a stencil that is even in every offset for
+//     a == b and odd in the offsets along a and b for a != b (tensor products of the 1-D mass / stiffness / gradient
+//     matrices), so 153 coefficients collapse to 36 magnitudes -> 4x fewer constant loads (the sign is a free operand
+//     modifier of DFMA).  The planner checks the symmetry numerically before choosing this variant;
+//   * running 64-bit offsets instead of per-row index products.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int stencil_sym_idx(int di, int b, int dj, int s, int a) {
+    int d[3] = {di - 1, dj - 1, 1 - s};
+    if (a == b) {
+        for (int c = 0; c < 3; c++) d[c] = d[c] != 0 ? -1 : 0;
+    } else {
+        const int c = 3 - a - b;
+        d[c] = d[c] != 0 ? -1 : 0;
+        d[a] = -1; d[b] = -1;
+    }
+    return (((d[0] + 1) * 3 + b) * 3 + (d[1] + 1)) * 10 + (1 - d[2]) * 3 + a;
+}
+__host__ __device__ constexpr bool stencil_sym_neg(int di, int b, int dj, int s, int a) {
+    if (a == b) return false;
+    const int d[3] = {di - 1, dj - 1, 1 - s};
+    return d[a] * d[b] < 0;
+}
+
+template <int R, bool SYM, int SLOT, int ROT>
+__device__ __forceinline__ void stencil3_plane4(const double *pl, const int (&rowp)[R + 2], double (&A)[3][R][3]) {
+#pragma unroll
+    for (int di = 0; di < 3; di++) {
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            double u[R + 2];
+#pragma unroll
+            for (int q = 0; q < R + 2; q++) u[q] = pl[rowp[q] + 3 * di + b];
+#pragma unroll
+            for (int dj = 0; dj < 3; dj++)
+#pragma unroll
+                for (int s = 0; s < 3; s++)
+#pragma unroll
+                    for (int a = 0; a < 3; a++) {
+                        if (!stencil_nz(di, b, dj, s, a)) continue;
+                        // the coefficient stays a uniform-register / constant-bank operand; the sign rides on u
+                        const double c = cK[SLOT][SYM ? stencil_sym_idx(di, b, dj, s, a) : ((di * 3 + b) * 3 + dj) * 10 + s * 3 + a];
+                        if (SYM && stencil_sym_neg(di, b, dj, s, a)) {
+#pragma unroll
+                            for (int r = 0; r < R; r++) A[(s + ROT) % 3][r][a] = fma(-u[r + dj], c, A[(s + ROT) % 3][r][a]);
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < R; r++) A[(s + ROT) % 3][r][a] = fma(u[r + dj], c, A[(s + ROT) % 3][r][a]);
+                        }
+                    }
+        }
+    }
+}
+
+template <int NW, int R, int SLOT, bool SYM, bool NOBAR>
+__global__ void __launch_bounds__(NW * 32, (NW * R <= 16) ? 3 : 2) k_stencil3_v4(const Dom3 p) {
+    // NOBAR: prefetch distance 1 plane, a stage is refilled one full iteration after its release (all threads poll
+    // the "empty" mbarrier, which has normally completed long before); otherwise distance 2 and a CTA barrier per plane.
+    // (A wait executed by the producer lanes only would be cheaper still, but any blocking operation under a
+    // thread-dependent branch makes ptxas give up the uniform datapath for the coefficient loads: LDC instead of LDCU.)
+    constexpr int DIST = NOBAR ? 1 : 2;
+    constexpr int TY = NW * R, TYH = TY + 2, NS = 4, NT = NW * 32;
+    constexpr int PLANE = TYH * kT3Row;
+    static_assert(TYH <= 32, "the TMA-issuing lanes must sit in one warp");
+    extern __shared__ __align__(16) double pl[];
+    double *ups_all = pl + NS * PLANE;
+    uint64_t *full = reinterpret_cast<uint64_t *>(ups_all + NT * R * 3);
+    uint64_t *empty = full + NS;
+
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int item = blockIdx.x;
+    const int txi = item % p.tiles_x; item /= p.tiles_x;
+    const int tyi = item % p.tiles_y; item /= p.tiles_y;
+    const int i0 = p.bi0 + txi * 32, j0 = p.bj0 + tyi * TY;
+    const int k0 = p.bk0 + item * p.kz, k1 = min(k0 + p.kz, p.bk1);
+    const int gi = i0 + lane, gjb = j0 + w * R;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; s++) { mbar_init(&full[s], TYH); mbar_init(&empty[s], NW); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    const int e0 = 3 * (i0 - 1);
+    const int ea = max(e0, 0), eb = min(3 * (i0 + 33), 3 * p.nx);
+    const int q0 = ((ea - e0) + (int)(p.dof0 & 1) + ea) & 1;            // shift parity of row y = 0, k = 0
+    const int altx = p.nx & 1, alty = p.ny & 1;
+
+    // producer lanes 0 .. TYH-1 of warp 0: one row of plane k each, into `stage`
+    const int prow_y = j0 - 1 + (int)threadIdx.x;
+    const bool prow_ok = (threadIdx.x < TYH) && prow_y >= 0 && prow_y < p.ny && eb > ea;
+    auto issue_plane = [&](int k, int stage) {
+        if (!prow_ok || k < 0 || k >= p.nz) { mbar_arrive(&full[stage]); return; }
+        const long long g = p.dof0 + 3ll * p.nx * (prow_y + (long long)p.ny * k) + ea;
+        const int par = (int)(g & 1);
+        int len = eb - ea + par;
+        len += len & 1;
+        const int dsti = (ea - par - e0) + ((ea - par - e0) & 1);
+        mbar_arrive_expect_tx(&full[stage], (unsigned)len * 8u);
+        bulk_g2s(pl + stage * PLANE + (int)threadIdx.x * kT3Row + dsti, p.U + (g - par), (unsigned)len * 8u, &full[stage]);
+    };
+
+    double *ups = ups_all + threadIdx.x;
+    double A[3][R][3];
+#pragma unroll
+    for (int s = 0; s < 3; s++)
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int a = 0; a < 3; a++) A[s][r][a] = 0.0;
+
+    const bool col_in = (gi >= p.bi0) && (gi < p.bi1);
+    bool rowin[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) rowin[r] = col_in && (gjb + r >= p.bj0) && (gjb + r < p.bj1);
+
+    if (threadIdx.x < TYH) {
+        issue_plane(k0 - 1, 0);
+        if (DIST == 2) issue_plane(k0, 1);
+    }
+
+    const long long pstride = 3ll * p.nx * p.ny;
+    const int rstride = 3 * p.nx;
+    long long off = p.dof0 + 3ll * (gi + (long long)p.nx * (gjb + (long long)p.ny * (k0 - 2)));   // node (gi, gjb, kk-1)
+    const int nit = k1 - k0 + 2;
+
+    auto body = [&](const int it, auto rot_tag) {
+        constexpr int ROT = decltype(rot_tag)::value;
+        const int kk = k0 - 1 + it;
+        if (NOBAR) {
+            // stage (it+1)%NS held plane it-3, released by every warp at the end of iteration it-2
+            if (it >= 3 && kk + 1 <= k1) mbar_wait(&empty[(it + 1) % NS], (unsigned)(((it - 3) / NS) & 1));
+        } else {
+            __syncthreads();                               // everyone is done with the stage that is refilled now
+        }
+        if (threadIdx.x < TYH && kk + DIST <= k1) issue_plane(kk + DIST, (it + DIST) % NS);
+        const bool fin = (kk - 1 >= k0) && (kk - 1 < k1);  // plane kk-1 is finished by this iteration
+        if (p.mode == 0 && fin) {
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                if (rowin[r]) {
+                    const double *q = p.Up + (off + r * rstride);
+                    cp_async8(ups + (3 * r + 0) * NT, q + 0, true);
+                    cp_async8(ups + (3 * r + 1) * NT, q + 1, true);
+                    cp_async8(ups + (3 * r + 2) * NT, q + 2, true);
+                }
+        }
+        cp_async_commit();
+        const int shk = (q0 + altx * ((alty * kk) & 1)) & 1;
+        int rowp[R + 2];
+#pragma unroll
+        for (int q = 0; q < R + 2; q++) {
+            const int y = gjb - 1 + q;
+            rowp[q] = (it % NS) * PLANE + (w * R + q) * kT3Row + 3 * lane + ((shk + altx * (y & 1)) & 1);
+        }
+        mbar_wait(&full[it % NS], (unsigned)((it / NS) & 1));
+        stencil3_plane4<R, SYM, SLOT, ROT>(pl, rowp, A);
+        cp_async_wait<0>();
+        constexpr int J = ROT % 3;                         // accumulator of output plane kk-1
+        const int shp = (q0 + altx * ((alty * (kk - 1)) & 1)) & 1;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (fin && rowin[r]) {
+                // U_n of this node: still staged (plane kk-1 lives in the previous stage until it is released below)
+                const double *uc = pl + ((it + NS - 1) % NS) * PLANE + (w * R + r + 1) * kT3Row + 3 * lane + 3 +
+                                   ((shp + altx * ((gjb + r) & 1)) & 1);
+                double *o = p.Un + (off + r * rstride);
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    if (p.mode == 0) {
+                        const double un = uc[a];
+                        o[a] = un + (cK[SLOT][273 + a] * (un - ups[(3 * r + a) * NT]) - A[J][r][a]) * cK[SLOT][270 + a];
+                    } else {
+                        o[a] = A[J][r][a];
+                    }
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < 3; a++) A[J][r][a] = 0.0;   // becomes the accumulator of output plane kk+2
+        }
+        off += pstride;
+        if (NOBAR && it >= 1) {                            // hand the stage of plane kk-1 back to the producer lanes
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[(it + NS - 1) % NS]);
+        }
+    };
+    for (int it = 0; it < nit; it += 3) {
+        body(it, std::integral_constant<int, 0>{});
+        if (it + 1 < nit) body(it + 1, std::integral_constant<int, 1>{});
+        if (it + 2 < nit) body(it + 2, std::integral_constant<int, 2>{});
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // 3-D block stencil, remaining node classes (faces / edges / corners / material interfaces):
 // one thread per listed node, coefficients from the per-class table (warp-uniform -> L1
 // broadcast because the list is sorted by class), neighbours through L1/L2.
@@ -444,6 +643,78 @@ __global__ void __launch_bounds__(128) k_stencil3_gather(const Gat3 p) {
             p.Un[d0 + a] = un + (T[273 + a] * (un - p.Up[d0 + a]) - F[a]) * T[270 + a];
         } else {
             p.Un[d0 + a] = F[a];
+        }
+    }
+}
+
+// Shell classes, step pass: the list is cut into chunks of kShellChunk nodes of ONE class (padded with -1 by the
+// planner), one CTA per chunk.  The class table is staged in shared memory once and every thread advances kShellNPT
+// nodes, so a coefficient is read once per kShellNPT DFMAs instead of once per DFMA (the per-node kernel above is
+// bound by those loads: profiles/r1j).  Same neighbour and summation order as k_stencil3_gather.
+struct Shell3 {
+    const double *U, *Up;
+    double *Un;
+    const double *tbl;        // [ncls][276]
+    const int32_t *list;      // [n_chunks][kShellChunk] lattice-local node ids or -1
+    const uint8_t *chunk_cls; // [n_chunks]
+    long long dof0;
+    int nx, ny, nz, mode;
+};
+__global__ void __launch_bounds__(128) k_stencil3_shell(const Shell3 p) {
+    __shared__ double T[kTbl3Stride];
+    {
+        const double *Tg = p.tbl + (size_t)p.chunk_cls[blockIdx.x] * kTbl3Stride;
+        for (int i = threadIdx.x; i < kTbl3Stride; i += 128) T[i] = Tg[i];
+    }
+    __syncthreads();
+    int q[kShellNPT], ci[kShellNPT], cj[kShellNPT], ck[kShellNPT];
+    double F[kShellNPT][3];
+#pragma unroll
+    for (int n = 0; n < kShellNPT; n++) {
+        q[n] = p.list[(size_t)blockIdx.x * kShellChunk + n * 128 + threadIdx.x];
+        const int qq = max(q[n], 0);
+        ci[n] = qq % p.nx; cj[n] = (qq / p.nx) % p.ny; ck[n] = qq / (p.nx * p.ny);
+        if (q[n] < 0) ci[n] = -4;                       // padding: every neighbour is "outside"
+        F[n][0] = F[n][1] = F[n][2] = 0.0;
+    }
+    for (int s = 0; s < 3; s++) {
+        for (int dj = 0; dj < 3; dj++) {
+#pragma unroll
+            for (int di = 0; di < 3; di++) {
+                const double *u[kShellNPT];
+#pragma unroll
+                for (int n = 0; n < kShellNPT; n++) {
+                    const int x = ci[n] + di - 1, y = cj[n] + dj - 1, z = ck[n] + 1 - s;
+                    const bool ok = x >= 0 && x < p.nx && y >= 0 && y < p.ny && z >= 0 && z < p.nz;
+                    u[n] = ok ? p.U + p.dof0 + 3ll * (x + (long long)p.nx * (y + (long long)p.ny * z)) : nullptr;
+                }
+#pragma unroll
+                for (int b = 0; b < 3; b++) {
+                    const double *c = T + ((di * 3 + b) * 3 + dj) * 10 + s * 3;
+                    const double c0 = c[0], c1 = c[1], c2 = c[2];
+#pragma unroll
+                    for (int n = 0; n < kShellNPT; n++) {
+                        const double ub = u[n] ? u[n][b] : 0.0;
+                        F[n][0] = fma(c0, ub, F[n][0]);
+                        F[n][1] = fma(c1, ub, F[n][1]);
+                        F[n][2] = fma(c2, ub, F[n][2]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < kShellNPT; n++) {
+        if (q[n] < 0) continue;
+        const long long d0 = p.dof0 + 3ll * q[n];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            if (p.mode == 0) {
+                const double un = p.U[d0 + a];
+                p.Un[d0 + a] = un + (T[273 + a] * (un - p.Up[d0 + a]) - F[n][a]) * T[270 + a];
+            } else {
+                p.Un[d0 + a] = F[n][a];
+            }
         }
     }
 }
@@ -958,13 +1229,34 @@ __global__ void k_drm_field(const DrmArgs a) {
 }
 // forces of the DRM rows for one step into a compact buffer F[row][ndim] (one thread per row and component);
 // they depend on the step index only, never on the state, so they are computed one step ahead on a side stream
+// (a one-thread-per-row ELL variant was measured slower: fewer threads in flight, profiles/r1l)
 __global__ void k_drm(const DrmArgs a, double *F) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int nd = a.ndim;
     if (t >= a.n * nd) return;
     const int row = t / nd, r = t - row * nd;
     double f = 0.0;
-    for (int q = a.ptr[row]; q < a.ptr[row + 1]; q++) {
+    const int q1 = a.ptr[row + 1];
+    int q = a.ptr[row];
+    // four entries at a time: their index and operand loads are independent and go out together (the kernel is
+    // bound by the ptr -> col/bid -> u/B dependent-load chain); the sum keeps the ascending entry order
+    for (; q + 4 <= q1; q += 4) {
+        int cq[4], bq[4];
+#pragma unroll
+        for (int z = 0; z < 4; z++) { cq[z] = a.col[q + z]; bq[z] = a.bid[q + z]; }
+        double uu[4][3], BB[4][3];
+#pragma unroll
+        for (int z = 0; z < 4; z++)
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                if (c < nd) { uu[z][c] = a.uo[(long long)cq[z] * nd + c]; BB[z][c] = a.dict[(long long)bq[z] * nd * nd + r * nd + c]; }
+#pragma unroll
+        for (int z = 0; z < 4; z++)
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                if (c < nd) f += BB[z][c] * uu[z][c];
+    }
+    for (; q < q1; q++) {
         const double *u = a.uo + (long long)a.col[q] * nd;
         const double *B = a.dict + (long long)a.bid[q] * nd * nd + r * nd;
         for (int c = 0; c < nd; c++) f += B[c] * u[c];
@@ -1096,6 +1388,22 @@ static void launch_tma(const Dom3 &p, int slot, bool ortho, unsigned grid, cudaS
     default: launch_tma_so<NW, R, 3>(p, ortho, grid, st); break;
     }
 }
+size_t stencil3_v4_smem(int nw, int r) { return stencil3_tma_smem(nw, r); }
+template <int NW, int R, int SLOT>
+static void launch_v4_so(const Dom3 &p, bool nobar, unsigned grid, cudaStream_t st) {
+    const size_t sm = stencil3_v4_smem(NW, R);
+    if (nobar) k_stencil3_v4<NW, R, SLOT, true, true><<<grid, NW * 32, sm, st>>>(p);
+    else k_stencil3_v4<NW, R, SLOT, true, false><<<grid, NW * 32, sm, st>>>(p);
+}
+template <int NW, int R>
+static void launch_v4(const Dom3 &p, int slot, bool nobar, unsigned grid, cudaStream_t st) {
+    switch (slot) {
+    case 0: launch_v4_so<NW, R, 0>(p, nobar, grid, st); break;
+    case 1: launch_v4_so<NW, R, 1>(p, nobar, grid, st); break;
+    case 2: launch_v4_so<NW, R, 2>(p, nobar, grid, st); break;
+    default: launch_v4_so<NW, R, 3>(p, nobar, grid, st); break;
+    }
+}
 template <int NW, int R>
 static void launch_dom(const Dom3 &p, int slot, bool ortho, unsigned grid, cudaStream_t st) {
     switch (slot) {
@@ -1151,20 +1459,21 @@ static int launch_node_update(svlgpu_model *m, const double *U, const double *Up
                 p.tiles_x = d.tiles_x; p.tiles_y = d.tiles_y; p.kz = d.kz; p.dom = d.cls; p.mode = mode;
                 const unsigned grid = (unsigned)(d.tiles_x * d.tiles_y * d.zchunks);
                 timer_begin(m, 0);
-                if (d.pure) launch_tma<kDomNW, kDomR>(p, d.slot, d.ortho, grid, m->stream);
+                if (d.pure && d.sym && d.v4 && d.rows == 6) launch_v4<kDomNW, 6>(p, d.slot, d.nobar, grid, m->stream);
+                else if (d.pure && d.sym && d.v4) launch_v4<kDomNW, kDomR>(p, d.slot, d.nobar, grid, m->stream);
+                else if (d.pure) launch_tma<kDomNW, kDomR>(p, d.slot, d.ortho, grid, m->stream);
                 else launch_dom<kDomNW, kDomR>(p, d.slot, d.ortho, grid, m->stream);
                 timer_end(m, 0);
                 m->total_launches++;
             }
-            if (b.n_glist) {
+            if (b.n_shell_chunks) {
                 // the shell classes write nodes no other kernel of the step writes: run them beside the bulk kernels
-                Gat3 p;
-                p.U = U; p.Up = Up; p.Un = Un; p.cls = b.d_cls; p.tbl = b.d_tbl; p.list = b.d_glist;
-                p.dof0 = b.dof0; p.n = b.n_glist; p.nx = b.nx; p.ny = b.ny; p.nz = b.nz; p.mode = mode;
-                p.target = nullptr; p.hF = nullptr;
+                Shell3 p;
+                p.U = U; p.Up = Up; p.Un = Un; p.tbl = b.d_tbl; p.list = b.d_shell_list; p.chunk_cls = b.d_shell_cls;
+                p.dof0 = b.dof0; p.nx = b.nx; p.ny = b.ny; p.nz = b.nz; p.mode = mode;
                 cudaStream_t st = (m->overlap && !m->kernel_timing) ? m->side[1] : m->stream;
                 timer_begin(m, 4);
-                k_stencil3_gather<<<(b.n_glist + 127) / 128, 128, 0, st>>>(p);
+                k_stencil3_shell<<<b.n_shell_chunks, 128, 0, st>>>(p);
                 timer_end(m, 4);
                 if (st != m->stream) shell_on_side = true;
                 m->total_launches++;
@@ -1461,6 +1770,10 @@ template <int SLOT> static int cfg_slot() {
     CUDA_OK(cudaFuncSetAttribute(k_stencil3_dom<kDomNW, kDomR, SLOT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stencil3_smem(kDomNW, kDomR)));
     CUDA_OK(cudaFuncSetAttribute(k_stencil3_tma<kDomNW, kDomR, SLOT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stencil3_tma_smem(kDomNW, kDomR)));
     CUDA_OK(cudaFuncSetAttribute(k_stencil3_tma<kDomNW, kDomR, SLOT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stencil3_tma_smem(kDomNW, kDomR)));
+    CUDA_OK(cudaFuncSetAttribute(k_stencil3_v4<kDomNW, kDomR, SLOT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stencil3_v4_smem(kDomNW, kDomR)));
+    CUDA_OK(cudaFuncSetAttribute(k_stencil3_v4<kDomNW, kDomR, SLOT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stencil3_v4_smem(kDomNW, kDomR)));
+    CUDA_OK(cudaFuncSetAttribute(k_stencil3_v4<kDomNW, 6, SLOT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stencil3_v4_smem(kDomNW, 6)));
+    CUDA_OK(cudaFuncSetAttribute(k_stencil3_v4<kDomNW, 6, SLOT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stencil3_v4_smem(kDomNW, 6)));
     return 0;
 }
 int configure_kernels() {
@@ -1469,5 +1782,7 @@ int configure_kernels() {
     return 0;
 }
 bool stencil_entry_nonzero(int di, int b, int dj, int s, int a) { return stencil_nz(di, b, dj, s, a); }
+int stencil_entry_sym_index(int di, int b, int dj, int s, int a) { return stencil_sym_idx(di, b, dj, s, a); }
+bool stencil_entry_sym_negated(int di, int b, int dj, int s, int a) { return stencil_sym_neg(di, b, dj, s, a); }
 
 }  // namespace svl

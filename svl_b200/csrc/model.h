@@ -55,14 +55,23 @@ struct Block {
         int bi0 = 0, bj0 = 0, bk0 = 0, bk1 = 0;      // box of the nodes of this class
         int bi1 = 0, bj1 = 0;
         bool pure = false;                           // the class fills its box and all 27 neighbours exist -> TMA kernel
+        bool sym = false;                            // stencil even / odd in the offsets (k_stencil3_v4 SYM)
+        bool v4 = true;                              // barrier-free renaming kernel (SVLGPU_STENCIL_V=3 selects the older one)
+        int rows = 4;                                // lattice rows per thread (4 or 6)
+        bool nobar = false;                          // k_stencil3_v4 without the per-plane CTA barrier (SVLGPU_STENCIL_NOBAR)
         int tiles_x = 0, tiles_y = 0, zchunks = 0, kz = 0;
         double tbl[276];
         int64_t nodes = 0;
     };
     std::vector<Dom> doms;
-    int32_t *d_glist = nullptr;
+    int32_t *d_glist = nullptr;      // remaining stencil nodes sorted by class (halo-free listing)
     int n_glist = 0;
+    int32_t *d_shell_list = nullptr; // the same nodes cut into one-class chunks of kShellChunk (padded with -1)
+    uint8_t *d_shell_cls = nullptr;  // class of each chunk
+    int n_shell_chunks = 0;
 };
+constexpr int kShellNPT = 4;         // nodes per thread of k_stencil3_shell
+constexpr int kShellChunk = 128 * kShellNPT;
 constexpr int kDomNW = 4;            // warps per CTA of k_stencil3_dom
 constexpr int kDomR = 4;             // lattice rows per thread
 
@@ -140,6 +149,7 @@ struct HaloDev {
 // PML block: the dofs of the PML nodes plus the soil dofs they are tied to form the part of
 // Keff = M/dt^2 + C/2dt that is not diagonal; it is solved every step by a matrix-free,
 // Jacobi-scaled BiCGStab (pml.cu).  All element matrices live in per-class tables.
+constexpr int kPmlChunk = 8;         // elements of one class per chunk of k_pml_elem_sp (= kPmlG in pml.cu)
 struct PmlDev {
     bool present = false;
     int nde = 72;                    // dofs per element (72 | 20)
@@ -147,6 +157,11 @@ struct PmlDev {
     double *d_A = nullptr;           // [n_cls][nde*nde] Keff_e, stored transposed ([col][row])
     double *d_K = nullptr;           // [n_cls][...] K_e
     double *d_Km = nullptr;          // [n_cls][...] M/dt^2 - C/2dt
+    // pattern-sparse twins [n_cls][npe][sp_q][nde] + one-class element chunks (k_pml_elem_sp); sp_q == 0: dense kernel
+    double *d_sA = nullptr, *d_sK = nullptr, *d_sKm = nullptr;
+    int sp_q = 0, n_chunks = 0;
+    int8_t sp_pat[9][4] = {};
+    int32_t *d_chunk_cls = nullptr, *d_chunk_elem = nullptr;
     int32_t *d_ecls = nullptr;       // [n_elem]
     int32_t *d_edof = nullptr;       // [n_elem][nde] internal dof of every element dof
     int32_t *d_ecd = nullptr;        // [n_elem][nde] unknown index (slaves -> their master's) or -1 (restrained)
@@ -266,6 +281,8 @@ void timer_flush(svlgpu_model *m);
 int configure_kernels();
 size_t stencil3_smem(int nw, int r);
 bool stencil_entry_nonzero(int di, int b, int dj, int s, int a);
+int stencil_entry_sym_index(int di, int b, int dj, int s, int a);
+bool stencil_entry_sym_negated(int di, int b, int dj, int s, int a);
 void forget_const_owner(svlgpu_model *m);
 void graph_destroy(svlgpu_model *m);
 // halo.cu

@@ -426,6 +426,17 @@ int plan_and_upload(svlgpu_model *m) {
                         if (!stencil_entry_nonzero(di, bb, dj, s, a) &&
                             std::fabs(d.tbl[((di * 3 + bb) * 3 + dj) * 10 + s * 3 + a]) > 1e-13 * mx) d.ortho = false;
                 if (getenv("SVLGPU_NO_ORTHO")) d.ortho = false;
+                d.sym = d.ortho && !getenv("SVLGPU_NO_SYM");
+                for (int di = 0; di < 3 && d.sym; di++) for (int bb = 0; bb < 3; bb++) for (int dj = 0; dj < 3; dj++)
+                    for (int s = 0; s < 3; s++) for (int a = 0; a < 3; a++) {
+                        if (!stencil_entry_nonzero(di, bb, dj, s, a)) continue;
+                        const double v = d.tbl[((di * 3 + bb) * 3 + dj) * 10 + s * 3 + a];
+                        const double rep = d.tbl[stencil_entry_sym_index(di, bb, dj, s, a)];
+                        if (std::fabs(v - (stencil_entry_sym_negated(di, bb, dj, s, a) ? -rep : rep)) > 1e-13 * mx) d.sym = false;
+                    }
+                { const char *v = getenv("SVLGPU_STENCIL_V"); d.v4 = !(v && atoi(v) == 3); }
+                { const char *v = getenv("SVLGPU_STENCIL_R"); d.rows = (v && atoi(v) == 6) ? 6 : 4; }
+                d.nobar = getenv("SVLGPU_STENCIL_NOBAR") != nullptr;   // measured slower (prefetch distance 1): profiles/r1l
                 int lo[3] = {NX, NY, NZ}, hi[3] = {-1, -1, -1};
                 for (long long q = 0; q < nbn; q++) {
                     if (cls[q] != c) continue;
@@ -437,13 +448,14 @@ int plan_and_upload(svlgpu_model *m) {
                 d.pure = (cpop[c] == (long long)(hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1)) &&
                          lo[0] >= 1 && lo[1] >= 1 && lo[2] >= 1 && hi[0] <= NX - 2 && hi[1] <= NY - 2 && hi[2] <= NZ - 2 &&
                          !getenv("SVLGPU_NO_TMA");
-                const int TY = kDomNW * kDomR;
+                if (!(d.pure && d.sym && d.v4)) d.rows = 4;
+                const int TY = kDomNW * d.rows;
                 d.tiles_x = (hi[0] - lo[0] + 1 + 31) / 32; d.tiles_y = (hi[1] - lo[1] + 1 + TY - 1) / TY;
                 const int nzb = d.bk1 - d.bk0;
                 int kz = kzs ? atoi(kzs) : 0;
                 if (kz <= 0) {
                     const long long tiles = (long long)d.tiles_x * d.tiles_y;
-                    const long long slots = 148 * 3;              // resident CTAs of the stencil kernel on a B200
+                    const long long slots = 148 * (d.rows == 6 ? 2 : 3);   // resident CTAs of the stencil kernel on a B200
                     const long long one_wave = slots / tiles;     // z-chunks that still fit a single wave
                     if (one_wave >= 1 && (nzb + one_wave - 1) / one_wave <= 48) {
                         // small lattice (e.g. one of 8 partitions of 10^8 DOF): one wave, as many chunks as fit
@@ -464,6 +476,24 @@ int plan_and_upload(svlgpu_model *m) {
             std::stable_sort(glist.begin(), glist.end(), [&](int32_t a, int32_t c2) { return cls[a] < cls[c2]; });
             b.n_glist = (int)glist.size();
             b.d_glist = dupload(m, glist);
+            {
+                std::vector<int32_t> sl;
+                std::vector<uint8_t> sc;
+                size_t i = 0;
+                while (i < glist.size()) {
+                    const uint8_t c = cls[glist[i]];
+                    size_t j = i;
+                    while (j < glist.size() && cls[glist[j]] == c) j++;
+                    for (size_t at = i; at < j; at += kShellChunk) {
+                        sc.push_back(c);
+                        for (size_t q = at; q < at + kShellChunk; q++) sl.push_back(q < j ? glist[q] : -1);
+                    }
+                    i = j;
+                }
+                b.n_shell_chunks = (int)sc.size();
+                b.d_shell_list = dupload(m, sl);
+                b.d_shell_cls = dupload(m, sc);
+            }
         }
         m->n_block_nodes += nst;
         m->n_node_classes += ncls - 1;
@@ -936,6 +966,64 @@ static int plan_pml_nd(svlgpu_model *m, const std::vector<int32_t> &alias, const
     }
     P.d_sc = dupload(m, scl);
     P.d_A = dupload(m, tA); P.d_K = dupload(m, tP); P.d_Km = dupload(m, tK);
+    // pattern-sparse tables + one-class chunks for k_pml_elem_sp
+    if (!getenv("SVLGPU_PML_DENSE")) {
+        constexpr int QMAX = (ND == 3) ? 4 : 3;
+        bool nz[nn][nn] = {};
+        for (size_t c = 0; c < keys.size(); c++)
+            for (int i = 0; i < nde; i++)
+                for (int j = 0; j < nde; j++) {
+                    const size_t at = c * nde * nde + (size_t)j * nde + i;
+                    if (tA[at] != 0.0 || tP[at] != 0.0 || tK[at] != 0.0) nz[i % nn][j % nn] = true;
+                }
+        int q_needed = 0;
+        std::memset(P.sp_pat, 0, sizeof(P.sp_pat));
+        for (int r = 0; r < nn; r++) {
+            int cnt_r = 0;
+            for (int c = 0; c < nn; c++) if (nz[r][c]) { if (cnt_r < 4) P.sp_pat[r][cnt_r] = (int8_t)c; cnt_r++; }
+            q_needed = std::max(q_needed, cnt_r);
+            // padding entries point at the row's own component with a zero coefficient
+            for (int q = cnt_r; q < 4; q++) P.sp_pat[r][q] = (int8_t)r;
+        }
+        if (q_needed <= QMAX) {
+            P.sp_q = QMAX;
+            const size_t per = (size_t)npe * QMAX * nde;
+            std::vector<double> sA(keys.size() * per, 0.0), sK(keys.size() * per, 0.0), sKm(keys.size() * per, 0.0);
+            for (size_t c = 0; c < keys.size(); c++)
+                for (int i = 0; i < nde; i++) {
+                    const int r = i % nn;
+                    int cnt_r = 0;
+                    for (int cc = 0; cc < nn; cc++) {
+                        if (!nz[r][cc]) continue;
+                        for (int k = 0; k < npe; k++) {
+                            const int j = k * nn + cc;
+                            const size_t from = c * nde * nde + (size_t)j * nde + i;
+                            const size_t to = c * per + (size_t)(k * QMAX + cnt_r) * nde + i;
+                            sA[to] = tA[from]; sK[to] = tP[from]; sKm[to] = tK[from];
+                        }
+                        cnt_r++;
+                    }
+                }
+            P.d_sA = dupload(m, sA); P.d_sK = dupload(m, sK); P.d_sKm = dupload(m, sKm);
+            std::vector<int32_t> order(P.n_elem);
+            for (int z = 0; z < P.n_elem; z++) order[z] = z;
+            std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return ecls[x] < ecls[y]; });
+            std::vector<int32_t> ccls, celem;
+            size_t i = 0;
+            while (i < order.size()) {
+                const int c = ecls[order[i]];
+                size_t j = i;
+                while (j < order.size() && ecls[order[j]] == c) j++;
+                for (size_t at = i; at < j; at += kPmlChunk) {
+                    ccls.push_back(c);
+                    for (size_t q = at; q < at + kPmlChunk; q++) celem.push_back(q < j ? order[q] : -1);
+                }
+                i = j;
+            }
+            P.n_chunks = (int)ccls.size();
+            P.d_chunk_cls = dupload(m, ccls); P.d_chunk_elem = dupload(m, celem);
+        }
+    }
     P.d_ecls = dupload(m, ecls); P.d_edof = dupload(m, edof); P.d_ecd = dupload(m, ecd);
     P.d_ye = dalloc<double>(m, (size_t)P.n_elem * nde);
     P.d_c_dof = dupload(m, c_dof); P.d_c_ptr = dupload(m, cnt); P.d_c_slot = dupload(m, slot); P.d_c_hf = dupload(m, c_hf);

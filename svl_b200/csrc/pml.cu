@@ -101,6 +101,100 @@ __global__ void __launch_bounds__(NDE * EPB) k_pml_elem(int n_elem, int mode, co
     ye[(size_t)e * NDE + i] = acc;
 }
 
+// ---- element products, class-blocked and pattern-sparse --------------------------------------------------------------
+// The 9x9 (3-D) / 5x5 (2-D) node-pair blocks of M, C, K carry 33 / 13 structural non-zeros (one
+// diagonal term per row, the s11-s22-s33 compliance block and the u-sigma gradient coupling), so a row of the element
+// matrix holds at most Q = 4 / 3 entries per neighbour node.  Elements are processed in chunks of kPmlG elements of ONE
+// class: a CTA row-thread keeps kPmlG accumulators, so a table entry is loaded once per kPmlG DFMAs and the element
+// vectors come from shared memory as 128-bit loads -- the dense kernel above issues one global and one shared load per
+// DFMA and runs at the LSU limit.  The retained terms are summed in the dense kernel's order (ascending column), the
+// skipped ones are exact zeros, so both kernels return the same bits.
+//   tables  Ts[class][node k][entry q][row i]   (row fastest: coalesced), columns  k * NN + pat[i % NN][q]
+constexpr int kPmlG = kPmlChunk;
+struct PmlSp {
+    int n_chunks, mode;
+    const int32_t *chunk_cls;      // [n_chunks]
+    const int32_t *chunk_elem;     // [n_chunks][kPmlG] element index or -1
+    const int32_t *idx;            // [n_elem][NDE] gather index of every element dof (or -1)
+    const double *T1, *T2;         // sparse class tables
+    const double *x1, *x2, *xs;
+    double *ye;
+    double ftol;
+    const double *part;
+    int rr_slot;
+    double tol2;
+    int8_t pat[9][4];              // column component of entry q of a row of component r (padding: coefficient 0)
+};
+template <int NN, int NPE, int Q, int CPB>
+__global__ void __launch_bounds__(NN * NPE * CPB) k_pml_elem_sp(const PmlSp a) {
+    constexpr int NDE = NN * NPE;
+    __shared__ __align__(16) double sx1[CPB][NDE][kPmlG];
+    __shared__ __align__(16) double sx2[CPB][NDE][kPmlG];
+    if (a.part && slot_total(a.part, a.rr_slot) <= a.tol2 * slot_total(a.part, S_BB) + 1e-280) return;   // converged
+    const int lc = threadIdx.x / NDE, i = threadIdx.x - lc * NDE;
+    const int ch = blockIdx.x * CPB + lc;
+    const bool act = ch < a.n_chunks;
+    int ez[kPmlG];
+    if (act) {
+#pragma unroll
+        for (int g = 0; g < kPmlG; g++) {
+            ez[g] = a.chunk_elem[(size_t)ch * kPmlG + g];
+            double v = 0.0, v2 = 0.0;
+            if (ez[g] >= 0) {
+                const int q = a.idx[(size_t)ez[g] * NDE + i];
+                if (q >= 0) {
+                    v = a.xs ? a.x1[q] * a.xs[q] : a.x1[q];
+                    if (a.mode == 1) v2 = v - a.x2[q];
+                }
+            }
+            sx1[lc][i][g] = v;
+            if (a.mode == 1) sx2[lc][i][g] = v2;
+        }
+    }
+    __syncthreads();
+    if (!act) return;
+    const int r = i % NN;
+    int col[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) col[q] = a.pat[r][q];
+    const size_t tb = (size_t)a.chunk_cls[ch] * NPE * Q * NDE + i;
+    double acc[kPmlG], acc2[kPmlG];
+#pragma unroll
+    for (int g = 0; g < kPmlG; g++) { acc[g] = 0.0; acc2[g] = 0.0; }
+#pragma unroll
+    for (int k = 0; k < NPE; k++) {
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const double t1 = __ldg(a.T1 + tb + (size_t)(k * Q + q) * NDE);
+            const double2 *xv = reinterpret_cast<const double2 *>(&sx1[lc][k * NN + col[q]][0]);
+#pragma unroll
+            for (int g = 0; g < kPmlG / 2; g++) {
+                const double2 x = xv[g];
+                acc[2 * g] = fma(t1, x.x, acc[2 * g]);
+                acc[2 * g + 1] = fma(t1, x.y, acc[2 * g + 1]);
+            }
+            if (a.mode == 1) {
+                const double t2 = __ldg(a.T2 + tb + (size_t)(k * Q + q) * NDE);
+                const double2 *yv = reinterpret_cast<const double2 *>(&sx2[lc][k * NN + col[q]][0]);
+#pragma unroll
+                for (int g = 0; g < kPmlG / 2; g++) {
+                    const double2 x = yv[g];
+                    acc2[2 * g] = fma(t2, x.x, acc2[2 * g]);
+                    acc2[2 * g + 1] = fma(t2, x.y, acc2[2 * g + 1]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < kPmlG; g++) {
+        if (ez[g] < 0) continue;
+        double v = acc[g];
+        if (a.mode == 1) v = acc2[g] - (fabs(v) > a.ftol ? v : 0.0);
+        else if (a.mode == 2 && !(fabs(v) > a.ftol)) v = 0.0;
+        a.ye[(size_t)ez[g] * NDE + i] = v;
+    }
+}
+
 // ---- right-hand side: b~ = W (bext + gather(ye) + soil part);  partial ||b~||^2 ---------------------------------
 __global__ void __launch_bounds__(kRedThreads) k_pml_rhs(int nc, const int32_t *ptr, const int32_t *slot, const double *ye,
                                                          const int32_t *c_dof, const int32_t *c_hf, const double *kms,
@@ -240,7 +334,21 @@ static void launch_elem(svlgpu_model *m, int mode, const int32_t *idx, const dou
 }
 static void elem_products(svlgpu_model *m, int mode, const int32_t *idx, const double *T1, const double *x1, const double *T2,
                           const double *x2, const double *xs, const double *part, int rr_slot, double tol2) {
-    if (m->pml.nde == 72) launch_elem<72, 4>(m, mode, idx, T1, x1, T2, x2, xs, part, rr_slot, tol2);
+    PmlDev &P = m->pml;
+    if (P.sp_q > 0) {
+        // class-blocked sparse kernel: T1 / T2 name the dense tables; use their sparse twins
+        auto sp = [&](const double *T) { return T == P.d_A ? P.d_sA : T == P.d_K ? P.d_sK : T == P.d_Km ? P.d_sKm : nullptr; };
+        PmlSp a;
+        a.n_chunks = P.n_chunks; a.mode = mode; a.chunk_cls = P.d_chunk_cls; a.chunk_elem = P.d_chunk_elem; a.idx = idx;
+        a.T1 = sp(T1); a.T2 = sp(T2); a.x1 = x1; a.x2 = x2; a.xs = xs; a.ye = P.d_ye; a.ftol = P.ftol;
+        a.part = part; a.rr_slot = rr_slot; a.tol2 = tol2;
+        std::memcpy(a.pat, P.sp_pat, sizeof(a.pat));
+        if (P.nde == 72) k_pml_elem_sp<9, 8, 4, 2><<<(P.n_chunks + 1) / 2, 144, 0, m->stream>>>(a);
+        else k_pml_elem_sp<5, 4, 3, 8><<<(P.n_chunks + 7) / 8, 160, 0, m->stream>>>(a);
+        m->total_launches++;
+        return;
+    }
+    if (P.nde == 72) launch_elem<72, 4>(m, mode, idx, T1, x1, T2, x2, xs, part, rr_slot, tol2);
     else launch_elem<20, 8>(m, mode, idx, T1, x1, T2, x2, xs, part, rr_slot, tol2);
 }
 

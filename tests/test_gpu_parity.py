@@ -88,6 +88,29 @@ def test_box_block_vs_oracle(oracle, ne):
     assert np.abs(U - Uref).max() / np.abs(Uref).max() < TOL_LINEAR
 
 
+@pytest.mark.parametrize("env", [{"SVLGPU_STENCIL_V": "3"}, {"SVLGPU_NO_SYM": "1"}, {"SVLGPU_STENCIL_R": "6"},
+                                 {"SVLGPU_STENCIL_R": "6", "SVLGPU_STENCIL_KZ": "5"}, {"SVLGPU_STENCIL_KZ": "4"},
+                                 {"SVLGPU_STENCIL_NOBAR": "1"}, {"SVLGPU_STENCIL_NOBAR": "1", "SVLGPU_STENCIL_KZ": "3"},
+                                 {"SVLGPU_STENCIL_KZ": "1"}, {"SVLGPU_STENCIL_KZ": "2"}])
+@pytest.mark.parametrize("ne", [(40, 35, 20), (67, 30, 13)])
+def test_dominant_class_kernel_variants(oracle, monkeypatch, env, ne):
+    """Every variant of the dominant-class block-stencil kernel (TMA v3, barrier-free v4 with / without the
+    symmetric-coefficient table, 4 or 6 rows per thread, short z-chunks) against the oracle."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    nt = 30
+    m = M.make_box_model(ne, 0.5, nt=nt, rec_nodes=None)
+    nn = m.n_nodes
+    m.rec_nodes = np.array(sorted({0, nn - 1, nn // 2, nn // 3, m.point_loads[0].nodes[0]}), dtype=np.int32)
+    ref, Uref = oracle.run(m, nthreads=8)
+    d = _device(m)
+    out = d.run()[0]
+    assert d.counters()["n_block_nodes"] == nn
+    assert rel_err(out, ref) < TOL_LINEAR
+    U = d.get_state(0)
+    assert np.abs(U - Uref).max() / np.abs(Uref).max() < TOL_LINEAR
+
+
 def test_vel_accel_recorders(oracle):
     m = kat_model()
     d = _device(m, fields=(0, 1, 2))
