@@ -37,13 +37,15 @@ enum svlgpu_elem_kind {          /* Driver.hpp:1185-1305 element names        */
     SVLGPU_LIN3DHEXA8 = 1,       /* 04-Elements/10-Hexahedron/lin3DHexa8.cpp  */
     SVLGPU_LIN2DQUAD4 = 2,       /* 04-Elements/06-Quadrilateral/lin2DQuad4   */
     SVLGPU_PML3DHEXA8 = 3,       /* 04-Elements/10-Hexahedron/PML3DHexa8.cpp  */
-    SVLGPU_PML2DQUAD4 = 4        /* 04-Elements/06-Quadrilateral/PML2DQuad4   */
+    SVLGPU_PML2DQUAD4 = 4,       /* 04-Elements/06-Quadrilateral/PML2DQuad4   */
+    SVLGPU_ZEROLENGTH1D = 5      /* 04-Elements/01-Zero/ZeroLength1D.cpp (Lysmer dashpots, Builder.py:1086-1131) */
 };
 enum svlgpu_mat_kind {           /* Driver.hpp:567-757 material names         */
     SVLGPU_ELASTIC3DLINEAR      = 1,  /* params: E, nu, rho                   */
     SVLGPU_ELASTIC2DPLANESTRAIN = 2,  /* params: E, nu, rho                   */
     SVLGPU_PLASTIC3DJ2          = 3,  /* params: K, G, rho, H, beta, SigmaY   */
-    SVLGPU_PLASTICPLANESTRAINJ2 = 4   /* params: K, G, rho, H, beta, SigmaY   */
+    SVLGPU_PLASTICPLANESTRAINJ2 = 4,  /* params: K, G, rho, H, beta, SigmaY   */
+    SVLGPU_VISCOUS1DLINEAR      = 5   /* params: eta (Driver.hpp:602-607)      */
 };
 enum svlgpu_field {              /* Recorder.cpp:239-269 "resp" values        */
     SVLGPU_DISP = 0, SVLGPU_VEL = 1, SVLGPU_ACCEL = 2, SVLGPU_REACTION = 3
@@ -79,6 +81,10 @@ int svlgpu_add_material(svlgpu_model *m, int kind, const double *params, int npa
  *   LIN3DHEXA8: nattr=0;  LIN2DQUAD4: [th];
  *   PML3DHEXA8: [n, L, R, x0(3), npml(3)]      (Driver.hpp:1288-1305)
  *   PML2DQUAD4: [th, n, L, R, x0(2), npml(2)]  (Driver.hpp:1203-1219)
+ *   ZEROLENGTH1D: 2 nodes per element, [dir]   (Driver.hpp:1072-1078); with
+ *     VISCOUS1DLINEAR it adds eta to the damping diagonal of its free dof
+ *     (ZeroLength1D.cpp:212-231); both ends free would couple two dofs in
+ *     Keff = M/dt^2 + C/2dt and is refused.
  * Elements are numbered in call order (ascending = the reference's std::map
  * iteration order, Assembler.cpp:251).  Returns first element index or -1.      */
 int svlgpu_add_elements(svlgpu_model *m, int kind, int n, const int32_t *conn,

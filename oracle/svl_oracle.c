@@ -499,7 +499,27 @@ static csr tl_to_csr(tlist *l, int n) {
 }
 static void csr_free(csr *A) { free(A->ptr); free(A->col); free(A->val); }
 
-static int elem_nn(int kind) { return (kind == SVLO_LIN3DHEXA8 || kind == SVLO_PML3DHEXA8) ? 8 : 4; }
+static int elem_nn(int kind) { return (kind == SVLO_LIN3DHEXA8 || kind == SVLO_PML3DHEXA8) ? 8 : (kind == SVLO_ZEROLENGTH1D) ? 2 : 4; }
+/* ZeroLength1D::ComputeLocalAxes (04-Elements/01-Zero/ZeroLength1D.cpp:318-352): -1 on node i, +1 on node j, direction dir */
+static void zl_axes(int ndim, int dir, double a[6]) {
+    for (int i = 0; i < 2 * ndim; i++) a[i] = 0.0;
+    a[dir] = -1.0; a[ndim + dir] = 1.0;
+}
+/* PlasticPlaneStrainJ2 (02-Materials/02-NonLinear/PlasticPlaneStrainJ2.cpp:227-278): the 3-D return map on the embedded
+ * tensor [0, e11, e22, 0, e12/2, 0] (:235), stress read back from slots 1, 2, 4 (:118-122)                            */
+static void j2ps_update(const double par[6], const double eps[3], double st[13], double sig[3]) {
+    double e6[6] = {0.0, eps[0], eps[1], 0.0, eps[2], 0.0}, s6[6];
+    svlo_j2_update(par, e6, st, s6);
+    sig[0] = s6[1]; sig[1] = s6[2]; sig[2] = s6[4];
+}
+/* initial tangent K*D + 2G(I - D/3) restricted to slots 1, 2, 4 (PlasticPlaneStrainJ2.cpp:150-166) */
+static void j2ps_C0(const double par[6], double C[9]) {
+    const double K = par[0], G = par[1];
+    const double a = K + 2.0 * G * (1.0 - 1.0 / 3.0), b = K + 2.0 * G * (0.0 - 1.0 / 3.0), c = 2.0 * G * 0.5;
+    double t[9] = {a, b, 0, b, a, 0, 0, 0, c};
+    memcpy(C, t, sizeof t);
+}
+
 static int elem_is_pml(int kind) { return kind == SVLO_PML3DHEXA8 || kind == SVLO_PML2DQUAD4; }
 
 typedef struct {
@@ -537,6 +557,13 @@ static void elem_MC(const svlo_model *m, int e, const elem_rt *rt, double *Me, d
         svlo_quad4_mass(rt->X, at[0], mp[2], m->lumped, Me);
     } else if (kind == SVLO_PML3DHEXA8) {
         svlo_pml3d_matrices(rt->X, mp[0], mp[1], mp[2], at, Me, Ce, NULL, NULL);
+    } else if (kind == SVLO_ZEROLENGTH1D) {
+        /* M = 0 (ZeroLength1D.cpp:176-190); C = eta a a^T (:212-231, Viscous1DLinear.cpp GetDamping) */
+        double a[6];
+        zl_axes(m->ndim, (int)at[0], a);
+        memset(Me, 0, nd * nd * sizeof(double));
+        for (int i = 0; i < nd; i++) for (int j = 0; j < nd; j++) Ce[i * nd + j] = mp[0] * a[i] * a[j];
+        return;
     } else {
         svlo_pml2d_matrices(rt->X, mp[0], mp[1], mp[2], at, Me, Ce, NULL);
     }
@@ -556,7 +583,8 @@ static void elem_MC(const svlo_model *m, int e, const elem_rt *rt, double *Me, d
                 }
                 svlo_hex8_stiffness(rt->X, Cm, K0);
             } else {
-                svlo_planestrain_C(mp[0], mp[1], Cm);
+                if (mk == SVLO_PLASTICPLANESTRAINJ2) j2ps_C0(mp, Cm);
+                else svlo_planestrain_C(mp[0], mp[1], Cm);
                 svlo_quad4_stiffness(rt->X, at[0], Cm, K0);
             }
             for (int i = 0; i < nd * nd; i++) Ce[i] += am * Me[i] + ak * K0[i];
@@ -626,6 +654,10 @@ static void material_update(const svlo_model *m, int e, elem_rt *rt, const doubl
     } else if (kind == SVLO_LIN2DQUAD4) {
         double eps[4][3], C[9];
         svlo_quad4_strain(rt->X, ue, eps);
+        if (mk == SVLO_PLASTICPLANESTRAINJ2) {
+            for (int g = 0; g < 4; g++) j2ps_update(mp, eps[g], rt->st[g], rt->sig[g]);
+            return;
+        }
         svlo_planestrain_C(mp[0], mp[1], C);
         for (int g = 0; g < 4; g++)
             for (int a = 0; a < 3; a++) {
@@ -643,6 +675,10 @@ static void elem_fint(const svlo_model *m, int e, const elem_rt *rt, const doubl
         double s3[4][3];
         for (int g = 0; g < 4; g++) for (int a = 0; a < 3; a++) s3[g][a] = rt->sig[g][a];
         svlo_quad4_force(rt->X, m->elem_attr[10 * e], s3, fe);
+    } else if (kind == SVLO_ZEROLENGTH1D) {
+        /* stress(0) * localAxes with Viscous1DLinear::GetStress() == 0 (ZeroLength1D.cpp:241-256): the dashpot acts
+         * through the damping matrix only                                       */
+        for (int i = 0; i < rt->nd; i++) fe[i] = 0.0;
     } else {
         /* PML: f = K_e u_e, PML3DHexa8.cpp:716-743, PML2DQuad4.cpp:474-494       */
         int nd = rt->nd;

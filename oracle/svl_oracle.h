@@ -24,9 +24,10 @@ extern "C" {
 #endif
 
 /* element kinds / material kinds: same numbers as include/svlgpu.h */
-enum { SVLO_LIN3DHEXA8 = 1, SVLO_LIN2DQUAD4 = 2, SVLO_PML3DHEXA8 = 3, SVLO_PML2DQUAD4 = 4 };
+enum { SVLO_LIN3DHEXA8 = 1, SVLO_LIN2DQUAD4 = 2, SVLO_PML3DHEXA8 = 3, SVLO_PML2DQUAD4 = 4,
+       SVLO_ZEROLENGTH1D = 5 /* attr[0] = direction; conn uses the first 2 slots */ };
 enum { SVLO_ELASTIC3DLINEAR = 1, SVLO_ELASTIC2DPLANESTRAIN = 2, SVLO_PLASTIC3DJ2 = 3,
-       SVLO_PLASTICPLANESTRAINJ2 = 4 };
+       SVLO_PLASTICPLANESTRAINJ2 = 4, SVLO_VISCOUS1DLINEAR = 5 /* par[0] = eta */ };
 
 /* ---- element / material level ------------------------------------------- */
 void svlo_elastic3d_C(double E, double nu, double C[36]);

@@ -149,9 +149,9 @@ class DeviceModel:
             while end < len(ek) and ek[end] == ek[start]:
                 end += 1
             kind = int(ek[start])
-            npe = 8 if kind in (1, 3) else 4
+            npe = {1: 8, 2: 4, 3: 8, 4: 4, 5: 2}[kind]
             conn = A(m.elem_conn[start:end, :npe], np.int32)
-            nattr = {1: 0, 2: 1, 3: 9, 4: 8}[kind]
+            nattr = {1: 0, 2: 1, 3: 9, 4: 8, 5: 1}[kind]
             attrs = A(m.elem_attr[start:end, :nattr], np.float64) if nattr else None  # hex8: none
             if self.L.svlgpu_add_elements(self.h, kind, end - start, _i(conn), _i(A(m.elem_mat[start:end], np.int32)),
                                           _d(attrs), nattr) < 0:

@@ -107,7 +107,7 @@ int svlgpu_add_constraint(svlgpu_model *m, int tag, int slave_total_dof, int nma
 
 int svlgpu_add_material(svlgpu_model *m, int kind, const double *params, int nparams) {
     try {
-        if (!m || m->finalized || nparams > 8 || nparams < 3) { set_error("add_material: bad arguments"); return -1; }
+        if (!m || m->finalized || nparams > 8 || nparams < (kind == SVLGPU_VISCOUS1DLINEAR ? 1 : 3)) { set_error("add_material: bad arguments"); return -1; }
         Material mat;
         mat.kind = kind;
         for (int i = 0; i < 8; i++) mat.p[i] = (i < nparams) ? params[i] : 0.0;
@@ -120,15 +120,17 @@ int svlgpu_add_elements(svlgpu_model *m, int kind, int n, const int32_t *conn, c
                         const double *attrs, int nattr) {
     try {
         if (!m || m->finalized || !m->n_nodes || n <= 0 || !conn || !material) { set_error("add_elements: bad arguments"); return -1; }
-        if (kind < SVLGPU_LIN3DHEXA8 || kind > SVLGPU_PML2DQUAD4) { set_error("add_elements: unknown element kind"); return -1; }
-        const int npe = (kind == SVLGPU_LIN3DHEXA8 || kind == SVLGPU_PML3DHEXA8) ? 8 : 4;
-        if ((npe == 8) != (m->ndim == 3)) { set_error("add_elements: element kind does not match ndim"); return -1; }
+        if (kind < SVLGPU_LIN3DHEXA8 || kind > SVLGPU_ZEROLENGTH1D) { set_error("add_elements: unknown element kind"); return -1; }
+        const int npe = (kind == SVLGPU_LIN3DHEXA8 || kind == SVLGPU_PML3DHEXA8) ? 8 : (kind == SVLGPU_ZEROLENGTH1D) ? 2 : 4;
+        if (kind != SVLGPU_ZEROLENGTH1D && (npe == 8) != (m->ndim == 3)) { set_error("add_elements: element kind does not match ndim"); return -1; }
+        if (kind == SVLGPU_ZEROLENGTH1D && (nattr < 1 || !attrs)) { set_error("add_elements: ZeroLength1D needs its direction"); return -1; }
         if (nattr > 10 || (nattr > 0 && !attrs)) { set_error("add_elements: bad attrs"); return -1; }
         const int first = (int)m->elem_kind.size();
         m->elem_kind.resize(first + n, kind);
         m->elem_conn.resize(8ull * (first + n), 0);
         m->elem_mat.resize(first + n);
         if (nattr > 0 || kind == SVLGPU_LIN2DQUAD4 || !m->elem_attr.empty()) m->elem_attr.resize(10ull * (first + n), 0.0);
+        if (!m->elem_am.empty()) m->elem_am.resize(first + n, 0.0);
         for (int e = 0; e < n; e++) {
             for (int l = 0; l < npe; l++) {
                 const int nd = conn[(size_t)e * npe + l];
@@ -416,7 +418,7 @@ int svlgpu_set_kernel_timing(svlgpu_model *m, int on) {
     return 0;
 }
 int svlgpu_kernel_time(svlgpu_model *m, int which, double *avg_ms, int64_t *launches, int reset) {
-    REQUIRE(m && which >= 0 && which < 6, "kernel_time: bad arguments");
+    REQUIRE(m && which >= 0 && which < kNumTimers, "kernel_time: bad arguments");
     timer_flush(m);
     KernelTimer &t = m->timers[which];
     if (avg_ms) *avg_ms = t.launches ? t.total_ms / t.launches : 0.0;

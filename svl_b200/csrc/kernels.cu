@@ -1062,8 +1062,24 @@ __global__ void __launch_bounds__(128) k_gen_quad4(const GenArgs a) {
     const int mi = a.mat[e];
     const double *mp = a.matpar + 8 * mi;
     double sg[3];
-    iso_stress2(iso_from_E_nu(mp[0], mp[1]), ep, sg);
     const long long ngp = 4ll * a.n, q = 4ll * e + g;
+    if (a.matkind[mi] == SVLGPU_PLASTICPLANESTRAINJ2) {
+        // PlasticPlaneStrainJ2.cpp:227-278: the 3-D return map on the embedded tensor [0, e11, e22, 0, e12/2, 0] (:235),
+        // stress read back from slots 1, 2, 4 (:118-122); the 13 state values keep that embedding
+        J2Par jp = {mp[0], mp[1], mp[3], mp[4], mp[5]};
+        const double e6[6] = {0.0, ep[0], ep[1], 0.0, ep[2], 0.0};
+        double st[13], s6[6];
+#pragma unroll
+        for (int i = 0; i < 13; i++) st[i] = a.state[i * ngp + q];
+        const bool yielded = j2_return_map(jp, e6, st, s6);
+        if (a.commit && act && yielded) {
+#pragma unroll
+            for (int i = 0; i < 13; i++) a.state[i * ngp + q] = st[i];
+        }
+        sg[0] = s6[1]; sg[1] = s6[2]; sg[2] = s6[4];
+    } else {
+        iso_stress2(iso_from_E_nu(mp[0], mp[1]), ep, sg);
+    }
     if (a.gp && act) {
 #pragma unroll
         for (int i = 0; i < 3; i++) { a.gp[i * ngp + q] = ep[i]; a.gp[(3 + i) * ngp + q] = sg[i]; }
@@ -1320,7 +1336,7 @@ __global__ void k_setk(int32_t *kctl, int slot, int off) { kctl[slot] = kctl[0] 
 // ------------------------------------------------------------------------------------------
 // host drivers
 // ------------------------------------------------------------------------------------------
-static void timer_begin(svlgpu_model *m, int which) {
+void timer_begin(svlgpu_model *m, int which) {
     if (!m->kernel_timing) return;
     KernelTimer &t = m->timers[which];
     if (!t.e0) { cudaEventCreate(&t.e0); cudaEventCreate(&t.e1); }
@@ -1332,7 +1348,7 @@ static void timer_begin(svlgpu_model *m, int which) {
     }
     cudaEventRecord(t.e0, m->stream);
 }
-static void timer_end(svlgpu_model *m, int which) {
+void timer_end(svlgpu_model *m, int which) {
     if (!m->kernel_timing) return;
     KernelTimer &t = m->timers[which];
     cudaEventRecord(t.e1, m->stream);
@@ -1340,7 +1356,7 @@ static void timer_end(svlgpu_model *m, int which) {
     t.launches++;
 }
 void timer_flush(svlgpu_model *m) {
-    for (int i = 0; i < 6; i++) {
+    for (int i = 0; i < kNumTimers; i++) {
         KernelTimer &t = m->timers[i];
         if (t.pending) {
             float ms = 0;

@@ -79,6 +79,9 @@ constexpr int kDomR = 4;             // lattice rows per thread
 constexpr int kTbl3Stride = 276;     // 27 x (9 coefficients + 1 pad) + kinv[3] + km[3]
 constexpr int kTbl2Stride = 40;      // 9 x (2x2) + kinv[2] + km[2]
 
+// kernel timers: 0 dominant stencil, 1 Gauss-point elements, 2 generic node gather, 3 point loads, 4 shell classes,
+// 5 DRM, 6 PML element products, 7 PML gathers / right-hand side, 8 PML Krylov vector updates + scatter
+constexpr int kNumTimers = 9;
 struct KernelTimer {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     double total_ms = 0.0;
@@ -265,7 +268,7 @@ struct svlgpu_model {
     int64_t total_launches = 0, launches_per_step = 0;
     int64_t n_block_nodes = 0, n_generic_elements = 0, n_elem_classes = 0, n_node_classes = 0;
     bool kernel_timing = false;
-    svl::KernelTimer timers[6];
+    svl::KernelTimer timers[svl::kNumTimers];
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_step_ms = 0.0;
     int steps_done = 0;
@@ -278,6 +281,8 @@ int run_steps(svlgpu_model *m, int k0, int k1, const double *dev_amp);      // k
 int compute_internal_force(svlgpu_model *m, double *F_host);
 int gather_state(svlgpu_model *m, int field, const int32_t *dofs, int n, double *out);
 void timer_flush(svlgpu_model *m);
+void timer_begin(svlgpu_model *m, int which);
+void timer_end(svlgpu_model *m, int which);
 int configure_kernels();
 size_t stencil3_smem(int nw, int r);
 bool stencil_entry_nonzero(int di, int b, int dj, int s, int a);

@@ -57,7 +57,7 @@ struct ElemClass {
     double mnode[8];             // lumped nodal mass of each local node
 };
 
-static int kind_npe(int k) { return (k == SVLGPU_LIN3DHEXA8 || k == SVLGPU_PML3DHEXA8) ? 8 : 4; }
+static int kind_npe(int k) { return (k == SVLGPU_LIN3DHEXA8 || k == SVLGPU_PML3DHEXA8) ? 8 : (k == SVLGPU_ZEROLENGTH1D) ? 2 : 4; }
 static const int kHexPos[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
 static const int kQuadPos[4][2] = {{0, 0}, {1, 0}, {1, 1}, {0, 1}};
 
@@ -122,7 +122,8 @@ int plan_and_upload(svlgpu_model *m) {
         const int mk = m->materials[m->elem_mat[e]].kind;
         const bool pml = (k == SVLGPU_PML3DHEXA8 || k == SVLGPU_PML2DQUAD4);
         const bool ok = (k == SVLGPU_LIN3DHEXA8 && (mk == SVLGPU_ELASTIC3DLINEAR || mk == SVLGPU_PLASTIC3DJ2)) ||
-                        (k == SVLGPU_LIN2DQUAD4 && mk == SVLGPU_ELASTIC2DPLANESTRAIN) ||
+                        (k == SVLGPU_LIN2DQUAD4 && (mk == SVLGPU_ELASTIC2DPLANESTRAIN || mk == SVLGPU_PLASTICPLANESTRAINJ2)) ||
+                        (k == SVLGPU_ZEROLENGTH1D && mk == SVLGPU_VISCOUS1DLINEAR) ||
                         (k == SVLGPU_PML3DHEXA8 && mk == SVLGPU_ELASTIC3DLINEAR) ||
                         (k == SVLGPU_PML2DQUAD4 && mk == SVLGPU_ELASTIC2DPLANESTRAIN);
         if (!ok) { set_error("unsupported element/material combination"); return 1; }
@@ -149,7 +150,7 @@ int plan_and_upload(svlgpu_model *m) {
         std::vector<int64_t> key;
         for (int e = 0; e < nE; e++) {
             const int kind = m->elem_kind[e], npe = kind_npe(kind);
-            if (kind == SVLGPU_PML3DHEXA8 || kind == SVLGPU_PML2DQUAD4) { elem_cls[e] = -1; continue; }
+            if (kind == SVLGPU_PML3DHEXA8 || kind == SVLGPU_PML2DQUAD4 || kind == SVLGPU_ZEROLENGTH1D) { elem_cls[e] = -1; continue; }
             const int32_t *cn = &m->elem_conn[8ll * e];
             const double *x0 = &m->coords[(size_t)nd * cn[0]], *x1 = &m->coords[(size_t)nd * cn[1]];
             double h = 0;
@@ -209,6 +210,20 @@ int plan_and_upload(svlgpu_model *m) {
     }
     std::vector<int32_t> inc_count(nN, 0);
     for (int e = 0; e < nE; e++) {
+        if (m->elem_kind[e] == SVLGPU_ZEROLENGTH1D) {
+            // Lysmer dashpot: no mass, no internal force (Viscous1DLinear::GetStress() == 0), C_e = eta a a^T with
+            // a = -1 on node i, +1 on node j along `dir` (ZeroLength1D.cpp:212-231, 318-352).  With one end
+            // restrained the free-free part of C is the diagonal entry eta.
+            const int dir = (int)m->attr(e, 0);
+            const double eta = m->materials[m->elem_mat[e]].p[0];
+            const int ni = m->elem_conn[8ll * e], nj = m->elem_conn[8ll * e + 1];
+            if (dir < 0 || dir >= nd || m->node_ndof[ni] <= dir || m->node_ndof[nj] <= dir) { set_error("ZeroLength1D: direction out of range"); return 1; }
+            const int qi = m->node_ptr[ni] + dir, qj = m->node_ptr[nj] + dir;
+            const bool fi = m->freedof[qi] != -1, fj = m->freedof[qj] != -1;
+            if (fi && fj) { set_error("ZeroLength1D between two unrestrained dofs couples them in Keff: not supported by the explicit device path"); return 1; }
+            if (std::fabs(eta) > mtol) { if (fi) cdiag[qi] += eta; if (fj) cdiag[qj] += eta; }
+            continue;
+        }
         if (elem_cls[e] < 0) continue;               // PML: consistent M and C, handled by the block solve
         const ElemClass &ec = classes[elem_cls[e]];
         const int npe = kind_npe(ec.kind);
@@ -516,7 +531,7 @@ int plan_and_upload(svlgpu_model *m) {
             gidx[e] = (int)g.elems.size();
             g.elems.push_back(e);
             gset_of[e] = (m->elem_kind[e] == SVLGPU_LIN3DHEXA8) ? 0 : 1;
-            if (m->materials[m->elem_mat[e]].kind == SVLGPU_PLASTIC3DJ2) g.has_j2 = true;
+            if (m->materials[m->elem_mat[e]].kind == SVLGPU_PLASTIC3DJ2 || m->materials[m->elem_mat[e]].kind == SVLGPU_PLASTICPLANESTRAINJ2) g.has_j2 = true;
         }
         m->gsets.push_back(gh);
         m->gsets.push_back(gq);

@@ -29,6 +29,7 @@ constexpr int kRedBlocks = 296;      // 2 per SM; every reduction writes kRedBlo
 constexpr int kRedThreads = 256;
 // partial-sum slots
 enum { S_BB = 0, S_RHO = 1, S_RHV = 2, S_TS = 3, S_TT = 4, S_RR0 = 5, S_RR1 = 6, S_NSLOT = 7 };
+constexpr int kFlagAt = S_NSLOT * kRedBlocks + 16;   // converged flag, behind the partial slots and the 8 carried scalars
 
 __device__ __forceinline__ double block_sum(double v) {
     __shared__ double sh[kRedThreads / 32];
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(NDE * EPB) k_pml_elem(int n_elem, int mode, co
                                                        const double *__restrict__ xs, double ftol, const double *part,
                                                        int rr_slot, double tol2) {
     __shared__ double sx1[EPB][NDE], sx2[EPB][NDE];
-    if (part && slot_total(part, rr_slot) <= tol2 * slot_total(part, S_BB) + 1e-280) return;   // solver already converged
+    if (part && part[kFlagAt] != 0.0) return;             // solver already converged
     const int le = threadIdx.x / NDE, i = threadIdx.x - le * NDE;
     const int e = blockIdx.x * EPB + le;
     const bool act = e < n_elem;
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(NN * NPE * CPB) k_pml_elem_sp(const PmlSp a) {
     constexpr int NDE = NN * NPE;
     __shared__ __align__(16) double sx1[CPB][NDE][kPmlG];
     __shared__ __align__(16) double sx2[CPB][NDE][kPmlG];
-    if (a.part && slot_total(a.part, a.rr_slot) <= a.tol2 * slot_total(a.part, S_BB) + 1e-280) return;   // converged
+    if (a.part && a.part[kFlagAt] != 0.0) return;         // solver already converged
     const int lc = threadIdx.x / NDE, i = threadIdx.x - lc * NDE;
     const int ch = blockIdx.x * CPB + lc;
     const bool act = ch < a.n_chunks;
@@ -212,7 +213,10 @@ __global__ void __launch_bounds__(kRedThreads) k_pml_rhs(int nc, const int32_t *
         acc = fma(v, v, acc);
     }
     const double s = block_sum(acc);
-    if (threadIdx.x == 0) part[S_BB * kRedBlocks + blockIdx.x] = s;
+    if (threadIdx.x == 0) {
+        part[S_BB * kRedBlocks + blockIdx.x] = s;
+        if (blockIdx.x == 0) part[kFlagAt] = 0.0;
+    }
 }
 
 // ---- out = W (dsoil * in + gather(ye)); optional dots with up to two vectors -----------------------------------
@@ -224,7 +228,7 @@ __global__ void __launch_bounds__(kRedThreads) k_pml_gather(int nc, int mode, co
                                                             const double *sc, const double *in, double *out, const double *b, double *r,
                                                             double *rh, double *p, const double *s, double *part,
                                                             int rr_slot, double tol2) {
-    if (mode != 0 && slot_total(part, rr_slot) <= tol2 * slot_total(part, S_BB) + 1e-280) return;
+    if (mode != 0 && part[kFlagAt] != 0.0) return;
     double a0 = 0.0, a1 = 0.0;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
         double v = dsoil[c] * (sc[c] * in[c]);
@@ -256,7 +260,7 @@ __global__ void __launch_bounds__(kRedThreads) k_pml_gather(int nc, int mode, co
 // p = r + beta (p - omega v)
 __global__ void __launch_bounds__(kRedThreads) k_bicg_p(int nc, int first, const double *r, double *p, const double *v,
                                                         double *scal, const double *part, int rr_slot, double tol2) {
-    if (slot_total(part, rr_slot) <= tol2 * slot_total(part, S_BB) + 1e-280) return;
+    if (part[kFlagAt] != 0.0) return;
     const double rho = slot_total(part, S_RHO);
     if (!first) {
         const double beta = (rho / scal[0]) * (scal[1] / scal[2]);
@@ -269,7 +273,7 @@ __global__ void __launch_bounds__(kRedThreads) k_bicg_p(int nc, int first, const
 // s = r - alpha v
 __global__ void __launch_bounds__(kRedThreads) k_bicg_s(int nc, const double *r, const double *v, double *s, double *scal,
                                                         const double *part, int rr_slot, double tol2) {
-    if (slot_total(part, rr_slot) <= tol2 * slot_total(part, S_BB) + 1e-280) return;
+    if (part[kFlagAt] != 0.0) return;
     const double rhv = slot_total(part, S_RHV);
     const double alpha = scal[3] / rhv;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) s[c] = r[c] - alpha * v[c];
@@ -279,13 +283,8 @@ __global__ void __launch_bounds__(kRedThreads) k_bicg_s(int nc, const double *r,
 __global__ void __launch_bounds__(kRedThreads) k_bicg_x(int nc, double *x, const double *p, const double *s, const double *t,
                                                         double *r, const double *rh, double *scal, double *part,
                                                         int rr_slot, double tol2) {
-    const bool conv = slot_total(part, rr_slot) <= tol2 * slot_total(part, S_BB) + 1e-280;
+    if (part[kFlagAt] != 0.0) return;
     const int nslot = (rr_slot == S_RR0) ? S_RR1 : S_RR0;
-    if (conv) {
-        // keep the converged flag alive in the slot the next iteration reads
-        if (threadIdx.x == 0) part[nslot * kRedBlocks + blockIdx.x] = part[rr_slot * kRedBlocks + blockIdx.x];
-        return;
-    }
     const double tt = slot_total(part, S_TT), ts = slot_total(part, S_TS);
     const double omega = tt > 0.0 ? ts / tt : 0.0;
     const double alpha = scal[4];
@@ -306,9 +305,16 @@ __global__ void __launch_bounds__(kRedThreads) k_bicg_x(int nc, double *x, const
         if (blockIdx.x == 0) { scal[0] = scal[3]; scal[1] = alpha; scal[2] = omega; }
     }
 }
-__global__ void k_pml_norms(const double *part, int rr_slot, double *out) {
+// convergence test after every residual update: one warp sums the partials once, every later kernel of the solve reads
+// one word (a per-CTA re-summation of the partials cost 86 us per launch on 38 000 CTAs: profiles/r1n).  out = {rr, bb}
+// of the last test that ran; the flag is sticky until the next right-hand side clears it.
+__global__ void k_pml_flag(double *part, int rr_slot, double tol2, double *out) {
+    if (part[kFlagAt] != 0.0) return;
     const double rr = slot_total(part, rr_slot), bb = slot_total(part, S_BB);
-    if (threadIdx.x == 0) { out[0] = rr; out[1] = bb; }
+    if (threadIdx.x == 0) {
+        out[0] = rr; out[1] = bb;
+        if (rr <= tol2 * bb + 1e-280 || !(rr == rr)) part[kFlagAt] = 1.0;
+    }
 }
 // U_{n+1} = U_n + T dU on every dof of the block (slaves take their master's increment, Mesh.cpp:360-375)
 __global__ void k_pml_scatter(int n, const int32_t *dof, const int32_t *cix, const double *x, const double *sc,
@@ -335,6 +341,8 @@ static void launch_elem(svlgpu_model *m, int mode, const int32_t *idx, const dou
 static void elem_products(svlgpu_model *m, int mode, const int32_t *idx, const double *T1, const double *x1, const double *T2,
                           const double *x2, const double *xs, const double *part, int rr_slot, double tol2) {
     PmlDev &P = m->pml;
+    timer_begin(m, 6);
+    struct End { svlgpu_model *m; ~End() { timer_end(m, 6); } } end_{m};
     if (P.sp_q > 0) {
         // class-blocked sparse kernel: T1 / T2 name the dense tables; use their sparse twins
         auto sp = [&](const double *T) { return T == P.d_A ? P.d_sA : T == P.d_K ? P.d_sK : T == P.d_Km ? P.d_sKm : nullptr; };
@@ -360,32 +368,47 @@ int pml_step(svlgpu_model *m, const double *U, const double *Up, double *Un) {
     double *scal = P.d_part + S_NSLOT * kRedBlocks;       // 8 carried scalars behind the partial slots
     // right-hand side
     elem_products(m, 1, P.d_edof, P.d_K, U, P.d_Km, Up, nullptr, nullptr, 0, 0.0);
+    timer_begin(m, 7);
     k_pml_rhs<<<kRedBlocks, kRedThreads, 0, st>>>(P.nc, P.d_c_ptr, P.d_c_slot, P.d_ye, P.d_c_dof, P.d_c_hf, P.d_kms, m->halo.d_hF,
                                                   U, Up, P.d_bext, P.d_w, P.d_b, P.d_part);
+    timer_end(m, 7);
     // initial residual with the previous increment as the starting guess
     elem_products(m, 0, P.d_ecd, P.d_A, P.d_x, nullptr, nullptr, P.d_sc, nullptr, 0, 0.0);
     int rr = S_RR0;
+    timer_begin(m, 7);
     k_pml_gather<<<kRedBlocks, kRedThreads, 0, st>>>(P.nc, 0, P.d_c_ptr, P.d_c_slot, P.d_ye, P.d_diag, P.d_w, P.d_sc, P.d_x, nullptr, P.d_b,
                                                      P.d_r, P.d_rh, P.d_p, nullptr, P.d_part, rr, tol2);
-    m->total_launches += 2;
+    timer_end(m, 7);
+    k_pml_flag<<<1, 32, 0, st>>>(P.d_part, rr, tol2, scal + 6);
+    m->total_launches += 3;
     int it = 0;
     bool done = false;
     int batch = std::max(2, std::min(P.last_iters, P.max_iter));
     while (!done) {
         for (int q = 0; q < batch; q++, it++) {
+            timer_begin(m, 8);
             k_bicg_p<<<kRedBlocks, kRedThreads, 0, st>>>(P.nc, it == 0, P.d_r, P.d_p, P.d_v, scal, P.d_part, rr, tol2);
+            timer_end(m, 8);
             elem_products(m, 0, P.d_ecd, P.d_A, P.d_p, nullptr, nullptr, P.d_sc, P.d_part, rr, tol2);
+            timer_begin(m, 7);
             k_pml_gather<<<kRedBlocks, kRedThreads, 0, st>>>(P.nc, 1, P.d_c_ptr, P.d_c_slot, P.d_ye, P.d_diag, P.d_w, P.d_sc, P.d_p, P.d_v,
                                                              nullptr, nullptr, P.d_rh, nullptr, nullptr, P.d_part, rr, tol2);
+            timer_end(m, 7);
+            timer_begin(m, 8);
             k_bicg_s<<<kRedBlocks, kRedThreads, 0, st>>>(P.nc, P.d_r, P.d_v, P.d_s, scal, P.d_part, rr, tol2);
+            timer_end(m, 8);
             elem_products(m, 0, P.d_ecd, P.d_A, P.d_s, nullptr, nullptr, P.d_sc, P.d_part, rr, tol2);
+            timer_begin(m, 7);
             k_pml_gather<<<kRedBlocks, kRedThreads, 0, st>>>(P.nc, 2, P.d_c_ptr, P.d_c_slot, P.d_ye, P.d_diag, P.d_w, P.d_sc, P.d_s, P.d_t,
                                                              nullptr, nullptr, nullptr, nullptr, P.d_s, P.d_part, rr, tol2);
+            timer_end(m, 7);
+            timer_begin(m, 8);
             k_bicg_x<<<kRedBlocks, kRedThreads, 0, st>>>(P.nc, P.d_x, P.d_p, P.d_s, P.d_t, P.d_r, P.d_rh, scal, P.d_part, rr, tol2);
+            timer_end(m, 8);
             rr = (rr == S_RR0) ? S_RR1 : S_RR0;
-            m->total_launches += 5;
+            k_pml_flag<<<1, 32, 0, st>>>(P.d_part, rr, tol2, scal + 6);
+            m->total_launches += 6;
         }
-        k_pml_norms<<<1, 32, 0, st>>>(P.d_part, rr, scal + 6);
         CUDA_OK(cudaMemcpyAsync(P.h_scal, scal + 6, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
         CUDA_OK(cudaStreamSynchronize(st));
         const double rrv = P.h_scal[0], bb = P.h_scal[1];
@@ -396,7 +419,9 @@ int pml_step(svlgpu_model *m, const double *U, const double *Up, double *Un) {
     }
     P.last_iters = std::max(2, it - 1);
     P.total_iters += it; P.solves++;
+    timer_begin(m, 8);
     k_pml_scatter<<<(P.n_sc + 255) / 256, 256, 0, st>>>(P.n_sc, P.d_sc_dof, P.d_sc_c, P.d_x, P.d_sc, U, Un);
+    timer_end(m, 8);
     m->total_launches++;
     CUDA_OK(cudaGetLastError());
     return 0;

@@ -99,6 +99,8 @@ bool UpdateMesh(Mesh &mesh, const JValue &J) {
         if (ieq(name, "ELASTIC3DLINEAR")) { m.kind = SVLGPU_ELASTIC3DLINEAR; m.par = {a["E"].as_double(), a["nu"].as_double(), a["rho"].as_double()}; }
         else if (ieq(name, "ELASTIC2DPLANESTRAIN")) { m.kind = SVLGPU_ELASTIC2DPLANESTRAIN; m.par = {a["E"].as_double(), a["nu"].as_double(), a["rho"].as_double()}; }
         else if (ieq(name, "PLASTIC3DJ2")) { m.kind = SVLGPU_PLASTIC3DJ2; m.par = {a["K"].as_double(), a["G"].as_double(), a["rho"].as_double(), a["h"].as_double(), a["beta"].as_double(), a["Sy"].as_double()}; }
+        else if (ieq(name, "PLASTICPLANESTRAINJ2")) { m.kind = SVLGPU_PLASTICPLANESTRAINJ2; m.par = {a["K"].as_double(), a["G"].as_double(), a["rho"].as_double(), a["h"].as_double(), a["beta"].as_double(), a["Sy"].as_double()}; }
+        else if (ieq(name, "VISCOUS1DLINEAR")) { m.kind = SVLGPU_VISCOUS1DLINEAR; m.par = {a["eta"].as_double()}; }   // Driver.hpp:602-607
         else { std::cout << "\x1B[31m ERROR: \x1B[0mmaterial " << name << " is not on the GPU explicit path\n"; return true; }
         mesh.Materials[m.tag] = m;
     }
@@ -127,6 +129,7 @@ bool UpdateMesh(Mesh &mesh, const JValue &J) {
         else if (ieq(name, "LIN2DQUAD4")) { e.kind = SVLGPU_LIN2DQUAD4; e.attr = {a["th"].as_double(1.0)}; }
         else if (ieq(name, "PML3DHEXA8")) { e.kind = SVLGPU_PML3DHEXA8; e.attr = {a["n"].as_double(), a["L"].as_double(), a["R"].as_double()}; vec("x0"); vec("npml"); }
         else if (ieq(name, "PML2DQUAD4")) { e.kind = SVLGPU_PML2DQUAD4; e.attr = {a["th"].as_double(1.0), a["n"].as_double(), a["L"].as_double(), a["R"].as_double()}; vec("x0"); vec("npml"); }
+        else if (ieq(name, "ZEROLENGTH1D")) { e.kind = SVLGPU_ZEROLENGTH1D; e.attr = {(double)a["dir"].as_int()}; }   // Driver.hpp:1072-1078
         else { std::cout << "\x1B[31m ERROR: \x1B[0melement " << name << " is not on the GPU explicit path\n"; return true; }
         mesh.Elements[e.tag] = e;
     }

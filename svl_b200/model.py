@@ -22,16 +22,20 @@ from typing import Dict, List, Optional
 
 import numpy as np
 
-LIN3DHEXA8, LIN2DQUAD4, PML3DHEXA8, PML2DQUAD4 = 1, 2, 3, 4
-ELASTIC3DLINEAR, ELASTIC2DPLANESTRAIN, PLASTIC3DJ2, PLASTICPLANESTRAINJ2 = 1, 2, 3, 4
+LIN3DHEXA8, LIN2DQUAD4, PML3DHEXA8, PML2DQUAD4, ZEROLENGTH1D = 1, 2, 3, 4, 5
+ELASTIC3DLINEAR, ELASTIC2DPLANESTRAIN, PLASTIC3DJ2, PLASTICPLANESTRAINJ2, VISCOUS1DLINEAR = 1, 2, 3, 4, 5
 
 ELEM_NAME = {LIN3DHEXA8: "LIN3DHEXA8", LIN2DQUAD4: "LIN2DQUAD4", PML3DHEXA8: "PML3DHEXA8",
-             PML2DQUAD4: "PML2DQUAD4"}
+             PML2DQUAD4: "PML2DQUAD4", ZEROLENGTH1D: "ZEROLENGTH1D"}
+ELEM_NODES = {LIN3DHEXA8: 8, LIN2DQUAD4: 4, PML3DHEXA8: 8, PML2DQUAD4: 4, ZEROLENGTH1D: 2}
+ELEM_NATTR = {LIN3DHEXA8: 0, LIN2DQUAD4: 1, PML3DHEXA8: 9, PML2DQUAD4: 8, ZEROLENGTH1D: 1}
 MAT_NAME = {ELASTIC3DLINEAR: "ELASTIC3DLINEAR", ELASTIC2DPLANESTRAIN: "ELASTIC2DPLANESTRAIN",
-            PLASTIC3DJ2: "PLASTIC3DJ2", PLASTICPLANESTRAINJ2: "PLASTICPLANESTRAINJ2"}
+            PLASTIC3DJ2: "PLASTIC3DJ2", PLASTICPLANESTRAINJ2: "PLASTICPLANESTRAINJ2",
+            VISCOUS1DLINEAR: "VISCOUS1DLINEAR"}
 MAT_KEYS = {ELASTIC3DLINEAR: ["E", "nu", "rho"], ELASTIC2DPLANESTRAIN: ["E", "nu", "rho"],
             PLASTIC3DJ2: ["K", "G", "rho", "h", "beta", "Sy"],
-            PLASTICPLANESTRAINJ2: ["K", "G", "rho", "h", "beta", "Sy"]}
+            PLASTICPLANESTRAINJ2: ["K", "G", "rho", "h", "beta", "Sy"],
+            VISCOUS1DLINEAR: ["eta"]}
 
 
 @dataclass
@@ -257,6 +261,49 @@ def make_area_model(ne, h=1.0, th=1.0, mat=(ELASTIC2DPLANESTRAIN, [1.3e7, 0.3, 2
     return m.number_dofs()
 
 
+def add_base_dashpots(m: Model, vs: float, vp: float, rho: float, h: float, th: float = 1.0) -> Model:
+    """Lysmer-Kuhlemeyer base: every node of the bottom plane (z = min in 3-D, y = min in 2-D) gets a fixed twin
+    node and one ZeroLength1D + Viscous1DLinear dashpot per direction, eta = rho * V * tributary area (Vp along
+    the normal, Vs tangentially) -- what 01-Pre_Process/Method/Builder.py:1086-1131 emits.  The bottom plane must
+    be unrestrained (fix=None).  Call before number_dofs-dependent data (loads, recorders) refer to new nodes;
+    existing node / element indices are unchanged (new nodes and elements are appended)."""
+    nd = m.ndim
+    up = nd - 1
+    zmin = m.coords[:, up].min()
+    base = np.nonzero(np.abs(m.coords[:, up] - zmin) < 1e-9 * max(1.0, h))[0]
+    lo = m.coords[base][:, :up].min(axis=0)
+    hi = m.coords[base][:, :up].max(axis=0)
+    n0 = m.n_nodes
+    twins = np.arange(n0, n0 + len(base), dtype=np.int32)
+    m.coords = np.vstack([m.coords, m.coords[base]])
+    m.node_ndof = np.concatenate([m.node_ndof, np.full(len(base), nd, dtype=np.int32)])
+    fd = np.asarray(m.freedof).reshape(-1)
+    m.freedof = np.concatenate([fd, np.full(len(base) * nd, -1, dtype=np.int32)])
+    mat_of: Dict[float, int] = {}
+    conn, mats, attrs = [], [], []
+    for b, t in zip(base, twins):
+        on_edge = [(abs(m.coords[b, c] - lo[c]) < 1e-9 or abs(m.coords[b, c] - hi[c]) < 1e-9) for c in range(up)]
+        area = (th if nd == 2 else 1.0) * float(np.prod([h * (0.5 if e else 1.0) for e in on_edge]))
+        for d in range(nd):
+            eta = rho * (vp if d == up else vs) * area
+            if eta not in mat_of:
+                mat_of[eta] = len(m.materials)
+                m.materials = list(m.materials) + [(VISCOUS1DLINEAR, [eta])]
+            row = np.zeros(8, dtype=np.int32)
+            row[0], row[1] = t, b                 # fixed twin first, soil node second (Builder.py:1118)
+            conn.append(row); mats.append(mat_of[eta]); a = np.zeros(10); a[0] = d; attrs.append(a)
+    ne0 = m.n_elem
+    m.elem_conn = np.vstack([m.elem_conn, np.array(conn, dtype=np.int32)])
+    m.elem_kind = np.concatenate([m.elem_kind, np.full(len(conn), ZEROLENGTH1D, dtype=np.int32)])
+    m.elem_mat = np.concatenate([m.elem_mat, np.array(mats, dtype=np.int32)])
+    old_attr = m.elem_attr if m.elem_attr is not None else np.zeros((ne0, 10))
+    m.elem_attr = np.vstack([old_attr, np.array(attrs)])
+    if m.elem_am is not None:
+        m.elem_am = np.concatenate([m.elem_am, np.zeros(len(conn))])
+        m.elem_ak = np.concatenate([m.elem_ak, np.zeros(len(conn))])
+    return m.number_dofs()
+
+
 # -------------------------------------------------------------------------------
 # reference JSON writer (SURVEY.md App. D; Core/SeismoVLAB.py:49-298, Outputs.py:29-51)
 # -------------------------------------------------------------------------------
@@ -290,10 +337,12 @@ def write_reference_json(m: Model, directory: str, name: str = "Model", combo: s
     J["Elements"] = {}
     for e in range(m.n_elem):
         kind = int(m.elem_kind[e])
-        nn = 8 if kind in (LIN3DHEXA8, PML3DHEXA8) else 4
+        nn = ELEM_NODES[kind]
         at = m.elem_attr[e] if m.elem_attr is not None else np.zeros(10)
         attr = {"material": int(m.elem_mat[e]) + 1, "rule": "GAUSS", "np": nn}
-        if kind == LIN2DQUAD4:
+        if kind == ZEROLENGTH1D:               # Driver.hpp:1072-1078
+            attr = {"material": int(m.elem_mat[e]) + 1, "dir": int(at[0])}
+        elif kind == LIN2DQUAD4:
             attr["th"] = float(at[0])
         elif kind == PML3DHEXA8:
             attr.update({"n": float(at[0]), "L": float(at[1]), "R": float(at[2]),

@@ -95,10 +95,37 @@ def pml3d():
     return m
 
 
+def _soil_speeds():
+    lam = SOIL[0] * SOIL[1] / ((1 + SOIL[1]) * (1 - 2 * SOIL[1])); mu = SOIL[0] / (2 * (1 + SOIL[1]))
+    return math.sqrt(mu / SOIL[2]), math.sqrt((lam + 2 * mu) / SOIL[2])
+
+
+def lysmer_column():
+    """Soil column on a Lysmer-Kuhlemeyer base: ZeroLength1D + Viscous1DLinear dashpots between every base node and a
+    fixed twin (Builder.py:1086-1131), as in fixture J05 but under CentralDifference."""
+    m = M.make_box_model((3, 3, 6), 1.0, nt=90, fix=None, load_dir=(4e3, -2e3, 1e4), rec_nodes=[0, 5, 53, 111])
+    vs, vp = _soil_speeds()
+    return M.add_base_dashpots(m, vs, vp, SOIL[2], 1.0)
+
+
+def lysmer_area():
+    m = M.make_area_model((6, 5), 0.5, th=0.8, nt=90, fix=None, load_dir=(3e3, 1e4), rec_nodes=[0, 3, 20, 41])
+    vs, vp = _soil_speeds()
+    return M.add_base_dashpots(m, vs, vp, SOIL[2], 0.5, th=0.8)
+
+
+def j2ps_area():
+    """lin2DQuad4 + PlasticPlaneStrainJ2 (PlasticPlaneStrainJ2.cpp:227-278), loaded into yield."""
+    vp = math.sqrt((J2[0] + 4.0 * J2[1] / 3.0) / J2[2])
+    return M.make_area_model((4, 8), 1.0, th=1.0, mat=(M.PLASTICPLANESTRAINJ2, J2), nt=110, dt=0.5 / vp,
+                             load_dir=(3.0e5, 1.0e5), rec_nodes=[12, 27, 40, 44])
+
+
 CASES = {f.__name__: f for f in (kat444, hex8_distorted, hex8_layered_rayleigh, quad4_area, quad4_distorted,
-                                 j2_column, drm_box, drm_area, pml2d, pml3d)}
+                                 j2_column, drm_box, drm_area, pml2d, pml3d, lysmer_column, lysmer_area, j2ps_area)}
 # tolerance of |oracle - reference| and |device - oracle| per case (max_t|d| / max_t|ref| per dof)
 TOL = {name: 1e-10 for name in CASES}
+TOL["j2ps_area"] = 1e-8
 TOL["j2_column"] = 1e-8        # plastic: looser bound (BASELINE.json north_star), stated in DESIGN.md
 TOL["pml2d"] = 1e-9            # PML: Keff is not diagonal -> iterative block solve (rtol 1e-14), see DESIGN.md
 TOL["pml3d"] = 1e-9

@@ -270,7 +270,8 @@ def test_multigpu_interface_exchange():
 
 
 # ---- the reference's command line / file formats on top of the C ABI (svl_b200/host) ----------------------
-@pytest.mark.parametrize("name", ["kat444", "quad4_area", "drm_box", "j2_column", "hex8_layered_rayleigh", "pml2d", "pml3d"])
+@pytest.mark.parametrize("name", ["kat444", "quad4_area", "drm_box", "j2_column", "hex8_layered_rayleigh", "pml2d", "pml3d",
+                                  "lysmer_column", "lysmer_area", "j2ps_area"])
 def test_host_driver_reads_reference_files_and_writes_reference_recorders(tmp_path, name):
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
