@@ -659,6 +659,8 @@ struct Shell3 {
     const uint8_t *chunk_cls; // [n_chunks]
     long long dof0;
     int nx, ny, nz, mode;
+    const int32_t *target;    // halo pass: interface index of each list entry (else null)
+    double *hF;               // halo pass: [n_if][3] partial internal force
 };
 __global__ void __launch_bounds__(128) k_stencil3_shell(const Shell3 p) {
     __shared__ double T[kTbl3Stride];
@@ -702,6 +704,15 @@ __global__ void __launch_bounds__(128) k_stencil3_shell(const Shell3 p) {
                 }
             }
         }
+    }
+    if (p.hF) {
+#pragma unroll
+        for (int n = 0; n < kShellNPT; n++) {
+            if (q[n] < 0) continue;
+            double *o = p.hF + 3ll * p.target[(size_t)blockIdx.x * kShellChunk + n * 128 + threadIdx.x];
+            o[0] = F[n][0]; o[1] = F[n][1]; o[2] = F[n][2];
+        }
+        return;
     }
 #pragma unroll
     for (int n = 0; n < kShellNPT; n++) {
@@ -1482,14 +1493,17 @@ static int launch_node_update(svlgpu_model *m, const double *U, const double *Up
                 timer_end(m, 0);
                 m->total_launches++;
             }
-            if (b.n_shell_chunks) {
+            if (mode == 0 ? b.n_shell_chunks : b.n_shell_all) {
                 // the shell classes write nodes no other kernel of the step writes: run them beside the bulk kernels
                 Shell3 p;
-                p.U = U; p.Up = Up; p.Un = Un; p.tbl = b.d_tbl; p.list = b.d_shell_list; p.chunk_cls = b.d_shell_cls;
-                p.dof0 = b.dof0; p.nx = b.nx; p.ny = b.ny; p.nz = b.nz; p.mode = mode;
+                p.U = U; p.Up = Up; p.Un = Un; p.tbl = b.d_tbl;
+                p.list = mode == 0 ? b.d_shell_list : b.d_shell_all_list;
+                p.chunk_cls = mode == 0 ? b.d_shell_cls : b.d_shell_all_cls;
+                const int nchunks = mode == 0 ? b.n_shell_chunks : b.n_shell_all;
+                p.dof0 = b.dof0; p.nx = b.nx; p.ny = b.ny; p.nz = b.nz; p.mode = mode; p.target = nullptr; p.hF = nullptr;
                 cudaStream_t st = (m->overlap && !m->kernel_timing) ? m->side[1] : m->stream;
                 timer_begin(m, 4);
-                k_stencil3_shell<<<b.n_shell_chunks, 128, 0, st>>>(p);
+                k_stencil3_shell<<<nchunks, 128, 0, st>>>(p);
                 timer_end(m, 4);
                 if (st != m->stream) shell_on_side = true;
                 m->total_launches++;
@@ -1531,7 +1545,12 @@ int halo_lattice_force(svlgpu_model *m, const double *U) {
     for (auto &l : h.lats) {
         if (!l.n) continue;
         const Block &b = m->blocks[l.block];
-        if (b.ndim == 3) {
+        if (b.ndim == 3 && l.n_chunks) {
+            Shell3 p;
+            p.U = U; p.Up = nullptr; p.Un = nullptr; p.tbl = b.d_tbl; p.list = l.d_chunk_list; p.chunk_cls = l.d_chunk_cls;
+            p.dof0 = b.dof0; p.nx = b.nx; p.ny = b.ny; p.nz = b.nz; p.mode = 1; p.target = l.d_chunk_target; p.hF = h.d_hF;
+            k_stencil3_shell<<<l.n_chunks, 128, 0, m->stream>>>(p);
+        } else if (b.ndim == 3) {
             Gat3 p;
             p.U = U; p.Up = nullptr; p.Un = nullptr; p.cls = b.d_cls; p.tbl = b.d_tbl; p.list = l.d_list;
             p.dof0 = b.dof0; p.n = l.n; p.nx = b.nx; p.ny = b.ny; p.nz = b.nz; p.mode = 1;

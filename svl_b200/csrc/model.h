@@ -66,9 +66,13 @@ struct Block {
     std::vector<Dom> doms;
     int32_t *d_glist = nullptr;      // remaining stencil nodes sorted by class (halo-free listing)
     int n_glist = 0;
-    int32_t *d_shell_list = nullptr; // the same nodes cut into one-class chunks of kShellChunk (padded with -1)
-    uint8_t *d_shell_cls = nullptr;  // class of each chunk
+    int32_t *d_shell_list = nullptr; // those nodes minus the interface nodes, cut into one-class chunks of kShellChunk
+    uint8_t *d_shell_cls = nullptr;  // (padded with -1) + class of each chunk: the step pass of k_stencil3_shell
     int n_shell_chunks = 0;
+    int32_t *d_shell_all_list = nullptr;   // all of them: the force-only pass (Assembler::ComputeInternalForceVector)
+    uint8_t *d_shell_all_cls = nullptr;
+    int n_shell_all = 0;
+    std::vector<uint8_t> h_cls;      // host copy of the class ids (planner scratch)
 };
 constexpr int kShellNPT = 4;         // nodes per thread of k_stencil3_shell
 constexpr int kShellChunk = 128 * kShellNPT;
@@ -141,7 +145,14 @@ struct HaloDev {
     int32_t *d_g_ndof = nullptr, *d_g_ptr = nullptr, *d_g_target = nullptr;
     int64_t *d_g_slot = nullptr;
     // lattice interface nodes, per block: lattice-local ids + interface index
-    struct Lat { int block = 0, n = 0; int32_t *d_list = nullptr, *d_target = nullptr; };
+    struct Lat {
+        int block = 0, n = 0;
+        int32_t *d_list = nullptr, *d_target = nullptr;
+        // 3-D: the same nodes as one-class chunks for k_stencil3_shell (interface index per entry, -1 = padding)
+        int n_chunks = 0;
+        int32_t *d_chunk_list = nullptr, *d_chunk_target = nullptr;
+        uint8_t *d_chunk_cls = nullptr;
+    };
     std::vector<Lat> lats;
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t e_ready = nullptr, e_done = nullptr;

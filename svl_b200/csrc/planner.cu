@@ -57,6 +57,27 @@ struct ElemClass {
     double mnode[8];             // lumped nodal mass of each local node
 };
 
+// one-class chunks of kShellChunk lattice nodes for k_stencil3_shell: `nodes` sorted by class, padded with -1
+static void shell_chunks(const std::vector<int32_t> &nodes, const std::vector<int32_t> *targets, const std::vector<uint8_t> &cls,
+                         std::vector<int32_t> &sl, std::vector<int32_t> &st, std::vector<uint8_t> &sc) {
+    std::vector<int32_t> order(nodes.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = (int32_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return cls[nodes[a]] < cls[nodes[b]]; });
+    size_t i = 0;
+    while (i < order.size()) {
+        const uint8_t c = cls[nodes[order[i]]];
+        size_t j = i;
+        while (j < order.size() && cls[nodes[order[j]]] == c) j++;
+        for (size_t at = i; at < j; at += kShellChunk) {
+            sc.push_back(c);
+            for (size_t q = at; q < at + kShellChunk; q++) {
+                sl.push_back(q < j ? nodes[order[q]] : -1);
+                if (targets) st.push_back(q < j ? (*targets)[order[q]] : -1);
+            }
+        }
+        i = j;
+    }
+}
 static int kind_npe(int k) { return (k == SVLGPU_LIN3DHEXA8 || k == SVLGPU_PML3DHEXA8) ? 8 : (k == SVLGPU_ZEROLENGTH1D) ? 2 : 4; }
 static const int kHexPos[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
 static const int kQuadPos[4][2] = {{0, 0}, {1, 0}, {1, 1}, {0, 1}};
@@ -253,6 +274,10 @@ int plan_and_upload(svlgpu_model *m) {
     }
     m->d_kinv = dupload(m, kinv);
     m->d_km = dupload(m, km);
+
+    std::vector<uint8_t> is_if(nN, 0);                 // interface nodes (filled in for good in the halo section below)
+    for (auto &hp : m->halo_peers) for (int n : hp.nodes) if (n >= 0 && n < nN) is_if[n] = 1;
+    for (int q = 0; q < m->n_int; q++) if (alias[q] != q) is_if[node_of_dof[alias[q]]] = 1;
 
     // ---- D. lattice blocks -> node classes ------------------------------------------------
     // Without a hint (e.g. a model that arrives through the reference's JSON files) guess the lattice of
@@ -492,22 +517,23 @@ int plan_and_upload(svlgpu_model *m) {
             b.n_glist = (int)glist.size();
             b.d_glist = dupload(m, glist);
             {
-                std::vector<int32_t> sl;
+                // step pass: interface nodes (shared with other ranks or tied to the PML block) are finished by
+                // k_halo_fix / the block solve, so the shell kernel skips them; the force-only pass keeps them
+                std::vector<int32_t> sl, st, own;
                 std::vector<uint8_t> sc;
-                size_t i = 0;
-                while (i < glist.size()) {
-                    const uint8_t c = cls[glist[i]];
-                    size_t j = i;
-                    while (j < glist.size() && cls[glist[j]] == c) j++;
-                    for (size_t at = i; at < j; at += kShellChunk) {
-                        sc.push_back(c);
-                        for (size_t q = at; q < at + kShellChunk; q++) sl.push_back(q < j ? glist[q] : -1);
-                    }
-                    i = j;
+                shell_chunks(glist, nullptr, cls, sl, st, sc);
+                b.n_shell_all = (int)sc.size();
+                b.d_shell_all_list = dupload(m, sl); b.d_shell_all_cls = dupload(m, sc);
+                for (int32_t q : glist) if (!is_if[h.node0 + q]) own.push_back(q);
+                if (own.size() == glist.size()) {
+                    b.n_shell_chunks = b.n_shell_all; b.d_shell_list = b.d_shell_all_list; b.d_shell_cls = b.d_shell_all_cls;
+                } else {
+                    sl.clear(); sc.clear();
+                    shell_chunks(own, nullptr, cls, sl, st, sc);
+                    b.n_shell_chunks = (int)sc.size();
+                    b.d_shell_list = dupload(m, sl); b.d_shell_cls = dupload(m, sc);
                 }
-                b.n_shell_chunks = (int)sc.size();
-                b.d_shell_list = dupload(m, sl);
-                b.d_shell_cls = dupload(m, sc);
+                b.h_cls = cls;                      // kept for the halo lists built below
             }
         }
         m->n_block_nodes += nst;
@@ -689,6 +715,13 @@ int plan_and_upload(svlgpu_model *m) {
             HaloDev::Lat l;
             l.block = (int)b; l.n = (int)llist[b].size();
             l.d_list = dupload(m, llist[b]); l.d_target = dupload(m, ltgt[b]);
+            if (m->blocks[b].ndim == 3) {
+                std::vector<int32_t> sl, st;
+                std::vector<uint8_t> sc;
+                shell_chunks(llist[b], &ltgt[b], m->blocks[b].h_cls, sl, st, sc);
+                l.n_chunks = (int)sc.size();
+                l.d_chunk_list = dupload(m, sl); l.d_chunk_target = dupload(m, st); l.d_chunk_cls = dupload(m, sc);
+            }
             h.lats.push_back(l);
         }
         h.n_gen = (int)g_tgt.size();

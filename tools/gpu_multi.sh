@@ -1,0 +1,18 @@
+#!/bin/bash
+# multi-GPU pass (run with gpurun --gpus N): parity of the interface exchange + contract bench at N GPUs
+N=${1:-8}; TAG=${2:-multi}
+O=gpurun_out/$TAG
+mkdir -p $O
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+timeout 600 $TR --master-port 29511 tests/multigpu_check.py > $O/check_n$N.log 2>&1; echo "check exit $?" >> $O/check_n$N.log
+grep -E "multigpu|exit" $O/check_n$N.log | tail -12
+timeout 900 $TR --master-port 29512 bench.py --gpus $N --steps 100 --warmup 5 > $O/bench_weak_n$N.json 2> $O/bench_weak_n$N.err
+timeout 600 $TR --master-port 29513 bench.py --gpus $N --steps 200 --warmup 10 --scaling strong > $O/bench_strong_n$N.json 2> $O/bench_strong_n$N.err
+python - <<PY
+import json
+for k in ("weak","strong"):
+    try:
+        d=json.load(open("$O/bench_%s_n$N.json"%k)); print(k, "N=$N %.4g el/s"%d["value"], "ms/step %.4f"%d["ms_per_step"], "e2e %.4g"%d["e2e"]["value"], d["config"]["partition_grid"], "if nodes", d["config"]["interface_nodes_rank0"])
+    except Exception as e: print(k, "failed", e)
+PY
+tail -3 $O/bench_weak_n$N.err
