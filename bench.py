@@ -353,9 +353,11 @@ def main():
     e2e = {"value": n_elem_total * K / e2e_s, "unit": "element-updates/s",
            "h2d_bytes_per_step": int(allsum(8 * len(m.point_loads))),
            "d2h_bytes_per_step": int(allsum(row.nbytes)), "ms_per_step": 1e3 * e2e_s / K,
-           "note": "one svlgpu_step_host call per step and rank: pinned H2D of the step's load amplitudes, all kernels "
-                   "(+ NCCL interface exchange), pinned D2H of the recorder row, stream sync; the state vectors stay "
-                   "resident in HBM exactly as the reference keeps U,V,A resident in host RAM between steps"}
+           "note": "one svlgpu_step_host call per step and rank with HOST buffers: the step's load amplitudes are read "
+                   "from pinned host memory and the recorder row is written to pinned host memory by the step's own "
+                   "kernels (zero-copy over the bus, no separate copy-engine submissions), all kernels (+ NCCL interface "
+                   "exchange), stream sync; the state vectors stay resident in HBM exactly as the reference keeps "
+                   "U,V,A resident in host RAM between steps"}
     if not np.all(np.isfinite(row)):
         raise SystemExit("non-finite response")
 

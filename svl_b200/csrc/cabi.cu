@@ -291,20 +291,23 @@ int svlgpu_step_host(svlgpu_model *m, int k, const double *amplitudes, int nload
     REQUIRE(m && m->finalized, "step_host: model not finalized");
     REQUIRE(nloads == m->n_ploads, "step_host: amplitude count differs from the number of point loads");
     cudaSetDevice(m->device);
+    // host buffers, zero-copy: the step's load amplitudes are read by k_nodal_loads straight from mapped pinned host
+    // memory and the recorder row is written by k_record straight into mapped pinned host memory, so the bytes
+    // cross the bus inside the step without two extra copy-engine submissions
     const double *damp = nullptr;
     if (nloads > 0) {
         std::memcpy(m->h_pl_amp, amplitudes, sizeof(double) * nloads);
-        cudaMemcpyAsync(m->d_pl_amp, m->h_pl_amp, sizeof(double) * nloads, cudaMemcpyHostToDevice, m->stream);
-        damp = m->d_pl_amp;
+        damp = m->h_pl_amp;
     }
-    if (run_steps(m, k, k + 1, damp)) return 1;
     if (rec >= 0) {
         REQUIRE(rec < (int)m->recorders.size(), "step_host: recorder out of range");
         Recorder &r = m->recorders[rec];
-        REQUIRE(row_len == r.width && r.rows > 0, "step_host: row length differs from the recorder width");
-        cudaMemcpyAsync(m->h_row, r.d_rows + (size_t)(r.rows - 1) * r.width, sizeof(double) * r.width,
-                        cudaMemcpyDeviceToHost, m->stream);
+        REQUIRE(row_len == r.width && r.rows < r.max_rows, "step_host: row length differs from the recorder width");
+        m->mirror_rec = rec;
     }
+    const int rc = run_steps(m, k, k + 1, damp);
+    m->mirror_rec = -1;
+    if (rc) return 1;
     cudaError_t e = cudaStreamSynchronize(m->stream);
     if (e != cudaSuccess) { set_error(std::string("device failure: ") + cudaGetErrorString(e)); return 1; }
     if (rec >= 0) {

@@ -662,7 +662,7 @@ struct Shell3 {
     const int32_t *target;    // halo pass: interface index of each list entry (else null)
     double *hF;               // halo pass: [n_if][3] partial internal force
 };
-__global__ void __launch_bounds__(128) k_stencil3_shell(const Shell3 p) {
+__global__ void __launch_bounds__(128, 5) k_stencil3_shell(const Shell3 p) {
     __shared__ double T[kTbl3Stride];
     {
         const double *Tg = p.tbl + (size_t)p.chunk_cls[blockIdx.x] * kTbl3Stride;
@@ -1307,7 +1307,7 @@ __global__ void k_drm_apply(int n, int nd, int phase, const int32_t *dof0, const
 // NODE recorder row (Recorder.cpp:239-269); V, A as in CentralDifference.cpp:141-144
 // ------------------------------------------------------------------------------------------
 __global__ void k_record(int n, const int32_t *dofs, const double *Un, const double *U, const double *Up,
-                         double dt, int field, double *row, const int32_t *kctl, int max_rows) {
+                         double dt, int field, double *row, const int32_t *kctl, int max_rows, double *mirror) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     if (kctl) {                                   // graph replay: `row` is the recorder base, the row index lives on the device
@@ -1321,6 +1321,7 @@ __global__ void k_record(int n, const int32_t *dofs, const double *Un, const dou
     else if (field == SVLGPU_VEL) v = 1.0 / 2.0 / dt * (un - up);
     else v = 1.0 / dt / dt * ((un - u) - u + up);
     row[t] = v;
+    if (mirror) mirror[t] = v;                    // svlgpu_step_host: the row also goes straight to mapped pinned host memory
 }
 
 __global__ void k_gather(int n, const int32_t *dofs, const int32_t *int_of_total, const double *Un,
@@ -1581,12 +1582,15 @@ int halo_generic_force(svlgpu_model *m) {
 }
 
 void record_rows(svlgpu_model *m, bool devk) {
+    int ri = -1;
     for (auto &r : m->recorders) {
+        ri++;
         if (r.rows >= r.max_rows || !r.width) continue;
         k_record<<<(r.width + 127) / 128, 128, 0, m->stream>>>(r.width, r.d_dofs, m->d_U[m->next], m->d_U[m->cur],
                                                                  m->d_U[m->prev], m->dt, r.field,
                                                                  devk ? r.d_rows : r.d_rows + (size_t)r.rows * r.width,
-                                                                 devk ? m->d_kctl : nullptr, r.max_rows);
+                                                                 devk ? m->d_kctl : nullptr, r.max_rows,
+                                                                 (ri == m->mirror_rec && !devk) ? m->h_row : nullptr);
         r.rows++;
         m->total_launches++;
     }
@@ -1662,13 +1666,14 @@ static int step_once(svlgpu_model *m, int k, const double *dev_amp) {
     const double *U = m->d_U[m->cur], *Up = m->d_U[m->prev];
     double *Un = m->d_U[m->next];
     m->k_of_step = k;
-    if (m->overlap && !m->drm_dev.empty() && !m->kernel_timing) {
+    const bool prefetch = m->overlap && !m->drm_dev.empty() && !m->kernel_timing;
+    if (prefetch) {
         // DRM forces of step k+1 are computed on side stream 0 while this step runs; its buffer was last read
-        // by step k-1, which is complete on the main stream at this point
+        // by step k-1, which is complete on the main stream at this point.  Only the fork point is taken here: the
+        // prefetch kernels themselves are enqueued after the bulk kernels so that an idle GPU (per-step host calls,
+        // small partitions) starts on the stencil at once.
         if (m->graph_capturing) { k_setk<<<1, 1, 0, m->stream>>>(m->d_kctl, 2 + ((k + 1) & 1), 1); m->total_launches++; }
         CUDA_OK(cudaEventRecord(m->ev_fork2, m->stream));
-        CUDA_OK(cudaStreamWaitEvent(m->side[0], m->ev_fork2, 0));
-        if (drm_prefetch(m, k + 1)) return 1;
     }
     if (launch_generic_elements(m, U, 1)) return 1;
     if (halo) {
@@ -1678,6 +1683,10 @@ static int step_once(svlgpu_model *m, int k, const double *dev_amp) {
         if (xchg && halo_exchange_begin(m)) return 1;
     }
     if (launch_node_update(m, U, Up, Un, 0)) return 1;
+    if (prefetch) {
+        CUDA_OK(cudaStreamWaitEvent(m->side[0], m->ev_fork2, 0));
+        if (drm_prefetch(m, k + 1)) return 1;
+    }
     if (xchg && halo_exchange_end(m, U, Up, Un, 0)) return 1;
     if (m->pml.present && pml_step(m, U, Up, Un)) return 1;
     if (launch_external(m, k, dev_amp, Un, 1)) return 1;
