@@ -171,7 +171,11 @@ int halo_comm_init(svlgpu_model *m, const void *id128, int rank, int nranks) {
     std::memcpy(&id, id128, 128);
     NCCL_OK(g_nccl.CommInitRank(&h.comm, nranks, id, rank));
     h.rank = rank; h.nranks = nranks;
-    CUDA_OK(cudaStreamCreateWithFlags(&h.comm_stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;                            // the exchange must not queue behind the bulk kernels' CTAs
+        CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_OK(cudaStreamCreateWithPriority(&h.comm_stream, cudaStreamNonBlocking, getenv("SVLGPU_NO_PRIO") ? lo : hi));
+    }
     CUDA_OK(cudaEventCreateWithFlags(&h.e_ready, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&h.e_done, cudaEventDisableTiming));
     // summation order: ascending rank, own contribution at its place

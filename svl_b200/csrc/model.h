@@ -265,6 +265,7 @@ struct svlgpu_model {
     double *d_pl_amp = nullptr;                     // per-load amplitude of the current step (host-fed)
     double *h_pl_amp = nullptr, *h_row = nullptr;   // pinned staging
     int h_row_len = 0;
+    bool shell_lowreg = false;                      // SVLGPU_SHELL_LOWREG: 96-register shell kernel (co-resides with the stencil)
     int mirror_rec = -1;                            // recorder whose next row k_record also writes to h_row (step_host)
 
     std::vector<svl::DrmDev> drm_dev;

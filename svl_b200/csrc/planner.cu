@@ -95,8 +95,16 @@ int plan_and_upload(svlgpu_model *m) {
     // equal stream priorities on purpose: with the bulk kernel prioritised the side-stream kernels only ran in its tail
     // (measured 0.697 -> 0.78 ms per step at 320^3); interleaved they fill the issue slots the FP64-bound bulk leaves
     CUDA_OK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
-    CUDA_OK(cudaStreamCreateWithFlags(&m->side[0], cudaStreamNonBlocking));
-    CUDA_OK(cudaStreamCreateWithFlags(&m->side[1], cudaStreamNonBlocking));
+    {
+        // the side streams carry short kernels (shell classes, DRM forces of the next step) beside the bulk stencil kernel;
+        // SVLGPU_SIDE_PRIO gives them the highest stream priority
+        int lo = 0, hi = 0;
+        CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        const int pr = getenv("SVLGPU_SIDE_PRIO") ? hi : lo;   // measured neutral on one GPU (profiles/r1t): default priority
+        CUDA_OK(cudaStreamCreateWithPriority(&m->side[0], cudaStreamNonBlocking, pr));
+        CUDA_OK(cudaStreamCreateWithPriority(&m->side[1], cudaStreamNonBlocking, pr));
+    }
+    m->shell_lowreg = getenv("SVLGPU_SHELL_LOWREG") != nullptr;
     CUDA_OK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&m->ev_fork2, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
