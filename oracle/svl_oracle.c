@@ -730,8 +730,28 @@ int svlo_internal_force(const svlo_model *m, const double *U, double *F) {
     return 0;
 }
 
-int svlo_run_central_difference(const svlo_model *m, int nt, int field, int n_rec,
-                                const int32_t *rec_dofs, double *out, double *Ufinal, int nthreads) {
+/* element tangent stiffness for the implicit integrators (Assembler::ComputeStiffnessMatrix, Assembler.cpp:70-113):
+ * linear materials only                                                         */
+static int elem_K(const svlo_model *m, int e, const elem_rt *rt, double *Ke) {
+    int kind = m->elem_kind[e], mk = m->mat_kind[m->elem_mat[e]];
+    const double *mp = m->mat_par + 8 * m->elem_mat[e];
+    double Cm[36];
+    memset(Ke, 0, (size_t)rt->nd * rt->nd * sizeof(double));
+    if (kind == SVLO_LIN3DHEXA8 && mk == SVLO_ELASTIC3DLINEAR) {
+        svlo_elastic3d_C(mp[0], mp[1], Cm); svlo_hex8_stiffness(rt->X, Cm, Ke); return 0;
+    }
+    if (kind == SVLO_LIN2DQUAD4 && mk == SVLO_ELASTIC2DPLANESTRAIN) {
+        svlo_planestrain_C(mp[0], mp[1], Cm); svlo_quad4_stiffness(rt->X, m->elem_attr[10 * e], Cm, Ke); return 0;
+    }
+    if (kind == SVLO_ZEROLENGTH1D) return 0;      /* Viscous1DLinear::GetTangentStiffness() == 0 */
+    return 1;
+}
+
+/* integrator: 0 CentralDifference (10-Integrators/02-CentralDifference/CentralDifference.cpp),
+ *             1 NewmarkBeta, average acceleration (10-Integrators/03-Newmark/NewmarkBeta.cpp:21-36 Initialize,
+ *               :64-79 ComputeNewStep, :106-121 ComputeEffectiveForce, :124-133 ComputeEffectiveStiffness)      */
+static int run_dynamic(const svlo_model *m, int integrator, int nt, int field, int n_rec,
+                       const int32_t *rec_dofs, double *out, double *Ufinal, int nthreads) {
     const int nT = m->n_total, nF = m->n_free, nE = m->n_elem;
     const double dt = m->dt;
     int rc = 0;
@@ -782,8 +802,25 @@ int svlo_run_central_difference(const svlo_model *m, int nt, int field, int n_re
         }
         free(Me); free(Ce);
     }
-    /* Keff = M/dt^2 + C/2dt (:70) and Kminus = M/dt^2 - C/2dt (:217) */
+    /* CentralDifference: Keff = M/dt^2 + C/2dt (:70) and Kminus = M/dt^2 - C/2dt (:217).
+     * NewmarkBeta: Keff = K + 4/dt^2 M + 2/dt C (NewmarkBeta.cpp:128-130); Kminus carries M, lC stays C           */
     tlist lKp = {0, 0, NULL}, lKm = {0, 0, NULL};
+    if (integrator == 1) {
+        double *Ke = (double *)malloc(72 * 72 * sizeof(double));
+        for (int e = 0; e < nE && !rc; e++) {
+            if (elem_K(m, e, &rt[e], Ke)) { rc = 4; break; }
+            int nd = rt[e].nd;
+            for (int j = 0; j < nd; j++)
+                for (int i = 0; i < nd; i++)
+                    if (fabs(Ke[i * nd + j]) > 1e-12 /* ktol, Driver.hpp:1805 default */) tl_push(&lKp, rt[e].dofs[i], rt[e].dofs[j], Ke[i * nd + j]);
+        }
+        free(Ke);
+        for (int k = 0; k < lM.n; k++) {
+            tl_push(&lKp, lM.t[k].i, lM.t[k].j, 4.0 / dt / dt * lM.t[k].v);
+            tl_push(&lKm, lM.t[k].i, lM.t[k].j, lM.t[k].v);
+        }
+        for (int k = 0; k < lC.n; k++) tl_push(&lKp, lC.t[k].i, lC.t[k].j, 2.0 / dt * lC.t[k].v);
+    } else {
     for (int k = 0; k < lM.n; k++) {
         tl_push(&lKp, lM.t[k].i, lM.t[k].j, 1.0 / dt / dt * lM.t[k].v);
         tl_push(&lKm, lM.t[k].i, lM.t[k].j, 1.0 / dt / dt * lM.t[k].v);
@@ -792,6 +829,8 @@ int svlo_run_central_difference(const svlo_model *m, int nt, int field, int n_re
         tl_push(&lKp, lC.t[k].i, lC.t[k].j, 1.0 / 2.0 / dt * lC.t[k].v);
         tl_push(&lKm, lC.t[k].i, lC.t[k].j, -(1.0 / 2.0 / dt * lC.t[k].v));
     }
+    }
+    csr Cs = tl_to_csr(&lC, nT);
     csr Kp = tl_to_csr(&lKp, nT), Km = tl_to_csr(&lKm, nT);
     csr T = build_T(m);
     /* Keff_free = T' Keff T (:224-231) */
@@ -827,6 +866,7 @@ int svlo_run_central_difference(const svlo_model *m, int nt, int field, int n_re
         }
         if (ldlt_factor(Kc, nc)) { rc = 2; goto done; }
     }
+    if (rc) goto done;
 
     for (int k = 1; k < nt; k++) {            /* DynamicAnalysis.cpp:36 */
         /* --- Fint: Assembler.cpp:239-269 (ascending element order, ftol filter) */
@@ -882,12 +922,24 @@ int svlo_run_central_difference(const svlo_model *m, int nt, int field, int n_re
             }
             for (int i = 0; i < nT; i++) Fext[i] += m->drm_factor * Ftmp[i];
         }
+        if (integrator == 1) {
+            /* Fext + Fbar - Fint + M (4/dt V + A - 4/dt^2 dU) + C (V - 2/dt dU) with dU = 0 (Linear.cpp:25):
+             * NewmarkBeta.cpp:116-118                                               */
+            for (int i = 0; i < nT; i++) Ftmp[i] = 4.0 / dt * V[i] + A[i];
+            for (int i = 0; i < nT; i++) {
+                double v = 0, w = 0;
+                for (int p = Km.ptr[i]; p < Km.ptr[i + 1]; p++) v += Km.val[p] * Ftmp[Km.col[p]];
+                for (int p = Cs.ptr[i]; p < Cs.ptr[i + 1]; p++) w += Cs.val[p] * V[Cs.col[p]];
+                rhs[i] = Fext[i] - Fint[i] + v + w;
+            }
+        } else {
         /* --- Feff = T'(Fext - Fint + Kminus (U-Up)) : CentralDifference.cpp:217-220 */
         for (int i = 0; i < nT; i++) Ftmp[i] = U[i] - Up[i];
         for (int i = 0; i < nT; i++) {
             double v = 0;
             for (int p = Km.ptr[i]; p < Km.ptr[i + 1]; p++) v += Km.val[p] * Ftmp[Km.col[p]];
             rhs[i] = Fext[i] - Fint[i] + v;
+        }
         }
         memset(Feff, 0, nF * sizeof(double));
         for (int i = 0; i < nT; i++)
@@ -908,6 +960,14 @@ int svlo_run_central_difference(const svlo_model *m, int nt, int field, int n_re
         }
 #pragma omp parallel for schedule(static)
         for (int e = 0; e < nE; e++) material_update(m, e, &rt[e], Utr);
+        if (integrator == 1) {
+            /* NewmarkBeta.cpp:73-76 */
+            for (int i = 0; i < nT; i++) {
+                U[i] += dUt[i];
+                A[i] = 4.0 / dt / dt * dUt[i] - 4.0 / dt * V[i] - A[i];
+                V[i] = 2.0 / dt * dUt[i] - V[i];
+            }
+        } else
         /* --- CentralDifference.cpp:138-148 */
         for (int i = 0; i < nT; i++) {
             V[i] = 1.0 / 2.0 / dt * (U[i] + dUt[i] - Up[i]);
@@ -924,7 +984,16 @@ done:
     for (int e = 0; e < nE; e++) free(rt[e].Kpml);
     free(rt); free(U); free(V); free(A); free(Up); free(Fint); free(Fext); free(Ftmp); free(rhs);
     free(dUt); free(Utr); free(Feff); free(dU); free(fe_all); free(lM.t); free(lC.t); free(lKp.t);
-    free(lKm.t); free(lF.t); csr_free(&Kp); csr_free(&Km); csr_free(&T); csr_free(&Kf);
+    free(lKm.t); free(lF.t); csr_free(&Kp); csr_free(&Km); csr_free(&T); csr_free(&Kf); csr_free(&Cs);
     free(cidx); free(Kdiag); free(Kc); free(bc);
     return rc;
+}
+
+int svlo_run_central_difference(const svlo_model *m, int nt, int field, int n_rec,
+                                const int32_t *rec_dofs, double *out, double *Ufinal, int nthreads) {
+    return run_dynamic(m, 0, nt, field, n_rec, rec_dofs, out, Ufinal, nthreads);
+}
+int svlo_run_newmark(const svlo_model *m, int nt, int field, int n_rec,
+                     const int32_t *rec_dofs, double *out, double *Ufinal, int nthreads) {
+    return run_dynamic(m, 1, nt, field, n_rec, rec_dofs, out, Ufinal, nthreads);
 }

@@ -126,6 +126,11 @@ int svlo_run_central_difference(const svlo_model *m, int nt, int field, int n_re
                                 const int32_t *rec_dofs, double *out, double *Ufinal,
                                 int nthreads);
 
+/* Same with NewmarkBeta (average acceleration) + Linear + a direct solve: 10-Integrators/03-Newmark/NewmarkBeta.cpp.
+ * Linear materials only (the tangent is the elastic stiffness); returns 4 otherwise.                           */
+int svlo_run_newmark(const svlo_model *m, int nt, int field, int n_rec,
+                     const int32_t *rec_dofs, double *out, double *Ufinal, int nthreads);
+
 /* Assembler::ComputeInternalForceVector on a given displacement state (all
  * materials start from the virgin state, one UpdateState with U).            */
 int svlo_internal_force(const svlo_model *m, const double *U, double *F);

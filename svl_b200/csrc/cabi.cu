@@ -43,6 +43,7 @@ void svlgpu_destroy(svlgpu_model *m) {
         graph_destroy(m);
         halo_destroy(m);
         pml_destroy(m);
+        newmark_destroy(m);
         for (void *p : m->allocs) cudaFree(p);
         if (m->h_pl_amp) cudaFreeHost(m->h_pl_amp);
         if (m->h_row) cudaFreeHost(m->h_row);
@@ -166,6 +167,8 @@ int svlgpu_set_option(svlgpu_model *m, const char *name, double value) {
     if (n == "lattice_guess") m->opt_lattice_guess = value != 0.0;
     else if (n == "keep_gauss") m->opt_keep_gauss = value != 0.0;
     else if (n == "cuda_graph") m->opt_graph = value != 0.0 ? 1 : 0;
+    else if (n == "integrator") { REQUIRE(value == 0.0 || value == 1.0, "set_option: integrator must be 0 (CentralDifference) or 1 (NewmarkBeta)"); m->opt_integrator = (int)value; }
+    else if (n == "newmark_rtol") { REQUIRE(value > 0.0 && value < 1.0, "set_option: newmark_rtol out of range"); m->nm.rtol = value; }
     else if (n == "pml_rtol") { REQUIRE(value > 0.0 && value < 1.0, "set_option: pml_rtol out of range"); m->pml.rtol = value; }
     else if (n == "ftol") { REQUIRE(value >= 0.0, "set_option: ftol must be >= 0"); m->pml.ftol = value; }
     else { set_error("set_option: unknown option " + n); return 1; }

@@ -1208,7 +1208,7 @@ __global__ void k_nodal_loads(const PLArgs a) {
     }
     if (tg != -1) return;
     const int d = a.dof[t];
-    a.Un[d] += a.kinv[d] * F;
+    a.Un[d] += (a.kinv ? a.kinv[d] : 1.0) * F;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1301,14 +1301,15 @@ __global__ void k_drm_apply(int n, int nd, int phase, const int32_t *dof0, const
     if ((phase == 0) != (tg >= 0)) return;
     if (tg >= 0) { hF[tg + r] -= F[t]; return; }
     const int d = dof0[row] + r;
-    Un[d] += kinv[d] * F[t];
+    Un[d] += (kinv ? kinv[d] : 1.0) * F[t];
 }
 
 // ------------------------------------------------------------------------------------------
 // NODE recorder row (Recorder.cpp:239-269); V, A as in CentralDifference.cpp:141-144
 // ------------------------------------------------------------------------------------------
 __global__ void k_record(int n, const int32_t *dofs, const double *Un, const double *U, const double *Up,
-                         double dt, int field, double *row, const int32_t *kctl, int max_rows, double *mirror) {
+                         double dt, int field, double *row, const int32_t *kctl, int max_rows, double *mirror,
+                         const double *Vs, const double *As) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     if (kctl) {                                   // graph replay: `row` is the recorder base, the row index lives on the device
@@ -1319,6 +1320,7 @@ __global__ void k_record(int n, const int32_t *dofs, const double *Un, const dou
     const double un = Un[d], u = U[d], up = Up[d];
     double v;
     if (field == SVLGPU_DISP) v = un;
+    else if (Vs) v = (field == SVLGPU_VEL) ? Vs[d] : As[d];      // Newmark keeps V, A as state (NewmarkBeta.cpp:75-76)
     else if (field == SVLGPU_VEL) v = 1.0 / 2.0 / dt * (un - up);
     else v = 1.0 / dt / dt * ((un - u) - u + up);
     row[t] = v;
@@ -1326,10 +1328,12 @@ __global__ void k_record(int n, const int32_t *dofs, const double *Un, const dou
 }
 
 __global__ void k_gather(int n, const int32_t *dofs, const int32_t *int_of_total, const double *Un,
-                         const double *U, const double *Up, double dt, int field, double *out) {
+                         const double *U, const double *Up, double dt, int field, double *out, const double *Vs,
+                         const double *As) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const int d = int_of_total[dofs ? dofs[t] : t];
+    if (Vs && field != SVLGPU_DISP) { out[t] = (field == SVLGPU_VEL) ? Vs[d] : As[d]; return; }
     // state after the last step: Un = U_{n+1} (current), U = U_n, Up = U_{n-1}
     const double un = Un[d], u = U[d], up = Up[d];
     double v;
@@ -1592,7 +1596,8 @@ void record_rows(svlgpu_model *m, bool devk) {
                                                                  m->d_U[m->prev], m->dt, r.field,
                                                                  devk ? r.d_rows : r.d_rows + (size_t)r.rows * r.width,
                                                                  devk ? m->d_kctl : nullptr, r.max_rows,
-                                                                 (ri == m->mirror_rec && !devk) ? m->h_row : nullptr);
+                                                                 (ri == m->mirror_rec && !devk) ? m->h_row : nullptr,
+                                                                 m->nm.present ? m->nm.d_V : nullptr, m->nm.present ? m->nm.d_A : nullptr);
         r.rows++;
         m->total_launches++;
     }
@@ -1716,6 +1721,11 @@ int run_steps(svlgpu_model *m, int k0, int k1, const double *dev_amp) {
     if (!m->halo_peers.empty() && !m->halo.active) { set_error("step: halos were declared but svlgpu_comm_init was not called"); return 1; }
     if (upload_dom_tables(m)) return 1;
     int k = k0;
+    if (m->nm.present) {                                      // NewmarkBeta + Linear (newmark.cu)
+        for (; k < k1; k++) if (newmark_step(m, k, dev_amp)) return 1;
+        if (k1 > k0) m->launches_per_step = (m->total_launches - before) / (k1 - k0);
+        return 0;
+    }
     while (k < k1) {
         if (m->dev_k != k) {                                  // (re)synchronise the device step control block
             const int32_t h[2] = {k, m->recorders.empty() ? 0 : m->recorders[0].rows};
@@ -1777,6 +1787,21 @@ int run_steps(svlgpu_model *m, int k0, int k1, const double *dev_amp) {
     return 0;
 }
 
+// out = K x for any vector x in the internal dof layout: the force-only pass of the explicit path
+// (Gauss-point elements + lattice stencils + generic node gather); used by the Newmark Krylov solve
+int operator_K(svlgpu_model *m, const double *x, double *out) {
+    if (launch_generic_elements(m, x, 0)) return 1;
+    return launch_node_update(m, x, nullptr, out, 1);
+}
+// b += Fext(k) on every loaded dof (point loads, DRM), no Keff scaling
+int external_forces_raw(svlgpu_model *m, int k, const double *dev_amp, double *b) {
+    double *kinv = m->d_kinv;
+    m->d_kinv = nullptr;
+    const int rc = launch_external(m, k, dev_amp, b, 1);
+    m->d_kinv = kinv;
+    return rc;
+}
+
 // Assembler::ComputeInternalForceVector for the current displacement state
 int compute_internal_force(svlgpu_model *m, double *F_host) {
     double *tmp = m->d_U[m->next];
@@ -1801,7 +1826,8 @@ int gather_state(svlgpu_model *m, int field, const int32_t *dofs, int n, double 
     CUDA_OK(cudaMalloc(&d_out, sizeof(double) * n));
     // after a step the newest state sits in `cur`; U_n in `prev`, U_{n-1} in `next`
     k_gather<<<(n + 255) / 256, 256, 0, m->stream>>>(n, d_dofs, m->d_int_of_total, m->d_U[m->cur], m->d_U[m->prev],
-                                                      m->d_U[m->next], m->dt, m->steps_done ? field : SVLGPU_DISP, d_out);
+                                                      m->d_U[m->next], m->dt, (m->steps_done || m->nm.present) ? field : SVLGPU_DISP, d_out,
+                                                      m->nm.present ? m->nm.d_V : nullptr, m->nm.present ? m->nm.d_A : nullptr);
     CUDA_OK(cudaMemcpyAsync(out, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, m->stream));
     CUDA_OK(cudaStreamSynchronize(m->stream));
     cudaFree(d_dofs); cudaFree(d_out);

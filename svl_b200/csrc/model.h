@@ -198,6 +198,20 @@ struct PmlDev {
     int64_t total_iters = 0, solves = 0;
 };
 
+// NewmarkBeta + Linear on the device (newmark.cu)
+struct NewmarkDev {
+    bool present = false;
+    double *d_V = nullptr, *d_A = nullptr;           // velocity / acceleration state (internal dof order)
+    double *d_mass = nullptr, *d_cd = nullptr;       // lumped mass / damping diagonal
+    double *d_mask = nullptr;                        // 1 free, 0 restrained
+    double *d_dd = nullptr, *d_dinv = nullptr;       // D = 4/dt^2 M + 2/dt C and mask / D
+    double *d_b = nullptr, *d_x = nullptr, *d_r = nullptr, *d_p = nullptr, *d_q = nullptr;
+    double *d_part = nullptr, *h_scal = nullptr;
+    double rtol = 1e-13;
+    int max_iter = 5000, last_iters = 8;
+    int64_t total_iters = 0, solves = 0;
+};
+
 }  // namespace svl
 
 struct svlgpu_model {
@@ -220,6 +234,8 @@ struct svlgpu_model {
     std::vector<double> U0, V0, A0;
     bool opt_lattice_guess = true, opt_keep_gauss = false;
     int opt_graph = -1;                             // -1: environment decides
+    int opt_integrator = 0;                         // 0 CentralDifference, 1 NewmarkBeta (+ Linear)
+    svl::NewmarkDev nm;
 
     // ---- plan / device state ----
     bool finalized = false;
@@ -316,4 +332,12 @@ void halo_destroy(svlgpu_model *m);
 int pml_step(svlgpu_model *m, const double *U, const double *Up, double *Un);
 int pml_internal_force(svlgpu_model *m, const double *U, double *F);
 void pml_destroy(svlgpu_model *m);
+// newmark.cu / kernels.cu
+int newmark_plan(svlgpu_model *m);
+int newmark_step(svlgpu_model *m, int k, const double *dev_amp);
+int newmark_set_initial(svlgpu_model *m, const double *V_int, const double *A_int);
+void newmark_destroy(svlgpu_model *m);
+int operator_K(svlgpu_model *m, const double *x, double *out);
+int external_forces_raw(svlgpu_model *m, int k, const double *dev_amp, double *b);
+void record_rows(svlgpu_model *m, bool devk);
 }  // namespace svl

@@ -888,6 +888,17 @@ int plan_and_upload(svlgpu_model *m) {
         CUDA_OK(cudaMemcpy(m->d_U[1], Up.data(), sizeof(double) * m->n_int, cudaMemcpyHostToDevice));
         CUDA_OK(cudaMemset(m->d_U[2], 0, sizeof(double) * m->n_int));
     }
+    if (m->opt_integrator == 1) {
+        // NewmarkBeta::Initialize (NewmarkBeta.cpp:21-36): U, V, A from the nodes
+        if (newmark_plan(m)) return 1;
+        std::vector<double> V(m->n_int, 0.0), A(m->n_int, 0.0);
+        for (int t = 0; t < m->n_total; t++) {
+            const int q = m->int_of_total[t];
+            V[q] = m->V0.empty() ? 0.0 : m->V0[t];
+            A[q] = m->A0.empty() ? 0.0 : m->A0[t];
+        }
+        if (newmark_set_initial(m, V.data(), A.data())) return 1;
+    }
     CUDA_OK(cudaDeviceSynchronize());
     m->finalized = true;
     return 0;

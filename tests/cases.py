@@ -131,6 +131,19 @@ TOL["pml2d"] = 1e-9            # PML: Keff is not diagonal -> iterative block so
 TOL["pml3d"] = 1e-9
 
 
+# NewmarkBeta + Linear cases: the same generators run at 4x the explicit time step, i.e. beyond the
+# CentralDifference stability limit; goldens `newmark_<case>.npz` come from the unmodified reference executable with
+# integrator NEWMARK (Driver.hpp:1811-1813).
+NEWMARK_CASES = ("kat444", "quad4_area", "lysmer_column", "hex8_layered_rayleigh", "hex8_distorted", "drm_box")
+TOL_NEWMARK = 1e-9             # the device solves Keff dU = Feff by conjugate gradients (rtol 1e-13), the reference by LDL^T
+
+
+def newmark_case(name):
+    m = CASES[name]()
+    m.dt *= 4.0
+    return m
+
+
 def fingerprint(m) -> str:
     """Hash of the model inputs, stored beside each golden history so that drift of a generator is
     detected instead of silently comparing different models."""

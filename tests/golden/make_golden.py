@@ -31,9 +31,9 @@ from oracle_lib import RefProbe  # noqa: E402
 EXE = os.path.join(ROOT, "oracle", "_ref", "SeismoVLAB.exe")
 
 
-def run_reference(m, resp=("disp",)):
+def run_reference(m, resp=("disp",), integrator="CENTRALDIFFERENCE"):
     tmp = tempfile.mkdtemp(prefix="svlgold_")
-    part = M.write_reference_json(m, tmp, "Case", "Run", resp=resp, ndps=17)
+    part = M.write_reference_json(m, tmp, "Case", "Run", resp=resp, ndps=17, integrator=integrator)
     subprocess.run([EXE, "-dir", part, "-file", "Case.1.$.json"], stdout=subprocess.DEVNULL, check=True)
     return {r: M.read_node_recorder(os.path.join(tmp, "Solution", "Run", f"{r}.0.out")) for r in resp}
 
@@ -47,6 +47,16 @@ def history_cases(names):
         np.savez_compressed(os.path.join(HERE, f"{name}.npz"), fingerprint=cases.fingerprint(m),
                             rec_nodes=m.rec_nodes, dt=m.dt, nt=m.nt, **out)
         print(f"{name}: {out['disp'].shape} peak |u| = {np.abs(out['disp']).max():.6e}")
+
+
+def newmark_cases(names):
+    for name in names:
+        m = cases.newmark_case(name)
+        out = run_reference(m, ("disp", "vel", "accel"), integrator="NEWMARK")
+        assert out["disp"].shape[0] == m.nt - 1, (name, out["disp"].shape)
+        np.savez_compressed(os.path.join(HERE, f"newmark_{name}.npz"), fingerprint=cases.fingerprint(m),
+                            rec_nodes=m.rec_nodes, dt=m.dt, nt=m.nt, **out)
+        print(f"newmark_{name}: {out['disp'].shape} peak |u| = {np.abs(out['disp']).max():.6e}")
 
 
 def element_kat():
@@ -112,7 +122,12 @@ def element_kat():
 if __name__ == "__main__":
     if not os.path.exists(EXE) or not RefProbe.available():
         raise SystemExit("oracle/_ref is missing: run `make -C oracle ref` in the build container first")
-    names = sys.argv[1:] or list(cases.CASES)
-    if not sys.argv[1:]:
+    args = sys.argv[1:]
+    if args and args[0] == "newmark":
+        newmark_cases(args[1:] or list(cases.NEWMARK_CASES))
+        raise SystemExit(0)
+    names = args or list(cases.CASES)
+    if not args:
         element_kat()
+        newmark_cases(list(cases.NEWMARK_CASES))
     history_cases(names)

@@ -59,6 +59,8 @@ class Oracle:
         L.svlo_run_central_difference.restype = C.c_int
         L.svlo_run_central_difference.argtypes = [C.POINTER(SvloModel), C.c_int, C.c_int, C.c_int, _ip, _dp,
                                                   _dp, C.c_int]
+        L.svlo_run_newmark.restype = C.c_int
+        L.svlo_run_newmark.argtypes = L.svlo_run_central_difference.argtypes
         L.svlo_internal_force.argtypes = [C.POINTER(SvloModel), _dp, _dp]
         L.svlo_mass_diagonal.argtypes = [C.POINTER(SvloModel), _dp]
         L.svlo_elastic3d_C.argtypes = [C.c_double, C.c_double, _dp]
@@ -229,14 +231,14 @@ class Oracle:
             s.U0 = _d(A(U0, np.float64))
         return s, keep
 
-    def run(self, m, nt=None, field=0, rec_dofs=None, nthreads=1, U0=None):
+    def run(self, m, nt=None, field=0, rec_dofs=None, nthreads=1, U0=None, integrator="CENTRALDIFFERENCE"):
         s, keep = self.pack(m, U0)
         nt = nt or m.nt
         rd = np.ascontiguousarray(m.rec_dofs() if rec_dofs is None else rec_dofs, np.int32)
         out = np.zeros((nt - 1, len(rd)))
         Uf = np.zeros(m.n_total)
-        rc = self.lib.svlo_run_central_difference(C.byref(s), nt, field, len(rd), _i(rd), _d(out), _d(Uf),
-                                                  nthreads)
+        fn = self.lib.svlo_run_newmark if integrator.upper() == "NEWMARK" else self.lib.svlo_run_central_difference
+        rc = fn(C.byref(s), nt, field, len(rd), _i(rd), _d(out), _d(Uf), nthreads)
         if rc:
             raise RuntimeError(f"oracle stop code {rc}")
         return out, Uf

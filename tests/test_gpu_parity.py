@@ -310,3 +310,49 @@ def test_cuda_graph_replay_matches(oracle, name):
     assert cases.rel_err(out, ref) < cases.TOL[name]
     plain = _device(m).run()[0]
     assert np.array_equal(out, plain)
+
+
+# ---- NewmarkBeta + Linear on the device ----------------------------------------------------------
+@pytest.mark.parametrize("name", list(cases.NEWMARK_CASES))
+def test_newmark_device_matches_reference_golden(oracle, name):
+    """Matrix-free conjugate-gradient Newmark step against the histories the unmodified reference executable wrote with
+    integrator NEWMARK (direct LDL^T solve) and against the oracle; displacement, velocity and acceleration."""
+    m = cases.newmark_case(name)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"newmark_{name}.npz"))
+    assert str(g["fingerprint"]) == cases.fingerprint(m)
+    d = _device(m, fields=(0, 1, 2), options={"integrator": 1.0})
+    out = d.run()
+    for f, key in ((0, "disp"), (1, "vel"), (2, "accel")):
+        ref, _ = oracle.run(m, field=f, integrator="NEWMARK")
+        assert cases.rel_err(out[f], g[key]) < cases.TOL_NEWMARK, (key, "vs reference")
+        assert cases.rel_err(out[f], ref) < cases.TOL_NEWMARK, (key, "vs oracle")
+    U = d.get_state(0)
+    _, Uref = oracle.run(m, integrator="NEWMARK")
+    assert np.abs(U - Uref).max() / np.abs(Uref).max() < cases.TOL_NEWMARK
+    assert d.counters()["total_launches"] > 0
+
+
+def test_newmark_generic_path_and_refusals(oracle):
+    m = cases.newmark_case("kat444")
+    m.blocks = []                                   # Gauss-point kernels as the K operator
+    ref, _ = oracle.run(m, integrator="NEWMARK")
+    out = _device(m, options={"integrator": 1.0}).run()[0]
+    assert cases.rel_err(out, ref) < cases.TOL_NEWMARK
+    from svl_b200.capi import SvlError
+    with pytest.raises(SvlError):                   # non-linear material: the tangent is not the elastic stiffness
+        _device(cases.j2_column(), options={"integrator": 1.0})
+    with pytest.raises(SvlError):                   # PML needs ExtendedNewmarkBeta
+        _device(cases.pml2d(), options={"integrator": 1.0})
+
+
+def test_host_driver_newmark(tmp_path):
+    """The C++ host driver reads integrator NEWMARK from the reference's JSON and writes the reference's recorder files."""
+    import subprocess
+    name = "lysmer_column"
+    m = cases.newmark_case(name)
+    part = M.write_reference_json(m, str(tmp_path), "Case", "Run", resp=("disp",), ndps=17, integrator="NEWMARK")
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "svl_b200", "SeismoVLAB_gpu.exe")
+    subprocess.run([exe, "-dir", part, "-file", "Case.1.$.json"], check=True, stdout=subprocess.DEVNULL)
+    out = M.read_node_recorder(os.path.join(str(tmp_path), "Solution", "Run", "disp.0.out"))
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"newmark_{name}.npz"))
+    assert cases.rel_err(out, g["disp"]) < cases.TOL_NEWMARK

@@ -38,6 +38,19 @@ def test_oracle_history_matches_reference_executable(oracle, name):
     assert cases.rel_err(out, g["disp"]) < cases.TOL[name]
 
 
+@pytest.mark.parametrize("name", list(cases.NEWMARK_CASES))
+def test_oracle_newmark_history_matches_reference_executable(oracle, name):
+    """NewmarkBeta + Linear (10-Integrators/03-Newmark/NewmarkBeta.cpp) at 4x the explicit step: displacement, velocity
+    and acceleration histories of the unmodified reference executable."""
+    m = cases.newmark_case(name)
+    g = gold(f"newmark_{name}")
+    assert str(g["fingerprint"]) == cases.fingerprint(m), "case generator drifted: regenerate tests/golden"
+    for f, key in ((0, "disp"), (1, "vel"), (2, "accel")):
+        out, _ = oracle.run(m, field=f, integrator="NEWMARK")
+        assert out.shape == g[key].shape and np.abs(g[key]).max() > 0
+        assert cases.rel_err(out, g[key]) < 1e-10, key
+
+
 def test_oracle_vel_accel_match_reference_executable(oracle):
     m = cases.kat444()
     g = gold("kat444")
