@@ -131,7 +131,7 @@ int svlgpu_add_elements(svlgpu_model *m, int kind, int n, const int32_t *conn, c
         m->elem_conn.resize(8ull * (first + n), 0);
         m->elem_mat.resize(first + n);
         if (nattr > 0 || kind == SVLGPU_LIN2DQUAD4 || !m->elem_attr.empty()) m->elem_attr.resize(10ull * (first + n), 0.0);
-        if (!m->elem_am.empty()) m->elem_am.resize(first + n, 0.0);
+        if (!m->elem_am.empty()) { m->elem_am.resize(first + n, 0.0); m->elem_ak.resize(first + n, 0.0); }
         for (int e = 0; e < n; e++) {
             for (int l = 0; l < npe; l++) {
                 const int nd = conn[(size_t)e * npe + l];
@@ -150,11 +150,13 @@ int svlgpu_add_elements(svlgpu_model *m, int kind, int n, const int32_t *conn, c
 int svlgpu_set_rayleigh(svlgpu_model *m, int n, const int32_t *elems, double am, double ak) {
     GUARD_BEGIN
     REQUIRE(m && !m->finalized, "set_rayleigh: model missing or finalized");
-    REQUIRE(ak == 0.0, "set_rayleigh: stiffness-proportional damping makes Keff non-diagonal (not supported on the explicit device path)");
+    // ak != 0 makes the CentralDifference Keff non-diagonal (refused at finalize); NewmarkBeta takes it (newmark.cu)
     m->elem_am.resize(m->elem_kind.size(), 0.0);
+    m->elem_ak.resize(m->elem_kind.size(), 0.0);
     for (int i = 0; i < n; i++) {
         REQUIRE(elems[i] >= 0 && elems[i] < (int)m->elem_kind.size(), "set_rayleigh: element out of range");
         m->elem_am[elems[i]] = am;
+        m->elem_ak[elems[i]] = ak;
     }
     return 0;
     GUARD_END

@@ -208,6 +208,7 @@ struct NewmarkDev {
     double *d_b = nullptr, *d_x = nullptr, *d_r = nullptr, *d_p = nullptr, *d_q = nullptr;
     double *d_part = nullptr, *h_scal = nullptr;
     double rtol = 1e-13;
+    double ak = 0.0;                                 // uniform stiffness-proportional Rayleigh coefficient (C = am M + ak K)
     int max_iter = 5000, last_iters = 8;
     int64_t total_iters = 0, solves = 0;
 };
@@ -225,7 +226,7 @@ struct svlgpu_model {
     std::vector<Constraint> constraints;
     std::vector<svl::Material> materials;
     std::vector<int32_t> elem_kind, elem_conn /*8 per elem*/, elem_mat;
-    std::vector<double> elem_attr /*10 per elem, allocated only once an element carries attributes*/, elem_am;
+    std::vector<double> elem_attr /*10 per elem, allocated only once an element carries attributes*/, elem_am, elem_ak;
     double attr(long long e, int a) const { return elem_attr.empty() ? 0.0 : elem_attr[10 * e + a]; }
     std::vector<svl::PointLoad> ploads;
     std::vector<svl::DrmLoad> drms;

@@ -9,8 +9,9 @@
 // search direction (block-stencil kernels on lattices, Gauss-point kernels elsewhere), M and C are the lumped
 // diagonals, and the system is solved by conjugate gradients preconditioned with D = 4/dt^2 M + 2/dt C (so the
 // iteration count depends on (omega_max dt)^2 only).  Scalars and the convergence flag live on the device; reductions
-// have a fixed shape (deterministic).  Scope: linear materials, lumped mass, mass-proportional Rayleigh damping and
-// dashpots (diagonal C), restrained dofs; one GPU.
+// have a fixed shape (deterministic).  Scope: linear materials, lumped mass, Rayleigh damping (mass-proportional part
+// on the diagonal, a uniform stiffness-proportional part folded into the K operator), dashpots (diagonal C),
+// restrained dofs; one GPU.
 #include <algorithm>
 #include <cstring>
 #include "model.h"
@@ -82,13 +83,18 @@ __global__ void __launch_bounds__(kNmThreads) k_nm_init(int n, const double *mas
         part[N_RZ0 * kNmBlocks + blockIdx.x] = s1;
     }
 }
-// q = mask (K p + D p) with K p already in q; partial (p, q)
-__global__ void __launch_bounds__(kNmThreads) k_nm_ap(int n, const double *mask, const double *dd, const double *p, double *q,
+// w = U - ak V: the right-hand side holds -Fint + C V with C = am M + ak K (lin3DHexa8.cpp:360-366), and for linear
+// materials -K U + ak K V = -K (U - ak V): one operator application serves both terms
+__global__ void __launch_bounds__(kNmThreads) k_nm_w(int n, double ak, const double *U, const double *V, double *w) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) w[i] = fma(-ak, V[i], U[i]);
+}
+// q = mask (ck K p + D p) with K p already in q, ck = 1 + 2 ak / dt; partial (p, q)
+__global__ void __launch_bounds__(kNmThreads) k_nm_ap(int n, double ck, const double *mask, const double *dd, const double *p, double *q,
                                                        double *part) {
     if (part[kNmFlag] != 0.0) return;
     double a0 = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const double pv = p[i], qv = mask[i] * (q[i] + dd[i] * pv);
+        const double pv = p[i], qv = mask[i] * (ck * q[i] + dd[i] * pv);
         q[i] = qv;
         a0 = fma(pv, qv, a0);
     }
@@ -199,7 +205,11 @@ int newmark_step(svlgpu_model *m, int k, const double *dev_amp) {
     double *Un = m->d_U[m->next];
     m->k_of_step = k;
     // Fint(U_n) = K U_n: the explicit path's force-only pass (Assembler::ComputeInternalForceVector)
-    if (operator_K(m, U, N.d_q)) return 1;
+    if (N.ak != 0.0) {
+        k_nm_w<<<kNmBlocks, kNmThreads, 0, st>>>(n, N.ak, U, N.d_V, N.d_r);
+        m->total_launches++;
+        if (operator_K(m, N.d_r, N.d_q)) return 1;
+    } else if (operator_K(m, U, N.d_q)) return 1;
     k_nm_rhs<<<kNmBlocks, kNmThreads, 0, st>>>(n, 4.0 / dt, N.d_q, N.d_mass, N.d_cd, N.d_mask, N.d_V, N.d_A, N.d_b, N.d_part);
     if (external_forces_raw(m, k, dev_amp, N.d_b)) return 1;           // b += Fext(k)  (Assembler::ComputeExternalForceVector)
     k_nm_init<<<kNmBlocks, kNmThreads, 0, st>>>(n, N.d_mask, N.d_dinv, N.d_b, N.d_x, N.d_r, N.d_p, N.d_part);
@@ -211,7 +221,7 @@ int newmark_step(svlgpu_model *m, int k, const double *dev_amp) {
     while (!done) {
         for (int q = 0; q < batch; q++, it++) {
             if (operator_K(m, N.d_p, N.d_q)) return 1;
-            k_nm_ap<<<kNmBlocks, kNmThreads, 0, st>>>(n, N.d_mask, N.d_dd, N.d_p, N.d_q, N.d_part);
+            k_nm_ap<<<kNmBlocks, kNmThreads, 0, st>>>(n, 1.0 + 2.0 * N.ak / dt, N.d_mask, N.d_dd, N.d_p, N.d_q, N.d_part);
             k_nm_xr<<<kNmBlocks, kNmThreads, 0, st>>>(n, rz, N.d_dinv, N.d_p, N.d_q, N.d_x, N.d_r, N.d_part);
             k_nm_flag<<<1, 32, 0, st>>>(N.d_part, tol2);
             k_nm_p<<<kNmBlocks, kNmThreads, 0, st>>>(n, rz, N.d_dinv, N.d_r, N.d_p, N.d_part);

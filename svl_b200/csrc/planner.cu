@@ -229,6 +229,23 @@ int plan_and_upload(svlgpu_model *m) {
     }
     m->n_elem_classes = (int64_t)classes.size();
 
+    // stiffness-proportional Rayleigh damping (lin3DHexa8.cpp:360-366): C = am M + ak K0 couples dofs, so the explicit
+    // Keff = M/dt^2 + C/2dt stops being diagonal; the Newmark solve is matrix-free and takes a uniform ak
+    {
+        bool any = false, uniform = true;
+        double ak = 0.0;
+        for (int e = 0; e < nE; e++) {
+            if (elem_cls[e] < 0 || m->elem_ak.empty()) continue;
+            if (!any) { ak = m->elem_ak[e]; any = true; }
+            else if (m->elem_ak[e] != ak) uniform = false;
+        }
+        if (any && (ak != 0.0 || !uniform)) {
+            if (m->opt_integrator != 1) { set_error("stiffness-proportional Rayleigh damping makes Keff non-diagonal: not supported by the explicit device path (use the Newmark integrator)"); return 1; }
+            if (!uniform) { set_error("Newmark: stiffness-proportional Rayleigh damping must be the same on all solid elements"); return 1; }
+            m->nm.ak = ak;
+        }
+    }
+
     // ---- C. lumped mass, damping, CentralDifference coefficients ---------------------------
     const double mtol = 1e-12;                       // Driver.hpp:1804 default, Assembler.cpp:647,687
     std::vector<double> mass(m->n_int, 0.0), cdiag(m->n_int, 0.0);

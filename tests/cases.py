@@ -144,6 +144,41 @@ def newmark_case(name):
     return m
 
 
+def fixture_j05():
+    """The reference's own validation fixture 03-Validations/01-Debugging/J05-DY_Lin_3DSoilColumn_Elastic_Hexa8 rebuilt with
+    the repo's model layer: 1 x 1 x 100 lin3DHexa8 column (Elastic3DLinear 1.3e7 / 0.3 / 2000), z restrained everywhere,
+    Rayleigh am = 0.1244195110, ak = 0.0007878958 on the solids, four ZeroLength1D + Viscous1DLinear (eta 2.5e4) dashpots
+    per horizontal direction between base nodes 1-4 and fixed twins 405-408, point loads 25000 * ricker.in in x on the base
+    nodes, lumped mass, Newmark + Linear, dt 0.01, nt 1000; recorded nodes 1 and 401.  Its golden data are the OpenSees
+    histories shipped with the fixture (tests/golden/J05/opensees.npz, 6 significant digits)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "J05", "opensees.npz"))
+    m = M.make_box_model((1, 1, 100), 1.0, nt=1000, dt=0.01, fix=None, series=np.zeros(1000), rec_nodes=[0, 400])
+    fd = np.asarray(m.freedof).reshape(-1, 3).copy()
+    fd[:, 2] = -1                                                   # addRestrain(dof=[3]) on every soil node
+    n0 = m.n_nodes
+    m.coords = np.vstack([m.coords, m.coords[:4]])                  # Lysmer twins 405..408
+    m.node_ndof = np.concatenate([m.node_ndof, np.full(4, 3, dtype=np.int32)])
+    m.freedof = np.concatenate([fd.reshape(-1), np.full(12, -1, dtype=np.int32)])
+    m.materials = [(M.ELASTIC3DLINEAR, SOIL), (M.VISCOUS1DLINEAR, [2.5e4])]
+    conn, attr = [], []
+    for b in range(4):
+        for d in (0, 1):                                            # 'dir': 1, 2 in the script = 0, 1 in the JSON (Attach.py:496-497)
+            row = np.zeros(8, dtype=np.int32); row[0], row[1] = b, n0 + b
+            a = np.zeros(10); a[0] = d
+            conn.append(row); attr.append(a)
+    ne0 = m.n_elem
+    m.elem_conn = np.vstack([m.elem_conn, np.array(conn, dtype=np.int32)])
+    m.elem_kind = np.concatenate([m.elem_kind, np.full(8, M.ZEROLENGTH1D, dtype=np.int32)])
+    m.elem_mat = np.concatenate([m.elem_mat, np.ones(8, dtype=np.int32)])
+    m.elem_attr = np.vstack([np.zeros((ne0, 10)), np.array(attr)])
+    m.elem_am = np.concatenate([np.full(ne0, 0.1244195110), np.zeros(8)])
+    m.elem_ak = np.concatenate([np.full(ne0, 0.0007878958), np.zeros(8)])
+    series = np.asarray(g["ricker"], float)
+    m.point_loads = [M.PointLoad(np.array([b], dtype=np.int32), np.array([25000.0, 0.0, 0.0]), series.copy()) for b in range(4)]
+    return m.number_dofs()
+
+
 def fingerprint(m) -> str:
     """Hash of the model inputs, stored beside each golden history so that drift of a generator is
     detected instead of silently comparing different models."""

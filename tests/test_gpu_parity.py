@@ -356,3 +356,19 @@ def test_host_driver_newmark(tmp_path):
     out = M.read_node_recorder(os.path.join(str(tmp_path), "Solution", "Run", "disp.0.out"))
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"newmark_{name}.npz"))
     assert cases.rel_err(out, g["disp"]) < cases.TOL_NEWMARK
+
+
+def test_newmark_device_matches_reference_fixture_j05(oracle):
+    """Fixture J05 of the reference's own validation suite (OpenSees golden histories, 6 significant digits) and the
+    oracle, on the device: Newmark with both Rayleigh coefficients, Lysmer dashpots, 1000 steps."""
+    m = cases.fixture_j05()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "J05", "opensees.npz"))
+    d = _device(m, fields=(0, 1, 2), options={"integrator": 1.0})
+    out = d.run()
+    for f, key in ((0, "disp"), (1, "vel"), (2, "accel")):
+        for col, ours in ((1, 0), (3, 3)):
+            ref = g[key][:, col]
+            err = np.sqrt(np.mean((out[f][:, ours] - ref) ** 2)) / np.sqrt(np.mean(ref ** 2))
+            assert err < 5e-6, (key, col, err)
+        ref, _ = oracle.run(m, field=f, integrator="NEWMARK")
+        assert cases.rel_err(out[f], ref) < 1e-8, key

@@ -51,6 +51,28 @@ def test_oracle_newmark_history_matches_reference_executable(oracle, name):
         assert cases.rel_err(out, g[key]) < 1e-10, key
 
 
+def _j05_errors(hist, g):
+    """relative RMS error per OpenSees column (t, node 1 x, node 1 y, node 401 x, node 401 y) against our recorder
+    layout (node 1 xyz, node 401 xyz), as 03-Validations/.../LaTeX/cmpResults.py compares them"""
+    errs = []
+    for col, ours in ((1, 0), (3, 3)):
+        ref = g[:, col]
+        errs.append(np.sqrt(np.mean((hist[:, ours] - ref) ** 2)) / np.sqrt(np.mean(ref ** 2)))
+    return max(errs)
+
+
+def test_oracle_newmark_matches_reference_fixture_j05_opensees_golden(oracle):
+    """The reference's OWN golden vector for this path: fixture J05 (soil column on Lysmer dashpots, Rayleigh damping
+    with both coefficients, Newmark) ships OpenSees displacement / velocity / acceleration histories printed with
+    6 significant digits."""
+    m = cases.fixture_j05()
+    g = np.load(os.path.join(GOLD, "J05", "opensees.npz"))
+    for f, key, tol in ((0, "disp", 5e-6), (1, "vel", 5e-6), (2, "accel", 5e-6)):
+        out, _ = oracle.run(m, field=f, integrator="NEWMARK")
+        assert out.shape == (999, 6)
+        assert _j05_errors(out, g[key]) < tol, key
+
+
 def test_oracle_vel_accel_match_reference_executable(oracle):
     m = cases.kat444()
     g = gold("kat444")
