@@ -413,6 +413,96 @@ def write_reference_json(m: Model, directory: str, name: str = "Model", combo: s
     return part
 
 
+def read_reference_json(path: str, base_dir: Optional[str] = None) -> Model:
+    """Inverse of write_reference_json for the subset of the schema on this path (SURVEY.md App. D;
+    12-Utilities/Driver.hpp:1981-2046): builds a Model from a per-rank JSON file the reference's pre-processor wrote.
+    Entities are taken in ascending tag order; node / element indices are positions in that order.  Relative load
+    files are resolved against `base_dir` (default: the directory the run is started from = parent of Partition/).
+    Adds m.integrator (the JSON's integrator name) and m.rec_spec = [(resp, [node indices])]."""
+    with open(path) as f:
+        J = json.load(f)
+    base = base_dir or os.path.dirname(os.path.dirname(os.path.abspath(path)))
+    G = J["Global"]
+    m = Model(ndim=int(G["ndim"]), lumped=str(G.get("massform", "LUMPED")).upper() == "LUMPED")
+    ntags = sorted(J["Nodes"], key=int)
+    nidx = {int(t): i for i, t in enumerate(ntags)}
+    m.coords = np.array([[float(v) for v in J["Nodes"][t]["coords"]][:m.ndim] for t in ntags])
+    m.node_ndof = np.array([int(J["Nodes"][t]["ndof"]) for t in ntags], dtype=np.int32)
+    fd = []
+    for t in ntags:
+        row = [int(v) for v in J["Nodes"][t]["freedof"]]
+        if any(v < -1 for v in row):
+            raise ValueError("read_reference_json: constrained dofs are not handled by this reader")
+        fd.append(np.array([0 if v > -1 else -1 for v in row], dtype=np.int32))
+    m.freedof = fd
+    kinds = {v: k for k, v in MAT_NAME.items()}
+    mtags = sorted(J["Materials"], key=int)
+    midx = {int(t): i for i, t in enumerate(mtags)}
+    for t in mtags:
+        M_ = J["Materials"][t]
+        kind = kinds[M_["name"].upper()]
+        m.materials.append((kind, [float(M_["attributes"][k]) for k in MAT_KEYS[kind]]))
+    ekinds = {v: k for k, v in ELEM_NAME.items()}
+    etags = sorted(J["Elements"], key=int)
+    eidx = {int(t): i for i, t in enumerate(etags)}
+    ne = len(etags)
+    m.elem_kind = np.zeros(ne, dtype=np.int32); m.elem_conn = np.zeros((ne, 8), dtype=np.int32)
+    m.elem_mat = np.zeros(ne, dtype=np.int32); m.elem_attr = np.zeros((ne, 10))
+    for i, t in enumerate(etags):
+        E = J["Elements"][t]
+        kind = ekinds[E["name"].upper()]
+        a = E["attributes"]
+        m.elem_kind[i] = kind
+        m.elem_conn[i, :len(E["conn"])] = [nidx[int(n)] for n in E["conn"]]
+        m.elem_mat[i] = midx[int(a["material"])]
+        if kind == LIN2DQUAD4:
+            m.elem_attr[i, 0] = float(a.get("th", 1.0))
+        elif kind == ZEROLENGTH1D:
+            m.elem_attr[i, 0] = int(a["dir"])
+        elif kind == PML3DHEXA8:
+            m.elem_attr[i, :9] = [a["n"], a["L"], a["R"], *a["x0"], *a["npml"]]
+        elif kind == PML2DQUAD4:
+            m.elem_attr[i, :8] = [a.get("th", 1.0), a["n"], a["L"], a["R"], *a["x0"], *a["npml"]]
+    m.elem_am = np.zeros(ne); m.elem_ak = np.zeros(ne)
+    for D in J.get("Dampings", {}).values():
+        if D["name"].upper() == "RAYLEIGH":
+            for t in D["attributes"]["list"]:
+                if m.elem_kind[eidx[int(t)]] != ZEROLENGTH1D:          # ZeroLength1D::SetDamping does nothing
+                    m.elem_am[eidx[int(t)]] = float(D["attributes"]["am"])
+                    m.elem_ak[eidx[int(t)]] = float(D["attributes"]["ak"])
+    if not m.elem_am.any() and not m.elem_ak.any():
+        m.elem_am = m.elem_ak = None
+    for t, v in J.get("Masses", {}).items():
+        m.masses.append((nidx[int(t)], [float(x) for x in v["mass"]]))
+    sim = J["Simulations"]
+    combo = J["Combinations"][str(sim["combo"])]["attributes"]
+    for ltag, factor in zip(combo.get("load", []), combo.get("factor", [])):
+        L = J["Loads"][str(ltag)]
+        a = L["attributes"]
+        if L["name"].upper() != "POINTLOAD" or a["type"].upper() != "CONCENTRATED":
+            raise ValueError("read_reference_json: only CONCENTRATED point loads are handled by this reader")
+        if a["name"].upper() == "CONSTANT":
+            series = np.array([float(a["mag"])])
+        else:
+            fn = a["file"] if os.path.isabs(a["file"]) else os.path.join(base, a["file"])
+            tok = open(fn).read().split()                           # Driver.hpp:1514-1527: count, then the values
+            series = np.array([float(v) for v in tok[1:1 + int(tok[0])]])
+        d = np.zeros(3); d[:len(a["dir"])] = a["dir"]
+        m.point_loads.append(PointLoad(np.array([nidx[int(n)] for n in a["list"]], dtype=np.int32), d[:max(m.ndim, len(a["dir"]))][:3],
+                                       series, float(factor)))
+    A = sim["attributes"]
+    m.dt, m.nt = float(A["integrator"]["dt"]), int(A["analysis"]["nt"])
+    m.integrator = A["integrator"]["name"].upper()
+    m.rec_spec = []
+    for r in sorted(J.get("Recorders", {}), key=int):
+        R = J["Recorders"][r]
+        if R["name"].upper() == "NODE":
+            m.rec_spec.append((R["resp"].lower(), [nidx[int(n)] for n in R["list"]]))
+    m.rec_nodes = np.array(m.rec_spec[0][1] if m.rec_spec else [0], dtype=np.int32)
+    m.blocks = []
+    return m.number_dofs()
+
+
 def read_node_recorder(path: str) -> np.ndarray:
     """NODE recorder text file (Recorder.cpp:73-105, 239-269) -> [nrows, ncols] array."""
     with open(path) as f:

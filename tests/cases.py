@@ -179,6 +179,38 @@ def fixture_j05():
     return m.number_dofs()
 
 
+# The reference's own validation fixtures that sit on this path, as INPUT FILES: tests/golden/fixtures/<name>/Partition/*.json
+# is what the reference's pre-processor (01-Pre_Process, run on the fixture's script by tests/golden/make_fixture_inputs.py)
+# wrote, the load files are the fixture's, opensees.npz holds the fixture's OpenSees golden histories.  `cols` maps an
+# OpenSees column to a column of our NODE recorder (as each fixture's LaTeX/cmpResults.py pairs them).
+REF_FIXTURES = {
+    "F02": dict(json="Debugging_F02.1.0.json", cols=((1, 0), (2, 1)), tol=5e-6),             # 1 lin2DQuad4, lumped
+    "F06": dict(json="Debugging_F06.1.0.json", cols=((1, 0), (3, 2)), tol=5e-6),             # quad4 column + dashpots + Rayleigh
+    "J02": dict(json="Debugging_J02.1.0.json", cols=((3, 0), (1, 1), (2, 2)), tol=5e-6),     # 1 lin3DHexa8, CONSISTENT mass
+}
+
+
+def fixture_dir(name):
+    import os
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fixtures", name)
+
+
+def fixture_model(name):
+    import os
+    return M.read_reference_json(os.path.join(fixture_dir(name), "Partition", REF_FIXTURES[name]["json"]))
+
+
+def fixture_errors(name, hist, key):
+    """max over the paired columns of the relative RMS error against the fixture's OpenSees history `key`"""
+    import os
+    g = np.load(os.path.join(fixture_dir(name), "opensees.npz"))[key]
+    errs = []
+    for col, ours in REF_FIXTURES[name]["cols"]:
+        ref = g[:, col]
+        errs.append(np.sqrt(np.mean((hist[:, ours] - ref) ** 2)) / np.sqrt(np.mean(ref ** 2)))
+    return max(errs)
+
+
 def fingerprint(m) -> str:
     """Hash of the model inputs, stored beside each golden history so that drift of a generator is
     detected instead of silently comparing different models."""

@@ -372,3 +372,36 @@ def test_newmark_device_matches_reference_fixture_j05(oracle):
             assert err < 5e-6, (key, col, err)
         ref, _ = oracle.run(m, field=f, integrator="NEWMARK")
         assert cases.rel_err(out[f], ref) < 1e-8, key
+
+
+@pytest.mark.parametrize("name", ["F02", "F06"])
+def test_device_matches_reference_fixture_from_its_own_input_files(oracle, tmp_path, name):
+    """The reference's fixtures F02 / F06 as the reference's pre-processor wrote them: (i) through the Python binding,
+    (ii) through the C++ host driver reading the JSON + load files and writing the reference's recorder files; both
+    against the fixture's OpenSees golden histories and the oracle."""
+    import shutil
+    import subprocess
+    m = cases.fixture_model(name)
+    d = _device(m, fields=(0, 1, 2), options={"integrator": 1.0})
+    out = d.run()
+    for f, key in ((0, "disp"), (1, "vel"), (2, "accel")):
+        assert cases.fixture_errors(name, out[f], key) < cases.REF_FIXTURES[name]["tol"], key
+        ref, _ = oracle.run(m, field=f, integrator="NEWMARK")
+        assert cases.rel_err(out[f], ref) < 1e-8, key
+    work = os.path.join(str(tmp_path), name)
+    shutil.copytree(cases.fixture_dir(name), work)
+    J = __import__("json").load(open(os.path.join(work, "Partition", cases.REF_FIXTURES[name]["json"])))
+    combo = J["Combinations"][str(J["Simulations"]["combo"])]["attributes"]["folder"]
+    os.makedirs(os.path.join(work, "Solution", combo), exist_ok=True)
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "svl_b200", "SeismoVLAB_gpu.exe")
+    subprocess.run([exe, "-dir", os.path.join(work, "Partition"), "-file", cases.REF_FIXTURES[name]["json"].replace(".0.json", ".$.json")],
+                   check=True, stdout=subprocess.DEVNULL, cwd=work)
+    for key, fn in (("disp", "Displacement.0.out"), ("vel", "Velocity.0.out"), ("accel", "Acceleration.0.out")):
+        hist = M.read_node_recorder(os.path.join(work, "Solution", combo, fn))
+        assert cases.fixture_errors(name, hist, key) < 2e-5, key          # recorder files carry ndps = 8 digits
+
+
+def test_consistent_mass_fixture_is_refused_loudly():
+    from svl_b200.capi import SvlError
+    with pytest.raises(SvlError):
+        _device(cases.fixture_model("J02"), options={"integrator": 1.0})

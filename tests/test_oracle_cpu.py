@@ -73,6 +73,17 @@ def test_oracle_newmark_matches_reference_fixture_j05_opensees_golden(oracle):
         assert _j05_errors(out, g[key]) < tol, key
 
 
+@pytest.mark.parametrize("name", list(cases.REF_FIXTURES))
+def test_oracle_matches_reference_fixture_from_its_own_input_files(oracle, name):
+    """Fixtures F02 / F06 / J02 of the reference's validation suite, read from the JSON the reference's pre-processor wrote,
+    against the OpenSees golden histories the fixtures ship (6 significant digits)."""
+    m = cases.fixture_model(name)
+    assert m.integrator == "NEWMARK"
+    for f, key in ((0, "disp"), (1, "vel"), (2, "accel")):
+        out, _ = oracle.run(m, field=f, integrator=m.integrator)
+        assert cases.fixture_errors(name, out, key) < cases.REF_FIXTURES[name]["tol"], key
+
+
 def test_oracle_vel_accel_match_reference_executable(oracle):
     m = cases.kat444()
     g = gold("kat444")
