@@ -663,7 +663,7 @@ struct Shell3 {
     double *hF;               // halo pass: [n_if][3] partial internal force
 };
 template <bool LOWREG>
-__global__ void __launch_bounds__(128, LOWREG ? 5 : 4) k_stencil3_shell(const Shell3 p) {
+__global__ void __launch_bounds__(128, LOWREG ? 8 : 6) k_stencil3_shell(const Shell3 p) {
     __shared__ double T[kTbl3Stride];
     {
         const double *Tg = p.tbl + (size_t)p.chunk_cls[blockIdx.x] * kTbl3Stride;
@@ -1217,7 +1217,9 @@ __global__ void k_nodal_loads(const PLArgs a) {
 // ------------------------------------------------------------------------------------------
 struct DrmArgs {
     int n, nn, ndim, nt, nf, k, analytic;
-    const int32_t *dof0, *ptr, *col, *bid;
+    const int32_t *dof0, *ptr;
+    const int2 *cb;               // per entry: (local DRM node index of the column node, id of the unique K block)
+    int us;                       // doubles per node in uo (ndim padded to 4 / 2)
     const uint8_t *ext;
     const double *dict;           // unique K blocks [nblk][ndim*ndim]
     const double *field;          // [nn][nt][nf]
@@ -1248,46 +1250,55 @@ __global__ void k_drm_field(const DrmArgs a) {
         double s = 0.0;
         for (int c = 0; c < a.ndim; c++) s += (a.xyz[(long long)t * a.ndim + c] - a.xref[c]) * a.dir[c];
         const double val = a.amp * ricker_disp(k * a.dt - a.t0 - s / a.c, a.f0);
-        for (int c = 0; c < a.ndim; c++) a.uo[(long long)t * a.ndim + c] = sgn * (val * a.pol[c]);
+        for (int c = 0; c < a.ndim; c++) a.uo[(long long)t * a.us + c] = sgn * (val * a.pol[c]);
     } else {
-        if (k >= a.nt) { for (int c = 0; c < a.ndim; c++) a.uo[(long long)t * a.ndim + c] = 0.0; return; }
+        if (k >= a.nt) { for (int c = 0; c < a.ndim; c++) a.uo[(long long)t * a.us + c] = 0.0; return; }
         const double *row = a.field + ((long long)t * a.nt + k) * a.nf;
-        for (int c = 0; c < a.ndim; c++) a.uo[(long long)t * a.ndim + c] = sgn * row[c];
+        for (int c = 0; c < a.ndim; c++) a.uo[(long long)t * a.us + c] = sgn * row[c];
     }
 }
 // forces of the DRM rows for one step into a compact buffer F[row][ndim] (one thread per row and component);
-// they depend on the step index only, never on the state, so they are computed one step ahead on a side stream
-// (a one-thread-per-row ELL variant was measured slower: fewer threads in flight, profiles/r1l)
-__global__ void k_drm(const DrmArgs a, double *F) {
+// they depend on the step index only, never on the state, so they are computed one step ahead on a side stream.
+// The kernel is bound by L1 requests (profiles/r1y: 54 % LSU wavefronts, 7 sectors per request), so the operands are
+// laid out for wide loads: (column node, block id) pairs as int2, incident displacements and dictionary rows padded to
+// 4 doubles (3-D: one 128-bit + one 64-bit load each; 2-D: one 128-bit load) -- 5 requests per entry instead of 8.
+// (A one-thread-per-row ELL variant was measured slower: fewer threads in flight, profiles/r1l.)
+template <int ND>
+__global__ void __launch_bounds__(128) k_drm(const DrmArgs a, double *F) {
+    constexpr int NS = (ND == 3) ? 4 : 2;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int nd = a.ndim;
-    if (t >= a.n * nd) return;
-    const int row = t / nd, r = t - row * nd;
+    if (t >= a.n * ND) return;
+    const int row = t / ND, r = t - row * ND;
     double f = 0.0;
     const int q1 = a.ptr[row + 1];
     int q = a.ptr[row];
-    // four entries at a time: their index and operand loads are independent and go out together (the kernel is
-    // bound by the ptr -> col/bid -> u/B dependent-load chain); the sum keeps the ascending entry order
+    // four entries at a time: their index and operand loads are independent and go out together; the sum keeps the
+    // ascending entry order
     for (; q + 4 <= q1; q += 4) {
-        int cq[4], bq[4];
+        int2 cb[4];
 #pragma unroll
-        for (int z = 0; z < 4; z++) { cq[z] = a.col[q + z]; bq[z] = a.bid[q + z]; }
-        double uu[4][3], BB[4][3];
+        for (int z = 0; z < 4; z++) cb[z] = a.cb[q + z];
+        double2 u2[4], b2[4];
+        double u3[4], b3[4];
 #pragma unroll
-        for (int z = 0; z < 4; z++)
+        for (int z = 0; z < 4; z++) {
+            const double *u = a.uo + (long long)cb[z].x * NS;
+            const double *B = a.dict + ((long long)cb[z].y * ND + r) * NS;
+            u2[z] = *reinterpret_cast<const double2 *>(u); b2[z] = *reinterpret_cast<const double2 *>(B);
+            if (ND == 3) { u3[z] = u[2]; b3[z] = B[2]; }
+        }
 #pragma unroll
-            for (int c = 0; c < 3; c++)
-                if (c < nd) { uu[z][c] = a.uo[(long long)cq[z] * nd + c]; BB[z][c] = a.dict[(long long)bq[z] * nd * nd + r * nd + c]; }
-#pragma unroll
-        for (int z = 0; z < 4; z++)
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-                if (c < nd) f += BB[z][c] * uu[z][c];
+        for (int z = 0; z < 4; z++) {
+            f += b2[z].x * u2[z].x;
+            f += b2[z].y * u2[z].y;
+            if (ND == 3) f += b3[z] * u3[z];
+        }
     }
     for (; q < q1; q++) {
-        const double *u = a.uo + (long long)a.col[q] * nd;
-        const double *B = a.dict + (long long)a.bid[q] * nd * nd + r * nd;
-        for (int c = 0; c < nd; c++) f += B[c] * u[c];
+        const int2 cb = a.cb[q];
+        const double *u = a.uo + (long long)cb.x * NS;
+        const double *B = a.dict + ((long long)cb.y * ND + r) * NS;
+        for (int c = 0; c < ND; c++) f += B[c] * u[c];
     }
     F[t] = a.factor * f;
 }
@@ -1607,14 +1618,15 @@ void record_rows(svlgpu_model *m, bool devk) {
 static int drm_compute(svlgpu_model *m, DrmDev &d, int k, cudaStream_t st) {
     DrmArgs a;
     a.n = d.n_nodes; a.nn = d.n_all; a.ndim = m->ndim; a.nt = d.nt; a.nf = d.nf; a.k = k; a.analytic = d.analytic;
-    a.dof0 = d.d_node_dof0; a.ptr = d.d_row_ptr; a.col = d.d_col_node; a.bid = d.d_blk_id; a.ext = d.d_ext;
+    a.dof0 = d.d_node_dof0; a.ptr = d.d_row_ptr; a.cb = (const int2 *)d.d_col_blk; a.us = (m->ndim == 3) ? 4 : 2; a.ext = d.d_ext;
     a.dict = d.d_blk; a.field = d.d_field; a.xyz = d.d_xyz; a.uo = d.d_uo[k & 1];
     for (int c = 0; c < 3; c++) { a.dir[c] = d.dir[c]; a.pol[c] = d.pol[c]; a.xref[c] = d.xref[c]; }
     a.c = d.c; a.f0 = d.f0; a.t0 = d.t0; a.amp = d.amp; a.factor = d.factor; a.dt = m->dt;
     a.kinv = nullptr; a.Un = nullptr; a.target = nullptr; a.hF = nullptr; a.phase = 0;
     a.kctl = m->graph_capturing ? m->d_kctl + 2 + (k & 1) : nullptr; a.koff = 0;
     k_drm_field<<<(a.nn + 127) / 128, 128, 0, st>>>(a);
-    k_drm<<<(a.n * a.ndim + 127) / 128, 128, 0, st>>>(a, d.d_F[k & 1]);
+    if (m->ndim == 3) k_drm<3><<<(a.n * 3 + 127) / 128, 128, 0, st>>>(a, d.d_F[k & 1]);
+    else k_drm<2><<<(a.n * 2 + 127) / 128, 128, 0, st>>>(a, d.d_F[k & 1]);
     d.buf_k[k & 1] = k;
     m->total_launches += 2;
     CUDA_OK(cudaGetLastError());

@@ -74,7 +74,7 @@ struct Block {
     int n_shell_all = 0;
     std::vector<uint8_t> h_cls;      // host copy of the class ids (planner scratch)
 };
-constexpr int kShellNPT = 4;         // nodes per thread of k_stencil3_shell
+constexpr int kShellNPT = 2;         // nodes per thread of k_stencil3_shell
 constexpr int kShellChunk = 128 * kShellNPT;
 constexpr int kDomNW = 4;            // warps per CTA of k_stencil3_dom
 constexpr int kDomR = 4;             // lattice rows per thread
@@ -113,10 +113,10 @@ struct DrmDev {
     uint8_t *d_ext = nullptr;
     double *d_field = nullptr;       // [nnodes][nt][nf]
     int32_t *d_row_ptr = nullptr;    // CSR over DRM nodes
-    int32_t *d_col_node = nullptr;   // local DRM node index of the column node
-    int32_t *d_blk_id = nullptr;     // per entry: index into the dictionary of unique K blocks
-    double *d_blk = nullptr;         // [nblk][ndim*ndim] unique K blocks (row node <- col node)
-    double *d_uo[2] = {nullptr, nullptr};   // [n_all][ndim] incident displacement of step k in buffer k & 1
+    int32_t *d_col_blk = nullptr;    // per entry: (local DRM node index of the column node, index into the dictionary of
+                                     // unique K blocks) as int2
+    double *d_blk = nullptr;         // [nblk][ndim][4 | 2] unique K blocks (row node <- col node), rows padded for wide loads
+    double *d_uo[2] = {nullptr, nullptr};   // [n_all][4 | 2] incident displacement of step k in buffer k & 1 (padded)
     double *d_F[2] = {nullptr, nullptr};    // [n_nodes][ndim] row forces of step k in buffer k & 1
     int buf_k[2] = {-1, -1};
     cudaEvent_t ev_ready[2] = {nullptr, nullptr};

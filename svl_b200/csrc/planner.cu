@@ -855,9 +855,21 @@ int plan_and_upload(svlgpu_model *m) {
             for (size_t i = 0; i < dof0.size(); i++) tgt[i] = halo_slot_of_dof(dof0[i]);
             dd.d_target = dupload(m, tgt);
         }
-        dd.d_node_dof0 = dupload(m, dof0); dd.d_row_ptr = dupload(m, ptr); dd.d_col_node = dupload(m, col);
-        dd.d_blk_id = dupload(m, bid); dd.d_blk = dupload(m, dict); dd.d_ext = dupload(m, dl.ext);
-        dd.d_uo[0] = dalloc<double>(m, (size_t)nn * nd); dd.d_uo[1] = dalloc<double>(m, (size_t)nn * nd);
+        {
+            const int NS = (nd == 3) ? 4 : 2;                      // padded row / node stride (see k_drm)
+            std::vector<int32_t> cb(2 * col.size() + 2, 0);
+            for (size_t q = 0; q < col.size(); q++) { cb[2 * q] = col[q]; cb[2 * q + 1] = bid[q]; }
+            const size_t nblk = dict.size() / (nd * nd);
+            std::vector<double> dpad(nblk * nd * NS + 4, 0.0);
+            for (size_t b = 0; b < nblk; b++)
+                for (int r = 0; r < nd; r++)
+                    for (int c = 0; c < nd; c++) dpad[(b * nd + r) * NS + c] = dict[b * nd * nd + r * nd + c];
+            dd.d_col_blk = dupload(m, cb); dd.d_blk = dupload(m, dpad);
+            dd.d_uo[0] = dalloc<double>(m, (size_t)nn * NS + 4); dd.d_uo[1] = dalloc<double>(m, (size_t)nn * NS + 4);
+            CUDA_OK(cudaMemset(dd.d_uo[0], 0, sizeof(double) * ((size_t)nn * NS + 4)));
+            CUDA_OK(cudaMemset(dd.d_uo[1], 0, sizeof(double) * ((size_t)nn * NS + 4)));
+        }
+        dd.d_node_dof0 = dupload(m, dof0); dd.d_row_ptr = dupload(m, ptr); dd.d_ext = dupload(m, dl.ext);
         dd.d_F[0] = dalloc<double>(m, (size_t)rows.size() * nd + 1); dd.d_F[1] = dalloc<double>(m, (size_t)rows.size() * nd + 1);
         CUDA_OK(cudaEventCreateWithFlags(&dd.ev_ready[0], cudaEventDisableTiming));
         CUDA_OK(cudaEventCreateWithFlags(&dd.ev_ready[1], cudaEventDisableTiming));
