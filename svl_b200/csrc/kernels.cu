@@ -1860,6 +1860,7 @@ template <int SLOT> static int cfg_slot() {
 int configure_kernels() {
     if (cfg_slot<0>() || cfg_slot<1>() || cfg_slot<2>() || cfg_slot<3>()) return 1;
     CUDA_OK(cudaFuncSetAttribute(k_stencil2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    if (pml_configure()) return 1;
     return 0;
 }
 bool stencil_entry_nonzero(int di, int b, int dj, int s, int a) { return stencil_nz(di, b, dj, s, a); }

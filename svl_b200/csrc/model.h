@@ -163,7 +163,8 @@ struct HaloDev {
 // PML block: the dofs of the PML nodes plus the soil dofs they are tied to form the part of
 // Keff = M/dt^2 + C/2dt that is not diagonal; it is solved every step by a matrix-free,
 // Jacobi-scaled BiCGStab (pml.cu).  All element matrices live in per-class tables.
-constexpr int kPmlChunk = 8;         // elements of one class per chunk of k_pml_elem_sp (= kPmlG in pml.cu)
+constexpr int kPmlChunk3 = 64;       // elements of one class per CTA of k_pml_elem_rg (= 8 NEG in pml.cu): 3-D, 4 CTAs/SM
+constexpr int kPmlChunk2 = 128;      // 2-D
 struct PmlDev {
     bool present = false;
     int nde = 72;                    // dofs per element (72 | 20)
@@ -171,7 +172,7 @@ struct PmlDev {
     double *d_A = nullptr;           // [n_cls][nde*nde] Keff_e, stored transposed ([col][row])
     double *d_K = nullptr;           // [n_cls][...] K_e
     double *d_Km = nullptr;          // [n_cls][...] M/dt^2 - C/2dt
-    // pattern-sparse twins [n_cls][npe][sp_q][nde] + one-class element chunks (k_pml_elem_sp); sp_q == 0: dense kernel
+    // pattern-sparse twins [n_cls][npe][sp_q][ndofn][npe] + one-class element groups (k_pml_elem_rg); sp_q == 0: dense kernel
     double *d_sA = nullptr, *d_sK = nullptr, *d_sKm = nullptr;
     int sp_q = 0, n_chunks = 0;
     int8_t sp_pat[9][4] = {};
@@ -333,6 +334,7 @@ void halo_destroy(svlgpu_model *m);
 int pml_step(svlgpu_model *m, const double *U, const double *Up, double *Un);
 int pml_internal_force(svlgpu_model *m, const double *U, double *F);
 void pml_destroy(svlgpu_model *m);
+int pml_configure();
 // newmark.cu / kernels.cu
 int newmark_plan(svlgpu_model *m);
 int newmark_step(svlgpu_model *m, int k, const double *dev_amp);

@@ -1092,9 +1092,10 @@ static int plan_pml_nd(svlgpu_model *m, const std::vector<int32_t> &alias, const
                     for (int cc = 0; cc < nn; cc++) {
                         if (!nz[r][cc]) continue;
                         for (int k = 0; k < npe; k++) {
-                            const int j = k * nn + cc;
+                            const int j = k * nn + cc;                        // column dof
                             const size_t from = c * nde * nde + (size_t)j * nde + i;
-                            const size_t to = c * per + (size_t)(k * QMAX + cnt_r) * nde + i;
+                            // tiled layout [k][q][r][row node]: the rows (node, r) of one component are contiguous
+                            const size_t to = c * per + ((size_t)(k * QMAX + cnt_r) * nn + r) * npe + (i / nn);
                             sA[to] = tA[from]; sK[to] = tP[from]; sKm[to] = tK[from];
                         }
                         cnt_r++;
@@ -1110,9 +1111,10 @@ static int plan_pml_nd(svlgpu_model *m, const std::vector<int32_t> &alias, const
                 const int c = ecls[order[i]];
                 size_t j = i;
                 while (j < order.size() && ecls[order[j]] == c) j++;
-                for (size_t at = i; at < j; at += kPmlChunk) {
+                constexpr size_t EBp = (ND == 3) ? kPmlChunk3 : kPmlChunk2;
+                for (size_t at = i; at < j; at += EBp) {
                     ccls.push_back(c);
-                    for (size_t q = at; q < at + kPmlChunk; q++) celem.push_back(q < j ? order[q] : -1);
+                    for (size_t q = at; q < at + EBp; q++) celem.push_back(q < j ? order[q] : -1);
                 }
                 i = j;
             }

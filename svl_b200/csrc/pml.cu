@@ -102,98 +102,133 @@ __global__ void __launch_bounds__(NDE * EPB) k_pml_elem(int n_elem, int mode, co
     ye[(size_t)e * NDE + i] = acc;
 }
 
-// ---- element products, class-blocked and pattern-sparse --------------------------------------------------------------
+// ---- element products, class-blocked, pattern-sparse and register-tiled ---------------------------------------------
 // The 9x9 (3-D) / 5x5 (2-D) node-pair blocks of M, C, K carry 33 / 13 structural non-zeros (one
 // diagonal term per row, the s11-s22-s33 compliance block and the u-sigma gradient coupling), so a row of the element
-// matrix holds at most Q = 4 / 3 entries per neighbour node.  Elements are processed in chunks of kPmlG elements of ONE
-// class: a CTA row-thread keeps kPmlG accumulators, so a table entry is loaded once per kPmlG DFMAs and the element
-// vectors come from shared memory as 128-bit loads -- the dense kernel above issues one global and one shared load per
-// DFMA and runs at the LSU limit.  The retained terms are summed in the dense kernel's order (ascending column), the
-// skipped ones are exact zeros, so both kernels return the same bits.
-//   tables  Ts[class][node k][entry q][row i]   (row fastest: coalesced), columns  k * NN + pat[i % NN][q]
-constexpr int kPmlG = kPmlChunk;
-struct PmlSp {
-    int n_chunks, mode;
-    const int32_t *chunk_cls;      // [n_chunks]
-    const int32_t *chunk_elem;     // [n_chunks][kPmlG] element index or -1
+// matrix holds at most Q = 4 / 3 entries per neighbour node, and -- this is what the tiling uses -- the COLUMN pattern of a
+// row depends on its component r only, not on its node j.  One CTA takes up to EB = 8 NEG elements of ONE class:
+//   * the class table Ts[k][q][r][j] (18 KB) and the gathered element vectors xs[dof][element] (75 KB) sit in shared memory;
+//   * thread (r, eg) owns the NPE rows (j, r) of 8 elements: per (neighbour node k, entry q) it reads NPE table values and
+//     8 vector values with 128-bit shared loads and issues 8 NPE DFMAs -- one shared load per 8 DFMAs, where the dense
+//     kernel above needs a global and a shared load per DFMA (LSU-bound) and the previous chunked kernel re-read the
+//     table from L2 for every 8 elements (profiles/r1n, r1o: 11.7 of 15.1 ms per step at 200^3 + PML);
+//   * results go back through shared memory so that the element-force arena is written with coalesced stores.
+// The retained terms are summed in the dense kernel's order (ascending column), the skipped ones are exact zeros, so all
+// three kernels return the same bits.
+//   mode 0: ye = T x        mode 2: ye = filt(T x)        mode 3: ye = T (x1 - x2) - ye   (second pass of the right-hand side)
+constexpr int kPmlG = 8;
+struct PmlRg {
+    int mode;
+    const int32_t *grp_cls;        // [n_groups]
+    const int32_t *grp_elem;       // [n_groups][EB] element index or -1
     const int32_t *idx;            // [n_elem][NDE] gather index of every element dof (or -1)
-    const double *T1, *T2;         // sparse class tables
+    const double *T;               // class tables [cls][NPE][Q][NN][NPE]
     const double *x1, *x2, *xs;
     double *ye;
     double ftol;
-    const double *part;
-    int rr_slot;
-    double tol2;
+    const double *part;            // convergence flag (or null)
     int8_t pat[9][4];              // column component of entry q of a row of component r (padding: coefficient 0)
 };
-template <int NN, int NPE, int Q, int CPB>
-__global__ void __launch_bounds__(NN * NPE * CPB) k_pml_elem_sp(const PmlSp a) {
-    constexpr int NDE = NN * NPE;
-    __shared__ __align__(16) double sx1[CPB][NDE][kPmlG];
-    __shared__ __align__(16) double sx2[CPB][NDE][kPmlG];
+template <int NN, int NPE, int Q, int NEG>
+__global__ void __launch_bounds__(NN * NEG, (NEG == 8) ? 4 : 2) k_pml_elem_rg(const PmlRg a) {
+    constexpr int NDE = NN * NPE, EB = NEG * kPmlG, ROW = EB + 2, NT = NN * NEG, TSZ = NPE * Q * NN * NPE;
+    extern __shared__ __align__(16) double sm[];
+    double *xs = sm;                       // [NDE][ROW]: element e = eg + NEG t sits at (t / 2) * 2 NEG + 2 eg + (t & 1)
+    double *Ts = sm + NDE * ROW;           // [NPE][Q][NN][NPE]
+    __shared__ int spat[9 * 4];
     if (a.part && a.part[kFlagAt] != 0.0) return;         // solver already converged
-    const int lc = threadIdx.x / NDE, i = threadIdx.x - lc * NDE;
-    const int ch = blockIdx.x * CPB + lc;
-    const bool act = ch < a.n_chunks;
-    int ez[kPmlG];
-    if (act) {
+    const int tid = threadIdx.x;
+    if (tid < 36) spat[tid] = a.pat[tid >> 2][tid & 3];
+    const int32_t *ge = a.grp_elem + (size_t)blockIdx.x * EB;
+    {
+        const double *Tg = a.T + (size_t)a.grp_cls[blockIdx.x] * TSZ;
+        for (int i = tid; i < TSZ; i += NT) Ts[i] = Tg[i];
+    }
+    auto slot = [](int e) { const int eg = e % NEG, t = e / NEG; return (t >> 1) * (2 * NEG) + 2 * eg + (t & 1); };
+    // gather, 8 (element, dof) pairs per thread at a time: the index loads, then the value loads, go out together (the
+    // phase is pure latency: two dependent global loads per pair)
+    static_assert((EB * NDE) % (8 * NT) == 0, "gather batches must tile the group");
+    for (int p0 = tid; p0 < EB * NDE; p0 += 8 * NT) {
+        int zz[8], qq[8];
 #pragma unroll
-        for (int g = 0; g < kPmlG; g++) {
-            ez[g] = a.chunk_elem[(size_t)ch * kPmlG + g];
-            double v = 0.0, v2 = 0.0;
-            if (ez[g] >= 0) {
-                const int q = a.idx[(size_t)ez[g] * NDE + i];
-                if (q >= 0) {
-                    v = a.xs ? a.x1[q] * a.xs[q] : a.x1[q];
-                    if (a.mode == 1) v2 = v - a.x2[q];
-                }
-            }
-            sx1[lc][i][g] = v;
-            if (a.mode == 1) sx2[lc][i][g] = v2;
+        for (int b = 0; b < 8; b++) zz[b] = ge[(p0 + b * NT) / NDE];
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const int p = p0 + b * NT, e = p / NDE, d = p - e * NDE;
+            qq[b] = zz[b] >= 0 ? a.idx[(size_t)zz[b] * NDE + d] : -1;
+        }
+        double vv[8], ss[8], ww[8];
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            vv[b] = qq[b] >= 0 ? a.x1[qq[b]] : 0.0;
+            ss[b] = (qq[b] >= 0 && a.xs) ? a.xs[qq[b]] : 1.0;
+            ww[b] = (qq[b] >= 0 && a.mode == 3) ? a.x2[qq[b]] : 0.0;
+        }
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const int p = p0 + b * NT, e = p / NDE, d = p - e * NDE;
+            double v = a.xs ? vv[b] * ss[b] : vv[b];
+            if (a.mode == 3) v -= ww[b];
+            xs[d * ROW + slot(e)] = v;
         }
     }
     __syncthreads();
-    if (!act) return;
-    const int r = i % NN;
-    int col[Q];
+    const int r = tid / NEG, eg = tid - r * NEG;
+    int colo[Q];                           // row offset of the column component of entry q
 #pragma unroll
-    for (int q = 0; q < Q; q++) col[q] = a.pat[r][q];
-    const size_t tb = (size_t)a.chunk_cls[ch] * NPE * Q * NDE + i;
-    double acc[kPmlG], acc2[kPmlG];
+    for (int q = 0; q < Q; q++) colo[q] = spat[r * 4 + q] * ROW + 2 * eg;
+    double acc[NPE][kPmlG];
 #pragma unroll
-    for (int g = 0; g < kPmlG; g++) { acc[g] = 0.0; acc2[g] = 0.0; }
+    for (int j = 0; j < NPE; j++)
+#pragma unroll
+        for (int t = 0; t < kPmlG; t++) acc[j][t] = 0.0;
 #pragma unroll
     for (int k = 0; k < NPE; k++) {
 #pragma unroll
         for (int q = 0; q < Q; q++) {
-            const double t1 = __ldg(a.T1 + tb + (size_t)(k * Q + q) * NDE);
-            const double2 *xv = reinterpret_cast<const double2 *>(&sx1[lc][k * NN + col[q]][0]);
+            double tv[NPE], xv[kPmlG];
+            const double2 *tp = reinterpret_cast<const double2 *>(Ts + ((k * Q + q) * NN + r) * NPE);
 #pragma unroll
-            for (int g = 0; g < kPmlG / 2; g++) {
-                const double2 x = xv[g];
-                acc[2 * g] = fma(t1, x.x, acc[2 * g]);
-                acc[2 * g + 1] = fma(t1, x.y, acc[2 * g + 1]);
-            }
-            if (a.mode == 1) {
-                const double t2 = __ldg(a.T2 + tb + (size_t)(k * Q + q) * NDE);
-                const double2 *yv = reinterpret_cast<const double2 *>(&sx2[lc][k * NN + col[q]][0]);
+            for (int j = 0; j < NPE / 2; j++) { const double2 w = tp[j]; tv[2 * j] = w.x; tv[2 * j + 1] = w.y; }
+            const double2 *xp = reinterpret_cast<const double2 *>(xs + k * NN * ROW + colo[q]);
 #pragma unroll
-                for (int g = 0; g < kPmlG / 2; g++) {
-                    const double2 x = yv[g];
-                    acc2[2 * g] = fma(t2, x.x, acc2[2 * g]);
-                    acc2[2 * g + 1] = fma(t2, x.y, acc2[2 * g + 1]);
-                }
-            }
+            for (int u = 0; u < kPmlG / 2; u++) { const double2 w = xp[u * NEG]; xv[2 * u] = w.x; xv[2 * u + 1] = w.y; }
+#pragma unroll
+            for (int j = 0; j < NPE; j++)
+#pragma unroll
+                for (int t = 0; t < kPmlG; t++) acc[j][t] = fma(tv[j], xv[t], acc[j][t]);
         }
     }
+    __syncthreads();                       // all reads of xs done: reuse it for the results
 #pragma unroll
-    for (int g = 0; g < kPmlG; g++) {
-        if (ez[g] < 0) continue;
-        double v = acc[g];
-        if (a.mode == 1) v = acc2[g] - (fabs(v) > a.ftol ? v : 0.0);
-        else if (a.mode == 2 && !(fabs(v) > a.ftol)) v = 0.0;
-        a.ye[(size_t)ez[g] * NDE + i] = v;
+    for (int j = 0; j < NPE; j++) {
+        double2 *op = reinterpret_cast<double2 *>(xs + (j * NN + r) * ROW + 2 * eg);
+#pragma unroll
+        for (int u = 0; u < kPmlG / 2; u++) op[u * NEG] = make_double2(acc[j][2 * u], acc[j][2 * u + 1]);
     }
+    __syncthreads();
+    for (int p0 = tid; p0 < EB * NDE; p0 += 8 * NT) {
+        double old[8];
+        int zz[8];
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const int p = p0 + b * NT, e = p / NDE, d = p - e * NDE;
+            zz[b] = ge[e];
+            old[b] = (a.mode == 3 && zz[b] >= 0) ? a.ye[(size_t)zz[b] * NDE + d] : 0.0;
+        }
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const int p = p0 + b * NT, e = p / NDE, d = p - e * NDE;
+            if (zz[b] < 0) continue;
+            double v = xs[d * ROW + slot(e)];
+            if (a.mode == 2 && !(fabs(v) > a.ftol)) v = 0.0;
+            if (a.mode == 3) v -= old[b];
+            a.ye[(size_t)zz[b] * NDE + d] = v;
+        }
+    }
+}
+template <int NN, int NPE, int Q, int NEG> constexpr size_t pml_rg_smem() {
+    return sizeof(double) * ((size_t)NN * NPE * (NEG * kPmlG + 2) + (size_t)NPE * Q * NN * NPE);
 }
 
 // ---- right-hand side: b~ = W (bext + gather(ye) + soil part);  partial ||b~||^2 ---------------------------------
@@ -344,16 +379,20 @@ static void elem_products(svlgpu_model *m, int mode, const int32_t *idx, const d
     timer_begin(m, 6);
     struct End { svlgpu_model *m; ~End() { timer_end(m, 6); } } end_{m};
     if (P.sp_q > 0) {
-        // class-blocked sparse kernel: T1 / T2 name the dense tables; use their sparse twins
+        // class-blocked register-tiled kernel: T1 / T2 name the dense tables; use their tiled twins
         auto sp = [&](const double *T) { return T == P.d_A ? P.d_sA : T == P.d_K ? P.d_sK : T == P.d_Km ? P.d_sKm : nullptr; };
-        PmlSp a;
-        a.n_chunks = P.n_chunks; a.mode = mode; a.chunk_cls = P.d_chunk_cls; a.chunk_elem = P.d_chunk_elem; a.idx = idx;
-        a.T1 = sp(T1); a.T2 = sp(T2); a.x1 = x1; a.x2 = x2; a.xs = xs; a.ye = P.d_ye; a.ftol = P.ftol;
-        a.part = part; a.rr_slot = rr_slot; a.tol2 = tol2;
+        PmlRg a;
+        a.grp_cls = P.d_chunk_cls; a.grp_elem = P.d_chunk_elem; a.idx = idx;
+        a.x1 = x1; a.x2 = x2; a.xs = xs; a.ye = P.d_ye; a.ftol = P.ftol; a.part = part;
         std::memcpy(a.pat, P.sp_pat, sizeof(a.pat));
-        if (P.nde == 72) k_pml_elem_sp<9, 8, 4, 2><<<(P.n_chunks + 1) / 2, 144, 0, m->stream>>>(a);
-        else k_pml_elem_sp<5, 4, 3, 8><<<(P.n_chunks + 7) / 8, 160, 0, m->stream>>>(a);
-        m->total_launches++;
+        auto launch = [&](int md, const double *T) {
+            a.mode = md; a.T = T;
+            if (P.nde == 72) k_pml_elem_rg<9, 8, 4, kPmlChunk3 / 8><<<P.n_chunks, 9 * (kPmlChunk3 / 8), pml_rg_smem<9, 8, 4, kPmlChunk3 / 8>(), m->stream>>>(a);
+            else k_pml_elem_rg<5, 4, 3, 16><<<P.n_chunks, 5 * 16, pml_rg_smem<5, 4, 3, 16>(), m->stream>>>(a);
+            m->total_launches++;
+        };
+        if (mode == 1) { launch(2, sp(T1)); launch(3, sp(T2)); }      // ye = Kminus (x1 - x2) - filt(K x1)
+        else launch(mode, sp(T1));
         return;
     }
     if (P.nde == 72) launch_elem<72, 4>(m, mode, idx, T1, x1, T2, x2, xs, part, rr_slot, tol2);
@@ -435,6 +474,12 @@ int pml_internal_force(svlgpu_model *m, const double *U, double *F) {
     const int n = P.n_elem * P.nde;
     k_pml_fint_add<<<(n + 255) / 256, 256, 0, m->stream>>>(n, P.d_edof, P.d_ye, F);
     CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int pml_configure() {
+    CUDA_OK(cudaFuncSetAttribute(k_pml_elem_rg<9, 8, 4, kPmlChunk3 / 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pml_rg_smem<9, 8, 4, kPmlChunk3 / 8>()));
+    CUDA_OK(cudaFuncSetAttribute(k_pml_elem_rg<5, 4, 3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pml_rg_smem<5, 4, 3, 16>()));
     return 0;
 }
 
