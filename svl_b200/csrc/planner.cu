@@ -1133,8 +1133,8 @@ static int plan_pml_nd(svlgpu_model *m, const std::vector<int32_t> &alias, const
         if (!*v) { set_error("out of device memory (PML vectors)"); return 1; }
         CUDA_OK(cudaMemset(*v, 0, sizeof(double) * std::max(1, P.nc)));
     }
-    P.d_part = dalloc<double>(m, 8 * 1024);
-    CUDA_OK(cudaMemset(P.d_part, 0, sizeof(double) * 8 * 1024));
+    P.d_part = dalloc<double>(m, 16 * 1024);
+    CUDA_OK(cudaMemset(P.d_part, 0, sizeof(double) * 16 * 1024));
     CUDA_OK(cudaMallocHost(&P.h_scal, sizeof(double) * 8));
     const char *rt = getenv("SVLGPU_PML_RTOL");
     if (rt) P.rtol = atof(rt);

@@ -25,7 +25,7 @@ namespace svl {
         }                                                                                   \
     } while (0)
 
-constexpr int kRedBlocks = 296;      // 2 per SM; every reduction writes kRedBlocks partials
+constexpr int kRedBlocks = 1184;     // 8 per SM (full occupancy: the gathers are latency-bound); every reduction writes kRedBlocks partials
 constexpr int kRedThreads = 256;
 // partial-sum slots
 enum { S_BB = 0, S_RHO = 1, S_RHV = 2, S_TS = 3, S_TT = 4, S_RR0 = 5, S_RR1 = 6, S_NSLOT = 7 };
