@@ -35,9 +35,13 @@ MAT = [1.3e7, 0.3, 2000.0]   # fixture J05 soil
 
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
+    try:
         with open(p) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            v = float(json.load(f)["hbm_gbs"])
+        if v > 0:
+            return v, "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except (OSError, KeyError, TypeError, ValueError):
+        pass
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
@@ -222,7 +226,11 @@ def ncu_traffic(n):
     `ncu --set full` capture of this very command (profiles/ncu_traffic.json); None when no capture matches."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            return json.load(f).get(f"k_stencil3_tma@n{n}", {}).get("dram_bytes_per_launch")
+            j = json.load(f)
+        for kern in ("k_stencil3_v4", "k_stencil3_tma"):          # newest capture of the dominant kernel first
+            if f"{kern}@n{n}" in j:
+                return j[f"{kern}@n{n}"].get("dram_bytes_per_launch")
+        return None
     except OSError:
         return None
 
@@ -328,7 +336,7 @@ def main():
     st_ms, st_n = kt[0]
     ach = HEX8_BYTES * c["n_block_nodes"] / (st_ms * 1e-3) / 1e9 if st_n else None
     own_bytes = 3 * 8 * 3 + 1           # U_n, U_{n-1} reads + U_{n+1} write + 1 class byte per node
-    roof = {"bound": "hbm", "kernel": "k_stencil3_dom (block-stencil force + CentralDifference update, rank 0)",
+    roof = {"bound": "hbm", "kernel": "k_stencil3_v4 (block-stencil force + CentralDifference update, rank 0)",
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
             "traffic": ncu_traffic(args.n if world == 1 else None),
             "peak_source": peak_src, "avg_launch_ms": st_ms, "launches_timed": st_n,

@@ -25,7 +25,10 @@ PEAK = 6650.0
 
 def peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else PEAK
+    try:
+        return float(json.load(open(p))["hbm_gbs"])
+    except (OSError, KeyError, TypeError, ValueError):
+        return PEAK
 
 
 def run(name, m, bytes_per_elem, steps, warm=5, note="", options=None):

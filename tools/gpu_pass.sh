@@ -10,7 +10,7 @@ timeout 600 python bench.py --steps 100 --warmup 5 > $O/bench_n320.json 2> $O/be
 timeout 300 python bench.py --n 200 --steps 100 --warmup 5 --no-cpu-baseline > $O/bench_n200.json 2> $O/bench_n200.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 80 --csv --log-file $O/launches_n320.csv \
     python bench.py --steps 4 --warmup 3 --no-cpu-baseline > $O/ncu_launch.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_stencil3_tma -s 6 -c 1 -o $O/stencil_tma_n320 -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_stencil3_v4 -s 6 -c 1 -o $O/stencil_v4_n320 -f \
     python bench.py --steps 4 --warmup 3 --no-cpu-baseline > $O/ncu_full.log 2>&1
 timeout 900 python tools/bench_configs.py > $O/configs.jsonl 2> $O/configs.err
 tail -3 $O/pytest_gpu.log; cat $O/bench_n320.json
