@@ -196,7 +196,7 @@ typedef struct svlgpu_counters {
     double  stencil_ms;          /* ... of which block-stencil kernel (if timed)   */
     int64_t n_pml_elements;      /* PML elements (block solve)       */
     int64_t n_pml_unknowns;      /* dofs of the non-diagonal block of Keff         */
-    int64_t pml_solves, pml_iterations;   /* BiCGStab solves / iterations so far   */
+    int64_t pml_solves, pml_iterations;   /* Krylov solves / iterations so far (PML block BiCGStab + Newmark CG) */
 } svlgpu_counters;
 int svlgpu_get_counters(svlgpu_model *m, svlgpu_counters *out);
 

@@ -416,7 +416,7 @@ int svlgpu_get_counters(svlgpu_model *m, svlgpu_counters *o) {
     o->last_step_ms = m->last_step_ms;
     o->stencil_ms = m->timers[0].launches ? m->timers[0].total_ms / m->timers[0].launches : 0.0;
     o->n_pml_elements = m->pml.n_elem; o->n_pml_unknowns = m->pml.nc;
-    o->pml_solves = m->pml.solves; o->pml_iterations = m->pml.total_iters;
+    o->pml_solves = m->pml.solves + m->nm.solves; o->pml_iterations = m->pml.total_iters + m->nm.total_iters;
     return 0;
 }
 

@@ -95,6 +95,13 @@ def main():
             m = M.make_box_model(ne, 1.0, mat=(M.ELASTIC3DLINEAR, SOIL), nt=4000)
             m.blocks = []
             run(f"{ne[0]}^3 lin3DHexa8 elastic, Gauss-point path (no lattice)", m, 140.0, a.steps)
+        elif w == "newmark":   # the implicit NewmarkBeta + Linear step at 4x the explicit time step
+            n = int(160 * S)
+            m = M.make_box_model((n, n, n), 1.0, mat=(M.ELASTIC3DLINEAR, SOIL), nt=4000)
+            m.dt *= 4.0
+            run(f"NewmarkBeta + Linear, {n}^3 lin3DHexa8 lattice, dt = 2 h/Vp (matrix-free CG, rtol 1e-13)", m, 140.0,
+                max(4, a.steps // 4), note="one step = 1 + CG-iterations applications of the K operator; pml_iterations_per_step counts CG iterations",
+                options={"integrator": 1.0})
         elif w == "c2":     # configs[1]: quad4 half-space + PML2DQuad4 layer, left / right / bottom
             ne = (int(2000 * S), int(1000 * S))
             m = M.make_pml_model(ne, 10, 1.0, soil=(M.ELASTIC2DPLANESTRAIN, SOIL), nt=4000)
