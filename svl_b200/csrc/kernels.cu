@@ -1647,14 +1647,16 @@ static int drm_prefetch(svlgpu_model *m, int knext) {
 // external forces of step k (Assembler::ComputeExternalForceVector).  phase 0: contributions to interface
 // dofs, subtracted from the partial force that is about to be exchanged; phase 1: everything else,
 // applied to U_{n+1} directly (the solve is diagonal there).
-static int launch_external(svlgpu_model *m, int k, const double *dev_amp, double *Un, int phase) {
+// `scaled`: forces are divided by the diagonal Keff on the way into U_{n+1} (CentralDifference); otherwise they are added raw
+static int launch_external(svlgpu_model *m, int k, const double *dev_amp, double *Un, int phase, bool scaled = true) {
+    const double *kinv = scaled ? m->d_kinv : nullptr;
     const bool halo = m->halo.active || m->pml.present;
     if (phase == 0 && !halo) return 0;
     if (m->n_pl_dofs) {
         PLArgs a;
         a.n = m->n_pl_dofs; a.dof = m->d_pl_dof; a.ptr = m->d_pl_ptr; a.load = m->d_pl_load;
         a.coef = m->d_pl_coef; a.series = m->d_pl_series; a.soff = m->d_pl_soff; a.snt = m->d_pl_nt;
-        a.amp = dev_amp; a.kinv = m->d_kinv; a.Un = Un; a.k = k;
+        a.amp = dev_amp; a.kinv = kinv; a.Un = Un; a.k = k;
         a.target = halo ? m->d_pl_target : nullptr; a.hF = m->halo.d_hF; a.bext = m->pml.d_bext; a.phase = phase;
         a.kctl = m->graph_capturing ? m->d_kctl : nullptr;
         timer_begin(m, 3);
@@ -1670,7 +1672,7 @@ static int launch_external(svlgpu_model *m, int k, const double *dev_amp, double
         if (d.buf_k[b] != k) { if (drm_compute(m, d, k, m->stream)) return 1; }        // not precomputed: do it now
         else if (d.ev_valid[b]) cudaStreamWaitEvent(m->stream, d.ev_ready[b], 0);
         k_drm_apply<<<(d.n_nodes * m->ndim + 127) / 128, 128, 0, m->stream>>>(d.n_nodes, m->ndim, phase, d.d_node_dof0,
-                                                                              halo ? d.d_target : nullptr, d.d_F[b], m->d_kinv, Un,
+                                                                              halo ? d.d_target : nullptr, d.d_F[b], kinv, Un,
                                                                               m->halo.d_hF);
         timer_end(m, 5);
         m->total_launches++;
@@ -1807,11 +1809,7 @@ int operator_K(svlgpu_model *m, const double *x, double *out) {
 }
 // b += Fext(k) on every loaded dof (point loads, DRM), no Keff scaling
 int external_forces_raw(svlgpu_model *m, int k, const double *dev_amp, double *b) {
-    double *kinv = m->d_kinv;
-    m->d_kinv = nullptr;
-    const int rc = launch_external(m, k, dev_amp, b, 1);
-    m->d_kinv = kinv;
-    return rc;
+    return launch_external(m, k, dev_amp, b, 1, false);
 }
 
 // Assembler::ComputeInternalForceVector for the current displacement state

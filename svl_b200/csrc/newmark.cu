@@ -27,7 +27,7 @@ namespace svl {
         }                                                                                   \
     } while (0)
 
-constexpr int kNmBlocks = 296;       // 2 per SM; every reduction writes kNmBlocks partials
+constexpr int kNmBlocks = 1184;      // 8 per SM (the vector kernels are streaming / latency-bound); every reduction writes kNmBlocks partials
 constexpr int kNmThreads = 256;
 // partial-sum slots and scalar cells behind them
 enum { N_BB = 0, N_RZ0 = 1, N_RZ1 = 2, N_PAP = 3, N_RR = 4, N_NSLOT = 5 };
@@ -178,9 +178,9 @@ int newmark_plan(svlgpu_model *m) {
         m->allocs.push_back(*v);
         CUDA_OK(cudaMemset(*v, 0, sizeof(double) * (n + 2)));
     }
-    CUDA_OK(cudaMalloc(&N.d_part, sizeof(double) * 4096));
+    CUDA_OK(cudaMalloc(&N.d_part, sizeof(double) * 8192));
     m->allocs.push_back(N.d_part);
-    CUDA_OK(cudaMemset(N.d_part, 0, sizeof(double) * 4096));
+    CUDA_OK(cudaMemset(N.d_part, 0, sizeof(double) * 8192));
     CUDA_OK(cudaMallocHost(&N.h_scal, sizeof(double) * 4));
     N.present = true;
     return 0;
