@@ -140,6 +140,24 @@ int halo_exchange_begin(svlgpu_model *m) {
     return 0;
 }
 
+// Asynchronous variant: the whole interface pass (partial forces of the interface nodes, external forces acting on them,
+// pack, NCCL) is enqueued on the high-priority comm stream, so the bulk kernels on the main stream start at once and the
+// interface pass runs beside them instead of in front of them.  halo_async_begin forks the comm stream off the main
+// stream (U_n and the element-force arena are final there); the caller then enqueues the interface kernels on
+// halo.comm_stream and calls halo_async_exchange.
+int halo_async_begin(svlgpu_model *m) {
+    HaloDev &h = m->halo;
+    CUDA_OK(cudaEventRecord(h.e_ready, m->stream));
+    CUDA_OK(cudaStreamWaitEvent(h.comm_stream, h.e_ready, 0));
+    return 0;
+}
+int halo_async_exchange(svlgpu_model *m) {
+    HaloDev &h = m->halo;
+    if (exchange_on(m, h.comm_stream)) return 1;
+    CUDA_OK(cudaEventRecord(h.e_done, h.comm_stream));
+    return 0;
+}
+
 int halo_exchange_end(svlgpu_model *m, const double *U, const double *Up, double *Un, int mode) {
     HaloDev &h = m->halo;
     CUDA_OK(cudaStreamWaitEvent(m->stream, h.e_done, 0));

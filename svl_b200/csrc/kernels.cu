@@ -1699,10 +1699,22 @@ static int step_once(svlgpu_model *m, int k, const double *dev_amp) {
     }
     if (launch_generic_elements(m, U, 1)) return 1;
     if (halo) {
-        // interface partial forces first, so that their exchange overlaps the bulk of the step
-        if (halo_lattice_force(m, U) || halo_generic_force(m)) return 1;
-        if (launch_external(m, k, dev_amp, Un, 0)) return 1;
-        if (xchg && halo_exchange_begin(m)) return 1;
+        const bool async_if = xchg && m->overlap && !m->kernel_timing && !m->pml.present && !m->graph_capturing &&
+                              !getenv("SVLGPU_HALO_SYNC");
+        if (async_if) {
+            // interface pass on the comm stream: the bulk kernels below do not wait for it
+            if (halo_async_begin(m)) return 1;
+            cudaStream_t main_stream = m->stream;
+            m->stream = m->halo.comm_stream;
+            const int rc = halo_lattice_force(m, U) || halo_generic_force(m) || launch_external(m, k, dev_amp, Un, 0);
+            m->stream = main_stream;
+            if (rc || halo_async_exchange(m)) return 1;
+        } else {
+            // interface partial forces first, so that their exchange overlaps the bulk of the step
+            if (halo_lattice_force(m, U) || halo_generic_force(m)) return 1;
+            if (launch_external(m, k, dev_amp, Un, 0)) return 1;
+            if (xchg && halo_exchange_begin(m)) return 1;
+        }
     }
     if (launch_node_update(m, U, Up, Un, 0)) return 1;
     if (xchg && halo_exchange_end(m, U, Up, Un, 0)) return 1;

@@ -325,6 +325,8 @@ void graph_destroy(svlgpu_model *m);
 int halo_plan(svlgpu_model *m);                        // after the node lists are known (planner)
 int halo_comm_init(svlgpu_model *m, const void *id128, int rank, int nranks);
 int halo_unique_id(void *out128);
+int halo_async_begin(svlgpu_model *m);                 // interface pass on the comm stream, beside the bulk kernels
+int halo_async_exchange(svlgpu_model *m);
 int halo_exchange_begin(svlgpu_model *m);              // main stream: hF complete -> comm stream: pack + NCCL
 int halo_exchange_end(svlgpu_model *m, const double *U, const double *Up, double *Un, int mode);
 int halo_lattice_force(svlgpu_model *m, const double *U);   // partial forces of lattice interface nodes -> hF

@@ -16,3 +16,9 @@ for l in open("$O/newmark.jsonl"):
     d=json.loads(l); print(d["config"][:70], "ms %.4f"%d["ms_per_step"], "el/s %.4g"%d["element_updates_per_s"], "cg it/step", d["pml_iterations_per_step"])
 PY
 tail -2 $O/newmark.err
+# A/B: synchronous interface pass (the round-1 default before the comm-stream variant)
+SVLGPU_HALO_SYNC=1 timeout 600 $TR --master-port 29514 bench.py --gpus 2 --steps 100 --warmup 5 > $O/bench_weak_n2_sync.json 2> $O/bench_weak_n2_sync.err
+python - <<PY
+import json
+d=json.load(open("$O/bench_weak_n2_sync.json")); print("weak N=2 SYNC halo pass %.4g el/s"%d["value"], "ms/step %.4f"%d["ms_per_step"], "e2e %.4g"%d["e2e"]["value"])
+PY
