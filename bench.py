@@ -151,7 +151,7 @@ def run_reference_arm(args, emit):
     if not os.path.exists(exe):
         cb = cpu_baseline_port()
         line = {"metric": "element-updates/sec (FP64 explicit step)", "value": cb["value"], "unit": "element-updates/s",
-                "n_gpus": 0, "steps": K, "warmup": W, "ms_per_step": None, "higher_is_better": True,
+                "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": None, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
                 "config": {"workload": "oracle port (reference executable absent on this box)"},
                 "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "element-updates/s",
@@ -211,7 +211,7 @@ def run_reference_arm(args, emit):
                     f"lin3DHexa8 box (+DRM layer), {S} CentralDifference steps per bench step, timed as the difference "
                     f"between runs with nt={2 + S} and nt=2 (parse/Initialize cancel); Eigen replaced by oracle/shim"}
     line = {"metric": "element-updates/sec (FP64 explicit step)", "value": rate, "unit": "element-updates/s",
-            "n_gpus": 0, "steps": K, "warmup": W, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True,
+            "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
             "config": {"workload": f"3-D elastic half-space, lin3DHexa8 + Elastic3DLinear, lumped CentralDifference, DRM SV "
                                    f"plane-wave layer, 1 point load, 16 recorded nodes (BASELINE configs[3]-like) -- reference "
