@@ -744,12 +744,17 @@ static int elem_K(const svlo_model *m, int e, const elem_rt *rt, double *Ke) {
         svlo_planestrain_C(mp[0], mp[1], Cm); svlo_quad4_stiffness(rt->X, m->elem_attr[10 * e], Cm, Ke); return 0;
     }
     if (kind == SVLO_ZEROLENGTH1D) return 0;      /* Viscous1DLinear::GetTangentStiffness() == 0 */
+    if (elem_is_pml(kind) && rt->Kpml) { memcpy(Ke, rt->Kpml, (size_t)rt->nd * rt->nd * sizeof(double)); return 0; }
     return 1;
 }
 
 /* integrator: 0 CentralDifference (10-Integrators/02-CentralDifference/CentralDifference.cpp),
  *             1 NewmarkBeta, average acceleration (10-Integrators/03-Newmark/NewmarkBeta.cpp:21-36 Initialize,
- *               :64-79 ComputeNewStep, :106-121 ComputeEffectiveForce, :124-133 ComputeEffectiveStiffness)      */
+ *               :64-79 ComputeNewStep, :106-121 ComputeEffectiveForce, :124-133 ComputeEffectiveStiffness),
+ *             2 ExtendedNewmarkBeta (10-Integrators/03-Newmark/ExtendedNewmarkBeta.cpp): NewmarkBeta plus the PML history
+ *               term, Keff += dt/3 G, rhs -= G (Ubar + dt U + dt^2/6 V), Ubar += dt U + dt/3 dU + dt^2/6 V with
+ *               G = Assembler::ComputePMLHistoryMatrix (Assembler.cpp:162-205; PML3DHexa8::ComputePMLMatrix,
+ *               PML2DQuad4 returns an empty matrix)                                                                 */
 static int run_dynamic(const svlo_model *m, int integrator, int nt, int field, int n_rec,
                        const int32_t *rec_dofs, double *out, double *Ufinal, int nthreads) {
     const int nT = m->n_total, nF = m->n_free, nE = m->n_elem;
@@ -805,7 +810,8 @@ static int run_dynamic(const svlo_model *m, int integrator, int nt, int field, i
     /* CentralDifference: Keff = M/dt^2 + C/2dt (:70) and Kminus = M/dt^2 - C/2dt (:217).
      * NewmarkBeta: Keff = K + 4/dt^2 M + 2/dt C (NewmarkBeta.cpp:128-130); Kminus carries M, lC stays C           */
     tlist lKp = {0, 0, NULL}, lKm = {0, 0, NULL};
-    if (integrator == 1) {
+    tlist lG = {0, 0, NULL};
+    if (integrator >= 1) {
         double *Ke = (double *)malloc(72 * 72 * sizeof(double));
         for (int e = 0; e < nE && !rc; e++) {
             if (elem_K(m, e, &rt[e], Ke)) { rc = 4; break; }
@@ -813,6 +819,20 @@ static int run_dynamic(const svlo_model *m, int integrator, int nt, int field, i
             for (int j = 0; j < nd; j++)
                 for (int i = 0; i < nd; i++)
                     if (fabs(Ke[i * nd + j]) > 1e-12 /* ktol, Driver.hpp:1805 default */) tl_push(&lKp, rt[e].dofs[i], rt[e].dofs[j], Ke[i * nd + j]);
+        }
+        if (integrator == 2) {
+            for (int e = 0; e < nE; e++) {
+                if (m->elem_kind[e] != SVLO_PML3DHEXA8) continue;
+                const double *mp = m->mat_par + 8 * m->elem_mat[e];
+                int nd = rt[e].nd;
+                svlo_pml3d_matrices(rt[e].X, mp[0], mp[1], mp[2], m->elem_attr + 10 * e, NULL, NULL, NULL, Ke);
+                for (int j = 0; j < nd; j++)
+                    for (int i = 0; i < nd; i++)
+                        if (fabs(Ke[i * nd + j]) > 1e-12) {
+                            tl_push(&lG, rt[e].dofs[i], rt[e].dofs[j], Ke[i * nd + j]);
+                            tl_push(&lKp, rt[e].dofs[i], rt[e].dofs[j], dt / 3.0 * Ke[i * nd + j]);
+                        }
+            }
         }
         free(Ke);
         for (int k = 0; k < lM.n; k++) {
@@ -830,7 +850,8 @@ static int run_dynamic(const svlo_model *m, int integrator, int nt, int field, i
         tl_push(&lKm, lC.t[k].i, lC.t[k].j, -(1.0 / 2.0 / dt * lC.t[k].v));
     }
     }
-    csr Cs = tl_to_csr(&lC, nT);
+    csr Cs = tl_to_csr(&lC, nT), Gs = tl_to_csr(&lG, nT);
+    double *Ubar = (double *)calloc(nT, sizeof(double)), *Gtmp = (double *)calloc(nT, sizeof(double));
     csr Kp = tl_to_csr(&lKp, nT), Km = tl_to_csr(&lKm, nT);
     csr T = build_T(m);
     /* Keff_free = T' Keff T (:224-231) */
@@ -922,7 +943,7 @@ static int run_dynamic(const svlo_model *m, int integrator, int nt, int field, i
             }
             for (int i = 0; i < nT; i++) Fext[i] += m->drm_factor * Ftmp[i];
         }
-        if (integrator == 1) {
+        if (integrator >= 1) {
             /* Fext + Fbar - Fint + M (4/dt V + A - 4/dt^2 dU) + C (V - 2/dt dU) with dU = 0 (Linear.cpp:25):
              * NewmarkBeta.cpp:116-118                                               */
             for (int i = 0; i < nT; i++) Ftmp[i] = 4.0 / dt * V[i] + A[i];
@@ -931,6 +952,14 @@ static int run_dynamic(const svlo_model *m, int integrator, int nt, int field, i
                 for (int p = Km.ptr[i]; p < Km.ptr[i + 1]; p++) v += Km.val[p] * Ftmp[Km.col[p]];
                 for (int p = Cs.ptr[i]; p < Cs.ptr[i + 1]; p++) w += Cs.val[p] * V[Cs.col[p]];
                 rhs[i] = Fext[i] - Fint[i] + v + w;
+            }
+            if (integrator == 2) {                 /* - G (Ubar + dt U + dt^2/6 V): ExtendedNewmarkBeta.cpp ComputeEffectiveForce */
+                for (int i = 0; i < nT; i++) Gtmp[i] = Ubar[i] + dt * U[i] + dt * dt / 6.0 * V[i];
+                for (int i = 0; i < nT; i++) {
+                    double g = 0;
+                    for (int p = Gs.ptr[i]; p < Gs.ptr[i + 1]; p++) g += Gs.val[p] * Gtmp[Gs.col[p]];
+                    rhs[i] -= g;
+                }
             }
         } else {
         /* --- Feff = T'(Fext - Fint + Kminus (U-Up)) : CentralDifference.cpp:217-220 */
@@ -960,9 +989,10 @@ static int run_dynamic(const svlo_model *m, int integrator, int nt, int field, i
         }
 #pragma omp parallel for schedule(static)
         for (int e = 0; e < nE; e++) material_update(m, e, &rt[e], Utr);
-        if (integrator == 1) {
-            /* NewmarkBeta.cpp:73-76 */
+        if (integrator >= 1) {
+            /* NewmarkBeta.cpp:73-76; ExtendedNewmarkBeta updates the PML history first */
             for (int i = 0; i < nT; i++) {
+                if (integrator == 2) Ubar[i] = Ubar[i] + dt * U[i] + dt / 3.0 * dUt[i] + dt * dt / 6.0 * V[i];
                 U[i] += dUt[i];
                 A[i] = 4.0 / dt / dt * dUt[i] - 4.0 / dt * V[i] - A[i];
                 V[i] = 2.0 / dt * dUt[i] - V[i];
@@ -984,7 +1014,7 @@ done:
     for (int e = 0; e < nE; e++) free(rt[e].Kpml);
     free(rt); free(U); free(V); free(A); free(Up); free(Fint); free(Fext); free(Ftmp); free(rhs);
     free(dUt); free(Utr); free(Feff); free(dU); free(fe_all); free(lM.t); free(lC.t); free(lKp.t);
-    free(lKm.t); free(lF.t); csr_free(&Kp); csr_free(&Km); csr_free(&T); csr_free(&Kf); csr_free(&Cs);
+    free(lKm.t); free(lF.t); csr_free(&Kp); csr_free(&Km); csr_free(&T); csr_free(&Kf); csr_free(&Cs); csr_free(&Gs); free(lG.t); free(Ubar); free(Gtmp);
     free(cidx); free(Kdiag); free(Kc); free(bc);
     return rc;
 }
@@ -996,4 +1026,8 @@ int svlo_run_central_difference(const svlo_model *m, int nt, int field, int n_re
 int svlo_run_newmark(const svlo_model *m, int nt, int field, int n_rec,
                      const int32_t *rec_dofs, double *out, double *Ufinal, int nthreads) {
     return run_dynamic(m, 1, nt, field, n_rec, rec_dofs, out, Ufinal, nthreads);
+}
+int svlo_run_extended_newmark(const svlo_model *m, int nt, int field, int n_rec,
+                              const int32_t *rec_dofs, double *out, double *Ufinal, int nthreads) {
+    return run_dynamic(m, 2, nt, field, n_rec, rec_dofs, out, Ufinal, nthreads);
 }

@@ -131,6 +131,10 @@ int svlo_run_central_difference(const svlo_model *m, int nt, int field, int n_re
 int svlo_run_newmark(const svlo_model *m, int nt, int field, int n_rec,
                      const int32_t *rec_dofs, double *out, double *Ufinal, int nthreads);
 
+/* ExtendedNewmarkBeta (NewmarkBeta + the PML history matrix G): 10-Integrators/03-Newmark/ExtendedNewmarkBeta.cpp.   */
+int svlo_run_extended_newmark(const svlo_model *m, int nt, int field, int n_rec,
+                              const int32_t *rec_dofs, double *out, double *Ufinal, int nthreads);
+
 /* Assembler::ComputeInternalForceVector on a given displacement state (all
  * materials start from the virgin state, one UpdateState with U).            */
 int svlo_internal_force(const svlo_model *m, const double *U, double *F);

@@ -428,13 +428,25 @@ def read_reference_json(path: str, base_dir: Optional[str] = None) -> Model:
     nidx = {int(t): i for i, t in enumerate(ntags)}
     m.coords = np.array([[float(v) for v in J["Nodes"][t]["coords"]][:m.ndim] for t in ntags])
     m.node_ndof = np.array([int(J["Nodes"][t]["ndof"]) for t in ntags], dtype=np.int32)
-    fd = []
+    # the file's own total / free numbering (any scheme of 01-Pre_Process/Core/Numberer.py) is mapped to the Model's
+    # node-major numbering: constraints refer to slave TOTAL and master FREE dofs of the file (Driver.hpp:440-505)
+    fd, tot_map, free_map, nfree = [], {}, {}, 0
+    ntot = 0
     for t in ntags:
-        row = [int(v) for v in J["Nodes"][t]["freedof"]]
-        if any(v < -1 for v in row):
-            raise ValueError("read_reference_json: constrained dofs are not handled by this reader")
-        fd.append(np.array([0 if v > -1 else -1 for v in row], dtype=np.int32))
+        N = J["Nodes"][t]
+        row = []
+        for ft, tt in zip(N["freedof"], N["totaldof"]):
+            tot_map[int(tt)] = ntot; ntot += 1
+            if int(ft) > -1:
+                free_map[int(ft)] = nfree; nfree += 1
+                row.append(0)
+            else:
+                row.append(int(ft))                                  # -1 restrained, < -1 constraint tag
+        fd.append(np.array(row, dtype=np.int32))
     m.freedof = fd
+    for ctag, Cn in J.get("Constraints", {}).items():
+        m.constraints.append((int(ctag), tot_map[int(Cn["stag"])], [free_map[int(v)] for v in Cn["mtag"]],
+                              [float(v) for v in Cn["factor"]]))
     kinds = {v: k for k, v in MAT_NAME.items()}
     mtags = sorted(J["Materials"], key=int)
     midx = {int(t): i for i, t in enumerate(mtags)}

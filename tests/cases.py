@@ -188,6 +188,12 @@ REF_FIXTURES = {
     "F06": dict(json="Debugging_F06.1.0.json", cols=((1, 0), (3, 2)), tol=5e-6),             # quad4 column + dashpots + Rayleigh
     "J02": dict(json="Debugging_J02.1.0.json", cols=((3, 0), (1, 1), (2, 2)), tol=5e-6),     # 1 lin3DHexa8, CONSISTENT mass
 }
+# Fixtures the reference validates by a plot only (no shipped numbers): reference.npz = the unmodified reference executable on
+# exactly these input files.  Both carry EQUAL constraints (soil-PML ties) and the consistent mass matrix.
+EXE_FIXTURES = {
+    "F11": dict(json="Debugging_F11.1.0.json"),      # lin2DQuad4 column + PML2DQuad4, NEWMARK
+    "J12": dict(json="Debugging_J12.1.0.json"),      # lin3DHexa8 rod + PML3DHexa8, EXTENDEDNEWMARK (history matrix G)
+}
 
 
 def fixture_dir(name):
@@ -197,7 +203,8 @@ def fixture_dir(name):
 
 def fixture_model(name):
     import os
-    return M.read_reference_json(os.path.join(fixture_dir(name), "Partition", REF_FIXTURES[name]["json"]))
+    spec = REF_FIXTURES.get(name) or EXE_FIXTURES[name]
+    return M.read_reference_json(os.path.join(fixture_dir(name), "Partition", spec["json"]))
 
 
 def fixture_errors(name, hist, key):

@@ -6,6 +6,9 @@
                               matplotlib, which the pre-processor imports at module scope, is replaced by an empty stub
   *.txt / *.in                the fixture's load time series
   opensees.npz                the fixture's OpenSees golden histories (displacement / velocity / acceleration .out)
+  reference.npz               fixtures without shipped numbers (F11, J12: the reference validates them by a plot): NODE
+                              recorder histories written by the unmodified reference executable oracle/_ref/SeismoVLAB.exe
+                              run on exactly these input files (PARAVIEW recorder removed, 17 digits)
 
 Usage: python tests/golden/make_fixture_inputs.py
 """
@@ -21,7 +24,30 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = "/root/reference"
 FIXTURES = {"F02": "F02-DY_Lin_2DPointLoad_ElasticPStrain_Quad4", "F06": "F06-DY_Lin_2DSoilColumn_ElasticPStrain_Quad4",
-            "J02": "J02-DY_Lin_3DPointLoad_Elastic_Hexa8"}
+            "J02": "J02-DY_Lin_3DPointLoad_Elastic_Hexa8", "F11": "F11-DY_Lin_2DPMLSoilColumn_ElasticPStrain_Quad4",
+            "J12": "J12-DY_Axial_Load_Long_Rod_PML3D"}
+EXE = os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle", "_ref", "SeismoVLAB.exe")
+
+
+def run_reference_on(src, dst):
+    """NODE recorder histories of the unmodified reference executable on the fixture's own input files"""
+    import json
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from svl_b200 import model as M
+    jp = [os.path.join(src, "Partition", f) for f in os.listdir(os.path.join(src, "Partition")) if f.endswith(".json")][0]
+    J = json.load(open(jp))
+    J["Recorders"] = {k: dict(v, ndps=17) for k, v in J["Recorders"].items() if v["name"] == "NODE"}   # SURVEY App. B.2
+    run_json = jp.replace(".1.0.json", "R.1.0.json")
+    json.dump(J, open(run_json, "w"))
+    combo = J["Combinations"][str(J["Simulations"]["combo"])]["attributes"]["folder"]
+    os.makedirs(os.path.join(src, "Solution", combo), exist_ok=True)
+    subprocess.run([EXE, "-dir", os.path.join(src, "Partition"), "-file", os.path.basename(run_json).replace(".0.json", ".$.json")],
+                   cwd=src, check=True, stdout=subprocess.DEVNULL)
+    os.remove(run_json)
+    out = {}
+    for r in J["Recorders"].values():
+        out[r["resp"]] = M.read_node_recorder(os.path.join(src, "Solution", combo, r["file"]))
+    np.savez_compressed(os.path.join(dst, "reference.npz"), **out)
 
 
 def main():
@@ -47,8 +73,11 @@ def main():
             if fn.endswith((".txt", ".in")):
                 shutil.copy(os.path.join(src, fn), os.path.join(dst, fn))
         o = os.path.join(src, "OpenSees")
-        np.savez_compressed(os.path.join(dst, "opensees.npz"), disp=np.loadtxt(os.path.join(o, "displacement.out")),
-                            vel=np.loadtxt(os.path.join(o, "velocity.out")), accel=np.loadtxt(os.path.join(o, "acceleration.out")))
+        if os.path.isdir(o):
+            np.savez_compressed(os.path.join(dst, "opensees.npz"), disp=np.loadtxt(os.path.join(o, "displacement.out")),
+                                vel=np.loadtxt(os.path.join(o, "velocity.out")), accel=np.loadtxt(os.path.join(o, "acceleration.out")))
+        else:
+            run_reference_on(src, dst)
         print(name, "->", dst)
 
 

@@ -59,6 +59,16 @@ def newmark_cases(names):
         print(f"newmark_{name}: {out['disp'].shape} peak |u| = {np.abs(out['disp']).max():.6e}")
 
 
+def extended_newmark_cases():
+    for name in ("pml2d", "pml3d"):
+        m = cases.CASES[name]()
+        m.dt *= 2.0
+        out = run_reference(m, ("disp",), integrator="EXTENDEDNEWMARK")
+        np.savez_compressed(os.path.join(HERE, f"extnewmark_{name}.npz"), fingerprint=cases.fingerprint(m),
+                            rec_nodes=m.rec_nodes, dt=m.dt, nt=m.nt, **out)
+        print(f"extnewmark_{name}: {out['disp'].shape} peak |u| = {np.abs(out['disp']).max():.6e}")
+
+
 def element_kat():
     rp = RefProbe()
     rng = np.random.default_rng(20260117)
@@ -125,9 +135,11 @@ if __name__ == "__main__":
     args = sys.argv[1:]
     if args and args[0] == "newmark":
         newmark_cases(args[1:] or list(cases.NEWMARK_CASES))
+        extended_newmark_cases()
         raise SystemExit(0)
     names = args or list(cases.CASES)
     if not args:
         element_kat()
         newmark_cases(list(cases.NEWMARK_CASES))
+        extended_newmark_cases()
     history_cases(names)

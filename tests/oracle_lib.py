@@ -61,6 +61,8 @@ class Oracle:
                                                   _dp, C.c_int]
         L.svlo_run_newmark.restype = C.c_int
         L.svlo_run_newmark.argtypes = L.svlo_run_central_difference.argtypes
+        L.svlo_run_extended_newmark.restype = C.c_int
+        L.svlo_run_extended_newmark.argtypes = L.svlo_run_central_difference.argtypes
         L.svlo_internal_force.argtypes = [C.POINTER(SvloModel), _dp, _dp]
         L.svlo_mass_diagonal.argtypes = [C.POINTER(SvloModel), _dp]
         L.svlo_elastic3d_C.argtypes = [C.c_double, C.c_double, _dp]
@@ -237,7 +239,8 @@ class Oracle:
         rd = np.ascontiguousarray(m.rec_dofs() if rec_dofs is None else rec_dofs, np.int32)
         out = np.zeros((nt - 1, len(rd)))
         Uf = np.zeros(m.n_total)
-        fn = self.lib.svlo_run_newmark if integrator.upper() == "NEWMARK" else self.lib.svlo_run_central_difference
+        fn = {"NEWMARK": self.lib.svlo_run_newmark, "EXTENDEDNEWMARK": self.lib.svlo_run_extended_newmark}.get(
+            integrator.upper(), self.lib.svlo_run_central_difference)
         rc = fn(C.byref(s), nt, field, len(rd), _i(rd), _d(out), _d(Uf), nthreads)
         if rc:
             raise RuntimeError(f"oracle stop code {rc}")
