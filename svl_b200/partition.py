@@ -15,7 +15,7 @@ from typing import Dict, List
 
 import numpy as np
 
-from .model import DRMLoad, Model, PointLoad, make_box_model, add_drm_box
+from .model import ELEM_NODES, DRMLoad, Model, PointLoad, make_box_model, add_drm_box
 
 
 def proc_grid(nparts: int):
@@ -58,12 +58,34 @@ def split_model(m: Model, epart: np.ndarray, nparts: int) -> List[Model]:
     `.halos = {peer: local node indices}`, `.global_nodes`, `.global_elems`."""
     if m.constraints:
         raise ValueError("constraints (PML interfaces) are not partitioned yet: keep PML models on one GPU")
-    npe_of = lambda k: 8 if k in (1, 3) else 4
-    npe = npe_of(int(m.elem_kind[0]))
+    npe_e = np.array([ELEM_NODES[int(k)] for k in m.elem_kind], dtype=np.int32)
+
+    def nodes_of(el):
+        """unique nodes of the listed elements (each element uses its own node count)"""
+        if len(el) == 0:
+            return np.zeros(0, dtype=np.int64)
+        return np.unique(np.concatenate([m.elem_conn[e, :npe_e[e]] for e in el]))
+
+    epart = np.asarray(epart, dtype=np.int32)
+    if len(epart) < m.n_elem:
+        # elements beyond the partitioned solids (ZeroLength1D dashpots appended after the lattice): each goes to the
+        # lowest rank that holds one of its nodes, so its damping is counted exactly once (svlgpu_comm_init sums the
+        # lumped mass / damping diagonals of the interface dofs over the ranks)
+        first_rank = np.full(m.n_nodes, nparts, dtype=np.int32)
+        for e in range(len(epart)):
+            nn = m.elem_conn[e, :npe_e[e]]
+            first_rank[nn] = np.minimum(first_rank[nn], epart[e])
+        extra = []
+        for e in range(len(epart), m.n_elem):
+            r = int(first_rank[m.elem_conn[e, :npe_e[e]]].min())
+            if r >= nparts:
+                raise ValueError("element outside the partitioned mesh touches no partitioned node")
+            extra.append(r)
+        epart = np.concatenate([epart, np.array(extra, dtype=np.int32)])
     node_sets = []
     for r in range(nparts):
         el = np.nonzero(epart == r)[0]
-        node_sets.append(np.unique(m.elem_conn[el, :npe]))
+        node_sets.append(nodes_of(el))
     # owner of a node = lowest rank that holds it
     owner = np.full(m.n_nodes, nparts, dtype=np.int32)
     for r in reversed(range(nparts)):
@@ -81,7 +103,8 @@ def split_model(m: Model, epart: np.ndarray, nparts: int) -> List[Model]:
         s.freedof = [np.where(fd[m.node_ptr[n]:m.node_ptr[n + 1]] > -1, 0, -1).astype(np.int32) for n in gn]
         s.materials = list(m.materials)
         conn = np.zeros((len(el), 8), dtype=np.int32)
-        conn[:, :npe] = loc[m.elem_conn[el, :npe]]
+        for i, e in enumerate(el):
+            conn[i, :npe_e[e]] = loc[m.elem_conn[e, :npe_e[e]]]
         s.elem_conn = conn
         s.elem_kind = m.elem_kind[el]
         s.elem_mat = m.elem_mat[el]
@@ -101,7 +124,7 @@ def split_model(m: Model, epart: np.ndarray, nparts: int) -> List[Model]:
             mine = eloc[d.elems] >= 0
             if mine.any():
                 de = eloc[d.elems[mine]].astype(np.int32)
-                dn_glob = np.unique(m.elem_conn[d.elems[mine], :npe])
+                dn_glob = nodes_of(d.elems[mine])
                 pos = np.searchsorted(d.nodes, dn_glob)
                 assert (d.nodes[pos] == dn_glob).all()
                 s.drm = DRMLoad(elems=de, nodes=loc[dn_glob].astype(np.int32), exterior=d.exterior[pos].copy(),
@@ -134,8 +157,13 @@ def _sub_lattice_hint(m: Model, gn: np.ndarray):
         return []
     n0, NX, NY, NZ = m.blocks[0]
     q = gn - n0
-    if q.min() < 0 or q.max() >= NX * NY * NZ:
+    inl = (q >= 0) & (q < NX * NY * NZ)
+    nl = int(inl.sum())
+    # nodes outside the lattice (e.g. the fixed twins of Lysmer dashpots) must follow the lattice nodes in the local numbering
+    if nl == 0 or n0 != 0 or not inl[:nl].all():
         return []
+    q = q[:nl]
+    gn = gn[:nl]
     i, j, k = q % NX, (q // NX) % NY, q // (NX * NY)
     ni, nj, nk = i.max() - i.min() + 1, j.max() - j.min() + 1, k.max() - k.min() + 1
     if ni * nj * nk != len(gn):

@@ -22,7 +22,8 @@ import cases  # noqa: E402
 from svl_b200 import capi, partition as P  # noqa: E402
 
 NE = {"kat444": (4, 4, 4), "drm_box": (6, 6, 5), "quad4_area": (8, 6), "j2_column": (2, 2, 6),
-      "hex8_layered_rayleigh": (4, 3, 6), "hex8_distorted": (3, 4, 5), "drm_area": (8, 6)}
+      "hex8_layered_rayleigh": (4, 3, 6), "hex8_distorted": (3, 4, 5), "drm_area": (8, 6),
+      "lysmer_column": (3, 3, 6)}            # ZeroLength1D dashpots follow the rank of their soil node
 
 
 def main():

@@ -107,6 +107,29 @@ def test_split_hands_loads_and_recorders_to_one_partition():
     assert (a == b).all() and (np.diff(a) > 0).all()
 
 
+def test_split_with_dashpots_counts_every_dashpot_once():
+    """ZeroLength1D dashpots (appended after the lattice elements) follow the lowest rank that holds their soil node; the
+    fixed twin nodes travel with them; the summed damping diagonal over the partitions equals the global one."""
+    m = cases.lysmer_column()
+    n_solid = int((m.elem_kind == 1).sum())
+    subs = P.split_model(m, P.block_epart((3, 3, 6), (2, 1, 2)), 4)
+    from svl_b200.model import ZEROLENGTH1D
+    assert sum(int((s.elem_kind == ZEROLENGTH1D).sum()) for s in subs) == m.n_elem - n_solid
+    assert sum(int((s.elem_kind == 1).sum()) for s in subs) == n_solid
+    eta_global = np.zeros(m.n_total)
+    for e in np.nonzero(m.elem_kind == ZEROLENGTH1D)[0]:
+        node = m.elem_conn[e, 1]                                   # soil node (the twin comes first)
+        eta_global[m.node_ptr[node] + int(m.elem_attr[e, 0])] += m.materials[m.elem_mat[e]][1][0]
+    eta_sum = np.zeros(m.n_total)
+    for s in subs:
+        for e in np.nonzero(s.elem_kind == ZEROLENGTH1D)[0]:
+            tw, node = s.elem_conn[e, 0], s.elem_conn[e, 1]
+            assert (np.asarray(s.freedof[tw]) == -1).all()         # the twin stays fully restrained
+            g = s.global_nodes[node]
+            eta_sum[m.node_ptr[g] + int(s.elem_attr[e, 0])] += s.materials[s.elem_mat[e]][1][0]
+    assert np.array_equal(eta_sum, eta_global) and eta_global.sum() > 0
+
+
 def test_local_box_matches_split_of_global_box():
     from svl_b200 import model as M
     grid = (2, 2, 2)
