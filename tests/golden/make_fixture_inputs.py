@@ -50,8 +50,25 @@ def run_reference_on(src, dst):
     np.savez_compressed(os.path.join(dst, "reference.npz"), **out)
 
 
+def j2_plane_strain_paths(tmp):
+    """Gauss-point strain / stress histories (points 1 and 3 of element 1) of the two PlasticPlaneStrainJ2 fixtures: the
+    OpenSees element recorders the fixtures ship.  Material-level golden: the integrator (Newmark + Newton) does not matter."""
+    out = {}
+    for name, fx in (("F03", "F03-DY_Lin_2DPointLoad_J2PStrain_Quad4"), ("F07", "F07-DY_Lin_2DSoilColumn_J2PStrain_Quad4")):
+        zipfile.ZipFile(os.path.join(REF, "03-Validations", "01-Debugging", fx + ".zip")).extractall(tmp)
+        e = np.loadtxt(os.path.join(tmp, fx, "OpenSees", "strain.out"))
+        s = np.loadtxt(os.path.join(tmp, fx, "OpenSees", "stress.out"))
+        for g in (0, 2):
+            out[f"{name}_strain_gp{g}"] = e[:, 1 + 3 * g:4 + 3 * g]      # e11, e22, gamma12 (engineering)
+            out[f"{name}_stress_gp{g}"] = s[:, 1 + 3 * g:4 + 3 * g]
+    os.makedirs(os.path.join(HERE, "fixtures", "J2PS"), exist_ok=True)
+    np.savez_compressed(os.path.join(HERE, "fixtures", "J2PS", "opensees_stress_strain.npz"), **out)
+    print("J2PS ->", os.path.join(HERE, "fixtures", "J2PS"))
+
+
 def main():
     tmp = tempfile.mkdtemp(prefix="svlfix_")
+    j2_plane_strain_paths(tmp)
     stub = os.path.join(tmp, "stub", "matplotlib")
     os.makedirs(stub)
     open(os.path.join(stub, "__init__.py"), "w").close()

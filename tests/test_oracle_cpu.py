@@ -108,6 +108,32 @@ def test_oracle_extended_newmark_matches_reference_executable(oracle, name):
     assert cases.rel_err(out, g["disp"]) < 1e-10
 
 
+@pytest.mark.parametrize("name,par", [("F03", [1.333333e8, 8.0e7, 0.0, 8.0e7, 1.0, 4.0e7]),
+                                      ("F07", [2.9e7, 2.0e7, 2000.0, 1.0e7, 1.0, 1.0e4])])
+def test_j2_plane_strain_return_map_matches_reference_fixture_stress_paths(oracle, name, par):
+    """PlasticPlaneStrainJ2 (the embedding of PlasticPlaneStrainJ2.cpp:235 around the 3-D return map) driven by the
+    Gauss-point strain histories of the reference's fixtures F03 / F07 reproduces their OpenSees stress histories
+    (6 printed digits, accumulated along a plastic path).  F03 is loaded well into yield (|s| reaches Sy)."""
+    import ctypes as C
+    g = np.load(os.path.join(GOLD, "fixtures", "J2PS", "opensees_stress_strain.npz"))
+    dp = C.POINTER(C.c_double)
+    p = np.array(par, float)
+    for gp in (0, 2):
+        strain, ref = g[f"{name}_strain_gp{gp}"], g[f"{name}_stress_gp{gp}"]
+        st = np.zeros(13)
+        sig = np.zeros_like(ref)
+        yielded = 0
+        for k, e in enumerate(strain):
+            e6 = np.array([0.0, e[0], e[1], 0.0, e[2], 0.0]); s6 = np.zeros(6); before = st[12]
+            oracle.lib.svlo_j2_update(p.ctypes.data_as(dp), e6.ctypes.data_as(dp), st.ctypes.data_as(dp), s6.ctypes.data_as(dp))
+            yielded += st[12] != before
+            sig[k] = (s6[1], s6[2], s6[4])
+        err = np.abs(sig - ref).max(axis=0) / np.abs(ref).max(axis=0)
+        assert err.max() < 3e-5, (gp, err)
+        if name == "F03":
+            assert yielded > 5
+
+
 def test_oracle_vel_accel_match_reference_executable(oracle):
     m = cases.kat444()
     g = gold("kat444")
