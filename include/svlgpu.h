@@ -91,7 +91,8 @@ int svlgpu_add_elements(svlgpu_model *m, int kind, int n, const int32_t *conn,
                         const int32_t *material, const double *attrs, int nattr);
 
 /* Damping: Damping.cpp, lin3DHexa8.cpp:354-366.  Only FREE and the mass-
- * proportional part of RAYLEIGH keep Keff diagonal; ak != 0 is refused.        */
+ * proportional part of RAYLEIGH keep the CentralDifference Keff diagonal: there
+ * ak != 0 is refused at finalize; the Newmark integrator takes a uniform ak.     */
 int svlgpu_set_rayleigh(svlgpu_model *m, int n, const int32_t *elems, double am, double ak);
 
 /* Optional hint: nodes [node0, node0+nx*ny*nz) form a lattice numbered
@@ -104,7 +105,11 @@ int svlgpu_hint_structured_block(svlgpu_model *m, int node0, int nx, int ny, int
  * "cuda_graph" (1: replay steps from a CUDA graph of 6 consecutive steps; default 0),
  * "pml_rtol" (relative residual of the PML block solve, default 1e-14), "keep_gauss" (1: keep Gauss-point
  * strain / stress for svlgpu_get_gauss, default 0), "ftol" (Assembler.cpp:262 filter of the PML element
- * forces, default 1e-12).                                                        */
+ * forces, default 1e-12), "integrator" (0: CentralDifference, 10-Integrators/02-CentralDifference, the
+ * default; 1: NewmarkBeta + Linear, 10-Integrators/03-Newmark/NewmarkBeta.cpp:64-133 with Linear.cpp:22-56:
+ * linear materials, lumped mass, Rayleigh damping with both coefficients, dashpots, one GPU; the sparse
+ * factorisation of Keff = K + 4/dt^2 M + 2/dt C is replaced by matrix-free conjugate gradients),
+ * "newmark_rtol" (relative residual of that solve, default 1e-13).                */
 int svlgpu_set_option(svlgpu_model *m, const char *name, double value);
 
 /* ---- loads (replaces Assembler::ComputeExternalForceVector:290-489) ------ */
