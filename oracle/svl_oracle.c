@@ -77,6 +77,47 @@ void svlo_j2_update(const double par[6], const double e_in[6], double st[13], do
     }
 }
 
+/* Same update plus the consistent tangent (Plastic3DJ2.cpp:221-224 elastic, :254-256 plastic; identical expressions in
+ * PlasticPlaneStrainJ2.cpp:245,262): D = 1 (x) 1 on the normal components, I = diag(1,1,1,1/2,1/2,1/2), Id = I - D/3,
+ *   elastic: K D + 2G Id;   plastic: K D + 2G (Id - n n^T / (1 + H/(3G))) - 4 G^2 dgamma / |xi| (Id - n n^T)              */
+void svlo_j2_update_tangent(const double par[6], const double e_in[6], double st[13], double sig[6], double Ct[36]) {
+    const double K = par[0], G = par[1], H = par[3], beta = par[4], Sy = par[5];
+    double e[6] = {e_in[0], e_in[1], e_in[2], 0.5 * e_in[3], 0.5 * e_in[4], 0.5 * e_in[5]};
+    double tr = e[0] + e[1] + e[2];
+    double one[6] = {1, 1, 1, 0, 0, 0};
+    double s_tr[6], xi[6], D[36], Id[36];
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) {
+            D[6 * i + j] = one[i] * one[j];
+            Id[6 * i + j] = (i == j ? (i < 3 ? 1.0 : 0.5) : 0.0) - 1.0 / 3.0 * D[6 * i + j];
+        }
+    for (int i = 0; i < 6; i++) {
+        double dev = e[i] - 1.0 / 3.0 * tr * one[i];
+        s_tr[i] = 2.0 * G * (dev - st[i]);
+        xi[i] = s_tr[i] - st[6 + i];
+    }
+    double nrm = sqrt(xi[0] * xi[0] + xi[1] * xi[1] + xi[2] * xi[2] +
+                      2.0 * (xi[3] * xi[3] + xi[4] * xi[4] + xi[5] * xi[5]));
+    double f = nrm - sqrt(2.0 / 3.0) * (Sy + st[12] * beta * H);
+    if (f <= 0) {
+        for (int i = 0; i < 6; i++) sig[i] = K * tr * one[i] + s_tr[i];
+        for (int i = 0; i < 36; i++) Ct[i] = K * D[i] + 2.0 * G * Id[i];
+    } else {
+        double dg = f / (2.0 * G + 2.0 / 3.0 * H), n[6];
+        st[12] += sqrt(2.0 / 3.0) * dg;
+        for (int i = 0; i < 6; i++) {
+            n[i] = xi[i] / nrm;
+            st[6 + i] += 2.0 / 3.0 * (1.0 - beta) * H * dg * n[i];
+            st[i] += dg * n[i];
+            sig[i] = K * tr * one[i] + s_tr[i] - 2.0 * G * dg * n[i];
+        }
+        for (int i = 0; i < 6; i++)
+            for (int j = 0; j < 6; j++)
+                Ct[6 * i + j] = K * D[6 * i + j] + 2.0 * G * (Id[6 * i + j] - 1.0 / (1.0 + H / G / 3.0) * n[i] * n[j]) -
+                                4.0 * G * G * dg / nrm * (Id[6 * i + j] - n[i] * n[j]);
+    }
+}
+
 /* ------------------------------------------------------------------------ */
 /* hex8 kinematics: lin3DHexa8.cpp:755-785 (J), :810-853 (B)                 */
 /* ------------------------------------------------------------------------ */
@@ -177,9 +218,13 @@ static void hex8_B(const double d[8][3], double B[6][24]) {
     }
 }
 /* lin3DHexa8.cpp:288-318 */
-void svlo_hex8_stiffness(const double *X, const double C[36], double K[576]) {
+static void hex8_stiffness_gp(const double *X, const double *Cgp, int stride, double K[576]);
+void svlo_hex8_stiffness(const double *X, const double C[36], double K[576]) { hex8_stiffness_gp(X, C, 0, K); }
+/* K = sum_gp w |J| B^T C_gp B with one tangent per Gauss point (stride 36) or one for all (stride 0): lin3DHexa8.cpp:288-318 */
+static void hex8_stiffness_gp(const double *X, const double *Cgp, int stride, double K[576]) {
     memset(K, 0, 576 * sizeof(double));
     for (int g = 0; g < 8; g++) {
+        const double *C = Cgp + (size_t)stride * g;
         double r, s, t, d[8][3], B[6][24], CB[6][24];
         hex8_gp(g, &r, &s, &t);
         double wd = 1.0 * hex8_grad(X, r, s, t, d, NULL);
@@ -267,9 +312,12 @@ void svlo_quad4_mass(const double *X, double th, double rho, int lumped, double 
                 if (i != j) { M[i * 8 + i] += M[i * 8 + j]; M[i * 8 + j] = 0.0; }
 }
 /* lin2DQuad4.cpp:289-319 */
-void svlo_quad4_stiffness(const double *X, double th, const double C[9], double K[64]) {
+static void quad4_stiffness_gp(const double *X, double th, const double *Cgp, int stride, double K[64]);
+void svlo_quad4_stiffness(const double *X, double th, const double C[9], double K[64]) { quad4_stiffness_gp(X, th, C, 0, K); }
+static void quad4_stiffness_gp(const double *X, double th, const double *Cgp, int stride, double K[64]) {
     memset(K, 0, 64 * sizeof(double));
     for (int g = 0; g < 4; g++) {
+        const double *C = Cgp + (size_t)stride * g;
         double r, s, d[4][2], B[3][8] = {{0}}, CB[3][8];
         quad4_gp(g, &r, &s);
         double wd = 1.0 * th * quad4_grad(X, r, s, d, NULL);
@@ -529,11 +577,13 @@ typedef struct {
     double *Kpml;          /* PML: nd*nd stiffness                                 */
     double sig[8][6];      /* stored Gauss-point stress (solid)                    */
     double st[8][13];      /* J2 state                                             */
+    double Ct[8][36];      /* Gauss-point tangents of the plastic materials (6x6 or 3x3 in the first 9), Newton only */
+    int has_Ct;
 } elem_rt;
 
 static void elem_setup(const svlo_model *m, int e, elem_rt *rt) {
     int kind = m->elem_kind[e], nn = elem_nn(kind);
-    rt->nd = 0; rt->Kpml = NULL;
+    rt->nd = 0; rt->Kpml = NULL; rt->has_Ct = 0;
     memset(rt->sig, 0, sizeof rt->sig); memset(rt->st, 0, sizeof rt->st);
     for (int i = 0; i < nn; i++) {
         int nd = m->elem_conn[8 * e + i];
@@ -613,6 +663,44 @@ static void ldlt_solve(const double *A, int n, double *b) {
     for (int i = n - 1; i >= 0; i--) { double v = b[i]; for (int k = i + 1; k < n; k++) v -= A[k * n + i] * b[k]; b[i] = v; }
 }
 
+/* The same factorisation and substitutions restricted to the skyline of A (lo[i] = first non-zero column of row i, hi[i] =
+ * last row that reaches column i): without pivoting the factor keeps the profile, and the skipped terms are exact zeros, so
+ * the results equal ldlt_factor / ldlt_solve bit for bit.  Used by the Newton iteration, which refactors every pass. */
+static void skyline_profile(const double *A, int n, int *lo, int *hi) {
+    for (int i = 0; i < n; i++) {
+        int k = 0;
+        while (k < i && A[i * n + k] == 0.0 && A[k * n + i] == 0.0) k++;
+        lo[i] = k;
+        hi[i] = i;
+    }
+    for (int i = 0; i < n; i++)
+        for (int k = lo[i]; k < i; k++) if (hi[k] < i) hi[k] = i;
+}
+static int ldlt_factor_sky(double *A, int n, const int *lo) {
+    for (int j = 0; j < n; j++) {
+        double d = A[j * n + j];
+        for (int k = lo[j]; k < j; k++) d -= A[j * n + k] * A[j * n + k] * A[k * n + k];
+        if (d == 0.0 || d != d) return 1;
+        A[j * n + j] = d;
+        for (int i = j + 1; i < n; i++) {
+            if (lo[i] > j) continue;
+            double v = A[i * n + j];
+            for (int k = (lo[i] > lo[j] ? lo[i] : lo[j]); k < j; k++) v -= A[i * n + k] * A[j * n + k] * A[k * n + k];
+            A[i * n + j] = v / d;
+        }
+    }
+    return 0;
+}
+static void ldlt_solve_sky(const double *A, int n, const int *lo, const int *hi, double *b) {
+    for (int i = 0; i < n; i++) { double v = b[i]; for (int k = lo[i]; k < i; k++) v -= A[i * n + k] * b[k]; b[i] = v; }
+    for (int i = 0; i < n; i++) b[i] /= A[i * n + i];
+    for (int i = n - 1; i >= 0; i--) {
+        double v = b[i];
+        for (int k = i + 1; k <= hi[i]; k++) if (lo[k] <= i) v -= A[k * n + i] * b[k];
+        b[i] = v;
+    }
+}
+
 /* Mesh::GetTotalToFreeMatrix (06-Mesh/Mesh.cpp:328-381) as a CSR over total dofs */
 static csr build_T(const svlo_model *m) {
     tlist l = {0, 0, NULL};
@@ -649,13 +737,22 @@ static void material_update(const svlo_model *m, int e, elem_rt *rt, const doubl
                     rt->sig[g][a] = v;
                 }
         } else {
-            for (int g = 0; g < 8; g++) svlo_j2_update(mp, eps[g], rt->st[g], rt->sig[g]);
+            for (int g = 0; g < 8; g++) svlo_j2_update_tangent(mp, eps[g], rt->st[g], rt->sig[g], rt->Ct[g]);
+            rt->has_Ct = 1;
         }
     } else if (kind == SVLO_LIN2DQUAD4) {
         double eps[4][3], C[9];
         svlo_quad4_strain(rt->X, ue, eps);
         if (mk == SVLO_PLASTICPLANESTRAINJ2) {
-            for (int g = 0; g < 4; g++) j2ps_update(mp, eps[g], rt->st[g], rt->sig[g]);
+            for (int g = 0; g < 4; g++) {
+                /* PlasticPlaneStrainJ2.cpp:235 embedding; tangent = rows / columns 1, 2, 4 (:151-159) */
+                double e6[6] = {0.0, eps[g][0], eps[g][1], 0.0, eps[g][2], 0.0}, s6[6], C6[36];
+                svlo_j2_update_tangent(mp, e6, rt->st[g], s6, C6);
+                rt->sig[g][0] = s6[1]; rt->sig[g][1] = s6[2]; rt->sig[g][2] = s6[4];
+                const int ix[3] = {1, 2, 4};
+                for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) rt->Ct[g][3 * a + b] = C6[6 * ix[a] + ix[b]];
+            }
+            rt->has_Ct = 1;
             return;
         }
         svlo_planestrain_C(mp[0], mp[1], C);
@@ -743,6 +840,17 @@ static int elem_K(const svlo_model *m, int e, const elem_rt *rt, double *Ke) {
     if (kind == SVLO_LIN2DQUAD4 && mk == SVLO_ELASTIC2DPLANESTRAIN) {
         svlo_planestrain_C(mp[0], mp[1], Cm); svlo_quad4_stiffness(rt->X, m->elem_attr[10 * e], Cm, Ke); return 0;
     }
+    if (kind == SVLO_LIN3DHEXA8 && mk == SVLO_PLASTIC3DJ2) {
+        if (rt->has_Ct) { hex8_stiffness_gp(rt->X, &rt->Ct[0][0], 36, Ke); return 0; }
+        memset(Cm, 0, sizeof Cm);                 /* virgin material: K D + 2G (I - D/3), Plastic3DJ2.cpp:28-31 */
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Cm[6 * i + j] = mp[0] + 2.0 * mp[1] * ((i == j ? 1.0 : 0.0) - 1.0 / 3.0);
+        Cm[21] = Cm[28] = Cm[35] = 2.0 * mp[1] * 0.5;
+        svlo_hex8_stiffness(rt->X, Cm, Ke); return 0;
+    }
+    if (kind == SVLO_LIN2DQUAD4 && mk == SVLO_PLASTICPLANESTRAINJ2) {
+        if (rt->has_Ct) { quad4_stiffness_gp(rt->X, m->elem_attr[10 * e], &rt->Ct[0][0], 36, Ke); return 0; }
+        j2ps_C0(mp, Cm); svlo_quad4_stiffness(rt->X, m->elem_attr[10 * e], Cm, Ke); return 0;
+    }
     if (kind == SVLO_ZEROLENGTH1D) return 0;      /* Viscous1DLinear::GetTangentStiffness() == 0 */
     if (elem_is_pml(kind) && rt->Kpml) { memcpy(Ke, rt->Kpml, (size_t)rt->nd * rt->nd * sizeof(double)); return 0; }
     return 1;
@@ -755,8 +863,20 @@ static int elem_K(const svlo_model *m, int e, const elem_rt *rt, double *Ke) {
  *               term, Keff += dt/3 G, rhs -= G (Ubar + dt U + dt^2/6 V), Ubar += dt U + dt/3 dU + dt^2/6 V with
  *               G = Assembler::ComputePMLHistoryMatrix (Assembler.cpp:162-205; PML3DHexa8::ComputePMLMatrix,
  *               PML2DQuad4 returns an empty matrix)                                                                 */
+/* algorithm: NULL = Linear (09-Algorithms/01-Linear/Linear.cpp:22-56); otherwise NewtonRaphson (09-Algorithms/02-Newton/
+ * NewtonRaphson.cpp:22-56) with tolerance, iteration cap and convergence test `flag` of Algorithm::ComputeConvergence
+ * (Algorithm.cpp:122-186): 1 |Feff|, 2 |du|, 3 |du.*Feff|, 4 |Feff| / |Feff_0|, 5 |du| / |dU_0|, 6 |du.*Feff| / |du.*Feff|_0,
+ * 7 |du| / |dU|, 8 none (one iteration).  NewmarkBeta only.
+ * Like the reference, every Newton iteration calls Material::UpdateState on the LIVE state.          */
+typedef struct { double tol; int nmax, flag; } svlo_newton;
+static int run_dynamic_alg(const svlo_model *m, int integrator, const svlo_newton *alg, int nt, int field, int n_rec,
+                           const int32_t *rec_dofs, double *out, double *Ufinal, int nthreads);
 static int run_dynamic(const svlo_model *m, int integrator, int nt, int field, int n_rec,
                        const int32_t *rec_dofs, double *out, double *Ufinal, int nthreads) {
+    return run_dynamic_alg(m, integrator, NULL, nt, field, n_rec, rec_dofs, out, Ufinal, nthreads);
+}
+static int run_dynamic_alg(const svlo_model *m, int integrator, const svlo_newton *alg, int nt, int field, int n_rec,
+                           const int32_t *rec_dofs, double *out, double *Ufinal, int nthreads) {
     const int nT = m->n_total, nF = m->n_free, nE = m->n_elem;
     const double dt = m->dt;
     int rc = 0;
@@ -973,6 +1093,109 @@ static int run_dynamic(const svlo_model *m, int integrator, int nt, int field, i
         memset(Feff, 0, nF * sizeof(double));
         for (int i = 0; i < nT; i++)
             for (int a = T.ptr[i]; a < T.ptr[i + 1]; a++) Feff[T.col[a]] += T.val[a] * rhs[i];
+        if (alg && integrator == 1) {
+            /* ---- NewtonRaphson::ComputeNewIncrement: iterate on the increment dU of this step ------------------------- */
+            double *Kn = (double *)malloc((size_t)nF * nF * sizeof(double)), *du = (double *)malloc((nF + 1) * sizeof(double));
+            double *Ke = (double *)malloc(72 * 72 * sizeof(double));
+            int *sky_lo = (int *)malloc((nF + 1) * sizeof(int)), *sky_hi = (int *)malloc((nF + 1) * sizeof(int));
+            double normfactor = 0.0, residual = 0.0;
+            int it = 0;
+            memset(dU, 0, (nF + 1) * sizeof(double));
+            memset(dUt, 0, nT * sizeof(double));
+            do {
+                if (it > 0) {
+                    /* effective force with the accumulated increment (NewmarkBeta.cpp:116-118) and the stresses of the
+                     * last UpdateState                                              */
+#pragma omp parallel for schedule(static)
+                    for (int e = 0; e < nE; e++) elem_fint(m, e, &rt[e], U, fe_all + (size_t)72 * e);
+                    memset(Fint, 0, nT * sizeof(double));
+                    for (int e = 0; e < nE; e++) {
+                        const double *fe = fe_all + (size_t)72 * e;
+                        for (int i = 0; i < rt[e].nd; i++)
+                            if (fabs(fe[i]) > m->ftol) Fint[rt[e].dofs[i]] += fe[i];
+                    }
+                    for (int i = 0; i < nT; i++) { Ftmp[i] = 4.0 / dt * V[i] + A[i] - 4.0 / dt / dt * dUt[i]; Utr[i] = V[i] - 2.0 / dt * dUt[i]; }
+                    for (int i = 0; i < nT; i++) {
+                        double v = 0, w = 0;
+                        for (int p = Km.ptr[i]; p < Km.ptr[i + 1]; p++) v += Km.val[p] * Ftmp[Km.col[p]];
+                        for (int p = Cs.ptr[i]; p < Cs.ptr[i + 1]; p++) w += Cs.val[p] * Utr[Cs.col[p]];
+                        rhs[i] = Fext[i] - Fint[i] + v + w;
+                    }
+                    memset(Feff, 0, nF * sizeof(double));
+                    for (int i = 0; i < nT; i++)
+                        for (int a = T.ptr[i]; a < T.ptr[i + 1]; a++) Feff[T.col[a]] += T.val[a] * rhs[i];
+                }
+                /* Keff = T' (K_t + 4/dt^2 M + 2/dt C) T from the CURRENT tangents (NewmarkBeta.cpp:124-133) */
+                memset(Kn, 0, (size_t)nF * nF * sizeof(double));
+                for (int p = 0; p < lM.n; p++) {          /* element + nodal masses, already filtered */
+                    int i = lM.t[p].i, j = lM.t[p].j;
+                    for (int a = T.ptr[i]; a < T.ptr[i + 1]; a++)
+                        for (int b = T.ptr[j]; b < T.ptr[j + 1]; b++)
+                            Kn[(size_t)T.col[a] * nF + T.col[b]] += T.val[a] * T.val[b] * 4.0 / dt / dt * lM.t[p].v;
+                }
+                for (int p = 0; p < lC.n; p++) {
+                    int i = lC.t[p].i, j = lC.t[p].j;
+                    for (int a = T.ptr[i]; a < T.ptr[i + 1]; a++)
+                        for (int b = T.ptr[j]; b < T.ptr[j + 1]; b++)
+                            Kn[(size_t)T.col[a] * nF + T.col[b]] += T.val[a] * T.val[b] * 2.0 / dt * lC.t[p].v;
+                }
+                for (int e = 0; e < nE; e++) {
+                    if (elem_K(m, e, &rt[e], Ke)) { rc = 4; break; }
+                    int nd = rt[e].nd;
+                    for (int j = 0; j < nd; j++)
+                        for (int i = 0; i < nd; i++) {
+                            if (!(fabs(Ke[i * nd + j]) > 1e-12)) continue;
+                            int gi = rt[e].dofs[i], gj = rt[e].dofs[j];
+                            for (int a = T.ptr[gi]; a < T.ptr[gi + 1]; a++)
+                                for (int b = T.ptr[gj]; b < T.ptr[gj + 1]; b++)
+                                    Kn[(size_t)T.col[a] * nF + T.col[b]] += T.val[a] * T.val[b] * Ke[i * nd + j];
+                        }
+                }
+                if (rc) break;
+                skyline_profile(Kn, nF, sky_lo, sky_hi);
+                if (ldlt_factor_sky(Kn, nF, sky_lo)) { rc = 2; break; }
+                memcpy(du, Feff, nF * sizeof(double));
+                ldlt_solve_sky(Kn, nF, sky_lo, sky_hi, du);
+                double n_du = 0, n_dU = 0, n_F = 0, n_E = 0;
+                for (int i = 0; i < nF; i++) {
+                    dU[i] += du[i]; n_du += du[i] * du[i]; n_dU += dU[i] * dU[i]; n_F += Feff[i] * Feff[i];
+                    n_E += (du[i] * Feff[i]) * (du[i] * Feff[i]);      /* norm of the componentwise product, :137-141 */
+                }
+                n_du = sqrt(n_du); n_dU = sqrt(n_dU); n_F = sqrt(n_F); n_E = sqrt(n_E);
+                switch (alg->flag) {                       /* Algorithm.cpp:122-186 */
+                case 1: residual = n_F; break;
+                case 2: residual = n_du; break;
+                case 3: residual = n_E; break;
+                case 4: if (it) residual = n_F / normfactor; else { normfactor = n_F; residual = n_F; } break;
+                case 5: if (it) residual = n_du / normfactor; else { normfactor = n_dU; residual = n_du; } break;
+                case 6: if (it) residual = n_E / normfactor; else { normfactor = n_E; residual = n_E; } break;
+                case 7: residual = n_du / n_dU; break;
+                case 8: residual = -1.0; break;            /* "maximum number of iterations": one pass, :179-182 */
+                default: residual = 0.0; break;            /* undefined test: Residual stays 0.0, :127,183-185 */
+                }
+                /* UpdateStatesIncrements (Algorithm.cpp:18-56) */
+                for (int i = 0; i < nT; i++) {
+                    double v = 0;
+                    for (int a = T.ptr[i]; a < T.ptr[i + 1]; a++) v += T.val[a] * dU[T.col[a]];
+                    dUt[i] = v;
+                    Utr[i] = U[i] + v;
+                }
+#pragma omp parallel for schedule(static)
+                for (int e = 0; e < nE; e++) material_update(m, e, &rt[e], Utr);
+                it++;
+            } while (residual > alg->tol && it < alg->nmax);
+            free(Kn); free(du); free(Ke); free(sky_lo); free(sky_hi);
+            if (rc) goto done;
+            for (int i = 0; i < nT; i++) {                 /* NewmarkBeta.cpp:73-76 */
+                U[i] += dUt[i];
+                A[i] = 4.0 / dt / dt * dUt[i] - 4.0 / dt * V[i] - A[i];
+                V[i] = 2.0 / dt * dUt[i] - V[i];
+            }
+            for (int i = 0; i < nT; i++) if (U[i] != U[i]) rc = 3;
+            const double *srcn = field == 0 ? U : field == 1 ? V : A;
+            for (int q = 0; q < n_rec; q++) out[(size_t)(k - 1) * n_rec + q] = srcn[rec_dofs[q]];
+            continue;
+        }
         /* --- solve (EigenSolver.cpp:19-60) */
         for (int i = 0; i < nF; i++)
             if (cidx[i] < 0) dU[i] = Feff[i] / Kdiag[i]; else bc[cidx[i]] = Feff[i];
@@ -1030,4 +1253,10 @@ int svlo_run_newmark(const svlo_model *m, int nt, int field, int n_rec,
 int svlo_run_extended_newmark(const svlo_model *m, int nt, int field, int n_rec,
                               const int32_t *rec_dofs, double *out, double *Ufinal, int nthreads) {
     return run_dynamic(m, 2, nt, field, n_rec, rec_dofs, out, Ufinal, nthreads);
+}
+/* NewmarkBeta + NewtonRaphson (plastic materials): tol / nmax / flag = the JSON's cnvgtol / nstep / cnvgtest (Driver.hpp:1792-1795) */
+int svlo_run_newmark_newton(const svlo_model *m, double tol, int nmax, int flag, int nt, int field, int n_rec,
+                            const int32_t *rec_dofs, double *out, double *Ufinal, int nthreads) {
+    svlo_newton alg = {tol, nmax, flag};
+    return run_dynamic_alg(m, 1, &alg, nt, field, n_rec, rec_dofs, out, Ufinal, nthreads);
 }

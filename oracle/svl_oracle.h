@@ -135,6 +135,12 @@ int svlo_run_newmark(const svlo_model *m, int nt, int field, int n_rec,
 int svlo_run_extended_newmark(const svlo_model *m, int nt, int field, int n_rec,
                               const int32_t *rec_dofs, double *out, double *Ufinal, int nthreads);
 
+/* NewmarkBeta + NewtonRaphson with the materials' consistent tangents (09-Algorithms/02-Newton/NewtonRaphson.cpp);
+ * tol / nmax / flag as in the JSON's algorithm block (cnvgtol / nstep / cnvgtest).                                    */
+int svlo_run_newmark_newton(const svlo_model *m, double tol, int nmax, int flag, int nt, int field, int n_rec,
+                            const int32_t *rec_dofs, double *out, double *Ufinal, int nthreads);
+void svlo_j2_update_tangent(const double par[6], const double eps_eng[6], double state[13], double sig[6], double Ct[36]);
+
 /* Assembler::ComputeInternalForceVector on a given displacement state (all
  * materials start from the virgin state, one UpdateState with U).            */
 int svlo_internal_force(const svlo_model *m, const double *U, double *F);

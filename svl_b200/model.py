@@ -308,7 +308,7 @@ def add_base_dashpots(m: Model, vs: float, vp: float, rho: float, h: float, th: 
 # reference JSON writer (Core/SeismoVLAB.py:49-298, Outputs.py:29-51)
 # -------------------------------------------------------------------------------
 def write_reference_json(m: Model, directory: str, name: str = "Model", combo: str = "Run",
-                         resp=("disp",), integrator: str = "CENTRALDIFFERENCE", ndps: int = 16) -> str:
+                         resp=("disp",), integrator: str = "CENTRALDIFFERENCE", ndps: int = 16, newton=None) -> str:
     """Writes <directory>/Partition/<name>.1.0.json (+ load / .drm text files) in the schema the
     reference executable reads.  Tags are index+1.  Returns the partition directory."""
     part = os.path.join(directory, "Partition")
@@ -405,9 +405,10 @@ def write_reference_json(m: Model, directory: str, name: str = "Model", combo: s
                                       "list": [int(v) + 1 for v in m.rec_nodes], "nsamp": 1}
     J["Simulations"] = {"combo": 1, "attributes": {
         "analysis": {"name": "DYNAMIC", "nt": int(m.nt)},
-        "algorithm": {"name": "LINEAR", "nstep": 1},
+        "algorithm": ({"name": "LINEAR", "nstep": 1} if newton is None else
+                      {"name": "NEWTON", "cnvgtol": float(newton[0]), "nstep": int(newton[1]), "cnvgtest": int(newton[2])}),
         "integrator": {"name": integrator, "dt": float(m.dt), "ktol": 1e-12, "mtol": 1e-12, "ftol": 1e-12},
-        "solver": {"name": "EIGEN", "update": 1}}}
+        "solver": {"name": "EIGEN", "update": 1 if newton is None else 0}}}
     with open(os.path.join(part, f"{name}.1.0.json"), "w") as f:
         json.dump(J, f, indent=4)
     return part
@@ -505,6 +506,9 @@ def read_reference_json(path: str, base_dir: Optional[str] = None) -> Model:
     A = sim["attributes"]
     m.dt, m.nt = float(A["integrator"]["dt"]), int(A["analysis"]["nt"])
     m.integrator = A["integrator"]["name"].upper()
+    alg = A.get("algorithm", {})
+    m.newton = ((float(alg.get("cnvgtol", 1e-6)), int(alg.get("nstep", 1)), int(alg.get("cnvgtest", 4)))
+                if str(alg.get("name", "LINEAR")).upper() == "NEWTON" else None)
     m.rec_spec = []
     for r in sorted(J.get("Recorders", {}), key=int):
         R = J["Recorders"][r]

@@ -144,6 +144,18 @@ def newmark_case(name):
     return m
 
 
+# NewmarkBeta + NewtonRaphson on the plastic cases (fixtures F03 / F07): (cnvgtol, nstep, cnvgtest) per run, one
+# setting for each convergence test of Algorithm.cpp:122-186; goldens `newton_<case>.npz` from the unmodified reference executable.
+# The settings stop the iteration before a Gauss point's trial state lands ON the yield surface to the last bit: beyond that the
+# reference's `TrialF <= 0` branch (and with it the tangent of the next step's first iteration) is decided by rounding, so
+# two correct implementations of the same algorithm separate at ~cnvgtol.
+NEWTON_CASES = {
+    "j2_column": ((1e-6, 50, 5), (1e1, 30, 1), (1e-7, 30, 3), (1e-4, 30, 4)),
+    "j2ps_area": ((1e-8, 20, 2), (1e-10, 30, 6), (1e-5, 30, 7), (1.0, 30, 8)),
+}
+TOL_NEWTON = 1e-12
+
+
 def fixture_j05():
     """The reference's own validation fixture 03-Validations/01-Debugging/J05-DY_Lin_3DSoilColumn_Elastic_Hexa8 rebuilt with
     the repo's model layer: 1 x 1 x 100 lin3DHexa8 column (Elastic3DLinear 1.3e7 / 0.3 / 2000), z restrained everywhere,
@@ -188,6 +200,13 @@ REF_FIXTURES = {
     "F06": dict(json="Debugging_F06.1.0.json", cols=((1, 0), (3, 2)), tol=5e-6),             # quad4 column + dashpots + Rayleigh
     "J02": dict(json="Debugging_J02.1.0.json", cols=((3, 0), (1, 1), (2, 2)), tol=5e-6),     # 1 lin3DHexa8, CONSISTENT mass
 }
+# NewmarkBeta + NewtonRaphson + PlasticPlaneStrainJ2 fixtures: reference.npz (the unmodified reference executable on these files)
+# pins the algorithm; opensees.npz is the fixture's shipped golden (a different Newton scheme: the reference itself is only this
+# close to it).  tol_exe: max |d| / max |ref|;  tol_os: relative RMS per column as cmpResults.py pairs them (disp, vel, accel).
+NEWTON_FIXTURES = {
+    "F03": dict(json="Debugging_F03.1.0.json", cols=((1, 0),), tol_exe=1e-11, tol_os=(2e-3, 2e-2, 3e-2)),   # 1 quad, rho = 0
+    "F07": dict(json="Debugging_F07.1.0.json", cols=((1, 0), (3, 2)), tol_exe=5e-5, tol_os=(1e-4, 2e-4, 5e-4)),
+}
 # Fixtures the reference validates by a plot only (no shipped numbers): reference.npz = the unmodified reference executable on
 # exactly these input files.  Both carry EQUAL constraints (soil-PML ties) and the consistent mass matrix.
 EXE_FIXTURES = {
@@ -203,7 +222,7 @@ def fixture_dir(name):
 
 def fixture_model(name):
     import os
-    spec = REF_FIXTURES.get(name) or EXE_FIXTURES[name]
+    spec = REF_FIXTURES.get(name) or EXE_FIXTURES.get(name) or NEWTON_FIXTURES[name]
     return M.read_reference_json(os.path.join(fixture_dir(name), "Partition", spec["json"]))
 
 
@@ -212,7 +231,7 @@ def fixture_errors(name, hist, key):
     import os
     g = np.load(os.path.join(fixture_dir(name), "opensees.npz"))[key]
     errs = []
-    for col, ours in REF_FIXTURES[name]["cols"]:
+    for col, ours in (REF_FIXTURES.get(name) or NEWTON_FIXTURES[name])["cols"]:
         ref = g[:, col]
         errs.append(np.sqrt(np.mean((hist[:, ours] - ref) ** 2)) / np.sqrt(np.mean(ref ** 2)))
     return max(errs)

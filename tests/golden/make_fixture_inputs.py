@@ -6,11 +6,12 @@
                               matplotlib, which the pre-processor imports at module scope, is replaced by an empty stub
   *.txt / *.in                the fixture's load time series
   opensees.npz                the fixture's OpenSees golden histories (displacement / velocity / acceleration .out)
-  reference.npz               fixtures without shipped numbers (F11, J12: the reference validates them by a plot): NODE
+  reference.npz               fixtures without shipped numbers (F11, J12: the reference validates them by a plot) and the
+                              Newton-Raphson fixtures (F03, F07): NODE
                               recorder histories written by the unmodified reference executable oracle/_ref/SeismoVLAB.exe
                               run on exactly these input files (PARAVIEW recorder removed, 17 digits)
 
-Usage: python tests/golden/make_fixture_inputs.py
+Usage: python tests/golden/make_fixture_inputs.py [fixture names, default all]
 """
 import os
 import shutil
@@ -25,7 +26,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF = "/root/reference"
 FIXTURES = {"F02": "F02-DY_Lin_2DPointLoad_ElasticPStrain_Quad4", "F06": "F06-DY_Lin_2DSoilColumn_ElasticPStrain_Quad4",
             "J02": "J02-DY_Lin_3DPointLoad_Elastic_Hexa8", "F11": "F11-DY_Lin_2DPMLSoilColumn_ElasticPStrain_Quad4",
-            "J12": "J12-DY_Axial_Load_Long_Rod_PML3D"}
+            "J12": "J12-DY_Axial_Load_Long_Rod_PML3D",
+            "F03": "F03-DY_Lin_2DPointLoad_J2PStrain_Quad4", "F07": "F07-DY_Lin_2DSoilColumn_J2PStrain_Quad4"}
+# NewmarkBeta + NewtonRaphson on PlasticPlaneStrainJ2: OpenSees histories AND the reference executable's (the reference's
+# Newton iteration updates the LIVE material state, so it is not OpenSees' algorithm: SURVEY.md App. C q9)
+NEWTON_FIXTURES = ("F03", "F07")
 EXE = os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle", "_ref", "SeismoVLAB.exe")
 
 
@@ -76,7 +81,10 @@ def main():
         with open(os.path.join(stub, mod + ".py"), "w") as f:
             f.write("def __getattr__(n):\n    raise AttributeError(n)\n")
     env = dict(os.environ, PYTHONPATH=os.path.join(REF, "01-Pre_Process") + os.pathsep + os.path.join(tmp, "stub"))
+    only = set(sys.argv[1:])
     for name, fx in FIXTURES.items():
+        if only and name not in only:
+            continue
         zipfile.ZipFile(os.path.join(REF, "03-Validations", "01-Debugging", fx + ".zip")).extractall(tmp)
         src = os.path.join(tmp, fx)
         subprocess.run([sys.executable, fx + ".py"], cwd=src, env=env, check=True, stdout=subprocess.DEVNULL)
@@ -93,7 +101,7 @@ def main():
         if os.path.isdir(o):
             np.savez_compressed(os.path.join(dst, "opensees.npz"), disp=np.loadtxt(os.path.join(o, "displacement.out")),
                                 vel=np.loadtxt(os.path.join(o, "velocity.out")), accel=np.loadtxt(os.path.join(o, "acceleration.out")))
-        else:
+        if not os.path.isdir(o) or name in NEWTON_FIXTURES:
             run_reference_on(src, dst)
         print(name, "->", dst)
 

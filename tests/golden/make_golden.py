@@ -31,9 +31,9 @@ from oracle_lib import RefProbe  # noqa: E402
 EXE = os.path.join(ROOT, "oracle", "_ref", "SeismoVLAB.exe")
 
 
-def run_reference(m, resp=("disp",), integrator="CENTRALDIFFERENCE"):
+def run_reference(m, resp=("disp",), integrator="CENTRALDIFFERENCE", newton=None):
     tmp = tempfile.mkdtemp(prefix="svlgold_")
-    part = M.write_reference_json(m, tmp, "Case", "Run", resp=resp, ndps=17, integrator=integrator)
+    part = M.write_reference_json(m, tmp, "Case", "Run", resp=resp, ndps=17, integrator=integrator, newton=newton)
     subprocess.run([EXE, "-dir", part, "-file", "Case.1.$.json"], stdout=subprocess.DEVNULL, check=True)
     return {r: M.read_node_recorder(os.path.join(tmp, "Solution", "Run", f"{r}.0.out")) for r in resp}
 
@@ -57,6 +57,15 @@ def newmark_cases(names):
         np.savez_compressed(os.path.join(HERE, f"newmark_{name}.npz"), fingerprint=cases.fingerprint(m),
                             rec_nodes=m.rec_nodes, dt=m.dt, nt=m.nt, **out)
         print(f"newmark_{name}: {out['disp'].shape} peak |u| = {np.abs(out['disp']).max():.6e}")
+
+
+def newton_cases():
+    for name, settings in cases.NEWTON_CASES.items():
+        m = cases.CASES[name]()
+        out = {f"disp_{i}": run_reference(m, ("disp",), integrator="NEWMARK", newton=nw)["disp"] for i, nw in enumerate(settings)}
+        np.savez_compressed(os.path.join(HERE, f"newton_{name}.npz"), fingerprint=cases.fingerprint(m), rec_nodes=m.rec_nodes,
+                            dt=m.dt, nt=m.nt, settings=np.array(settings, float), **out)
+        print(f"newton_{name}: {len(settings)} x {out['disp_0'].shape} peak |u| = {np.abs(out['disp_0']).max():.6e}")
 
 
 def extended_newmark_cases():
@@ -136,10 +145,12 @@ if __name__ == "__main__":
     if args and args[0] == "newmark":
         newmark_cases(args[1:] or list(cases.NEWMARK_CASES))
         extended_newmark_cases()
+        newton_cases()
         raise SystemExit(0)
     names = args or list(cases.CASES)
     if not args:
         element_kat()
         newmark_cases(list(cases.NEWMARK_CASES))
         extended_newmark_cases()
+        newton_cases()
     history_cases(names)

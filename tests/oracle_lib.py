@@ -61,6 +61,9 @@ class Oracle:
                                                   _dp, C.c_int]
         L.svlo_run_newmark.restype = C.c_int
         L.svlo_run_newmark.argtypes = L.svlo_run_central_difference.argtypes
+        L.svlo_run_newmark_newton.restype = C.c_int
+        L.svlo_run_newmark_newton.argtypes = [C.POINTER(SvloModel), C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip,
+                                              _dp, _dp, C.c_int]
         L.svlo_run_extended_newmark.restype = C.c_int
         L.svlo_run_extended_newmark.argtypes = L.svlo_run_central_difference.argtypes
         L.svlo_internal_force.argtypes = [C.POINTER(SvloModel), _dp, _dp]
@@ -233,15 +236,21 @@ class Oracle:
             s.U0 = _d(A(U0, np.float64))
         return s, keep
 
-    def run(self, m, nt=None, field=0, rec_dofs=None, nthreads=1, U0=None, integrator="CENTRALDIFFERENCE"):
+    def run(self, m, nt=None, field=0, rec_dofs=None, nthreads=1, U0=None, integrator="CENTRALDIFFERENCE", newton=None):
+        """newton = (cnvgtol, nstep, cnvgtest) selects NewtonRaphson (NewmarkBeta only); default Linear."""
         s, keep = self.pack(m, U0)
         nt = nt or m.nt
         rd = np.ascontiguousarray(m.rec_dofs() if rec_dofs is None else rec_dofs, np.int32)
         out = np.zeros((nt - 1, len(rd)))
         Uf = np.zeros(m.n_total)
-        fn = {"NEWMARK": self.lib.svlo_run_newmark, "EXTENDEDNEWMARK": self.lib.svlo_run_extended_newmark}.get(
-            integrator.upper(), self.lib.svlo_run_central_difference)
-        rc = fn(C.byref(s), nt, field, len(rd), _i(rd), _d(out), _d(Uf), nthreads)
+        if newton is not None:
+            assert integrator.upper() == "NEWMARK"
+            rc = self.lib.svlo_run_newmark_newton(C.byref(s), float(newton[0]), int(newton[1]), int(newton[2]), nt, field,
+                                                  len(rd), _i(rd), _d(out), _d(Uf), nthreads)
+        else:
+            fn = {"NEWMARK": self.lib.svlo_run_newmark, "EXTENDEDNEWMARK": self.lib.svlo_run_extended_newmark}.get(
+                integrator.upper(), self.lib.svlo_run_central_difference)
+            rc = fn(C.byref(s), nt, field, len(rd), _i(rd), _d(out), _d(Uf), nthreads)
         if rc:
             raise RuntimeError(f"oracle stop code {rc}")
         return out, Uf

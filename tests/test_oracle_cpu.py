@@ -108,6 +108,44 @@ def test_oracle_extended_newmark_matches_reference_executable(oracle, name):
     assert cases.rel_err(out, g["disp"]) < 1e-10
 
 
+@pytest.mark.parametrize("name", list(cases.NEWTON_CASES))
+def test_oracle_newton_raphson_matches_reference_executable(oracle, name):
+    """NewmarkBeta + NewtonRaphson with the consistent tangents of Plastic3DJ2 / PlasticPlaneStrainJ2, one setting per
+    convergence test of Algorithm.cpp:122-186 (unbalanced force, increment, energy, their relative forms, total relative
+    increment, fixed iteration count), against the unmodified reference executable."""
+    m = cases.CASES[name]()
+    g = gold(f"newton_{name}")
+    assert str(g["fingerprint"]) == cases.fingerprint(m)
+    tests_seen = set()
+    for i, nw in enumerate(cases.NEWTON_CASES[name]):
+        assert tuple(g["settings"][i]) == tuple(map(float, nw))
+        out, _ = oracle.run(m, integrator="NEWMARK", newton=nw)
+        assert cases.rel_err(out, g[f"disp_{i}"]) < cases.TOL_NEWTON, nw
+        tests_seen.add(nw[2])
+    lin, _ = oracle.run(m, integrator="NEWMARK")                   # the iteration matters: Linear gives another history
+    assert cases.rel_err(lin, g["disp_0"]) > 1e-6
+    assert len(tests_seen) == 4
+
+
+@pytest.mark.parametrize("name", list(cases.NEWTON_FIXTURES))
+def test_oracle_newton_raphson_matches_reference_fixtures_f03_f07(oracle, name):
+    """The reference's own Newton fixtures, read from the JSON its pre-processor wrote: F03 (one PlasticPlaneStrainJ2 quad loaded
+    far into yield, no mass) and F07 (100-quad J2 soil column on Lysmer dashpots, stiffness-proportional Rayleigh damping from
+    the INITIAL tangent, lin2DQuad4.cpp:363).  Against the reference executable run on the same files the bound is set by
+    quirk q10 (F07: a Gauss point whose trial state sits on the yield surface to the last bit picks its tangent branch by
+    rounding); against the fixtures' OpenSees histories the bounds are what the reference itself achieves."""
+    spec = cases.NEWTON_FIXTURES[name]
+    m = cases.fixture_model(name)
+    assert m.integrator == "NEWMARK" and m.newton is not None and m.newton[2] == 5
+    ref = np.load(os.path.join(cases.fixture_dir(name), "reference.npz"))
+    for f, key, amp in ((0, "disp", 1.0), (1, "vel", 10.0), (2, "accel", 100.0)):
+        out, _ = oracle.run(m, field=f, integrator=m.integrator, newton=m.newton)
+        assert out.shape == ref[key].shape
+        assert cases.rel_err(out, ref[key]) < spec["tol_exe"] * amp, key
+        assert cases.fixture_errors(name, out, key) < spec["tol_os"][f], key
+        assert abs(cases.fixture_errors(name, out, key) - cases.fixture_errors(name, ref[key], key)) < spec["tol_exe"] * amp
+
+
 @pytest.mark.parametrize("name,par", [("F03", [1.333333e8, 8.0e7, 0.0, 8.0e7, 1.0, 4.0e7]),
                                       ("F07", [2.9e7, 2.0e7, 2000.0, 1.0e7, 1.0, 1.0e4])])
 def test_j2_plane_strain_return_map_matches_reference_fixture_stress_paths(oracle, name, par):
