@@ -48,6 +48,21 @@ def block_epart(ne, pgrid) -> np.ndarray:
     return part
 
 
+def centroid_epart(m: Model, pgrid) -> np.ndarray:
+    """Element -> partition by the position of the element centroid in the model's bounding box (a geometric block split
+    for models that are not one lattice, e.g. a soil box wrapped in its PML layer); pgrid has one entry per axis."""
+    npe_e = np.array([ELEM_NODES[int(k)] for k in m.elem_kind])
+    cen = np.stack([m.coords[m.elem_conn[e, :npe_e[e]]].mean(axis=0) for e in range(m.n_elem)])
+    lo, hi = m.coords.min(axis=0), m.coords.max(axis=0)
+    part = np.zeros(m.n_elem, dtype=np.int32)
+    mult = 1
+    for a in range(m.ndim):
+        pa = np.minimum(((cen[:, a] - lo[a]) / (hi[a] - lo[a]) * pgrid[a]).astype(np.int64), pgrid[a] - 1)
+        part += (pa * mult).astype(np.int32)
+        mult *= pgrid[a]
+    return part
+
+
 def read_epart(path: str) -> np.ndarray:
     """METIS `<graph>.epart.<nparts>` file: one partition id per element line (Partition.py:150-201)."""
     return np.loadtxt(path, dtype=np.int32)
@@ -56,8 +71,6 @@ def read_epart(path: str) -> np.ndarray:
 def split_model(m: Model, epart: np.ndarray, nparts: int) -> List[Model]:
     """Global model + element partition -> one sub-model per rank, each carrying
     `.halos = {peer: local node indices}`, `.global_nodes`, `.global_elems`."""
-    if m.constraints:
-        raise ValueError("constraints (PML interfaces) are not partitioned yet: keep PML models on one GPU")
     npe_e = np.array([ELEM_NODES[int(k)] for k in m.elem_kind], dtype=np.int32)
 
     def nodes_of(el):
@@ -86,6 +99,31 @@ def split_model(m: Model, epart: np.ndarray, nparts: int) -> List[Model]:
     for r in range(nparts):
         el = np.nonzero(epart == r)[0]
         node_sets.append(nodes_of(el))
+    # EQUAL constraints (the soil-PML ties of Builder.py:653-666): a partition that holds the slave or a master of a tie
+    # gets all of its nodes, so every replica of a tied dof resolves to the same unknown and the interface lists stay
+    # mirror images (the reference writes the constraint into every partition that holds its slave: SeismoVLAB.py:360-372)
+    fd_all = np.asarray(m.freedof_flat)
+    node_of_total = np.repeat(np.arange(m.n_nodes), np.diff(m.node_ptr))
+    total_of_free = -np.ones(max(1, m.n_free), dtype=np.int64)
+    total_of_free[fd_all[fd_all > -1]] = np.nonzero(fd_all > -1)[0]
+    ties = []                                              # (tag, slave total dof, [master total dofs], factors)
+    for tag, slave, masters, factors in m.constraints:
+        ties.append((int(tag), int(slave), [int(total_of_free[f]) for f in masters], list(factors)))
+    if ties:
+        tie_nodes = [np.unique([node_of_total[sl]] + [node_of_total[t] for t in mt]) for _, sl, mt, _ in ties]
+        for r in range(nparts):
+            have = np.zeros(m.n_nodes, dtype=bool)
+            have[node_sets[r]] = True
+            changed = True
+            while changed:
+                changed = False
+                for tn in tie_nodes:
+                    h = have[tn]
+                    if h.any() and not h.all():
+                        have[tn] = True
+                        changed = True
+            node_sets[r] = np.nonzero(have)[0]
+    pml_anywhere = bool(np.isin(m.elem_kind, (3, 4)).any())
     # owner of a node = lowest rank that holds it
     owner = np.full(m.n_nodes, nparts, dtype=np.int32)
     for r in reversed(range(nparts)):
@@ -100,7 +138,9 @@ def split_model(m: Model, epart: np.ndarray, nparts: int) -> List[Model]:
         s = Model(ndim=m.ndim, lumped=m.lumped)
         s.coords = m.coords[gn]
         s.node_ndof = m.node_ndof[gn]
-        s.freedof = [np.where(fd[m.node_ptr[n]:m.node_ptr[n + 1]] > -1, 0, -1).astype(np.int32) for n in gn]
+        # free dofs get a placeholder (renumbered below), restrained (-1) and constrained (tag < -1) codes are kept
+        s.freedof = [np.where(fd[m.node_ptr[n]:m.node_ptr[n + 1]] > -1, 0, fd[m.node_ptr[n]:m.node_ptr[n + 1]]).astype(np.int32)
+                     for n in gn]
         s.materials = list(m.materials)
         conn = np.zeros((len(el), 8), dtype=np.int32)
         for i, e in enumerate(el):
@@ -138,6 +178,19 @@ def split_model(m: Model, epart: np.ndarray, nparts: int) -> List[Model]:
         s.blocks = _sub_lattice_hint(m, gn)
         s.number_dofs()
         s.global_nodes, s.global_elems = gn, el
+
+        def local_total(t):
+            n = node_of_total[t]
+            return int(s.node_ptr[loc[n]] + (t - m.node_ptr[n]))
+
+        s.constraints = []
+        for tag, sl, mt, fac in ties:
+            if loc[node_of_total[sl]] < 0:
+                continue
+            s.constraints.append((tag, local_total(sl), [int(s.freedof_flat[local_total(t)]) for t in mt], list(fac)))
+        # every rank of a model with PML elements takes part in the block solve's reductions, also a rank without PML
+        # unknowns (svlgpu option "pml_collective")
+        s.pml_collective = pml_anywhere
         s.halos = {}
         subs.append(s)
     for r in range(nparts):

@@ -29,23 +29,31 @@ def _worker(rank, world, port, case, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         m = cases.CASES[case]()
-        ne = {"kat444": (4, 4, 4), "drm_box": (6, 6, 5), "quad4_area": (8, 6), "j2_column": (2, 2, 6)}[case]
-        grid = P.proc_grid(world)[3 - len(ne):] if len(ne) == 3 else (1, world)
-        subs = P.split_model(m, P.block_epart(ne, grid), world)
+        if case.startswith("pml"):
+            # soil box + PML layer with EQUAL ties: geometric split by element centroid, cut through soil and PML alike
+            subs = P.split_model(m, P.centroid_epart(m, (world, 1) if m.ndim == 2 else (1, 1, world)), world)
+        else:
+            ne = {"kat444": (4, 4, 4), "drm_box": (6, 6, 5), "quad4_area": (8, 6), "j2_column": (2, 2, 6)}[case]
+            grid = P.proc_grid(world)[3 - len(ne):] if len(ne) == 3 else (1, world)
+            subs = P.split_model(m, P.block_epart(ne, grid), world)
         s = subs[rank]
         o = Oracle()
         rng = np.random.default_rng(42)
         Ug = rng.uniform(-1e-3, 1e-3, m.n_total)
-        # local restriction of the global state (node-major dofs on both sides)
-        nd = m.ndim
-        gd = (s.global_nodes[:, None] * nd + np.arange(nd)[None, :]).ravel()
+
+        def dofs_of(model, nodes):
+            """node-major total dofs of the listed nodes (PML nodes carry 9 / 5 dofs, soil nodes ndim)"""
+            return np.concatenate([np.arange(model.node_ptr[n], model.node_ptr[n + 1]) for n in nodes])
+
+        # local restriction of the global state
+        gd = dofs_of(m, s.global_nodes)
         out = {}
         for name, vec in (("F", o.internal_force(s, Ug[gd])), ("M", o.mass_diagonal(s))):
             vec = vec.copy()
             part = vec.copy()
             reqs, recv = [], {}
             for peer, nodes in sorted(s.halos.items()):
-                dofs = (nodes[:, None] * nd + np.arange(nd)[None, :]).ravel()
+                dofs = dofs_of(s, nodes)
                 recv[peer] = (dofs, torch.zeros(len(dofs), dtype=torch.float64))
                 reqs.append(dist.isend(torch.from_numpy(part[dofs].copy()), peer))
                 reqs.append(dist.irecv(recv[peer][1], peer))
@@ -68,7 +76,7 @@ def _worker(rank, world, port, case, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", ["kat444", "drm_box", "quad4_area"])
+@pytest.mark.parametrize("case", ["kat444", "drm_box", "quad4_area", "pml2d", "pml3d"])
 def test_two_rank_interface_sum_matches_single_domain(oracle, case):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
@@ -86,7 +94,7 @@ def test_two_rank_interface_sum_matches_single_domain(oracle, case):
     Ug = rng.uniform(-1e-3, 1e-3, m.n_total)
     Fg, Mg = oracle.internal_force(m, Ug), oracle.mass_diagonal(m)
     for rank, out, halo_sizes, blocks in res:
-        assert halo_sizes and halo_sizes[0] > 0 and len(blocks) == 1
+        assert halo_sizes and halo_sizes[0] > 0 and (len(blocks) == 1 or case.startswith("pml"))
         gd, F = out["F"]
         assert np.abs(F - Fg[gd]).max() <= 1e-12 * np.abs(Fg).max()
         gd, Mv = out["M"]
@@ -144,3 +152,39 @@ def test_local_box_matches_split_of_global_box():
         for peer in lb.halos:
             assert (lb.halos[peer] == subs[r].halos[peer]).all()
         assert (np.asarray(lb.freedof_flat) < 0).sum() == (np.asarray(subs[r].freedof_flat) < 0).sum()
+
+
+@pytest.mark.parametrize("case,grid", [("pml2d", (2, 1)), ("pml2d", (1, 2)), ("pml3d", (2, 2, 2))])
+def test_split_carries_equal_constraints_and_mirrors_pml_halos(case, grid):
+    """Soil-PML ties under partitioning: every partition that holds the slave or the master of an EQUAL constraint holds
+    both and the constraint itself, renumbered to its own total / free dofs; the halo lists (9- / 5-dof PML nodes included)
+    are mirror images in global numbering; every rank of a PML model is told to join the block solve's reductions."""
+    m = cases.CASES[case]()
+    n = int(np.prod(grid))
+    subs = P.split_model(m, P.centroid_epart(m, grid), n)
+    fd = np.asarray(m.freedof_flat)
+    node_of_total = np.repeat(np.arange(m.n_nodes), np.diff(m.node_ptr))
+    total_of_free = {int(f): q for q, f in enumerate(fd) if f > -1}
+    glob = {t: (node_of_total[sl], sl - m.node_ptr[node_of_total[sl]], node_of_total[total_of_free[ms[0]]],
+                total_of_free[ms[0]] - m.node_ptr[node_of_total[total_of_free[ms[0]]]]) for t, sl, ms, _ in m.constraints}
+    seen = set()
+    assert sum(s.n_elem for s in subs) == m.n_elem
+    for r, s in enumerate(subs):
+        assert s.pml_collective
+        sfd = np.asarray(s.freedof_flat)
+        s_node_of_total = np.repeat(np.arange(s.n_nodes), np.diff(s.node_ptr))
+        s_total_of_free = {int(f): q for q, f in enumerate(sfd) if f > -1}
+        for t, sl, ms, fac in s.constraints:
+            assert sfd[sl] == t and fac == [1.0]
+            sn, mq = s_node_of_total[sl], s_total_of_free[ms[0]]
+            mn = s_node_of_total[mq]
+            assert (s.global_nodes[sn], sl - s.node_ptr[sn], s.global_nodes[mn], mq - s.node_ptr[mn]) == glob[t]
+            seen.add(t)
+        # no constrained dof without its constraint, no master left behind
+        assert set(int(v) for v in sfd[sfd < -1]) == {t for t, *_ in s.constraints}
+        for peer, nodes in s.halos.items():
+            a = s.global_nodes[nodes]
+            b = subs[peer].global_nodes[subs[peer].halos[r]]
+            assert (a == b).all() and (np.diff(a) > 0).all()
+        assert any((s.node_ndof[nodes] > m.ndim).any() for nodes in s.halos.values())      # PML nodes on the cut
+    assert seen == set(glob)
