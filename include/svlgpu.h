@@ -109,7 +109,10 @@ int svlgpu_hint_structured_block(svlgpu_model *m, int node0, int nx, int ny, int
  * default; 1: NewmarkBeta + Linear, 10-Integrators/03-Newmark/NewmarkBeta.cpp:64-133 with Linear.cpp:22-56:
  * linear materials, lumped mass, Rayleigh damping with both coefficients, dashpots, one GPU; the sparse
  * factorisation of Keff = K + 4/dt^2 M + 2/dt C is replaced by matrix-free conjugate gradients),
- * "newmark_rtol" (relative residual of that solve, default 1e-13).                */
+ * "newmark_rtol" (relative residual of that solve, default 1e-13), "pml_collective" (1 on EVERY rank of a
+ * partitioned model that has PML elements anywhere, also on ranks without one: the PML block solve exchanges the
+ * unknowns on shared nodes and all-reduces its dot products, so all ranks must issue the same collectives;
+ * svlgpu_add_halo lists may then contain 9- / 5-dof PML nodes; default 0).          */
 int svlgpu_set_option(svlgpu_model *m, const char *name, double value);
 
 /* ---- loads (replaces Assembler::ComputeExternalForceVector:290-489) ------ */

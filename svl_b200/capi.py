@@ -123,6 +123,9 @@ class DeviceModel:
                  U0=None, V0=None, A0=None, comm=None, options=None):
         """comm = (rank, nranks, unique_id_bytes) joins the NCCL communicator after finalize; the
         model's `.halos` ({peer: local node indices}, svl_b200.partition) are registered before it."""
+        if getattr(m, "newton", None) is not None:
+            raise SvlError("the model asks for the NewtonRaphson algorithm: the device path implements Linear only "
+                           "(09-Algorithms/01-Linear/Linear.cpp); refusing to run a different algorithm silently")
         self.L = load_library()
         self.m = m
         self.h = self.L.svlgpu_create(m.ndim, int(m.lumped))
@@ -165,6 +168,8 @@ class DeviceModel:
                 ak = float(m.elem_ak[idx[0]]) if m.elem_ak is not None else 0.0
                 self._ck(self.L.svlgpu_set_rayleigh(self.h, len(idx), _i(idx), float(am), ak))
         opts = {"lattice_guess": 0.0} if not m.blocks else {}      # a model without lattice hints asks for the generic path
+        if getattr(m, "pml_collective", False) and getattr(m, "halos", None):
+            opts["pml_collective"] = 1.0                            # partition of a PML model: every rank joins the block solve
         opts.update(options or {})
         for k, v in opts.items():
             self._ck(self.L.svlgpu_set_option(self.h, k.encode(), float(v)))

@@ -172,6 +172,7 @@ int svlgpu_set_option(svlgpu_model *m, const char *name, double value) {
     else if (n == "integrator") { REQUIRE(value == 0.0 || value == 1.0, "set_option: integrator must be 0 (CentralDifference) or 1 (NewmarkBeta)"); m->opt_integrator = (int)value; }
     else if (n == "newmark_rtol") { REQUIRE(value > 0.0 && value < 1.0, "set_option: newmark_rtol out of range"); m->nm.rtol = value; }
     else if (n == "pml_rtol") { REQUIRE(value > 0.0 && value < 1.0, "set_option: pml_rtol out of range"); m->pml.rtol = value; }
+    else if (n == "pml_collective") m->pml.collective = value != 0.0;
     else if (n == "ftol") { REQUIRE(value >= 0.0, "set_option: ftol must be >= 0"); m->pml.ftol = value; }
     else { set_error("set_option: unknown option " + n); return 1; }
     return 0;

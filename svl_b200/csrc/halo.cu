@@ -31,10 +31,12 @@ struct Nccl {
     int (*GroupEnd)() = nullptr;
     int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
 };
 static Nccl g_nccl;
 static const int kNcclDouble = 8;   // ncclFloat64 (nccl.h)
+static const int kNcclSum = 0;      // ncclSum
 
 static int nccl_load() {
     if (g_nccl.lib) return 0;
@@ -49,7 +51,7 @@ static int nccl_load() {
     if (!g_nccl.field) { set_error(std::string("multi-GPU: NCCL symbol missing: ") + name); return 1; }
     SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
     SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv")
-    SYM(GetErrorString, "ncclGetErrorString")
+    SYM(AllReduce, "ncclAllReduce") SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
     return 0;
 }
@@ -123,6 +125,7 @@ static int exchange_on(svlgpu_model *m, cudaStream_t st) {
     NCCL_OK(g_nccl.GroupStart());
     for (auto &hp : m->halo_peers) {
         const size_t cnt = hp.nodes.size() * (size_t)nd;
+        if (!cnt) continue;                              // a peer that shares PML nodes only (exchanged inside the block solve)
         NCCL_OK(g_nccl.Send(h.d_send + (size_t)hp.offset * nd, cnt, kNcclDouble, hp.peer, h.comm, st));
         NCCL_OK(g_nccl.Recv(h.d_recv + (size_t)hp.offset * nd, cnt, kNcclDouble, hp.peer, h.comm, st));
     }
@@ -244,6 +247,98 @@ int halo_comm_init(svlgpu_model *m, const void *id128, int rank, int nranks) {
         // ranks without interface nodes still take part in nothing: no peers, no NCCL calls
     }
     CUDA_OK(cudaGetLastError());
+    return pmlx_setup(m);
+}
+
+// ---- PML block on several ranks (pml.cu): exchange of the shared unknowns, all-reduce of the dot products --------------
+__global__ void k_pmlx_pack(int n, const int32_t *unk, const double *raw, double *sbuf) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) sbuf[t] = raw[unk[t]];
+}
+// every holder of a shared unknown adds the parts in ascending rank order (its own at its place): same bits everywhere
+__global__ void k_pmlx_sum(int n, const int32_t *unk, const int32_t *ptr, const int32_t *src, double *raw, const double *rbuf) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int c = unk[t];
+    const double mine = raw[c];
+    double v = 0.0;
+    for (int q = ptr[t]; q < ptr[t + 1]; q++) v += (src[q] < 0) ? mine : rbuf[src[q]];
+    raw[c] = v;
+}
+
+int pmlx_exchange(svlgpu_model *m, cudaStream_t st) {
+    PmlDev &P = m->pml;
+    HaloDev &h = m->halo;
+    if (!P.n_xe) return 0;
+    k_pmlx_pack<<<(P.n_xe + 255) / 256, 256, 0, st>>>(P.n_xe, P.d_x_send, P.d_raw, P.d_x_sbuf);
+    NCCL_OK(g_nccl.GroupStart());
+    for (auto &hp : m->halo_peers) {
+        if (hp.unk.empty()) continue;
+        NCCL_OK(g_nccl.Send(P.d_x_sbuf + hp.unk_offset, hp.unk.size(), kNcclDouble, hp.peer, h.comm, st));
+        NCCL_OK(g_nccl.Recv(P.d_x_rbuf + hp.unk_offset, hp.unk.size(), kNcclDouble, hp.peer, h.comm, st));
+    }
+    NCCL_OK(g_nccl.GroupEnd());
+    k_pmlx_sum<<<(P.n_xu + 255) / 256, 256, 0, st>>>(P.n_xu, P.d_x_unk, P.d_x_ptr, P.d_x_src, P.d_raw, P.d_x_rbuf);
+    m->total_launches += 2;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int pmlx_allreduce(svlgpu_model *m, double *a, size_t na, double *b, size_t nb, cudaStream_t st) {
+    HaloDev &h = m->halo;
+    NCCL_OK(g_nccl.AllReduce(a, a, na, kNcclDouble, kNcclSum, h.comm, st));
+    if (b && nb) NCCL_OK(g_nccl.AllReduce(b, b, nb, kNcclDouble, kNcclSum, h.comm, st));
+    return 0;
+}
+
+// after the communicator exists: rank-ordered source lists of the shared unknowns, the ownership mask of the dot products,
+// and the row / column scaling from the diagonal of Keff summed over the ranks
+int pmlx_setup(svlgpu_model *m) {
+    PmlDev &P = m->pml;
+    HaloDev &h = m->halo;
+    if (!P.present || !P.d_raw) return 0;                 // no PML block, or one that was planned for a single rank
+    const int rank = h.rank;
+    std::vector<std::vector<std::pair<int, int>>> srcs(P.nc);      // per unknown: (rank, index into rbuf | -1)
+    std::vector<double> own(std::max(1, P.nc), 1.0);
+    for (auto &hp : m->halo_peers)
+        for (size_t j = 0; j < hp.unk.size(); j++) {
+            const int c = hp.unk[j];
+            if (c < 0 || c >= P.nc) { set_error("comm_init: PML exchange list refers to an unknown that does not exist"); return 1; }
+            srcs[c].push_back({hp.peer, hp.unk_offset + (int)j});
+            if (hp.peer < rank) own[c] = 0.0;
+        }
+    std::vector<int32_t> unk, ptr(1, 0), src;
+    for (int c = 0; c < P.nc; c++) {
+        if (srcs[c].empty()) continue;
+        srcs[c].push_back({rank, -1});
+        std::sort(srcs[c].begin(), srcs[c].end());
+        unk.push_back(c);
+        for (auto &pr : srcs[c]) src.push_back(pr.second);
+        ptr.push_back((int32_t)src.size());
+    }
+    P.n_xu = (int)unk.size();
+    int32_t *d_unk = nullptr, *d_ptr = nullptr, *d_src = nullptr;
+    CUDA_OK(cudaMalloc(&d_unk, sizeof(int32_t) * std::max<size_t>(1, unk.size())));
+    CUDA_OK(cudaMalloc(&d_ptr, sizeof(int32_t) * ptr.size()));
+    CUDA_OK(cudaMalloc(&d_src, sizeof(int32_t) * std::max<size_t>(1, src.size())));
+    m->allocs.push_back(d_unk); m->allocs.push_back(d_ptr); m->allocs.push_back(d_src);
+    CUDA_OK(cudaMemcpy(d_unk, unk.data(), sizeof(int32_t) * unk.size(), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(d_ptr, ptr.data(), sizeof(int32_t) * ptr.size(), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(d_src, src.data(), sizeof(int32_t) * src.size(), cudaMemcpyHostToDevice));
+    P.d_x_unk = d_unk; P.d_x_ptr = d_ptr; P.d_x_src = d_src;
+    CUDA_OK(cudaMemcpy(P.d_own, own.data(), sizeof(double) * P.nc, cudaMemcpyHostToDevice));
+    // global diagonal -> scaling
+    if ((int)P.h_diag.size() != P.nc) { set_error("comm_init: PML diagonal missing"); return 1; }
+    CUDA_OK(cudaMemcpy(P.d_raw, P.h_diag.data(), sizeof(double) * P.nc, cudaMemcpyHostToDevice));
+    if (pmlx_exchange(m, m->stream)) return 1;
+    std::vector<double> tot(std::max(1, P.nc));
+    CUDA_OK(cudaMemcpyAsync(tot.data(), P.d_raw, sizeof(double) * P.nc, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_OK(cudaStreamSynchronize(m->stream));
+    for (int c = 0; c < P.nc; c++)
+        if (tot[c] == 0.0 || !(tot[c] == tot[c])) { set_error("PML block: zero diagonal in Keff (EigenSolver.cpp:52-55 would fail too)"); return 1; }
+    if (pml_rescale(m)) return 1;
+    CUDA_OK(cudaStreamSynchronize(m->stream));
+    P.multi = true;
     return 0;
 }
 

@@ -130,7 +130,15 @@ struct DrmDev {
 // Multi-GPU: interface nodes shared with other ranks.  Every rank computes the partial
 // (internal - external) force of its own elements at the interface nodes, exchanges the partials with
 // the ranks sharing each node, and every replica applies the same rank-ordered sum.
-struct HaloPeer { int peer = 0; std::vector<int32_t> nodes; int offset = 0; };
+struct HaloPeer {
+    int peer = 0;
+    std::vector<int32_t> nodes;        // shared soil nodes (ndim dofs each), ascending global id on both sides
+    int offset = 0;
+    // shared nodes of the PML block (9- / 5-dof PML nodes and the soil nodes tied to them) are exchanged per unknown
+    // inside the block solve: unknown indices in the order of the peer's mirror list, first entry in the send buffer
+    std::vector<int32_t> unk;
+    int unk_offset = 0;
+};
 struct HaloDev {
     bool active = false;
     int n_if = 0, nd = 3;              // interface nodes, dofs per node exchanged (= ndim)
@@ -197,6 +205,19 @@ struct PmlDev {
     double rtol = 1e-14, ftol = 1e-12;   // ftol: Assembler.cpp:262 (Driver.hpp:1806 default)
     int max_iter = 2000, last_iters = 8;
     int64_t total_iters = 0, solves = 0;
+    // multi-GPU: unknowns on nodes shared with other ranks are replicated; every operator application and
+    // the right-hand side exchange their partial sums (rank-ordered, so all replicas hold the same bits), the dot products
+    // count every unknown once (d_own) and are all-reduced
+    bool collective = false;         // option "pml_collective": this rank joins the reductions even without PML unknowns
+    bool multi = false;              // communicator joined (halo_comm_init)
+    int n_xe = 0, n_xu = 0;          // send entries (sum over the peers) / distinct shared unknowns
+    int32_t *d_x_send = nullptr;     // [n_xe] unknown of each send entry
+    double *d_x_sbuf = nullptr, *d_x_rbuf = nullptr;     // [n_xe]
+    int32_t *d_x_unk = nullptr;      // [n_xu] shared unknowns, ascending
+    int32_t *d_x_ptr = nullptr, *d_x_src = nullptr;      // per shared unknown: sources in rank order (-1 = own, else rbuf index)
+    double *d_own = nullptr;         // [nc] 1 where this rank is the lowest one that holds the unknown, else 0
+    double *d_raw = nullptr;         // [nc] operator / right-hand-side values before the exchange and the row scaling
+    std::vector<double> h_diag;      // this rank's part of diag(Keff) per unknown (summed over the ranks at comm_init)
 };
 
 // NewmarkBeta + Linear on the device (newmark.cu)
@@ -332,7 +353,11 @@ int halo_exchange_end(svlgpu_model *m, const double *U, const double *Up, double
 int halo_lattice_force(svlgpu_model *m, const double *U);   // partial forces of lattice interface nodes -> hF
 int halo_generic_force(svlgpu_model *m);                    // ... of generic interface nodes -> hF
 void halo_destroy(svlgpu_model *m);
+int pmlx_setup(svlgpu_model *m);                                                     // lists + global diag(Keff); from halo_comm_init
+int pmlx_exchange(svlgpu_model *m, cudaStream_t st);                                 // raw[shared] <- rank-ordered sum over the holders
+int pmlx_allreduce(svlgpu_model *m, double *a, size_t na, double *b, size_t nb, cudaStream_t st);   // in place, sum
 // pml.cu
+int pml_rescale(svlgpu_model *m);                                                    // w, sc from the summed diagonal in d_raw
 int pml_step(svlgpu_model *m, const double *U, const double *Up, double *Un);
 int pml_internal_force(svlgpu_model *m, const double *U, double *F);
 void pml_destroy(svlgpu_model *m);

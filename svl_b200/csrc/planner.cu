@@ -166,7 +166,22 @@ int plan_and_upload(svlgpu_model *m) {
             }
         }
     }
-    if (has_pml && !m->halo_peers.empty()) { set_error("PML models are not partitioned across GPUs yet"); return 1; }
+    // Multi-GPU: a partition can hold PML nodes without a PML element of its own (the tie closure of the partitioner brings the
+    // slave of every master it holds), and every rank of a PML model runs the block solve's reductions ("pml_collective").
+    std::vector<std::vector<int32_t>> halo_all(m->halo_peers.size());     // the peers' lists as declared: soil and PML nodes
+    if (!m->halo_peers.empty()) {
+        if (has_pml && !m->pml.collective) { set_error("PML model on several GPUs: set option pml_collective on every rank"); return 1; }
+        if (m->pml.collective) {
+            const int want = (nd == 3) ? 9 : 5;
+            for (int n = 0; n < nN; n++) if (m->node_ndof[n] == want) node_is_pml[n] = 1;
+        }
+        for (size_t i = 0; i < m->halo_peers.size(); i++) {
+            auto &hp = m->halo_peers[i];
+            halo_all[i] = hp.nodes;
+            hp.nodes.erase(std::remove_if(hp.nodes.begin(), hp.nodes.end(), [&](int32_t n) { return node_is_pml[n] != 0; }), hp.nodes.end());
+        }
+    }
+    const bool plan_pml_block = has_pml || (m->pml.collective && !m->halo_peers.empty());
 
     // ---- B. element classes ---------------------------------------------------------------
     const char *tol_s = getenv("SVLGPU_CLASS_TOL");
@@ -289,11 +304,17 @@ int plan_and_upload(svlgpu_model *m) {
     std::vector<double> kinv(m->n_int, 0.0), km(m->n_int, 0.0);
     std::vector<int32_t> node_of_dof(m->n_int);
     for (int n = 0; n < nN; n++) for (int q = m->node_ptr[n]; q < m->node_ptr[n + 1]; q++) node_of_dof[q] = n;
+    std::vector<uint8_t> in_halo(nN, 0);
+    for (auto &hp : m->halo_peers) for (int n : hp.nodes) in_halo[n] = 1;
     for (int q = 0; q < m->n_int; q++) {
         if (m->freedof[q] < 0) continue;             // restrained: dU = 0 (Mesh.cpp:354-357); slaves follow their master
         if (node_is_pml[node_of_dof[q]]) continue;   // advanced by the PML block solve
         const double keff = 1.0 / dt / dt * mass[q] + 1.0 / 2.0 / dt * cdiag[q];
-        if (!(keff > 0.0)) { set_error("free dof without mass: Keff is singular (EigenSolver.cpp:52-55)"); return 1; }
+        if (!(keff > 0.0)) {
+            // a shared node may get all of its mass from other ranks: svlgpu_comm_init sums the diagonals and sets 1/Keff
+            if (in_halo[node_of_dof[q]] && keff == 0.0) continue;
+            set_error("free dof without mass: Keff is singular (EigenSolver.cpp:52-55)"); return 1;
+        }
         kinv[q] = 1.0 / keff;
         km[q] = 1.0 / dt / dt * mass[q] - 1.0 / 2.0 / dt * cdiag[q];
     }
@@ -756,7 +777,28 @@ int plan_and_upload(svlgpu_model *m) {
         }
     }
     std::vector<int32_t> cmap;                             // internal dof -> PML unknown or -1
-    if (has_pml && plan_pml(m, alias, node_is_pml, node_of_dof, kinv, km, cmap)) return 1;
+    if (plan_pml_block && plan_pml(m, alias, node_is_pml, node_of_dof, kinv, km, cmap)) return 1;
+    if (plan_pml_block && !m->halo_peers.empty()) {
+        // unknowns shared with each peer, in the order of the declared node list (mirror image on the peer: the free /
+        // restrained / tied status of a dof is a property of the global model)
+        PmlDev &P = m->pml;
+        std::vector<int32_t> send;
+        for (size_t i = 0; i < m->halo_peers.size(); i++) {
+            auto &hp = m->halo_peers[i];
+            hp.unk_offset = (int)send.size();
+            for (int n : halo_all[i])
+                for (int q = m->node_ptr[n]; q < m->node_ptr[n + 1]; q++)
+                    if (cmap[q] >= 0 && alias[q] == q) hp.unk.push_back(cmap[q]);
+            send.insert(send.end(), hp.unk.begin(), hp.unk.end());
+        }
+        P.n_xe = (int)send.size();
+        P.d_x_send = dupload(m, send);
+        P.d_x_sbuf = dalloc<double>(m, send.size());
+        P.d_x_rbuf = dalloc<double>(m, send.size());
+        P.d_raw = dalloc<double>(m, P.nc);
+        P.d_own = dupload(m, std::vector<double>(std::max(1, P.nc), 1.0));
+        if (!P.d_x_sbuf || !P.d_x_rbuf || !P.d_raw || !P.d_own) { set_error("out of device memory (PML exchange)"); return 1; }
+    }
     auto halo_slot_of_dof = [&](int q) -> int32_t {       // internal dof -> slot in hF, -2-c (PML unknown c) or -1
         const int node = node_of_dof[q];
         const int i = m->if_of_node[node];
@@ -1042,7 +1084,8 @@ static int plan_pml_nd(svlgpu_model *m, const std::vector<int32_t> &alias, const
     for (int c = 0; c < P.nc; c++) {
         const int q = c_dof[c];
         if (!node_is_pml[node_of_dof[q]]) {
-            dsoil[c] = 1.0 / kinv[q]; kms[c] = km[q];
+            dsoil[c] = kinv[q] > 0.0 ? 1.0 / kinv[q] : 0.0;      // 0: all of this dof's mass sits on other ranks
+            kms[c] = km[q];
             c_hf[c] = m->if_of_node[node_of_dof[q]] * ND + (q - m->node_ptr[node_of_dof[q]]);
         }
         diag[c] = dsoil[c];
@@ -1056,10 +1099,15 @@ static int plan_pml_nd(svlgpu_model *m, const std::vector<int32_t> &alias, const
         }
     std::vector<double> w(P.nc), scl(P.nc);
     for (int c = 0; c < P.nc; c++) {
-        if (diag[c] == 0.0) { set_error("PML block: zero diagonal in Keff (EigenSolver.cpp:52-55 would fail too)"); return 1; }
+        if (diag[c] == 0.0) {
+            // several ranks: the diagonal is summed over the holders of the unknown at comm_init, which rescales (pmlx_setup)
+            if (!m->halo_peers.empty()) { scl[c] = 0.0; w[c] = 0.0; continue; }
+            set_error("PML block: zero diagonal in Keff (EigenSolver.cpp:52-55 would fail too)"); return 1;
+        }
         scl[c] = 1.0 / std::sqrt(std::fabs(diag[c]));
         w[c] = diag[c] > 0.0 ? scl[c] : -scl[c];          // stress rows have a negative diagonal
     }
+    P.h_diag = diag;
     P.d_sc = dupload(m, scl);
     P.d_A = dupload(m, tA); P.d_K = dupload(m, tP); P.d_Km = dupload(m, tK);
     // pattern-sparse tables + one-class chunks for k_pml_elem_sp

@@ -235,7 +235,8 @@ template <int NN, int NPE, int Q, int NEG> constexpr size_t pml_rg_smem() {
 __global__ void __launch_bounds__(kRedThreads) k_pml_rhs(int nc, const int32_t *ptr, const int32_t *slot, const double *ye,
                                                          const int32_t *c_dof, const int32_t *c_hf, const double *kms,
                                                          const double *hF, const double *U, const double *Up,
-                                                         double *bext, const double *w, double *b, double *part) {
+                                                         double *bext, const double *w, double *b, double *part,
+                                                         double *raw) {
     double acc = 0.0;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
         double v = bext[c];
@@ -243,10 +244,12 @@ __global__ void __launch_bounds__(kRedThreads) k_pml_rhs(int nc, const int32_t *
         for (int q = ptr[c]; q < ptr[c + 1]; q++) v += ye[slot[q]];
         const int hs = c_hf[c];
         if (hs >= 0) { const int d = c_dof[c]; v += kms[c] * (U[d] - Up[d]) - hF[hs]; }
+        if (raw) { raw[c] = v; continue; }                  // several ranks: this rank's part; k_pml_post finishes it
         v *= w[c];
         b[c] = v;
         acc = fma(v, v, acc);
     }
+    if (raw) return;
     const double s = block_sum(acc);
     if (threadIdx.x == 0) {
         part[S_BB * kRedBlocks + blockIdx.x] = s;
@@ -262,12 +265,13 @@ __global__ void __launch_bounds__(kRedThreads) k_pml_gather(int nc, int mode, co
                                                             const double *ye, const double *dsoil, const double *w,
                                                             const double *sc, const double *in, double *out, const double *b, double *r,
                                                             double *rh, double *p, const double *s, double *part,
-                                                            int rr_slot, double tol2) {
+                                                            int rr_slot, double tol2, double *raw) {
     if (mode != 0 && part[kFlagAt] != 0.0) return;
     double a0 = 0.0, a1 = 0.0;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
         double v = dsoil[c] * (sc[c] * in[c]);
         for (int q = ptr[c]; q < ptr[c + 1]; q++) v += ye[slot[q]];
+        if (raw) { raw[c] = v; continue; }                  // several ranks: this rank's part; k_pml_post finishes it
         v *= w[c];
         if (mode == 0) {
             const double rv = b[c] - v;
@@ -282,6 +286,7 @@ __global__ void __launch_bounds__(kRedThreads) k_pml_gather(int nc, int mode, co
             a1 = fma(v, v, a1);
         }
     }
+    if (raw) return;
     const double s0 = block_sum(a0);
     const double s1 = block_sum(a1);
     if (threadIdx.x == 0) {
@@ -289,6 +294,51 @@ __global__ void __launch_bounds__(kRedThreads) k_pml_gather(int nc, int mode, co
         else if (mode == 1) part[S_RHV * kRedBlocks + blockIdx.x] = s0;
         else { part[S_TS * kRedBlocks + blockIdx.x] = s0; part[S_TT * kRedBlocks + blockIdx.x] = s1; }
     }
+}
+
+// ---- several ranks: second half of k_pml_rhs / k_pml_gather after the exchange of the shared unknowns ----------------
+// raw holds the complete sums (identical bits on every rank that holds the unknown); the dot products count an unknown on
+// its lowest rank only (own = 1 there, 0 elsewhere) and are all-reduced by the caller.
+// mode -1: b = W raw, partial ||b||^2, clears the converged flag;   modes 0, 1, 2: as k_pml_gather
+__global__ void __launch_bounds__(kRedThreads) k_pml_post(int nc, int mode, const double *raw, const double *w, const double *own,
+                                                          double *out, double *b, double *r, double *rh, double *p,
+                                                          const double *s, double *part, int rr_slot) {
+    if (mode > 0 && part[kFlagAt] != 0.0) return;
+    double a0 = 0.0, a1 = 0.0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
+        const double v = raw[c] * w[c], o = own[c];
+        if (mode == -1) {
+            b[c] = v;
+            a0 = fma(o * v, v, a0);
+        } else if (mode == 0) {
+            const double rv = b[c] - v;
+            r[c] = rv; rh[c] = rv; p[c] = rv;
+            a0 = fma(o * rv, rv, a0);
+        } else if (mode == 1) {
+            out[c] = v;
+            a0 = fma(o * rh[c], v, a0);
+        } else {
+            out[c] = v;
+            a0 = fma(o * v, s[c], a0);
+            a1 = fma(o * v, v, a1);
+        }
+    }
+    const double s0 = block_sum(a0);
+    const double s1 = block_sum(a1);
+    if (threadIdx.x == 0) {
+        if (mode == -1) { part[S_BB * kRedBlocks + blockIdx.x] = s0; if (blockIdx.x == 0) part[kFlagAt] = 0.0; }
+        else if (mode == 0) { part[S_RHO * kRedBlocks + blockIdx.x] = s0; part[rr_slot * kRedBlocks + blockIdx.x] = s0; }
+        else if (mode == 1) part[S_RHV * kRedBlocks + blockIdx.x] = s0;
+        else { part[S_TS * kRedBlocks + blockIdx.x] = s0; part[S_TT * kRedBlocks + blockIdx.x] = s1; }
+    }
+}
+// w = sign(d) / sqrt|d|, sc = 1 / sqrt|d| from the diagonal of Keff summed over the ranks (in raw)
+__global__ void k_pml_rescale(int nc, const double *diag, double *w, double *sc) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc) return;
+    const double d = diag[c], s = 1.0 / sqrt(fabs(d));
+    sc[c] = s;
+    w[c] = d > 0.0 ? s : -s;
 }
 
 // scalars carried between kernels: [0] rho of the previous iteration, [1] alpha, [2] omega, [3] rho of this iteration
@@ -317,7 +367,7 @@ __global__ void __launch_bounds__(kRedThreads) k_bicg_s(int nc, const double *r,
 // x += alpha p + omega s; r = s - omega t; partial rho_next = (rh, r), rr = (r, r) into the other rr slot
 __global__ void __launch_bounds__(kRedThreads) k_bicg_x(int nc, double *x, const double *p, const double *s, const double *t,
                                                         double *r, const double *rh, double *scal, double *part,
-                                                        int rr_slot, double tol2) {
+                                                        int rr_slot, double tol2, const double *own) {
     if (part[kFlagAt] != 0.0) return;
     const int nslot = (rr_slot == S_RR0) ? S_RR1 : S_RR0;
     const double tt = slot_total(part, S_TT), ts = slot_total(part, S_TS);
@@ -329,8 +379,9 @@ __global__ void __launch_bounds__(kRedThreads) k_bicg_x(int nc, double *x, const
         x[c] += alpha * p[c] + omega * sv;
         const double rv = sv - omega * t[c];
         r[c] = rv;
-        a0 = fma(rh[c], rv, a0);
-        a1 = fma(rv, rv, a1);
+        const double o = own ? own[c] : 1.0;              // several ranks: an unknown counts on its lowest rank only
+        a0 = fma(o * rh[c], rv, a0);
+        a1 = fma(o * rv, rv, a1);
     }
     const double s0 = block_sum(a0);
     const double s1 = block_sum(a1);
@@ -376,6 +427,7 @@ static void launch_elem(svlgpu_model *m, int mode, const int32_t *idx, const dou
 static void elem_products(svlgpu_model *m, int mode, const int32_t *idx, const double *T1, const double *x1, const double *T2,
                           const double *x2, const double *xs, const double *part, int rr_slot, double tol2) {
     PmlDev &P = m->pml;
+    if (P.n_elem == 0) return;                            // a rank that only holds replicas of PML unknowns
     timer_begin(m, 6);
     struct End { svlgpu_model *m; ~End() { timer_end(m, 6); } } end_{m};
     if (P.sp_q > 0) {
@@ -399,25 +451,48 @@ static void elem_products(svlgpu_model *m, int mode, const int32_t *idx, const d
     else launch_elem<20, 8>(m, mode, idx, T1, x1, T2, x2, xs, part, rr_slot, tol2);
 }
 
+// Several ranks: finish a right-hand side / operator application whose local part sits in d_raw -- exchange the shared
+// unknowns (rank-ordered sums: identical bits on every holder), scale, update the vectors, all-reduce the dot products.
+static int post_exchange(svlgpu_model *m, int mode, double *out, const double *s, int rr) {
+    PmlDev &P = m->pml;
+    cudaStream_t st = m->stream;
+    if (pmlx_exchange(m, st)) return 1;
+    timer_begin(m, 7);
+    k_pml_post<<<kRedBlocks, kRedThreads, 0, st>>>(P.nc, mode, P.d_raw, P.d_w, P.d_own, out, P.d_b, P.d_r, P.d_rh, P.d_p, s, P.d_part, rr);
+    timer_end(m, 7);
+    m->total_launches++;
+    double *part = P.d_part;
+    switch (mode) {
+    case -1: return pmlx_allreduce(m, part + S_BB * kRedBlocks, kRedBlocks, nullptr, 0, st);
+    case 0: return pmlx_allreduce(m, part + S_RHO * kRedBlocks, kRedBlocks, part + rr * kRedBlocks, kRedBlocks, st);
+    case 1: return pmlx_allreduce(m, part + S_RHV * kRedBlocks, kRedBlocks, nullptr, 0, st);
+    default: return pmlx_allreduce(m, part + S_TS * kRedBlocks, 2 * kRedBlocks, nullptr, 0, st);      // S_TS, S_TT are adjacent
+    }
+}
+
 int pml_step(svlgpu_model *m, const double *U, const double *Up, double *Un) {
     PmlDev &P = m->pml;
-    if (!P.present || !P.nc) return 0;
+    const bool mg = P.multi;                              // several ranks: every rank runs the same sequence of collectives
+    if (!P.present || (!P.nc && !mg)) return 0;
     cudaStream_t st = m->stream;
     const double tol2 = P.rtol * P.rtol;
     double *scal = P.d_part + S_NSLOT * kRedBlocks;       // 8 carried scalars behind the partial slots
+    double *raw = mg ? P.d_raw : nullptr;
     // right-hand side
     elem_products(m, 1, P.d_edof, P.d_K, U, P.d_Km, Up, nullptr, nullptr, 0, 0.0);
     timer_begin(m, 7);
     k_pml_rhs<<<kRedBlocks, kRedThreads, 0, st>>>(P.nc, P.d_c_ptr, P.d_c_slot, P.d_ye, P.d_c_dof, P.d_c_hf, P.d_kms, m->halo.d_hF,
-                                                  U, Up, P.d_bext, P.d_w, P.d_b, P.d_part);
+                                                  U, Up, P.d_bext, P.d_w, P.d_b, P.d_part, raw);
     timer_end(m, 7);
+    if (mg && post_exchange(m, -1, nullptr, nullptr, 0)) return 1;
     // initial residual with the previous increment as the starting guess
     elem_products(m, 0, P.d_ecd, P.d_A, P.d_x, nullptr, nullptr, P.d_sc, nullptr, 0, 0.0);
     int rr = S_RR0;
     timer_begin(m, 7);
     k_pml_gather<<<kRedBlocks, kRedThreads, 0, st>>>(P.nc, 0, P.d_c_ptr, P.d_c_slot, P.d_ye, P.d_diag, P.d_w, P.d_sc, P.d_x, nullptr, P.d_b,
-                                                     P.d_r, P.d_rh, P.d_p, nullptr, P.d_part, rr, tol2);
+                                                     P.d_r, P.d_rh, P.d_p, nullptr, P.d_part, rr, tol2, raw);
     timer_end(m, 7);
+    if (mg && post_exchange(m, 0, nullptr, nullptr, rr)) return 1;
     k_pml_flag<<<1, 32, 0, st>>>(P.d_part, rr, tol2, scal + 6);
     m->total_launches += 3;
     int it = 0;
@@ -431,20 +506,25 @@ int pml_step(svlgpu_model *m, const double *U, const double *Up, double *Un) {
             elem_products(m, 0, P.d_ecd, P.d_A, P.d_p, nullptr, nullptr, P.d_sc, P.d_part, rr, tol2);
             timer_begin(m, 7);
             k_pml_gather<<<kRedBlocks, kRedThreads, 0, st>>>(P.nc, 1, P.d_c_ptr, P.d_c_slot, P.d_ye, P.d_diag, P.d_w, P.d_sc, P.d_p, P.d_v,
-                                                             nullptr, nullptr, P.d_rh, nullptr, nullptr, P.d_part, rr, tol2);
+                                                             nullptr, nullptr, P.d_rh, nullptr, nullptr, P.d_part, rr, tol2, raw);
             timer_end(m, 7);
+            if (mg && post_exchange(m, 1, P.d_v, nullptr, rr)) return 1;
             timer_begin(m, 8);
             k_bicg_s<<<kRedBlocks, kRedThreads, 0, st>>>(P.nc, P.d_r, P.d_v, P.d_s, scal, P.d_part, rr, tol2);
             timer_end(m, 8);
             elem_products(m, 0, P.d_ecd, P.d_A, P.d_s, nullptr, nullptr, P.d_sc, P.d_part, rr, tol2);
             timer_begin(m, 7);
             k_pml_gather<<<kRedBlocks, kRedThreads, 0, st>>>(P.nc, 2, P.d_c_ptr, P.d_c_slot, P.d_ye, P.d_diag, P.d_w, P.d_sc, P.d_s, P.d_t,
-                                                             nullptr, nullptr, nullptr, nullptr, P.d_s, P.d_part, rr, tol2);
+                                                             nullptr, nullptr, nullptr, nullptr, P.d_s, P.d_part, rr, tol2, raw);
             timer_end(m, 7);
+            if (mg && post_exchange(m, 2, P.d_t, P.d_s, rr)) return 1;
             timer_begin(m, 8);
-            k_bicg_x<<<kRedBlocks, kRedThreads, 0, st>>>(P.nc, P.d_x, P.d_p, P.d_s, P.d_t, P.d_r, P.d_rh, scal, P.d_part, rr, tol2);
+            k_bicg_x<<<kRedBlocks, kRedThreads, 0, st>>>(P.nc, P.d_x, P.d_p, P.d_s, P.d_t, P.d_r, P.d_rh, scal, P.d_part, rr, tol2,
+                                                         mg ? P.d_own : nullptr);
             timer_end(m, 8);
             rr = (rr == S_RR0) ? S_RR1 : S_RR0;
+            // k_bicg_x wrote the partials of the next rho and of ||r||^2 (into the slot rr now names)
+            if (mg && pmlx_allreduce(m, P.d_part + S_RHO * kRedBlocks, kRedBlocks, P.d_part + rr * kRedBlocks, kRedBlocks, st)) return 1;
             k_pml_flag<<<1, 32, 0, st>>>(P.d_part, rr, tol2, scal + 6);
             m->total_launches += 6;
         }
@@ -458,10 +538,20 @@ int pml_step(svlgpu_model *m, const double *U, const double *Up, double *Un) {
     }
     P.last_iters = std::max(2, it - 1);
     P.total_iters += it; P.solves++;
-    timer_begin(m, 8);
-    k_pml_scatter<<<(P.n_sc + 255) / 256, 256, 0, st>>>(P.n_sc, P.d_sc_dof, P.d_sc_c, P.d_x, P.d_sc, U, Un);
-    timer_end(m, 8);
-    m->total_launches++;
+    if (P.n_sc) {
+        timer_begin(m, 8);
+        k_pml_scatter<<<(P.n_sc + 255) / 256, 256, 0, st>>>(P.n_sc, P.d_sc_dof, P.d_sc_c, P.d_x, P.d_sc, U, Un);
+        timer_end(m, 8);
+        m->total_launches++;
+    }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// several ranks, once: w and sc from the diagonal of Keff summed over the holders of each unknown (pmlx_setup left it in d_raw)
+int pml_rescale(svlgpu_model *m) {
+    PmlDev &P = m->pml;
+    if (P.nc) k_pml_rescale<<<(P.nc + 255) / 256, 256, 0, m->stream>>>(P.nc, P.d_raw, P.d_w, P.d_sc);
     CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -51,8 +51,11 @@ def block_epart(ne, pgrid) -> np.ndarray:
 def centroid_epart(m: Model, pgrid) -> np.ndarray:
     """Element -> partition by the position of the element centroid in the model's bounding box (a geometric block split
     for models that are not one lattice, e.g. a soil box wrapped in its PML layer); pgrid has one entry per axis."""
-    npe_e = np.array([ELEM_NODES[int(k)] for k in m.elem_kind])
-    cen = np.stack([m.coords[m.elem_conn[e, :npe_e[e]]].mean(axis=0) for e in range(m.n_elem)])
+    npe_e = np.array([ELEM_NODES[int(k)] for k in np.unique(m.elem_kind)])[np.searchsorted(np.unique(m.elem_kind), m.elem_kind)]
+    cen = np.zeros((m.n_elem, m.ndim))
+    for npe in np.unique(npe_e):                           # vectorised per node count (millions of elements at bench sizes)
+        sel = np.nonzero(npe_e == npe)[0]
+        cen[sel] = m.coords[m.elem_conn[sel, :npe]].mean(axis=1)
     lo, hi = m.coords.min(axis=0), m.coords.max(axis=0)
     part = np.zeros(m.n_elem, dtype=np.int32)
     mult = 1
@@ -71,13 +74,15 @@ def read_epart(path: str) -> np.ndarray:
 def split_model(m: Model, epart: np.ndarray, nparts: int) -> List[Model]:
     """Global model + element partition -> one sub-model per rank, each carrying
     `.halos = {peer: local node indices}`, `.global_nodes`, `.global_elems`."""
-    npe_e = np.array([ELEM_NODES[int(k)] for k in m.elem_kind], dtype=np.int32)
+    kinds = np.unique(m.elem_kind)
+    npe_e = np.array([ELEM_NODES[int(k)] for k in kinds], dtype=np.int32)[np.searchsorted(kinds, m.elem_kind)]
 
     def nodes_of(el):
         """unique nodes of the listed elements (each element uses its own node count)"""
+        el = np.asarray(el)
         if len(el) == 0:
             return np.zeros(0, dtype=np.int64)
-        return np.unique(np.concatenate([m.elem_conn[e, :npe_e[e]] for e in el]))
+        return np.unique(np.concatenate([m.elem_conn[el[npe_e[el] == npe], :npe].ravel() for npe in np.unique(npe_e[el])]))
 
     epart = np.asarray(epart, dtype=np.int32)
     if len(epart) < m.n_elem:
@@ -110,18 +115,18 @@ def split_model(m: Model, epart: np.ndarray, nparts: int) -> List[Model]:
     for tag, slave, masters, factors in m.constraints:
         ties.append((int(tag), int(slave), [int(total_of_free[f]) for f in masters], list(factors)))
     if ties:
-        tie_nodes = [np.unique([node_of_total[sl]] + [node_of_total[t] for t in mt]) for _, sl, mt, _ in ties]
+        # (slave node, master node) pairs, one per master of every tie
+        ta = np.array([node_of_total[sl] for _, sl, mt, _ in ties for _t in mt], dtype=np.int64)
+        tb = np.array([node_of_total[t] for _, sl, mt, _ in ties for t in mt], dtype=np.int64)
         for r in range(nparts):
             have = np.zeros(m.n_nodes, dtype=bool)
             have[node_sets[r]] = True
-            changed = True
-            while changed:
-                changed = False
-                for tn in tie_nodes:
-                    h = have[tn]
-                    if h.any() and not h.all():
-                        have[tn] = True
-                        changed = True
+            while True:
+                ha, hb = have[ta], have[tb]
+                if (ha == hb).all():
+                    break
+                have[ta[hb]] = True
+                have[tb[ha]] = True
             node_sets[r] = np.nonzero(have)[0]
     pml_anywhere = bool(np.isin(m.elem_kind, (3, 4)).any())
     # owner of a node = lowest rank that holds it
@@ -143,8 +148,9 @@ def split_model(m: Model, epart: np.ndarray, nparts: int) -> List[Model]:
                      for n in gn]
         s.materials = list(m.materials)
         conn = np.zeros((len(el), 8), dtype=np.int32)
-        for i, e in enumerate(el):
-            conn[i, :npe_e[e]] = loc[m.elem_conn[e, :npe_e[e]]]
+        for npe in np.unique(npe_e[el]):
+            sel = np.nonzero(npe_e[el] == npe)[0]
+            conn[sel, :npe] = loc[m.elem_conn[el[sel], :npe]]
         s.elem_conn = conn
         s.elem_kind = m.elem_kind[el]
         s.elem_mat = m.elem_mat[el]

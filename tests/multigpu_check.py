@@ -23,7 +23,10 @@ from svl_b200 import capi, partition as P  # noqa: E402
 
 NE = {"kat444": (4, 4, 4), "drm_box": (6, 6, 5), "quad4_area": (8, 6), "j2_column": (2, 2, 6),
       "hex8_layered_rayleigh": (4, 3, 6), "hex8_distorted": (3, 4, 5), "drm_area": (8, 6),
-      "lysmer_column": (3, 3, 6)}            # ZeroLength1D dashpots follow the rank of their soil node
+      "lysmer_column": (3, 3, 6),            # ZeroLength1D dashpots follow the rank of their soil node
+      # soil box + PML layer (EQUAL ties, 9- / 5-dof PML nodes on the cuts): split by element centroid; the block solve
+      # exchanges the shared unknowns and all-reduces its dot products
+      "pml2d": None, "pml3d": None}
 
 
 def main():
@@ -40,29 +43,34 @@ def main():
             uid.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
         m = cases.CASES[name]()
-        if len(ne) == 3:
+        if ne is None:
+            grid = P.proc_grid(world) if m.ndim == 3 else ((world, 1) if world <= 2 else (2, world // 2))
+            subs = P.split_model(m, P.centroid_epart(m, grid), world)
+        elif len(ne) == 3:
             grid = P.proc_grid(world)
             if name == "j2_column" and world <= 6:
                 grid = (1, 1, world)
         else:
             grid = (1, world) if world <= 2 else (2, world // 2)
-        subs = P.split_model(m, P.block_epart(ne, grid), world)
+        if ne is not None:
+            subs = P.split_model(m, P.block_epart(ne, grid), world)
         s = subs[rank]
         d = capi.DeviceModel(s, device=local, comm=(rank, world, bytes(uid.cpu().numpy())))
         d.step(1, m.nt, True)
         U = d.get_state(0)
         rec = d.read_recorder(0) if len(s.rec_nodes) else np.zeros((m.nt - 1, 0))
         nd = m.ndim
-        gd = (s.global_nodes[:, None] * nd + np.arange(nd)[None, :]).ravel()
+        gd = np.concatenate([np.arange(m.node_ptr[n], m.node_ptr[n + 1]) for n in s.global_nodes])    # PML nodes: 9 / 5 dofs
+        rec_w = [int(s.node_ndof[n]) for n in s.rec_nodes]
         gathered = [None] * world
-        dist.all_gather_object(gathered, (gd, U, s.rec_global, rec, d.counters()))
+        dist.all_gather_object(gathered, (gd, U, s.rec_global, rec, d.counters(), rec_w))
         d.close()
         if rank == 0:
             from oracle_lib import Oracle
             ref, Uref = Oracle().run(m)
             Ug = np.full(m.n_total, np.nan)
             spread = 0.0
-            for gd_r, U_r, _, _, _ in gathered:
+            for gd_r, U_r, *_ in gathered:
                 seen = ~np.isnan(Ug[gd_r])
                 if seen.any():
                     spread = max(spread, np.abs(Ug[gd_r][seen] - U_r[seen]).max())   # replicas must agree bit for bit
@@ -70,9 +78,10 @@ def main():
             err_u = np.abs(Ug - Uref).max() / np.abs(Uref).max()
             # recorder columns back in the global recorder order
             cols = {}
-            for _, _, rg, rc, _ in gathered:
+            for _, _, rg, rc, _, rw in gathered:
+                off = np.concatenate([[0], np.cumsum(rw)]).astype(int)
                 for i, n in enumerate(rg):
-                    cols[int(n)] = rc[:, nd * i:nd * (i + 1)]
+                    cols[int(n)] = rc[:, off[i]:off[i + 1]]
             out = np.concatenate([cols[int(n)] for n in m.rec_nodes], axis=1)
             err_r = cases.rel_err(out, ref)
             tol = cases.TOL[name]

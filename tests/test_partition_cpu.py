@@ -188,3 +188,63 @@ def test_split_carries_equal_constraints_and_mirrors_pml_halos(case, grid):
             assert (a == b).all() and (np.diff(a) > 0).all()
         assert any((s.node_ndof[nodes] > m.ndim).any() for nodes in s.halos.values())      # PML nodes on the cut
     assert seen == set(glob)
+
+
+@pytest.mark.parametrize("case,grid", [("pml2d", (2, 2)), ("pml3d", (2, 2, 2)), ("pml3d", (1, 1, 3))])
+def test_pml_block_unknowns_shared_between_ranks_are_mirror_images(case, grid):
+    """What the multi-rank PML block solve relies on (planner.cu: hp.unk lists, halo.cu: pmlx_setup): walking a halo list
+    in its declared order and keeping the dofs that CARRY a block unknown -- free dofs of 9- / 5-dof PML nodes and soil
+    dofs that are the master of a tie present in the partition -- gives the same (global node, component) sequence on both
+    sides of every pair of ranks; and every unknown is owned (lowest holder) by exactly one rank."""
+    m = cases.CASES[case]()
+    n = int(np.prod(grid))
+    subs = P.split_model(m, P.centroid_epart(m, grid), n)
+    want = 9 if m.ndim == 3 else 5
+
+    def carriers(s):
+        fd = np.asarray(s.freedof_flat)
+        total_of_free = {int(f): q for q, f in enumerate(fd) if f > -1}
+        car = np.zeros(s.n_total, dtype=bool)
+        for nd_ in np.nonzero(s.node_ndof == want)[0]:
+            q = np.arange(s.node_ptr[nd_], s.node_ptr[nd_ + 1])
+            car[q[fd[q] > -1]] = True
+        for _, _, ms, _ in s.constraints:
+            car[total_of_free[ms[0]]] = True
+        return car
+
+    car = [carriers(s) for s in subs]
+    seqs = {}
+    for r, s in enumerate(subs):
+        for peer, nodes in s.halos.items():
+            seq = []
+            for nd_ in nodes:
+                for k, q in enumerate(range(s.node_ptr[nd_], s.node_ptr[nd_ + 1])):
+                    if car[r][q]:
+                        seq.append((int(s.global_nodes[nd_]), k))
+            seqs[(r, peer)] = seq
+    assert any(len(v) for v in seqs.values())
+    for (r, peer), seq in seqs.items():
+        assert seq == seqs[(peer, r)]
+    # ownership: the global carrier set is covered exactly once by the lowest holders
+    owned = {}
+    for r, s in enumerate(subs):
+        lower = set()
+        for peer, nodes in s.halos.items():
+            if peer < r:
+                lower.update(x for x in seqs[(r, peer)])
+        for nd_ in range(s.n_nodes):
+            for k, q in enumerate(range(s.node_ptr[nd_], s.node_ptr[nd_ + 1])):
+                if car[r][q] and (int(s.global_nodes[nd_]), k) not in lower:
+                    key = (int(s.global_nodes[nd_]), k)
+                    assert key not in owned, key
+                    owned[key] = r
+    gfd = np.asarray(m.freedof_flat)
+    g_total_of_free = {int(f): q for q, f in enumerate(gfd) if f > -1}
+    gcar = np.zeros(m.n_total, dtype=bool)
+    for nd_ in np.nonzero(m.node_ndof == want)[0]:
+        q = np.arange(m.node_ptr[nd_], m.node_ptr[nd_ + 1])
+        gcar[q[gfd[q] > -1]] = True
+    for _, _, ms, _ in m.constraints:
+        gcar[g_total_of_free[ms[0]]] = True
+    node_of_total = np.repeat(np.arange(m.n_nodes), np.diff(m.node_ptr))
+    assert set(owned) == {(int(node_of_total[q]), int(q - m.node_ptr[node_of_total[q]])) for q in np.nonzero(gcar)[0]}
