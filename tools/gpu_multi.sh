@@ -6,6 +6,9 @@ mkdir -p $O
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 timeout 600 $TR --master-port 29511 tests/multigpu_check.py > $O/check_n$N.log 2>&1; echo "check exit $?" >> $O/check_n$N.log
 grep -E "multigpu|exit" $O/check_n$N.log | tail -12
+# opt-in cases: PML models across ranks (see tests/multigpu_check.py)
+SVL_MULTIGPU_PML=1 timeout 600 $TR --master-port 29514 tests/multigpu_check.py > $O/check_pml_n$N.log 2>&1; echo "check(pml) exit $?" >> $O/check_pml_n$N.log
+grep -E "pml|exit" $O/check_pml_n$N.log | tail -6
 timeout 900 $TR --master-port 29512 bench.py --gpus $N --steps 100 --warmup 5 > $O/bench_weak_n$N.json 2> $O/bench_weak_n$N.err
 timeout 600 $TR --master-port 29513 bench.py --gpus $N --steps 200 --warmup 10 --scaling strong > $O/bench_strong_n$N.json 2> $O/bench_strong_n$N.err
 python - <<PY
