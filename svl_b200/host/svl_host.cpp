@@ -1,6 +1,9 @@
 // svl_host.cpp -- the reference's run-time, re-hosted on libsvlgpu (C++17, no third-party dependencies).
 //
-//   SeismoVLAB_gpu.exe -dir <Partition dir> -file '<name>.$.json'
+//   SeismoVLAB_gpu.exe -dir <Partition dir> -file '<name>.$.json'                    one partition, one GPU
+//   SeismoVLAB_gpu.exe -np N -dir <Partition dir> -file '<name>.$.json'              N partitions, one process per GPU
+//     (what `mpirun -np N SeismoVLAB.exe ...` is for the reference; -np forks the ranks itself, or start the N processes
+//      yourself with RANK / LOCAL_RANK / WORLD_SIZE set, e.g. under torchrun; `-plan` stops after the partition plan)
 //
 // keeps the outer boundary of SeismoVLAB.exe verbatim: the same command line
 // (12-Utilities/Utilities.hpp:97-161; '$' -> rank, Driver.hpp:250-276), the same per-rank JSON partition files
@@ -22,6 +25,10 @@
 #include <sstream>
 #include <string>
 #include <strings.h>
+#include <sys/wait.h>
+#include <time.h>
+#include <tuple>
+#include <unistd.h>
 #include <vector>
 
 #include "../../include/svlgpu.h"
@@ -44,7 +51,8 @@ std::vector<std::pair<long, const JValue *>> by_tag(const JValue &o) {
 // ---- Geometry module (01-Node ... 06-Mesh): plain data, the device owns the arithmetic ----------------------
 struct Node {            // 01-Node/Node.cpp:3-21
     unsigned tag; int index; int ndof;
-    std::vector<int> total, free;
+    std::vector<int> total, free;        // as in the file: GLOBAL numbers when the model is partitioned
+    std::vector<int> ltotal, lfree;      // this partition's own compact numbering (several ranks only; else empty)
     std::vector<double> coords;
 };
 struct Material { unsigned tag; int index; int kind; std::vector<double> par; };      // 02-Materials/Material.hpp
@@ -63,7 +71,10 @@ struct RecorderSpec { std::string name, file, resp; int precision = 6, nsample =
 class Mesh {             // 06-Mesh/Mesh.cpp
   public:
     int ndim = 3, ntotal = 0, nfree = 0;
+    int ntotal_dev = 0, nfree_dev = 0;   // what the device model is built with: the partition's own counts (== ntotal / nfree on one rank)
     bool lumped = true;
+    bool pml_collective = false;         // several ranks and PML nodes anywhere in the model: every rank joins the block solve
+    std::map<int, std::vector<int32_t>> Halos;                                             // peer rank -> shared nodes (device indices)
     std::map<unsigned, Node> Nodes;
     std::map<unsigned, Material> Materials;
     std::map<unsigned, Element> Elements;
@@ -74,11 +85,12 @@ class Mesh {             // 06-Mesh/Mesh.cpp
 };
 
 // ---- Driver (12-Utilities/Driver.hpp UpdateMesh :1981-2046) ------------------------------------------------------------
-bool UpdateMesh(Mesh &mesh, const JValue &J) {
+bool UpdateMesh(Mesh &mesh, const JValue &J, bool geometry_only = false) {
     const JValue &G = J["Global"];
     mesh.ndim = G["ndim"].as_int(3);
     mesh.ntotal = G["ntotal"].as_int();
     mesh.nfree = G["nfree"].as_int();
+    mesh.ntotal_dev = mesh.ntotal; mesh.nfree_dev = mesh.nfree;
     mesh.lumped = ieq(G["massform"].as_string("LUMPED"), "LUMPED");
     int idx = 0;
     for (auto &kv : by_tag(J["Nodes"])) {
@@ -90,6 +102,14 @@ bool UpdateMesh(Mesh &mesh, const JValue &J) {
         for (auto &v : (*kv.second)["coords"].arr) n.coords.push_back(v.as_double());
         mesh.Nodes[n.tag] = n;
     }
+    for (auto &kv : J["Constraints"].obj) {
+        const long tag = std::strtol(kv.first.c_str(), nullptr, 10);
+        std::vector<int> mt; std::vector<double> f;
+        for (auto &x : kv.second["mtag"].arr) mt.push_back(x.as_int());
+        for (auto &x : kv.second["factor"].arr) f.push_back(x.as_double());
+        mesh.Constraints[tag] = std::make_tuple(kv.second["stag"].as_int(), mt, f);
+    }
+    if (geometry_only) return false;     // a peer's file: only its nodes and ties matter here
     idx = 0;
     for (auto &kv : by_tag(J["Materials"])) {
         Material m;
@@ -108,13 +128,6 @@ bool UpdateMesh(Mesh &mesh, const JValue &J) {
         std::vector<double> v;
         for (auto &x : (*kv.second)["mass"].arr) v.push_back(x.as_double());
         mesh.Masses[(unsigned)kv.first] = v;
-    }
-    for (auto &kv : J["Constraints"].obj) {
-        const long tag = std::strtol(kv.first.c_str(), nullptr, 10);
-        std::vector<int> mt; std::vector<double> f;
-        for (auto &x : kv.second["mtag"].arr) mt.push_back(x.as_int());
-        for (auto &x : kv.second["factor"].arr) f.push_back(x.as_double());
-        mesh.Constraints[tag] = std::make_tuple(kv.second["stag"].as_int(), mt, f);
     }
     idx = 0;
     for (auto &kv : by_tag(J["Elements"])) {
@@ -165,6 +178,127 @@ bool UpdateMesh(Mesh &mesh, const JValue &J) {
     return false;
 }
 
+// ---- several ranks -------------------------------------------------------------------------------------------------------
+// The reference's ranks meet in one globally numbered system (Global.ntotal / nfree, MumpsSolver.cpp:56,161).  Here every
+// rank drives its own GPU with its own compact numbering and exchanges interface values with the ranks that share nodes
+// with it, so three things are derived from the per-rank files (all ranks read all files and derive the same answer):
+//   (i)  tie closure: the pre-processor gives a partition the master nodes of the constraints whose slave it holds
+//        (SeismoVLAB.py:381-392); the device also wants the slave wherever the master is, so that every replica of a tied
+//        dof resolves to the same unknown -- missing nodes / constraints are copied from the rank that has them;
+//   (ii) local total / free numbers (ascending node tag, then dof);
+//   (iii) per peer: the shared node tags, ascending -- svlgpu_add_halo wants mirror-image lists.
+bool PlanPartitions(std::vector<Mesh> &all, int rank) {
+    const int world = (int)all.size();
+    Mesh &me = all[rank];
+    std::map<unsigned, const Node *> catalog;                       // any copy of a node (replicas are identical)
+    std::map<long, std::tuple<int, std::vector<int>, std::vector<double>>> ties;
+    for (auto &m : all) {
+        for (auto &kv : m.Nodes) catalog.emplace(kv.first, &kv.second);
+        for (auto &kv : m.Constraints) ties.emplace(kv.first, kv.second);
+    }
+    std::map<int, unsigned> node_of_total, node_of_free;
+    for (auto &kv : catalog)
+        for (size_t k = 0; k < kv.second->total.size(); k++) {
+            node_of_total[kv.second->total[k]] = kv.first;
+            if (kv.second->free[k] >= 0) node_of_free[kv.second->free[k]] = kv.first;
+        }
+    struct Tie { long tag; std::vector<unsigned> nodes; };
+    std::vector<Tie> tl;
+    for (auto &kv : ties) {
+        Tie t; t.tag = kv.first;
+        auto &[stag, mt, f] = kv.second;
+        if (!node_of_total.count(stag)) { std::cout << "\x1B[31m ERROR: \x1B[0mconstraint " << kv.first << ": slave dof not found in any partition\n"; return true; }
+        t.nodes.push_back(node_of_total[stag]);
+        for (int m : mt) {
+            if (!node_of_free.count(m)) { std::cout << "\x1B[31m ERROR: \x1B[0mconstraint " << kv.first << ": master dof not found in any partition\n"; return true; }
+            t.nodes.push_back(node_of_free[m]);
+        }
+        tl.push_back(t);
+    }
+    for (auto &m : all) {
+        bool changed = true;
+        while (changed) {
+            changed = false;
+            for (auto &t : tl) {
+                bool any = false, allp = true;
+                for (unsigned n : t.nodes) { const bool h = m.Nodes.count(n) != 0; any |= h; allp &= h; }
+                if (!any) continue;
+                if (!allp) { for (unsigned n : t.nodes) if (!m.Nodes.count(n)) m.Nodes[n] = *catalog.at(n); changed = true; }
+                if (!m.Constraints.count(t.tag)) m.Constraints[t.tag] = ties.at(t.tag);
+            }
+        }
+        int idx = 0;
+        for (auto &kv : m.Nodes) kv.second.index = idx++;         // ascending tag, as UpdateMesh numbers them
+    }
+    // local numbering of this rank
+    std::map<int, int> ltot, lfre;
+    for (auto &kv : me.Nodes) {
+        Node &n = kv.second;
+        n.ltotal.clear(); n.lfree.clear();
+        for (size_t k = 0; k < n.total.size(); k++) {
+            n.ltotal.push_back((int)ltot.size()); ltot[n.total[k]] = n.ltotal.back();
+            if (n.free[k] >= 0) { n.lfree.push_back((int)lfre.size()); lfre[n.free[k]] = n.lfree.back(); }
+            else n.lfree.push_back(n.free[k]);
+        }
+    }
+    me.ntotal_dev = (int)ltot.size(); me.nfree_dev = (int)lfre.size();
+    for (auto &kv : me.Constraints) {
+        auto &[stag, mt, f] = kv.second;
+        stag = ltot.at(stag);
+        for (int &m : mt) m = lfre.at(m);
+    }
+    const int pml_ndof = me.ndim == 3 ? 9 : 5;
+    for (auto &kv : catalog) if (kv.second->ndof == pml_ndof) me.pml_collective = true;
+    for (int q = 0; q < world; q++) {
+        if (q == rank) continue;
+        std::vector<int32_t> shared;
+        auto a = me.Nodes.begin();
+        auto b = all[q].Nodes.begin();
+        while (a != me.Nodes.end() && b != all[q].Nodes.end()) {
+            if (a->first < b->first) ++a;
+            else if (b->first < a->first) ++b;
+            else { shared.push_back(a->second.index); ++a; ++b; }
+        }
+        if (!shared.empty()) me.Halos[q] = shared;
+    }
+    return false;
+}
+void PrintPlan(const Mesh &me, int rank) {
+    std::cout << "PLAN rank " << rank << " nodes " << me.Nodes.size() << " ntotal " << me.ntotal_dev << " nfree " << me.nfree_dev
+              << " constraints " << me.Constraints.size() << " pml_collective " << (me.pml_collective ? 1 : 0) << "\n";
+    std::vector<unsigned> tag_of;
+    for (auto &kv : me.Nodes) tag_of.push_back(kv.first);
+    for (auto &kv : me.Halos) {
+        unsigned long long h = 1469598103934665603ull;             // FNV-1a over the shared tags
+        for (int32_t i : kv.second) { h ^= tag_of[i]; h *= 1099511628211ull; }
+        std::cout << "PLAN rank " << rank << " peer " << kv.first << " shared " << kv.second.size() << " hash " << h << "\n";
+    }
+}
+
+// NCCL bootstrap without MPI: rank 0 drops the unique id into the partition directory, the others pick it up
+std::string NcclIdPath(const std::string &dir) {
+    const char *job = getenv("SVLGPU_JOB_ID");
+    if (!job) job = getenv("MASTER_PORT");
+    return dir + "/.svlgpu_nccl_id." + (job ? job : "0");
+}
+bool ExchangeNcclId(const std::string &dir, int rank, char id[128]) {
+    const std::string path = NcclIdPath(dir);
+    if (rank == 0) {
+        if (svlgpu_nccl_unique_id(id)) return true;
+        const std::string tmp = path + ".tmp";
+        { std::ofstream f(tmp, std::ios::binary); f.write(id, 128); }
+        return std::rename(tmp.c_str(), path.c_str()) != 0;
+    }
+    for (int tries = 0; tries < 3000; tries++) {                     // up to 5 minutes: rank 0 may still be parsing
+        std::ifstream f(path, std::ios::binary);
+        if (f.is_open() && f.read(id, 128) && f.gcount() == 128) return false;
+        struct timespec ts = {0, 100000000};
+        nanosleep(&ts, nullptr);
+    }
+    std::cout << "\x1B[31m ERROR: \x1B[0mrank " << rank << " did not find the NCCL id file " << path << "\n";
+    return true;
+}
+
 // ---- Assembler (07-Assembler/Assembler.cpp): host-vector access to the device passes -------------------------------
 class Assembler {
   public:
@@ -193,11 +327,12 @@ class CentralDifference {
         for (auto &kv : mesh.Nodes) {
             const Node &n = kv.second;
             ndof.push_back(n.ndof);
-            total.insert(total.end(), n.total.begin(), n.total.end());
-            freed.insert(freed.end(), n.free.begin(), n.free.end());
+            const std::vector<int> &tt = n.ltotal.empty() ? n.total : n.ltotal, &ff = n.lfree.empty() ? n.free : n.lfree;
+            total.insert(total.end(), tt.begin(), tt.end());
+            freed.insert(freed.end(), ff.begin(), ff.end());
             for (int c = 0; c < mesh.ndim; c++) xyz.push_back(c < (int)n.coords.size() ? n.coords[c] : 0.0);
         }
-        if (svlgpu_set_nodes(h, (int)ndof.size(), ndof.data(), xyz.data(), total.data(), freed.data(), mesh.ntotal, mesh.nfree)) return fail();
+        if (svlgpu_set_nodes(h, (int)ndof.size(), ndof.data(), xyz.data(), total.data(), freed.data(), mesh.ntotal_dev, mesh.nfree_dev)) return fail();
         for (auto &kv : mesh.Masses) {
             const int32_t node = mesh.Nodes.at(kv.first).index;
             if (svlgpu_add_nodal_mass(h, 1, &node, kv.second.data())) return fail();
@@ -250,7 +385,18 @@ class CentralDifference {
             if (svlgpu_add_node_recorder(h, field, (int)nodes.size(), nodes.data(), nt) < 0) return fail();
         }
         if (newmark && svlgpu_set_option(h, "integrator", 1.0)) return fail();
+        for (auto &kv : mesh.Halos)
+            if (svlgpu_add_halo(h, kv.first, (int)kv.second.size(), kv.second.data())) return fail();
+        if (mesh.pml_collective && !mesh.Halos.empty() && svlgpu_set_option(h, "pml_collective", 1.0)) return fail();
         if (svlgpu_finalize(h, dt, device)) return fail();
+        return false;
+    }
+    // several ranks: joins the NCCL communicator (svlgpu_comm_init sums the interface mass / damping diagonals)
+    bool JoinRanks(const std::string &dir, int rank, int world) {
+        char id[128];
+        if (ExchangeNcclId(dir, rank, id)) return true;
+        if (svlgpu_comm_init(h, id, rank, world)) return fail();
+        if (rank == 0) std::remove(NcclIdPath(dir).c_str());       // every rank has read it: comm_init is collective
         return false;
     }
 
@@ -258,9 +404,9 @@ class CentralDifference {
     // CommitState, recorder row) happens on the device
     bool ComputeNewStep(unsigned k) { return svlgpu_step(h, (int)k, (int)k + 1, 0) != 0 && fail(); }
     bool ComputeSteps(unsigned k0, unsigned k1) { return svlgpu_step(h, (int)k0, (int)k1, 1) != 0 && fail(); }
-    bool GetDisplacements(std::vector<double> &U) { U.assign(mesh.ntotal, 0.0); return svlgpu_get_state(h, SVLGPU_DISP, nullptr, 0, U.data()) != 0; }
-    bool GetVelocities(std::vector<double> &V) { V.assign(mesh.ntotal, 0.0); return svlgpu_get_state(h, SVLGPU_VEL, nullptr, 0, V.data()) != 0; }
-    bool GetAccelerations(std::vector<double> &A) { A.assign(mesh.ntotal, 0.0); return svlgpu_get_state(h, SVLGPU_ACCEL, nullptr, 0, A.data()) != 0; }
+    bool GetDisplacements(std::vector<double> &U) { U.assign(mesh.ntotal_dev, 0.0); return svlgpu_get_state(h, SVLGPU_DISP, nullptr, 0, U.data()) != 0; }
+    bool GetVelocities(std::vector<double> &V) { V.assign(mesh.ntotal_dev, 0.0); return svlgpu_get_state(h, SVLGPU_VEL, nullptr, 0, V.data()) != 0; }
+    bool GetAccelerations(std::vector<double> &A) { A.assign(mesh.ntotal_dev, 0.0); return svlgpu_get_state(h, SVLGPU_ACCEL, nullptr, 0, A.data()) != 0; }
 
   private:
     bool fail() { std::cout << "\x1B[31m ERROR: \x1B[0m" << svlgpu_last_error() << "\n"; return true; }
@@ -372,21 +518,62 @@ std::string read_file(const std::string &path) {
 int main(int argc, char **argv) {
     std::string dir = ".";
     std::vector<std::string> files;
+    int np = 0;
+    bool plan_only = false;
     for (int i = 1; i < argc; i++) {                                     // Utilities.hpp:97-161
         if (ieq(argv[i], "-dir") && i + 1 < argc) dir = argv[++i];
         else if (ieq(argv[i], "-file")) { while (i + 1 < argc && argv[i + 1][0] != '-') files.push_back(argv[++i]); }
+        else if (ieq(argv[i], "-np") && i + 1 < argc) np = atoi(argv[++i]);
+        else if (ieq(argv[i], "-plan")) plan_only = true;
     }
-    if (files.empty()) { std::cout << " usage: SeismoVLAB_gpu.exe -dir <Partition dir> -file '<name>.$.json'\n"; return 1; }
-    const char *rk = getenv("RANK"), *lr = getenv("LOCAL_RANK");
-    const int rank = rk ? atoi(rk) : 0, device = lr ? atoi(lr) : 0;
+    if (files.empty()) { std::cout << " usage: SeismoVLAB_gpu.exe [-np N] -dir <Partition dir> -file '<name>.$.json'\n"; return 1; }
+    if (np > 1) {
+        // the launcher `mpirun -np N` is for the reference: one child per rank / GPU, forked before any CUDA call
+        const std::string job = std::to_string((long)getpid()) + "." + std::to_string((long)time(nullptr));
+        std::vector<pid_t> kids;
+        for (int r = 0; r < np; r++) {
+            const pid_t pid = fork();
+            if (pid < 0) { std::cout << "\x1B[31m ERROR: \x1B[0mfork failed\n"; return 1; }
+            if (pid == 0) {
+                setenv("RANK", std::to_string(r).c_str(), 1);
+                setenv("LOCAL_RANK", std::to_string(r).c_str(), 1);
+                setenv("WORLD_SIZE", std::to_string(np).c_str(), 1);
+                setenv("SVLGPU_JOB_ID", job.c_str(), 1);
+                np = 0;
+                kids.clear();
+                break;
+            }
+            kids.push_back(pid);
+        }
+        if (!kids.empty()) {
+            int worst = 0;
+            for (pid_t k : kids) { int st = 0; waitpid(k, &st, 0); worst = std::max(worst, WIFEXITED(st) ? WEXITSTATUS(st) : 1); }
+            return worst;
+        }
+    }
+    const char *rk = getenv("RANK"), *lr = getenv("LOCAL_RANK"), *ws = getenv("WORLD_SIZE");
+    const int rank = rk ? atoi(rk) : 0, device = lr ? atoi(lr) : 0, world = ws ? std::max(1, atoi(ws)) : 1;
     try {
-        for (std::string file : files) {                                 // staged analyses run in sequence (Driver.hpp:2058-2100)
-            const size_t pos = file.find('$');
-            if (pos != std::string::npos) file.replace(pos, 1, std::to_string(rank));
+        for (std::string pattern : files) {                              // staged analyses run in sequence (Driver.hpp:2058-2100)
+            auto file_of = [&](int r) {
+                std::string f = pattern;
+                const size_t pos = f.find('$');
+                if (pos != std::string::npos) f.replace(pos, 1, std::to_string(r));
+                return f;
+            };
+            const std::string file = file_of(rank);
             const std::string text = read_file(dir + "/" + file);
             const JValue J = svlhost::JParser(text).parse();
-            Mesh mesh;
+            std::vector<Mesh> all(world);
+            Mesh &mesh = all[rank];
             if (UpdateMesh(mesh, J)) return 1;
+            if (world > 1) {
+                if (pattern.find('$') == std::string::npos) { std::cout << "\x1B[31m ERROR: \x1B[0mseveral ranks need a '$' in -file\n"; return 1; }
+                for (int q = 0; q < world; q++)
+                    if (q != rank && UpdateMesh(all[q], svlhost::JParser(read_file(dir + "/" + file_of(q))).parse(), true)) return 1;
+                if (PlanPartitions(all, rank)) return 1;
+            }
+            if (plan_only) { PrintPlan(mesh, rank); continue; }
             // combination / recorders / simulation (Driver.hpp:1930-1975, 1859-1925, 1748-1856)
             const JValue &S = J["Simulations"];
             const unsigned comboTag = (unsigned)S["combo"].as_int(1);
@@ -420,6 +607,7 @@ int main(int argc, char **argv) {
             }
             CentralDifference integrator(mesh, dt, newmark);
             if (integrator.Initialize(combo, specs, (int)nt, device)) return 1;
+            if (world > 1 && integrator.JoinRanks(dir, rank, world)) return 1;
             std::vector<Recorder> recorders;
             for (size_t i = 0; i < specs.size(); i++) recorders.emplace_back(specs[i], (int)i);
             DynamicAnalysis analysis(mesh, integrator, recorders, nt);

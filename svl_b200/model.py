@@ -308,7 +308,8 @@ def add_base_dashpots(m: Model, vs: float, vp: float, rho: float, h: float, th: 
 # reference JSON writer (Core/SeismoVLAB.py:49-298, Outputs.py:29-51)
 # -------------------------------------------------------------------------------
 def write_reference_json(m: Model, directory: str, name: str = "Model", combo: str = "Run",
-                         resp=("disp",), integrator: str = "CENTRALDIFFERENCE", ndps: int = 16, newton=None) -> str:
+                         resp=("disp",), integrator: str = "CENTRALDIFFERENCE", ndps: int = 16, newton=None,
+                         _return_entities: bool = False) -> str:
     """Writes <directory>/Partition/<name>.1.0.json (+ load / .drm text files) in the schema the
     reference executable reads.  Tags are index+1.  Returns the partition directory."""
     part = os.path.join(directory, "Partition")
@@ -409,8 +410,75 @@ def write_reference_json(m: Model, directory: str, name: str = "Model", combo: s
                       {"name": "NEWTON", "cnvgtol": float(newton[0]), "nstep": int(newton[1]), "cnvgtest": int(newton[2])}),
         "integrator": {"name": integrator, "dt": float(m.dt), "ktol": 1e-12, "mtol": 1e-12, "ftol": 1e-12},
         "solver": {"name": "EIGEN", "update": 1 if newton is None else 0}}}
+    if _return_entities:
+        return part, J
     with open(os.path.join(part, f"{name}.1.0.json"), "w") as f:
         json.dump(J, f, indent=4)
+    return part
+
+
+def write_reference_partitions(m: Model, epart, nparts: int, directory: str, name: str = "Model", combo: str = "Run",
+                               resp=("disp",), integrator: str = "CENTRALDIFFERENCE", ndps: int = 16) -> str:
+    """One JSON file per rank, <directory>/Partition/<name>.1.<rank>.json, the way the reference pre-processor splits a model
+    after METIS (Core/SeismoVLAB.py:300-420 createPartitions, :49-298 Entities2Processor): GLOBAL tags and GLOBAL total /
+    free dof numbers everywhere (`Global.ntotal / nfree` are the whole model's), a partition holds the nodes of its elements
+    plus the master nodes of the constraints whose slave dofs it holds (:381-392), nodal masses and the nodes of a point load
+    go to the first partition that holds them (:117-122, :163-180), NODE recorders list the partition's own nodes and write
+    `<resp>.<rank>.out` (:237-246), combinations keep the loads present in the partition.  `epart[e]` is the rank of element e
+    (elements beyond len(epart), e.g. dashpots, follow partition.split_model's rule).  Returns the partition directory."""
+    from . import partition as P
+    part, J = write_reference_json(m, directory, name, combo, resp, integrator, ndps, _return_entities=True)
+    subs = P.split_model(m, epart, nparts, tie_closure="slave")       # element / node sets only; numbering stays global here
+    taken_mass, taken_load = set(), {k: set() for k in J["Loads"]}
+    for r, s in enumerate(subs):
+        ntags = [int(n) + 1 for n in s.global_nodes]
+        nset = set(ntags)
+        etags = [int(e) + 1 for e in s.global_elems]
+        eset = set(etags)
+        K = {"Global": J["Global"], "Materials": J["Materials"]}
+        K["Nodes"] = {str(t): J["Nodes"][str(t)] for t in ntags}
+        masses = {t: v for t, v in J.get("Masses", {}).items() if int(t) in nset and t not in taken_mass}
+        taken_mass.update(masses)
+        if masses:
+            K["Masses"] = masses
+        cons = {}
+        for t in ntags:
+            for f in J["Nodes"][str(t)]["freedof"]:
+                if f < -1:
+                    cons[str(f)] = J["Constraints"][str(f)]
+        if cons:
+            K["Constraints"] = cons
+        K["Elements"] = {str(t): J["Elements"][str(t)] for t in etags}
+        K["Dampings"] = {}
+        for d, D in J["Dampings"].items():
+            lst = [t for t in D["attributes"]["list"] if t in eset]
+            if lst:
+                K["Dampings"][d] = {"name": D["name"], "attributes": dict(D["attributes"], list=lst)}
+        loads = {}
+        for l, L in J["Loads"].items():
+            if L["name"] == "POINTLOAD":
+                lst = sorted(t for t in L["attributes"]["list"] if t in nset and t not in taken_load[l])
+                taken_load[l].update(lst)
+            else:
+                lst = sorted(t for t in L["attributes"]["list"] if t in eset)
+            if lst:
+                loads[l] = {"name": L["name"], "attributes": dict(L["attributes"], list=lst)}
+        if loads:
+            K["Loads"] = loads
+        C = J["Combinations"]["1"]
+        keep = [(l, f) for l, f in zip(C["attributes"]["load"], C["attributes"]["factor"]) if str(l) in loads]
+        K["Combinations"] = {"1": {"name": C["name"], "attributes": (
+            {"folder": C["attributes"]["folder"], "load": [l for l, _ in keep], "factor": [f for _, f in keep]} if keep else {})}}
+        recs = {}
+        for q, R in J["Recorders"].items():
+            lst = sorted(t for t in R["list"] if t in nset)
+            if lst:
+                recs[q] = dict(R, file=R["file"].replace(".0.out", f".{r}.out"), list=lst)
+        if recs:
+            K["Recorders"] = recs
+        K["Simulations"] = J["Simulations"]
+        with open(os.path.join(part, f"{name}.1.{r}.json"), "w") as f:
+            json.dump(K, f, indent=4)
     return part
 
 

@@ -71,9 +71,12 @@ def read_epart(path: str) -> np.ndarray:
     return np.loadtxt(path, dtype=np.int32)
 
 
-def split_model(m: Model, epart: np.ndarray, nparts: int) -> List[Model]:
+def split_model(m: Model, epart: np.ndarray, nparts: int, tie_closure: str = "both") -> List[Model]:
     """Global model + element partition -> one sub-model per rank, each carrying
-    `.halos = {peer: local node indices}`, `.global_nodes`, `.global_elems`."""
+    `.halos = {peer: local node indices}`, `.global_nodes`, `.global_elems`.
+    tie_closure: "both" (what the device needs: a partition that holds the slave OR a master of an EQUAL constraint gets all
+    of its nodes) or "slave" (what the reference pre-processor writes: only the partition of the slave gets the masters,
+    SeismoVLAB.py:381-392; the host driver completes the closure when it reads the files)."""
     kinds = np.unique(m.elem_kind)
     npe_e = np.array([ELEM_NODES[int(k)] for k in kinds], dtype=np.int32)[np.searchsorted(kinds, m.elem_kind)]
 
@@ -125,8 +128,11 @@ def split_model(m: Model, epart: np.ndarray, nparts: int) -> List[Model]:
                 ha, hb = have[ta], have[tb]
                 if (ha == hb).all():
                     break
-                have[ta[hb]] = True
+                if tie_closure == "both":
+                    have[ta[hb]] = True
                 have[tb[ha]] = True
+                if tie_closure != "both":
+                    break
             node_sets[r] = np.nonzero(have)[0]
     pml_anywhere = bool(np.isin(m.elem_kind, (3, 4)).any())
     # owner of a node = lowest rank that holds it

@@ -248,3 +248,49 @@ def test_pml_block_unknowns_shared_between_ranks_are_mirror_images(case, grid):
         gcar[g_total_of_free[ms[0]]] = True
     node_of_total = np.repeat(np.arange(m.n_nodes), np.diff(m.node_ptr))
     assert set(owned) == {(int(node_of_total[q]), int(q - m.node_ptr[node_of_total[q]])) for q in np.nonzero(gcar)[0]}
+
+
+def _fnv(tags):
+    h = 1469598103934665603
+    for t in tags:
+        h ^= int(t)
+        h = (h * 1099511628211) % (1 << 64)
+    return h
+
+
+@pytest.mark.parametrize("case,nparts,how", [("kat444", 8, "block"), ("lysmer_column", 4, "block"), ("pml3d", 2, "centroid"),
+                                             ("pml2d", 3, "random"), ("pml3d", 4, "random")])
+def test_host_driver_plans_reference_partition_files_like_the_partitioner(tmp_path, case, nparts, how):
+    """The C++ host driver in several-rank mode (`SeismoVLAB_gpu.exe -np N -plan`, no GPU touched): per-rank JSON files in the
+    reference's schema (GLOBAL tags / dof numbers, masters travel with slaves only: write_reference_partitions mirrors
+    createPartitions, SeismoVLAB.py:300-420) -> tie closure, compact local numbering, mirror-image shared-node lists.  Must
+    equal what partition.split_model derives from the global model.  The random partitions put masters and slaves on
+    different ranks, so the driver's own closure is exercised."""
+    import subprocess
+    from svl_b200 import model as M
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "svl_b200", "SeismoVLAB_gpu.exe")
+    assert os.path.exists(exe), "host driver not built: python -c 'import __graft_entry__ as g; g.build()'"
+    m = cases.CASES[case]()
+    if how == "block":
+        ne = {"kat444": (4, 4, 4), "lysmer_column": (3, 3, 6)}[case]
+        ep = P.block_epart(ne, P.proc_grid(nparts) if nparts == 8 else (2, 1, 2))
+    elif how == "centroid":
+        ep = P.centroid_epart(m, (1, 1, nparts))
+    else:
+        ep = np.random.default_rng(5).integers(0, nparts, m.n_elem).astype(np.int32)
+    part = M.write_reference_partitions(m, ep, nparts, str(tmp_path))
+    out = subprocess.run([exe, "-np", str(nparts), "-plan", "-dir", part, "-file", "Model.1.$.json"],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    got = sorted(l for l in out.stdout.splitlines() if l.startswith("PLAN"))
+    subs = P.split_model(m, ep, nparts)
+    want = []
+    for r, s in enumerate(subs):
+        want.append(f"PLAN rank {r} nodes {s.n_nodes} ntotal {s.n_total} nfree {s.n_free} constraints {len(s.constraints)} "
+                    f"pml_collective {int(s.pml_collective)}")
+        for peer, nodes in sorted(s.halos.items()):
+            want.append(f"PLAN rank {r} peer {peer} shared {len(nodes)} hash {_fnv(s.global_nodes[nodes] + 1)}")
+    assert got == sorted(want)
+    if how == "random":
+        slave_only = P.split_model(m, ep, nparts, tie_closure="slave")
+        assert sum(b.n_nodes - a.n_nodes for a, b in zip(slave_only, subs)) > 0      # the closure had work to do

@@ -9,6 +9,9 @@ grep -E "multigpu|exit" $O/check_n$N.log | tail -12
 # opt-in cases: PML models across ranks (see tests/multigpu_check.py)
 SVL_MULTIGPU_PML=1 timeout 600 $TR --master-port 29514 tests/multigpu_check.py > $O/check_pml_n$N.log 2>&1; echo "check(pml) exit $?" >> $O/check_pml_n$N.log
 grep -E "pml|exit" $O/check_pml_n$N.log | tail -6
+# the C++ host driver over per-rank JSON files in the reference's schema (SeismoVLAB_gpu.exe -np N)
+SVL_MULTIGPU_PML=1 timeout 600 python tests/multigpu_host_check.py $N > $O/check_host_n$N.log 2>&1; echo "check(host) exit $?" >> $O/check_host_n$N.log
+grep -E "multigpu host|exit" $O/check_host_n$N.log | tail -8
 timeout 900 $TR --master-port 29512 bench.py --gpus $N --steps 100 --warmup 5 > $O/bench_weak_n$N.json 2> $O/bench_weak_n$N.err
 timeout 600 $TR --master-port 29513 bench.py --gpus $N --steps 200 --warmup 10 --scaling strong > $O/bench_strong_n$N.json 2> $O/bench_strong_n$N.err
 python - <<PY
