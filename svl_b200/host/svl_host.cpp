@@ -85,7 +85,26 @@ class Mesh {             // 06-Mesh/Mesh.cpp
 };
 
 // ---- Driver (12-Utilities/Driver.hpp UpdateMesh :1981-2046) ------------------------------------------------------------
-bool UpdateMesh(Mesh &mesh, const JValue &J, bool geometry_only = false) {
+// binary sidecars of a partition file (svl_b200/model.py::pack_partition_tables): flat little-endian arrays
+struct BinFile {
+    std::ifstream f;
+    bool open(const std::string &path, const char magic[4]) {
+        f.open(path, std::ios::binary);
+        char m[4]; uint32_t ver = 0;
+        if (!f.is_open() || !f.read(m, 4) || std::memcmp(m, magic, 4) != 0 || !f.read((char *)&ver, 4) || ver != 1) {
+            std::cout << "\x1B[31m ERROR: \x1B[0mcannot read binary table " << path << "\n";
+            return false;
+        }
+        return true;
+    }
+    template <typename T> bool read(std::vector<T> &v, size_t n) {
+        v.resize(n);
+        return n == 0 || (bool)f.read((char *)v.data(), (std::streamsize)(n * sizeof(T)));
+    }
+    template <typename T> bool read1(T &v) { return (bool)f.read((char *)&v, sizeof(T)); }
+};
+
+bool UpdateMesh(Mesh &mesh, const JValue &J, const std::string &dir, bool geometry_only = false) {
     const JValue &G = J["Global"];
     mesh.ndim = G["ndim"].as_int(3);
     mesh.ntotal = G["ntotal"].as_int();
@@ -93,6 +112,27 @@ bool UpdateMesh(Mesh &mesh, const JValue &J, bool geometry_only = false) {
     mesh.ntotal_dev = mesh.ntotal; mesh.nfree_dev = mesh.nfree;
     mesh.lumped = ieq(G["massform"].as_string("LUMPED"), "LUMPED");
     int idx = 0;
+    if (J["Nodes"].has("binary")) {
+        BinFile b;
+        uint64_t n = 0; uint32_t nc = 0;
+        std::vector<uint32_t> tags; std::vector<int32_t> ndof, tot, fre; std::vector<double> xyz;
+        if (!b.open(dir + "/" + J["Nodes"]["binary"].as_string(), "SVLN") || !b.read1(n) || !b.read1(nc) || !b.read(tags, n) ||
+            !b.read(ndof, n) || !b.read(xyz, n * nc)) return true;
+        size_t S = 0;
+        for (int32_t d : ndof) S += (size_t)d;
+        if (!b.read(tot, S) || !b.read(fre, S)) { std::cout << "\x1B[31m ERROR: \x1B[0mtruncated node table\n"; return true; }
+        size_t at = 0;
+        for (uint64_t i = 0; i < n; i++) {
+            Node nd;
+            nd.tag = tags[i]; nd.index = 0; nd.ndof = ndof[i];
+            nd.total.assign(tot.begin() + at, tot.begin() + at + ndof[i]);
+            nd.free.assign(fre.begin() + at, fre.begin() + at + ndof[i]);
+            nd.coords.assign(xyz.begin() + i * nc, xyz.begin() + (i + 1) * nc);
+            at += (size_t)ndof[i];
+            mesh.Nodes[nd.tag] = std::move(nd);
+        }
+        for (auto &kv : mesh.Nodes) kv.second.index = idx++;      // ascending tag
+    } else
     for (auto &kv : by_tag(J["Nodes"])) {
         Node n;
         n.tag = (unsigned)kv.first; n.index = idx++;
@@ -102,6 +142,14 @@ bool UpdateMesh(Mesh &mesh, const JValue &J, bool geometry_only = false) {
         for (auto &v : (*kv.second)["coords"].arr) n.coords.push_back(v.as_double());
         mesh.Nodes[n.tag] = n;
     }
+    if (J["Constraints"].has("binary")) {
+        BinFile b;
+        uint64_t n = 0;
+        std::vector<int64_t> tg; std::vector<int32_t> st, mt; std::vector<double> fc;
+        if (!b.open(dir + "/" + J["Constraints"]["binary"].as_string(), "SVLC") || !b.read1(n) || !b.read(tg, n) || !b.read(st, n) ||
+            !b.read(mt, n) || !b.read(fc, n)) return true;
+        for (uint64_t i = 0; i < n; i++) mesh.Constraints[(long)tg[i]] = std::make_tuple((int)st[i], std::vector<int>{mt[i]}, std::vector<double>{fc[i]});
+    } else
     for (auto &kv : J["Constraints"].obj) {
         const long tag = std::strtol(kv.first.c_str(), nullptr, 10);
         std::vector<int> mt; std::vector<double> f;
@@ -130,6 +178,25 @@ bool UpdateMesh(Mesh &mesh, const JValue &J, bool geometry_only = false) {
         mesh.Masses[(unsigned)kv.first] = v;
     }
     idx = 0;
+    if (J["Elements"].has("binary")) {
+        BinFile b;
+        uint64_t n = 0;
+        std::vector<uint32_t> tags, mat, conn; std::vector<int32_t> kind, nconn; std::vector<double> attr, am, ak; std::vector<uint8_t> ray;
+        if (!b.open(dir + "/" + J["Elements"]["binary"].as_string(), "SVLE") || !b.read1(n) || !b.read(tags, n) || !b.read(kind, n) ||
+            !b.read(mat, n) || !b.read(nconn, n) || !b.read(conn, n * 8) || !b.read(attr, n * 10) || !b.read(am, n) || !b.read(ak, n) ||
+            !b.read(ray, n)) { std::cout << "\x1B[31m ERROR: \x1B[0mtruncated element table\n"; return true; }
+        static const int nattr_of[6] = {0, 0, 1, 9, 8, 1};       // attributes per kind, the order of the JSON branch below
+        for (uint64_t i = 0; i < n; i++) {
+            Element e;
+            e.tag = tags[i]; e.index = 0; e.kind = kind[i]; e.material = mat[i];
+            if (e.kind < SVLGPU_LIN3DHEXA8 || e.kind > SVLGPU_ZEROLENGTH1D || nconn[i] < 0 || nconn[i] > 8) { std::cout << "\x1B[31m ERROR: \x1B[0mbad element record\n"; return true; }
+            e.conn.assign(conn.begin() + i * 8, conn.begin() + i * 8 + nconn[i]);
+            e.attr.assign(attr.begin() + i * 10, attr.begin() + i * 10 + nattr_of[e.kind]);
+            if (ray[i]) mesh.Rayleigh[e.tag] = {am[i], ak[i]};
+            mesh.Elements[e.tag] = std::move(e);
+        }
+        for (auto &kv : mesh.Elements) kv.second.index = idx++;
+    } else
     for (auto &kv : by_tag(J["Elements"])) {
         Element e;
         e.tag = (unsigned)kv.first; e.index = idx++;
@@ -146,6 +213,7 @@ bool UpdateMesh(Mesh &mesh, const JValue &J, bool geometry_only = false) {
         else { std::cout << "\x1B[31m ERROR: \x1B[0melement " << name << " is not on the GPU explicit path\n"; return true; }
         mesh.Elements[e.tag] = e;
     }
+    if (!J["Dampings"].has("binary"))                              // binary form: the Rayleigh columns of the element table
     for (auto &kv : by_tag(J["Dampings"])) {
         const std::string name = (*kv.second)["name"].as_string();
         const JValue &a = (*kv.second)["attributes"];
@@ -266,6 +334,29 @@ bool PlanPartitions(std::vector<Mesh> &all, int rank) {
 void PrintPlan(const Mesh &me, int rank) {
     std::cout << "PLAN rank " << rank << " nodes " << me.Nodes.size() << " ntotal " << me.ntotal_dev << " nfree " << me.nfree_dev
               << " constraints " << me.Constraints.size() << " pml_collective " << (me.pml_collective ? 1 : 0) << "\n";
+    {   // digest of everything UpdateMesh built: equal for a JSON file and its binary-sidecar twin
+        unsigned long long h = 1469598103934665603ull;
+        auto mixb = [&](const void *p, size_t n) { const unsigned char *c = (const unsigned char *)p; for (size_t i = 0; i < n; i++) { h ^= c[i]; h *= 1099511628211ull; } };
+        auto mixi = [&](long long v) { mixb(&v, sizeof v); };
+        auto mixd = [&](double v) { mixb(&v, sizeof v); };
+        for (auto &kv : me.Nodes) {
+            const Node &n = kv.second;
+            mixi(n.tag); mixi(n.index); mixi(n.ndof);
+            for (int v : n.total) mixi(v);
+            for (int v : n.free) mixi(v);
+            for (double v : n.coords) mixd(v);
+        }
+        for (auto &kv : me.Elements) {
+            const Element &e = kv.second;
+            mixi(e.tag); mixi(e.index); mixi(e.kind); mixi(e.material);
+            for (unsigned v : e.conn) mixi(v);
+            for (double v : e.attr) mixd(v);
+        }
+        for (auto &kv : me.Constraints) { mixi(kv.first); mixi(std::get<0>(kv.second)); for (int v : std::get<1>(kv.second)) mixi(v); for (double v : std::get<2>(kv.second)) mixd(v); }
+        for (auto &kv : me.Rayleigh) { mixi(kv.first); mixd(kv.second.first); mixd(kv.second.second); }
+        for (auto &kv : me.Masses) { mixi(kv.first); for (double v : kv.second) mixd(v); }
+        std::cout << "PLAN rank " << rank << " mesh digest " << h << " elements " << me.Elements.size() << " rayleigh " << me.Rayleigh.size() << "\n";
+    }
     std::vector<unsigned> tag_of;
     for (auto &kv : me.Nodes) tag_of.push_back(kv.first);
     for (auto &kv : me.Halos) {
@@ -566,11 +657,11 @@ int main(int argc, char **argv) {
             const JValue J = svlhost::JParser(text).parse();
             std::vector<Mesh> all(world);
             Mesh &mesh = all[rank];
-            if (UpdateMesh(mesh, J)) return 1;
+            if (UpdateMesh(mesh, J, dir)) return 1;
             if (world > 1) {
                 if (pattern.find('$') == std::string::npos) { std::cout << "\x1B[31m ERROR: \x1B[0mseveral ranks need a '$' in -file\n"; return 1; }
                 for (int q = 0; q < world; q++)
-                    if (q != rank && UpdateMesh(all[q], svlhost::JParser(read_file(dir + "/" + file_of(q))).parse(), true)) return 1;
+                    if (q != rank && UpdateMesh(all[q], svlhost::JParser(read_file(dir + "/" + file_of(q))).parse(), dir, true)) return 1;
                 if (PlanPartitions(all, rank)) return 1;
             }
             if (plan_only) { PrintPlan(mesh, rank); continue; }

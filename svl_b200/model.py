@@ -482,14 +482,164 @@ def write_reference_partitions(m: Model, epart, nparts: int, directory: str, nam
     return part
 
 
+# -------------------------------------------------------------------------------
+# binary sidecars for the big tables of a partition file
+# -------------------------------------------------------------------------------
+# The per-rank JSON spends > 99 % of its bytes on "Nodes" and "Elements" (one dict per entity, indent=4): ~400 B per node
+# and ~300 B per element, i.e. tens of GB and minutes of parsing at 10^8 DOF.  pack_partition_tables moves these tables (and
+# the constraint / damping lists that scale with them) into flat little-endian arrays next to the JSON; everything else
+# (materials, loads, combinations, recorders, simulation) stays JSON, so the file remains the reference's schema with
+# three keys replaced by {"binary": <file>, "count": n}.  Both readers (load_partition_json here, UpdateMesh in
+# svl_host.cpp) accept either form.
+#   <stem>.nodes.bin  "SVLN" u32 version u64 n u32 ncoord | tag u32[n] ndof i32[n] coords f64[n*ncoord] total i32[S] free i32[S]
+#   <stem>.elems.bin  "SVLE" u32 version u64 n | tag u32[n] kind i32[n] material-tag u32[n] nconn i32[n] conn u32[n*8]
+#                     attr f64[n*10] (order of read_reference_json) am f64[n] ak f64[n] rayleigh u8[n]
+#   <stem>.cons.bin   "SVLC" u32 version u64 n | tag i64[n] slave-total i32[n] master-free i32[n] factor f64[n]
+_ELEM_KIND_OF = {v: k for k, v in ELEM_NAME.items()}
+
+
+def _elem_attr_row(kind, a):
+    row = np.zeros(10)
+    if kind == LIN2DQUAD4:
+        row[0] = float(a.get("th", 1.0))
+    elif kind == ZEROLENGTH1D:
+        row[0] = int(a["dir"])
+    elif kind == PML3DHEXA8:
+        row[:9] = [a["n"], a["L"], a["R"], *a["x0"], *a["npml"]]
+    elif kind == PML2DQUAD4:
+        row[:8] = [a.get("th", 1.0), a["n"], a["L"], a["R"], *a["x0"], *a["npml"]]
+    return row
+
+
+def _elem_attr_dict(kind, mat_tag, row):
+    if kind == ZEROLENGTH1D:
+        return {"material": int(mat_tag), "dir": int(row[0])}
+    a = {"material": int(mat_tag), "rule": "GAUSS", "np": ELEM_NODES[kind]}
+    if kind == LIN2DQUAD4:
+        a["th"] = float(row[0])
+    elif kind == PML3DHEXA8:
+        a.update({"n": float(row[0]), "L": float(row[1]), "R": float(row[2]), "x0": [float(v) for v in row[3:6]],
+                  "npml": [float(v) for v in row[6:9]]})
+    elif kind == PML2DQUAD4:
+        a.update({"th": float(row[0]), "n": float(row[1]), "L": float(row[2]), "R": float(row[3]),
+                  "x0": [float(v) for v in row[4:6]], "npml": [float(v) for v in row[6:8]]})
+    return a
+
+
+def pack_partition_tables(json_path: str, out_path: Optional[str] = None) -> str:
+    """Rewrites a per-rank partition JSON (from the reference's pre-processor or from this module) with its Nodes / Elements /
+    Constraints / Dampings tables moved into binary sidecars.  Returns the path of the new JSON (default <stem>.bin.json ->
+    replace the '.json' of the -file pattern by '.bin.json')."""
+    with open(json_path) as f:
+        J = json.load(f)
+    stem = json_path[:-5] if json_path.endswith(".json") else json_path
+    out_path = out_path or stem + ".bin.json"
+    ntags = sorted(J["Nodes"], key=int)
+    n = len(ntags)
+    ncoord = len(J["Nodes"][ntags[0]]["coords"]) if n else 0
+    ndof = np.array([int(J["Nodes"][t]["ndof"]) for t in ntags], dtype="<i4")
+    with open(stem + ".nodes.bin", "wb") as f:
+        f.write(b"SVLN" + np.array([1], "<u4").tobytes() + np.array([n], "<u8").tobytes() + np.array([ncoord], "<u4").tobytes())
+        f.write(np.array([int(t) for t in ntags], dtype="<u4").tobytes())
+        f.write(ndof.tobytes())
+        f.write(np.array([J["Nodes"][t]["coords"] for t in ntags], dtype="<f8").tobytes())
+        f.write(np.array([v for t in ntags for v in J["Nodes"][t]["totaldof"]], dtype="<i4").tobytes())
+        f.write(np.array([v for t in ntags for v in J["Nodes"][t]["freedof"]], dtype="<i4").tobytes())
+    etags = sorted(J["Elements"], key=int)
+    ne = len(etags)
+    eidx = {int(t): i for i, t in enumerate(etags)}
+    kind = np.zeros(ne, "<i4"); mat = np.zeros(ne, "<u4"); nconn = np.zeros(ne, "<i4"); conn = np.zeros((ne, 8), "<u4")
+    attr = np.zeros((ne, 10), "<f8"); am = np.zeros(ne, "<f8"); ak = np.zeros(ne, "<f8"); ray = np.zeros(ne, "u1")
+    for i, t in enumerate(etags):
+        E = J["Elements"][t]
+        if E["name"].upper() not in _ELEM_KIND_OF:
+            raise ValueError(f"pack_partition_tables: element {E['name']} is not on this path")
+        kind[i] = _ELEM_KIND_OF[E["name"].upper()]
+        mat[i] = int(E["attributes"]["material"])
+        nconn[i] = len(E["conn"])
+        conn[i, :nconn[i]] = E["conn"]
+        attr[i] = _elem_attr_row(int(kind[i]), E["attributes"])
+    for D in J.get("Dampings", {}).values():
+        if D["name"].upper() == "RAYLEIGH":
+            for t in D["attributes"]["list"]:
+                am[eidx[int(t)]] = float(D["attributes"]["am"]); ak[eidx[int(t)]] = float(D["attributes"]["ak"]); ray[eidx[int(t)]] = 1
+        elif D["name"].upper() != "FREE":
+            raise ValueError(f"pack_partition_tables: damping {D['name']} is not on this path")
+    with open(stem + ".elems.bin", "wb") as f:
+        f.write(b"SVLE" + np.array([1], "<u4").tobytes() + np.array([ne], "<u8").tobytes())
+        for a in (np.array([int(t) for t in etags], dtype="<u4"), kind, mat, nconn, conn, attr, am, ak, ray):
+            f.write(a.tobytes())
+    K = dict(J)
+    K["Nodes"] = {"binary": os.path.basename(stem + ".nodes.bin"), "count": n}
+    K["Elements"] = {"binary": os.path.basename(stem + ".elems.bin"), "count": ne}
+    K["Dampings"] = {"binary": os.path.basename(stem + ".elems.bin")}
+    cons = J.get("Constraints", {})
+    if cons and all(len(c["mtag"]) == 1 for c in cons.values()):
+        ct = list(cons)                                            # the file's own order
+        with open(stem + ".cons.bin", "wb") as f:
+            f.write(b"SVLC" + np.array([1], "<u4").tobytes() + np.array([len(ct)], "<u8").tobytes())
+            f.write(np.array([int(t) for t in ct], "<i8").tobytes())
+            f.write(np.array([cons[t]["stag"] for t in ct], "<i4").tobytes())
+            f.write(np.array([cons[t]["mtag"][0] for t in ct], "<i4").tobytes())
+            f.write(np.array([cons[t]["factor"][0] for t in ct], "<f8").tobytes())
+        K["Constraints"] = {"binary": os.path.basename(stem + ".cons.bin"), "count": len(ct)}
+    with open(out_path, "w") as f:
+        json.dump(K, f, indent=4)
+    return out_path
+
+
+def load_partition_json(path: str) -> dict:
+    """json.load of a partition file with binary sidecars (pack_partition_tables) expanded back into the reference's
+    dict-per-entity schema; a plain file is returned as it is."""
+    with open(path) as f:
+        J = json.load(f)
+    here = os.path.dirname(os.path.abspath(path))
+
+    def rd(f, dt, count):
+        return np.frombuffer(f.read(np.dtype(dt).itemsize * count), dtype=dt, count=count)
+
+    if isinstance(J.get("Nodes"), dict) and "binary" in J["Nodes"]:
+        with open(os.path.join(here, J["Nodes"]["binary"]), "rb") as f:
+            assert f.read(4) == b"SVLN" and rd(f, "<u4", 1)[0] == 1
+            n = int(rd(f, "<u8", 1)[0]); nc = int(rd(f, "<u4", 1)[0])
+            tags = rd(f, "<u4", n); ndof = rd(f, "<i4", n); xyz = rd(f, "<f8", n * nc).reshape(n, nc)
+            S = int(ndof.sum())
+            tot = rd(f, "<i4", S); fre = rd(f, "<i4", S)
+        ptr = np.concatenate([[0], np.cumsum(ndof)])
+        J["Nodes"] = {str(int(tags[i])): {"ndof": int(ndof[i]), "freedof": [int(v) for v in fre[ptr[i]:ptr[i + 1]]],
+                                          "totaldof": [int(v) for v in tot[ptr[i]:ptr[i + 1]]],
+                                          "coords": [float(v) for v in xyz[i]]} for i in range(n)}
+    if isinstance(J.get("Elements"), dict) and "binary" in J["Elements"]:
+        with open(os.path.join(here, J["Elements"]["binary"]), "rb") as f:
+            assert f.read(4) == b"SVLE" and rd(f, "<u4", 1)[0] == 1
+            ne = int(rd(f, "<u8", 1)[0])
+            tags = rd(f, "<u4", ne); kind = rd(f, "<i4", ne); mat = rd(f, "<u4", ne); nconn = rd(f, "<i4", ne)
+            conn = rd(f, "<u4", ne * 8).reshape(ne, 8); attr = rd(f, "<f8", ne * 10).reshape(ne, 10)
+            am = rd(f, "<f8", ne); ak = rd(f, "<f8", ne); ray = rd(f, "u1", ne)
+        J["Elements"] = {str(int(tags[i])): {"name": ELEM_NAME[int(kind[i])], "conn": [int(v) for v in conn[i, :nconn[i]]],
+                                             "attributes": _elem_attr_dict(int(kind[i]), mat[i], attr[i])} for i in range(ne)}
+        groups: Dict[tuple, list] = {}
+        for i in range(ne):
+            groups.setdefault((bool(ray[i]), float(am[i]), float(ak[i])), []).append(int(tags[i]))
+        J["Dampings"] = {str(q + 1): ({"name": "RAYLEIGH", "attributes": {"am": a_, "ak": k_, "list": lst}} if r_ else
+                                      {"name": "FREE", "attributes": {"list": lst}})
+                         for q, ((r_, a_, k_), lst) in enumerate(groups.items())}
+    if isinstance(J.get("Constraints"), dict) and "binary" in J["Constraints"]:
+        with open(os.path.join(here, J["Constraints"]["binary"]), "rb") as f:
+            assert f.read(4) == b"SVLC" and rd(f, "<u4", 1)[0] == 1
+            nc_ = int(rd(f, "<u8", 1)[0])
+            tg = rd(f, "<i8", nc_); st = rd(f, "<i4", nc_); mt = rd(f, "<i4", nc_); fc = rd(f, "<f8", nc_)
+        J["Constraints"] = {str(int(tg[i])): {"stag": int(st[i]), "mtag": [int(mt[i])], "factor": [float(fc[i])]} for i in range(nc_)}
+    return J
+
+
 def read_reference_json(path: str, base_dir: Optional[str] = None) -> Model:
     """Inverse of write_reference_json for the subset of the schema on this path (SURVEY.md App. D;
     12-Utilities/Driver.hpp:1981-2046): builds a Model from a per-rank JSON file the reference's pre-processor wrote.
     Entities are taken in ascending tag order; node / element indices are positions in that order.  Relative load
     files are resolved against `base_dir` (default: the directory the run is started from = parent of Partition/).
     Adds m.integrator (the JSON's integrator name) and m.rec_spec = [(resp, [node indices])]."""
-    with open(path) as f:
-        J = json.load(f)
+    J = load_partition_json(path)                                 # plain JSON, or JSON + binary sidecars
     base = base_dir or os.path.dirname(os.path.dirname(os.path.abspath(path)))
     G = J["Global"]
     m = Model(ndim=int(G["ndim"]), lumped=str(G.get("massform", "LUMPED")).upper() == "LUMPED")

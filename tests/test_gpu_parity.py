@@ -269,6 +269,29 @@ def test_multigpu_interface_exchange():
     assert r.returncode == 0
 
 
+@pytest.mark.parametrize("name", ["kat444", "pml2d", "hex8_layered_rayleigh"])
+def test_host_driver_runs_from_binary_partition_tables(tmp_path, name):
+    """the same run from a partition file whose Nodes / Elements / Constraints / Dampings tables sit in binary
+    sidecars (model.pack_partition_tables) -- same recorder file as from the plain JSON, same golden."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "svl_b200", "SeismoVLAB_gpu.exe")
+    m = cases.CASES[name]()
+    g = np.load(os.path.join(root, "tests", "golden", f"{name}.npz"))
+    part = M.write_reference_json(m, str(tmp_path), "Case", "Run", resp=("disp",), ndps=17)
+    M.pack_partition_tables(os.path.join(part, "Case.1.0.json"))
+    out_file = os.path.join(str(tmp_path), "Solution", "Run", "disp.0.out")
+    outs = []
+    for pattern in ("Case.1.$.json", "Case.1.$.bin.json"):
+        r = subprocess.run([exe, "-dir", part, "-file", pattern], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append((open(out_file).readline(), M.read_node_recorder(out_file)))
+        os.remove(out_file)
+    assert outs[0][0] == outs[1][0]                                   # identical header line
+    assert cases.rel_err(outs[1][1], outs[0][1]) < 1e-13              # the same object graph reaches the device
+    assert cases.rel_err(outs[1][1], g["disp"]) < cases.TOL[name]
+
+
 # ---- the reference's command line / file formats on top of the C ABI (svl_b200/host) ----------------------
 @pytest.mark.parametrize("name", ["kat444", "quad4_area", "drm_box", "j2_column", "hex8_layered_rayleigh", "pml2d", "pml3d",
                                   "lysmer_column", "lysmer_area", "j2ps_area"])
