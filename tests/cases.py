@@ -121,7 +121,19 @@ def j2ps_area():
                              load_dir=(3.0e5, 1.0e5), rec_nodes=[12, 27, 40, 44])
 
 
-CASES = {f.__name__: f for f in (kat444, hex8_distorted, hex8_layered_rayleigh, quad4_area, quad4_distorted,
+def c1_column20():
+    """BASELINE.json configs[0] at its full size: 3-D linear elastic soil column, 20 x 20 x 20 lin3DHexa8 + Elastic3DLinear
+    (fixture J05's soil), bottom fixed, lumped CentralDifference at dt = 0.5 h / Vp, Ricker point load at the centre of the free
+    surface; 80 steps carry the P front to the base and back.  16 recorded nodes: a 4 x 4 grid over the free surface plus
+    interior points on the load axis."""
+    n = 20
+    N1 = n + 1
+    top = [i + N1 * j + N1 * N1 * n for j in (0, 7, 13, 20) for i in (0, 7, 13, 20)]
+    axis = [10 + N1 * 10 + N1 * N1 * k for k in (5, 10, 15)]
+    return M.make_box_model((n, n, n), 1.0, mat=(M.ELASTIC3DLINEAR, SOIL), nt=81, rec_nodes=top[:13] + axis)
+
+
+CASES = {f.__name__: f for f in (c1_column20, kat444, hex8_distorted, hex8_layered_rayleigh, quad4_area, quad4_distorted,
                                  j2_column, drm_box, drm_area, pml2d, pml3d, lysmer_column, lysmer_area, j2ps_area)}
 # tolerance of |oracle - reference| and |device - oracle| per case (max_t|d| / max_t|ref| per dof)
 TOL = {name: 1e-10 for name in CASES}
