@@ -6,6 +6,7 @@
                               matplotlib, which the pre-processor imports at module scope, is replaced by an empty stub
   *.txt / *.in                the fixture's load time series
   opensees.npz                the fixture's OpenSees golden histories (displacement / velocity / acceleration .out)
+  opensees_gauss.npz          J02 / F02: the OpenSees element recorder files strain.out / stress.out (Gauss points of the one element)
   reference.npz               fixtures without shipped numbers (F11, J12: the reference validates them by a plot) and the
                               Newton-Raphson fixtures (F03, F07): NODE
                               recorder histories written by the unmodified reference executable oracle/_ref/SeismoVLAB.exe
@@ -101,6 +102,10 @@ def main():
         if os.path.isdir(o):
             np.savez_compressed(os.path.join(dst, "opensees.npz"), disp=np.loadtxt(os.path.join(o, "displacement.out")),
                                 vel=np.loadtxt(os.path.join(o, "velocity.out")), accel=np.loadtxt(os.path.join(o, "acceleration.out")))
+        if os.path.exists(os.path.join(o, "stress.out")) and name in ("J02", "F02"):
+            # Gauss-point histories of the single element (OpenSees element recorder: time, then ngp x ncomp columns)
+            np.savez_compressed(os.path.join(dst, "opensees_gauss.npz"), strain=np.loadtxt(os.path.join(o, "strain.out")),
+                                stress=np.loadtxt(os.path.join(o, "stress.out")))
         if not os.path.isdir(o) or name in NEWTON_FIXTURES:
             run_reference_on(src, dst)
         print(name, "->", dst)

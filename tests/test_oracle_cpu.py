@@ -84,6 +84,43 @@ def test_oracle_matches_reference_fixture_from_its_own_input_files(oracle, name)
         assert cases.fixture_errors(name, out, key) < cases.REF_FIXTURES[name]["tol"], key
 
 
+@pytest.mark.parametrize("name", ["J02", "F02"])
+def test_oracle_gauss_point_strain_stress_match_reference_fixture_opensees_recorders(oracle, name):
+    """Fixtures J02 (one lin3DHexa8) and F02 (one lin2DQuad4) ship the OpenSees ELEMENT recorder files strain.out / stress.out.
+    The oracle's kinematics (B matrix, Gauss-point order, Voigt order) and elastic law applied to the oracle's own nodal
+    history reproduce them at the Gauss point and in the column pairing the fixtures' LaTeX/cmpResults.py use
+    (J02: 8th point, SVL [11 22 33 12 23 13] <-> OpenSees columns 43 45 44 48 47 46; F02: 4th point <-> columns 7 8 9),
+    to the 6 printed digits."""
+    import ctypes as C
+    dp = C.POINTER(C.c_double)
+    m = cases.fixture_model(name)
+    g = np.load(os.path.join(cases.fixture_dir(name), "opensees_gauss.npz"))
+    out, _ = oracle.run(m, integrator=m.integrator, rec_dofs=np.arange(m.n_total, dtype=np.int32))
+    assert m.n_elem == 1 and out.shape[0] == g["strain"].shape[0]
+    is3 = m.ndim == 3
+    npe, ngp, ncomp = (8, 8, 6) if is3 else (4, 4, 3)
+    conn = m.elem_conn[0, :npe]
+    X = np.ascontiguousarray(m.coords[conn].ravel())
+    Cm = np.zeros(ncomp * ncomp)
+    E, nu = m.materials[0][1][:2]
+    (oracle.lib.svlo_elastic3d_C if is3 else oracle.lib.svlo_planestrain_C)(C.c_double(E), C.c_double(nu), Cm.ctypes.data_as(dp))
+    Cm = Cm.reshape(ncomp, ncomp)
+    eps = np.zeros((out.shape[0], ngp, ncomp))
+    for k in range(out.shape[0]):
+        Ue = np.ascontiguousarray(np.concatenate([out[k, m.node_ptr[n]:m.node_ptr[n] + m.ndim] for n in conn]))
+        e = np.zeros((ngp, ncomp))
+        (oracle.lib.svlo_hex8_strain if is3 else oracle.lib.svlo_quad4_strain)(X.ctypes.data_as(dp), Ue.ctypes.data_as(dp),
+                                                                              e.ctypes.data_as(dp))
+        eps[k] = e
+    sig = eps @ Cm.T
+    gp, cols = (7, (43, 45, 44, 48, 47, 46)) if is3 else (3, (7, 8, 9))
+    rrms = lambda a, b: np.sqrt(np.mean((a - b) ** 2)) / np.sqrt(np.mean(b ** 2))      # noqa: E731
+    for c, col in enumerate(cols):
+        assert rrms(sig[:, gp, c], g["stress"][:, col]) < 5e-6, ("stress", c)
+        if is3:                                                                          # F02's script compares stresses only
+            assert rrms(eps[:, gp, c], g["strain"][:, col]) < 5e-6, ("strain", c)
+
+
 @pytest.mark.parametrize("name", list(cases.EXE_FIXTURES))
 def test_oracle_matches_reference_executable_on_pml_fixture_inputs(oracle, name):
     """Fixtures F11 (PML2DQuad4, Newmark) and J12 (PML3DHexa8, ExtendedNewmarkBeta with the history matrix G), read from
