@@ -66,6 +66,29 @@ def centroid_epart(m: Model, pgrid) -> np.ndarray:
     return part
 
 
+def write_metis_graph(m: Model, path: str) -> str:
+    """The METIS mesh file the reference's pre-processor hands to `mpmetis` (Core/Partition.py:87-144 SetMetisInputFile):
+    first line = number of elements, then one line of 1-based node ids per element in ascending element order, every id
+    followed by a blank.  The slave node of an EQUAL constraint carries the id of its master (:121-126), so that METIS sees
+    the soil-PML interface as connected and keeps tied nodes together.  `mpmetis <path> <nparts>` then writes
+    `<path>.epart.<nparts>`, which read_epart turns into the `epart` of split_model / write_reference_partitions."""
+    ids = np.arange(1, m.n_nodes + 1, dtype=np.int64)
+    if m.constraints:
+        fd = np.asarray(m.freedof_flat)
+        node_of_total = np.repeat(np.arange(m.n_nodes), np.diff(m.node_ptr))
+        total_of_free = -np.ones(max(1, m.n_free), dtype=np.int64)
+        total_of_free[fd[fd > -1]] = np.nonzero(fd > -1)[0]
+        aux = ids.copy()
+        for _, slave, masters, _ in m.constraints:
+            if len(masters) == 1:                                   # EQUAL
+                ids[node_of_total[slave]] = aux[node_of_total[total_of_free[masters[0]]]]
+    with open(path, "w") as f:
+        f.write(f"{m.n_elem}\n")
+        for e in range(m.n_elem):
+            f.write("".join(f"{ids[n]} " for n in m.elem_conn[e, :ELEM_NODES[int(m.elem_kind[e])]]) + "\n")
+    return path
+
+
 def read_epart(path: str) -> np.ndarray:
     """METIS `<graph>.epart.<nparts>` file: one partition id per element line (Partition.py:150-201)."""
     return np.loadtxt(path, dtype=np.int32)

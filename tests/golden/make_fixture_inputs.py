@@ -32,6 +32,7 @@ FIXTURES = {"F02": "F02-DY_Lin_2DPointLoad_ElasticPStrain_Quad4", "F06": "F06-DY
 # NewmarkBeta + NewtonRaphson on PlasticPlaneStrainJ2: OpenSees histories AND the reference executable's (the reference's
 # Newton iteration updates the LIVE material state, so it is not OpenSees' algorithm: SURVEY.md App. C q9)
 NEWTON_FIXTURES = ("F03", "F07")
+METIS_FIXTURES = ("F11", "J12", "F06")          # keep the reference's METIS input file (EQUAL ties collapse slave onto master)
 EXE = os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle", "_ref", "SeismoVLAB.exe")
 
 
@@ -89,12 +90,21 @@ def main():
         zipfile.ZipFile(os.path.join(REF, "03-Validations", "01-Debugging", fx + ".zip")).extractall(tmp)
         src = os.path.join(tmp, fx)
         subprocess.run([sys.executable, fx + ".py"], cwd=src, env=env, check=True, stdout=subprocess.DEVNULL)
+        if name in METIS_FIXTURES:
+            # the METIS mesh file the reference's pre-processor writes for this model (Core/Partition.py:87-144 SetMetisInputFile;
+            # createPartitions deletes it again, so it is rebuilt here from the script's entities with the cluster map cleared)
+            code = ("import runpy, sys\nsys.argv=['x']\nrunpy.run_path(%r, run_name='__main__')\n"
+                    "from Core.Definitions import Options\nfrom Core.Partition import SetMetisInputFile\n"
+                    "Options['clustermap'] = {}\nSetMetisInputFile()\n" % (fx + ".py"))
+            subprocess.run([sys.executable, "-c", code], cwd=src, env=env, check=True, stdout=subprocess.DEVNULL)
         dst = os.path.join(HERE, "fixtures", name)
         shutil.rmtree(dst, ignore_errors=True)
         os.makedirs(os.path.join(dst, "Partition"))
         for fn in os.listdir(os.path.join(src, "Partition")):
             if fn.endswith(".json"):
                 shutil.copy(os.path.join(src, "Partition", fn), os.path.join(dst, "Partition", fn))
+        if name in METIS_FIXTURES:
+            shutil.copy(os.path.join(src, "Partition", "Graph.out"), os.path.join(dst, "Graph.out"))
         for fn in os.listdir(src):
             if fn.endswith((".txt", ".in")):
                 shutil.copy(os.path.join(src, fn), os.path.join(dst, fn))

@@ -334,3 +334,23 @@ def test_binary_partition_tables_round_trip_and_host_driver_digest(tmp_path, cas
         M.pack_partition_tables(os.path.join(part, f"Split.1.{r}.json"))
     two_json, two_bin = plan(["-np", "2", "-file", "Split.1.$.json"]), plan(["-np", "2", "-file", "Split.1.$.bin.json"])
     assert two_json == two_bin and len([l for l in two_json if "digest" in l]) == 2
+
+
+@pytest.mark.parametrize("name", ["F11", "J12", "F06"])
+def test_metis_mesh_file_equals_the_reference_preprocessors(tmp_path, name):
+    """partition.write_metis_graph on the model read back from the fixture's JSON reproduces, byte for byte, the `Graph.out`
+    the reference's pre-processor writes for `mpmetis` (Core/Partition.py:87-144; golden kept by make_fixture_inputs.py):
+    F11 / J12 carry EQUAL soil-PML ties (the slave takes its master's id), F06 mixes quads with 2-node ZeroLength1D
+    dashpots."""
+    m = cases.fixture_model(name)
+    out = P.write_metis_graph(m, str(tmp_path / "Graph.out"))
+    ref = os.path.join(cases.fixture_dir(name), "Graph.out")
+    assert open(out).read() == open(ref).read()
+    if name != "F06":
+        assert len(m.constraints) > 0
+        ids = set(int(v) for line in open(out).read().splitlines()[1:] for v in line.split())
+        assert len(ids) < m.n_nodes                                 # tied nodes collapsed
+    # and the way back: an epart file as mpmetis writes it (one rank per line) drives the splitter
+    ep = np.arange(m.n_elem) % 2
+    np.savetxt(str(tmp_path / "Graph.out.epart.2"), ep, fmt="%d")
+    assert (P.read_epart(str(tmp_path / "Graph.out.epart.2")) == ep).all()
