@@ -382,7 +382,10 @@ bool ExchangeNcclId(const std::string &dir, int rank, char id[128]) {
     }
     for (int tries = 0; tries < 3000; tries++) {                     // up to 5 minutes: rank 0 may still be parsing
         std::ifstream f(path, std::ios::binary);
-        if (f.is_open() && f.read(id, 128) && f.gcount() == 128) return false;
+        if (f.is_open() && f.read(id, 128) && f.gcount() == 128) {
+            std::ofstream ack(path + ".ack." + std::to_string(rank));  // rank 0 keeps the file until every rank has it
+            return false;
+        }
         struct timespec ts = {0, 100000000};
         nanosleep(&ts, nullptr);
     }
@@ -487,7 +490,18 @@ class CentralDifference {
         char id[128];
         if (ExchangeNcclId(dir, rank, id)) return true;
         if (svlgpu_comm_init(h, id, rank, world)) return fail();
-        if (rank == 0) std::remove(NcclIdPath(dir).c_str());       // every rank has read it: comm_init is collective
+        if (rank == 0) {                                            // clean up once every rank has acknowledged the id
+            const std::string path = NcclIdPath(dir);
+            for (int q = 1; q < world; q++) {
+                const std::string ack = path + ".ack." + std::to_string(q);
+                for (int tries = 0; tries < 3000 && !std::ifstream(ack).is_open(); tries++) {
+                    struct timespec ts = {0, 100000000};
+                    nanosleep(&ts, nullptr);
+                }
+                std::remove(ack.c_str());
+            }
+            std::remove(path.c_str());
+        }
         return false;
     }
 

@@ -1,0 +1,139 @@
+"""What reaches the C ABI, checked on CPU: the C++ host driver and the ctypes binding run against a RECORDING stand-in for
+libsvlgpu.so (tests/trace_shim/svlgpu_trace.c: every entry point of include/svlgpu.h, one trace line per builder call with
+digests of the array arguments, no GPU and no physics).  The same model must produce the same calls
+  * from a plain partition JSON and from its binary-table twin,
+  * on several ranks: from the C++ driver reading per-rank files in the reference's schema (global tags / dof numbers, tie
+    closure and renumbering done by the driver) and from the Python partitioner + binding that the GPU parity runs use."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import cases
+from svl_b200 import model as M, partition as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "svl_b200", "SeismoVLAB_gpu.exe")
+
+
+@pytest.fixture(scope="module")
+def shim(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("shim") / "libsvlgpu_trace.so")
+    subprocess.run(["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-o", so, os.path.join(ROOT, "tests", "trace_shim", "svlgpu_trace.c")],
+                   check=True)
+    return so
+
+
+def run_driver(shim, part, pattern, trace, nparts=1):
+    env = dict(os.environ, LD_PRELOAD=shim, SVLGPU_TRACE=trace)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    args = [EXE] + (["-np", str(nparts)] if nparts > 1 else []) + ["-dir", part, "-file", pattern]
+    r = subprocess.run(args, capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return [open(trace + (f".{q}" if nparts > 1 else "")).read().splitlines() for q in range(nparts)]
+
+
+@pytest.mark.parametrize("case", ["kat444", "drm_box", "pml2d", "pml3d", "lysmer_column", "hex8_layered_rayleigh", "j2ps_area"])
+def test_driver_hands_the_same_calls_from_json_and_from_binary_tables(shim, tmp_path, case):
+    m = cases.CASES[case]()
+    part = M.write_reference_json(m, str(tmp_path), "Case", "Run")
+    M.pack_partition_tables(os.path.join(part, "Case.1.0.json"))
+    a = run_driver(shim, part, "Case.1.$.json", str(tmp_path / "a.trace"))[0]
+    b = run_driver(shim, part, "Case.1.$.bin.json", str(tmp_path / "b.trace"))[0]
+    assert a == b
+    kinds = {l.split()[0] for l in a}
+    assert {"create", "set_nodes", "add_material", "add_elements", "add_node_recorder", "finalize"} <= kinds
+    if case.startswith("pml"):
+        assert sum(l.startswith("add_constraint") for l in a) == len(m.constraints)
+    if case == "drm_box":
+        assert "add_drm_load" in kinds
+    # the run completed against the stand-in: a recorder file of the right shape exists
+    rec = M.read_node_recorder(os.path.join(str(tmp_path), "Solution", "Run", "disp.0.out"))
+    assert rec.shape == (m.nt - 1, len(m.rec_dofs()))
+
+
+_PY_RANK = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, cases
+from svl_b200 import capi, partition as P
+case, nparts, rank, how = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
+capi.LIB_PATH = {shim!r}                       # the recording stand-in instead of svl_b200/libsvlgpu.so (this test only)
+m = cases.CASES[case]()
+ep = eval(how)
+s = P.split_model(m, ep, nparts)[rank]
+d = capi.DeviceModel(s, comm=(rank, nparts, b"\x5a" * 128))
+d.close()
+"""
+
+
+def _kv(line):
+    tok = line.split()
+    return tok[0], dict(t.split("=", 1) for t in tok[1:] if "=" in t)
+
+
+def _canon(lines):
+    """the order-independent content of a trace that both front ends must agree on"""
+    out = {"constraints": set(), "rayleigh": set(), "halos": [], "elements": [], "loads": set(), "recorders": [], "options": set()}
+    for l in lines:
+        name, kv = _kv(l)
+        if name in ("create", "set_nodes", "finalize", "comm_init"):
+            out[name] = kv
+        elif name == "add_material":
+            out.setdefault("materials", []).append(kv)
+        elif name == "add_elements":
+            out["elements"].append(kv)
+        elif name == "add_constraint":
+            out["constraints"].add(tuple(sorted(kv.items())))
+        elif name == "set_rayleigh":
+            out["rayleigh"].add(tuple(sorted(kv.items())))
+        elif name == "add_halo":
+            out["halos"].append(kv)
+        elif name == "add_point_load":
+            out["loads"].add((kv["nnodes"], kv["nt"], kv["factor"], kv["nodes"], kv["series"]))
+        elif name == "add_node_recorder":
+            out["recorders"].append((kv["field"], kv["nnodes"], kv["nodes"]))
+        elif name == "set_option" and "pml_collective" in l:
+            out["options"].add(l)
+    return out
+
+
+@pytest.mark.parametrize("case,nparts,how", [
+    ("kat444", 2, "P.block_epart((4, 4, 4), (1, 1, 2))"),
+    ("lysmer_column", 4, "P.block_epart((3, 3, 6), (2, 1, 2))"),
+    ("hex8_layered_rayleigh", 2, "P.block_epart((4, 3, 6), (1, 1, 2))"),
+    ("pml3d", 2, "P.centroid_epart(m, (1, 1, 2))"),
+    ("pml2d", 3, "np.random.default_rng(5).integers(0, 3, m.n_elem).astype(np.int32)"),
+])
+def test_driver_on_reference_rank_files_matches_python_partitioner_at_the_c_abi(shim, tmp_path, case, nparts, how):
+    """Several ranks.  Left: write_reference_partitions (global numbering, masters travel with slaves only, as createPartitions
+    writes them) -> `SeismoVLAB_gpu.exe -np N` (PlanPartitions: tie closure, local numbering, halos; NCCL id through the
+    partition directory; svlgpu_comm_init).  Right: partition.split_model -> capi.DeviceModel, the pair the GPU multi-rank
+    parity runs use.  Both must hand every rank the same nodes, numbering, elements, constraints, halo lists, loads,
+    recorders, options and communicator arguments."""
+    m = cases.CASES[case]()
+    ep = eval(how)
+    part = M.write_reference_partitions(m, ep, nparts, str(tmp_path), "Case", "Run")
+    left = run_driver(shim, part, "Case.1.$.json", str(tmp_path / "cpp.trace"), nparts)
+    assert not [f for f in os.listdir(part) if f.startswith(".svlgpu_nccl_id")]          # rank 0 removed the id file
+    for rank in range(nparts):
+        env = dict(os.environ, SVLGPU_TRACE=str(tmp_path / "py.trace"), RANK=str(rank))
+        r = subprocess.run([sys.executable, "-c", _PY_RANK.format(root=ROOT, shim=shim), case, str(nparts), str(rank), how],
+                           capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        right = open(str(tmp_path / "py.trace") + f".{rank}").read().splitlines()
+        a, b = _canon(left[rank]), _canon(right)
+        for key in ("create", "set_nodes", "finalize", "comm_init", "materials", "elements", "constraints", "halos", "loads",
+                    "options"):
+            assert a.get(key) == b.get(key), (rank, key)
+        # recorders differ by design: the reference's files list a recorded node in EVERY partition that holds it
+        # (SeismoVLAB.py:237-246), split_model hands it to its owner only
+        assert sum(int(r[1]) for r in a["recorders"]) >= sum(int(r[1]) for r in b["recorders"])
+        if case == "hex8_layered_rayleigh":
+            assert a["rayleigh"] == b["rayleigh"] and a["rayleigh"]
+        assert a["comm_init"]["rank"] == str(rank) and a["comm_init"]["nranks"] == str(nparts)
+        if case.startswith("pml"):
+            assert a["options"] and a["constraints"]
