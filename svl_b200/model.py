@@ -309,9 +309,12 @@ def add_base_dashpots(m: Model, vs: float, vp: float, rho: float, h: float, th: 
 # -------------------------------------------------------------------------------
 def write_reference_json(m: Model, directory: str, name: str = "Model", combo: str = "Run",
                          resp=("disp",), integrator: str = "CENTRALDIFFERENCE", ndps: int = 16, newton=None,
-                         _return_entities: bool = False) -> str:
+                         _return_entities: bool = False, binary: bool = False) -> str:
     """Writes <directory>/Partition/<name>.1.0.json (+ load / .drm text files) in the schema the
-    reference executable reads.  Tags are index+1.  Returns the partition directory."""
+    reference executable reads.  Tags are index+1.  Returns the partition directory.
+    binary=True writes <name>.1.0.bin.json instead, with the Nodes / Elements / Constraints / Dampings tables in binary sidecars
+    (the form pack_partition_tables produces), straight from the model's arrays: no per-entity dict is ever built, which is
+    what makes 10^7-element models writable at all."""
     part = os.path.join(directory, "Partition")
     os.makedirs(part, exist_ok=True)
     # the reference's recorders write into <dir>/../Solution/<combo>/ and expect it to exist
@@ -324,7 +327,7 @@ def write_reference_json(m: Model, directory: str, name: str = "Model", combo: s
         J["Materials"][str(i + 1)] = {"name": MAT_NAME[kind],
                                       "attributes": dict(zip(MAT_KEYS[kind], [float(p) for p in par]))}
     J["Nodes"] = {}
-    for i in range(m.n_nodes):
+    for i in range(0 if binary else m.n_nodes):
         a, b = m.node_ptr[i], m.node_ptr[i + 1]
         J["Nodes"][str(i + 1)] = {"ndof": int(m.node_ndof[i]),
                                   "freedof": [int(v) for v in m.freedof_flat[a:b]],
@@ -332,11 +335,11 @@ def write_reference_json(m: Model, directory: str, name: str = "Model", combo: s
                                   "coords": [float(v) for v in m.coords[i]]}
     if m.masses:
         J["Masses"] = {str(n + 1): {"ndof": len(v), "mass": [float(x) for x in v]} for n, v in m.masses}
-    if m.constraints:
+    if m.constraints and not binary:
         J["Constraints"] = {str(t): {"stag": int(s), "mtag": [int(x) for x in mt], "factor": [float(x) for x in f]}
                             for t, s, mt, f in m.constraints}
     J["Elements"] = {}
-    for e in range(m.n_elem):
+    for e in range(0 if binary else m.n_elem):
         kind = int(m.elem_kind[e])
         nn = ELEM_NODES[kind]
         at = m.elem_attr[e] if m.elem_attr is not None else np.zeros(10)
@@ -354,7 +357,15 @@ def write_reference_json(m: Model, directory: str, name: str = "Model", combo: s
         J["Elements"][str(e + 1)] = {"name": ELEM_NAME[kind],
                                      "conn": [int(v) + 1 for v in m.elem_conn[e, :nn]], "attributes": attr}
     # dampings: FREE on everything unless Rayleigh given (SeismoVLAB.py:704-707)
-    if m.elem_am is not None and (np.any(m.elem_am != 0) or np.any(m.elem_ak != 0)):
+    if binary:
+        stem = os.path.join(part, f"{name}.1.0")
+        _write_binary_tables(m, stem)
+        J["Nodes"] = {"binary": os.path.basename(stem + ".nodes.bin"), "count": m.n_nodes}
+        J["Elements"] = {"binary": os.path.basename(stem + ".elems.bin"), "count": m.n_elem}
+        J["Dampings"] = {"binary": os.path.basename(stem + ".elems.bin")}
+        if m.constraints:
+            J["Constraints"] = {"binary": os.path.basename(stem + ".cons.bin"), "count": len(m.constraints)}
+    elif m.elem_am is not None and (np.any(m.elem_am != 0) or np.any(m.elem_ak != 0)):
         groups: Dict[tuple, list] = {}
         for e in range(m.n_elem):
             groups.setdefault((float(m.elem_am[e]), float(m.elem_ak[e])), []).append(e + 1)
@@ -412,9 +423,44 @@ def write_reference_json(m: Model, directory: str, name: str = "Model", combo: s
         "solver": {"name": "EIGEN", "update": 1 if newton is None else 0}}}
     if _return_entities:
         return part, J
-    with open(os.path.join(part, f"{name}.1.0.json"), "w") as f:
+    with open(os.path.join(part, f"{name}.1.0.bin.json" if binary else f"{name}.1.0.json"), "w") as f:
         json.dump(J, f, indent=4)
     return part
+
+
+def _write_binary_tables(m: Model, stem: str):
+    """the sidecars of pack_partition_tables written from the model's arrays (tags = index + 1), vectorised"""
+    n, ne = m.n_nodes, m.n_elem
+    with open(stem + ".nodes.bin", "wb") as f:
+        f.write(b"SVLN" + np.array([1], "<u4").tobytes() + np.array([n], "<u8").tobytes() + np.array([m.ndim], "<u4").tobytes())
+        for a in (np.arange(1, n + 1, dtype="<u4"), np.asarray(m.node_ndof, "<i4"), np.asarray(m.coords, "<f8"),
+                  np.asarray(m.totaldof, "<i4"), np.asarray(m.freedof_flat, "<i4")):
+            f.write(np.ascontiguousarray(a).tobytes())
+    kind = np.asarray(m.elem_kind, "<i4")
+    nconn = np.array([0] + [ELEM_NODES[k] for k in (1, 2, 3, 4, 5)], "<i4")[kind]
+    conn = np.zeros((ne, 8), "<u4")
+    for npe in np.unique(nconn):
+        sel = nconn == npe
+        conn[sel, :npe] = np.asarray(m.elem_conn)[sel, :npe] + 1
+    attr = np.zeros((ne, 10), "<f8") if m.elem_attr is None else np.asarray(m.elem_attr, "<f8").copy()
+    nattr = np.array([0, 0, 1, 9, 8, 1])[kind]                       # meaningful leading entries per kind
+    attr[np.arange(10)[None, :] >= nattr[:, None]] = 0.0
+    am = np.zeros(ne, "<f8") if m.elem_am is None else np.asarray(m.elem_am, "<f8")
+    ak = np.zeros(ne, "<f8") if m.elem_ak is None else np.asarray(m.elem_ak, "<f8")
+    ray = ((am != 0) | (ak != 0)).astype("u1")
+    with open(stem + ".elems.bin", "wb") as f:
+        f.write(b"SVLE" + np.array([1], "<u4").tobytes() + np.array([ne], "<u8").tobytes())
+        for a in (np.arange(1, ne + 1, dtype="<u4"), kind, (np.asarray(m.elem_mat) + 1).astype("<u4"), nconn, conn, attr, am, ak, ray):
+            f.write(np.ascontiguousarray(a).tobytes())
+    if m.constraints:
+        if any(len(c[2]) != 1 for c in m.constraints):
+            raise ValueError("binary tables hold single-master (EQUAL) constraints only")
+        with open(stem + ".cons.bin", "wb") as f:
+            f.write(b"SVLC" + np.array([1], "<u4").tobytes() + np.array([len(m.constraints)], "<u8").tobytes())
+            f.write(np.array([c[0] for c in m.constraints], "<i8").tobytes())
+            f.write(np.array([c[1] for c in m.constraints], "<i4").tobytes())
+            f.write(np.array([c[2][0] for c in m.constraints], "<i4").tobytes())
+            f.write(np.array([c[3][0] for c in m.constraints], "<f8").tobytes())
 
 
 def write_reference_partitions(m: Model, epart, nparts: int, directory: str, name: str = "Model", combo: str = "Run",

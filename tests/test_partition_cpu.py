@@ -310,6 +310,11 @@ def test_binary_partition_tables_round_trip_and_host_driver_digest(tmp_path, cas
     jp = os.path.join(part, "Case.1.0.json")
     bp = M.pack_partition_tables(jp)
     assert bp.endswith("Case.1.0.bin.json")
+    # the direct writer (arrays -> sidecars, no per-entity dicts) produces the same bytes
+    import filecmp
+    direct = M.write_reference_json(m, str(tmp_path / "direct"), "Case", "Run", binary=True)
+    for suffix in ("nodes.bin", "elems.bin") + (("cons.bin",) if m.constraints else ()):
+        assert filecmp.cmp(os.path.join(part, f"Case.1.0.{suffix}"), os.path.join(direct, f"Case.1.0.{suffix}"), shallow=False), suffix
     a, b = M.read_reference_json(jp), M.read_reference_json(bp)
     for k in ("coords", "node_ndof", "elem_conn", "elem_kind", "elem_mat", "elem_attr", "freedof_flat"):
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
