@@ -559,7 +559,7 @@ int pml_rescale(svlgpu_model *m) {
 // adds the PML part of Assembler::ComputeInternalForceVector (K_e u_e per element) to F (internal dof order)
 int pml_internal_force(svlgpu_model *m, const double *U, double *F) {
     PmlDev &P = m->pml;
-    if (!P.present) return 0;
+    if (!P.present || !P.n_elem) return 0;
     elem_products(m, 2, P.d_edof, P.d_K, U, nullptr, nullptr, nullptr, nullptr, 0, 0.0);
     const int n = P.n_elem * P.nde;
     k_pml_fint_add<<<(n + 255) / 256, 256, 0, m->stream>>>(n, P.d_edof, P.d_ye, F);
