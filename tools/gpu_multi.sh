@@ -22,3 +22,8 @@ for k in ("weak","strong"):
     except Exception as e: print(k, "failed", e)
 PY
 tail -3 $O/bench_weak_n$N.err
+# BASELINE configs[2] across the GPUs (only meaningful once the pml lines above are OK)
+if grep -q "check(pml) exit 0" $O/check_pml_n$N.log; then
+  timeout 900 $TR --master-port 29515 tools/bench_pml_multi.py --n ${PML_N:-200} --steps 20 > $O/bench_pml_n$N.json 2> $O/bench_pml_n$N.err
+  cat $O/bench_pml_n$N.json
+fi
