@@ -107,7 +107,8 @@ int svlgpu_hint_structured_block(svlgpu_model *m, int node0, int nx, int ny, int
  * strain / stress for svlgpu_get_gauss, default 0), "ftol" (Assembler.cpp:262 filter of the PML element
  * forces, default 1e-12), "integrator" (0: CentralDifference, 10-Integrators/02-CentralDifference, the
  * default; 1: NewmarkBeta + Linear, 10-Integrators/03-Newmark/NewmarkBeta.cpp:64-133 with Linear.cpp:22-56:
- * linear materials, lumped mass, Rayleigh damping with both coefficients, dashpots, one GPU; the sparse
+ * linear materials, lumped mass, Rayleigh damping with both coefficients, dashpots (several ranks: interface sums inside
+ * the K operator and all-reduced dot products are written but have not run on hardware yet); the sparse
  * factorisation of Keff = K + 4/dt^2 M + 2/dt C is replaced by matrix-free conjugate gradients),
  * "newmark_rtol" (relative residual of that solve, default 1e-13), "pml_collective" (1 on EVERY rank of a
  * partitioned model that has PML elements anywhere, also on ranks without one: the PML block solve exchanges the

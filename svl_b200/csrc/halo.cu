@@ -173,6 +173,23 @@ int halo_exchange_end(svlgpu_model *m, const double *U, const double *Up, double
     return 0;
 }
 
+// any vector in the internal dof layout: interface values summed over the ranks that hold the node (Newmark Krylov solve)
+int halo_vec_load(svlgpu_model *m, const double *src) {
+    HaloDev &h = m->halo;
+    if (h.n_if) k_halo_load<<<(h.n_if * h.nd + 255) / 256, 256, 0, m->stream>>>(h.n_if, h.nd, h.d_if_dof0, src, h.d_hF);
+    m->total_launches++;
+    return 0;
+}
+int halo_vec_sum(svlgpu_model *m, double *dst) {
+    HaloDev &h = m->halo;
+    if (exchange_on(m, m->stream)) return 1;
+    if (h.n_if) k_halo_sum_to<<<(h.n_if * h.nd + 255) / 256, 256, 0, m->stream>>>(h.n_if, h.nd, h.d_if_dof0, h.d_fix_ptr, h.d_fix_src, h.d_hF,
+                                                                                  h.d_recv, dst);
+    m->total_launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int halo_unique_id(void *out128) {
     if (nccl_load()) return 1;
     nccl_uid id;
@@ -242,9 +259,13 @@ int halo_comm_init(svlgpu_model *m, const void *id128, int rank, int nranks) {
         k_halo_coeffs<<<(nthr + 255) / 256, 256, 0, m->stream>>>(h.n_if, nd, h.d_if_dof0, dm, dc, dfree, m->dt, m->d_kinv, m->d_km);
         CUDA_OK(cudaMemcpyAsync(m->h_mass.data(), dm, sizeof(double) * m->n_int, cudaMemcpyDeviceToHost, m->stream));
         CUDA_OK(cudaStreamSynchronize(m->stream));
+        const int rc = newmark_comm_setup(m, dm, dc);
         cudaFree(dm); cudaFree(dc); cudaFree(dfree);
+        if (rc) return 1;
     } else {
-        // ranks without interface nodes still take part in nothing: no peers, no NCCL calls
+        // ranks without interface nodes still take part in nothing: no peers, no NCCL calls -- except the all-reduces of a
+        // Krylov solve (Newmark, PML block), which every rank of the communicator issues
+        if (newmark_comm_setup(m, nullptr, nullptr)) return 1;
     }
     CUDA_OK(cudaGetLastError());
     return pmlx_setup(m);

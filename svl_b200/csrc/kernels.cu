@@ -1824,6 +1824,11 @@ int external_forces_raw(svlgpu_model *m, int k, const double *dev_amp, double *b
     return launch_external(m, k, dev_amp, b, 1, false);
 }
 
+// hF -= Fext(k) at the interface dofs (loads are handed to one partition only, so they travel with the exchange)
+int external_forces_interface(svlgpu_model *m, int k, const double *dev_amp) {
+    return launch_external(m, k, dev_amp, nullptr, 0, false);
+}
+
 // Assembler::ComputeInternalForceVector for the current displacement state
 int compute_internal_force(svlgpu_model *m, double *F_host) {
     double *tmp = m->d_U[m->next];

@@ -233,6 +233,9 @@ struct NewmarkDev {
     double ak = 0.0;                                 // uniform stiffness-proportional Rayleigh coefficient (C = am M + ak K)
     int max_iter = 5000, last_iters = 8;
     int64_t total_iters = 0, solves = 0;
+    // several ranks: replicated interface dofs count once in the dot products; the communicator is joined
+    double *d_own = nullptr;
+    bool multi = false;
 };
 
 }  // namespace svl
@@ -366,6 +369,10 @@ int pml_configure();
 int newmark_plan(svlgpu_model *m);
 int newmark_step(svlgpu_model *m, int k, const double *dev_amp);
 int newmark_set_initial(svlgpu_model *m, const double *V_int, const double *A_int);
+int newmark_comm_setup(svlgpu_model *m, const double *mglob, const double *cglob);     // from halo_comm_init
+int halo_vec_load(svlgpu_model *m, const double *src);                                  // hF <- src at the interface dofs (main stream)
+int halo_vec_sum(svlgpu_model *m, double *dst);                                         // exchange hF; dst <- rank-ordered sum at the interface dofs
+int external_forces_interface(svlgpu_model *m, int k, const double *dev_amp);           // hF -= Fext(k) at the interface dofs
 void newmark_destroy(svlgpu_model *m);
 int operator_K(svlgpu_model *m, const double *x, double *out);
 int external_forces_raw(svlgpu_model *m, int k, const double *dev_amp, double *b);

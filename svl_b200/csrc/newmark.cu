@@ -11,7 +11,8 @@
 // iteration count depends on (omega_max dt)^2 only).  Scalars and the convergence flag live on the device; reductions
 // have a fixed shape (deterministic).  Scope: linear materials, lumped mass, Rayleigh damping (mass-proportional part
 // on the diagonal, a uniform stiffness-proportional part folded into the K operator), dashpots (diagonal C),
-// restrained dofs; one GPU.
+// restrained dofs.  Several GPUs (written, not yet run on hardware): interface values of K p are summed over the ranks
+// with the force halo lists, dot products count every dof on its lowest rank and are all-reduced (newmark_comm_setup).
 #include <algorithm>
 #include <cstring>
 #include "model.h"
@@ -70,12 +71,13 @@ __global__ void __launch_bounds__(kNmThreads) k_nm_rhs(int n, double c4, const d
 }
 // start of the solve: x = 0 (Linear.cpp:25), r = mask b, z = r / D, p = z; partials bb = (r, r), rz = (r, z)
 __global__ void __launch_bounds__(kNmThreads) k_nm_init(int n, const double *mask, const double *dinv, const double *b, double *x,
-                                                         double *r, double *p, double *part) {
+                                                         double *r, double *p, double *part, const double *own) {
     double a0 = 0.0, a1 = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double rv = mask[i] * b[i], zv = rv * dinv[i];
         x[i] = 0.0; r[i] = rv; p[i] = zv;
-        a0 = fma(rv, rv, a0); a1 = fma(rv, zv, a1);
+        const double o = own ? own[i] : 1.0;              // several ranks: a replicated dof counts on its lowest rank
+        a0 = fma(o * rv, rv, a0); a1 = fma(o * rv, zv, a1);
     }
     const double s0 = nm_block_sum(a0), s1 = nm_block_sum(a1);
     if (threadIdx.x == 0) {
@@ -90,20 +92,20 @@ __global__ void __launch_bounds__(kNmThreads) k_nm_w(int n, double ak, const dou
 }
 // q = mask (ck K p + D p) with K p already in q, ck = 1 + 2 ak / dt; partial (p, q)
 __global__ void __launch_bounds__(kNmThreads) k_nm_ap(int n, double ck, const double *mask, const double *dd, const double *p, double *q,
-                                                       double *part) {
+                                                       double *part, const double *own) {
     if (part[kNmFlag] != 0.0) return;
     double a0 = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double pv = p[i], qv = mask[i] * (ck * q[i] + dd[i] * pv);
         q[i] = qv;
-        a0 = fma(pv, qv, a0);
+        a0 = fma((own ? own[i] : 1.0) * pv, qv, a0);
     }
     const double s0 = nm_block_sum(a0);
     if (threadIdx.x == 0) part[N_PAP * kNmBlocks + blockIdx.x] = s0;
 }
 // x += alpha p, r -= alpha q; partials rr = (r, r), rz_next = (r, r / D)
 __global__ void __launch_bounds__(kNmThreads) k_nm_xr(int n, int rz_slot, const double *dinv, const double *p, const double *q,
-                                                       double *x, double *r, double *part) {
+                                                       double *x, double *r, double *part, const double *own) {
     if (part[kNmFlag] != 0.0) return;
     const double pap = nm_total(part, N_PAP), rz = nm_total(part, rz_slot);
     const double alpha = pap != 0.0 ? rz / pap : 0.0;
@@ -113,7 +115,8 @@ __global__ void __launch_bounds__(kNmThreads) k_nm_xr(int n, int rz_slot, const 
         x[i] = fma(alpha, p[i], x[i]);
         const double rv = fma(-alpha, q[i], r[i]);
         r[i] = rv;
-        a0 = fma(rv, rv, a0); a1 = fma(rv * dinv[i], rv, a1);
+        const double o = own ? own[i] : 1.0;
+        a0 = fma(o * rv, rv, a0); a1 = fma(o * (rv * dinv[i]), rv, a1);
     }
     const double s0 = nm_block_sum(a0), s1 = nm_block_sum(a1);
     if (threadIdx.x == 0) { part[N_RR * kNmBlocks + blockIdx.x] = s0; part[nslot * kNmBlocks + blockIdx.x] = s1; }
@@ -146,11 +149,20 @@ __global__ void __launch_bounds__(kNmThreads) k_nm_update(int n, double dt, cons
     }
 }
 
+// several ranks: lumped mass / damping summed over the ranks at the interface dofs -> D and 1 / D
+__global__ void k_nm_refresh(int n, double dt, const double *mglob, const double *cglob, const double *mask, double *mass, double *cd,
+                             double *dd, double *dinv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double d = 4.0 / dt / dt * mglob[i] + 2.0 / dt * cglob[i];
+    mass[i] = mglob[i]; cd[i] = cglob[i]; dd[i] = d;
+    dinv[i] = (mask[i] != 0.0 && d > 0.0) ? 1.0 / d : 0.0;
+}
+
 int newmark_plan(svlgpu_model *m) {
     NewmarkDev &N = m->nm;
     const int n = m->n_int;
     const double dt = m->dt;
-    if (!m->halo_peers.empty()) { set_error("Newmark: the device path runs on one GPU (the Krylov solve has no cross-rank reductions yet)"); return 1; }
     if (m->pml.present) { set_error("Newmark: PML elements need ExtendedNewmarkBeta (history term G), not built"); return 1; }
     if (!m->constraints.empty()) { set_error("Newmark: constrained dofs are not supported on the device path"); return 1; }
     for (auto &mat : m->materials)
@@ -162,7 +174,8 @@ int newmark_plan(svlgpu_model *m) {
     for (int q = 0; q < n; q++) {
         mask[q] = m->freedof[q] >= 0 ? 1.0 : 0.0;
         dd[q] = 4.0 / dt / dt * m->h_mass[q] + 2.0 / dt * m->h_cdiag[q];
-        if (mask[q] != 0.0 && !(dd[q] > 0.0)) { set_error("Newmark: free dof without mass (the D-preconditioner needs a positive diagonal)"); return 1; }
+        // several ranks: an interface dof may get all of its mass from other ranks (newmark_comm_setup refreshes D and checks)
+        if (mask[q] != 0.0 && !(dd[q] > 0.0) && m->halo_peers.empty()) { set_error("Newmark: free dof without mass (the D-preconditioner needs a positive diagonal)"); return 1; }
         dinv[q] = mask[q] != 0.0 ? 1.0 / dd[q] : 0.0;
     }
     auto up = [&](const std::vector<double> &h, double **d) -> int {
@@ -185,6 +198,31 @@ int newmark_plan(svlgpu_model *m) {
     N.present = true;
     return 0;
 }
+// after the communicator exists (halo_comm_init): mglob / cglob = the lumped diagonals with the interface dofs summed over
+// the ranks (null on a rank without interface nodes); ownership mask of the dot products
+int newmark_comm_setup(svlgpu_model *m, const double *mglob, const double *cglob) {
+    NewmarkDev &N = m->nm;
+    if (!N.present) return 0;
+    const int n = m->n_int, rank = m->halo.rank;
+    std::vector<double> own(n, 1.0);
+    for (auto &hp : m->halo_peers)
+        if (hp.peer < rank)
+            for (int node : hp.nodes)
+                for (int q = m->node_ptr[node]; q < m->node_ptr[node + 1]; q++) own[q] = 0.0;
+    CUDA_OK(cudaMalloc(&N.d_own, sizeof(double) * (n + 2)));
+    m->allocs.push_back(N.d_own);
+    CUDA_OK(cudaMemcpy(N.d_own, own.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    if (mglob && cglob) {
+        k_nm_refresh<<<(n + 255) / 256, 256, 0, m->stream>>>(n, m->dt, mglob, cglob, N.d_mask, N.d_mass, N.d_cd, N.d_dd, N.d_dinv);
+        std::vector<double> dd(n);
+        CUDA_OK(cudaMemcpyAsync(dd.data(), N.d_dd, sizeof(double) * n, cudaMemcpyDeviceToHost, m->stream));
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+        for (int q = 0; q < n; q++)
+            if (m->freedof[q] >= 0 && !(dd[q] > 0.0)) { set_error("Newmark: free dof without mass (the D-preconditioner needs a positive diagonal)"); return 1; }
+    }
+    N.multi = true;
+    return 0;
+}
 void newmark_destroy(svlgpu_model *m) {
     if (m->nm.h_scal) cudaFreeHost(m->nm.h_scal);
     m->nm.h_scal = nullptr;
@@ -204,15 +242,22 @@ int newmark_step(svlgpu_model *m, int k, const double *dev_amp) {
     const double *U = m->d_U[m->cur];
     double *Un = m->d_U[m->next];
     m->k_of_step = k;
+    const bool mg = N.multi;                              // several ranks: every rank issues the same collectives
+    const double *own = mg ? N.d_own : nullptr;
     // Fint(U_n) = K U_n: the explicit path's force-only pass (Assembler::ComputeInternalForceVector)
     if (N.ak != 0.0) {
         k_nm_w<<<kNmBlocks, kNmThreads, 0, st>>>(n, N.ak, U, N.d_V, N.d_r);
         m->total_launches++;
         if (operator_K(m, N.d_r, N.d_q)) return 1;
     } else if (operator_K(m, U, N.d_q)) return 1;
+    if (mg) {
+        // interface dofs: this rank's part of K U minus the external forces it was handed, summed over the holders
+        if (halo_vec_load(m, N.d_q) || external_forces_interface(m, k, dev_amp) || halo_vec_sum(m, N.d_q)) return 1;
+    }
     k_nm_rhs<<<kNmBlocks, kNmThreads, 0, st>>>(n, 4.0 / dt, N.d_q, N.d_mass, N.d_cd, N.d_mask, N.d_V, N.d_A, N.d_b, N.d_part);
     if (external_forces_raw(m, k, dev_amp, N.d_b)) return 1;           // b += Fext(k)  (Assembler::ComputeExternalForceVector)
-    k_nm_init<<<kNmBlocks, kNmThreads, 0, st>>>(n, N.d_mask, N.d_dinv, N.d_b, N.d_x, N.d_r, N.d_p, N.d_part);
+    k_nm_init<<<kNmBlocks, kNmThreads, 0, st>>>(n, N.d_mask, N.d_dinv, N.d_b, N.d_x, N.d_r, N.d_p, N.d_part, own);
+    if (mg && pmlx_allreduce(m, N.d_part, (size_t)N_NSLOT * kNmBlocks, nullptr, 0, st)) return 1;   // slots not written here are rewritten before use
     k_nm_flag<<<1, 32, 0, st>>>(N.d_part, tol2);
     m->total_launches += 3;
     int it = 0, rz = N_RZ0;
@@ -221,8 +266,12 @@ int newmark_step(svlgpu_model *m, int k, const double *dev_amp) {
     while (!done) {
         for (int q = 0; q < batch; q++, it++) {
             if (operator_K(m, N.d_p, N.d_q)) return 1;
-            k_nm_ap<<<kNmBlocks, kNmThreads, 0, st>>>(n, 1.0 + 2.0 * N.ak / dt, N.d_mask, N.d_dd, N.d_p, N.d_q, N.d_part);
-            k_nm_xr<<<kNmBlocks, kNmThreads, 0, st>>>(n, rz, N.d_dinv, N.d_p, N.d_q, N.d_x, N.d_r, N.d_part);
+            if (mg && (halo_vec_load(m, N.d_q) || halo_vec_sum(m, N.d_q))) return 1;
+            k_nm_ap<<<kNmBlocks, kNmThreads, 0, st>>>(n, 1.0 + 2.0 * N.ak / dt, N.d_mask, N.d_dd, N.d_p, N.d_q, N.d_part, own);
+            if (mg && pmlx_allreduce(m, N.d_part + N_PAP * kNmBlocks, kNmBlocks, nullptr, 0, st)) return 1;
+            k_nm_xr<<<kNmBlocks, kNmThreads, 0, st>>>(n, rz, N.d_dinv, N.d_p, N.d_q, N.d_x, N.d_r, N.d_part, own);
+            if (mg && pmlx_allreduce(m, N.d_part + N_RR * kNmBlocks, kNmBlocks,
+                                     N.d_part + ((rz == N_RZ0) ? N_RZ1 : N_RZ0) * kNmBlocks, kNmBlocks, st)) return 1;
             k_nm_flag<<<1, 32, 0, st>>>(N.d_part, tol2);
             k_nm_p<<<kNmBlocks, kNmThreads, 0, st>>>(n, rz, N.d_dinv, N.d_r, N.d_p, N.d_part);
             rz = (rz == N_RZ0) ? N_RZ1 : N_RZ0;

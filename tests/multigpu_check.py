@@ -31,6 +31,10 @@ NE = {"kat444": (4, 4, 4), "drm_box": (6, 6, 5), "quad4_area": (8, 6), "j2_colum
 # opt-in until a GPU pass has seen them green, so that the suite the driver runs keeps testing what was verified.
 if os.environ.get("SVL_MULTIGPU_PML", "0") != "1":
     NE = {k: v for k, v in NE.items() if v is not None}
+RUNS = [(name, ne, "CENTRALDIFFERENCE") for name, ne in NE.items()]
+# NewmarkBeta + Linear across ranks (interface sums inside the K operator, all-reduced dot products): same status, opt-in
+if os.environ.get("SVL_MULTIGPU_NEWMARK", "0") == "1":
+    RUNS += [(name, NE[name], "NEWMARK") for name in cases.NEWMARK_CASES if NE.get(name) is not None]
 
 
 def main():
@@ -41,12 +45,13 @@ def main():
     if rank == 0:
         uid.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
     ok = True
-    for name, ne in NE.items():
+    for name, ne, integrator in RUNS:
         # a fresh communicator per model keeps the check independent of call order
         if rank == 0:
             uid.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
-        m = cases.CASES[name]()
+        newmark = integrator == "NEWMARK"
+        m = cases.newmark_case(name) if newmark else cases.CASES[name]()
         if ne is None:
             grid = P.proc_grid(world) if m.ndim == 3 else ((world, 1) if world <= 2 else (2, world // 2))
             subs = P.split_model(m, P.centroid_epart(m, grid), world)
@@ -59,7 +64,8 @@ def main():
         if ne is not None:
             subs = P.split_model(m, P.block_epart(ne, grid), world)
         s = subs[rank]
-        d = capi.DeviceModel(s, device=local, comm=(rank, world, bytes(uid.cpu().numpy())))
+        d = capi.DeviceModel(s, device=local, comm=(rank, world, bytes(uid.cpu().numpy())),
+                             options={"integrator": 1.0} if newmark else None)
         d.step(1, m.nt, True)
         U = d.get_state(0)
         rec = d.read_recorder(0) if len(s.rec_nodes) else np.zeros((m.nt - 1, 0))
@@ -71,7 +77,7 @@ def main():
         d.close()
         if rank == 0:
             from oracle_lib import Oracle
-            ref, Uref = Oracle().run(m)
+            ref, Uref = Oracle().run(m, integrator=integrator)
             Ug = np.full(m.n_total, np.nan)
             spread = 0.0
             for gd_r, U_r, *_ in gathered:
@@ -88,11 +94,11 @@ def main():
                     cols[int(n)] = rc[:, off[i]:off[i + 1]]
             out = np.concatenate([cols[int(n)] for n in m.rec_nodes], axis=1)
             err_r = cases.rel_err(out, ref)
-            tol = cases.TOL[name]
+            tol = cases.TOL_NEWMARK if newmark else cases.TOL[name]
             good = err_u < tol and err_r < tol and spread == 0.0
             ok &= good
             c = gathered[0][4]
-            print(f"[multigpu world={world}] {name:24s} grid={grid} max rel err U={err_u:.2e} rec={err_r:.2e} "
+            print(f"[multigpu world={world}] {(name + ' newmark') if newmark else name:24s} grid={grid} max rel err U={err_u:.2e} rec={err_r:.2e} "
                   f"replica spread={spread:.1e} block_nodes(r0)={c['n_block_nodes']} generic(r0)={c['n_generic_elements']} "
                   f"{'OK' if good else 'FAIL'}", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")

@@ -6,9 +6,9 @@ mkdir -p $O
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 timeout 600 $TR --master-port 29511 tests/multigpu_check.py > $O/check_n$N.log 2>&1; echo "check exit $?" >> $O/check_n$N.log
 grep -E "multigpu|exit" $O/check_n$N.log | tail -12
-# opt-in cases: PML models across ranks (see tests/multigpu_check.py)
-SVL_MULTIGPU_PML=1 timeout 600 $TR --master-port 29514 tests/multigpu_check.py > $O/check_pml_n$N.log 2>&1; echo "check(pml) exit $?" >> $O/check_pml_n$N.log
-grep -E "pml|exit" $O/check_pml_n$N.log | tail -6
+# opt-in cases: PML models and NewmarkBeta across ranks (see tests/multigpu_check.py)
+SVL_MULTIGPU_PML=1 SVL_MULTIGPU_NEWMARK=1 timeout 900 $TR --master-port 29514 tests/multigpu_check.py > $O/check_pml_n$N.log 2>&1; echo "check(pml) exit $?" >> $O/check_pml_n$N.log
+grep -E "pml|newmark|exit" $O/check_pml_n$N.log | tail -14
 # the C++ host driver over per-rank JSON files in the reference's schema (SeismoVLAB_gpu.exe -np N)
 SVL_MULTIGPU_PML=1 timeout 600 python tests/multigpu_host_check.py $N > $O/check_host_n$N.log 2>&1; echo "check(host) exit $?" >> $O/check_host_n$N.log
 grep -E "multigpu host|exit" $O/check_host_n$N.log | tail -8
