@@ -257,8 +257,19 @@ int halo_comm_init(svlgpu_model *m, const void *id128, int rank, int nranks) {
             k_halo_sum_to<<<(nthr + 255) / 256, 256, 0, m->stream>>>(h.n_if, nd, h.d_if_dof0, h.d_fix_ptr, h.d_fix_src, h.d_hF, h.d_recv, arr);
         }
         k_halo_coeffs<<<(nthr + 255) / 256, 256, 0, m->stream>>>(h.n_if, nd, h.d_if_dof0, dm, dc, dfree, m->dt, m->d_kinv, m->d_km);
+        std::vector<double> cglob(m->n_int);
         CUDA_OK(cudaMemcpyAsync(m->h_mass.data(), dm, sizeof(double) * m->n_int, cudaMemcpyDeviceToHost, m->stream));
+        CUDA_OK(cudaMemcpyAsync(cglob.data(), dc, sizeof(double) * m->n_int, cudaMemcpyDeviceToHost, m->stream));
         CUDA_OK(cudaStreamSynchronize(m->stream));
+        // the planner let interface dofs pass without local mass (it may all sit on other ranks): the global sum must have some
+        for (auto &hp : m->halo_peers)
+            for (int node : hp.nodes)
+                for (int q = m->node_ptr[node]; q < m->node_ptr[node + 1]; q++)
+                    if (isfree[q] && !(1.0 / m->dt / m->dt * m->h_mass[q] + 1.0 / 2.0 / m->dt * cglob[q] > 0.0)) {
+                        cudaFree(dm); cudaFree(dc); cudaFree(dfree);
+                        set_error("free dof without mass: Keff is singular (EigenSolver.cpp:52-55)");
+                        return 1;
+                    }
         const int rc = newmark_comm_setup(m, dm, dc);
         cudaFree(dm); cudaFree(dc); cudaFree(dfree);
         if (rc) return 1;
