@@ -241,6 +241,38 @@ def test_device_matches_reference_golden(oracle, name):
               f"err vs reference golden {cases.rel_err(out, g['disp']):.2e}")
 
 
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: first hardware run decides; remove the marker then")
+@pytest.mark.parametrize("name", ["hex8_distorted", "quad4_distorted"])
+def test_gauss_point_strain_stress_at_the_current_state(oracle, name):
+    """svlgpu_get_gauss (Element::GetStrain / GetStress at Gauss points, lin3DHexa8.cpp:150-200): after an internal-force pass on
+    the current state the kept Gauss-point strains equal the oracle's B u of that state and the stresses C eps."""
+    import ctypes as C
+    dp = C.POINTER(C.c_double)
+    m = cases.CASES[name]()
+    d = _device(m, options={"keep_gauss": 1.0})
+    d.step(1, m.nt // 2, True)
+    d.internal_force()                                   # Gauss-point pass on the current state, nothing committed
+    U = d.get_state(0)
+    elems = np.arange(m.n_elem, dtype=np.int32)
+    eps, sig = d.gauss(0, elems), d.gauss(1, elems)
+    is3 = m.ndim == 3
+    npe, ngp, ncomp = (8, 8, 6) if is3 else (4, 4, 3)
+    Cm = np.zeros(ncomp * ncomp)
+    E, nu = m.materials[0][1][:2]
+    (oracle.lib.svlo_elastic3d_C if is3 else oracle.lib.svlo_planestrain_C)(C.c_double(E), C.c_double(nu), Cm.ctypes.data_as(dp))
+    Cm = Cm.reshape(ncomp, ncomp)
+    ref = np.zeros((m.n_elem, ngp, ncomp))
+    for e in range(m.n_elem):
+        conn = m.elem_conn[e, :npe]
+        X = np.ascontiguousarray(m.coords[conn].ravel())
+        Ue = np.ascontiguousarray(np.concatenate([U[m.node_ptr[n]:m.node_ptr[n] + m.ndim] for n in conn]))
+        (oracle.lib.svlo_hex8_strain if is3 else oracle.lib.svlo_quad4_strain)(X.ctypes.data_as(dp), Ue.ctypes.data_as(dp),
+                                                                              ref[e].ctypes.data_as(dp))
+    assert np.abs(ref).max() > 0
+    assert np.abs(eps - ref).max() <= 1e-12 * np.abs(ref).max()
+    assert np.abs(sig - ref @ Cm.T).max() <= 1e-12 * np.abs(ref @ Cm.T).max()
+
+
 def test_pml_internal_force(oracle):
     for name in ("pml2d", "pml3d"):
         m = cases.CASES[name]()
