@@ -23,6 +23,14 @@ def kat444():
                             series=series, rec_nodes=[62, 112, 124])
 
 
+def kat444_masses():
+    """kat444 with nodal point masses (Assembler::AssembleNodalMass, Assembler.cpp:622-657; JSON "Masses"): unequal per-dof values,
+    one of them zero (dropped by the |m| > mtol filter), on the loaded node and on an interior node."""
+    m = kat444()
+    m.masses = [(112, [500.0, 500.0, 250.0]), (62, [100.0, 0.0, 300.0])]
+    return m
+
+
 def hex8_distorted():
     nt = 41
     series = np.array([math.sin(2 * math.pi * k / 16) for k in range(nt)])
@@ -133,7 +141,7 @@ def c1_column20():
     return M.make_box_model((n, n, n), 1.0, mat=(M.ELASTIC3DLINEAR, SOIL), nt=81, rec_nodes=top[:13] + axis)
 
 
-CASES = {f.__name__: f for f in (c1_column20, kat444, hex8_distorted, hex8_layered_rayleigh, quad4_area, quad4_distorted,
+CASES = {f.__name__: f for f in (c1_column20, kat444, kat444_masses, hex8_distorted, hex8_layered_rayleigh, quad4_area, quad4_distorted,
                                  j2_column, drm_box, drm_area, pml2d, pml3d, lysmer_column, lysmer_area, j2ps_area)}
 # tolerance of |oracle - reference| and |device - oracle| per case (max_t|d| / max_t|ref| per dof)
 TOL = {name: 1e-10 for name in CASES}
@@ -258,6 +266,8 @@ def fingerprint(m) -> str:
     h.update(repr((m.dt, m.nt, [(k, list(map(float, p))) for k, p in m.materials])).encode())
     for pl in m.point_loads:
         h.update(np.ascontiguousarray(pl.series).tobytes())
+    if m.masses:                                   # only models that carry nodal masses (older goldens keep their hash)
+        h.update(repr([(int(n), list(map(float, v))) for n, v in m.masses]).encode())
     return h.hexdigest()[:16]
 
 

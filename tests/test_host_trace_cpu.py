@@ -36,7 +36,7 @@ def run_driver(shim, part, pattern, trace, nparts=1):
     return [open(trace + (f".{q}" if nparts > 1 else "")).read().splitlines() for q in range(nparts)]
 
 
-@pytest.mark.parametrize("case", ["kat444", "drm_box", "pml2d", "pml3d", "lysmer_column", "hex8_layered_rayleigh", "j2ps_area"])
+@pytest.mark.parametrize("case", ["kat444", "kat444_masses", "drm_box", "pml2d", "pml3d", "lysmer_column", "hex8_layered_rayleigh", "j2ps_area"])
 def test_driver_hands_the_same_calls_from_json_and_from_binary_tables(shim, tmp_path, case):
     m = cases.CASES[case]()
     part = M.write_reference_json(m, str(tmp_path), "Case", "Run")
@@ -50,6 +50,8 @@ def test_driver_hands_the_same_calls_from_json_and_from_binary_tables(shim, tmp_
         assert sum(l.startswith("add_constraint") for l in a) == len(m.constraints)
     if case == "drm_box":
         assert "add_drm_load" in kinds
+    if case == "kat444_masses":
+        assert sum(l.startswith("add_nodal_mass") for l in a) == 2
     # the run completed against the stand-in: a recorder file of the right shape exists
     rec = M.read_node_recorder(os.path.join(str(tmp_path), "Solution", "Run", "disp.0.out"))
     assert rec.shape == (m.nt - 1, len(m.rec_dofs()))
