@@ -160,13 +160,16 @@ class DeviceModel:
                                           _d(attrs), nattr) < 0:
                 raise SvlError(self._err())
             start = end
-        if m.elem_am is not None:
-            for am in np.unique(m.elem_am):
-                if am == 0.0:
+        if m.elem_am is not None or m.elem_ak is not None:
+            am_e = np.zeros(m.n_elem) if m.elem_am is None else np.asarray(m.elem_am, float)
+            ak_e = np.zeros(m.n_elem) if m.elem_ak is None else np.asarray(m.elem_ak, float)
+            # one call per distinct (am, ak) pair, ascending; a stiffness-proportional part without a mass-proportional one
+            # is a pair of its own (it used to be dropped with am == 0: the library must get to refuse or honour it)
+            for am, ak in sorted(set(zip(am_e.tolist(), ak_e.tolist()))):
+                if am == 0.0 and ak == 0.0:
                     continue
-                idx = A(np.nonzero(m.elem_am == am)[0], np.int32)
-                ak = float(m.elem_ak[idx[0]]) if m.elem_ak is not None else 0.0
-                self._ck(self.L.svlgpu_set_rayleigh(self.h, len(idx), _i(idx), float(am), ak))
+                idx = A(np.nonzero((am_e == am) & (ak_e == ak))[0], np.int32)
+                self._ck(self.L.svlgpu_set_rayleigh(self.h, len(idx), _i(idx), float(am), float(ak)))
         opts = {"lattice_guess": 0.0} if not m.blocks else {}      # a model without lattice hints asks for the generic path
         if getattr(m, "pml_collective", False) and getattr(m, "halos", None):
             opts["pml_collective"] = 1.0                            # partition of a PML model: every rank joins the block solve
