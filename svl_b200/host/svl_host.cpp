@@ -456,7 +456,11 @@ class CentralDifference {
         }
         {   // Rayleigh damping groups (lin3DHexa8.cpp:354-366)
             std::map<std::pair<double, double>, std::vector<int32_t>> groups;
-            for (auto &kv : mesh.Rayleigh) groups[kv.second].push_back(mesh.Elements.at(kv.first).index);
+            for (auto &kv : mesh.Rayleigh) {
+                const Element &el = mesh.Elements.at(kv.first);
+                if (el.kind == SVLGPU_ZEROLENGTH1D) continue;     // ZeroLength1D::SetDamping does nothing (ZeroLength1D.cpp)
+                groups[kv.second].push_back(el.index);
+            }
             for (auto &g : groups)
                 if (svlgpu_set_rayleigh(h, (int)g.second.size(), g.second.data(), g.first.first, g.first.second)) return fail();
         }

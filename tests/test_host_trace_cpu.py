@@ -139,3 +139,56 @@ def test_driver_on_reference_rank_files_matches_python_partitioner_at_the_c_abi(
         assert a["comm_init"]["rank"] == str(rank) and a["comm_init"]["nranks"] == str(nparts)
         if case.startswith("pml"):
             assert a["options"] and a["constraints"]
+
+
+_PY_ONE = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+from svl_b200 import capi, model as M
+capi.LIB_PATH = {shim!r}                       # the recording stand-in instead of svl_b200/libsvlgpu.so (this test only)
+m = M.read_reference_json(sys.argv[1])
+d = capi.DeviceModel(m, options={{"integrator": 1.0}} if m.integrator == "NEWMARK" else None)
+d.close()
+"""
+
+
+@pytest.mark.parametrize("case", ["kat444", "kat444_masses", "pml2d", "pml3d", "lysmer_column", "hex8_layered_rayleigh", "j2ps_area",
+                                  "F06", "F11"])
+def test_cpp_driver_and_python_binding_hand_the_device_the_same_model(shim, tmp_path, case):
+    """One partition file, two front ends: `SeismoVLAB_gpu.exe` (svl_host.cpp UpdateMesh + Initialize) and
+    `model.read_reference_json` + `capi.DeviceModel` (what the GPU parity tests drive).  Nodes, numbering, materials, elements,
+    constraints, Rayleigh groups, nodal masses, loads, recorder nodes and dt reach the C ABI identically -- also for the
+    reference's own pre-processor output (fixtures F06: Rayleigh + dashpots under Newmark, F11: EQUAL ties)."""
+    if case in cases.CASES:
+        m = cases.CASES[case]()
+        part = M.write_reference_json(m, str(tmp_path), "Case", "Run")
+        jp, pattern = os.path.join(part, "Case.1.0.json"), "Case.1.$.json"
+    else:
+        import shutil
+        src = cases.fixture_dir(case)
+        shutil.copytree(src, str(tmp_path / "fx"))
+        part = str(tmp_path / "fx" / "Partition")
+        name = [f for f in os.listdir(part) if f.endswith(".json")][0]
+        jp, pattern = os.path.join(part, name), name.replace(".0.json", ".$.json")
+        import json
+        J = json.load(open(jp))
+        os.makedirs(os.path.join(str(tmp_path / "fx"), "Solution", J["Combinations"][str(J["Simulations"]["combo"])]["attributes"]["folder"]),
+                    exist_ok=True)
+    env = dict(os.environ, LD_PRELOAD=shim, SVLGPU_TRACE=str(tmp_path / "cpp.trace"))
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    cwd = os.path.dirname(part)                          # the reference resolves relative load files against the run directory
+    r = subprocess.run([EXE, "-dir", part, "-file", pattern], capture_output=True, text=True, env=env, timeout=300, cwd=cwd)
+    assert r.returncode == 0, r.stdout + r.stderr
+    env = dict(os.environ, SVLGPU_TRACE=str(tmp_path / "py.trace"))
+    env.pop("RANK", None)
+    r = subprocess.run([sys.executable, "-c", _PY_ONE.format(root=ROOT, shim=shim), jp], capture_output=True, text=True, env=env,
+                       timeout=300, cwd=cwd)
+    assert r.returncode == 0, r.stdout + r.stderr
+    a = _canon(open(str(tmp_path / "cpp.trace")).read().splitlines())
+    b = _canon(open(str(tmp_path / "py.trace")).read().splitlines())
+    for key in ("create", "set_nodes", "finalize", "materials", "elements", "constraints", "rayleigh", "loads"):
+        assert a.get(key) == b.get(key), key
+    assert a["recorders"][0] == b["recorders"][0]
+    masses = lambda path: sorted(l for l in open(path).read().splitlines() if l.startswith("add_nodal_mass"))     # noqa: E731
+    assert masses(str(tmp_path / "cpp.trace")) == masses(str(tmp_path / "py.trace"))
