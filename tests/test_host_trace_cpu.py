@@ -192,3 +192,32 @@ def test_cpp_driver_and_python_binding_hand_the_device_the_same_model(shim, tmp_
     assert a["recorders"][0] == b["recorders"][0]
     masses = lambda path: sorted(l for l in open(path).read().splitlines() if l.startswith("add_nodal_mass"))     # noqa: E731
     assert masses(str(tmp_path / "cpp.trace")) == masses(str(tmp_path / "py.trace"))
+
+
+_PY_CASE = r"""
+import sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+import cases
+from svl_b200 import capi
+capi.LIB_PATH = {shim!r}                       # the recording stand-in instead of svl_b200/libsvlgpu.so (this test only)
+d = capi.DeviceModel(cases.CASES[sys.argv[1]]())
+d.close()
+"""
+
+
+@pytest.mark.parametrize("case", ["drm_box", "drm_area"])
+def test_drm_text_files_reach_the_c_abi_bit_for_bit(shim, tmp_path, case):
+    """ELEMENTLOAD / GENERALWAVE: the per-node `.drm` text files (Driver.hpp:1689-1721: `nt nFields cond`, then nt rows) written
+    from the model's tabulated field and read back by the C++ driver give the same svlgpu_add_drm_load call -- element list,
+    node list, interior / exterior flags and every field value -- as the Python binding makes from the arrays."""
+    m = cases.CASES[case]()
+    part = M.write_reference_json(m, str(tmp_path), "Case", "Run")
+    a = run_driver(shim, part, "Case.1.$.json", str(tmp_path / "cpp.trace"))[0]
+    env = dict(os.environ, SVLGPU_TRACE=str(tmp_path / "py.trace"))
+    env.pop("RANK", None)
+    r = subprocess.run([sys.executable, "-c", _PY_CASE.format(root=ROOT, shim=shim), case], capture_output=True, text=True, env=env,
+                       timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    b = open(str(tmp_path / "py.trace")).read().splitlines()
+    da, db = [l for l in a if l.startswith("add_drm_load")], [l for l in b if l.startswith("add_drm_load")]
+    assert len(da) == 1 and da == db
