@@ -98,6 +98,8 @@ def _canon(lines):
             out["loads"].add((kv["nnodes"], kv["nt"], kv["factor"], kv["nodes"], kv["series"]))
         elif name == "add_node_recorder":
             out["recorders"].append((kv["field"], kv["nnodes"], kv["nodes"]))
+        elif name == "add_drm_load":
+            out["drm"] = kv
         elif name == "set_option" and "pml_collective" in l:
             out["options"].add(l)
     return out
@@ -107,6 +109,7 @@ def _canon(lines):
     ("kat444", 2, "P.block_epart((4, 4, 4), (1, 1, 2))"),
     ("lysmer_column", 4, "P.block_epart((3, 3, 6), (2, 1, 2))"),
     ("hex8_layered_rayleigh", 2, "P.block_epart((4, 3, 6), (1, 1, 2))"),
+    ("drm_box", 4, "P.block_epart((6, 6, 5), (2, 2, 1))"),
     ("pml3d", 2, "P.centroid_epart(m, (1, 1, 2))"),
     ("pml2d", 3, "np.random.default_rng(5).integers(0, 3, m.n_elem).astype(np.int32)"),
 ])
@@ -136,6 +139,8 @@ def test_driver_on_reference_rank_files_matches_python_partitioner_at_the_c_abi(
         assert sum(int(r[1]) for r in a["recorders"]) >= sum(int(r[1]) for r in b["recorders"])
         if case == "hex8_layered_rayleigh":
             assert a["rayleigh"] == b["rayleigh"] and a["rayleigh"]
+        if case == "drm_box":
+            assert a.get("drm") == b.get("drm") and a.get("drm")            # every rank of this split holds DRM elements
         assert a["comm_init"]["rank"] == str(rank) and a["comm_init"]["nranks"] == str(nparts)
         if case.startswith("pml"):
             assert a["options"] and a["constraints"]
