@@ -386,3 +386,17 @@ def test_cabi_builder_argument_errors_and_no_cpu_fallback():
         m = cases.kat444()
         with pytest.raises(capi.SvlError, match="no CUDA device|no usable CUDA"):
             capi.DeviceModel(m)
+
+
+def test_bench_reads_the_hbm_peak_from_any_reasonable_measured_peaks_schema():
+    """bench.py takes roofline.peak from the driver-written MEASURED_PEAKS.json, whose schema this repo does not control."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert b.pick_hbm_peak({"hbm_gbs": 6540.0}) == (6540.0, "hbm_gbs")
+    assert b.pick_hbm_peak({"hbm_copy_gbs": {"burst": 7100, "sustained": 6540}, "bf16_dense_tflops": 1500})[0] == 6540.0
+    assert b.pick_hbm_peak({"peaks": {"hbm_tb_s": 6.54, "bf16_tf_s": 1600}})[0] == pytest.approx(6540.0)
+    assert b.pick_hbm_peak({"copy_bandwidth_GBps": 6600, "cublas_bf16_TFLOPs": 1700})[0] == 6600.0
+    assert b.pick_hbm_peak({"bf16_tflops": 1700}) is None and b.pick_hbm_peak({}) is None
