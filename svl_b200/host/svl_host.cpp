@@ -25,6 +25,7 @@
 #include <sstream>
 #include <string>
 #include <strings.h>
+#include <signal.h>
 #include <sys/wait.h>
 #include <time.h>
 #include <tuple>
@@ -655,8 +656,19 @@ int main(int argc, char **argv) {
             kids.push_back(pid);
         }
         if (!kids.empty()) {
+            // a rank that stops (bad input, solver stop) would leave the others waiting in a collective: take them down with it
             int worst = 0;
-            for (pid_t k : kids) { int st = 0; waitpid(k, &st, 0); worst = std::max(worst, WIFEXITED(st) ? WEXITSTATUS(st) : 1); }
+            size_t left = kids.size();
+            while (left) {
+                int st = 0;
+                const pid_t done = waitpid(-1, &st, 0);
+                if (done < 0) break;
+                left--;
+                const int rc = WIFEXITED(st) ? WEXITSTATUS(st) : 1;
+                if (rc != 0 && worst == 0)
+                    for (pid_t k : kids) if (k != done) kill(k, SIGTERM);
+                worst = std::max(worst, rc);
+            }
             return worst;
         }
     }

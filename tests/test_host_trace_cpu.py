@@ -226,3 +226,26 @@ def test_drm_text_files_reach_the_c_abi_bit_for_bit(shim, tmp_path, case):
     b = open(str(tmp_path / "py.trace")).read().splitlines()
     da, db = [l for l in a if l.startswith("add_drm_load")], [l for l in b if l.startswith("add_drm_load")]
     assert len(da) == 1 and da == db
+
+
+def test_launcher_takes_the_other_ranks_down_when_one_stops(shim, tmp_path):
+    """`-np N`: a rank that stops (here: rank 1 cannot read its load file) must not leave the others waiting for it -- in a real run
+    they would sit in an NCCL collective until a timeout kills the job.  The launcher returns promptly with a non-zero code."""
+    import json
+    import time
+    m = cases.kat444()
+    m.point_loads[0].nodes[:] = 124                                   # a node of the upper half: the load goes to rank 1
+    part = M.write_reference_partitions(m, P.block_epart((4, 4, 4), (1, 1, 2)), 2, str(tmp_path), "Case", "Run")
+    jp = os.path.join(part, "Case.1.1.json")
+    J = json.load(open(jp))
+    assert "Loads" in J and "Loads" not in json.load(open(os.path.join(part, "Case.1.0.json")))
+    for L in J["Loads"].values():
+        L["attributes"]["file"] = os.path.join(part, "missing_series.txt")
+    json.dump(J, open(jp, "w"))
+    env = dict(os.environ, LD_PRELOAD=shim, SVLGPU_TRACE=str(tmp_path / "t"))
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    t0 = time.time()
+    r = subprocess.run([EXE, "-np", "2", "-dir", part, "-file", "Case.1.$.json"], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode != 0 and time.time() - t0 < 30.0
+    assert "cannot read load file" in r.stdout
