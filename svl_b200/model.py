@@ -359,7 +359,8 @@ def write_reference_json(m: Model, directory: str, name: str = "Model", combo: s
     # dampings: FREE on everything unless Rayleigh given (SeismoVLAB.py:704-707)
     if binary:
         stem = os.path.join(part, f"{name}.1.0")
-        _write_binary_tables(m, stem)
+        if not _return_entities:                                      # write_reference_partitions writes each rank's share itself
+            _write_binary_tables(m, stem)
         J["Nodes"] = {"binary": os.path.basename(stem + ".nodes.bin"), "count": m.n_nodes}
         J["Elements"] = {"binary": os.path.basename(stem + ".elems.bin"), "count": m.n_elem}
         J["Dampings"] = {"binary": os.path.basename(stem + ".elems.bin")}
@@ -428,44 +429,56 @@ def write_reference_json(m: Model, directory: str, name: str = "Model", combo: s
     return part
 
 
-def _write_binary_tables(m: Model, stem: str):
-    """the sidecars of pack_partition_tables written from the model's arrays (tags = index + 1), vectorised"""
-    n, ne = m.n_nodes, m.n_elem
+def _write_binary_tables(m: Model, stem: str, nodes=None, elems=None, cons=None):
+    """the sidecars of pack_partition_tables written from the model's arrays (tags = index + 1), vectorised.  nodes / elems /
+    cons select a partition's share (ascending node / element indices, constraint list); numbering stays the model's."""
+    nsel = np.arange(m.n_nodes) if nodes is None else np.asarray(nodes, dtype=np.int64)
+    esel = np.arange(m.n_elem) if elems is None else np.asarray(elems, dtype=np.int64)
+    cons = m.constraints if cons is None else cons
+    n, ne = len(nsel), len(esel)
+    ndof = np.asarray(m.node_ndof, "<i4")[nsel]
+    if nodes is None:
+        dofs = np.arange(m.n_total)
+    else:                                                             # dofs of the selected nodes, node-major
+        start = np.asarray(m.node_ptr)[nsel]
+        dofs = np.repeat(start - np.concatenate([[0], np.cumsum(ndof)[:-1]]), ndof) + np.arange(int(ndof.sum()))
     with open(stem + ".nodes.bin", "wb") as f:
         f.write(b"SVLN" + np.array([1], "<u4").tobytes() + np.array([n], "<u8").tobytes() + np.array([m.ndim], "<u4").tobytes())
-        for a in (np.arange(1, n + 1, dtype="<u4"), np.asarray(m.node_ndof, "<i4"), np.asarray(m.coords, "<f8"),
-                  np.asarray(m.totaldof, "<i4"), np.asarray(m.freedof_flat, "<i4")):
+        for a in ((nsel + 1).astype("<u4"), ndof, np.asarray(m.coords, "<f8")[nsel],
+                  np.asarray(m.totaldof, "<i4")[dofs], np.asarray(m.freedof_flat, "<i4")[dofs]):
             f.write(np.ascontiguousarray(a).tobytes())
-    kind = np.asarray(m.elem_kind, "<i4")
+    kind = np.asarray(m.elem_kind, "<i4")[esel]
     nconn = np.array([0] + [ELEM_NODES[k] for k in (1, 2, 3, 4, 5)], "<i4")[kind]
     conn = np.zeros((ne, 8), "<u4")
+    econn = np.asarray(m.elem_conn)[esel]
     for npe in np.unique(nconn):
         sel = nconn == npe
-        conn[sel, :npe] = np.asarray(m.elem_conn)[sel, :npe] + 1
-    attr = np.zeros((ne, 10), "<f8") if m.elem_attr is None else np.asarray(m.elem_attr, "<f8").copy()
+        conn[sel, :npe] = econn[sel, :npe] + 1
+    attr = np.zeros((ne, 10), "<f8") if m.elem_attr is None else np.asarray(m.elem_attr, "<f8")[esel].copy()
     nattr = np.array([0, 0, 1, 9, 8, 1])[kind]                       # meaningful leading entries per kind
     attr[np.arange(10)[None, :] >= nattr[:, None]] = 0.0
-    am = np.zeros(ne, "<f8") if m.elem_am is None else np.asarray(m.elem_am, "<f8")
-    ak = np.zeros(ne, "<f8") if m.elem_ak is None else np.asarray(m.elem_ak, "<f8")
+    am = np.zeros(ne, "<f8") if m.elem_am is None else np.asarray(m.elem_am, "<f8")[esel]
+    ak = np.zeros(ne, "<f8") if m.elem_ak is None else np.asarray(m.elem_ak, "<f8")[esel]
     ray = ((am != 0) | (ak != 0)).astype("u1")
     with open(stem + ".elems.bin", "wb") as f:
         f.write(b"SVLE" + np.array([1], "<u4").tobytes() + np.array([ne], "<u8").tobytes())
-        for a in (np.arange(1, ne + 1, dtype="<u4"), kind, (np.asarray(m.elem_mat) + 1).astype("<u4"), nconn, conn, attr, am, ak, ray):
+        for a in ((esel + 1).astype("<u4"), kind, (np.asarray(m.elem_mat)[esel] + 1).astype("<u4"), nconn, conn, attr, am, ak, ray):
             f.write(np.ascontiguousarray(a).tobytes())
-    if m.constraints:
-        if any(len(c[2]) != 1 for c in m.constraints):
+    if cons:
+        if any(len(c[2]) != 1 for c in cons):
             raise ValueError("binary tables hold single-master (EQUAL) constraints only")
         with open(stem + ".cons.bin", "wb") as f:
-            f.write(b"SVLC" + np.array([1], "<u4").tobytes() + np.array([len(m.constraints)], "<u8").tobytes())
-            f.write(np.array([c[0] for c in m.constraints], "<i8").tobytes())
-            f.write(np.array([c[1] for c in m.constraints], "<i4").tobytes())
-            f.write(np.array([c[2][0] for c in m.constraints], "<i4").tobytes())
-            f.write(np.array([c[3][0] for c in m.constraints], "<f8").tobytes())
+            f.write(b"SVLC" + np.array([1], "<u4").tobytes() + np.array([len(cons)], "<u8").tobytes())
+            f.write(np.array([c[0] for c in cons], "<i8").tobytes())
+            f.write(np.array([c[1] for c in cons], "<i4").tobytes())
+            f.write(np.array([c[2][0] for c in cons], "<i4").tobytes())
+            f.write(np.array([c[3][0] for c in cons], "<f8").tobytes())
 
 
 def write_reference_partitions(m: Model, epart, nparts: int, directory: str, name: str = "Model", combo: str = "Run",
-                               resp=("disp",), integrator: str = "CENTRALDIFFERENCE", ndps: int = 16) -> str:
-    """One JSON file per rank, <directory>/Partition/<name>.1.<rank>.json, the way the reference pre-processor splits a model
+                               resp=("disp",), integrator: str = "CENTRALDIFFERENCE", ndps: int = 16, binary: bool = False) -> str:
+    """binary=True: <name>.1.<rank>.bin.json with the big tables in sidecars, written from the arrays (no per-entity dicts).
+    One JSON file per rank, <directory>/Partition/<name>.1.<rank>.json, the way the reference pre-processor splits a model
     after METIS (Core/SeismoVLAB.py:300-420 createPartitions, :49-298 Entities2Processor): GLOBAL tags and GLOBAL total /
     free dof numbers everywhere (`Global.ntotal / nfree` are the whole model's), a partition holds the nodes of its elements
     plus the master nodes of the constraints whose slave dofs it holds (:381-392), nodal masses and the nodes of a point load
@@ -473,33 +486,50 @@ def write_reference_partitions(m: Model, epart, nparts: int, directory: str, nam
     `<resp>.<rank>.out` (:237-246), combinations keep the loads present in the partition.  `epart[e]` is the rank of element e
     (elements beyond len(epart), e.g. dashpots, follow partition.split_model's rule).  Returns the partition directory."""
     from . import partition as P
-    part, J = write_reference_json(m, directory, name, combo, resp, integrator, ndps, _return_entities=True)
+    part, J = write_reference_json(m, directory, name, combo, resp, integrator, ndps, _return_entities=True, binary=binary)
     subs = P.split_model(m, epart, nparts, tie_closure="slave")       # element / node sets only; numbering stays global here
     taken_mass, taken_load = set(), {k: set() for k in J["Loads"]}
+    fd_all = np.asarray(m.freedof_flat)
     for r, s in enumerate(subs):
         ntags = [int(n) + 1 for n in s.global_nodes]
         nset = set(ntags)
         etags = [int(e) + 1 for e in s.global_elems]
         eset = set(etags)
         K = {"Global": J["Global"], "Materials": J["Materials"]}
-        K["Nodes"] = {str(t): J["Nodes"][str(t)] for t in ntags}
         masses = {t: v for t, v in J.get("Masses", {}).items() if int(t) in nset and t not in taken_mass}
         taken_mass.update(masses)
-        if masses:
-            K["Masses"] = masses
-        cons = {}
-        for t in ntags:
-            for f in J["Nodes"][str(t)]["freedof"]:
-                if f < -1:
-                    cons[str(f)] = J["Constraints"][str(f)]
-        if cons:
-            K["Constraints"] = cons
-        K["Elements"] = {str(t): J["Elements"][str(t)] for t in etags}
-        K["Dampings"] = {}
-        for d, D in J["Dampings"].items():
-            lst = [t for t in D["attributes"]["list"] if t in eset]
-            if lst:
-                K["Dampings"][d] = {"name": D["name"], "attributes": dict(D["attributes"], list=lst)}
+        if binary:
+            # constraints whose slave dof sits on a node of this partition, in the model's order
+            held = np.zeros(m.n_nodes, dtype=bool)
+            held[s.global_nodes] = True
+            node_of_total = np.repeat(np.arange(m.n_nodes), np.diff(m.node_ptr))
+            mine = [c for c in m.constraints if held[node_of_total[c[1]]]]
+            stem = os.path.join(part, f"{name}.1.{r}")
+            _write_binary_tables(m, stem, nodes=s.global_nodes, elems=s.global_elems, cons=mine)
+            K["Nodes"] = {"binary": os.path.basename(stem + ".nodes.bin"), "count": len(ntags)}
+            if masses:
+                K["Masses"] = masses
+            if mine:
+                K["Constraints"] = {"binary": os.path.basename(stem + ".cons.bin"), "count": len(mine)}
+            K["Elements"] = {"binary": os.path.basename(stem + ".elems.bin"), "count": len(etags)}
+            K["Dampings"] = {"binary": os.path.basename(stem + ".elems.bin")}
+        else:
+            K["Nodes"] = {str(t): J["Nodes"][str(t)] for t in ntags}
+            if masses:
+                K["Masses"] = masses
+            cons = {}
+            for t in ntags:
+                for f in J["Nodes"][str(t)]["freedof"]:
+                    if f < -1:
+                        cons[str(f)] = J["Constraints"][str(f)]
+            if cons:
+                K["Constraints"] = cons
+            K["Elements"] = {str(t): J["Elements"][str(t)] for t in etags}
+            K["Dampings"] = {}
+            for d, D in J["Dampings"].items():
+                lst = [t for t in D["attributes"]["list"] if t in eset]
+                if lst:
+                    K["Dampings"][d] = {"name": D["name"], "attributes": dict(D["attributes"], list=lst)}
         loads = {}
         for l, L in J["Loads"].items():
             if L["name"] == "POINTLOAD":
@@ -523,7 +553,7 @@ def write_reference_partitions(m: Model, epart, nparts: int, directory: str, nam
         if recs:
             K["Recorders"] = recs
         K["Simulations"] = J["Simulations"]
-        with open(os.path.join(part, f"{name}.1.{r}.json"), "w") as f:
+        with open(os.path.join(part, f"{name}.1.{r}.bin.json" if binary else f"{name}.1.{r}.json"), "w") as f:
             json.dump(K, f, indent=4)
     return part
 

@@ -124,6 +124,9 @@ def test_driver_on_reference_rank_files_matches_python_partitioner_at_the_c_abi(
     part = M.write_reference_partitions(m, ep, nparts, str(tmp_path), "Case", "Run")
     left = run_driver(shim, part, "Case.1.$.json", str(tmp_path / "cpp.trace"), nparts)
     assert not [f for f in os.listdir(part) if f.startswith(".svlgpu_nccl_id")]          # rank 0 removed the id file
+    # the same rank files with their tables in binary sidecars, written straight from the arrays: identical calls
+    M.write_reference_partitions(m, ep, nparts, str(tmp_path), "Case", "Run", binary=True)
+    assert run_driver(shim, part, "Case.1.$.bin.json", str(tmp_path / "cppbin.trace"), nparts) == left
     for rank in range(nparts):
         env = dict(os.environ, SVLGPU_TRACE=str(tmp_path / "py.trace"), RANK=str(rank))
         r = subprocess.run([sys.executable, "-c", _PY_RANK.format(root=ROOT, shim=shim), case, str(nparts), str(rank), how],
