@@ -400,3 +400,55 @@ def test_bench_reads_the_hbm_peak_from_any_reasonable_measured_peaks_schema():
     assert b.pick_hbm_peak({"peaks": {"hbm_tb_s": 6.54, "bf16_tf_s": 1600}})[0] == pytest.approx(6540.0)
     assert b.pick_hbm_peak({"copy_bandwidth_GBps": 6600, "cublas_bf16_TFLOPs": 1700})[0] == 6600.0
     assert b.pick_hbm_peak({"bf16_tflops": 1700}) is None and b.pick_hbm_peak({}) is None
+
+
+def test_interior_hex8_stencil_is_a_sum_of_tensor_products(oracle):
+    """Groundwork for the next kernel round: on a uniform lattice of cubes the 27 x (3 x 3) stencil the
+    block-stencil kernel applies at an interior node -- assembled here from the oracle's lin3DHexa8 stiffness (lin3DHexa8.cpp:288-318)
+    over the 8 surrounding elements -- equals, to rounding,
+        K_aa = (lam + 2 mu) S_a M_b M_c + mu (M_a S_b M_c + M_a M_b S_c),      K_ab = -(lam + mu) D_a D_b M_c   (a != b)
+    with the 1-D stencils M = h/6 [1 4 1], S = 1/h [-1 2 -1], D = 1/2 [-1 0 1]: about 70 FP64 instructions per node when applied
+    direction by direction, instead of the 153 DFMA of the symmetric 27-point form."""
+    import ctypes as C
+    dp = C.POINTER(C.c_double)
+    E, nu, h = 1.3e7, 0.3, 0.7
+    lam, mu = E * nu / ((1 + nu) * (1 - 2 * nu)), E / (2 * (1 + nu))
+    Cm = np.zeros(36)
+    oracle.lib.svlo_elastic3d_C(C.c_double(E), C.c_double(nu), Cm.ctypes.data_as(dp))
+    nid = lambda i, j, k: i + 3 * j + 9 * k                                  # noqa: E731
+    pos = [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]
+    K = np.zeros((81, 81))
+    for ck in range(2):
+        for cj in range(2):
+            for ci in range(2):
+                nodes = [nid(ci + a, cj + b, ck + c) for a, b, c in pos]
+                X = np.array([[(ci + a) * h, (cj + b) * h, (ck + c) * h] for a, b, c in pos]).ravel()
+                Ke = np.zeros(576)
+                oracle.lib.svlo_hex8_stiffness(X.ctypes.data_as(dp), Cm.ctypes.data_as(dp), Ke.ctypes.data_as(dp))
+                Ke = Ke.reshape(24, 24)
+                for p, n_p in enumerate(nodes):
+                    for q, n_q in enumerate(nodes):
+                        K[3 * n_p:3 * n_p + 3, 3 * n_q:3 * n_q + 3] += Ke[3 * p:3 * p + 3, 3 * q:3 * q + 3]
+    c = nid(1, 1, 1)
+    st = np.zeros((3, 3, 3, 3, 3))                                           # [di+1][dj+1][dk+1][a][b]
+    for k in range(3):
+        for j in range(3):
+            for i in range(3):
+                st[i, j, k] = K[3 * c:3 * c + 3, 3 * nid(i, j, k):3 * nid(i, j, k) + 3]
+    M1, S1, D1 = h / 6 * np.array([1, 4, 1.0]), 1 / h * np.array([-1, 2, -1.0]), 0.5 * np.array([-1, 0, 1.0])
+    T = lambda a, b, c_: np.einsum("i,j,k->ijk", a, b, c_)                  # noqa: E731
+    F = np.zeros_like(st)
+    for a in range(3):
+        for b in range(3):
+            t = [M1, M1, M1]
+            if a == b:
+                t[a] = S1
+                F[..., a, a] += (lam + 2 * mu) * T(*t)
+            else:
+                t[b] = S1
+                F[..., a, a] += mu * T(*t)
+                t = [M1, M1, M1]
+                t[a] = D1
+                t[b] = D1
+                F[..., a, b] += -(lam + mu) * T(*t)
+    assert np.abs(F - st).max() <= 1e-14 * np.abs(st).max()
