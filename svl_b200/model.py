@@ -786,8 +786,27 @@ def read_reference_json(path: str, base_dir: Optional[str] = None) -> Model:
     for ltag, factor in zip(combo.get("load", []), combo.get("factor", [])):
         L = J["Loads"][str(ltag)]
         a = L["attributes"]
+        if L["name"].upper() == "ELEMENTLOAD" and a["type"].upper() == "GENERALWAVE":
+            # DRM: one `.drm` text file per node of the listed elements, `nt nFields cond` then nt rows (Driver.hpp:1689-1721);
+            # '$' in the file pattern -> node tag; nodes in ascending tag order (the reference's std::map)
+            if m.drm is not None:
+                raise ValueError("read_reference_json: one GENERALWAVE load per combination")
+            elems = np.array([eidx[int(t)] for t in a["list"]], dtype=np.int32)
+            etag_of = {i: t for t, i in eidx.items()}
+            tags = sorted({int(n) for e in elems for n in J["Elements"][str(etag_of[int(e)])]["conn"]})
+            fields, ext = [], []
+            for t in tags:
+                fn = a["file"].replace("$", str(t))
+                fn = fn if os.path.isabs(fn) else os.path.join(base, fn)
+                tok = open(fn).read().split()
+                nt_, nf_, cond = int(tok[0]), int(tok[1]), int(tok[2])
+                fields.append(np.array([float(v) for v in tok[3:3 + nt_ * nf_]]).reshape(nt_, nf_))
+                ext.append(1 if cond else 0)
+            m.drm = DRMLoad(elems=elems, nodes=np.array([nidx[t] for t in tags], dtype=np.int32), exterior=np.array(ext, dtype=np.uint8),
+                            field=np.stack(fields), factor=float(factor))
+            continue
         if L["name"].upper() != "POINTLOAD" or a["type"].upper() != "CONCENTRATED":
-            raise ValueError("read_reference_json: only CONCENTRATED point loads are handled by this reader")
+            raise ValueError("read_reference_json: only CONCENTRATED point loads and GENERALWAVE element loads are handled by this reader")
         if a["name"].upper() == "CONSTANT":
             series = np.array([float(a["mag"])])
         else:

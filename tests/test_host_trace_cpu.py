@@ -161,7 +161,7 @@ d.close()
 
 
 @pytest.mark.parametrize("case", ["kat444", "kat444_masses", "pml2d", "pml3d", "lysmer_column", "hex8_layered_rayleigh", "j2ps_area",
-                                  "F06", "F11"])
+                                  "drm_box", "drm_area", "F06", "F11"])
 def test_cpp_driver_and_python_binding_hand_the_device_the_same_model(shim, tmp_path, case):
     """One partition file, two front ends: `SeismoVLAB_gpu.exe` (svl_host.cpp UpdateMesh + Initialize) and
     `model.read_reference_json` + `capi.DeviceModel` (what the GPU parity tests drive).  Nodes, numbering, materials, elements,
@@ -195,9 +195,11 @@ def test_cpp_driver_and_python_binding_hand_the_device_the_same_model(shim, tmp_
     assert r.returncode == 0, r.stdout + r.stderr
     a = _canon(open(str(tmp_path / "cpp.trace")).read().splitlines())
     b = _canon(open(str(tmp_path / "py.trace")).read().splitlines())
-    for key in ("create", "set_nodes", "finalize", "materials", "elements", "constraints", "rayleigh", "loads"):
+    for key in ("create", "set_nodes", "finalize", "materials", "elements", "constraints", "rayleigh", "loads", "drm"):
         assert a.get(key) == b.get(key), key
     assert a["recorders"][0] == b["recorders"][0]
+    if case.startswith("drm"):
+        assert a.get("drm")
     masses = lambda path: sorted(l for l in open(path).read().splitlines() if l.startswith("add_nodal_mass"))     # noqa: E731
     assert masses(str(tmp_path / "cpp.trace")) == masses(str(tmp_path / "py.trace"))
 

@@ -209,7 +209,7 @@ def test_j2_plane_strain_return_map_matches_reference_fixture_stress_paths(oracl
             assert yielded > 5
 
 
-@pytest.mark.parametrize("name", ["kat444", "lysmer_area", "pml2d", "hex8_layered_rayleigh", "j2ps_area"])
+@pytest.mark.parametrize("name", ["kat444", "lysmer_area", "pml2d", "hex8_layered_rayleigh", "j2ps_area", "drm_box"])
 def test_reference_json_writer_reader_round_trip(oracle, tmp_path, name):
     """write_reference_json -> read_reference_json gives a model the oracle advances to the same history (the reader
     renumbers nodes / dofs by ascending tag and maps the constraints' slave-total / master-free dofs)."""
