@@ -12,9 +12,13 @@
  * Parity pinning: validated against (a) the reference's own classes compiled
  * unmodified into oracle/_ref/libsvlref_probe.so (element vectors, matrices,
  * J2 return map), (b) NODE recorder histories written by the reference
- * executable oracle/_ref/SeismoVLAB.exe for CentralDifference runs, committed
- * as fixtures under tests/golden/ (generator: tests/golden/make_golden.py),
- * (c) the known answers of SURVEY.md App. B.5.
+ * executable oracle/_ref/SeismoVLAB.exe for CentralDifference, NewmarkBeta,
+ * ExtendedNewmarkBeta and NewmarkBeta + NewtonRaphson runs, committed as
+ * fixtures under tests/golden/ (generator: tests/golden/make_golden.py),
+ * (c) the known answers of SURVEY.md App. B.5, (d) the reference's own
+ * validation fixtures J05, J02, F02, F06, F03, F07 (OpenSees histories and
+ * Gauss-point recorder files) and F11, J12 (their input files run through the
+ * reference executable): tests/golden/fixtures/, tests/golden/J05/.
  */
 #ifndef SVL_ORACLE_H
 #define SVL_ORACLE_H
