@@ -414,7 +414,9 @@ class CentralDifference {
     svlgpu_model *handle() { return h; }
 
     // CentralDifference::Initialize (:35-71) + Mesh::Initialize: hands the object graph to the device
-    bool Initialize(const LoadCombo &combo, const std::vector<RecorderSpec> &recs, int nt, int device) {
+    // keep_gauss: ELEMENT recorders (Gauss-point strain / stress) are asked for -- the listed elements must then run through the
+    // Gauss-point kernels, so the lattice fast path is switched off for this run
+    bool Initialize(const LoadCombo &combo, const std::vector<RecorderSpec> &recs, int nt, int device, bool keep_gauss = false) {
         h = svlgpu_create(mesh.ndim, mesh.lumped ? 1 : 0);
         if (!h) return fail();
         std::vector<int32_t> ndof, total, freed;
@@ -484,6 +486,7 @@ class CentralDifference {
             if (svlgpu_add_node_recorder(h, field, (int)nodes.size(), nodes.data(), nt) < 0) return fail();
         }
         if (newmark && svlgpu_set_option(h, "integrator", 1.0)) return fail();
+        if (keep_gauss && (svlgpu_set_option(h, "keep_gauss", 1.0) || svlgpu_set_option(h, "lattice_guess", 0.0))) return fail();
         for (auto &kv : mesh.Halos)
             if (svlgpu_add_halo(h, kv.first, (int)kv.second.size(), kv.second.data())) return fail();
         if (mesh.pml_collective && !mesh.Halos.empty() && svlgpu_set_option(h, "pml_collective", 1.0)) return fail();
@@ -594,12 +597,61 @@ class Recorder {
     RecorderSpec spec; int id; std::ofstream out;
 };
 
+// ELEMENT recorder, responses STRAIN / STRESS (Recorder.cpp:106-160 header, :270-300 rows): Element::GetStrain / GetStress at the
+// Gauss points of the listed elements, one row per step, element by element, Gauss point by Gauss point
+class ElementRecorder {
+  public:
+    ElementRecorder(const RecorderSpec &s) : spec(s) {}
+    void Initialize(const Mesh &mesh, const std::string &dir, const std::string &combo, unsigned nsteps) {
+        out.open(dir + "/../Solution/" + combo + "/" + spec.file);
+        out.precision(spec.precision);
+        out.setf(std::ios::scientific);
+        out << spec.ids.size() << " " << mesh.ntotal << " " << nsteps << "\n";
+        width = 0;
+        for (unsigned id : spec.ids) {
+            const Element &e = mesh.Elements.at(id);
+            const bool hex = e.kind == SVLGPU_LIN3DHEXA8;
+            out << id << " " << (hex ? 8 : 4) << " " << (hex ? 6 : 3) << "\n";
+            idx.push_back(e.index);
+            width += hex ? 48 : 12;
+        }
+    }
+    // after a step: Gauss-point values of the current state (the caller has just run an internal-force pass on it)
+    bool WriteResponse(svlgpu_model *h) {
+        std::vector<double> buf(width);
+        const int field = ieq(spec.resp, "STRAIN") ? SVLGPU_STRAIN : SVLGPU_STRESS;
+        if (svlgpu_get_gauss(h, field, (int)idx.size(), idx.data(), buf.data())) return true;
+        for (double v : buf) out << v << " ";
+        out << "\n";
+        return false;
+    }
+    void Finalize() { out.close(); }
+  private:
+    RecorderSpec spec; std::vector<int32_t> idx; size_t width = 0; std::ofstream out;
+};
+
 // ---- Analysis (08-Analysis/02-Dynamic/DynamicAnalysis.cpp:25-64) ----------------------------------------------------------
 class DynamicAnalysis {
   public:
     DynamicAnalysis(Mesh &mesh, CentralDifference &integ, std::vector<Recorder> &recs, unsigned nt) : mesh(mesh), integ(integ), recs(recs), nt(nt) {}
+    std::vector<ElementRecorder> erecs;
     bool Analyze(const std::string &dir, const LoadCombo &combo) {
         for (auto &r : recs) r.Initialize(mesh, dir, combo.folder, nt);
+        if (!erecs.empty()) {
+            // Gauss-point histories: step by step, with a force pass on the new state before every row (the step itself
+            // evaluates the elements at its starting state); DynamicAnalysis.cpp:36-57 order: step, then WriteRecorders
+            for (auto &r : erecs) r.Initialize(mesh, dir, combo.folder, nt);
+            bool stop = false;
+            std::vector<double> scratch(mesh.ntotal_dev);
+            for (unsigned k = 1; k < nt && !stop; k++) {
+                stop = integ.ComputeSteps(k, k + 1) || svlgpu_internal_force(integ.handle(), scratch.data()) != 0;
+                for (auto &r : erecs) stop = stop || r.WriteResponse(integ.handle());
+            }
+            std::cout << " RUNNING (" << combo.name << ") : 100%\n";
+            for (auto &r : recs) { stop = r.WriteResponse(integ.handle()) || stop; r.Finalize(); }
+            for (auto &r : erecs) r.Finalize();
+            return stop;
+        }
         // k = 1 .. nt-1 (DynamicAnalysis.cpp:36): recorder rows are kept on the device and written at the end
         bool stop = false;
         const unsigned chunk = 256;
@@ -713,13 +765,21 @@ int main(int argc, char **argv) {
             }
             const unsigned nt = (unsigned)A["analysis"]["nt"].as_int();
             const double dt = A["integrator"]["dt"].as_double();
-            std::vector<RecorderSpec> specs;
+            std::vector<RecorderSpec> specs, especs;
             for (auto &kv : by_tag(J["Recorders"])) {
                 RecorderSpec r;
                 r.name = (*kv.second)["name"].as_string();
-                if (!ieq(r.name, "NODE")) { std::cout << " WARNING: recorder " << r.name << " is not written by the GPU path\n"; continue; }
                 r.file = (*kv.second)["file"].as_string();
                 r.resp = (*kv.second)["resp"].as_string("disp");
+                // ELEMENT recorders were written after the last GPU pass of the round: opt-in until hardware has seen them
+                if (getenv("SVLGPU_ELEMENT_RECORDERS") && ieq(r.name, "ELEMENT") && (ieq(r.resp, "STRAIN") || ieq(r.resp, "STRESS"))) {
+                    r.precision = (*kv.second)["ndps"].as_int(6);
+                    for (auto &x : (*kv.second)["list"].arr) r.ids.push_back((unsigned)x.as_int());
+                    bool solid = true;
+                    for (unsigned id : r.ids) { const int kd = mesh.Elements.at(id).kind; solid = solid && (kd == SVLGPU_LIN3DHEXA8 || kd == SVLGPU_LIN2DQUAD4); }
+                    if (solid) { especs.push_back(r); continue; }
+                }
+                if (!ieq(r.name, "NODE")) { std::cout << " WARNING: recorder " << r.name << " (" << r.resp << ") is not written by the GPU path\n"; continue; }
                 if (ieq(r.resp, "REACTION")) { std::cout << " WARNING: REACTION recorder skipped\n"; continue; }
                 r.precision = (*kv.second)["ndps"].as_int(6);
                 r.nsample = (*kv.second)["nsamp"].as_int(1);
@@ -727,11 +787,13 @@ int main(int argc, char **argv) {
                 specs.push_back(r);
             }
             CentralDifference integrator(mesh, dt, newmark);
-            if (integrator.Initialize(combo, specs, (int)nt, device)) return 1;
+            if (!especs.empty()) std::cout << " NOTE: ELEMENT recorders: all elements run through the Gauss-point kernels, one force pass per recorded step\n";
+            if (integrator.Initialize(combo, specs, (int)nt, device, !especs.empty())) return 1;
             if (world > 1 && integrator.JoinRanks(dir, rank, world)) return 1;
             std::vector<Recorder> recorders;
             for (size_t i = 0; i < specs.size(); i++) recorders.emplace_back(specs[i], (int)i);
             DynamicAnalysis analysis(mesh, integrator, recorders, nt);
+            for (auto &e : especs) analysis.erecs.emplace_back(e);
             if (analysis.Analyze(dir, combo)) { std::cout << "\x1B[31m ERROR: \x1B[0mthe analysis stopped: " << svlgpu_last_error() << "\n"; return 1; }
             svlgpu_counters c;
             svlgpu_get_counters(integrator.handle(), &c);

@@ -456,6 +456,30 @@ def test_device_matches_reference_fixture_from_its_own_input_files(oracle, tmp_p
         assert cases.fixture_errors(name, hist, key) < 2e-5, key          # recorder files carry ndps = 8 digits
 
 
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: first hardware run decides; remove the marker then")
+def test_host_driver_element_recorders_match_fixture_f02_opensees_stress(tmp_path):
+    """The reference's fixture F02 as shipped (NODE + ELEMENT recorders) through the C++ driver: Stress.0.out / Strain.0.out in the
+    reference's layout, compared the way the fixture's own cmpResults.py does it (4th Gauss point <-> OpenSees columns 7 8 9)."""
+    import json
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "svl_b200", "SeismoVLAB_gpu.exe")
+    shutil.copytree(cases.fixture_dir("F02"), str(tmp_path / "fx"))
+    part = str(tmp_path / "fx" / "Partition")
+    J = json.load(open(os.path.join(part, "Debugging_F02.1.0.json")))
+    folder = J["Combinations"][str(J["Simulations"]["combo"])]["attributes"]["folder"]
+    os.makedirs(os.path.join(str(tmp_path / "fx"), "Solution", folder))
+    r = subprocess.run([exe, "-dir", part, "-file", "Debugging_F02.1.$.json"], capture_output=True, text=True, timeout=300,
+                       cwd=str(tmp_path / "fx"), env=dict(os.environ, SVLGPU_ELEMENT_RECORDERS="1"))
+    assert r.returncode == 0, r.stdout + r.stderr
+    g = np.load(os.path.join(cases.fixture_dir("F02"), "opensees_gauss.npz"))
+    stress = np.loadtxt(os.path.join(str(tmp_path / "fx"), "Solution", folder, "Stress.0.out"), skiprows=2)
+    rrms = lambda a, b: np.sqrt(np.mean((a - b) ** 2)) / np.sqrt(np.mean(b ** 2))      # noqa: E731
+    for ours, col in ((9, 7), (10, 8), (11, 9)):
+        assert rrms(stress[:, ours], g["stress"][:, col]) < 5e-6
+
+
 def test_consistent_mass_fixture_is_refused_loudly():
     from svl_b200.capi import SvlError
     with pytest.raises(SvlError):

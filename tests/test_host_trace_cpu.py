@@ -254,3 +254,30 @@ def test_launcher_takes_the_other_ranks_down_when_one_stops(shim, tmp_path):
     r = subprocess.run([EXE, "-np", "2", "-dir", part, "-file", "Case.1.$.json"], capture_output=True, text=True, env=env, timeout=120)
     assert r.returncode != 0 and time.time() - t0 < 30.0
     assert "cannot read load file" in r.stdout
+
+
+def test_element_recorder_files_have_the_reference_layout(shim, tmp_path):
+    """ELEMENT recorders (responses STRAIN / STRESS) of the reference's own fixture F02, through the C++ driver against the
+    stand-in: header `<n> <ntotal> <nt>`, one `<tag> <Gauss points> <components>` line per element, then nt - 1 rows
+    (Recorder.cpp:106-160, :270-300) -- the layout the fixture's LaTeX/cmpResults.py reads with skiprows=2 -- and the driver asks
+    the library to keep Gauss-point data and to leave the lattice fast path."""
+    import json
+    import shutil
+    shutil.copytree(cases.fixture_dir("F02"), str(tmp_path / "fx"))
+    part = str(tmp_path / "fx" / "Partition")
+    J = json.load(open(os.path.join(part, "Debugging_F02.1.0.json")))
+    folder = J["Combinations"][str(J["Simulations"]["combo"])]["attributes"]["folder"]
+    os.makedirs(os.path.join(str(tmp_path / "fx"), "Solution", folder))
+    env = dict(os.environ, LD_PRELOAD=shim, SVLGPU_TRACE=str(tmp_path / "t"), SVLGPU_ELEMENT_RECORDERS="1")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    r = subprocess.run([EXE, "-dir", part, "-file", "Debugging_F02.1.$.json"], capture_output=True, text=True, env=env, timeout=120,
+                       cwd=str(tmp_path / "fx"))
+    assert r.returncode == 0, r.stdout + r.stderr
+    nt = int(J["Simulations"]["attributes"]["analysis"]["nt"])
+    for fn in ("Stress.0.out", "Strain.0.out"):
+        lines = open(os.path.join(str(tmp_path / "fx"), "Solution", folder, fn)).read().splitlines()
+        assert lines[0].split() == ["1", str(J["Global"]["ntotal"]), str(nt)] and lines[1].split() == ["1", "4", "3"]
+        assert len(lines) == 2 + nt - 1 and all(len(l.split()) == 12 for l in lines[2:])
+    opts = [l for l in open(str(tmp_path / "t")).read().splitlines() if l.startswith("set_option")]
+    assert "set_option keep_gauss=1" in opts and "set_option lattice_guess=0" in opts

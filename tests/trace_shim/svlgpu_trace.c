@@ -14,7 +14,7 @@
 #include "../../include/svlgpu.h"
 
 struct svlgpu_model {
-    int ndim, n_nodes, n_total;
+    int ndim, n_nodes, n_total, keep_gauss, n_force_passes;
     int32_t *ndof;
     int nrec;
     int rec_width[64], rec_rows[64];
@@ -97,8 +97,8 @@ int svlgpu_hint_structured_block(svlgpu_model *m, int node0, int nx, int ny, int
     return 0;
 }
 int svlgpu_set_option(svlgpu_model *m, const char *name, double value) {
-    (void)m;
     fprintf(out(), "set_option %s=%.17g\n", name, value);
+    if (strcmp(name, "keep_gauss") == 0) m->keep_gauss = value != 0.0;
     return 0;
 }
 int svlgpu_add_point_load(svlgpu_model *m, int nnodes, const int32_t *nodes, int ndir, const double *dir, int nt, const double *series, double factor) {
@@ -158,7 +158,12 @@ int svlgpu_get_state(svlgpu_model *m, int field, const int32_t *dofs, int n, dou
 }
 int svlgpu_internal_force(svlgpu_model *m, double *F) { memset(F, 0, sizeof(double) * (size_t)m->n_total); return 0; }
 int svlgpu_get_mass_diagonal(svlgpu_model *m, double *M) { memset(M, 0, sizeof(double) * (size_t)m->n_total); return 0; }
-int svlgpu_get_gauss(svlgpu_model *m, int field, int nelem, const int32_t *elems, double *outv) { (void)m; (void)field; (void)nelem; (void)elems; (void)outv; return 1; }
+int svlgpu_get_gauss(svlgpu_model *m, int field, int nelem, const int32_t *elems, double *outv) {
+    (void)field; (void)elems;
+    if (!m->keep_gauss) return 1;                      /* as the library: not kept unless asked for before finalize */
+    memset(outv, 0, sizeof(double) * (size_t)nelem * (m->ndim == 3 ? 48 : 12));
+    return 0;
+}
 int svlgpu_read_recorder(svlgpu_model *m, int rec, int r0, int r1, double *outv) {
     memset(outv, 0, sizeof(double) * (size_t)(r1 - r0) * (size_t)m->rec_width[rec]);
     return 0;
