@@ -220,7 +220,9 @@ import os
 
 import cases
 
-DEVICE_CASES = [n for n in cases.CASES]
+# kat444_masses (nodal point masses) joined the cases after the round's last GPU pass: its first hardware run decides
+DEVICE_CASES = [pytest.param(n, marks=pytest.mark.xfail(strict=False, reason="first hardware run pending")) if n == "kat444_masses" else n
+                for n in cases.CASES]
 
 
 @pytest.mark.parametrize("name", DEVICE_CASES)
