@@ -452,3 +452,17 @@ def test_interior_hex8_stencil_is_a_sum_of_tensor_products(oracle):
                 t[b] = D1
                 F[..., a, b] += -(lam + mu) * T(*t)
     assert np.abs(F - st).max() <= 1e-14 * np.abs(st).max()
+
+
+def test_every_runtime_option_of_the_library_is_documented_in_the_header():
+    """svlgpu_set_option: the names cabi.cu accepts and the names include/svlgpu.h documents are the same set."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "svl_b200", "csrc", "cabi.cu")).read()
+    body = src[src.index("int svlgpu_set_option"):]
+    body = body[:body.index("GUARD_END")]
+    accepted = set(re.findall(r'n == "([a-z_0-9]+)"', body))
+    hdr = open(os.path.join(root, "include", "svlgpu.h")).read()
+    doc = hdr[hdr.index("Planner / solver options"):hdr.index("int svlgpu_set_option")]
+    documented = set(re.findall(r'"([a-z_0-9]+)"', doc))
+    assert accepted and accepted == documented, (accepted - documented, documented - accepted)
