@@ -323,12 +323,43 @@ int pmlx_allreduce(svlgpu_model *m, double *a, size_t na, double *b, size_t nb, 
     return 0;
 }
 
+// Both sides of every pair of ranks must have derived lists of the same length, or the first exchange would wait for data that
+// never comes: swap the counts (one double per peer) and stop loudly on a mismatch.  which: 0 soil halo nodes, 1 PML unknowns
+static int verify_peer_counts(svlgpu_model *m, int which) {
+    HaloDev &h = m->halo;
+    const size_t np = m->halo_peers.size();
+    if (!np) return 0;
+    std::vector<double> mine(np), theirs(np, -1.0);
+    for (size_t i = 0; i < np; i++) mine[i] = which ? (double)m->halo_peers[i].unk.size() : (double)m->halo_peers[i].nodes.size();
+    double *d = nullptr;
+    CUDA_OK(cudaMalloc(&d, sizeof(double) * 2 * np));
+    CUDA_OK(cudaMemcpy(d, mine.data(), sizeof(double) * np, cudaMemcpyHostToDevice));
+    NCCL_OK(g_nccl.GroupStart());
+    for (size_t i = 0; i < np; i++) {
+        NCCL_OK(g_nccl.Send(d + i, 1, kNcclDouble, m->halo_peers[i].peer, h.comm, m->stream));
+        NCCL_OK(g_nccl.Recv(d + np + i, 1, kNcclDouble, m->halo_peers[i].peer, h.comm, m->stream));
+    }
+    NCCL_OK(g_nccl.GroupEnd());
+    CUDA_OK(cudaMemcpyAsync(theirs.data(), d + np, sizeof(double) * np, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_OK(cudaStreamSynchronize(m->stream));
+    cudaFree(d);
+    for (size_t i = 0; i < np; i++)
+        if (mine[i] != theirs[i]) {
+            set_error(std::string("comm_init: rank ") + std::to_string(h.rank) + " and rank " + std::to_string(m->halo_peers[i].peer) +
+                      " disagree on the number of shared " + (which ? "PML unknowns (" : "interface nodes (") +
+                      std::to_string((long long)mine[i]) + " vs " + std::to_string((long long)theirs[i]) + "): the halo lists are not mirror images");
+            return 1;
+        }
+    return 0;
+}
+
 // after the communicator exists: rank-ordered source lists of the shared unknowns, the ownership mask of the dot products,
 // and the row / column scaling from the diagonal of Keff summed over the ranks
 int pmlx_setup(svlgpu_model *m) {
     PmlDev &P = m->pml;
     HaloDev &h = m->halo;
     if (!P.present || !P.d_raw) return 0;                 // no PML block, or one that was planned for a single rank
+    if (verify_peer_counts(m, 1)) return 1;
     const int rank = h.rank;
     std::vector<std::vector<std::pair<int, int>>> srcs(P.nc);      // per unknown: (rank, index into rbuf | -1)
     std::vector<double> own(std::max(1, P.nc), 1.0);
