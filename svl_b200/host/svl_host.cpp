@@ -798,7 +798,8 @@ int main(int argc, char **argv) {
             svlgpu_counters c;
             svlgpu_get_counters(integrator.handle(), &c);
             std::cout << " elements " << c.n_elements << ", lattice nodes " << c.n_block_nodes << ", Gauss-point elements "
-                      << c.n_generic_elements << ", PML unknowns " << c.n_pml_unknowns << ", kernel launches " << c.total_launches << "\n";
+                      << c.n_generic_elements << ", PML unknowns " << c.n_pml_unknowns << ", kernel launches " << c.total_launches
+                      << ", last svlgpu_step call " << c.last_step_ms << " ms on the device\n";
         }
     } catch (const std::exception &e) {
         std::cout << "\x1B[31m ERROR: \x1B[0m" << e.what() << "\n";
