@@ -745,6 +745,7 @@ int main(int argc, char **argv) {
                 for (int q = 0; q < world; q++)
                     if (q != rank && UpdateMesh(all[q], svlhost::JParser(read_file(dir + "/" + file_of(q))).parse(), dir, true)) return 1;
                 if (PlanPartitions(all, rank)) return 1;
+                for (int q = 0; q < world; q++) if (q != rank) all[q] = Mesh();     // the peers' tables were only needed for the plan
             }
             if (plan_only) { PrintPlan(mesh, rank); continue; }
             // combination / recorders / simulation (Driver.hpp:1930-1975, 1859-1925, 1748-1856)
