@@ -94,12 +94,14 @@ def read_epart(path: str) -> np.ndarray:
     return np.loadtxt(path, dtype=np.int32)
 
 
-def split_model(m: Model, epart: np.ndarray, nparts: int, tie_closure: str = "both") -> List[Model]:
+def split_model(m: Model, epart: np.ndarray, nparts: int, tie_closure: str = "both", ranks=None) -> List[Model]:
     """Global model + element partition -> one sub-model per rank, each carrying
     `.halos = {peer: local node indices}`, `.global_nodes`, `.global_elems`.
     tie_closure: "both" (what the device needs: a partition that holds the slave OR a master of an EQUAL constraint gets all
     of its nodes) or "slave" (what the reference pre-processor writes: only the partition of the slave gets the masters,
-    SeismoVLAB.py:381-392; the host driver completes the closure when it reads the files)."""
+    SeismoVLAB.py:381-392; the host driver completes the closure when it reads the files).
+    ranks: build only these partitions' sub-models (the others are None in the returned list) -- what one rank of a torchrun job
+    needs; the node sets of all partitions are still derived, so the halo lists are complete."""
     kinds = np.unique(m.elem_kind)
     npe_e = np.array([ELEM_NODES[int(k)] for k in kinds], dtype=np.int32)[np.searchsorted(kinds, m.elem_kind)]
 
@@ -165,6 +167,9 @@ def split_model(m: Model, epart: np.ndarray, nparts: int, tie_closure: str = "bo
     fd = np.asarray(m.freedof_flat)
     subs = []
     for r in range(nparts):
+        if ranks is not None and r not in ranks:
+            subs.append(None)
+            continue
         el = np.nonzero(epart == r)[0]
         gn = node_sets[r]
         loc = -np.ones(m.n_nodes, dtype=np.int64)
@@ -229,6 +234,8 @@ def split_model(m: Model, epart: np.ndarray, nparts: int, tie_closure: str = "bo
         s.halos = {}
         subs.append(s)
     for r in range(nparts):
+        if subs[r] is None:
+            continue
         for q in range(nparts):
             if q == r:
                 continue

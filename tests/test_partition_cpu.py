@@ -138,6 +138,18 @@ def test_split_with_dashpots_counts_every_dashpot_once():
     assert np.array_equal(eta_sum, eta_global) and eta_global.sum() > 0
 
 
+def test_split_of_one_rank_equals_its_entry_in_the_full_split():
+    m = cases.pml3d()
+    ep = P.centroid_epart(m, (2, 2, 2))
+    full = P.split_model(m, ep, 8)
+    one = P.split_model(m, ep, 8, ranks=(5,))
+    assert [s is None for s in one] == [r != 5 for r in range(8)]
+    a, b = full[5], one[5]
+    assert np.array_equal(a.global_nodes, b.global_nodes) and np.array_equal(a.elem_conn, b.elem_conn)
+    assert a.constraints == b.constraints and sorted(a.halos) == sorted(b.halos)
+    assert all(np.array_equal(a.halos[q], b.halos[q]) for q in a.halos)
+
+
 def test_local_box_matches_split_of_global_box():
     from svl_b200 import model as M
     grid = (2, 2, 2)

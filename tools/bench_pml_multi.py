@@ -43,7 +43,7 @@ def main():
     m = M.make_pml_model((a.n, a.n, a.n), 10, 1.0, soil=(M.ELASTIC3DLINEAR, SOIL), nt=4000)
     m.dt *= 0.5                                               # dt = 0.25 h / Vp as in tools/bench_configs.py c3
     grid = P.proc_grid(world)
-    s = P.split_model(m, P.centroid_epart(m, grid), world)[rank] if world > 1 else m
+    s = P.split_model(m, P.centroid_epart(m, grid), world, ranks=(rank,))[rank] if world > 1 else m
     t_build = time.perf_counter() - t0
     comm = (rank, world, bytes(uid.cpu().numpy())) if world > 1 else None
     d = capi.DeviceModel(s, device=local, max_rows=a.warmup + a.steps + 8, comm=comm)
