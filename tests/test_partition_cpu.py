@@ -371,3 +371,19 @@ def test_metis_mesh_file_equals_the_reference_preprocessors(tmp_path, name):
     ep = np.arange(m.n_elem) % 2
     np.savetxt(str(tmp_path / "Graph.out.epart.2"), ep, fmt="%d")
     assert (P.read_epart(str(tmp_path / "Graph.out.epart.2")) == ep).all()
+
+
+def test_rank_file_generator_tool_output_is_planned_by_the_driver(tmp_path):
+    """tools/gen_rank_files.py (BASELINE-like configs as rank files with binary tables) -> `SeismoVLAB_gpu.exe -np N -plan`."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_rank_files.py"), "c3", "--n", "8", "--np", "4", "--out",
+                        str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    exe = os.path.join(root, "svl_b200", "SeismoVLAB_gpu.exe")
+    p = subprocess.run([exe, "-np", "4", "-plan", "-dir", str(tmp_path / "Partition"), "-file", "C3.1.$.bin.json"],
+                       capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stdout + p.stderr
+    heads = [l for l in p.stdout.splitlines() if " nodes " in l]
+    assert len(heads) == 4 and all("pml_collective 1" in l for l in heads)
