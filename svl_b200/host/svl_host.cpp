@@ -130,7 +130,7 @@ bool UpdateMesh(Mesh &mesh, const JValue &J, const std::string &dir, bool geomet
             nd.free.assign(fre.begin() + at, fre.begin() + at + ndof[i]);
             nd.coords.assign(xyz.begin() + i * nc, xyz.begin() + (i + 1) * nc);
             at += (size_t)ndof[i];
-            mesh.Nodes[nd.tag] = std::move(nd);
+            mesh.Nodes.emplace_hint(mesh.Nodes.end(), nd.tag, std::move(nd));      // tags ascend in the table: O(1) inserts
         }
         for (auto &kv : mesh.Nodes) kv.second.index = idx++;      // ascending tag
     } else
@@ -194,7 +194,7 @@ bool UpdateMesh(Mesh &mesh, const JValue &J, const std::string &dir, bool geomet
             e.conn.assign(conn.begin() + i * 8, conn.begin() + i * 8 + nconn[i]);
             e.attr.assign(attr.begin() + i * 10, attr.begin() + i * 10 + nattr_of[e.kind]);
             if (ray[i]) mesh.Rayleigh[e.tag] = {am[i], ak[i]};
-            mesh.Elements[e.tag] = std::move(e);
+            mesh.Elements.emplace_hint(mesh.Elements.end(), e.tag, std::move(e));
         }
         for (auto &kv : mesh.Elements) kv.second.index = idx++;
     } else
