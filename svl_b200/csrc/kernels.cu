@@ -1831,7 +1831,14 @@ int external_forces_interface(svlgpu_model *m, int k, const double *dev_amp) {
 
 // Assembler::ComputeInternalForceVector for the current displacement state
 int compute_internal_force(svlgpu_model *m, double *F_host) {
-    double *tmp = m->d_U[m->next];
+    // a scratch vector of its own: the three rotating state buffers stay intact (d_U[next] holds U_{n-1}, which the
+    // VEL / ACCEL getters and recorders read)
+    if (!m->d_fscratch) {
+        CUDA_OK(cudaMalloc(&m->d_fscratch, sizeof(double) * m->n_int));
+        m->allocs.push_back(m->d_fscratch);
+        m->device_bytes += (int64_t)sizeof(double) * m->n_int;
+    }
+    double *tmp = m->d_fscratch;
     CUDA_OK(cudaMemsetAsync(tmp, 0, sizeof(double) * m->n_int, m->stream));
     if (launch_generic_elements(m, m->d_U[m->cur], 0)) return 1;
     if (launch_node_update(m, m->d_U[m->cur], m->d_U[m->prev], tmp, 1)) return 1;

@@ -287,6 +287,7 @@ struct svlgpu_model {
     double *d_U[3] = {nullptr, nullptr, nullptr};   // rotating buffers
     int cur = 0, prev = 1, next = 2;
     double *d_kinv = nullptr, *d_km = nullptr;      // per internal dof: 1/Keff, Kminus (0 if not free)
+    double *d_fscratch = nullptr;                   // force-only passes (svlgpu_internal_force, reactions): never a state buffer
     std::vector<double> h_mass, h_cdiag;            // lumped mass / damping diagonal per internal dof
 
     std::vector<svl::Block> blocks;

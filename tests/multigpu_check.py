@@ -27,14 +27,10 @@ NE = {"kat444": (4, 4, 4), "drm_box": (6, 6, 5), "quad4_area": (8, 6), "j2_colum
       # soil box + PML layer (EQUAL ties, 9- / 5-dof PML nodes on the cuts): split by element centroid; the block solve
       # exchanges the shared unknowns and all-reduces its dot products
       "pml2d": None, "pml3d": None}
-# The multi-rank PML block solve has not run on hardware yet (written after the round's GPU budget was spent): its cases are
-# opt-in until a GPU pass has seen them green, so that the suite the driver runs keeps testing what was verified.
-if os.environ.get("SVL_MULTIGPU_PML", "0") != "1":
-    NE = {k: v for k, v in NE.items() if v is not None}
 RUNS = [(name, ne, "CENTRALDIFFERENCE") for name, ne in NE.items()]
-# NewmarkBeta + Linear across ranks (interface sums inside the K operator, all-reduced dot products): same status, opt-in
-if os.environ.get("SVL_MULTIGPU_NEWMARK", "0") == "1":
-    RUNS += [(name, NE[name], "NEWMARK") for name in cases.NEWMARK_CASES if NE.get(name) is not None]
+# NewmarkBeta + Linear across ranks (interface sums inside the K operator, all-reduced dot products).  Both the PML and the
+# Newmark cases were first seen green on 2 B200s in profiles/r3a_multigpu_check_pml_newmark_n2.log.
+RUNS += [(name, NE[name], "NEWMARK") for name in cases.NEWMARK_CASES if NE.get(name) is not None]
 
 
 def main():

@@ -6,8 +6,7 @@
 For each case: the global model is written as N per-rank JSON files in the reference's schema (global tags / dof numbers,
 svl_b200.model.write_reference_partitions), `SeismoVLAB_gpu.exe -np N` runs them (one forked process per GPU, NCCL id
 through the partition directory), and the per-rank NODE recorder files `<resp>.<rank>.out` are compared with the
-single-domain oracle.  NOT yet run on hardware when it was written (GPU budget of the round spent): run it from
-tools/gpu_multi.sh.  PML cases additionally need SVL_MULTIGPU_PML=1 (see tests/multigpu_check.py)."""
+single-domain oracle (first green run on 2 B200s: profiles/r3a_multigpu_host_check_n2.log)."""
 import os
 import subprocess
 import sys
@@ -25,8 +24,6 @@ from svl_b200 import model as M, partition as P  # noqa: E402
 
 EXE = os.path.join(ROOT, "svl_b200", "SeismoVLAB_gpu.exe")
 NE = {"kat444": (4, 4, 4), "drm_box": (6, 6, 5), "quad4_area": (8, 6), "lysmer_column": (3, 3, 6), "pml2d": None, "pml3d": None}
-if os.environ.get("SVL_MULTIGPU_PML", "0") != "1":
-    NE = {k: v for k, v in NE.items() if v is not None}
 
 
 def main():

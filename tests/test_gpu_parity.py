@@ -143,6 +143,22 @@ def test_internal_force_and_mass(oracle):
     assert np.abs(F2 - Fref).max() / np.abs(Fref).max() < 1e-12
 
 
+def test_internal_force_leaves_the_state_buffers_alone(oracle):
+    """svlgpu_internal_force works in a scratch vector of its own: VEL / ACCEL read after it (Integrator::GetVelocities after
+    Assembler::ComputeInternalForceVector in the host facade) still equal the recorder rows of the last step."""
+    m = kat_model()
+    d = _device(m, fields=(0, 1, 2))
+    d.step(1, 30, True)
+    rows = [d.read_recorder(f)[-1] for f in (0, 1, 2)]
+    d.internal_force()
+    dofs = np.concatenate([m.totaldof[m.node_ptr[n]:m.node_ptr[n + 1]] for n in m.rec_nodes]).astype(np.int32)
+    for f in (0, 1, 2):
+        assert np.array_equal(d.get_state(f)[dofs], rows[f]), f
+    d.step(30, m.nt, True)                             # and the run continues as if nothing had happened
+    ref, _ = oracle.run(m)
+    assert rel_err(d.read_recorder(0), ref) < TOL_LINEAR
+
+
 def test_j2_plastic_column(oracle):
     mat = (M.PLASTIC3DJ2, [2.9e7, 2.0e7, 2000.0, 1.0e7, 0.5, 1.0e4])
     m = M.make_box_model((3, 3, 8), 1.0, mat=mat, nt=120, load_dir=(3.0e5, 0.0, 1.0e5))
@@ -220,9 +236,7 @@ import os
 
 import cases
 
-# kat444_masses (nodal point masses) joined the cases after the round's last GPU pass: its first hardware run decides
-DEVICE_CASES = [pytest.param(n, marks=pytest.mark.xfail(strict=False, reason="first hardware run pending")) if n == "kat444_masses" else n
-                for n in cases.CASES]
+DEVICE_CASES = list(cases.CASES)
 
 
 @pytest.mark.parametrize("name", DEVICE_CASES)
@@ -243,7 +257,6 @@ def test_device_matches_reference_golden(oracle, name):
               f"err vs reference golden {cases.rel_err(out, g['disp']):.2e}")
 
 
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: first hardware run decides; remove the marker then")
 @pytest.mark.parametrize("name", ["hex8_distorted", "quad4_distorted"])
 def test_gauss_point_strain_stress_at_the_current_state(oracle, name):
     """svlgpu_get_gauss (Element::GetStrain / GetStress at Gauss points, lin3DHexa8.cpp:150-200): after an internal-force pass on
@@ -458,7 +471,6 @@ def test_device_matches_reference_fixture_from_its_own_input_files(oracle, tmp_p
         assert cases.fixture_errors(name, hist, key) < 2e-5, key          # recorder files carry ndps = 8 digits
 
 
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: first hardware run decides; remove the marker then")
 def test_host_driver_element_recorders_match_fixture_f02_opensees_stress(tmp_path):
     """The reference's fixture F02 as shipped (NODE + ELEMENT recorders) through the C++ driver: Stress.0.out / Strain.0.out in the
     reference's layout, compared the way the fixture's own cmpResults.py does it (4th Gauss point <-> OpenSees columns 7 8 9)."""

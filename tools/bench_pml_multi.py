@@ -4,10 +4,9 @@ proc_grid(N)) by element centroid, one rank per GPU under torchrun.  Not the con
 line on rank 0.  Strong scaling: the global mesh is fixed, every rank keeps its partition.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 \
-      tools/bench_pml_multi.py --n 200 --steps 20
+      tools/bench_pml_multi.py --size 200 --steps 20
 
-UNVERIFIED ON HARDWARE at the time of writing (the multi-rank PML block solve was written after the round's GPU budget
-was spent): run tests/multigpu_check.py first, it carries the pml2d / pml3d parity cases.
+Parity of the multi-rank block solve: tests/multigpu_check.py (pml2d / pml3d cases).
 """
 import argparse
 import json
@@ -28,7 +27,7 @@ SOIL = [1.3e7, 0.3, 2000.0]
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=200)
+    ap.add_argument("--size", dest="n", type=int, default=200)   # (not --n: torchrun abbreviates it)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     a = ap.parse_args()

@@ -5,12 +5,9 @@ O=gpurun_out/$TAG
 mkdir -p $O
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 timeout 600 $TR --master-port 29511 tests/multigpu_check.py > $O/check_n$N.log 2>&1; echo "check exit $?" >> $O/check_n$N.log
-grep -E "multigpu|exit" $O/check_n$N.log | tail -12
-# opt-in cases: PML models and NewmarkBeta across ranks (see tests/multigpu_check.py)
-SVL_MULTIGPU_PML=1 SVL_MULTIGPU_NEWMARK=1 timeout 900 $TR --master-port 29514 tests/multigpu_check.py > $O/check_pml_n$N.log 2>&1; echo "check(pml) exit $?" >> $O/check_pml_n$N.log
-grep -E "pml|newmark|exit" $O/check_pml_n$N.log | tail -14
+grep -E "multigpu|exit" $O/check_n$N.log | tail -20
 # the C++ host driver over per-rank JSON files in the reference's schema (SeismoVLAB_gpu.exe -np N)
-SVL_MULTIGPU_PML=1 timeout 600 python tests/multigpu_host_check.py $N > $O/check_host_n$N.log 2>&1; echo "check(host) exit $?" >> $O/check_host_n$N.log
+timeout 600 python tests/multigpu_host_check.py $N > $O/check_host_n$N.log 2>&1; echo "check(host) exit $?" >> $O/check_host_n$N.log
 grep -E "multigpu host|exit" $O/check_host_n$N.log | tail -8
 timeout 900 $TR --master-port 29512 bench.py --gpus $N --steps 100 --warmup 5 > $O/bench_weak_n$N.json 2> $O/bench_weak_n$N.err
 timeout 600 $TR --master-port 29513 bench.py --gpus $N --steps 200 --warmup 10 --scaling strong > $O/bench_strong_n$N.json 2> $O/bench_strong_n$N.err
@@ -23,7 +20,7 @@ for k in ("weak","strong"):
 PY
 tail -3 $O/bench_weak_n$N.err
 # BASELINE configs[2] across the GPUs (only meaningful once the pml lines above are OK)
-if grep -q "check(pml) exit 0" $O/check_pml_n$N.log; then
-  timeout 900 $TR --master-port 29515 tools/bench_pml_multi.py --n ${PML_N:-200} --steps 20 > $O/bench_pml_n$N.json 2> $O/bench_pml_n$N.err
+if grep -q "check exit 0" $O/check_n$N.log; then
+  timeout 900 $TR --master-port 29515 tools/bench_pml_multi.py --size ${PML_N:-200} --steps 20 > $O/bench_pml_n$N.json 2> $O/bench_pml_n$N.err
   cat $O/bench_pml_n$N.json
 fi
