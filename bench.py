@@ -29,7 +29,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 HEX8_BYTES = 140.0      # algorithmic bytes per lin3DHexa8 element-update
-HEX8_FLOPS_STENCIL = 504.0   # minimum-known formulation (27 x 3x3 node stencil + update)
+HEX8_FLOPS_STENCIL = 504.0   # SURVEY 8(d) "minimum-known formulation" (27 x 3x3 node stencil + update)
+# FP64 instructions the dominant kernel EXECUTES per node (SASS of the built kernel, profiles/r3b_sass_k_stencil3_sep.md):
+#   k_stencil3_sep<4,4>: 48 DFMA + 27.4 DADD + 3 DMUL (x pass on R+2 rows per R nodes, y pass, z scatter, update)
+#   k_stencil3_v4<4,4,SYM>: 153 DFMA + 9 (update)
+KERNELS = {"sep": {"name": "k_stencil3_sep", "fp64_instr": 78.375, "flop": 2 * 48 + 27.375 + 3, "bytes": 72},
+           "v4": {"name": "k_stencil3_v4", "fp64_instr": 162.0, "flop": 2 * 153 + 15, "bytes": 73}}
 MAT = [1.3e7, 0.3, 2000.0]   # fixture J05 soil
 
 
@@ -54,11 +59,15 @@ def pick_hbm_peak(doc):
             and not any(t in k.lower() for t in ("flop", "bf16", "fp16", "tf"))]
     if not cand:
         return None
-    cand.sort(key=lambda kv: (0 if "sustain" in kv[0].lower() else 1 if "burst" not in kv[0].lower() else 2))
-    k, v = cand[0]
-    if v < 100.0:
-        v *= 1000.0                                   # TB/s
-    return (v, k) if 1000.0 <= v <= 20000.0 else None
+    # keys that name HBM outright win over generic "*bandwidth*" ones; then sustained > unlabelled > burst
+    cand.sort(key=lambda kv: (0 if "hbm" in kv[0].lower() else 1,
+                              0 if "sustain" in kv[0].lower() else 1 if "burst" not in kv[0].lower() else 2))
+    for k, v in cand:
+        if v < 100.0:
+            v *= 1000.0                               # TB/s
+        if 1000.0 <= v <= 20000.0:
+            return v, k
+    return None
 
 
 def measured_peaks():
@@ -80,14 +89,15 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.active = index, [], False, False
 
     def run(self):
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                       "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                self.samples.append([x.strip() for x in out.strip().split(",")])
+                if self.active:                       # only samples taken DURING the timed regions count
+                    self.samples.append([x.strip() for x in out.strip().split(",")])
             except Exception:
                 pass
             time.sleep(0.1)
@@ -249,18 +259,51 @@ def run_reference_arm(args, emit):
     emit(line)
 
 
-def ncu_traffic(n):
+def ncu_traffic(n, kern):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
     `ncu --set full` capture of this very command (profiles/ncu_traffic.json); None when no capture matches."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             j = json.load(f)
-        for kern in ("k_stencil3_v4", "k_stencil3_tma"):          # newest capture of the dominant kernel first
-            if f"{kern}@n{n}" in j:
-                return j[f"{kern}@n{n}"].get("dram_bytes_per_launch")
-        return None
+        return j.get(f"{kern}@n{n}", {}).get("dram_bytes_per_launch")
     except OSError:
         return None
+
+
+def parity_check(n, steps, device, emit_note=None):
+    """bench.py --verify (on by default at N = 1): the SAME kernel variant and tiling rules as the timed run on an
+    n^3 box with the DRM layer and the point load, every free dof started with a random velocity (so every
+    node's stencil row matters from step 2 on), `steps` CentralDifference steps, FULL final state against the CPU oracle
+    (oracle/svl_oracle.c, OpenMP over elements).  Tolerance 1e-10 (north_star)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import Oracle
+    from svl_b200 import model as M
+    from svl_b200.capi import DeviceModel
+    nt = steps + 1
+    m = build_workload(n, nt)
+    if m.drm is not None:                       # the oracle reads a tabulated field: tabulate the same plane wave
+        G = m.global_elems_per_axis
+        M.add_drm_box(m, x0=[G[0] / 2, G[1] / 2, G[2]], xl=[G[0] / 2 - 5.5, G[1] / 2 - 5.5, G[2] - 5.5],
+                      planewave=m.drm.planewave, tabulate_nt=nt)
+    # random initial VELOCITY (U0 = 0): the reference's first step uses the stored (zero) stresses whatever U0 is (SURVEY App. C q2)
+    V0 = np.random.default_rng(42).uniform(-1.0, 1.0, m.n_total)
+    V0[np.asarray(m.totaldof)[np.asarray(m.freedof_flat) < 0]] = 0.0
+    t0 = time.perf_counter()
+    d = DeviceModel(m, device=device, max_rows=nt + 2, V0=V0)
+    d.step(1, nt, True)
+    U = d.get_state(0)
+    c = d.counters()
+    d.close()
+    t_dev = time.perf_counter() - t0
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    _, Uref = Oracle().run(m, nt=nt, nthreads=cores, V0=V0)
+    t_cpu = time.perf_counter() - t0
+    err = float(np.abs(U - Uref).max() / np.abs(Uref).max())
+    return {"mesh": f"{n}^3 lin3DHexa8 + DRM layer + point load, random V0, {steps} steps", "dof": int(m.n_total),
+            "block_nodes": int(c["n_block_nodes"]), "generic_elements": int(c["n_generic_elements"]),
+            "max_rel_err_full_state_vs_oracle": err, "tol": 1e-10, "ok": bool(err < 1e-10),
+            "oracle_s": t_cpu, "device_s_incl_plan": t_dev, "oracle_threads": cores}
 
 
 def main():
@@ -273,6 +316,11 @@ def main():
     ap.add_argument("--ref-n", type=int, default=16)
     ap.add_argument("--ref-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the parity check of the timed kernel variant against the oracle")
+    ap.add_argument("--verify-n", type=int, default=64, help="mesh of the parity check (the oracle's set-up costs ~80 us per "
+                    "element: 64^3 ~ 20 s; profiles/ holds a 128^3 run)")
+    ap.add_argument("--verify-steps", type=int, default=12)
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling sub-record")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = n^3 elements per GPU (default), strong = the n^3 mesh split over the GPUs")
     args = ap.parse_args()
@@ -297,17 +345,11 @@ def main():
     K, W = args.steps, max(args.warmup, 3)
     nt = 4 * (W + K) + 40
     dist = None
-    comm = None
     if world > 1:
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        comm = (rank, world, bytes(uid.cpu().numpy()))
 
     def allmax(x):
         if dist is None:
@@ -328,102 +370,183 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    t0 = time.perf_counter()
-    m = build_workload(args.n, nt, rank, world, strong=(args.scaling == "strong"))
-    t_model = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    d = DeviceModel(m, device=local_rank, max_rows=nt + 4, comm=comm)
-    t_plan = time.perf_counter() - t0
-    c = d.counters()
-    n_elem_total = int(allsum(m.n_elem))
-    n_dof_total = int(allsum(m.n_total))          # interface dofs counted once per replica
-    amp = m.point_loads[0].series if m.point_loads else None
+    variant = "v4" if os.environ.get("SVLGPU_NO_SEP") else "sep"
+    KV = KERNELS[variant]
+    peak, peak_src = measured_peaks()
+    fp64_peak, copy_peak = capi.measure_peaks(local_rank) if rank == 0 else (None, None)
 
-    # ---- device-resident throughput: K steps in one C-ABI call, CUDA events on the launching stream,
-    #      barrier + synchronize on both sides, max over ranks
-    k = 1
-    d.step(k, k + W, True); k += W
+    def replica_check(m, d):
+        """every rank hashes the final displacements of the nodes it shares with each peer (the lists have the same
+        order on both sides); rank 0 compares the pairs: replicas must agree bit for bit"""
+        if dist is None:
+            return None
+        import hashlib
+        mine = {}
+        for peer, nodes in sorted(m.halos.items()):
+            dofs = np.concatenate([np.asarray(m.totaldof)[m.node_ptr[q]:m.node_ptr[q + 1]] for q in nodes]).astype(np.int32)
+            mine[int(peer)] = hashlib.sha256(d.get_state(0, dofs).tobytes()).hexdigest()
+        allh = [None] * world
+        dist.all_gather_object(allh, mine)
+        pairs = bad = 0
+        for r in range(world):
+            for p_, hsh in allh[r].items():
+                if p_ > r:
+                    pairs += 1
+                    bad += int(allh[p_].get(r) != hsh)
+        return {"interface_pairs": pairs, "pairs_differing": bad, "ok": bad == 0,
+                "what": "sha256 of U at the nodes shared by each pair of ranks after the timed steps"}
+
+    def run_case(strong, K, W, with_e2e=True, with_kernel_timing=True, sample_clocks=False):
+        t0 = time.perf_counter()
+        m = build_workload(args.n, nt, rank, world, strong=strong)
+        t_model = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        d = DeviceModel(m, device=local_rank, max_rows=nt + 4, comm=comm_for())
+        t_plan = time.perf_counter() - t0
+        c = d.counters()
+        n_elem_total = int(allsum(m.n_elem))
+        n_dof_total = int(allsum(m.n_total))          # interface dofs counted once per replica
+        amp = m.point_loads[0].series if m.point_loads else None
+        # ---- device-resident throughput: K steps in one C-ABI call, CUDA events on the launching stream,
+        #      barrier + synchronize on both sides, max over ranks
+        k = 1
+        d.step(k, k + W, True); k += W
+        barrier()
+        sampler.active = sample_clocks
+        w0 = time.perf_counter()
+        d.step(k, k + K, True); k += K
+        barrier()
+        wall = time.perf_counter() - w0
+        if wall < 0.35 and sample_clocks:             # short timed region (driver default --steps 20): keep the same kernels
+            d.step(k, k + K, True); k += K            # running untimed until nvidia-smi has been polled a few times
+            d.step(k, k + K, True); k += K
+        ms = allmax(d.counters()["last_step_ms"])
+        out = {"m": m, "value": n_elem_total * K / (ms * 1e-3), "ms_per_step": ms / K, "elements": n_elem_total,
+               "dof": n_dof_total, "launches": allsum(d.counters()["launches_per_step"] * K), "c": c,
+               "t_model": t_model, "t_plan": t_plan, "wall": wall}
+        if with_kernel_timing:                        # per-launch CUDA-event durations of the kernels (separate pass)
+            d.set_kernel_timing(True)
+            d.step(k, k + min(K, 20), True); k += min(K, 20)
+            out["kt"] = {w: d.kernel_time(w) for w in range(6)}
+            d.set_kernel_timing(False)
+        if with_e2e:                                  # end to end through the per-step C-ABI call with HOST buffers
+            row = np.zeros(3 * len(m.rec_nodes))
+            for _ in range(3):
+                d.step_host(k, [amp[k]] if amp is not None else [], rec=0, row=row); k += 1
+            barrier()
+            e0 = time.perf_counter()
+            for _ in range(K):
+                d.step_host(k, [amp[k]] if amp is not None else [], rec=0, row=row); k += 1
+            barrier()
+            e2e_s = allmax(time.perf_counter() - e0)
+            sampler.active = False
+            if not np.all(np.isfinite(row)):
+                raise SystemExit("non-finite response")
+            out["e2e"] = {"value": n_elem_total * K / e2e_s, "unit": "element-updates/s",
+                          "h2d_bytes_per_step": int(allsum(8 * len(m.point_loads))),
+                          "d2h_bytes_per_step": int(allsum(row.nbytes)), "ms_per_step": 1e3 * e2e_s / K,
+                          "note": "one svlgpu_step_host call per step and rank with HOST buffers: the step's load amplitudes "
+                                  "are read from pinned host memory and the recorder row is written to pinned host memory by "
+                                  "the step's own kernels (zero-copy over the bus, no separate copy-engine submissions), all "
+                                  "kernels (+ NCCL interface exchange), stream sync; the state vectors stay resident in HBM "
+                                  "exactly as the reference keeps U,V,A resident in host RAM between steps"}
+        U = d.get_state(0, np.asarray(m.rec_dofs(), np.int32))
+        if not np.all(np.isfinite(U)):
+            raise SystemExit("non-finite state")
+        out["replicas"] = replica_check(m, d)
+        d.close()
+        return out
+
+    uid_count = [0]
+
+    def comm_for():
+        """a fresh NCCL communicator per model (weak case, strong case)"""
+        if dist is None:
+            return None
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        uid_count[0] += 1
+        return (rank, world, bytes(uid.cpu().numpy()))
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    barrier()
-    w0 = time.perf_counter()
-    d.step(k, k + K, True); k += K
-    barrier()
-    wall = time.perf_counter() - w0
-    ms = allmax(d.counters()["last_step_ms"])
-    value = n_elem_total * K / (ms * 1e-3)
-    launches = allsum(d.counters()["launches_per_step"] * K)
-
-    # ---- roofline of the dominant kernel: per-launch CUDA-event durations (separate pass)
-    d.set_kernel_timing(True)
-    d.step(k, k + min(K, 20), True); k += min(K, 20)
-    kt = {w: d.kernel_time(w) for w in range(6)}
-    d.set_kernel_timing(False)
-    peak, peak_src = measured_peaks()
-    st_ms, st_n = kt[0]
-    ach = HEX8_BYTES * c["n_block_nodes"] / (st_ms * 1e-3) / 1e9 if st_n else None
-    own_bytes = 3 * 8 * 3 + 1           # U_n, U_{n-1} reads + U_{n+1} write + 1 class byte per node
-    roof = {"bound": "hbm", "kernel": "k_stencil3_v4 (block-stencil force + CentralDifference update, rank 0)",
-            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
-            "traffic": ncu_traffic(args.n if world == 1 else None),
-            "peak_source": peak_src, "avg_launch_ms": st_ms, "launches_timed": st_n,
-            "algorithmic_bytes_per_element_update": HEX8_BYTES,
-            "kernel_compulsory_bytes_per_node": own_bytes,
-            "achieved_kernel_bytes_GBs": own_bytes * c["n_block_nodes"] / (st_ms * 1e-3) / 1e9 if st_n else None,
-            "fp64_TFLOPs_stencil_form": HEX8_FLOPS_STENCIL * c["n_block_nodes"] / (st_ms * 1e-3) / 1e12 if st_n else None,
-            "frac_of_8TBs_nominal": (ach / 8000.0) if ach else None}
-
-    # ---- end to end through the per-step C-ABI call with HOST buffers
-    row = np.zeros(3 * len(m.rec_nodes))
-    for _ in range(3):
-        d.step_host(k, [amp[k]] if amp is not None else [], rec=0, row=row); k += 1
-    barrier()
-    e0 = time.perf_counter()
-    for _ in range(K):
-        d.step_host(k, [amp[k]] if amp is not None else [], rec=0, row=row); k += 1
-    barrier()
-    e2e_s = allmax(time.perf_counter() - e0)
+    strong_main = args.scaling == "strong"
+    R = run_case(strong_main, K, W, sample_clocks=True)
+    sampler.active = False
     if rank == 0:
         sampler.stop_flag = True; sampler.join(timeout=2)
-    e2e = {"value": n_elem_total * K / e2e_s, "unit": "element-updates/s",
-           "h2d_bytes_per_step": int(allsum(8 * len(m.point_loads))),
-           "d2h_bytes_per_step": int(allsum(row.nbytes)), "ms_per_step": 1e3 * e2e_s / K,
-           "note": "one svlgpu_step_host call per step and rank with HOST buffers: the step's load amplitudes are read "
-                   "from pinned host memory and the recorder row is written to pinned host memory by the step's own "
-                   "kernels (zero-copy over the bus, no separate copy-engine submissions), all kernels (+ NCCL interface "
-                   "exchange), stream sync; the state vectors stay resident in HBM exactly as the reference keeps "
-                   "U,V,A resident in host RAM between steps"}
-    if not np.all(np.isfinite(row)):
-        raise SystemExit("non-finite response")
+    m, c, kt = R["m"], R["c"], R["kt"]
+    st_ms, st_n = kt[0]
+    nodes = c["n_block_nodes"]
+    # the dominant kernel advances the interior class; shell classes are a separate (timed) kernel
+    real = KV["bytes"] * nodes / (st_ms * 1e-3) / 1e9 if st_n else None
+    contract = HEX8_BYTES * nodes / (st_ms * 1e-3) / 1e9 if st_n else None
+    fp64_exec = KV["flop"] * nodes / (st_ms * 1e-3) / 1e12 if st_n else None
+    fp64_slots = 2.0 * KV["fp64_instr"] * nodes / (st_ms * 1e-3) / 1e12 if st_n else None
+    roof = {"bound": "hbm", "kernel": f"{KV['name']} (block-stencil force + CentralDifference update, rank 0)",
+            "achieved": real, "peak": peak, "unit": "GB/s", "frac": (real / peak) if real else None,
+            "traffic": ncu_traffic(args.n if world == 1 else None, KV["name"]),
+            "peak_source": peak_src, "avg_launch_ms": st_ms, "launches_timed": st_n,
+            "bytes_per_node": KV["bytes"],
+            "what": "achieved = compulsory bytes of the kernel (U_n and U_{n-1} read, U_{n+1} written: 72 B per node; the class "
+                    "table replaces connectivity, coordinates and masses) x lattice nodes / CUDA-event launch time; ncu's "
+                    "dram__bytes per launch is `traffic`",
+            "contract_equivalent": {"bytes_per_element_update": HEX8_BYTES, "GBs": contract,
+                                    "frac": (contract / peak) if contract else None,
+                                    "note": "SURVEY 8(d) 140 B per element-update figure; exceeds 1 because the kernel does "
+                                            "not move connectivity / coordinates / mass at all"},
+            "copy_GBs_measured_here": copy_peak, "frac_of_copy_measured_here": (real / copy_peak) if real and copy_peak else None,
+            "frac_of_8TBs_nominal": (real / 8000.0) if real else None,
+            "fp64_peak_measured_TFLOPs": fp64_peak,
+            "fp64_executed_TFLOPs": fp64_exec,
+            "fp64_fraction": (fp64_slots / fp64_peak) if fp64_slots and fp64_peak else None,
+            "fp64_what": "fp64_fraction = FP64 instructions executed per node (SASS count: %.1f, every one a pipe slot of an "
+                         "FMA) x 2 flop / time / measured DFMA peak (svlgpu_measure_peaks); fp64_executed counts DADD / DMUL "
+                         "as 1 flop" % KV["fp64_instr"],
+            "step_floor": {"ms": KV["bytes"] * nodes / (peak * 1e9) * 1e3, "frac": KV["bytes"] * nodes / (peak * 1e9) * 1e3 / R["ms_per_step"],
+                           "note": "whole step (DRM layer, shell classes, loads, recorder included) against the time to move "
+                                   "the dominant kernel's compulsory bytes at peak"}}
 
     cb = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb = cpu_baseline_port()
+    pc = None
+    if rank == 0 and world == 1:
+        if not args.no_cpu_baseline:
+            cb = cpu_baseline_port()
+        if not args.no_verify:
+            pc = parity_check(args.verify_n, args.verify_steps, local_rank)
+    strong = None
+    if world > 1 and not strong_main and not args.no_strong:
+        # strong scaling of the SAME n^3 mesh (north_star: the 10^8-DOF mesh on 8 GPUs) next to the weak-scaling value
+        S = run_case(True, K, W, with_e2e=False, with_kernel_timing=False)
+        strong = {"value": S["value"], "unit": "element-updates/s", "ms_per_step": S["ms_per_step"], "elements": S["elements"],
+                  "dof": S["dof"], "mesh": "x".join(str(g) for g in S["m"].global_elems_per_axis), "replicas": S["replicas"],
+                  "note": "the N = 1 mesh split over the GPUs; efficiency = value / (N x the N = 1 line's value)"}
 
     G = m.global_elems_per_axis
-    line = {"metric": "element-updates/sec (FP64 explicit step)", "value": value, "unit": "element-updates/s",
-            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+    line = {"metric": "element-updates/sec (FP64 explicit step)", "value": R["value"], "unit": "element-updates/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": R["ms_per_step"], "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"3-D elastic half-space, {G[0]}x{G[1]}x{G[2]} lin3DHexa8 + Elastic3DLinear "
-                                   f"({n_dof_total} DOF), lumped CentralDifference, DRM SV plane-wave layer, "
+                                   f"({R['dof']} DOF), lumped CentralDifference, DRM SV plane-wave layer, "
                                    f"1 host-fed point load, 16 recorded nodes per partition (BASELINE configs[3]-like; "
                                    f"{world} block partition(s), one per GPU, NCCL interface-force exchange)",
-                       "elements": n_elem_total, "dof": n_dof_total, "dt": m.dt,
+                       "elements": R["elements"], "dof": R["dof"], "dt": m.dt,
                        "partition_grid": list(__import__("svl_b200.partition", fromlist=["x"]).proc_grid(world)),
                        "interface_nodes_rank0": int(sum(len(v) for v in m.halos.values())),
                        "l2": "state vectors (3 x %.0f MB per GPU) exceed the 126 MB L2" % (m.n_total * 8 / 1e6),
                        "block_nodes_rank0": c["n_block_nodes"], "generic_elements_rank0": c["n_generic_elements"],
-                       "node_classes_rank0": c["n_node_classes"], "model_build_s": t_model, "plan_upload_s": t_plan,
-                       "wall_s_timed_region": wall},
-            "clocks": sampler.summary() if rank == 0 else None, "e2e": e2e, "gpu_launches": int(launches),
+                       "node_classes_rank0": c["n_node_classes"], "model_build_s": R["t_model"], "plan_upload_s": R["t_plan"],
+                       "wall_s_timed_region": R["wall"], "dominant_kernel": KV["name"]},
+            "clocks": sampler.summary() if rank == 0 else None, "e2e": R["e2e"], "gpu_launches": int(R["launches"]),
             "roofline": roof,
             "kernel_ms": {"stencil_dom": kt[0][0], "stencil_shell_gather": kt[4][0], "gauss_elements": kt[1][0],
                           "gather_nodes": kt[2][0], "point_loads": kt[3][0], "drm": kt[5][0]},
-            "cpu_baseline": cb}
+            "cpu_baseline": cb, "parity_check": pc, "replicas": R["replicas"], "strong": strong}
     if rank == 0:
         emit(line)
-    d.close()
     if dist is not None:
         dist.destroy_process_group()
 

@@ -138,9 +138,24 @@ int svlgpu_add_drm_planewave(svlgpu_model *m, int nelems, const int32_t *elems, 
                              const double *dir, const double *pol, const double *xref,
                              double c, double f0, double t0, double amp, double factor);
 
+/* Support motion of one restrained dof: Supports{node: type, value | file, dof} (Driver.hpp:509-563,
+ * Mesh::SetSupportMotion -> Node.cpp:132-134) listed by a SUPPORTMOTION load of the combination (Driver.hpp:1725-1735,
+ * factor = its combination factor).  series = Xo (nt == 1: CONSTANT).  Each step the dof moves by
+ * factor * (g(k) - g(k-1)), g(k) = Xo[k] if k < nt else Xo[0] (Assembler::ComputeSupportMotionIncrement,
+ * Assembler.cpp:493-533; Node::GetSupportMotion, Node.cpp:228-247; CentralDifference.cpp:135,189-202).  Like the
+ * reference, the elements see the moved support one step late (Algorithm.cpp:23: UpdateStatesIncrements gets T dU only).
+ * CentralDifference only; the dof must be restrained (freedof -1) and its node must not carry a PML or ZeroLength1D
+ * element (their Keff rows are not diagonal); one entry per dof.                                                   */
+int svlgpu_add_support_motion(svlgpu_model *m, int node, int dof, int nt, const double *series, double factor);
+
 /* ---- recorders (Recorder.cpp:73-105,239-269) ----------------------------- */
 /* NODE recorder of `field` at `nodes`; returns recorder id.  Rows are kept on
- * the device (one per step) and fetched with svlgpu_read_recorder.             */
+ * the device (one per step) and fetched with svlgpu_read_recorder.
+ * SVLGPU_REACTION (Recorder.cpp:258): rows of Integrator::ComputeReactionForce as DynamicAnalysis::UpdateDomain
+ * stores them (DynamicAnalysis.cpp:130-150, CentralDifference.cpp:155-171, Assembler.cpp:272-287,568-619): at the dofs
+ * of FIXED nodes  F_int + C V + M A (elements and point masses) - F_ext(k),  zero rows for free nodes.  The reference
+ * evaluates this for the whole mesh every step; here it costs one extra force pass per RECORDED step.
+ * CentralDifference, models without PML elements.                                                                   */
 int svlgpu_add_node_recorder(svlgpu_model *m, int field, int nnodes, const int32_t *nodes,
                              int max_rows);
 
@@ -216,6 +231,11 @@ int svlgpu_set_kernel_timing(svlgpu_model *m, int on);
  * 0 = block stencil (dominant class), 1 = Gauss-point element force, 2 = generic node update,
  * 3 = point loads, 4 = block stencil (shell gather), 5 = DRM.  reset!=0 clears after reading.              */
 int svlgpu_kernel_time(svlgpu_model *m, int which, double *avg_ms, int64_t *launches, int reset);
+
+/* Device micro-benchmarks for the roofline record: FP64 FMA throughput (TFLOP/s, 2 flop per DFMA,
+ * dependent-chain-free kernel at full occupancy) and streaming-copy bandwidth (GB/s, read + write bytes of a 1 GiB
+ * copy).  Either pointer may be NULL.  No reference counterpart: measurement only.                              */
+int svlgpu_measure_peaks(int device, double *fp64_tflops, double *copy_gbs);
 
 /* raw device pointers for zero-copy interop (torch.from_blob / NCCL plumbing):
  * which: 0 = U_n, 1 = U_{n-1}, 2 = scratch U_{n+1}; length ntotal doubles.     */

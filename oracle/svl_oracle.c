@@ -893,6 +893,13 @@ static int run_dynamic_alg(const svlo_model *m, int integrator, const svlo_newto
            *dUt = (double *)calloc(nT, sizeof(double)), *Utr = (double *)calloc(nT, sizeof(double));
     double *Feff = (double *)calloc(nF + 1, sizeof(double)), *dU = (double *)calloc(nF + 1, sizeof(double));
     double *fe_all = (double *)malloc((size_t)nE * 72 * sizeof(double));
+    double *SM = (double *)calloc(nT, sizeof(double)), *Reac = (double *)calloc(nT, sizeof(double));
+    /* Node::IsFixed: any restrained dof (Driver.hpp:338-341); rows of R are kept for all dofs of such nodes */
+    unsigned char *node_fixed = (unsigned char *)calloc(m->n_nodes, 1), *is_fixed_dof = (unsigned char *)calloc(nT, 1);
+    for (int nd = 0; nd < m->n_nodes; nd++) {
+        for (int p = m->node_ptr[nd]; p < m->node_ptr[nd + 1]; p++) if (m->freedof[p] == -1) node_fixed[nd] = 1;
+        if (node_fixed[nd]) for (int p = m->node_ptr[nd]; p < m->node_ptr[nd + 1]; p++) is_fixed_dof[m->totaldof[p]] = 1;
+    }
     if (m->U0) memcpy(U, m->U0, nT * sizeof(double));
     if (m->V0) memcpy(V, m->V0, nT * sizeof(double));
     if (m->A0) memcpy(A, m->A0, nT * sizeof(double));
@@ -1093,6 +1100,25 @@ static int run_dynamic_alg(const svlo_model *m, int integrator, const svlo_newto
         memset(Feff, 0, nF * sizeof(double));
         for (int i = 0; i < nT; i++)
             for (int a = T.ptr[i]; a < T.ptr[i + 1]; a++) Feff[T.col[a]] += T.val[a] * rhs[i];
+        /* --- support motion (Linear.cpp:40 -> CentralDifference::ComputeSupportMotionVector, CentralDifference.cpp:189-202):
+         * SupportMotion = sum factor (g(k) - g(k-1)) with g(k) = Xo[k] if k < size else Xo[0] (Assembler.cpp:493-533,
+         * Node.cpp:228-247);  Feff -= T' (Keff SupportMotion) with Keff the integrator's `K` member (:70)            */
+        if (m->n_sup > 0) {
+            if (integrator != 0) { rc = 5; goto done; }    /* the Newmark variants are not restated */
+            memset(SM, 0, nT * sizeof(double));
+            for (int q = 0; q < m->n_sup; q++) {
+                const double *xo = m->sup_series + m->sup_ptr[q];
+                const int sz = m->sup_ptr[q + 1] - m->sup_ptr[q];
+                double dg = (k < sz) ? xo[k] : xo[0];
+                if (k > 0) dg -= (k - 1 < sz) ? xo[k - 1] : xo[0];
+                SM[m->sup_dof[q]] += m->sup_factor[q] * dg;
+            }
+            for (int i = 0; i < nT; i++) {
+                double v = 0;
+                for (int p = Kp.ptr[i]; p < Kp.ptr[i + 1]; p++) v += Kp.val[p] * SM[Kp.col[p]];
+                for (int a = T.ptr[i]; a < T.ptr[i + 1]; a++) Feff[T.col[a]] -= T.val[a] * v;
+            }
+        }
         if (alg && integrator == 1) {
             /* ---- NewtonRaphson::ComputeNewIncrement: iterate on the increment dU of this step ------------------------- */
             double *Kn = (double *)malloc((size_t)nF * nF * sizeof(double)), *du = (double *)malloc((nF + 1) * sizeof(double));
@@ -1212,6 +1238,9 @@ static int run_dynamic_alg(const svlo_model *m, int integrator, const svlo_newto
         }
 #pragma omp parallel for schedule(static)
         for (int e = 0; e < nE; e++) material_update(m, e, &rt[e], Utr);
+        /* CentralDifference.cpp:135: dU = T dU_free + SupportMotion -- added AFTER UpdateStatesIncrements, which only sees
+         * T dU_free (Algorithm.cpp:23): the element stresses lag the support displacement by one step */
+        if (m->n_sup > 0) for (int i = 0; i < nT; i++) dUt[i] += SM[i];
         if (integrator >= 1) {
             /* NewmarkBeta.cpp:73-76; ExtendedNewmarkBeta updates the PML history first */
             for (int i = 0; i < nT; i++) {
@@ -1229,7 +1258,37 @@ static int run_dynamic_alg(const svlo_model *m, int integrator, const svlo_newto
             U[i] += dUt[i];
         }
         for (int i = 0; i < nT; i++) if (U[i] != U[i]) rc = 3;
-        const double *src = field == 0 ? U : field == 1 ? V : A;
+        if (field == 3) {
+            /* DynamicAnalysis::UpdateDomain (DynamicAnalysis.cpp:130-150): R = ComputeDynamicInternalForceVector - Fext(k) - Fbar
+             * (CentralDifference.cpp:155-171; NewmarkBeta has the same body) with the node states of this step.
+             * Assembler.cpp:272-287, 568-619: node inertia forces Mass .* A of every node that carries a point mass, plus
+             * f_int + C_e V_e + M_e A_e of every element that HAS A FIXED NODE (Element.cpp:53-64, lin3DHexa8.cpp:415-436);
+             * no tolerance filter.  Only fixed nodes keep their rows (DynamicAnalysis.cpp:136-149).                     */
+            memset(Reac, 0, nT * sizeof(double));
+            int off = 0;
+            for (int q = 0; q < m->n_mass; q++) {
+                int nd = m->mass_node[q];
+                for (int p = m->node_ptr[nd]; p < m->node_ptr[nd + 1]; p++, off++) Reac[m->totaldof[p]] += m->mass_val[off] * A[m->totaldof[p]];
+            }
+            double *Me = (double *)malloc(72 * 72 * sizeof(double)), *Ce = (double *)malloc(72 * 72 * sizeof(double));
+            for (int e = 0; e < nE; e++) {
+                int nn = elem_nn(m->elem_kind[e]), fixed = 0;
+                for (int i = 0; i < nn && !fixed; i++) fixed = node_fixed[m->elem_conn[8 * e + i]];
+                if (!fixed) continue;
+                double fe[72];
+                elem_fint(m, e, &rt[e], U, fe);
+                elem_MC(m, e, &rt[e], Me, Ce);
+                int nd = rt[e].nd;
+                for (int i = 0; i < nd; i++) {
+                    double v = fe[i];
+                    for (int j = 0; j < nd; j++) v += Ce[i * nd + j] * V[rt[e].dofs[j]] + Me[i * nd + j] * A[rt[e].dofs[j]];
+                    Reac[rt[e].dofs[i]] += v;
+                }
+            }
+            free(Me); free(Ce);
+            for (int i = 0; i < nT; i++) Reac[i] = is_fixed_dof[i] ? Reac[i] - Fext[i] : 0.0;
+        }
+        const double *src = field == 0 ? U : field == 1 ? V : field == 2 ? A : Reac;
         for (int q = 0; q < n_rec; q++) out[(size_t)(k - 1) * n_rec + q] = src[rec_dofs[q]];
     }
     if (Ufinal) memcpy(Ufinal, U, nT * sizeof(double));
@@ -1238,7 +1297,7 @@ done:
     free(rt); free(U); free(V); free(A); free(Up); free(Fint); free(Fext); free(Ftmp); free(rhs);
     free(dUt); free(Utr); free(Feff); free(dU); free(fe_all); free(lM.t); free(lC.t); free(lKp.t);
     free(lKm.t); free(lF.t); csr_free(&Kp); csr_free(&Km); csr_free(&T); csr_free(&Kf); csr_free(&Cs); csr_free(&Gs); free(lG.t); free(Ubar); free(Gtmp);
-    free(cidx); free(Kdiag); free(Kc); free(bc);
+    free(cidx); free(Kdiag); free(Kc); free(bc); free(SM); free(Reac); free(node_fixed); free(is_fixed_dof);
     return rc;
 }
 

@@ -120,10 +120,20 @@ typedef struct svlo_model {
     /* analysis */
     double dt, ftol, mtol;
     const double *U0, *V0, *A0;    /* [n_total] or NULL                          */
+    /* support motions (Driver.hpp:509-563 UpdateSupportMotion; Node::GetSupportMotion, Node.cpp:228-247;
+     * Assembler::ComputeSupportMotionIncrement, Assembler.cpp:493-533): one entry per (node, dof) that a SUPPORTMOTION
+     * load of the combination lists; factor = that load's combination factor    */
+    int32_t n_sup;
+    const int32_t *sup_dof;        /* [n_sup] TOTAL dof                          */
+    const int32_t *sup_ptr;        /* [n_sup+1] into sup_series                  */
+    const double  *sup_series;     /* Xo of each entry (size 1 = CONSTANT)       */
+    const double  *sup_factor;     /* [n_sup]                                    */
 } svlo_model;
 
 /* Runs DynamicAnalysis::Analyze with CentralDifference+Linear for k=1..nt-1
- * and writes, for every step, the values of `field` (0 disp,1 vel,2 accel) at
+ * and writes, for every step, the values of `field` (0 disp,1 vel,2 accel,
+ * 3 reaction = Integrator::ComputeReactionForce as DynamicAnalysis::UpdateDomain
+ * stores it, DynamicAnalysis.cpp:130-150, CentralDifference.cpp:155-171) at
  * the total dofs rec_dofs[0..n_rec) into out[(nt-1)*n_rec].  Returns 0 on
  * success.  If Ufinal != NULL it receives the last U (n_total).              */
 int svlo_run_central_difference(const svlo_model *m, int nt, int field, int n_rec,

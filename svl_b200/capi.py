@@ -21,7 +21,7 @@ _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
 _bp = C.POINTER(C.c_uint8)
 
-DISP, VEL, ACCEL = 0, 1, 2
+DISP, VEL, ACCEL, REACTION = 0, 1, 2, 3
 
 EXPORTS = [
     "svlgpu_create", "svlgpu_destroy", "svlgpu_last_error", "svlgpu_set_nodes", "svlgpu_add_nodal_mass",
@@ -31,7 +31,8 @@ EXPORTS = [
     "svlgpu_step", "svlgpu_sync", "svlgpu_step_host", "svlgpu_get_state", "svlgpu_internal_force",
     "svlgpu_get_mass_diagonal", "svlgpu_get_gauss", "svlgpu_read_recorder", "svlgpu_recorder_rows",
     "svlgpu_recorder_width", "svlgpu_get_counters", "svlgpu_set_kernel_timing", "svlgpu_kernel_time",
-    "svlgpu_device_ptr", "svlgpu_add_halo", "svlgpu_nccl_unique_id", "svlgpu_comm_init",
+    "svlgpu_device_ptr", "svlgpu_add_halo", "svlgpu_nccl_unique_id", "svlgpu_comm_init", "svlgpu_measure_peaks",
+    "svlgpu_add_support_motion",
 ]
 
 
@@ -91,6 +92,8 @@ def load_library():
     L.svlgpu_add_halo.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip]
     L.svlgpu_nccl_unique_id.argtypes = [C.c_void_p]
     L.svlgpu_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.svlgpu_measure_peaks.argtypes = [C.c_int, _dp, _dp]
+    L.svlgpu_add_support_motion.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, C.c_double]
     _lib = L
     return L
 
@@ -106,6 +109,15 @@ def nccl_unique_id() -> bytes:
     if L.svlgpu_nccl_unique_id(buf):
         raise SvlError(L.svlgpu_last_error().decode())
     return buf.raw
+
+
+def measure_peaks(device: int = 0):
+    """(FP64 FMA TFLOP/s, streaming-copy GB/s) measured on the device by the library's micro-benchmarks."""
+    L = load_library()
+    tf, bw = C.c_double(0), C.c_double(0)
+    if L.svlgpu_measure_peaks(device, C.byref(tf), C.byref(bw)):
+        raise SvlError(L.svlgpu_last_error().decode())
+    return tf.value, bw.value
 
 
 def _d(a):
@@ -195,6 +207,9 @@ class DeviceModel:
                     self.h, len(d.elems), _i(A(d.elems, np.int32)), len(d.nodes), _i(A(d.nodes, np.int32)),
                     ext.ctypes.data_as(_bp), _d(A(pw["dir"], np.float64)), _d(A(pw["pol"], np.float64)),
                     _d(A(pw["xref"], np.float64)), pw["c"], pw["f0"], pw["t0"], pw["amp"], float(d.factor)))
+        for node, dof, series, fac in getattr(m, "supports", None) or []:
+            sr = A(series, np.float64)
+            self._ck(self.L.svlgpu_add_support_motion(self.h, int(node), int(dof), len(sr), _d(sr), float(fac)))
         self.recorders = {}
         rows = max_rows if max_rows is not None else max(m.nt, 1)
         if m.rec_nodes is not None and len(m.rec_nodes):

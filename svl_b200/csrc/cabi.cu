@@ -237,13 +237,24 @@ int svlgpu_add_drm_planewave(svlgpu_model *m, int nelems, const int32_t *elems, 
 
 int svlgpu_add_node_recorder(svlgpu_model *m, int field, int nnodes, const int32_t *nodes, int max_rows) {
     try {
-        if (!m || m->finalized || nnodes <= 0 || field < 0 || field > 2) { set_error("add_node_recorder: bad arguments (disp/vel/accel only)"); return -1; }
+        if (!m || m->finalized || nnodes <= 0 || field < 0 || field > 3) { set_error("add_node_recorder: bad arguments (disp / vel / accel / reaction)"); return -1; }
         Recorder r;
         r.field = field; r.nodes.assign(nodes, nodes + nnodes); r.max_rows = max_rows;
         for (int n : r.nodes) if (n < 0 || n >= m->n_nodes) { set_error("add_node_recorder: node out of range"); return -1; }
         m->recorders.push_back(std::move(r));
         return (int)m->recorders.size() - 1;
     } catch (...) { set_error("add_node_recorder: host out of memory"); return -1; }
+}
+
+int svlgpu_add_support_motion(svlgpu_model *m, int node, int dof, int nt, const double *series, double factor) {
+    GUARD_BEGIN
+    REQUIRE(m && !m->finalized && m->n_nodes && nt > 0 && series, "add_support_motion: bad arguments (set nodes first, before finalize)");
+    REQUIRE(node >= 0 && node < m->n_nodes && dof >= 0 && dof < m->node_ndof[node], "add_support_motion: node / dof out of range");
+    SupportMotion sm;
+    sm.node = node; sm.dof = dof; sm.series.assign(series, series + nt); sm.factor = factor;
+    m->supports.push_back(std::move(sm));
+    return 0;
+    GUARD_END
 }
 
 int svlgpu_set_initial_state(svlgpu_model *m, const double *U, const double *V, const double *A) {

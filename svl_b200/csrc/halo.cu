@@ -270,6 +270,7 @@ int halo_comm_init(svlgpu_model *m, const void *id128, int rank, int nranks) {
                         set_error("free dof without mass: Keff is singular (EigenSolver.cpp:52-55)");
                         return 1;
                     }
+        m->h_cdiag = cglob;                            // REACTION recorders read the global diagonals (uploaded at first use)
         const int rc = newmark_comm_setup(m, dm, dc);
         cudaFree(dm); cudaFree(dc); cudaFree(dfree);
         if (rc) return 1;

@@ -36,6 +36,11 @@ __device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, 
     int sz = valid ? 8 : 0;                       // src-size 0 => zero fill
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gsrc), "r"(sz));
 }
+// same, ordered against the surrounding shared-memory accesses of the issuing thread
+__device__ __forceinline__ void cp_async8m(double *smem_dst, const double *gsrc) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
@@ -582,6 +587,195 @@ __global__ void __launch_bounds__(NW * 32, (NW * R <= 16) ? 3 : 2) k_stencil3_v4
         body(it, std::integral_constant<int, 0>{});
         if (it + 1 < nit) body(it + 1, std::integral_constant<int, 1>{});
         if (it + 2 < nit) body(it + 2, std::integral_constant<int, 2>{});
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// 3-D block stencil, dominant node class, separable form ("v5").  Same tiles, TMA ring and update as k_stencil3_v4;
+// the 27 x (3x3) row of K is not applied entry by entry (153 DFMA per node) but direction by direction.  For the interior
+// class of a homogeneous lattice of rectangular cells the row is a sum of tensor products of the 1-D stencils
+// m = [1 4 1] (mass), s = [-1 2 -1] (stiffness), d = [-1 0 1] (gradient):
+//     K_aa = sum_axis c[a][axis] * (s along axis, m along the two others)        K_ab = e[ab] * (d along a, d along b, m along the third)
+// (tests/test_oracle_cpu.py::test_interior_hex8_stencil_is_a_sum_of_tensor_products).  The planner FITS c and e to the
+// class table it assembled from the element matrices and uses this kernel only if the tensor-product table reproduces
+// every entry to 1e-13 of the largest (no material or geometry formula is trusted).  Per input plane a thread
+//   1. applies m, s, d along x to the three components of rows j-1 .. j+R (operands are the 9 consecutive doubles
+//      u(i-1..i+1) of the staged row): 12 FP64 instructions per row, (R+2)/R rows per node;
+//   2. applies m, s, d along y to those 9 fields, only the 15 products the formula needs: 23 instructions per node;
+//   3. groups the results by their z operator -- A (through m_z), B (through s_z), C (through d_z) -- and scatters
+//      P = A - B, 4A + 2B, +-C into the accumulators of output planes kk-1, kk, kk+1: 28 instructions per node.
+// ~78 FP64 instructions per node with the update instead of 162, two accumulator planes instead of three (the plane kk+1
+// accumulator is initialised, not accumulated, so it takes the registers of the plane that was just finished: the loop
+// is unrolled by the period 2).  The summation order differs from the 27-point form (and from the reference's element
+// loop) at the 1e-16 level per operation; parity bar 1e-10 (tests/test_gpu_parity.py).
+// ------------------------------------------------------------------------------------------
+struct Sep3 {
+    double c[3][3];      // c[a][axis]
+    double e[3];         // xy, xz, yz
+    double kinv[3], km[3];
+};
+
+template <int NW, int R>
+__global__ void __launch_bounds__(NW * 32, 3) k_stencil3_sep(const Dom3 p, const Sep3 cf) {
+    constexpr int TY = NW * R, TYH = TY + 2, NS = 4, NT = NW * 32;
+    constexpr int PLANE = TYH * kT3Row;
+    static_assert(TYH <= 32, "the TMA-issuing lanes must sit in one warp");
+    extern __shared__ __align__(16) double pl[];
+    double *ups_all = pl + NS * PLANE;
+    uint64_t *full = reinterpret_cast<uint64_t *>(ups_all + NT * R * 3);
+
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int item = blockIdx.x;
+    const int txi = item % p.tiles_x; item /= p.tiles_x;
+    const int tyi = item % p.tiles_y; item /= p.tiles_y;
+    const int i0 = p.bi0 + txi * 32, j0 = p.bj0 + tyi * TY;
+    const int k0 = p.bk0 + item * p.kz, k1 = min(k0 + p.kz, p.bk1);
+    const int gi = i0 + lane, gjb = j0 + w * R;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; s++) mbar_init(&full[s], TYH);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    const int e0 = 3 * (i0 - 1);
+    const int ea = max(e0, 0), eb = min(3 * (i0 + 33), 3 * p.nx);
+    const int q0 = ((ea - e0) + (int)(p.dof0 & 1) + ea) & 1;            // shift parity of row y = 0, k = 0
+    const int altx = p.nx & 1, alty = p.ny & 1;
+
+    const int prow_y = j0 - 1 + (int)threadIdx.x;
+    const bool prow_ok = (threadIdx.x < TYH) && prow_y >= 0 && prow_y < p.ny && eb > ea;
+    auto issue_plane = [&](int k, int stage) {
+        if (!prow_ok || k < 0 || k >= p.nz) { mbar_arrive(&full[stage]); return; }
+        const long long g = p.dof0 + 3ll * p.nx * (prow_y + (long long)p.ny * k) + ea;
+        const int par = (int)(g & 1);
+        int len = eb - ea + par;
+        len += len & 1;
+        const int dsti = (ea - par - e0) + ((ea - par - e0) & 1);
+        mbar_arrive_expect_tx(&full[stage], (unsigned)len * 8u);
+        bulk_g2s(pl + stage * PLANE + (int)threadIdx.x * kT3Row + dsti, p.U + (g - par), (unsigned)len * 8u, &full[stage]);
+    };
+
+    double *ups = ups_all + threadIdx.x;
+    double A[2][R][3];
+#pragma unroll
+    for (int s = 0; s < 2; s++)
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int a = 0; a < 3; a++) A[s][r][a] = 0.0;
+
+    const bool col_in = (gi >= p.bi0) && (gi < p.bi1);
+    bool rowin[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) rowin[r] = col_in && (gjb + r >= p.bj0) && (gjb + r < p.bj1);
+
+    if (threadIdx.x < TYH) {
+        issue_plane(k0 - 1, 0);
+        issue_plane(k0, 1);
+    }
+
+    const long long pstride = 3ll * p.nx * p.ny;
+    const int rstride = 3 * p.nx;
+    long long off = p.dof0 + 3ll * (gi + (long long)p.nx * (gjb + (long long)p.ny * (k0 - 2)));   // node (gi, gjb, kk-1)
+    const int nit = k1 - k0 + 2;
+
+    auto body = [&](const int it, auto rot_tag) {
+        constexpr int ROT = decltype(rot_tag)::value;     // A[ROT]: output plane kk-1 (finished here, then re-used for kk+1)
+        const int kk = k0 - 1 + it;
+        __syncthreads();                                   // everyone is done with the stage that is refilled now
+        if (threadIdx.x < TYH && kk + 2 <= k1) issue_plane(kk + 2, (it + 2) % NS);
+        const bool fin = (kk - 1 >= k0) && (kk - 1 < k1);  // plane kk-1 is finished by this iteration
+        const bool finn = p.mode == 0 && (kk >= k0) && (kk < k1);   // plane kk will be finished by the next one
+        const int shk = (q0 + altx * ((alty * kk) & 1)) & 1;
+        const int shp = (q0 + altx * ((alty * (kk - 1)) & 1)) & 1;
+        const double *plk = pl + (it % NS) * PLANE + (w * R) * kT3Row + 3 * lane;
+        const double *plp = pl + ((it + NS - 1) % NS) * PLANE + (w * R + 1) * kT3Row + 3 * lane + 3;
+        mbar_wait(&full[it % NS], (unsigned)((it / NS) & 1));
+        cp_async_wait<0>();
+
+        // x-operator fields of three consecutive rows: X[row % 3][component][m, s, d]
+        double X[3][3][3];
+#pragma unroll
+        for (int q = 0; q < R + 2; q++) {
+            {
+                const double *s = plk + q * kT3Row + ((shk + altx * ((gjb - 1 + q) & 1)) & 1);
+#pragma unroll
+                for (int b = 0; b < 3; b++) {
+                    const double um = s[b], u0 = s[3 + b], up = s[6 + b];
+                    const double t = um + up;
+                    X[q % 3][b][0] = fma(4.0, u0, t);
+                    X[q % 3][b][1] = fma(2.0, u0, -t);
+                    X[q % 3][b][2] = up - um;
+                }
+            }
+            if (q < 2) continue;
+            const int r = q - 2;
+            const int lo = (q + 1) % 3, mi = (q + 2) % 3, hi = q % 3;
+            // y operators: my / sy / dy of the x fields that the formula needs
+            double tt;
+#define SVL_MY(b, f) (tt = X[lo][b][f] + X[hi][b][f], fma(4.0, X[mi][b][f], tt))
+#define SVL_DY(b, f) (X[hi][b][f] - X[lo][b][f])
+            const double my_sx_ux = SVL_MY(0, 1), my_sx_uy = SVL_MY(1, 1), my_sx_uz = SVL_MY(2, 1);
+            const double t_mx = X[lo][0][0] + X[hi][0][0];
+            const double my_mx_ux = fma(4.0, X[mi][0][0], t_mx), sy_mx_ux = fma(2.0, X[mi][0][0], -t_mx);
+            const double t_my = X[lo][1][0] + X[hi][1][0];
+            const double my_mx_uy = fma(4.0, X[mi][1][0], t_my), sy_mx_uy = fma(2.0, X[mi][1][0], -t_my);
+            const double t_mz = X[lo][2][0] + X[hi][2][0];
+            const double my_mx_uz = fma(4.0, X[mi][2][0], t_mz), sy_mx_uz = fma(2.0, X[mi][2][0], -t_mz);
+            const double dy_mx_uy = SVL_DY(1, 0), dy_mx_uz = SVL_DY(2, 0);
+            const double dy_dx_ux = SVL_DY(0, 2), dy_dx_uy = SVL_DY(1, 2);
+            const double my_dx_ux = SVL_MY(0, 2), my_dx_uz = SVL_MY(2, 2);
+#undef SVL_MY
+#undef SVL_DY
+            // grouped by z operator: A through m_z, B through s_z, C through d_z
+            const double Ax = fma(cf.c[0][0], my_sx_ux, fma(cf.c[0][1], sy_mx_ux, cf.e[0] * dy_dx_uy));
+            const double Ay = fma(cf.c[1][0], my_sx_uy, fma(cf.c[1][1], sy_mx_uy, cf.e[0] * dy_dx_ux));
+            const double Az = fma(cf.c[2][0], my_sx_uz, cf.c[2][1] * sy_mx_uz);
+            const double Px = fma(-cf.c[0][2], my_mx_ux, Ax), Py = fma(-cf.c[1][2], my_mx_uy, Ay), Pz = fma(-cf.c[2][2], my_mx_uz, Az);
+            // output plane kk-1: last contribution (+P + C), then the CentralDifference update (CentralDifference.cpp:138-148)
+            double F[3];
+            F[0] = fma(cf.e[1], my_dx_uz, A[ROT][r][0] + Px);
+            F[1] = fma(cf.e[2], dy_mx_uz, A[ROT][r][1] + Py);
+            F[2] = fma(cf.e[2], dy_mx_uy, fma(cf.e[1], my_dx_ux, A[ROT][r][2] + Pz));
+            // output plane kk: 4 A + 2 B
+            A[ROT ^ 1][r][0] = fma(2.0 * cf.c[0][2], my_mx_ux, fma(4.0, Ax, A[ROT ^ 1][r][0]));
+            A[ROT ^ 1][r][1] = fma(2.0 * cf.c[1][2], my_mx_uy, fma(4.0, Ay, A[ROT ^ 1][r][1]));
+            A[ROT ^ 1][r][2] = fma(2.0 * cf.c[2][2], my_mx_uz, fma(4.0, Az, A[ROT ^ 1][r][2]));
+            // output plane kk+1: first contribution (+P - C), into the registers of the plane that was just finished
+            A[ROT][r][0] = fma(-cf.e[1], my_dx_uz, Px);
+            A[ROT][r][1] = fma(-cf.e[2], dy_mx_uz, Py);
+            A[ROT][r][2] = fma(-cf.e[2], dy_mx_uy, fma(-cf.e[1], my_dx_ux, Pz));
+            if (fin && rowin[r]) {
+                // U_n of this node: still staged (plane kk-1 lives in the previous stage until the next refill)
+                const double *uc = plp + r * kT3Row + ((shp + altx * ((gjb + r) & 1)) & 1);
+                double *o = p.Un + (off + r * rstride);
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    if (p.mode == 0) {
+                        const double un = uc[a];
+                        o[a] = un + (cf.km[a] * (un - ups[(3 * r + a) * NT]) - F[a]) * cf.kinv[a];
+                    } else {
+                        o[a] = F[a];
+                    }
+                }
+            }
+            // U_{n-1} of the node one plane up (finished by the next iteration) into the slots this thread has just read:
+            // the slots are private to the thread, so program order is all the ordering the prefetch needs, and it gets a
+            // whole plane of compute to cover the DRAM latency
+            if (finn && rowin[r]) {
+                const double *g = p.Up + (off + pstride + r * rstride);
+                cp_async8m(ups + (3 * r + 0) * NT, g + 0);
+                cp_async8m(ups + (3 * r + 1) * NT, g + 1);
+                cp_async8m(ups + (3 * r + 2) * NT, g + 2);
+            }
+        }
+        cp_async_commit();
+        off += pstride;
+    };
+    for (int it = 0; it < nit; it += 2) {
+        body(it, std::integral_constant<int, 0>{});
+        if (it + 1 < nit) body(it + 1, std::integral_constant<int, 1>{});
     }
 }
 
@@ -1187,6 +1381,7 @@ struct PLArgs {
     const int32_t *target;        // per loaded dof: slot in hF (interface dof), -2-c (PML unknown c) or -1
     double *hF, *bext;
     int phase;                    // 0: interface / PML dofs (before the exchange / block solve), 1: all other dofs
+    double sign;                  // phase 1: +1, or -1 for the reaction pass (R = F_int - F_ext)
 };
 __global__ void k_nodal_loads(const PLArgs a) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1208,7 +1403,7 @@ __global__ void k_nodal_loads(const PLArgs a) {
     }
     if (tg != -1) return;
     const int d = a.dof[t];
-    a.Un[d] += (a.kinv ? a.kinv[d] : 1.0) * F;
+    a.Un[d] += a.sign * (a.kinv ? a.kinv[d] : 1.0) * F;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1304,7 +1499,7 @@ __global__ void __launch_bounds__(128) k_drm(const DrmArgs a, double *F) {
 }
 // phase 0: rows on interface nodes (hF -= F, before the exchange); phase 1: all other rows (U_{n+1} += F / Keff)
 __global__ void k_drm_apply(int n, int nd, int phase, const int32_t *dof0, const int32_t *target, const double *F,
-                            const double *kinv, double *Un, double *hF) {
+                            const double *kinv, double *Un, double *hF, double sign) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n * nd) return;
     const int row = t / nd, r = t - row * nd;
@@ -1312,7 +1507,48 @@ __global__ void k_drm_apply(int n, int nd, int phase, const int32_t *dof0, const
     if ((phase == 0) != (tg >= 0)) return;
     if (tg >= 0) { hF[tg + r] -= F[t]; return; }
     const int d = dof0[row] + r;
-    Un[d] += (kinv ? kinv[d] : 1.0) * F[t];
+    Un[d] += sign * (kinv ? kinv[d] : 1.0) * F[t];
+}
+
+// ------------------------------------------------------------------------------------------
+// Support motion (Assembler.cpp:493-533, Node.cpp:228-247).  The state buffers hold, at a moving support dof, the value the
+// ELEMENTS see: like the reference, one step behind the true displacement (Algorithm.cpp:23 passes T dU only to the element
+// update, CentralDifference.cpp:135 adds the increment afterwards).  With W_k the buffer read by step k:
+// W_{k+1}[s] = W_k[s] + dg(k-1) (k_support), and the true history of a support dof is U(k) = W_{k+1} + dg(k),
+// U(k-1) = W_{k+1}, U(k-2) = W_k -- what the recorders and getters report.
+struct SupArgs {
+    int n;
+    const int32_t *dof, *ptr;     // ascending internal dofs, CSR into series
+    const double *series, *fac;
+};
+__device__ __forceinline__ double sup_dg(const SupArgs &s, int q, int j) {      // factor (g(j) - g(j-1)), 0 for j < 1
+    if (j < 1) return 0.0;
+    const double *x = s.series + s.ptr[q];
+    const int sz = s.ptr[q + 1] - s.ptr[q];
+    const double g1 = (j < sz) ? x[j] : x[0], g0 = (j - 1 < sz) ? x[j - 1] : x[0];
+    return s.fac[q] * (g1 - g0);
+}
+__device__ __forceinline__ int sup_find(const SupArgs &s, int d) {
+    int lo = 0, hi = s.n - 1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) >> 1, v = s.dof[mid];
+        if (v == d) return mid;
+        if (v < d) lo = mid + 1; else hi = mid - 1;
+    }
+    return -1;
+}
+// true U(k), U(k-1), U(k-2) of dof d after step k (buffers: Un = newest, U, Up)
+__device__ __forceinline__ void state3(const SupArgs &s, int k, int d, const double *Un, const double *U, const double *Up,
+                                       double &un, double &u, double &up) {
+    un = Un[d]; u = U[d]; up = Up[d];
+    if (s.n) {
+        const int q = sup_find(s, d);
+        if (q >= 0) { up = u; u = un; un = un + sup_dg(s, q, k); }
+    }
+}
+__global__ void k_support(const SupArgs s, int k, double *Un) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < s.n) Un[s.dof[t]] += sup_dg(s, t, k - 1);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1320,7 +1556,7 @@ __global__ void k_drm_apply(int n, int nd, int phase, const int32_t *dof0, const
 // ------------------------------------------------------------------------------------------
 __global__ void k_record(int n, const int32_t *dofs, const double *Un, const double *U, const double *Up,
                          double dt, int field, double *row, const int32_t *kctl, int max_rows, double *mirror,
-                         const double *Vs, const double *As) {
+                         const double *Vs, const double *As, const SupArgs sup, int k) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     if (kctl) {                                   // graph replay: `row` is the recorder base, the row index lives on the device
@@ -1328,7 +1564,8 @@ __global__ void k_record(int n, const int32_t *dofs, const double *Un, const dou
         row += (size_t)kctl[1] * n;
     }
     const int d = dofs[t];
-    const double un = Un[d], u = U[d], up = Up[d];
+    double un, u, up;
+    state3(sup, k, d, Un, U, Up, un, u, up);
     double v;
     if (field == SVLGPU_DISP) v = un;
     else if (Vs) v = (field == SVLGPU_VEL) ? Vs[d] : As[d];      // Newmark keeps V, A as state (NewmarkBeta.cpp:75-76)
@@ -1338,15 +1575,51 @@ __global__ void k_record(int n, const int32_t *dofs, const double *Un, const dou
     if (mirror) mirror[t] = v;                    // svlgpu_step_host: the row also goes straight to mapped pinned host memory
 }
 
+// REACTION recorder row: R = F_int + C V + M A - F_ext at the dofs of fixed nodes, zero elsewhere (DynamicAnalysis.cpp:130-150,
+// CentralDifference.cpp:155-171).  Fs = F_int - F_ext of the newest state (force-only pass); M, C are the lumped diagonals
+// (Assembler.cpp:568-619 sums M_e A_e and C_e V_e of every element at a fixed node: with lumped mass and mass-proportional
+// damping these are diagonal), plus the off-diagonal couplings of ZeroLength1D dashpots.
+struct ReacArgs {
+    int n;
+    const int32_t *dofs;
+    const double *Fs, *Un, *U, *Up;
+    const double *mass, *cd, *ccoef;
+    const uint8_t *fixed;
+    const int32_t *cptr, *cdof;
+    double dt;
+    int k;
+    SupArgs sup;
+};
+__global__ void k_reaction(const ReacArgs a, double *row, double *mirror) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n) return;
+    double r = 0.0;
+    if (a.fixed[t]) {
+        const int d = a.dofs[t];
+        double un, u, up;
+        state3(a.sup, a.k, d, a.Un, a.U, a.Up, un, u, up);
+        const double V = 1.0 / 2.0 / a.dt * (un - up), A = 1.0 / a.dt / a.dt * ((un - u) - u + up);
+        r = a.Fs[d] + a.cd[t] * V + a.mass[t] * A;
+        for (int q = a.cptr[t]; q < a.cptr[t + 1]; q++) {
+            const int d2 = a.cdof[q];
+            state3(a.sup, a.k, d2, a.Un, a.U, a.Up, un, u, up);
+            r += a.ccoef[q] * (1.0 / 2.0 / a.dt * (un - up));
+        }
+    }
+    row[t] = r;
+    if (mirror) mirror[t] = r;
+}
+
 __global__ void k_gather(int n, const int32_t *dofs, const int32_t *int_of_total, const double *Un,
                          const double *U, const double *Up, double dt, int field, double *out, const double *Vs,
-                         const double *As) {
+                         const double *As, const SupArgs sup, int k) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const int d = int_of_total[dofs ? dofs[t] : t];
     if (Vs && field != SVLGPU_DISP) { out[t] = (field == SVLGPU_VEL) ? Vs[d] : As[d]; return; }
     // state after the last step: Un = U_{n+1} (current), U = U_n, Up = U_{n-1}
-    const double un = Un[d], u = U[d], up = Up[d];
+    double un, u, up;
+    state3(sup, k, d, Un, U, Up, un, u, up);
     double v;
     if (field == SVLGPU_DISP) v = un;
     else if (field == SVLGPU_VEL) v = 1.0 / 2.0 / dt * (un - up);
@@ -1503,7 +1776,14 @@ static int launch_node_update(svlgpu_model *m, const double *U, const double *Up
                 p.tiles_x = d.tiles_x; p.tiles_y = d.tiles_y; p.kz = d.kz; p.dom = d.cls; p.mode = mode;
                 const unsigned grid = (unsigned)(d.tiles_x * d.tiles_y * d.zchunks);
                 timer_begin(m, 0);
-                if (d.pure && d.sym && d.v4 && d.rows == 6) launch_v4<kDomNW, 6>(p, d.slot, d.nobar, grid, m->stream);
+                if (d.sep) {
+                    Sep3 cf;
+                    for (int a = 0; a < 3; a++) {
+                        for (int x = 0; x < 3; x++) cf.c[a][x] = d.sepc[3 * a + x];
+                        cf.e[a] = d.sepe[a]; cf.kinv[a] = d.tbl[270 + a]; cf.km[a] = d.tbl[273 + a];
+                    }
+                    k_stencil3_sep<kDomNW, kDomR><<<grid, kDomNW * 32, stencil3_tma_smem(kDomNW, kDomR), m->stream>>>(p, cf);
+                } else if (d.pure && d.sym && d.v4 && d.rows == 6) launch_v4<kDomNW, 6>(p, d.slot, d.nobar, grid, m->stream);
                 else if (d.pure && d.sym && d.v4) launch_v4<kDomNW, kDomR>(p, d.slot, d.nobar, grid, m->stream);
                 else if (d.pure) launch_tma<kDomNW, kDomR>(p, d.slot, d.ortho, grid, m->stream);
                 else launch_dom<kDomNW, kDomR>(p, d.slot, d.ortho, grid, m->stream);
@@ -1598,17 +1878,79 @@ int halo_generic_force(svlgpu_model *m) {
     return 0;
 }
 
+static SupArgs sup_args(const svlgpu_model *m) {
+    SupArgs s;
+    s.n = m->sup.n; s.dof = m->sup.d_dof; s.ptr = m->sup.d_ptr; s.series = m->sup.d_series; s.fac = m->sup.d_fac;
+    return s;
+}
+
+static int launch_external(svlgpu_model *m, int k, const double *dev_amp, double *Un, int phase, bool scaled = true, double sign = 1.0);
+static int launch_generic_elements(svlgpu_model *m, const double *U, int commit);
+static int launch_node_update(svlgpu_model *m, const double *U, const double *Up, double *Un, int mode);
+
+// F_int(newest state) - F_ext(k) of the whole mesh into the scratch vector, interface dofs summed over the ranks:
+// what Integrator::ComputeReactionForce assembles (CentralDifference.cpp:155-171), at the cost of one force-only pass
+static int reaction_pass(svlgpu_model *m, int k, const double *dev_amp) {
+    if (!m->d_fscratch) {
+        CUDA_OK(cudaMalloc(&m->d_fscratch, sizeof(double) * m->n_int));
+        m->allocs.push_back(m->d_fscratch);
+        m->device_bytes += (int64_t)sizeof(double) * m->n_int;
+    }
+    double *Fs = m->d_fscratch;
+    const double *Un = m->d_U[m->next];
+    CUDA_OK(cudaMemsetAsync(Fs, 0, sizeof(double) * m->n_int, m->stream));
+    if (launch_generic_elements(m, Un, 0)) return 1;             // stresses of the newest state, nothing committed
+    if (launch_node_update(m, Un, nullptr, Fs, 1)) return 1;
+    if (launch_external(m, k, dev_amp, Fs, 1, false, -1.0)) return 1;
+    if (m->halo.active && !m->halo_peers.empty()) {
+        if (halo_vec_load(m, Fs)) return 1;                        // hF <- partial F_int at the interface dofs
+        if (external_forces_interface(m, k, dev_amp)) return 1;    // hF -= F_ext handed to this rank
+        if (halo_vec_sum(m, Fs)) return 1;                         // rank-ordered sum: the same bits on every holder
+    }
+    return 0;
+}
+
 void record_rows(svlgpu_model *m, bool devk) {
     int ri = -1;
+    bool reaction_ready = false;
+    const SupArgs sup = sup_args(m);
     for (auto &r : m->recorders) {
         ri++;
         if (r.rows >= r.max_rows || !r.width) continue;
-        k_record<<<(r.width + 127) / 128, 128, 0, m->stream>>>(r.width, r.d_dofs, m->d_U[m->next], m->d_U[m->cur],
-                                                                 m->d_U[m->prev], m->dt, r.field,
-                                                                 devk ? r.d_rows : r.d_rows + (size_t)r.rows * r.width,
-                                                                 devk ? m->d_kctl : nullptr, r.max_rows,
-                                                                 (ri == m->mirror_rec && !devk) ? m->h_row : nullptr,
-                                                                 m->nm.present ? m->nm.d_V : nullptr, m->nm.present ? m->nm.d_A : nullptr);
+        double *row = devk ? r.d_rows : r.d_rows + (size_t)r.rows * r.width;
+        double *mirror = (ri == m->mirror_rec && !devk) ? m->h_row : nullptr;
+        if (r.field == SVLGPU_REACTION) {
+            if (!r.d_rmass) {                          // first use: after svlgpu_comm_init the diagonals are the global sums
+                std::vector<double> ms(r.width), cd(r.width);
+                for (int t = 0; t < r.width; t++) { ms[t] = m->h_mass[r.h_dofs[t]]; cd[t] = m->h_cdiag[r.h_dofs[t]] + r.h_cdg[t]; }
+                auto up = [&](const void *src, size_t bytes) -> void * {
+                    void *p = nullptr;
+                    if (cudaMalloc(&p, std::max<size_t>(bytes, 8)) != cudaSuccess) return nullptr;
+                    cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, m->stream);
+                    cudaStreamSynchronize(m->stream);
+                    m->allocs.push_back(p);
+                    return p;
+                };
+                r.d_rmass = (double *)up(ms.data(), sizeof(double) * r.width);
+                r.d_rcd = (double *)up(cd.data(), sizeof(double) * r.width);
+                r.d_fixed = (uint8_t *)up(r.h_fixed.data(), r.width);
+                r.d_cptr = (int32_t *)up(r.h_cptr.data(), sizeof(int32_t) * r.h_cptr.size());
+                r.d_cdof = (int32_t *)up(r.h_cdof.data(), sizeof(int32_t) * r.h_cdof.size());
+                r.d_ccoef = (double *)up(r.h_ccoef.data(), sizeof(double) * r.h_ccoef.size());
+            }
+            if (!reaction_ready) { if (reaction_pass(m, m->k_of_step, m->step_amp)) return; reaction_ready = true; }
+            ReacArgs a;
+            a.n = r.width; a.dofs = r.d_dofs; a.Fs = m->d_fscratch; a.Un = m->d_U[m->next]; a.U = m->d_U[m->cur]; a.Up = m->d_U[m->prev];
+            a.mass = r.d_rmass; a.cd = r.d_rcd; a.ccoef = r.d_ccoef; a.fixed = r.d_fixed; a.cptr = r.d_cptr; a.cdof = r.d_cdof;
+            a.dt = m->dt; a.k = m->k_of_step; a.sup = sup;
+            k_reaction<<<(r.width + 127) / 128, 128, 0, m->stream>>>(a, row, mirror);
+        } else {
+            k_record<<<(r.width + 127) / 128, 128, 0, m->stream>>>(r.width, r.d_dofs, m->d_U[m->next], m->d_U[m->cur],
+                                                                     m->d_U[m->prev], m->dt, r.field, row,
+                                                                     devk ? m->d_kctl : nullptr, r.max_rows, mirror,
+                                                                     m->nm.present ? m->nm.d_V : nullptr, m->nm.present ? m->nm.d_A : nullptr,
+                                                                     sup, m->k_of_step);
+        }
         r.rows++;
         m->total_launches++;
     }
@@ -1648,7 +1990,7 @@ static int drm_prefetch(svlgpu_model *m, int knext) {
 // dofs, subtracted from the partial force that is about to be exchanged; phase 1: everything else,
 // applied to U_{n+1} directly (the solve is diagonal there).
 // `scaled`: forces are divided by the diagonal Keff on the way into U_{n+1} (CentralDifference); otherwise they are added raw
-static int launch_external(svlgpu_model *m, int k, const double *dev_amp, double *Un, int phase, bool scaled = true) {
+static int launch_external(svlgpu_model *m, int k, const double *dev_amp, double *Un, int phase, bool scaled, double sign) {
     const double *kinv = scaled ? m->d_kinv : nullptr;
     const bool halo = m->halo.active || m->pml.present;
     if (phase == 0 && !halo) return 0;
@@ -1659,6 +2001,7 @@ static int launch_external(svlgpu_model *m, int k, const double *dev_amp, double
         a.amp = dev_amp; a.kinv = kinv; a.Un = Un; a.k = k;
         a.target = halo ? m->d_pl_target : nullptr; a.hF = m->halo.d_hF; a.bext = m->pml.d_bext; a.phase = phase;
         a.kctl = m->graph_capturing ? m->d_kctl : nullptr;
+        a.sign = sign;
         timer_begin(m, 3);
         k_nodal_loads<<<(a.n + 127) / 128, 128, 0, m->stream>>>(a);
         timer_end(m, 3);
@@ -1673,7 +2016,7 @@ static int launch_external(svlgpu_model *m, int k, const double *dev_amp, double
         else if (d.ev_valid[b]) cudaStreamWaitEvent(m->stream, d.ev_ready[b], 0);
         k_drm_apply<<<(d.n_nodes * m->ndim + 127) / 128, 128, 0, m->stream>>>(d.n_nodes, m->ndim, phase, d.d_node_dof0,
                                                                               halo ? d.d_target : nullptr, d.d_F[b], kinv, Un,
-                                                                              m->halo.d_hF);
+                                                                              m->halo.d_hF, sign);
         timer_end(m, 5);
         m->total_launches++;
     }
@@ -1720,6 +2063,11 @@ static int step_once(svlgpu_model *m, int k, const double *dev_amp) {
     if (xchg && halo_exchange_end(m, U, Up, Un, 0)) return 1;
     if (m->pml.present && pml_step(m, U, Up, Un)) return 1;
     if (launch_external(m, k, dev_amp, Un, 1)) return 1;
+    if (m->sup.n) {                                           // W_{k+1}[s] = W_k[s] + dg(k-1), see k_support
+        k_support<<<(m->sup.n + 127) / 128, 128, 0, m->stream>>>(sup_args(m), k, Un);
+        m->total_launches++;
+    }
+    m->step_amp = dev_amp;
     record_rows(m, m->graph_capturing);
     k_advance<<<1, 1, 0, m->stream>>>(m->d_kctl);
     m->total_launches++;
@@ -1735,7 +2083,7 @@ static int step_once(svlgpu_model *m, int k, const double *dev_amp) {
 // buffers and the 2 DRM buffers): per-step launch latency is what limits small partitions (8 GPUs on 10^8 DOF).
 constexpr int kGraphSteps = 6;
 static bool graph_usable(const svlgpu_model *m, const double *dev_amp) {
-    return m->use_graph && !dev_amp && !m->kernel_timing && !m->pml.present;
+    return m->use_graph && !dev_amp && !m->kernel_timing && !m->pml.present && !m->sup.n && !m->has_reaction_rec;
 }
 void graph_destroy(svlgpu_model *m) {
     if (m->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)m->graph_exec);
@@ -1861,7 +2209,8 @@ int gather_state(svlgpu_model *m, int field, const int32_t *dofs, int n, double 
     // after a step the newest state sits in `cur`; U_n in `prev`, U_{n-1} in `next`
     k_gather<<<(n + 255) / 256, 256, 0, m->stream>>>(n, d_dofs, m->d_int_of_total, m->d_U[m->cur], m->d_U[m->prev],
                                                       m->d_U[m->next], m->dt, (m->steps_done || m->nm.present) ? field : SVLGPU_DISP, d_out,
-                                                      m->nm.present ? m->nm.d_V : nullptr, m->nm.present ? m->nm.d_A : nullptr);
+                                                      m->nm.present ? m->nm.d_V : nullptr, m->nm.present ? m->nm.d_A : nullptr,
+                                                      sup_args(m), m->steps_done ? m->k_of_step : 0);
     CUDA_OK(cudaMemcpyAsync(out, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, m->stream));
     CUDA_OK(cudaStreamSynchronize(m->stream));
     cudaFree(d_dofs); cudaFree(d_out);
@@ -1881,6 +2230,7 @@ template <int SLOT> static int cfg_slot() {
 }
 int configure_kernels() {
     if (cfg_slot<0>() || cfg_slot<1>() || cfg_slot<2>() || cfg_slot<3>()) return 1;
+    CUDA_OK(cudaFuncSetAttribute(k_stencil3_sep<kDomNW, kDomR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stencil3_tma_smem(kDomNW, kDomR)));
     CUDA_OK(cudaFuncSetAttribute(k_stencil2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     if (pml_configure()) return 1;
     return 0;

@@ -35,6 +35,24 @@ struct Recorder {
     int32_t *d_dofs = nullptr;       // internal dof ids, `width` entries
     double *d_rows = nullptr;        // [max_rows][width]
     int width = 0, rows = 0;
+    // REACTION recorders (DynamicAnalysis.cpp:130-150): per recorded dof the lumped mass and damping diagonal (uploaded at the
+    // first use: svlgpu_comm_init replaces interface values by their global sums), whether the node is fixed (rows of free
+    // nodes stay zero), and the off-diagonal damping couplings of ZeroLength1D dashpots as a CSR (other dof, coefficient)
+    std::vector<int32_t> h_dofs, h_cptr, h_cdof;
+    std::vector<double> h_ccoef, h_cdg;      // h_cdg: dashpot diagonal on restrained ends (not part of the Keff diagonal)
+    std::vector<uint8_t> h_fixed;
+    double *d_rmass = nullptr, *d_rcd = nullptr, *d_ccoef = nullptr;
+    uint8_t *d_fixed = nullptr;
+    int32_t *d_cptr = nullptr, *d_cdof = nullptr;
+};
+
+// support motion of one restrained dof (Driver.hpp:509-563, Node.cpp:132-134,228-247)
+struct SupportMotion { int node = 0, dof = 0; std::vector<double> series; double factor = 1.0; };
+struct SupportDev {
+    int n = 0;
+    int32_t *d_dof = nullptr;        // [n] internal dof, ascending
+    int32_t *d_ptr = nullptr;        // [n+1] into d_series
+    double *d_series = nullptr, *d_fac = nullptr;
 };
 
 struct BlockHint { int node0, nx, ny, nz; };
@@ -57,6 +75,8 @@ struct Block {
         bool pure = false;                           // the class fills its box and all 27 neighbours exist -> TMA kernel
         bool sym = false;                            // stencil even / odd in the offsets (k_stencil3_v4 SYM)
         bool v4 = true;                              // barrier-free renaming kernel (SVLGPU_STENCIL_V=3 selects the older one)
+        bool sep = false;                            // k_stencil3_sep: the table is a sum of tensor products of 1-D stencils
+        double sepc[9] = {}, sepe[3] = {};           // fitted coefficients c[a][axis], e[xy, xz, yz] (planner)
         int rows = 4;                                // lattice rows per thread (4 or 6)
         bool nobar = false;                          // k_stencil3_v4 without the per-plane CTA barrier (SVLGPU_STENCIL_NOBAR)
         int tiles_x = 0, tiles_y = 0, zchunks = 0, kz = 0;
@@ -256,6 +276,9 @@ struct svlgpu_model {
     std::vector<svl::PointLoad> ploads;
     std::vector<svl::DrmLoad> drms;
     std::vector<svl::Recorder> recorders;
+    std::vector<svl::SupportMotion> supports;
+    svl::SupportDev sup;
+    bool has_reaction_rec = false;
     std::vector<svl::BlockHint> hints;
     std::vector<double> U0, V0, A0;
     bool opt_lattice_guess = true, opt_keep_gauss = false;
@@ -310,6 +333,7 @@ struct svlgpu_model {
     int h_row_len = 0;
     bool shell_lowreg = false;                      // SVLGPU_SHELL_LOWREG: 96-register shell kernel (co-resides with the stencil)
     int mirror_rec = -1;                            // recorder whose next row k_record also writes to h_row (step_host)
+    const double *step_amp = nullptr;               // host-fed load amplitudes of the step being recorded (reaction pass)
 
     std::vector<svl::DrmDev> drm_dev;
 

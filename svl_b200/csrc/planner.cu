@@ -535,6 +535,67 @@ int plan_and_upload(svlgpu_model *m) {
                          lo[0] >= 1 && lo[1] >= 1 && lo[2] >= 1 && hi[0] <= NX - 2 && hi[1] <= NY - 2 && hi[2] <= NZ - 2 &&
                          !getenv("SVLGPU_NO_TMA");
                 if (!(d.pure && d.sym && d.v4)) d.rows = 4;
+                if (d.pure && d.sym && d.v4 && !getenv("SVLGPU_NO_SEP")) {
+                    // separable form (k_stencil3_sep): fit  K_aa = sum_x c[a][x] (s along x, m along the others),
+                    // K_ab = e[ab] (d along a, d along b, m along the third)  to the table by least squares and accept it
+                    // only if it reproduces every one of the 27 x 9 entries
+                    static const double m1[3] = {1, 4, 1}, s1[3] = {-1, 2, -1}, d1[3] = {-1, 0, 1};
+                    auto T = [&](int o0, int o1, int o2, int a, int bb) {      // offsets + 1 along x, y, z; row a, column bb
+                        return d.tbl[((o0 * 3 + bb) * 3 + o1) * 10 + (2 - o2) * 3 + a];
+                    };
+                    bool ok = true;
+                    for (int a = 0; a < 3 && ok; a++) {
+                        double N[3][3] = {}, rhs[3] = {};
+                        for (int o0 = 0; o0 < 3; o0++) for (int o1 = 0; o1 < 3; o1++) for (int o2 = 0; o2 < 3; o2++) {
+                            const int o[3] = {o0, o1, o2};
+                            double basis[3];
+                            for (int x = 0; x < 3; x++) {
+                                basis[x] = 1.0;
+                                for (int y = 0; y < 3; y++) basis[x] *= (y == x) ? s1[o[y]] : m1[o[y]];
+                            }
+                            for (int x = 0; x < 3; x++) {
+                                rhs[x] += basis[x] * T(o0, o1, o2, a, a);
+                                for (int y = 0; y < 3; y++) N[x][y] += basis[x] * basis[y];
+                            }
+                        }
+                        // 3 x 3 normal equations by Cramer's rule
+                        auto det3 = [](const double (&Q)[3][3]) {
+                            return Q[0][0] * (Q[1][1] * Q[2][2] - Q[1][2] * Q[2][1]) - Q[0][1] * (Q[1][0] * Q[2][2] - Q[1][2] * Q[2][0]) +
+                                   Q[0][2] * (Q[1][0] * Q[2][1] - Q[1][1] * Q[2][0]);
+                        };
+                        const double D0 = det3(N);
+                        if (!(std::fabs(D0) > 0)) { ok = false; break; }
+                        for (int x = 0; x < 3; x++) {
+                            double Q[3][3];
+                            for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) Q[r][cc] = (cc == x) ? rhs[r] : N[r][cc];
+                            d.sepc[3 * a + x] = det3(Q) / D0;
+                        }
+                    }
+                    static const int pa[3] = {0, 0, 1}, pb[3] = {1, 2, 2};
+                    for (int z2 = 0; z2 < 3 && ok; z2++) {
+                        int o[3] = {1, 1, 1};
+                        o[pa[z2]] = 2; o[pb[z2]] = 2;
+                        d.sepe[z2] = T(o[0], o[1], o[2], pa[z2], pb[z2]) / 4.0;
+                    }
+                    for (int o0 = 0; o0 < 3 && ok; o0++) for (int o1 = 0; o1 < 3; o1++) for (int o2 = 0; o2 < 3; o2++)
+                        for (int a = 0; a < 3; a++) for (int bb = 0; bb < 3; bb++) {
+                            const int o[3] = {o0, o1, o2};
+                            double v = 0;
+                            if (a == bb) {
+                                for (int x = 0; x < 3; x++) {
+                                    double t = d.sepc[3 * a + x];
+                                    for (int y = 0; y < 3; y++) t *= (y == x) ? s1[o[y]] : m1[o[y]];
+                                    v += t;
+                                }
+                            } else {
+                                const int lo = std::min(a, bb), hi2 = std::max(a, bb), third = 3 - a - bb;
+                                v = d.sepe[lo == 0 ? (hi2 == 1 ? 0 : 1) : 2] * d1[o[a]] * d1[o[bb]] * m1[o[third]];
+                            }
+                            if (std::fabs(v - T(o0, o1, o2, a, bb)) > 1e-13 * mx) ok = false;
+                        }
+                    d.sep = ok;
+                    if (ok) d.rows = 4;
+                }
                 const int TY = kDomNW * d.rows;
                 d.tiles_x = (hi[0] - lo[0] + 1 + 31) / 32; d.tiles_y = (hi[1] - lo[1] + 1 + TY - 1) / TY;
                 const int nzb = d.bk1 - d.bk0;
@@ -928,11 +989,68 @@ int plan_and_upload(svlgpu_model *m) {
         m->drm_dev.push_back(dd);
     }
 
+    // ---- F3. support motions (Assembler::ComputeSupportMotionIncrement, Assembler.cpp:493-533) -----------------------------
+    if (!m->supports.empty()) {
+        if (m->opt_integrator == 1) { set_error("support motion is implemented for CentralDifference only"); return 1; }
+        std::vector<uint8_t> coupled(nN, 0);            // nodes whose Keff rows are not diagonal
+        for (int e = 0; e < nE; e++) {
+            const int k = m->elem_kind[e];
+            if (k != SVLGPU_ZEROLENGTH1D && k != SVLGPU_PML3DHEXA8 && k != SVLGPU_PML2DQUAD4) continue;
+            for (int l = 0; l < kind_npe(k); l++) coupled[m->elem_conn[8ll * e + l]] = 1;
+        }
+        std::map<int32_t, const SupportMotion *> by_dof;
+        for (const SupportMotion &sm : m->supports) {
+            const int q = m->node_ptr[sm.node] + sm.dof;
+            if (m->freedof[q] != -1) { set_error("support motion on a dof that is not restrained"); return 1; }
+            if (coupled[sm.node]) { set_error("support motion on a node of a PML / ZeroLength1D element: Keff couples it to free dofs (CentralDifference.cpp:198), not supported"); return 1; }
+            if (!by_dof.emplace(q, &sm).second) { set_error("support motion: one entry per dof"); return 1; }
+        }
+        std::vector<int32_t> dof, ptr(1, 0);
+        std::vector<double> series, fac;
+        for (auto &kv : by_dof) {
+            dof.push_back(kv.first); fac.push_back(kv.second->factor);
+            series.insert(series.end(), kv.second->series.begin(), kv.second->series.end());
+            ptr.push_back((int32_t)series.size());
+        }
+        m->sup.n = (int)dof.size();
+        m->sup.d_dof = dupload(m, dof); m->sup.d_ptr = dupload(m, ptr);
+        m->sup.d_series = dupload(m, series); m->sup.d_fac = dupload(m, fac);
+    }
+
     // ---- G. recorders -------------------------------------------------------------------
     int maxw = 1;
     for (Recorder &r : m->recorders) {
         std::vector<int32_t> dofs;
         for (int node : r.nodes) for (int c = 0; c < m->node_ndof[node]; c++) dofs.push_back(m->node_ptr[node] + c);
+        if (r.field == SVLGPU_REACTION) {
+            if (m->opt_integrator == 1) { set_error("REACTION recorders are implemented for CentralDifference only"); return 1; }
+            if (has_pml || plan_pml_block) { set_error("REACTION recorders are not implemented for models with PML elements"); return 1; }
+            m->has_reaction_rec = true;
+            // dashpot couplings of the recorded dofs: C_e = eta a a^T, a = -1 / +1 on the two ends (ZeroLength1D.cpp:212-231)
+            std::map<int32_t, std::vector<std::pair<int32_t, double>>> off;
+            std::map<int32_t, double> dg;
+            for (int e = 0; e < nE; e++) {
+                if (m->elem_kind[e] != SVLGPU_ZEROLENGTH1D) continue;
+                const int dir = (int)m->attr(e, 0);
+                const double eta = m->materials[m->elem_mat[e]].p[0];
+                const int qi = m->node_ptr[m->elem_conn[8ll * e]] + dir, qj = m->node_ptr[m->elem_conn[8ll * e + 1]] + dir;
+                off[qi].push_back({qj, -eta}); off[qj].push_back({qi, -eta});
+                if (m->freedof[qi] == -1) dg[qi] += eta;        // the free end's eta already sits in the damping diagonal
+                if (m->freedof[qj] == -1) dg[qj] += eta;
+            }
+            r.h_dofs = dofs; r.h_cptr.assign(1, 0);
+            for (int node : r.nodes) {
+                bool fixed = false;                             // Node::IsFixed: any restrained dof (Driver.hpp:338-341)
+                for (int q = m->node_ptr[node]; q < m->node_ptr[node + 1]; q++) fixed = fixed || m->freedof[q] == -1;
+                for (int q = m->node_ptr[node]; q < m->node_ptr[node + 1]; q++) {
+                    r.h_fixed.push_back(fixed ? 1 : 0);
+                    r.h_cdg.push_back(dg.count(q) ? dg[q] : 0.0);
+                    auto it = off.find(q);
+                    if (it != off.end()) for (auto &oc : it->second) { r.h_cdof.push_back(oc.first); r.h_ccoef.push_back(oc.second); }
+                    r.h_cptr.push_back((int32_t)r.h_cdof.size());
+                }
+            }
+        }
         r.width = (int)dofs.size(); r.rows = 0;
         r.d_dofs = dupload(m, dofs);
         r.d_rows = dalloc<double>(m, (size_t)r.width * std::max(1, r.max_rows));

@@ -61,7 +61,7 @@ struct Element {         // 04-Elements/Element.hpp:51-249
     unsigned tag; int index; int kind; std::vector<unsigned> conn; unsigned material; std::vector<double> attr;
 };
 struct Load {            // 05-Loads/Load.cpp
-    unsigned tag; bool drm = false;
+    unsigned tag; bool drm = false, support = false;      // support: POINTLOAD_SUPPORT_MOTION (Driver.hpp:1725-1735)
     std::vector<unsigned> nodes, elements;
     std::vector<double> dir, series;
     std::string drm_pattern;
@@ -83,6 +83,7 @@ class Mesh {             // 06-Mesh/Mesh.cpp
     std::map<long, std::tuple<int, std::vector<int>, std::vector<double>>> Constraints;   // tag -> slave total, master free, factor
     std::map<unsigned, std::vector<double>> Masses;
     std::map<unsigned, std::pair<double, double>> Rayleigh;                               // element tag -> (am, ak)
+    std::map<unsigned, std::vector<std::pair<int, std::vector<double>>>> Supports;         // node tag -> (dof, Xo) (Driver.hpp:509-563)
 };
 
 // ---- Driver (12-Utilities/Driver.hpp UpdateMesh :1981-2046) ------------------------------------------------------------
@@ -241,8 +242,27 @@ bool UpdateMesh(Mesh &mesh, const JValue &J, const std::string &dir, bool geomet
             l.drm = true;
             for (auto &x : a["list"].arr) l.elements.push_back((unsigned)x.as_int());
             l.drm_pattern = a["file"].as_string();
+        } else if (ieq(name, "SUPPORTMOTION")) {
+            l.support = true;
+            for (auto &x : a["list"].arr) l.nodes.push_back((unsigned)x.as_int());
         } else { std::cout << "\x1B[31m ERROR: \x1B[0mload " << name << " is not on the GPU explicit path\n"; return true; }
         mesh.Loads[l.tag] = l;
+    }
+    if (J.has("Supports"))
+    for (auto &kv : by_tag(J["Supports"])) {                       // UpdateSupportMotion, Driver.hpp:509-563
+        const JValue &S = *kv.second;
+        const bool constant = ieq(S["type"].as_string(), "CONSTANT");
+        for (size_t n = 0; n < S["dof"].arr.size(); n++) {
+            std::vector<double> xo;
+            if (constant) xo = {S["value"].arr[n].as_double()};
+            else {
+                std::ifstream f(S["file"].arr[n].as_string());
+                unsigned nt = 0;
+                if (f.is_open()) { f >> nt; xo.resize(nt); for (unsigned j = 0; j < nt; j++) f >> xo[j]; }
+                if (xo.empty()) { std::cout << "\x1B[31m ERROR: \x1B[0mcannot read support motion file " << S["file"].arr[n].as_string() << "\n"; return true; }
+            }
+            mesh.Supports[(unsigned)kv.first].push_back({S["dof"].arr[n].as_int(), xo});
+        }
     }
     return false;
 }
@@ -471,7 +491,14 @@ class CentralDifference {
         for (size_t q = 0; q < combo.loads.size(); q++) {
             const Load &l = mesh.Loads.at(combo.loads[q]);
             const double factor = q < combo.factors.size() ? combo.factors[q] : 1.0;
-            if (!l.drm) {
+            if (l.support) {                                       // Assembler::ComputeSupportMotionIncrement, Assembler.cpp:493-533
+                for (unsigned n : l.nodes) {
+                    auto it = mesh.Supports.find(n);
+                    if (it == mesh.Supports.end() || !mesh.Nodes.count(n)) continue;
+                    for (auto &ds : it->second)
+                        if (svlgpu_add_support_motion(h, mesh.Nodes.at(n).index, ds.first, (int)ds.second.size(), ds.second.data(), factor)) return fail();
+                }
+            } else if (!l.drm) {
                 std::vector<int32_t> nodes;
                 for (unsigned n : l.nodes) nodes.push_back(mesh.Nodes.at(n).index);
                 std::vector<double> dir = l.dir;
@@ -482,7 +509,7 @@ class CentralDifference {
         for (auto &r : recs) {
             std::vector<int32_t> nodes;
             for (unsigned id : r.ids) nodes.push_back(mesh.Nodes.at(id).index);
-            const int field = ieq(r.resp, "DISP") ? SVLGPU_DISP : ieq(r.resp, "VEL") ? SVLGPU_VEL : SVLGPU_ACCEL;
+            const int field = ieq(r.resp, "DISP") ? SVLGPU_DISP : ieq(r.resp, "VEL") ? SVLGPU_VEL : ieq(r.resp, "REACTION") ? SVLGPU_REACTION : SVLGPU_ACCEL;
             if (svlgpu_add_node_recorder(h, field, (int)nodes.size(), nodes.data(), nt) < 0) return fail();
         }
         if (newmark && svlgpu_set_option(h, "integrator", 1.0)) return fail();
@@ -781,7 +808,6 @@ int main(int argc, char **argv) {
                     if (solid) { especs.push_back(r); continue; }
                 }
                 if (!ieq(r.name, "NODE")) { std::cout << " WARNING: recorder " << r.name << " (" << r.resp << ") is not written by the GPU path\n"; continue; }
-                if (ieq(r.resp, "REACTION")) { std::cout << " WARNING: REACTION recorder skipped\n"; continue; }
                 r.precision = (*kv.second)["ndps"].as_int(6);
                 r.nsample = (*kv.second)["nsamp"].as_int(1);
                 for (auto &x : (*kv.second)["list"].arr) r.ids.push_back((unsigned)x.as_int());

@@ -78,6 +78,9 @@ class Model:
     dt: float = 0.0
     nt: int = 0
     rec_nodes: np.ndarray = None
+    # support motions: (node index, local dof, series Xo, combination factor of the SUPPORTMOTION load that lists the node)
+    # -- Driver.hpp:509-563 + :1725-1735, Assembler.cpp:493-533
+    supports: List[tuple] = field(default_factory=list)
 
     # ---- derived numbering (PlainScheme) -------------------------------------
     def number_dofs(self):
@@ -410,6 +413,30 @@ def write_reference_json(m: Model, directory: str, name: str = "Model", combo: s
             "file": os.path.join(drmdir, f"{name}-{tag}.$.drm"),
             "list": [int(v) + 1 for v in d.elems]}}
         factors.append(float(d.factor))
+    if m.supports:
+        # Supports{node tag: {type, file | value, dof (0-based)}} + one SUPPORTMOTION load per distinct factor
+        by_node: Dict[int, list] = {}
+        for node, dof, series, fac in m.supports:
+            by_node.setdefault(int(node), []).append((int(dof), np.asarray(series, float), float(fac)))
+        J["Supports"] = {}
+        for node, lst in sorted(by_node.items()):
+            if all(len(q[1]) == 1 for q in lst):
+                J["Supports"][str(node + 1)] = {"type": "CONSTANT", "value": [float(q[1][0]) for q in lst], "dof": [q[0] for q in lst]}
+            else:
+                files = []
+                for dof, series, _ in lst:
+                    fn = os.path.join(part, f"{name}_support{node + 1}_{dof}.txt")
+                    with open(fn, "w") as f:
+                        f.write(f"{len(series)}\n" + "\n".join(repr(float(v)) for v in series) + "\n")
+                    files.append(fn)
+                J["Supports"][str(node + 1)] = {"type": "TIMESERIES", "file": files, "dof": [q[0] for q in lst]}
+        for fac in sorted({q[2] for lst in by_node.values() for q in lst}):
+            tag += 1
+            nodes = sorted(n for n, lst in by_node.items() if any(q[2] == fac for q in lst))
+            if any(q[2] != fac for n in nodes for q in by_node[n]):
+                raise ValueError("write_reference_json: one combination factor per support node")
+            J["Loads"][str(tag)] = {"name": "SUPPORTMOTION", "attributes": {"list": [n + 1 for n in nodes]}}
+            factors.append(float(fac))
     J["Combinations"] = {"1": {"name": combo, "attributes": {
         "folder": combo, "load": list(range(1, tag + 1)), "factor": factors}}}
     J["Recorders"] = {}
@@ -804,6 +831,21 @@ def read_reference_json(path: str, base_dir: Optional[str] = None) -> Model:
                 ext.append(1 if cond else 0)
             m.drm = DRMLoad(elems=elems, nodes=np.array([nidx[t] for t in tags], dtype=np.int32), exterior=np.array(ext, dtype=np.uint8),
                             field=np.stack(fields), factor=float(factor))
+            continue
+        if L["name"].upper() == "SUPPORTMOTION":
+            # Driver.hpp:1725-1735 + :509-563: the load lists nodes, their motions sit in Supports{node tag}
+            for ntag in a["list"]:
+                S = J.get("Supports", {}).get(str(int(ntag)))
+                if S is None:
+                    continue
+                for q, dof in enumerate(S["dof"]):
+                    if S["type"].upper() == "CONSTANT":
+                        series = np.array([float(S["value"][q])])
+                    else:
+                        fn = S["file"][q] if os.path.isabs(S["file"][q]) else os.path.join(base, S["file"][q])
+                        tok = open(fn).read().split()
+                        series = np.array([float(v) for v in tok[1:1 + int(tok[0])]])
+                    m.supports.append((nidx[int(ntag)], int(dof), series, float(factor)))
             continue
         if L["name"].upper() != "POINTLOAD" or a["type"].upper() != "CONCENTRATED":
             raise ValueError("read_reference_json: only CONCENTRATED point loads and GENERALWAVE element loads are handled by this reader")

@@ -192,6 +192,8 @@ def split_model(m: Model, epart: np.ndarray, nparts: int, tie_closure: str = "bo
         s.elem_am = m.elem_am[el] if m.elem_am is not None else None
         s.elem_ak = m.elem_ak[el] if m.elem_ak is not None else None
         s.masses = [(int(loc[n]), v) for n, v in m.masses if owner[n] == r]
+        # a moving support moves on every replica of its node (it is a prescribed displacement, not a force to be summed)
+        s.supports = [(int(loc[n]), d, sr, fc) for n, d, sr, fc in (getattr(m, "supports", None) or []) if loc[n] >= 0]
         s.point_loads = []
         for pl in m.point_loads:
             keep = [int(loc[n]) for n in pl.nodes if owner[n] == r]

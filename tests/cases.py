@@ -141,10 +141,72 @@ def c1_column20():
     return M.make_box_model((n, n, n), 1.0, mat=(M.ELASTIC3DLINEAR, SOIL), nt=81, rec_nodes=top[:13] + axis)
 
 
+# ---- reactions and support motion (a7) ---------------------------------------------------
+def reaction_box():
+    """Bottom-fixed layered box with mass-proportional Rayleigh damping, point masses (one on a FIXED node: its inertia force
+    enters the reaction, Assembler.cpp:568-590) and a point load that also acts on a fixed node (Fext is subtracted from the
+    reaction, CentralDifference.cpp:168).  Recorded: base corner / edge / interior nodes and two free nodes (zero rows)."""
+    m = hex8_layered_rayleigh()
+    m.masses = [(7, [300.0, 200.0, 100.0]), (70, [150.0, 150.0, 150.0])]
+    pl = m.point_loads[0]
+    m.point_loads.append(M.PointLoad(np.array([6, 27], dtype=np.int32), np.array([5e2, -3e2, 2e3]), 0.5 * pl.series, 1.5))
+    m.rec_nodes = np.array([0, 2, 7, 12, 19, 27, 70], dtype=np.int32)
+    return m
+
+
+def reaction_area():
+    m = M.make_area_model((8, 6), 0.5, th=0.8, nt=70, rec_nodes=[0, 4, 8, 12, 40])
+    m.elem_am = np.full(m.n_elem, 0.6); m.elem_ak = np.zeros(m.n_elem)
+    return m
+
+
+def _pulse(nt, dt, amp, f0):
+    t = np.arange(nt) * dt
+    return amp * np.sin(2 * np.pi * f0 * t) * np.exp(-((t - 0.5 * nt * dt) / (0.25 * nt * dt)) ** 2)
+
+
+def support_column():
+    """Soil column shaken through its fixed base: TIMESERIES support motion on every base node in x (factor 1.25 from the
+    combination), in z on the same nodes with another history, one CONSTANT entry (which the dynamic loop never applies:
+    Node.cpp:236-243 with k >= 1) -- plus a point load at the top.  Reference semantics reproduced: the support increment
+    reaches the elements one step late."""
+    m = M.make_box_model((3, 3, 6), 1.0, nt=90, load_dir=(4e2, -2e2, 1e3), rec_nodes=[0, 5, 15, 53, 111])
+    gx = _pulse(m.nt, m.dt, 2e-3, 1.0 / (30 * m.dt)); gz = _pulse(m.nt, m.dt, -1e-3, 1.0 / (22 * m.dt))
+    for n in range(16):
+        m.supports.append((n, 0, gx, 1.25))
+        m.supports.append((n, 2, gz, 1.25))
+    m.supports.append((3, 1, np.array([5e-4]), 1.25))
+    return m
+
+
+def support_area():
+    m = M.make_area_model((6, 5), 0.5, th=0.8, nt=90, load_dir=(3e2, 1e3), rec_nodes=[0, 3, 6, 20, 41])
+    m.elem_am = np.full(m.n_elem, 0.4); m.elem_ak = np.zeros(m.n_elem)
+    g = _pulse(m.nt, m.dt, 1e-3, 1.0 / (25 * m.dt))
+    for n in range(7):
+        m.supports.append((n, 0, g, 1.0))
+    for n in (0, 6):
+        m.supports.append((n, 1, 0.5 * g[::-1].copy(), 1.0))
+    return m
+
+
+def reaction_lysmer():
+    """lysmer_column with the fixed dashpot twins recorded: their reaction is the force the Lysmer base absorbs
+    (ZeroLength1D::ComputeInternalDynamicForces, ZeroLength1D.cpp:257-277)."""
+    m = lysmer_column()
+    ns = 4 * 4 * 7
+    m.rec_nodes = np.array([0, 5, ns, ns + 5, ns + 15], dtype=np.int32)
+    return m
+
+
+# cases whose goldens also hold `reaction` (and vel / accel where the support moves): tests/golden/make_golden.py
+REACTION_CASES = ("reaction_box", "reaction_area", "support_column", "support_area", "reaction_lysmer")
+
 CASES = {f.__name__: f for f in (c1_column20, kat444, kat444_masses, hex8_distorted, hex8_layered_rayleigh, quad4_area, quad4_distorted,
                                  j2_column, drm_box, drm_area, pml2d, pml3d, lysmer_column, lysmer_area, j2ps_area)}
 # tolerance of |oracle - reference| and |device - oracle| per case (max_t|d| / max_t|ref| per dof)
-TOL = {name: 1e-10 for name in CASES}
+REACTION_CASE_FUNCS = {f.__name__: f for f in (reaction_box, reaction_area, support_column, support_area, reaction_lysmer)}
+TOL = {name: 1e-10 for name in list(CASES) + list(REACTION_CASE_FUNCS)}
 TOL["j2ps_area"] = 1e-8
 TOL["j2_column"] = 1e-8        # plastic: looser bound (BASELINE.json north_star), stated in DESIGN.md
 TOL["pml2d"] = 1e-9            # PML: Keff is not diagonal -> iterative block solve (rtol 1e-14), see DESIGN.md
@@ -268,6 +330,8 @@ def fingerprint(m) -> str:
         h.update(np.ascontiguousarray(pl.series).tobytes())
     if m.masses:                                   # only models that carry nodal masses (older goldens keep their hash)
         h.update(repr([(int(n), list(map(float, v))) for n, v in m.masses]).encode())
+    for n, d, series, fac in getattr(m, "supports", None) or []:
+        h.update(repr((int(n), int(d), float(fac))).encode()); h.update(np.ascontiguousarray(series, dtype=float).tobytes())
     return h.hexdigest()[:16]
 
 

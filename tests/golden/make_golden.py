@@ -49,6 +49,18 @@ def history_cases(names):
         print(f"{name}: {out['disp'].shape} peak |u| = {np.abs(out['disp']).max():.6e}")
 
 
+def reaction_cases(names):
+    """disp / vel / accel / reaction NODE recorders of the reference executable (Recorder.cpp:246-260) for the reaction and
+    support-motion cases"""
+    for name in names:
+        m = cases.REACTION_CASE_FUNCS[name]()
+        out = run_reference(m, ("disp", "vel", "accel", "reaction"))
+        assert out["disp"].shape[0] == m.nt - 1, (name, out["disp"].shape)
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), fingerprint=cases.fingerprint(m),
+                            rec_nodes=m.rec_nodes, dt=m.dt, nt=m.nt, **out)
+        print(f"{name}: {out['disp'].shape} peak |u| = {np.abs(out['disp']).max():.6e} peak |R| = {np.abs(out['reaction']).max():.6e}")
+
+
 def newmark_cases(names):
     for name in names:
         m = cases.newmark_case(name)
@@ -147,8 +159,12 @@ if __name__ == "__main__":
         extended_newmark_cases()
         newton_cases()
         raise SystemExit(0)
+    if args and args[0] == "reaction":
+        reaction_cases(args[1:] or list(cases.REACTION_CASES))
+        raise SystemExit(0)
     names = args or list(cases.CASES)
     if not args:
+        reaction_cases(list(cases.REACTION_CASES))
         element_kat()
         newmark_cases(list(cases.NEWMARK_CASES))
         extended_newmark_cases()

@@ -26,7 +26,9 @@ NE = {"kat444": (4, 4, 4), "drm_box": (6, 6, 5), "quad4_area": (8, 6), "j2_colum
       "lysmer_column": (3, 3, 6),            # ZeroLength1D dashpots follow the rank of their soil node
       # soil box + PML layer (EQUAL ties, 9- / 5-dof PML nodes on the cuts): split by element centroid; the block solve
       # exchanges the shared unknowns and all-reduces its dot products
-      "pml2d": None, "pml3d": None}
+      "pml2d": None, "pml3d": None,
+      # REACTION recorders on restrained nodes of the cut (partial F_int - F_ext summed over the ranks) and a moving support
+      "reaction_box": (4, 3, 6), "support_column": (3, 3, 6)}
 RUNS = [(name, ne, "CENTRALDIFFERENCE") for name, ne in NE.items()]
 # NewmarkBeta + Linear across ranks (interface sums inside the K operator, all-reduced dot products).  Both the PML and the
 # Newmark cases were first seen green on 2 B200s in profiles/r3a_multigpu_check_pml_newmark_n2.log.
@@ -47,7 +49,8 @@ def main():
             uid.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
         newmark = integrator == "NEWMARK"
-        m = cases.newmark_case(name) if newmark else cases.CASES[name]()
+        reac = name in cases.REACTION_CASE_FUNCS
+        m = cases.newmark_case(name) if newmark else (cases.REACTION_CASE_FUNCS[name]() if reac else cases.CASES[name]())
         if ne is None:
             grid = P.proc_grid(world) if m.ndim == 3 else ((world, 1) if world <= 2 else (2, world // 2))
             subs = P.split_model(m, P.centroid_epart(m, grid), world)
@@ -55,28 +58,31 @@ def main():
             grid = P.proc_grid(world)
             if name == "j2_column" and world <= 6:
                 grid = (1, 1, world)
+            if reac:                                  # cut THROUGH the restrained base so that reactions need the exchange
+                grid = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(world, grid)
         else:
             grid = (1, world) if world <= 2 else (2, world // 2)
         if ne is not None:
             subs = P.split_model(m, P.block_epart(ne, grid), world)
         s = subs[rank]
-        d = capi.DeviceModel(s, device=local, comm=(rank, world, bytes(uid.cpu().numpy())),
+        d = capi.DeviceModel(s, device=local, comm=(rank, world, bytes(uid.cpu().numpy())), fields=(0, 3) if reac else (0,),
                              options={"integrator": 1.0} if newmark else None)
         d.step(1, m.nt, True)
         U = d.get_state(0)
         rec = d.read_recorder(0) if len(s.rec_nodes) else np.zeros((m.nt - 1, 0))
+        recR = d.read_recorder(1) if reac and len(s.rec_nodes) else np.zeros((m.nt - 1, rec.shape[1]))
         nd = m.ndim
         gd = np.concatenate([np.arange(m.node_ptr[n], m.node_ptr[n + 1]) for n in s.global_nodes])    # PML nodes: 9 / 5 dofs
         rec_w = [int(s.node_ndof[n]) for n in s.rec_nodes]
         gathered = [None] * world
-        dist.all_gather_object(gathered, (gd, U, s.rec_global, rec, d.counters(), rec_w))
+        dist.all_gather_object(gathered, (gd, U, s.rec_global, rec, d.counters(), rec_w, recR))
         d.close()
         if rank == 0:
             from oracle_lib import Oracle
             ref, Uref = Oracle().run(m, integrator=integrator)
             Ug = np.full(m.n_total, np.nan)
             spread = 0.0
-            for gd_r, U_r, *_ in gathered:
+            for gd_r, U_r, *_rest in gathered:
                 seen = ~np.isnan(Ug[gd_r])
                 if seen.any():
                     spread = max(spread, np.abs(Ug[gd_r][seen] - U_r[seen]).max())   # replicas must agree bit for bit
@@ -84,12 +90,18 @@ def main():
             err_u = np.abs(Ug - Uref).max() / np.abs(Uref).max()
             # recorder columns back in the global recorder order
             cols = {}
-            for _, _, rg, rc, _, rw in gathered:
+            colsR = {}
+            for _, _, rg, rc, _, rw, rR in gathered:
                 off = np.concatenate([[0], np.cumsum(rw)]).astype(int)
                 for i, n in enumerate(rg):
                     cols[int(n)] = rc[:, off[i]:off[i + 1]]
+                    colsR[int(n)] = rR[:, off[i]:off[i + 1]]
             out = np.concatenate([cols[int(n)] for n in m.rec_nodes], axis=1)
             err_r = cases.rel_err(out, ref)
+            if reac:                                  # reaction rows against the single-domain oracle
+                refR, _ = Oracle().run(m, field=3)
+                outR = np.concatenate([colsR[int(n)] for n in m.rec_nodes], axis=1)
+                err_r = max(err_r, cases.rel_err(outR, refR))
             tol = cases.TOL_NEWMARK if newmark else cases.TOL[name]
             good = err_u < tol and err_r < tol and spread == 0.0
             ok &= good

@@ -49,6 +49,7 @@ class SvloModel(C.Structure):
         ("drm_factor", C.c_double),
         ("dt", C.c_double), ("ftol", C.c_double), ("mtol", C.c_double),
         ("U0", _dp), ("V0", _dp), ("A0", _dp),
+        ("n_sup", C.c_int32), ("sup_dof", _ip), ("sup_ptr", _ip), ("sup_series", _dp), ("sup_factor", _dp),
     ]
 
 
@@ -170,7 +171,7 @@ class Oracle:
         return f
 
     # ---- analysis level ------------------------------------------------------------
-    def pack(self, m, U0=None):
+    def pack(self, m, U0=None, V0=None):
         """svl_b200.model.Model -> (SvloModel, keepalive list)."""
         keep = []
 
@@ -231,14 +232,28 @@ class Oracle:
             e = A(d.exterior, np.uint8)
             s.drm_ext = e.ctypes.data_as(_bp)
             s.drm_field = _d(A(d.field, np.float64)); s.drm_factor = d.factor
+        sup = getattr(m, "supports", None) or []
+        s.n_sup = len(sup)
+        if sup:                                 # (node, dof, series, factor): Model.supports
+            ptr = np.zeros(len(sup) + 1, np.int32)
+            ptr[1:] = np.cumsum([len(q[2]) for q in sup])
+            s.sup_dof = _i(A([m.totaldof[m.node_ptr[q[0]] + q[1]] for q in sup], np.int32))
+            s.sup_ptr = _i(A(ptr, np.int32))
+            s.sup_series = _d(A(np.concatenate([np.asarray(q[2], float) for q in sup]), np.float64))
+            s.sup_factor = _d(A([q[3] for q in sup], np.float64))
         s.dt, s.ftol, s.mtol = m.dt, 1e-12, 1e-12
         if U0 is not None:
             s.U0 = _d(A(U0, np.float64))
+        if V0 is not None:
+            s.V0 = _d(A(V0, np.float64))
         return s, keep
 
-    def run(self, m, nt=None, field=0, rec_dofs=None, nthreads=1, U0=None, integrator="CENTRALDIFFERENCE", newton=None):
-        """newton = (cnvgtol, nstep, cnvgtest) selects NewtonRaphson (NewmarkBeta only); default Linear."""
-        s, keep = self.pack(m, U0)
+    def run(self, m, nt=None, field=0, rec_dofs=None, nthreads=1, U0=None, integrator="CENTRALDIFFERENCE", newton=None, V0=None):
+        """newton = (cnvgtol, nstep, cnvgtest) selects NewtonRaphson (NewmarkBeta only); default Linear.
+        Note: like the reference, the first step's internal force comes from the stresses stored by the
+        previous UpdateState, i.e. it is ZERO whatever U0 is -- the device evaluates F_int(U0).  Parity runs that want every
+        dof excited from the start therefore use an initial VELOCITY field (U0 = 0 keeps both sides identical)."""
+        s, keep = self.pack(m, U0, V0)
         nt = nt or m.nt
         rd = np.ascontiguousarray(m.rec_dofs() if rec_dofs is None else rec_dofs, np.int32)
         out = np.zeros((nt - 1, len(rd)))

@@ -88,14 +88,18 @@ def test_box_block_vs_oracle(oracle, ne):
     assert np.abs(U - Uref).max() / np.abs(Uref).max() < TOL_LINEAR
 
 
-@pytest.mark.parametrize("env", [{"SVLGPU_STENCIL_V": "3"}, {"SVLGPU_NO_SYM": "1"}, {"SVLGPU_STENCIL_R": "6"},
-                                 {"SVLGPU_STENCIL_R": "6", "SVLGPU_STENCIL_KZ": "5"}, {"SVLGPU_STENCIL_KZ": "4"},
-                                 {"SVLGPU_STENCIL_NOBAR": "1"}, {"SVLGPU_STENCIL_NOBAR": "1", "SVLGPU_STENCIL_KZ": "3"},
-                                 {"SVLGPU_STENCIL_KZ": "1"}, {"SVLGPU_STENCIL_KZ": "2"}])
+NS = {"SVLGPU_NO_SEP": "1"}            # the separable kernel is the default for the interior class: switch it off to reach the others
+
+
+@pytest.mark.parametrize("env", [{}, {"SVLGPU_STENCIL_KZ": "4"}, {"SVLGPU_STENCIL_KZ": "1"}, {"SVLGPU_STENCIL_KZ": "2"}, {"SVLGPU_STENCIL_KZ": "5"},
+                                 NS, {**NS, "SVLGPU_STENCIL_V": "3"}, {**NS, "SVLGPU_NO_SYM": "1"}, {**NS, "SVLGPU_STENCIL_R": "6"},
+                                 {**NS, "SVLGPU_STENCIL_R": "6", "SVLGPU_STENCIL_KZ": "5"}, {**NS, "SVLGPU_STENCIL_KZ": "4"},
+                                 {**NS, "SVLGPU_STENCIL_NOBAR": "1"}, {**NS, "SVLGPU_STENCIL_NOBAR": "1", "SVLGPU_STENCIL_KZ": "3"},
+                                 {**NS, "SVLGPU_STENCIL_KZ": "1"}, {**NS, "SVLGPU_STENCIL_KZ": "2"}])
 @pytest.mark.parametrize("ne", [(40, 35, 20), (67, 30, 13)])
 def test_dominant_class_kernel_variants(oracle, monkeypatch, env, ne):
-    """Every variant of the dominant-class block-stencil kernel (TMA v3, barrier-free v4 with / without the
-    symmetric-coefficient table, 4 or 6 rows per thread, short z-chunks) against the oracle."""
+    """Every variant of the dominant-class block-stencil kernel (separable v5 -- the default --, TMA v3, barrier-free v4
+    with / without the symmetric-coefficient table, 4 or 6 rows per thread, short z-chunks) against the oracle."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     nt = 30
@@ -109,6 +113,30 @@ def test_dominant_class_kernel_variants(oracle, monkeypatch, env, ne):
     assert rel_err(out, ref) < TOL_LINEAR
     U = d.get_state(0)
     assert np.abs(U - Uref).max() / np.abs(Uref).max() < TOL_LINEAR
+
+
+@pytest.mark.parametrize("ne,hs", [((37, 35, 21), (0.5, 0.8, 1.25)), ((66, 19, 9), (1.0, 1.0, 0.4))])
+def test_separable_kernel_on_rectangular_cells(oracle, ne, hs):
+    """k_stencil3_sep fits its tensor-product coefficients to the class table, so rectangular (non-cubic) cells and odd
+    lattice dimensions (row-alignment shifts of the TMA copies) go through the same kernel."""
+    nt = 30
+    m = M.make_box_model(ne, min(hs), nt=nt, rec_nodes=None)          # dt from the smallest edge
+    m.coords = m.coords * (np.array(hs) / min(hs))
+    nn = m.n_nodes
+    m.rec_nodes = np.array(sorted({0, nn - 1, nn // 2, nn // 3, m.point_loads[0].nodes[0]}), dtype=np.int32)
+    rng = np.random.default_rng(7)
+    V0 = rng.uniform(-1.0, 1.0, m.n_total)              # every dof moves from the first step on (U0 = 0: SURVEY App. C q2)
+    V0[np.asarray(m.totaldof)[np.asarray(m.freedof_flat) < 0]] = 0.0
+    ref, Uref = oracle.run(m, nthreads=8, V0=V0)
+    d = _device(m, V0=V0)
+    out = d.run()[0]
+    assert d.counters()["n_block_nodes"] == nn
+    assert rel_err(out, ref) < TOL_LINEAR
+    U = d.get_state(0)
+    assert np.abs(U - Uref).max() / np.abs(Uref).max() < TOL_LINEAR
+    F = d.internal_force()                              # force-only mode of the same kernel
+    Fref = oracle.internal_force(m, U)
+    assert np.abs(F - Fref).max() / np.abs(Fref).max() < 1e-11
 
 
 def test_vel_accel_recorders(oracle):
@@ -286,6 +314,47 @@ def test_gauss_point_strain_stress_at_the_current_state(oracle, name):
     assert np.abs(ref).max() > 0
     assert np.abs(eps - ref).max() <= 1e-12 * np.abs(ref).max()
     assert np.abs(sig - ref @ Cm.T).max() <= 1e-12 * np.abs(ref @ Cm.T).max()
+
+
+@pytest.mark.parametrize("name", list(cases.REACTION_CASES))
+def test_reactions_and_support_motion_match_reference_golden(oracle, name):
+    """REACTION recorders (restrained-row reaction pass at recorded steps) and support motion on the device against the
+    recorder files of the unmodified reference executable and against the oracle: disp, vel, accel, reaction."""
+    m = cases.REACTION_CASE_FUNCS[name]()
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"{name}.npz"))
+    assert str(g["fingerprint"]) == cases.fingerprint(m)
+    for hint in (True, False):                           # block-stencil kernels, then the Gauss-point kernels
+        if not hint:
+            m.blocks = []
+        d = _device(m, fields=(0, 1, 2, 3))
+        out = d.run()
+        for f, key in ((0, "disp"), (1, "vel"), (2, "accel"), (3, "reaction")):
+            assert cases.rel_err(out[f], g[key]) < cases.TOL[name], (key, hint, "vs reference")
+            ref, _ = oracle.run(m, field=f)
+            assert cases.rel_err(out[f], ref) < cases.TOL[name], (key, hint, "vs oracle")
+        # the getters report the true support displacement as well (the state buffers hold what the elements see)
+        dofs = np.asarray(m.rec_dofs(), np.int32)
+        for f in (0, 1, 2):
+            assert np.array_equal(d.get_state(f, dofs), out[f][-1]), f
+        d.close()
+
+
+def test_host_driver_writes_reaction_recorders_and_moves_supports(tmp_path):
+    """The C++ host driver reads Supports / SUPPORTMOTION / resp = reaction from the reference's JSON and writes the
+    reference's recorder files; compared with the files of the reference executable (goldens)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "svl_b200", "SeismoVLAB_gpu.exe")
+    for name in ("support_column", "reaction_lysmer"):
+        m = cases.REACTION_CASE_FUNCS[name]()
+        g = np.load(os.path.join(root, "tests", "golden", f"{name}.npz"))
+        work = os.path.join(str(tmp_path), name)
+        part = M.write_reference_json(m, work, "Case", "Run", resp=("disp", "accel", "reaction"), ndps=17)
+        r = subprocess.run([exe, "-dir", part, "-file", "Case.1.$.json"], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        for key in ("disp", "accel", "reaction"):
+            out = M.read_node_recorder(os.path.join(work, "Solution", "Run", f"{key}.0.out"))
+            assert cases.rel_err(out, g[key]) < cases.TOL[name], (name, key)
 
 
 def test_pml_internal_force(oracle):

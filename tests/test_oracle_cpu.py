@@ -38,6 +38,37 @@ def test_oracle_history_matches_reference_executable(oracle, name):
     assert cases.rel_err(out, g["disp"]) < cases.TOL[name]
 
 
+@pytest.mark.parametrize("name", list(cases.REACTION_CASES))
+def test_oracle_reactions_and_support_motion_match_reference_executable(oracle, name):
+    """Integrator::ComputeReactionForce rows (DynamicAnalysis.cpp:130-150, CentralDifference.cpp:155-171) and support motion
+    (Assembler.cpp:493-533, CentralDifference.cpp:135,189-202) against the disp / vel / accel / reaction NODE recorders the
+    unmodified reference executable wrote for the same model."""
+    m = cases.REACTION_CASE_FUNCS[name]()
+    g = gold(name)
+    assert str(g["fingerprint"]) == cases.fingerprint(m), "case generator drifted: regenerate tests/golden"
+    for f, key in ((0, "disp"), (1, "vel"), (2, "accel"), (3, "reaction")):
+        out, _ = oracle.run(m, field=f)
+        assert out.shape == g[key].shape and np.abs(g[key]).max() > 0
+        assert cases.rel_err(out, g[key]) < cases.TOL[name], key
+    if name.startswith("support"):
+        # the support really moves and really shakes the column
+        sup_dofs = {m.node_ptr[n] + d for n, d, sr, _ in m.supports if len(sr) > 1}
+        cols = [i for i, q in enumerate(m.rec_dofs()) if q in sup_dofs]
+        assert cols and np.abs(g["disp"][:, cols]).max() > 1e-4
+
+
+def test_reference_json_round_trip_with_supports_and_reaction_recorder(oracle, tmp_path):
+    from svl_b200 import model as M
+    m = cases.support_column()
+    part = M.write_reference_json(m, str(tmp_path), "Case", "Run", resp=("disp", "reaction"))
+    m2 = M.read_reference_json(os.path.join(part, "Case.1.0.json"))
+    assert len(m2.supports) == len(m.supports) and [r for r, _ in m2.rec_spec] == ["disp", "reaction"]
+    for f in (0, 3):
+        a, _ = oracle.run(m, field=f)
+        b, _ = oracle.run(m2, field=f)
+        assert np.abs(a - b).max() <= 1e-14 * np.abs(a).max()
+
+
 @pytest.mark.parametrize("name", list(cases.NEWMARK_CASES))
 def test_oracle_newmark_history_matches_reference_executable(oracle, name):
     """NewmarkBeta + Linear (10-Integrators/03-Newmark/NewmarkBeta.cpp) at 4x the explicit step: displacement, velocity
