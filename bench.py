@@ -417,9 +417,7 @@ def main():
         d.step(k, k + K, True); k += K
         barrier()
         wall = time.perf_counter() - w0
-        if wall < 0.35 and sample_clocks:             # short timed region (driver default --steps 20): keep the same kernels
-            d.step(k, k + K, True); k += K            # running untimed until nvidia-smi has been polled a few times
-            d.step(k, k + K, True); k += K
+
         ms = allmax(d.counters()["last_step_ms"])
         out = {"m": m, "value": n_elem_total * K / (ms * 1e-3), "ms_per_step": ms / K, "elements": n_elem_total,
                "dof": n_dof_total, "launches": allsum(d.counters()["launches_per_step"] * K), "c": c,
@@ -439,6 +437,14 @@ def main():
                 d.step_host(k, [amp[k]] if amp is not None else [], rec=0, row=row); k += 1
             barrier()
             e2e_s = allmax(time.perf_counter() - e0)
+            if sample_clocks and dist is None:
+                # nvidia-smi answers in ~0.1 s and the timed regions are shorter than that: keep the SAME kernels running
+                # (untimed) until the sampler has seen the GPU under this load a few times
+                t_end = time.perf_counter() + 4.0
+                while len(sampler.samples) < 6 and time.perf_counter() < t_end:
+                    d.step(k, k + 50, True); k += 50
+            elif sample_clocks:                       # several ranks: the same fixed number of extra steps on every rank
+                d.step(k, k + 800, True); k += 800
             sampler.active = False
             if not np.all(np.isfinite(row)):
                 raise SystemExit("non-finite response")

@@ -866,6 +866,18 @@ __global__ void __launch_bounds__(128, LOWREG ? 8 : 6) k_stencil3_shell(const Sh
     __syncthreads();
     int q[kShellNPT], ci[kShellNPT], cj[kShellNPT], ck[kShellNPT];
     double F[kShellNPT][3];
+    // a class whose three dofs are restrained (1 / Keff == 0: e.g. the fixed base of a soil box) keeps its displacement:
+    // the update below would add (..) * 0 to U_n, so the 27-point row is not evaluated at all in the step pass
+    if (p.mode == 0 && !p.hF && T[270] == 0.0 && T[271] == 0.0 && T[272] == 0.0) {
+#pragma unroll
+        for (int n = 0; n < kShellNPT; n++) {
+            const int qq = p.list[(size_t)blockIdx.x * kShellChunk + n * 128 + threadIdx.x];
+            if (qq < 0) continue;
+            const long long d0 = p.dof0 + 3ll * qq;
+            p.Un[d0] = p.U[d0]; p.Un[d0 + 1] = p.U[d0 + 1]; p.Un[d0 + 2] = p.U[d0 + 2];
+        }
+        return;
+    }
 #pragma unroll
     for (int n = 0; n < kShellNPT; n++) {
         q[n] = p.list[(size_t)blockIdx.x * kShellChunk + n * 128 + threadIdx.x];
@@ -1497,6 +1509,60 @@ __global__ void __launch_bounds__(128) k_drm(const DrmArgs a, double *F) {
     }
     F[t] = a.factor * f;
 }
+// Analytic plane wave: u_j(t) = +-amp ricker(t - t0 - s_j / c) pol, so the 3x3 (2x2) block products collapse to one scalar
+// per entry: F_i = factor sum_j (B_ij pol) val_j with the blocks contracted with pol once at plan time.  One thread per
+// DRM node evaluates the wave value; one thread per ROW then needs 3 requests per entry (index pair, scalar, contracted
+// block) for ND products instead of 5 requests for one.  Entries are summed in the same ascending order.
+__global__ void k_drm_field_pw(int nn, const uint8_t *ext, const double *sc, double amp, double f0, double t0, double dt, int k,
+                               const int32_t *kctl, int koff, double *sval) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nn) return;
+    const int kk = kctl ? kctl[0] + koff : k;
+    const double val = amp * ricker_disp(kk * dt - t0 - sc[t], f0);
+    sval[t] = ext[t] ? -val : val;
+}
+template <int ND>
+__global__ void __launch_bounds__(128) k_drm_pw(int n, const int32_t *ptr, const int2 *cb, const double *sval, const double *wdict,
+                                               double factor, double *F) {
+    constexpr int NS = (ND == 3) ? 4 : 2;
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    double f[ND];
+#pragma unroll
+    for (int r = 0; r < ND; r++) f[r] = 0.0;
+    const int q1 = ptr[row + 1];
+    int q = ptr[row];
+    for (; q + 4 <= q1; q += 4) {
+        int2 e[4];
+#pragma unroll
+        for (int z = 0; z < 4; z++) e[z] = cb[q + z];
+        double sv[4];
+        double2 w2[4];
+        double w3[4];
+#pragma unroll
+        for (int z = 0; z < 4; z++) {
+            sv[z] = sval[e[z].x];
+            const double *w = wdict + (long long)e[z].y * NS;
+            w2[z] = *reinterpret_cast<const double2 *>(w);
+            if (ND == 3) w3[z] = w[2];
+        }
+#pragma unroll
+        for (int z = 0; z < 4; z++) {
+            f[0] += w2[z].x * sv[z];
+            f[1] += w2[z].y * sv[z];
+            if (ND == 3) f[2] += w3[z] * sv[z];
+        }
+    }
+    for (; q < q1; q++) {
+        const int2 e = cb[q];
+        const double sv = sval[e.x];
+        const double *w = wdict + (long long)e.y * NS;
+#pragma unroll
+        for (int r = 0; r < ND; r++) f[r] += w[r] * sv;
+    }
+#pragma unroll
+    for (int r = 0; r < ND; r++) F[(long long)row * ND + r] = factor * f[r];
+}
 // phase 0: rows on interface nodes (hF -= F, before the exchange); phase 1: all other rows (U_{n+1} += F / Keff)
 __global__ void k_drm_apply(int n, int nd, int phase, const int32_t *dof0, const int32_t *target, const double *F,
                             const double *kinv, double *Un, double *hF, double sign) {
@@ -1507,7 +1573,7 @@ __global__ void k_drm_apply(int n, int nd, int phase, const int32_t *dof0, const
     if ((phase == 0) != (tg >= 0)) return;
     if (tg >= 0) { hF[tg + r] -= F[t]; return; }
     const int d = dof0[row] + r;
-    Un[d] += sign * (kinv ? kinv[d] : 1.0) * F[t];
+    Un[d] += sign * (kinv ? kinv[t] : 1.0) * F[t];          // kinv: compact per row dof (DrmDev::d_rkinv)
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1966,6 +2032,15 @@ static int drm_compute(svlgpu_model *m, DrmDev &d, int k, cudaStream_t st) {
     a.c = d.c; a.f0 = d.f0; a.t0 = d.t0; a.amp = d.amp; a.factor = d.factor; a.dt = m->dt;
     a.kinv = nullptr; a.Un = nullptr; a.target = nullptr; a.hF = nullptr; a.phase = 0;
     a.kctl = m->graph_capturing ? m->d_kctl + 2 + (k & 1) : nullptr; a.koff = 0;
+    if (d.analytic && d.d_wdict) {
+        k_drm_field_pw<<<(a.nn + 255) / 256, 256, 0, st>>>(a.nn, d.d_ext, d.d_sc, d.amp, d.f0, d.t0, m->dt, k, a.kctl, 0, d.d_sval[k & 1]);
+        if (m->ndim == 3) k_drm_pw<3><<<(a.n + 127) / 128, 128, 0, st>>>(a.n, d.d_row_ptr, (const int2 *)d.d_col_blk, d.d_sval[k & 1], d.d_wdict, d.factor, d.d_F[k & 1]);
+        else k_drm_pw<2><<<(a.n + 127) / 128, 128, 0, st>>>(a.n, d.d_row_ptr, (const int2 *)d.d_col_blk, d.d_sval[k & 1], d.d_wdict, d.factor, d.d_F[k & 1]);
+        d.buf_k[k & 1] = k;
+        m->total_launches += 2;
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     k_drm_field<<<(a.nn + 127) / 128, 128, 0, st>>>(a);
     if (m->ndim == 3) k_drm<3><<<(a.n * 3 + 127) / 128, 128, 0, st>>>(a, d.d_F[k & 1]);
     else k_drm<2><<<(a.n * 2 + 127) / 128, 128, 0, st>>>(a, d.d_F[k & 1]);
@@ -2015,7 +2090,7 @@ static int launch_external(svlgpu_model *m, int k, const double *dev_amp, double
         if (d.buf_k[b] != k) { if (drm_compute(m, d, k, m->stream)) return 1; }        // not precomputed: do it now
         else if (d.ev_valid[b]) cudaStreamWaitEvent(m->stream, d.ev_ready[b], 0);
         k_drm_apply<<<(d.n_nodes * m->ndim + 127) / 128, 128, 0, m->stream>>>(d.n_nodes, m->ndim, phase, d.d_node_dof0,
-                                                                              halo ? d.d_target : nullptr, d.d_F[b], kinv, Un,
+                                                                              halo ? d.d_target : nullptr, d.d_F[b], kinv ? d.d_rkinv : nullptr, Un,
                                                                               m->halo.d_hF, sign);
         timer_end(m, 5);
         m->total_launches++;
@@ -2069,13 +2144,15 @@ static int step_once(svlgpu_model *m, int k, const double *dev_amp) {
     }
     m->step_amp = dev_amp;
     record_rows(m, m->graph_capturing);
-    k_advance<<<1, 1, 0, m->stream>>>(m->d_kctl);
-    m->total_launches++;
+    if (m->use_graph) {                                       // the device-side step counter only serves graph replay
+        k_advance<<<1, 1, 0, m->stream>>>(m->d_kctl);
+        m->total_launches++;
+        m->dev_k = k + 1;
+    }
     // rotate: U_{n-1} <- U_n <- U_{n+1}
     const int old_prev = m->prev;
     m->prev = m->cur; m->cur = m->next; m->next = old_prev;
     m->steps_done++;
-    m->dev_k = k + 1;
     return 0;
 }
 
@@ -2101,7 +2178,7 @@ int run_steps(svlgpu_model *m, int k0, int k1, const double *dev_amp) {
         return 0;
     }
     while (k < k1) {
-        if (m->dev_k != k) {                                  // (re)synchronise the device step control block
+        if (m->use_graph && m->dev_k != k) {                  // (re)synchronise the device step control block
             const int32_t h[2] = {k, m->recorders.empty() ? 0 : m->recorders[0].rows};
             CUDA_OK(cudaMemcpyAsync(m->d_kctl, h, sizeof(h), cudaMemcpyHostToDevice, m->stream));
             CUDA_OK(cudaStreamSynchronize(m->stream));

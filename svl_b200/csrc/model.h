@@ -145,6 +145,11 @@ struct DrmDev {
     bool analytic = false;
     double dir[3], pol[3], xref[3], c = 0, f0 = 0, t0 = 0, amp = 0, factor = 1;
     int32_t *d_target = nullptr;     // per row: first slot in halo.d_hF (interface node) or -1
+    double *d_rkinv = nullptr;       // [n_nodes][ndim] 1 / Keff of the row dofs, compact (k_drm_apply reads it coalesced)
+    // analytic plane wave: blocks pre-contracted with the polarisation, one scalar wave value per DRM node (k_drm_pw)
+    double *d_wdict = nullptr;       // [nblk][4 | 2]  B . pol
+    double *d_sc = nullptr;          // [n_all] (x - xref) . dir / c
+    double *d_sval[2] = {nullptr, nullptr};   // [n_all] +-amp * ricker of step k in buffer k & 1
 };
 
 // Multi-GPU: interface nodes shared with other ranks.  Every rank computes the partial

@@ -977,10 +977,34 @@ int plan_and_upload(svlgpu_model *m) {
         CUDA_OK(cudaEventCreateWithFlags(&dd.ev_ready[0], cudaEventDisableTiming));
         CUDA_OK(cudaEventCreateWithFlags(&dd.ev_ready[1], cudaEventDisableTiming));
         dd.analytic = dl.analytic; dd.factor = dl.factor;
+        {
+            std::vector<double> rk(rows.size() * nd);
+            for (size_t i = 0; i < rows.size(); i++) for (int c = 0; c < nd; c++) rk[i * nd + c] = kinv[dof0[i] + c];
+            dd.d_rkinv = dupload(m, rk);
+        }
         if (dl.analytic) {
             std::vector<double> xyz((size_t)nn * nd);
             for (int i = 0; i < nn; i++) for (int c = 0; c < nd; c++) xyz[(size_t)i * nd + c] = m->coords[(size_t)nd * dl.nodes[i] + c];
             dd.d_xyz = dupload(m, xyz);
+            if (!getenv("SVLGPU_DRM_NO_PW")) {
+                // u_j = +-amp ricker(t - tau_j) pol: contract every unique block with pol once, keep one scalar per node
+                const int NS = (nd == 3) ? 4 : 2;
+                const size_t nblk = dict.size() / (nd * nd);
+                std::vector<double> wd(nblk * NS + 4, 0.0), sc(nn);
+                for (size_t b = 0; b < nblk; b++)
+                    for (int r = 0; r < nd; r++) {
+                        double w = 0.0;
+                        for (int c = 0; c < nd; c++) w += dict[b * nd * nd + r * nd + c] * dl.pol[c];
+                        wd[b * NS + r] = w;
+                    }
+                for (int i = 0; i < nn; i++) {
+                    double sx = 0.0;
+                    for (int c = 0; c < nd; c++) sx += (xyz[(size_t)i * nd + c] - dl.xref[c]) * dl.dir[c];
+                    sc[i] = sx / dl.c;
+                }
+                dd.d_wdict = dupload(m, wd); dd.d_sc = dupload(m, sc);
+                dd.d_sval[0] = dalloc<double>(m, (size_t)nn + 2); dd.d_sval[1] = dalloc<double>(m, (size_t)nn + 2);
+            }
             for (int c = 0; c < 3; c++) { dd.dir[c] = dl.dir[c]; dd.pol[c] = dl.pol[c]; dd.xref[c] = dl.xref[c]; }
             dd.c = dl.c; dd.f0 = dl.f0; dd.t0 = dl.t0; dd.amp = dl.amp;
         } else {
