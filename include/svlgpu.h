@@ -110,7 +110,10 @@ int svlgpu_hint_structured_block(svlgpu_model *m, int node0, int nx, int ny, int
  * linear materials, lumped mass, Rayleigh damping with both coefficients, dashpots (several ranks: interface sums inside
  * the K operator and all-reduced dot products are written but have not run on hardware yet); the sparse
  * factorisation of Keff = K + 4/dt^2 M + 2/dt C is replaced by matrix-free conjugate gradients),
- * "newmark_rtol" (relative residual of that solve, default 1e-13), "pml_collective" (1 on EVERY rank of a
+ * "newmark_rtol" (relative residual of that solve, default 1e-13), "nbr_classes" (1: nodes outside the lattice blocks
+ * whose incident elements are all linear and whose assembled row of K occurs at >= 64 nodes are advanced from pre-summed
+ * row blocks + an explicit neighbour list instead of the Gauss-point kernels + element-force arena; verified numerically,
+ * never trusted; default 1), "pml_collective" (1 on EVERY rank of a
  * partitioned model that has PML elements anywhere, also on ranks without one: the PML block solve exchanges the
  * unknowns on shared nodes and all-reduces its dot products, so all ranks must issue the same collectives;
  * svlgpu_add_halo lists may then contain 9- / 5-dof PML nodes; default 0).          */
@@ -221,6 +224,7 @@ typedef struct svlgpu_counters {
     int64_t n_pml_elements;      /* PML elements (block solve)       */
     int64_t n_pml_unknowns;      /* dofs of the non-diagonal block of Keff         */
     int64_t pml_solves, pml_iterations;   /* Krylov solves / iterations so far (PML block BiCGStab + Newmark CG) */
+    int64_t n_nbr_nodes, n_nbr_classes;   /* non-lattice nodes advanced through pre-summed rows + neighbour lists  */
 } svlgpu_counters;
 int svlgpu_get_counters(svlgpu_model *m, svlgpu_counters *out);
 

@@ -41,7 +41,7 @@ class Counters(C.Structure):
         "n_elements", "n_nodes", "n_total_dofs", "n_block_nodes", "n_generic_nodes", "n_generic_elements",
         "n_elem_classes", "n_node_classes", "launches_per_step", "total_launches", "device_bytes")] + \
         [("last_step_ms", C.c_double), ("stencil_ms", C.c_double)] + \
-        [(n, C.c_int64) for n in ("n_pml_elements", "n_pml_unknowns", "pml_solves", "pml_iterations")]
+        [(n, C.c_int64) for n in ("n_pml_elements", "n_pml_unknowns", "pml_solves", "pml_iterations", "n_nbr_nodes", "n_nbr_classes")]
 
 
 _lib = None

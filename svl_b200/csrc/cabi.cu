@@ -168,6 +168,7 @@ int svlgpu_set_option(svlgpu_model *m, const char *name, double value) {
     const std::string n(name);
     if (n == "lattice_guess") m->opt_lattice_guess = value != 0.0;
     else if (n == "keep_gauss") m->opt_keep_gauss = value != 0.0;
+    else if (n == "nbr_classes") m->opt_nbr_classes = value != 0.0;
     else if (n == "cuda_graph") m->opt_graph = value != 0.0 ? 1 : 0;
     else if (n == "integrator") { REQUIRE(value == 0.0 || value == 1.0, "set_option: integrator must be 0 (CentralDifference) or 1 (NewmarkBeta)"); m->opt_integrator = (int)value; }
     else if (n == "newmark_rtol") { REQUIRE(value > 0.0 && value < 1.0, "set_option: newmark_rtol out of range"); m->nm.rtol = value; }
@@ -429,6 +430,7 @@ int svlgpu_get_counters(svlgpu_model *m, svlgpu_counters *o) {
     o->stencil_ms = m->timers[0].launches ? m->timers[0].total_ms / m->timers[0].launches : 0.0;
     o->n_pml_elements = m->pml.n_elem; o->n_pml_unknowns = m->pml.nc;
     o->pml_solves = m->pml.solves + m->nm.solves; o->pml_iterations = m->pml.total_iters + m->nm.total_iters;
+    o->n_nbr_nodes = m->nbr.n_nodes; o->n_nbr_classes = m->nbr.n_cls;
     return 0;
 }
 

@@ -1376,6 +1376,73 @@ __global__ void __launch_bounds__(256) k_gen_nodes(const GNodeArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Non-lattice nodes with a repeating row of K (planner section D2): pre-summed row blocks per node class + explicit
+// neighbour list per node.  One CTA = one chunk of kNbrChunk nodes of ONE class: the class table is staged in shared
+// memory, every thread advances kNbrNPT nodes (one coefficient load per kNbrNPT DFMAs), the neighbour indices of a slot
+// are stored slot-major so that a warp reads them coalesced; displacements come through L1 / L2.  243 DFMA per hex8
+// node instead of ~2 800 in the Gauss-point kernels, and no element-force arena (192 B written + read per element).
+// ------------------------------------------------------------------------------------------
+struct NbrArgs {
+    const double *U, *Up;
+    double *Un;
+    const double *tbl;
+    const int32_t *cls_nn, *chunk_cls, *dof0, *nbr;
+    const long long *chunk_off;
+    int stride, mode;
+};
+template <int ND>
+__global__ void __launch_bounds__(128, 6) k_nbr_nodes(const NbrArgs p) {
+    __shared__ double T[kNbrSlots * ND * ND + 2 * ND];
+    const int c = p.chunk_cls[blockIdx.x];
+    const int nn = p.cls_nn[c];
+    {
+        const double *Tg = p.tbl + (size_t)c * p.stride;
+        for (int i = threadIdx.x; i < nn * ND * ND; i += 128) T[i] = Tg[i];
+        if (threadIdx.x < 2 * ND) T[kNbrSlots * ND * ND + threadIdx.x] = Tg[kNbrSlots * ND * ND + threadIdx.x];
+    }
+    __syncthreads();
+    int d0[kNbrNPT];
+    double F[kNbrNPT][ND];
+#pragma unroll
+    for (int n = 0; n < kNbrNPT; n++) {
+        d0[n] = p.dof0[(size_t)blockIdx.x * kNbrChunk + n * 128 + threadIdx.x];
+#pragma unroll
+        for (int a = 0; a < ND; a++) F[n][a] = 0.0;
+    }
+    const int32_t *nb = p.nbr + p.chunk_off[blockIdx.x] + threadIdx.x;
+    for (int s = 0; s < nn; s++) {
+        int idx[kNbrNPT];
+#pragma unroll
+        for (int n = 0; n < kNbrNPT; n++) idx[n] = nb[(size_t)s * kNbrChunk + n * 128];
+#pragma unroll
+        for (int b = 0; b < ND; b++) {
+            double cf[ND];
+#pragma unroll
+            for (int a = 0; a < ND; a++) cf[a] = T[(s * ND + b) * ND + a];
+#pragma unroll
+            for (int n = 0; n < kNbrNPT; n++) {
+                const double ub = idx[n] >= 0 ? p.U[idx[n] + b] : 0.0;
+#pragma unroll
+                for (int a = 0; a < ND; a++) F[n][a] = fma(cf[a], ub, F[n][a]);
+            }
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < kNbrNPT; n++) {
+        if (d0[n] < 0) continue;
+#pragma unroll
+        for (int a = 0; a < ND; a++) {
+            if (p.mode == 0) {
+                const double un = p.U[d0[n] + a];
+                p.Un[d0[n] + a] = un + (T[kNbrSlots * ND * ND + ND + a] * (un - p.Up[d0[n] + a]) - F[n][a]) * T[kNbrSlots * ND * ND + a];
+            } else {
+                p.Un[d0[n] + a] = F[n][a];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // nodal loads (Assembler.cpp:316-350 point loads): U_{n+1}[d] += kinv[d] * sum_l coef_l amp_l(k)
 // ------------------------------------------------------------------------------------------
 struct PLArgs {
@@ -1882,6 +1949,17 @@ static int launch_node_update(svlgpu_model *m, const double *U, const double *Up
             timer_end(m, 0);
             m->total_launches++;
         }
+    }
+    if (m->nbr.n_chunks) {
+        NbrArgs a;
+        a.U = U; a.Up = Up; a.Un = Un; a.tbl = m->nbr.d_tbl; a.cls_nn = m->nbr.d_cls_nn; a.chunk_cls = m->nbr.d_chunk_cls;
+        a.dof0 = m->nbr.d_dof0; a.nbr = m->nbr.d_nbr; a.chunk_off = (const long long *)m->nbr.d_chunk_off;
+        a.stride = m->nbr.stride; a.mode = mode;
+        timer_begin(m, 2);
+        if (m->ndim == 3) k_nbr_nodes<3><<<m->nbr.n_chunks, 128, 0, m->stream>>>(a);
+        else k_nbr_nodes<2><<<m->nbr.n_chunks, 128, 0, m->stream>>>(a);
+        timer_end(m, 2);
+        m->total_launches++;
     }
     if (m->n_gnodes) {
         GNodeArgs a;

@@ -127,6 +127,21 @@ struct GenericSet {                  // Gauss-point path: elements of one kind
     bool has_j2 = false;
 };
 
+// Non-lattice nodes whose incident elements are all linear and whose assembled row of K repeats across the mesh
+// ("neighbour-list node classes", k_nbr_nodes): pre-summed row blocks per class + an explicit neighbour list per node.
+constexpr int kNbrSlots = 32;        // neighbour nodes per row, the node itself included (27 in a regular hex8 mesh)
+constexpr int kNbrNPT = 2;           // nodes per thread
+constexpr int kNbrChunk = 128 * kNbrNPT;
+struct NbrDev {
+    int n_nodes = 0, n_chunks = 0, n_cls = 0, stride = 0;   // stride: doubles per class table
+    double *d_tbl = nullptr;         // [n_cls][kNbrSlots * nd * nd + 2 * nd]: blocks [slot][b][a], then 1/Keff, Kminus
+    int32_t *d_cls_nn = nullptr;     // [n_cls] slots in use
+    int32_t *d_chunk_cls = nullptr;  // [n_chunks]
+    int64_t *d_chunk_off = nullptr;  // [n_chunks] start of the chunk's neighbour lists in d_nbr
+    int32_t *d_dof0 = nullptr;       // [n_chunks][kNbrChunk] internal dof0 of the node, -1 = padding
+    int32_t *d_nbr = nullptr;        // per chunk [nn][kNbrChunk]: internal dof0 of the neighbour in each slot (slot-major: coalesced)
+};
+
 struct DrmDev {
     int n_nodes = 0, n_all = 0, nt = 0, nf = 0;   // rows with entries / all DRM nodes
     int32_t *d_node_dof0 = nullptr;  // internal dof0 of each row node
@@ -348,6 +363,8 @@ struct svlgpu_model {
     std::vector<int32_t> if_of_node;                // node -> interface index or -1 (host, plan time)
     int32_t *d_pl_target = nullptr;                 // per loaded dof: slot in halo.d_hF, -2-c for PML unknown c, or -1
     svl::PmlDev pml;
+    svl::NbrDev nbr;
+    bool opt_nbr_classes = true;
 
     // counters / timing
     int64_t total_launches = 0, launches_per_step = 0;

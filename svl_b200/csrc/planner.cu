@@ -648,6 +648,140 @@ int plan_and_upload(svlgpu_model *m) {
         m->blocks.push_back(b);
     }
 
+    // ---- D2. neighbour-list node classes (non-lattice nodes with a repeating assembled row of K) ---------------------------
+    // The lattice stencil needs the Builder.py node numbering.  Outside it -- unstructured numbering, several blocks,
+    // multi-material regions meshed with congruent cells -- a node whose incident elements are all linear still has a
+    // constant row of K: the sum of the K_e rows of its incident elements (ascending element id, Assembler.cpp:251).
+    // Nodes are classified by (element class, local index) of each incident element + the pattern in which the element
+    // corners coincide + 1/Keff, Kminus; a class that occurs at >= 64 nodes gets its pre-summed blocks [slot][b][a] and its
+    // nodes an explicit neighbour list (k_nbr_nodes).  Everything else stays on the Gauss-point path.
+    std::vector<uint8_t> node_nbr(nN, 0);
+    if (m->opt_nbr_classes && !getenv("SVLGPU_NO_NBR") && !(m->opt_keep_gauss || getenv("SVLGPU_KEEP_GAUSS"))) {
+        std::vector<int32_t> iptr(nN + 1, 0);
+        for (int e = 0; e < nE; e++) {
+            if (elem_cls[e] < 0) continue;
+            for (int l = 0; l < kind_npe(m->elem_kind[e]); l++) iptr[m->elem_conn[8ll * e + l] + 1]++;
+        }
+        for (int n = 0; n < nN; n++) iptr[n + 1] += iptr[n];
+        std::vector<int32_t> ie(iptr[nN]), il(iptr[nN]), fill(iptr.begin(), iptr.end() - 1);
+        for (int e = 0; e < nE; e++) {
+            if (elem_cls[e] < 0) continue;
+            for (int l = 0; l < kind_npe(m->elem_kind[e]); l++) { const int n = m->elem_conn[8ll * e + l]; ie[fill[n]] = e; il[fill[n]] = l; fill[n]++; }
+        }
+        struct NClass { std::vector<int64_t> key; int rep; long long pop; };
+        std::vector<NClass> ncl;
+        std::unordered_map<uint64_t, std::vector<int>> table;
+        std::vector<int32_t> ncls_of(nN, -1), nb_ptr(1, 0), nb_node;     // neighbour nodes of every classified node, slot order
+        std::vector<int32_t> cand;
+        std::vector<int64_t> key;
+        std::vector<int32_t> slots;
+        for (int n = 0; n < nN; n++) {
+            if (node_done[n] || node_is_pml[n] || is_if[n] || m->node_ndof[n] != nd || iptr[n + 1] == iptr[n]) continue;
+            bool ok = true;
+            for (int q = iptr[n]; q < iptr[n + 1] && ok; q++) ok = classes[elem_cls[ie[q]]].linear;
+            if (!ok) continue;
+            key.clear(); slots.clear();
+            slots.push_back(n);                               // slot 0: the node itself
+            for (int q = iptr[n]; q < iptr[n + 1] && ok; q++) {
+                const int e = ie[q];
+                key.push_back(elem_cls[e]); key.push_back(il[q]);
+                for (int j = 0; j < kind_npe(m->elem_kind[e]); j++) {
+                    const int nb = m->elem_conn[8ll * e + j];
+                    if (m->node_ndof[nb] < nd) { ok = false; break; }
+                    int sidx = -1;
+                    for (size_t z = 0; z < slots.size(); z++) if (slots[z] == nb) { sidx = (int)z; break; }
+                    if (sidx < 0) { sidx = (int)slots.size(); slots.push_back(nb); }
+                    key.push_back(sidx);
+                }
+            }
+            if (!ok || (int)slots.size() > kNbrSlots) continue;
+            for (int c = 0; c < nd; c++) {
+                int64_t b; std::memcpy(&b, &kinv[m->node_ptr[n] + c], 8); key.push_back(b);
+                std::memcpy(&b, &km[m->node_ptr[n] + c], 8); key.push_back(b);
+            }
+            uint64_t hsh = 0x51ed270b;
+            for (int64_t v : key) hsh = mix(hsh, (uint64_t)v);
+            auto &bucket = table[hsh];
+            int found = -1;
+            for (int c : bucket) if (ncl[c].key == key) { found = c; break; }
+            if (found < 0) { found = (int)ncl.size(); bucket.push_back(found); ncl.push_back({key, n, 0}); }
+            ncl[found].pop++;
+            ncls_of[n] = found;
+            cand.push_back(n);
+            nb_node.insert(nb_node.end(), slots.begin(), slots.end());
+            nb_ptr.push_back((int32_t)nb_node.size());
+        }
+        // keep the classes that fill at least a quarter of a chunk
+        std::vector<int32_t> newid(ncl.size(), -1);
+        int nkeep = 0;
+        for (size_t c = 0; c < ncl.size(); c++) if (ncl[c].pop >= kNbrChunk / 4) newid[c] = nkeep++;
+        if (nkeep > 0) {
+            NbrDev &N = m->nbr;
+            N.n_cls = nkeep; N.stride = kNbrSlots * nd * nd + 2 * nd;
+            std::vector<double> tbl((size_t)nkeep * N.stride, 0.0);
+            std::vector<int32_t> cls_nn(nkeep, 0);
+            std::vector<int32_t> cpos(cand.size());                 // position of each candidate in nb_ptr
+            for (size_t i = 0; i < cand.size(); i++) cpos[i] = (int32_t)i;
+            std::unordered_map<int32_t, int32_t> pos_of;
+            for (size_t i = 0; i < cand.size(); i++) pos_of[cand[i]] = (int32_t)i;
+            for (size_t c = 0; c < ncl.size(); c++) {
+                if (newid[c] < 0) continue;
+                const int n = ncl[c].rep;
+                const int32_t i = pos_of[n];
+                const int32_t *sl = &nb_node[nb_ptr[i]];
+                const int nn = nb_ptr[i + 1] - nb_ptr[i];
+                double *T = &tbl[(size_t)newid[c] * N.stride];
+                cls_nn[newid[c]] = nn;
+                for (int q = iptr[n]; q < iptr[n + 1]; q++) {        // ascending element id
+                    const int e = ie[q], l = il[q];
+                    const ElemClass &ec = classes[elem_cls[e]];
+                    const int npe = kind_npe(ec.kind), ned = npe * nd;
+                    for (int j = 0; j < npe; j++) {
+                        const int nb = m->elem_conn[8ll * e + j];
+                        int sidx = 0;
+                        while (sl[sidx] != nb) sidx++;
+                        for (int a = 0; a < nd; a++)
+                            for (int b = 0; b < nd; b++) T[(sidx * nd + b) * nd + a] += ec.Ke[(size_t)(nd * l + a) * ned + nd * j + b];
+                    }
+                }
+                for (int cc = 0; cc < nd; cc++) {
+                    T[kNbrSlots * nd * nd + cc] = kinv[m->node_ptr[n] + cc];
+                    T[kNbrSlots * nd * nd + nd + cc] = km[m->node_ptr[n] + cc];
+                }
+                (void)nn;
+            }
+            // nodes sorted by class (stable: ascending node id inside a class), cut into one-class chunks
+            std::vector<int32_t> order;
+            for (size_t i = 0; i < cand.size(); i++) if (newid[ncls_of[cand[i]]] >= 0) order.push_back((int32_t)i);
+            std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return newid[ncls_of[cand[a]]] < newid[ncls_of[cand[b]]]; });
+            std::vector<int32_t> chunk_cls, dof0v, nbrv;
+            std::vector<int64_t> chunk_off;
+            size_t z = 0;
+            while (z < order.size()) {
+                const int c = newid[ncls_of[cand[order[z]]]];
+                size_t z1 = z;
+                while (z1 < order.size() && z1 - z < (size_t)kNbrChunk && newid[ncls_of[cand[order[z1]]]] == c) z1++;
+                const int nn = cls_nn[c];
+                chunk_cls.push_back(c); chunk_off.push_back((int64_t)nbrv.size());
+                const size_t base = nbrv.size(), dbase = dof0v.size();
+                nbrv.resize(base + (size_t)nn * kNbrChunk, -1);
+                dof0v.resize(dbase + kNbrChunk, -1);
+                for (size_t y = z; y < z1; y++) {
+                    const int32_t i = order[y];
+                    const int n = cand[i];
+                    dof0v[dbase + (y - z)] = m->node_ptr[n];
+                    for (int sidx = 0; sidx < nn; sidx++) nbrv[base + (size_t)sidx * kNbrChunk + (y - z)] = m->node_ptr[nb_node[nb_ptr[i] + sidx]];
+                    node_nbr[n] = 1;
+                }
+                z = z1;
+            }
+            N.n_nodes = (int)order.size(); N.n_chunks = (int)chunk_cls.size();
+            N.d_tbl = dupload(m, tbl); N.d_cls_nn = dupload(m, cls_nn); N.d_chunk_cls = dupload(m, chunk_cls);
+            N.d_chunk_off = dupload(m, chunk_off); N.d_dof0 = dupload(m, dof0v); N.d_nbr = dupload(m, nbrv);
+            if (!N.d_tbl || !N.d_nbr || !N.d_dof0) { set_error("out of device memory (neighbour-list node classes)"); return 1; }
+        }
+    }
+
     // ---- E. generic Gauss-point sets + node gather lists -----------------------------------
     std::vector<int32_t> gset_of(nE, -1), gidx(nE, -1);
     {
@@ -658,7 +792,7 @@ int plan_and_upload(svlgpu_model *m) {
             if (elem_cls[e] < 0) continue;
             const int npe = kind_npe(m->elem_kind[e]);
             bool generic = false;
-            for (int l = 0; l < npe && !generic; l++) generic = !node_done[m->elem_conn[8ll * e + l]];
+            for (int l = 0; l < npe && !generic; l++) generic = !node_done[m->elem_conn[8ll * e + l]] && !node_nbr[m->elem_conn[8ll * e + l]];
             if (!generic) continue;
             GenericSet &g = (m->elem_kind[e] == SVLGPU_LIN3DHEXA8) ? gh : gq;
             gidx[e] = (int)g.elems.size();
@@ -744,7 +878,7 @@ int plan_and_upload(svlgpu_model *m) {
         // generic nodes and their incidences in ascending element order
         std::vector<int32_t> dof0, ndofv, ptr;
         for (int n = 0; n < nN; n++)
-            if (!node_done[n] && !node_is_pml[n]) { gn_of[n] = (int)dof0.size(); dof0.push_back(m->node_ptr[n]); ndofv.push_back(m->node_ndof[n]); }
+            if (!node_done[n] && !node_nbr[n] && !node_is_pml[n]) { gn_of[n] = (int)dof0.size(); dof0.push_back(m->node_ptr[n]); ndofv.push_back(m->node_ndof[n]); }
         const int ng = (int)dof0.size();
         ptr.assign(ng + 1, 0);
         for (int e = 0; e < nE; e++) {

@@ -14,6 +14,7 @@ reference executable reads.  Nothing here computes physics.
 """
 from __future__ import annotations
 
+import copy
 import json
 import math
 import os
@@ -310,6 +311,48 @@ def add_base_dashpots(m: Model, vs: float, vp: float, rho: float, h: float, th: 
 # -------------------------------------------------------------------------------
 # reference JSON writer (Core/SeismoVLAB.py:49-298, Outputs.py:29-51)
 # -------------------------------------------------------------------------------
+def shuffle_numbering(m: Model, seed: int = 1, nodes: bool = True, elems: bool = True) -> Model:
+    """The same mesh with node ids and element order permuted at random: what an unstructured mesher hands over.  The
+    lattice hints are dropped (no Builder.py numbering any more).  Models with constraints are not handled."""
+    if m.constraints:
+        raise ValueError("shuffle_numbering: models with constraints are not handled")
+    rng = np.random.default_rng(seed)
+    n, ne = m.n_nodes, m.n_elem
+    new_of_old = rng.permutation(n) if nodes else np.arange(n)
+    old_of_new = np.argsort(new_of_old)
+    eperm = rng.permutation(ne) if elems else np.arange(ne)              # new element q = old element eperm[q]
+    enew_of_old = np.argsort(eperm)
+    s = Model(ndim=m.ndim, lumped=m.lumped)
+    s.coords = m.coords[old_of_new]
+    s.node_ndof = m.node_ndof[old_of_new]
+    fd = np.asarray(m.freedof_flat if hasattr(m, "freedof_flat") else m.freedof)
+    ptr = np.concatenate([[0], np.cumsum(m.node_ndof)])
+    s.freedof = [np.where(fd[ptr[o]:ptr[o + 1]] > -1, 0, fd[ptr[o]:ptr[o + 1]]).astype(np.int32) for o in old_of_new]
+    s.materials = list(m.materials)
+    npe = np.array([ELEM_NODES[int(k)] for k in m.elem_kind])
+    conn = np.zeros_like(m.elem_conn)
+    for q, e in enumerate(eperm):
+        conn[q, :npe[e]] = new_of_old[m.elem_conn[e, :npe[e]]]
+    s.elem_conn = conn
+    s.elem_kind = m.elem_kind[eperm]; s.elem_mat = m.elem_mat[eperm]
+    s.elem_attr = m.elem_attr[eperm] if m.elem_attr is not None else None
+    s.elem_am = m.elem_am[eperm] if m.elem_am is not None else None
+    s.elem_ak = m.elem_ak[eperm] if m.elem_ak is not None else None
+    s.masses = [(int(new_of_old[q]), v) for q, v in m.masses]
+    s.point_loads = [PointLoad(new_of_old[pl.nodes].astype(np.int32), pl.dir.copy(), pl.series.copy(), pl.factor) for pl in m.point_loads]
+    s.supports = [(int(new_of_old[q]), d, sr, fc) for q, d, sr, fc in m.supports]
+    if m.drm is not None:
+        d = m.drm
+        nn = new_of_old[d.nodes]
+        o = np.argsort(nn)                                              # the reference keeps DRM nodes in ascending tag order
+        s.drm = DRMLoad(elems=np.sort(enew_of_old[d.elems]).astype(np.int32), nodes=nn[o].astype(np.int32), exterior=d.exterior[o].copy(),
+                        field=None if d.field is None else d.field[o].copy(), planewave=copy.deepcopy(d.planewave), factor=d.factor)
+    s.dt, s.nt = m.dt, m.nt
+    s.rec_nodes = new_of_old[m.rec_nodes].astype(np.int32) if m.rec_nodes is not None else None
+    s.blocks = []
+    return s.number_dofs()
+
+
 def write_reference_json(m: Model, directory: str, name: str = "Model", combo: str = "Run",
                          resp=("disp",), integrator: str = "CENTRALDIFFERENCE", ndps: int = 16, newton=None,
                          _return_entities: bool = False, binary: bool = False) -> str:

@@ -139,6 +139,39 @@ def test_separable_kernel_on_rectangular_cells(oracle, ne, hs):
     assert np.abs(F - Fref).max() / np.abs(Fref).max() < 1e-11
 
 
+@pytest.mark.parametrize("kind", ["hex8_layers", "hex8", "quad4"])
+def test_unstructured_numbering_uses_neighbour_list_node_classes(oracle, kind):
+    """Random node / element numbering (no lattice block): nodes whose assembled row of K repeats are advanced from
+    pre-summed row blocks + explicit neighbour lists (k_nbr_nodes), the rest by the Gauss-point kernels; both against
+    the oracle, and against each other with the option switched off."""
+    mats = [(M.ELASTIC3DLINEAR, [1.3e7, 0.3, 2000.0]), (M.ELASTIC3DLINEAR, [5.0e7, 0.25, 2200.0])]
+    if kind == "quad4":
+        m = M.make_area_model((40, 31), 0.5, th=0.8, nt=60)
+    else:
+        m = M.make_box_model((13, 11, 10), 1.0, nt=50, layers=mats if kind == "hex8_layers" else None)
+        if kind == "hex8_layers":
+            m.dt *= 0.5
+    m.rec_nodes = np.array(sorted({0, m.n_nodes - 1, m.n_nodes // 2, m.n_nodes // 3, int(m.point_loads[0].nodes[0])}), dtype=np.int32)
+    s = M.shuffle_numbering(m, 11)
+    V0 = np.random.default_rng(5).uniform(-1.0, 1.0, s.n_total)
+    V0[np.asarray(s.totaldof)[np.asarray(s.freedof_flat) < 0]] = 0.0
+    ref, Uref = oracle.run(s, nthreads=8, V0=V0)
+    d = _device(s, V0=V0)
+    out = d.run()[0]
+    c = d.counters()
+    assert c["n_block_nodes"] == 0 and c["n_nbr_nodes"] > s.n_nodes // 2 and c["n_generic_elements"] < s.n_elem
+    assert rel_err(out, ref) < TOL_LINEAR
+    U = d.get_state(0)
+    assert np.abs(U - Uref).max() / np.abs(Uref).max() < TOL_LINEAR
+    F = d.internal_force()
+    Fref = oracle.internal_force(s, U)
+    assert np.abs(F - Fref).max() / np.abs(Fref).max() < 1e-11
+    d2 = _device(s, V0=V0, options={"nbr_classes": 0.0})
+    out2 = d2.run()[0]
+    assert d2.counters()["n_nbr_nodes"] == 0 and d2.counters()["n_generic_elements"] == s.n_elem
+    assert rel_err(out2, out) < TOL_LINEAR
+
+
 def test_vel_accel_recorders(oracle):
     m = kat_model()
     d = _device(m, fields=(0, 1, 2))

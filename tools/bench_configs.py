@@ -58,6 +58,7 @@ def run(name, m, bytes_per_elem, steps, warm=5, note="", options=None):
             "algorithmic_bytes_per_element_update": bytes_per_elem,
             "algorithmic_GBs": rate * bytes_per_elem / 1e9, "frac_of_hbm_peak": rate * bytes_per_elem / 1e9 / peak(),
             "kernel_ms": kt, "block_nodes": c["n_block_nodes"], "generic_elements": c["n_generic_elements"],
+            "nbr_nodes": c2["n_nbr_nodes"], "nbr_classes": c2["n_nbr_classes"],
             "pml_elements": c2["n_pml_elements"], "pml_unknowns": c2["n_pml_unknowns"],
             "pml_iterations_per_step": (c2["pml_iterations"] / c2["pml_solves"]) if c2["pml_solves"] else 0,
             "launches_per_step": c2["launches_per_step"], "plan_s": t_plan, "finite": bool(np.isfinite(U).all()),
@@ -99,6 +100,30 @@ def main():
             m = M.make_box_model(ne, 1.0, mat=(M.ELASTIC3DLINEAR, SOIL), nt=4000)
             m.blocks = []
             run(f"{ne[0]}^3 lin3DHexa8 elastic, Gauss-point path (no lattice)", m, 140.0, a.steps)
+        elif w == "hexshuf":
+            # unstructured numbering: the same cells with node ids and element order permuted at random, two materials in
+            # layers -> no lattice block; pre-summed rows + neighbour lists (k_nbr_nodes) where the row repeats
+            ne = (int(160 * S),) * 3
+            mats = [(M.ELASTIC3DLINEAR, SOIL), (M.ELASTIC3DLINEAR, [5.0e7, 0.25, 2200.0])]
+            m = M.make_box_model(ne, 1.0, nt=4000, layers=mats)
+            m.dt *= 0.5
+            m = M.shuffle_numbering(m, 20260117)
+            run(f"{ne[0]}^3 lin3DHexa8, 2 materials, random node / element numbering (neighbour-list node classes)", m, 140.0, a.steps)
+        elif w == "hexshuf_gp":
+            ne = (int(160 * S),) * 3
+            mats = [(M.ELASTIC3DLINEAR, SOIL), (M.ELASTIC3DLINEAR, [5.0e7, 0.25, 2200.0])]
+            m = M.make_box_model(ne, 1.0, nt=4000, layers=mats)
+            m.dt *= 0.5
+            m = M.shuffle_numbering(m, 20260117)
+            run(f"{ne[0]}^3 lin3DHexa8, 2 materials, random numbering, Gauss-point path (nbr_classes = 0)", m, 140.0, a.steps,
+                options={"nbr_classes": 0.0})
+        elif w == "hexjit":
+            # geometry jitter +-0.1 h with default_rng(20260117): every element its own class -> Gauss-point path
+            ne = (int(160 * S),) * 3
+            m = M.make_box_model(ne, 1.0, mat=(M.ELASTIC3DLINEAR, SOIL), nt=4000, jitter=0.1, seed=20260117)
+            m.dt *= 0.5
+            m.blocks = []
+            run(f"{ne[0]}^3 lin3DHexa8, jittered geometry (+-0.1 h): Gauss-point path from the coordinates", m, 140.0, a.steps)
         elif w == "newmark":   # the implicit NewmarkBeta + Linear step at 4x the explicit time step
             n = int(160 * S)
             m = M.make_box_model((n, n, n), 1.0, mat=(M.ELASTIC3DLINEAR, SOIL), nt=4000)
