@@ -651,7 +651,7 @@ int plan_and_upload(svlgpu_model *m) {
     // ---- D2. neighbour-list node classes (non-lattice nodes with a repeating assembled row of K) ---------------------------
     // The lattice stencil needs the Builder.py node numbering.  Outside it -- unstructured numbering, several blocks,
     // multi-material regions meshed with congruent cells -- a node whose incident elements are all linear still has a
-    // constant row of K: the sum of the K_e rows of its incident elements (ascending element id, Assembler.cpp:251).
+    // constant row of K: the sum of the K_e rows of its incident elements (Assembler.cpp:239-269).
     // Nodes are classified by (element class, local index) of each incident element + the pattern in which the element
     // corners coincide + 1/Keff, Kminus; a class that occurs at >= 64 nodes gets its pre-summed blocks [slot][b][a] and its
     // nodes an explicit neighbour list (k_nbr_nodes).  Everything else stays on the Gauss-point path.
@@ -667,6 +667,19 @@ int plan_and_upload(svlgpu_model *m) {
         for (int e = 0; e < nE; e++) {
             if (elem_cls[e] < 0) continue;
             for (int l = 0; l < kind_npe(m->elem_kind[e]); l++) { const int n = m->elem_conn[8ll * e + l]; ie[fill[n]] = e; il[fill[n]] = l; fill[n]++; }
+        }
+        // canonical order of a node's incident elements: by (element class, local index), element id only as the tie
+        // break -- the class of a node must not depend on how the mesher happened to number the elements.  (The blocks of a
+        // class are summed in this order for every node of the class; the reference adds f_e in ascending element id:
+        // the association differs at the 1e-16 level, like the lattice stencil's.)
+        for (int n = 0; n < nN; n++) {
+            const int a = iptr[n], b = iptr[n + 1];
+            if (b - a < 2) continue;
+            std::pair<std::pair<int32_t, int32_t>, int32_t> tmp[64];
+            if (b - a > 64) continue;
+            for (int q = a; q < b; q++) tmp[q - a] = {{elem_cls[ie[q]], il[q]}, ie[q]};
+            std::sort(tmp, tmp + (b - a));
+            for (int q = a; q < b; q++) { ie[q] = tmp[q - a].second; il[q] = tmp[q - a].first.second; }
         }
         struct NClass { std::vector<int64_t> key; int rep; long long pop; };
         std::vector<NClass> ncl;
@@ -732,7 +745,7 @@ int plan_and_upload(svlgpu_model *m) {
                 const int nn = nb_ptr[i + 1] - nb_ptr[i];
                 double *T = &tbl[(size_t)newid[c] * N.stride];
                 cls_nn[newid[c]] = nn;
-                for (int q = iptr[n]; q < iptr[n + 1]; q++) {        // ascending element id
+                for (int q = iptr[n]; q < iptr[n + 1]; q++) {        // canonical order (see above)
                     const int e = ie[q], l = il[q];
                     const ElemClass &ec = classes[elem_cls[e]];
                     const int npe = kind_npe(ec.kind), ned = npe * nd;
@@ -753,7 +766,29 @@ int plan_and_upload(svlgpu_model *m) {
             // nodes sorted by class (stable: ascending node id inside a class), cut into one-class chunks
             std::vector<int32_t> order;
             for (size_t i = 0; i < cand.size(); i++) if (newid[ncls_of[cand[i]]] >= 0) order.push_back((int32_t)i);
-            std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return newid[ncls_of[cand[a]]] < newid[ncls_of[cand[b]]]; });
+            // inside a class: along a Morton curve through the node coordinates, so that the nodes of a chunk are neighbours in
+            // space whatever their ids are and their neighbour sets overlap in L1 / L2
+            std::vector<uint64_t> mort(cand.size(), 0);
+            {
+                double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+                for (int n : cand) for (int c = 0; c < nd; c++) { lo[c] = std::min(lo[c], m->coords[(size_t)nd * n + c]); hi[c] = std::max(hi[c], m->coords[(size_t)nd * n + c]); }
+                for (size_t i = 0; i < cand.size(); i++) {
+                    uint64_t key2 = 0;
+                    uint32_t q[3] = {0, 0, 0};
+                    for (int c = 0; c < nd; c++) {
+                        const double span = hi[c] - lo[c];
+                        q[c] = span > 0 ? (uint32_t)std::min(1048575.0, (m->coords[(size_t)nd * cand[i] + c] - lo[c]) / span * 1048575.0) : 0;
+                    }
+                    for (int bit = 19; bit >= 0; bit--) for (int c = nd - 1; c >= 0; c--) key2 = (key2 << 1) | ((q[c] >> bit) & 1u);
+                    mort[i] = key2;
+                }
+            }
+            std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+                const int ca = newid[ncls_of[cand[a]]], cb = newid[ncls_of[cand[b]]];
+                if (ca != cb) return ca < cb;
+                if (mort[a] != mort[b]) return mort[a] < mort[b];
+                return a < b;
+            });
             std::vector<int32_t> chunk_cls, dof0v, nbrv;
             std::vector<int64_t> chunk_off;
             size_t z = 0;

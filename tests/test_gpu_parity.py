@@ -472,6 +472,35 @@ def test_host_driver_reads_reference_files_and_writes_reference_recorders(tmp_pa
         assert open(out_file).readline() == open(out_file + ".gpu").readline()        # identical header line
 
 
+@pytest.mark.parametrize("name", ["kat444", "c1_column20", "kat444_masses", "hex8_layered_rayleigh", "quad4_area", "j2_column", "lysmer_column"])
+def test_reference_executable_with_the_gpu_integrator_linked_in(tmp_path, name):
+    """The drop-in at link time: oracle/_ref/SeismoVLAB_refgpu.exe is the reference's own objects (Driver, DynamicAnalysis,
+    Recorder, Mesh, elements ...) with CentralDifference.o replaced by integration/GPUCentralDifference.cpp + libsvlgpu.so.
+    It reads the same JSON, its own Recorder writes the files -- and they must equal the golden files the unmodified
+    executable wrote (and that executable's output on this very input, when it travelled to this box)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "SeismoVLAB_refgpu.exe")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/SeismoVLAB_refgpu.exe was not built (needs /root/reference at build time)")
+    m = cases.CASES[name]()
+    g = np.load(os.path.join(root, "tests", "golden", f"{name}.npz"))
+    part = M.write_reference_json(m, str(tmp_path), "Case", "Run", resp=("disp", "vel", "accel"), ndps=17)
+    r = subprocess.run([exe, "-dir", part, "-file", "Case.1.$.json"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "GPU CentralDifference:" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    out = {k: M.read_node_recorder(os.path.join(str(tmp_path), "Solution", "Run", f"{k}.0.out")) for k in ("disp", "vel", "accel")}
+    assert out["disp"].shape == g["disp"].shape
+    assert cases.rel_err(out["disp"], g["disp"]) < cases.TOL[name]
+    ref_exe = os.path.join(root, "oracle", "_ref", "SeismoVLAB.exe")
+    if os.path.exists(ref_exe):
+        for k in out:
+            os.rename(os.path.join(str(tmp_path), "Solution", "Run", f"{k}.0.out"), os.path.join(str(tmp_path), f"{k}.gpu"))
+        subprocess.run([ref_exe, "-dir", part, "-file", "Case.1.$.json"], stdout=subprocess.DEVNULL, check=True, timeout=900)
+        for k in out:
+            ref = M.read_node_recorder(os.path.join(str(tmp_path), "Solution", "Run", f"{k}.0.out"))
+            assert cases.rel_err(out[k], ref) < max(cases.TOL[name], 1e-9 if k != "disp" else 0.0), k
+
+
 @pytest.mark.parametrize("name", ["kat444", "drm_box", "quad4_area", "j2_column"])
 def test_cuda_graph_replay_matches(oracle, name):
     """steps replayed from a CUDA graph (device-resident step index / recorder row) give the same history"""
