@@ -183,8 +183,9 @@ class DeviceModel:
                 idx = A(np.nonzero((am_e == am) & (ak_e == ak))[0], np.int32)
                 self._ck(self.L.svlgpu_set_rayleigh(self.h, len(idx), _i(idx), float(am), float(ak)))
         opts = {"lattice_guess": 0.0} if not m.blocks else {}      # a model without lattice hints asks for the generic path
-        if getattr(m, "pml_collective", False) and getattr(m, "halos", None):
-            opts["pml_collective"] = 1.0                            # partition of a PML model: every rank joins the block solve
+        if getattr(m, "pml_collective", False) and (getattr(m, "halos", None) or comm is not None):
+            opts["pml_collective"] = 1.0                            # partition of a PML model: every rank joins the block solve,
+            #                                                         also one that shares no node with anybody
         opts.update(options or {})
         for k, v in opts.items():
             self._ck(self.L.svlgpu_set_option(self.h, k.encode(), float(v)))

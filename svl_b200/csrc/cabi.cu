@@ -1,6 +1,7 @@
 // cabi.cu -- extern "C" surface of libsvlgpu.so (include/svlgpu.h).  Thin: argument checks,
 // copies into the host model, and forwarding to the planner / kernels.  No exceptions cross
 // the boundary; failures return non-zero ("stop") and set svlgpu_last_error().
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <string>
@@ -169,6 +170,7 @@ int svlgpu_set_option(svlgpu_model *m, const char *name, double value) {
     if (n == "lattice_guess") m->opt_lattice_guess = value != 0.0;
     else if (n == "keep_gauss") m->opt_keep_gauss = value != 0.0;
     else if (n == "nbr_classes") m->opt_nbr_classes = value != 0.0;
+    else if (n == "renumber") m->opt_renumber = value != 0.0;
     else if (n == "cuda_graph") m->opt_graph = value != 0.0 ? 1 : 0;
     else if (n == "integrator") { REQUIRE(value == 0.0 || value == 1.0, "set_option: integrator must be 0 (CentralDifference) or 1 (NewmarkBeta)"); m->opt_integrator = (int)value; }
     else if (n == "newmark_rtol") { REQUIRE(value > 0.0 && value < 1.0, "set_option: newmark_rtol out of range"); m->nm.rtol = value; }
@@ -288,6 +290,7 @@ int svlgpu_step(svlgpu_model *m, int k_begin, int k_end, int sync) {
     cudaEventRecord(m->ev0, m->stream);
     if (run_steps(m, k_begin, k_end, nullptr)) return 1;
     cudaEventRecord(m->ev1, m->stream);
+    m->steps_since_check += k_end - k_begin;
     if (sync) return svlgpu_sync(m);
     return 0;
     GUARD_END
@@ -300,6 +303,8 @@ int svlgpu_sync(svlgpu_model *m) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, m->ev0, m->ev1) == cudaSuccess) m->last_step_ms = ms;
     timer_flush(m);
+    // NaN / Inf in U -> stop; one read of U_n per synchronised call, outside the event-timed region
+    if (m->steps_since_check > 0) { m->steps_since_check = 0; if (state_is_finite(m)) return 1; }
     return 0;
 }
 
@@ -331,8 +336,9 @@ int svlgpu_step_host(svlgpu_model *m, int k, const double *amplitudes, int nload
     if (rec >= 0) {
         std::memcpy(row_out, m->h_row, sizeof(double) * row_len);
         for (int i = 0; i < row_len; i++)
-            if (row_out[i] != row_out[i]) { set_error("NaN in recorded response"); return 1; }
+            if (!(std::fabs(row_out[i]) <= 1.7976931348623157e308)) { set_error("NaN / Inf in recorded response"); return 1; }
     }
+    if (++m->steps_since_check >= 256) { m->steps_since_check = 0; if (state_is_finite(m)) return 1; }   // whole state: every 256 calls
     return 0;
     GUARD_END
 }
@@ -405,7 +411,7 @@ int svlgpu_read_recorder(svlgpu_model *m, int rec, int r0, int r1, double *out) 
     if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return 1; }
     const size_t cnt = (size_t)(r1 - r0) * r.width;
     for (size_t i = 0; i < cnt; i++)
-        if (out[i] != out[i]) { set_error("NaN in recorded response"); return 1; }
+        if (!(std::fabs(out[i]) <= 1.7976931348623157e308)) { set_error("NaN / Inf in recorded response"); return 1; }
     return 0;
     GUARD_END
 }

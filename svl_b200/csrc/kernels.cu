@@ -2316,6 +2316,30 @@ int run_steps(svlgpu_model *m, int k0, int k1, const double *dev_amp) {
     return 0;
 }
 
+// NaN / Inf anywhere in the newest displacement vector -> flag (the reference does not check; SURVEY.md 8(b): must surface as stop)
+__global__ void __launch_bounds__(256) k_finite_check(const double *U, long long n, int *flag) {
+    bool bad = false;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = U[i];
+        bad = bad || !(fabs(v) <= 1.7976931348623157e308);
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) *flag = 1;
+}
+// returns 1 (and sets the error text) if the state holds a non-finite value; one streaming read of U_n
+int state_is_finite(svlgpu_model *m) {
+    if (!m->d_flag) {
+        CUDA_OK(cudaMalloc(&m->d_flag, sizeof(int)));
+        m->allocs.push_back(m->d_flag);
+    }
+    CUDA_OK(cudaMemsetAsync(m->d_flag, 0, sizeof(int), m->stream));
+    k_finite_check<<<148 * 8, 256, 0, m->stream>>>(m->d_U[m->cur], (long long)m->n_int, m->d_flag);
+    int h = 0;
+    CUDA_OK(cudaMemcpyAsync(&h, m->d_flag, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    CUDA_OK(cudaStreamSynchronize(m->stream));
+    if (h) { set_error("NaN / Inf in the displacement vector: the analysis diverged (time step above the stability limit?)"); return 1; }
+    return 0;
+}
+
 // out = K x for any vector x in the internal dof layout: the force-only pass of the explicit path
 // (Gauss-point elements + lattice stencils + generic node gather); used by the Newmark Krylov solve
 int operator_K(svlgpu_model *m, const double *x, double *out) {

@@ -330,6 +330,8 @@ struct svlgpu_model {
     double *d_U[3] = {nullptr, nullptr, nullptr};   // rotating buffers
     int cur = 0, prev = 1, next = 2;
     double *d_kinv = nullptr, *d_km = nullptr;      // per internal dof: 1/Keff, Kminus (0 if not free)
+    int *d_flag = nullptr;                          // non-finite state flag (state_is_finite)
+    int steps_since_check = 0;
     double *d_fscratch = nullptr;                   // force-only passes (svlgpu_internal_force, reactions): never a state buffer
     std::vector<double> h_mass, h_cdiag;            // lumped mass / damping diagonal per internal dof
 
@@ -364,7 +366,7 @@ struct svlgpu_model {
     int32_t *d_pl_target = nullptr;                 // per loaded dof: slot in halo.d_hF, -2-c for PML unknown c, or -1
     svl::PmlDev pml;
     svl::NbrDev nbr;
-    bool opt_nbr_classes = true;
+    bool opt_nbr_classes = true, opt_renumber = true;
 
     // counters / timing
     int64_t total_launches = 0, launches_per_step = 0;
@@ -382,6 +384,7 @@ int plan_and_upload(svlgpu_model *m);                                       // p
 int run_steps(svlgpu_model *m, int k0, int k1, const double *dev_amp);      // kernels.cu
 int compute_internal_force(svlgpu_model *m, double *F_host);
 int gather_state(svlgpu_model *m, int field, const int32_t *dofs, int n, double *out);
+int state_is_finite(svlgpu_model *m);
 void timer_flush(svlgpu_model *m);
 void timer_begin(svlgpu_model *m, int which);
 void timer_end(svlgpu_model *m, int which);

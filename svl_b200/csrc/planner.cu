@@ -86,7 +86,63 @@ static int plan_pml(svlgpu_model *m, const std::vector<int32_t> &alias, const st
                     const std::vector<int32_t> &node_of_dof, const std::vector<double> &kinv,
                     const std::vector<double> &km, std::vector<int32_t> &cmap);
 
+// Node ids of a mesh that does not follow the Builder.py lattice numbering carry no locality: the kernels that reach their
+// neighbours through index lists (Gauss-point elements, node gathers, neighbour-list classes) would touch one DRAM / L2
+// sector per value.  The state layout on the device is the planner's business (the caller only ever names total dofs), so
+// such a model is renumbered along a Morton curve through the node coordinates before anything is planned: neighbours in
+// space become neighbours in memory.  Element order -- the reference's assembly order -- is left alone.
+static void renumber_nodes_by_locality(svlgpu_model *m) {
+    const int nd = m->ndim, nN = m->n_nodes;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int n = 0; n < nN; n++) for (int c = 0; c < nd; c++) { lo[c] = std::min(lo[c], m->coords[(size_t)nd * n + c]); hi[c] = std::max(hi[c], m->coords[(size_t)nd * n + c]); }
+    std::vector<std::pair<uint64_t, int32_t>> key(nN);
+    for (int n = 0; n < nN; n++) {
+        uint32_t q[3] = {0, 0, 0};
+        for (int c = 0; c < nd; c++) {
+            const double span = hi[c] - lo[c];
+            q[c] = span > 0 ? (uint32_t)std::min(2097151.0, (m->coords[(size_t)nd * n + c] - lo[c]) / span * 2097151.0) : 0;
+        }
+        uint64_t k = 0;
+        for (int bit = 20; bit >= 0; bit--) for (int c = nd - 1; c >= 0; c--) k = (k << 1) | ((q[c] >> bit) & 1u);
+        key[n] = {k, n};
+    }
+    std::sort(key.begin(), key.end());
+    std::vector<int32_t> new_of_old(nN);
+    for (int i = 0; i < nN; i++) new_of_old[key[i].second] = i;
+    std::vector<int32_t> ndof(nN), ptr(nN + 1, 0), tot(m->totaldof.size()), fre(m->freedof.size());
+    std::vector<double> xyz(m->coords.size());
+    for (int i = 0; i < nN; i++) ndof[i] = m->node_ndof[key[i].second];
+    for (int i = 0; i < nN; i++) ptr[i + 1] = ptr[i] + ndof[i];
+    for (int i = 0; i < nN; i++) {
+        const int o = key[i].second;
+        for (int c = 0; c < nd; c++) xyz[(size_t)nd * i + c] = m->coords[(size_t)nd * o + c];
+        for (int c = 0; c < ndof[i]; c++) { tot[ptr[i] + c] = m->totaldof[m->node_ptr[o] + c]; fre[ptr[i] + c] = m->freedof[m->node_ptr[o] + c]; }
+    }
+    m->node_ndof.swap(ndof); m->node_ptr.swap(ptr); m->totaldof.swap(tot); m->freedof.swap(fre); m->coords.swap(xyz);
+    for (size_t e = 0; e < m->elem_kind.size(); e++)
+        for (int l = 0; l < kind_npe(m->elem_kind[e]); l++) m->elem_conn[8 * e + l] = new_of_old[m->elem_conn[8 * e + l]];
+    for (auto &pm : m->masses) pm.first = new_of_old[pm.first];
+    for (auto &pl : m->ploads) for (auto &n : pl.nodes) n = new_of_old[n];
+    for (auto &d : m->drms) for (auto &n : d.nodes) n = new_of_old[n];
+    for (auto &r : m->recorders) for (auto &n : r.nodes) n = new_of_old[n];
+    for (auto &sm : m->supports) sm.node = new_of_old[sm.node];
+    for (auto &hp : m->halo_peers) for (auto &n : hp.nodes) n = new_of_old[n];
+}
+
 int plan_and_upload(svlgpu_model *m) {
+    if (m->hints.empty() && m->opt_renumber && !getenv("SVLGPU_NO_RENUMBER")) {
+        // would the lattice guess of section D apply?  (same test on the first solid element)
+        bool lattice_like = false;
+        if (m->opt_lattice_guess)
+            for (size_t e = 0; e < m->elem_kind.size(); e++) {
+                const int k = m->elem_kind[e];
+                if (k != SVLGPU_LIN3DHEXA8 && k != SVLGPU_LIN2DQUAD4) continue;
+                const int32_t *cn = &m->elem_conn[8 * e];
+                lattice_like = cn[1] == cn[0] + 1 && cn[3] - cn[0] >= 2;
+                break;
+            }
+        if (!lattice_like) renumber_nodes_by_locality(m);
+    }
     const int nd = m->ndim;
     const int nE = (int)m->elem_kind.size();
     const int nN = m->n_nodes;
@@ -181,7 +237,9 @@ int plan_and_upload(svlgpu_model *m) {
             hp.nodes.erase(std::remove_if(hp.nodes.begin(), hp.nodes.end(), [&](int32_t n) { return node_is_pml[n] != 0; }), hp.nodes.end());
         }
     }
-    const bool plan_pml_block = has_pml || (m->pml.collective && !m->halo_peers.empty());
+    // "pml_collective": this rank joins the block solve's reductions even if it holds no PML unknown and shares no node with
+    // anybody (a disconnected partition of a PML model) -- the all-reduces are issued by every rank of the communicator
+    const bool plan_pml_block = has_pml || m->pml.collective;
 
     // ---- B. element classes ---------------------------------------------------------------
     const char *tol_s = getenv("SVLGPU_CLASS_TOL");
@@ -766,29 +824,7 @@ int plan_and_upload(svlgpu_model *m) {
             // nodes sorted by class (stable: ascending node id inside a class), cut into one-class chunks
             std::vector<int32_t> order;
             for (size_t i = 0; i < cand.size(); i++) if (newid[ncls_of[cand[i]]] >= 0) order.push_back((int32_t)i);
-            // inside a class: along a Morton curve through the node coordinates, so that the nodes of a chunk are neighbours in
-            // space whatever their ids are and their neighbour sets overlap in L1 / L2
-            std::vector<uint64_t> mort(cand.size(), 0);
-            {
-                double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-                for (int n : cand) for (int c = 0; c < nd; c++) { lo[c] = std::min(lo[c], m->coords[(size_t)nd * n + c]); hi[c] = std::max(hi[c], m->coords[(size_t)nd * n + c]); }
-                for (size_t i = 0; i < cand.size(); i++) {
-                    uint64_t key2 = 0;
-                    uint32_t q[3] = {0, 0, 0};
-                    for (int c = 0; c < nd; c++) {
-                        const double span = hi[c] - lo[c];
-                        q[c] = span > 0 ? (uint32_t)std::min(1048575.0, (m->coords[(size_t)nd * cand[i] + c] - lo[c]) / span * 1048575.0) : 0;
-                    }
-                    for (int bit = 19; bit >= 0; bit--) for (int c = nd - 1; c >= 0; c--) key2 = (key2 << 1) | ((q[c] >> bit) & 1u);
-                    mort[i] = key2;
-                }
-            }
-            std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
-                const int ca = newid[ncls_of[cand[a]]], cb = newid[ncls_of[cand[b]]];
-                if (ca != cb) return ca < cb;
-                if (mort[a] != mort[b]) return mort[a] < mort[b];
-                return a < b;
-            });
+            std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return newid[ncls_of[cand[a]]] < newid[ncls_of[cand[b]]]; });
             std::vector<int32_t> chunk_cls, dof0v, nbrv;
             std::vector<int64_t> chunk_off;
             size_t z = 0;

@@ -388,22 +388,42 @@ void PrintPlan(const Mesh &me, int rank) {
 }
 
 // NCCL bootstrap without MPI: rank 0 drops the unique id into the partition directory, the others pick it up
+// The file name carries the job: the -np launcher's own id, else torchrun's run id + port (the same on every rank of a job).
+// A run that died after rank 0 wrote the file must not poison the next one with the same name: (i) rank 0 removes stale
+// id / ack files as the very first thing it does (RemoveStaleNcclFiles, before it parses anything), (ii) the file carries the
+// wall-clock second it was written and a reader refuses one written long before the reader itself started.
 std::string NcclIdPath(const std::string &dir) {
     const char *job = getenv("SVLGPU_JOB_ID");
-    if (!job) job = getenv("MASTER_PORT");
-    return dir + "/.svlgpu_nccl_id." + (job ? job : "0");
+    std::string tag;
+    if (job) tag = job;
+    else {
+        const char *run = getenv("TORCHELASTIC_RUN_ID"), *port = getenv("MASTER_PORT");
+        tag = std::string(run ? run : "run") + "." + (port ? port : "0");
+    }
+    for (char &c : tag) if (c == '/' || c == ' ') c = '_';
+    return dir + "/.svlgpu_nccl_id." + tag;
+}
+static const long long g_process_start = (long long)time(nullptr);
+void RemoveStaleNcclFiles(const std::string &dir, int world) {
+    const std::string path = NcclIdPath(dir);
+    std::remove(path.c_str());
+    std::remove((path + ".tmp").c_str());
+    for (int q = 1; q < world; q++) std::remove((path + ".ack." + std::to_string(q)).c_str());
 }
 bool ExchangeNcclId(const std::string &dir, int rank, char id[128]) {
     const std::string path = NcclIdPath(dir);
     if (rank == 0) {
         if (svlgpu_nccl_unique_id(id)) return true;
         const std::string tmp = path + ".tmp";
-        { std::ofstream f(tmp, std::ios::binary); f.write(id, 128); }
+        const long long stamp = (long long)time(nullptr);
+        { std::ofstream f(tmp, std::ios::binary); f.write(id, 128); f.write((const char *)&stamp, sizeof stamp); }
         return std::rename(tmp.c_str(), path.c_str()) != 0;
     }
     for (int tries = 0; tries < 3000; tries++) {                     // up to 5 minutes: rank 0 may still be parsing
         std::ifstream f(path, std::ios::binary);
-        if (f.is_open() && f.read(id, 128) && f.gcount() == 128) {
+        long long stamp = 0;
+        if (f.is_open() && f.read(id, 128) && f.gcount() == 128 && f.read((char *)&stamp, sizeof stamp) &&
+            stamp >= g_process_start - 120) {                        // older: left behind by a run that died (ranks start together)
             std::ofstream ack(path + ".ack." + std::to_string(rank));  // rank 0 keeps the file until every rank has it
             return false;
         }
@@ -516,7 +536,7 @@ class CentralDifference {
         if (keep_gauss && (svlgpu_set_option(h, "keep_gauss", 1.0) || svlgpu_set_option(h, "lattice_guess", 0.0))) return fail();
         for (auto &kv : mesh.Halos)
             if (svlgpu_add_halo(h, kv.first, (int)kv.second.size(), kv.second.data())) return fail();
-        if (mesh.pml_collective && !mesh.Halos.empty() && svlgpu_set_option(h, "pml_collective", 1.0)) return fail();
+        if (mesh.pml_collective && svlgpu_set_option(h, "pml_collective", 1.0)) return fail();   // also on a rank without shared nodes: it still joins the all-reduces
         if (svlgpu_finalize(h, dt, device)) return fail();
         return false;
     }
@@ -744,8 +764,9 @@ int main(int argc, char **argv) {
                 if (done < 0) break;
                 left--;
                 const int rc = WIFEXITED(st) ? WEXITSTATUS(st) : 1;
+                kids.erase(std::remove(kids.begin(), kids.end(), done), kids.end());   // a reaped pid may be recycled: never signal it
                 if (rc != 0 && worst == 0)
-                    for (pid_t k : kids) if (k != done) kill(k, SIGTERM);
+                    for (pid_t k : kids) kill(k, SIGTERM);
                 worst = std::max(worst, rc);
             }
             return worst;
@@ -753,6 +774,11 @@ int main(int argc, char **argv) {
     }
     const char *rk = getenv("RANK"), *lr = getenv("LOCAL_RANK"), *ws = getenv("WORLD_SIZE");
     const int rank = rk ? atoi(rk) : 0, device = lr ? atoi(lr) : 0, world = ws ? std::max(1, atoi(ws)) : 1;
+    if (world > 1 && rank == 0 && !plan_only) RemoveStaleNcclFiles(dir, world);
+    struct IdFileGuard {                                                 // rank 0 leaves no id file behind on a failure path either
+        std::string dir; int world; bool armed;
+        ~IdFileGuard() { if (armed) RemoveStaleNcclFiles(dir, world); }
+    } guard{dir, world, world > 1 && rank == 0 && !plan_only};
     try {
         for (std::string pattern : files) {                              // staged analyses run in sequence (Driver.hpp:2058-2100)
             auto file_of = [&](int r) {

@@ -199,6 +199,41 @@ def reaction_lysmer():
     return m
 
 
+# ---- mid-size goldens in the shapes of BASELINE configs[1] / [2] / [4] (the toy meshes above exercise one tile of
+# the lattice kernels; these are the largest the reference executable finishes in minutes with the shim's envelope LDL^T) -------
+def mid_quad4_pml():
+    """configs[1] shape: 200 x 100 lin2DQuad4 half-space + 5-cell PML2DQuad4 layer (left / right / bottom), point source."""
+    m = M.make_pml_model((200, 100), 5, 1.0, soil=(M.ELASTIC2DPLANESTRAIN, SOIL), nt=160, dt=PML_DT)
+    ns = m.n_soil_nodes
+    N1 = 201
+    m.rec_nodes = np.array([0, 100 + N1 * 50, 100 + N1 * 100, 30 + N1 * 80, 199 + N1 * 3, int(m.point_loads[0].nodes[0]), ns + 7, ns + 900], dtype=np.int32)
+    return m
+
+
+def mid_pml3d():
+    """configs[2] shape: 14 x 14 x 12 lin3DHexa8 half-space + 3-cell PML3DHexa8 layer on 5 faces."""
+    m = M.make_pml_model((14, 14, 12), 3, 1.0, soil=(M.ELASTIC3DLINEAR, SOIL), nt=90, dt=PML_DT)
+    ns = m.n_soil_nodes
+    N1 = 15
+    m.rec_nodes = np.array([7 + N1 * 7 + N1 * N1 * 12, 7 + N1 * 7 + N1 * N1 * 6, 1 + N1 * 2 + N1 * N1 * 3, int(m.point_loads[0].nodes[0]), ns + 11, ns + 1500],
+                           dtype=np.int32)
+    return m
+
+
+def mid_j2():
+    """configs[4] shape: 10 x 10 x 40 lin3DHexa8 + Plastic3DJ2 column, base shear + vertical load through the free surface,
+    loaded into yield (checked by the GPU test against the elastic twin)."""
+    m = M.make_box_model((10, 10, 40), 1.0, mat=(M.PLASTIC3DJ2, J2), nt=140, load_dir=(3.0e5, 0.0, 1.0e5))
+    N1 = 11
+    top = np.arange(N1 * N1 * 40, N1 * N1 * 41, dtype=np.int32)
+    s = m.point_loads[0].series
+    m.point_loads = [M.PointLoad(top, np.array([6.0e3, 0.0, 2.0e3]), s.copy())]
+    m.rec_nodes = np.array([5 + N1 * 5 + N1 * N1 * k for k in (40, 30, 20, 10, 3)] + [0 + N1 * 0 + N1 * N1 * 40], dtype=np.int32)
+    return m
+
+
+MID_CASES = {f.__name__: f for f in (mid_quad4_pml, mid_pml3d, mid_j2)}
+
 # cases whose goldens also hold `reaction` (and vel / accel where the support moves): tests/golden/make_golden.py
 REACTION_CASES = ("reaction_box", "reaction_area", "support_column", "support_area", "reaction_lysmer")
 
@@ -207,6 +242,7 @@ CASES = {f.__name__: f for f in (c1_column20, kat444, kat444_masses, hex8_distor
 # tolerance of |oracle - reference| and |device - oracle| per case (max_t|d| / max_t|ref| per dof)
 REACTION_CASE_FUNCS = {f.__name__: f for f in (reaction_box, reaction_area, support_column, support_area, reaction_lysmer)}
 TOL = {name: 1e-10 for name in list(CASES) + list(REACTION_CASE_FUNCS)}
+TOL.update({"mid_quad4_pml": 1e-9, "mid_pml3d": 1e-9, "mid_j2": 1e-8})
 TOL["j2ps_area"] = 1e-8
 TOL["j2_column"] = 1e-8        # plastic: looser bound (BASELINE.json north_star), stated in DESIGN.md
 TOL["pml2d"] = 1e-9            # PML: Keff is not diagonal -> iterative block solve (rtol 1e-14), see DESIGN.md

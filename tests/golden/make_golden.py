@@ -159,6 +159,15 @@ if __name__ == "__main__":
         extended_newmark_cases()
         newton_cases()
         raise SystemExit(0)
+    if args and args[0] == "mid":
+        import time
+        for name in args[1:] or list(cases.MID_CASES):
+            m = cases.MID_CASES[name]()
+            t0 = time.time()
+            out = run_reference(m, ("disp",))
+            np.savez_compressed(os.path.join(HERE, f"{name}.npz"), fingerprint=cases.fingerprint(m), rec_nodes=m.rec_nodes, dt=m.dt, nt=m.nt, **out)
+            print(f"{name}: {out['disp'].shape} peak |u| = {np.abs(out['disp']).max():.6e}  ({time.time() - t0:.0f} s in the reference executable)", flush=True)
+        raise SystemExit(0)
     if args and args[0] == "reaction":
         reaction_cases(args[1:] or list(cases.REACTION_CASES))
         raise SystemExit(0)

@@ -220,6 +220,17 @@ def test_internal_force_leaves_the_state_buffers_alone(oracle):
     assert rel_err(d.read_recorder(0), ref) < TOL_LINEAR
 
 
+def test_diverged_run_stops_with_an_error():
+    """NaN / Inf in U must surface as stop (the reference does not check).  A time step ten times above the
+    stability limit overflows within a few hundred steps; the node that is recorded sits far from where it starts."""
+    from svl_b200.capi import SvlError
+    m = M.make_box_model((6, 6, 6), 1.0, dt=0.05, nt=1500, rec_nodes=[0])
+    d = _device(m)
+    with pytest.raises(SvlError, match="NaN / Inf"):
+        for k in range(1, 1500, 100):
+            d.step(k, k + 100, True)
+
+
 def test_j2_plastic_column(oracle):
     mat = (M.PLASTIC3DJ2, [2.9e7, 2.0e7, 2000.0, 1.0e7, 0.5, 1.0e4])
     m = M.make_box_model((3, 3, 8), 1.0, mat=mat, nt=120, load_dir=(3.0e5, 0.0, 1.0e5))

@@ -191,3 +191,9 @@ int svlgpu_comm_init(svlgpu_model *m, const void *id128, int rank, int nranks) {
     fflush(out());
     return 0;
 }
+int svlgpu_add_support_motion(svlgpu_model *m, int node, int dof, int nt, const double *series, double factor) {
+    (void)m;
+    fprintf(out(), "add_support_motion node=%d dof=%d nt=%d factor=%.17g series=%llx\n", node, dof, nt, factor, H(series, nt));
+    return 0;
+}
+int svlgpu_measure_peaks(int device, double *fp64_tflops, double *copy_gbs) { (void)device; (void)fp64_tflops; (void)copy_gbs; return 1; }
