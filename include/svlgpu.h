@@ -115,7 +115,9 @@ int svlgpu_hint_structured_block(svlgpu_model *m, int node0, int nx, int ny, int
  * row blocks + an explicit neighbour list instead of the Gauss-point kernels + element-force arena; verified numerically,
  * never trusted; default 1), "renumber" (1: a model without a lattice block -- no hint, and the lattice guess does not apply -- is
  * renumbered inside the library along a Morton curve through the node coordinates, so that neighbours in space are
- * neighbours in HBM; invisible to the caller, who only ever names total dofs; default 1), "pml_collective" (1 on EVERY rank of a
+ * neighbours in HBM; invisible to the caller, who only ever names total dofs; default 1), "reaction_collective" (1 on EVERY rank of a
+ * partitioned model that has a REACTION recorder on any rank: the reaction pass sums the partial forces of interface nodes
+ * over the ranks, so every rank must issue that exchange on every step, also a rank that records nothing; default 0), "pml_collective" (1 on EVERY rank of a
  * partitioned model that has PML elements anywhere, also on ranks without one: the PML block solve exchanges the
  * unknowns on shared nodes and all-reduces its dot products, so all ranks must issue the same collectives;
  * svlgpu_add_halo lists may then contain 9- / 5-dof PML nodes; default 0).          */

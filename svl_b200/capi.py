@@ -186,6 +186,8 @@ class DeviceModel:
         if getattr(m, "pml_collective", False) and (getattr(m, "halos", None) or comm is not None):
             opts["pml_collective"] = 1.0                            # partition of a PML model: every rank joins the block solve,
             #                                                         also one that shares no node with anybody
+        if comm is not None and REACTION in tuple(fields):
+            opts["reaction_collective"] = 1.0                       # also on a rank that holds none of the recorded nodes
         opts.update(options or {})
         for k, v in opts.items():
             self._ck(self.L.svlgpu_set_option(self.h, k.encode(), float(v)))

@@ -171,6 +171,7 @@ int svlgpu_set_option(svlgpu_model *m, const char *name, double value) {
     else if (n == "keep_gauss") m->opt_keep_gauss = value != 0.0;
     else if (n == "nbr_classes") m->opt_nbr_classes = value != 0.0;
     else if (n == "renumber") m->opt_renumber = value != 0.0;
+    else if (n == "reaction_collective") m->opt_reaction_collective = value != 0.0;
     else if (n == "cuda_graph") m->opt_graph = value != 0.0 ? 1 : 0;
     else if (n == "integrator") { REQUIRE(value == 0.0 || value == 1.0, "set_option: integrator must be 0 (CentralDifference) or 1 (NewmarkBeta)"); m->opt_integrator = (int)value; }
     else if (n == "newmark_rtol") { REQUIRE(value > 0.0 && value < 1.0, "set_option: newmark_rtol out of range"); m->nm.rtol = value; }

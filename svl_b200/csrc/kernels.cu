@@ -2058,6 +2058,11 @@ void record_rows(svlgpu_model *m, bool devk) {
     int ri = -1;
     bool reaction_ready = false;
     const SupArgs sup = sup_args(m);
+    if (m->opt_reaction_collective && m->halo.active && !m->halo_peers.empty()) {
+        // some rank records reactions: the pass exchanges interface partial forces, so every rank runs it on every step
+        if (reaction_pass(m, m->k_of_step, m->step_amp)) return;
+        reaction_ready = true;
+    }
     for (auto &r : m->recorders) {
         ri++;
         if (r.rows >= r.max_rows || !r.width) continue;
@@ -2238,7 +2243,7 @@ static int step_once(svlgpu_model *m, int k, const double *dev_amp) {
 // buffers and the 2 DRM buffers): per-step launch latency is what limits small partitions (8 GPUs on 10^8 DOF).
 constexpr int kGraphSteps = 6;
 static bool graph_usable(const svlgpu_model *m, const double *dev_amp) {
-    return m->use_graph && !dev_amp && !m->kernel_timing && !m->pml.present && !m->sup.n && !m->has_reaction_rec;
+    return m->use_graph && !dev_amp && !m->kernel_timing && !m->pml.present && !m->sup.n && !m->has_reaction_rec && !m->opt_reaction_collective;
 }
 void graph_destroy(svlgpu_model *m) {
     if (m->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)m->graph_exec);

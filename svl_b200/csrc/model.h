@@ -299,6 +299,7 @@ struct svlgpu_model {
     std::vector<svl::SupportMotion> supports;
     svl::SupportDev sup;
     bool has_reaction_rec = false;
+    bool opt_reaction_collective = false;           // several ranks: join the reaction pass's interface exchange on every step
     std::vector<svl::BlockHint> hints;
     std::vector<double> U0, V0, A0;
     bool opt_lattice_guess = true, opt_keep_gauss = false;

@@ -75,6 +75,7 @@ class Mesh {             // 06-Mesh/Mesh.cpp
     int ntotal_dev = 0, nfree_dev = 0;   // what the device model is built with: the partition's own counts (== ntotal / nfree on one rank)
     bool lumped = true;
     bool pml_collective = false;         // several ranks and PML nodes anywhere in the model: every rank joins the block solve
+    bool reaction_collective = false;    // several ranks and a REACTION recorder on any of them: every rank joins the reaction pass
     std::map<int, std::vector<int32_t>> Halos;                                             // peer rank -> shared nodes (device indices)
     std::map<unsigned, Node> Nodes;
     std::map<unsigned, Material> Materials;
@@ -536,6 +537,7 @@ class CentralDifference {
         if (keep_gauss && (svlgpu_set_option(h, "keep_gauss", 1.0) || svlgpu_set_option(h, "lattice_guess", 0.0))) return fail();
         for (auto &kv : mesh.Halos)
             if (svlgpu_add_halo(h, kv.first, (int)kv.second.size(), kv.second.data())) return fail();
+        if (mesh.reaction_collective && svlgpu_set_option(h, "reaction_collective", 1.0)) return fail();
         if (mesh.pml_collective && svlgpu_set_option(h, "pml_collective", 1.0)) return fail();   // also on a rank without shared nodes: it still joins the all-reduces
         if (svlgpu_finalize(h, dt, device)) return fail();
         return false;
@@ -795,8 +797,15 @@ int main(int argc, char **argv) {
             if (UpdateMesh(mesh, J, dir)) return 1;
             if (world > 1) {
                 if (pattern.find('$') == std::string::npos) { std::cout << "\x1B[31m ERROR: \x1B[0mseveral ranks need a '$' in -file\n"; return 1; }
-                for (int q = 0; q < world; q++)
-                    if (q != rank && UpdateMesh(all[q], svlhost::JParser(read_file(dir + "/" + file_of(q))).parse(), dir, true)) return 1;
+                for (int q = 0; q < world; q++) {
+                    if (q == rank) continue;
+                    const JValue Jq = svlhost::JParser(read_file(dir + "/" + file_of(q))).parse();
+                    if (UpdateMesh(all[q], Jq, dir, true)) return 1;
+                    if (Jq.has("Recorders"))                        // a REACTION recorder on any rank makes the reaction pass collective
+                        for (auto &kv : by_tag(Jq["Recorders"])) if (ieq((*kv.second)["resp"].as_string("disp"), "REACTION")) mesh.reaction_collective = true;
+                }
+                if (J.has("Recorders"))
+                    for (auto &kv : by_tag(J["Recorders"])) if (ieq((*kv.second)["resp"].as_string("disp"), "REACTION")) mesh.reaction_collective = true;
                 if (PlanPartitions(all, rank)) return 1;
                 for (int q = 0; q < world; q++) if (q != rank) all[q] = Mesh();     // the peers' tables were only needed for the plan
             }

@@ -360,6 +360,32 @@ def test_gauss_point_strain_stress_at_the_current_state(oracle, name):
     assert np.abs(sig - ref @ Cm.T).max() <= 1e-12 * np.abs(ref @ Cm.T).max()
 
 
+@pytest.mark.parametrize("name", list(cases.MID_CASES))
+def test_device_matches_reference_golden_on_mid_size_config_shapes(name):
+    """BASELINE configs[1] / [2] / [4] shapes at the largest size the reference executable finishes in minutes (200 x 100 quad4 +
+    PML2D, 14 x 14 x 12 hex8 + PML3D, 10 x 10 x 40 J2): many tiles / chunks / classes instead of the toy meshes' one."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"{name}.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{name}.npz has not been generated (tests/golden/make_golden.py mid)")
+    m = cases.MID_CASES[name]()
+    g = np.load(path)
+    assert str(g["fingerprint"]) == cases.fingerprint(m)
+    d = _device(m)
+    out = d.run()[0]
+    c = d.counters()
+    assert cases.rel_err(out, g["disp"]) < cases.TOL[name]
+    if name == "mid_j2":
+        assert c["n_generic_elements"] == m.n_elem
+        K, G = cases.J2[0], cases.J2[1]
+        lin = cases.mid_j2()
+        lin.materials = [(M.ELASTIC3DLINEAR, [9 * K * G / (3 * K + G), (3 * K - 2 * G) / (2 * (3 * K + G)), 2000.0])]
+        assert cases.rel_err(_device(lin).run()[0], g["disp"]) > 1e-3          # the load really drives Gauss points past yield
+    else:
+        assert c["n_pml_elements"] > 0 and c["n_block_nodes"] > 0
+        print(f"{name}: {c['n_pml_unknowns']} block unknowns, {c['pml_iterations'] / c['pml_solves']:.1f} BiCGStab iterations/step, "
+              f"err vs reference golden {cases.rel_err(out, g['disp']):.2e}")
+
+
 @pytest.mark.parametrize("name", list(cases.REACTION_CASES))
 def test_reactions_and_support_motion_match_reference_golden(oracle, name):
     """REACTION recorders (restrained-row reaction pass at recorded steps) and support motion on the device against the

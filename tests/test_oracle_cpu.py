@@ -38,6 +38,16 @@ def test_oracle_history_matches_reference_executable(oracle, name):
     assert cases.rel_err(out, g["disp"]) < cases.TOL[name]
 
 
+def test_oracle_matches_reference_executable_on_the_mid_size_j2_column(oracle):
+    """configs[4] shape (10 x 10 x 40 lin3DHexa8 + Plastic3DJ2, loaded into yield) against the reference executable.  (The two
+    mid-size PML goldens are device-only checks: the oracle's dense LDL^T of the coupled block would take an hour.)"""
+    m = cases.mid_j2()
+    g = gold("mid_j2")
+    assert str(g["fingerprint"]) == cases.fingerprint(m)
+    out, _ = oracle.run(m, nthreads=8)
+    assert cases.rel_err(out, g["disp"]) < cases.TOL["mid_j2"]
+
+
 @pytest.mark.parametrize("name", list(cases.REACTION_CASES))
 def test_oracle_reactions_and_support_motion_match_reference_executable(oracle, name):
     """Integrator::ComputeReactionForce rows (DynamicAnalysis.cpp:130-150, CentralDifference.cpp:155-171) and support motion
