@@ -66,6 +66,48 @@ def centroid_epart(m: Model, pgrid) -> np.ndarray:
     return part
 
 
+def weighted_epart(m: Model, pgrid, pml_weight: float = 250.0) -> np.ndarray:
+    """Element -> partition by recursive coordinate bisection with element WEIGHTS: per axis (z first, like proc_grid) every
+    group of the previous level is cut into pgrid[axis] slabs of equal total weight, cuts only BETWEEN layers of equal centroid
+    coordinate (so the interfaces stay planar).  A PML element costs ~250 soil elements per step on the device (9.0 ms for
+    2.16 M PML elements vs 0.51 ms for 32.8 M soil elements), so the cuts balance the PML shell and the soil follows: what
+    METIS does with vertex weights (`mpmetis` takes them the same way) instead of the plain geometric split of centroid_epart."""
+    npe_e = np.array([ELEM_NODES[int(k)] for k in np.unique(m.elem_kind)])[np.searchsorted(np.unique(m.elem_kind), m.elem_kind)]
+    cen = np.zeros((m.n_elem, m.ndim))
+    for npe in np.unique(npe_e):
+        sel = np.nonzero(npe_e == npe)[0]
+        cen[sel] = m.coords[m.elem_conn[sel, :npe]].mean(axis=1)
+    w = np.where(np.isin(m.elem_kind, (3, 4)), float(pml_weight), 1.0)
+    part = np.zeros(m.n_elem, dtype=np.int32)
+    mult = [1] * m.ndim
+    for a in range(1, m.ndim):
+        mult[a] = mult[a - 1] * pgrid[a - 1]
+    groups = [np.arange(m.n_elem)]
+    for a in reversed(range(m.ndim)):
+        nxt = []
+        for g in groups:
+            if pgrid[a] == 1 or len(g) == 0:
+                nxt.append(g)
+                continue
+            key = np.round(cen[g, a], 9)
+            layers, inv = np.unique(key, return_inverse=True)
+            lw = np.bincount(inv, weights=w[g], minlength=len(layers))
+            cum = np.cumsum(lw)
+            cuts = [0]
+            for q in range(1, pgrid[a]):
+                target = cum[-1] * q / pgrid[a]
+                j = int(np.argmin(np.abs(cum - target))) + 1                 # cut after layer j-1
+                cuts.append(min(max(j, cuts[-1] + 1), len(layers) - (pgrid[a] - q)))
+            cuts.append(len(layers))
+            slab = np.searchsorted(np.array(cuts[1:-1]), inv, side="right")
+            for q in range(pgrid[a]):
+                sel = g[slab == q]
+                part[sel] += q * mult[a]
+                nxt.append(sel)
+        groups = nxt
+    return part
+
+
 def write_metis_graph(m: Model, path: str) -> str:
     """The METIS mesh file the reference's pre-processor hands to `mpmetis` (Core/Partition.py:87-144 SetMetisInputFile):
     first line = number of elements, then one line of 1-based node ids per element in ascending element order, every id

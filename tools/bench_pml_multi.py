@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--size", dest="n", type=int, default=200)   # (not --n: torchrun abbreviates it)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--part", default="weighted", choices=["weighted", "centroid"],
+                    help="weighted: recursive bisection with PML elements weighted 250x (balances the block solve); centroid: plain geometric split")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -42,7 +44,8 @@ def main():
     m = M.make_pml_model((a.n, a.n, a.n), 10, 1.0, soil=(M.ELASTIC3DLINEAR, SOIL), nt=4000)
     m.dt *= 0.5                                               # dt = 0.25 h / Vp as in tools/bench_configs.py c3
     grid = P.proc_grid(world)
-    s = P.split_model(m, P.centroid_epart(m, grid), world, ranks=(rank,))[rank] if world > 1 else m
+    epart = (P.weighted_epart if a.part == "weighted" else P.centroid_epart)(m, grid) if world > 1 else None
+    s = P.split_model(m, epart, world, ranks=(rank,))[rank] if world > 1 else m
     t_build = time.perf_counter() - t0
     comm = (rank, world, bytes(uid.cpu().numpy())) if world > 1 else None
     d = capi.DeviceModel(s, device=local, max_rows=a.warmup + a.steps + 8, comm=comm)
@@ -58,7 +61,9 @@ def main():
     dist.all_reduce(fin, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(json.dumps({"config": f"configs[2] {a.n}^3 lin3DHexa8 + 10-cell PML3DHexa8 layer", "n_gpus": world,
-                          "partition_grid": grid, "elements": int(m.n_elem), "dof": int(m.n_total),
+                          "partition_grid": grid, "partitioner": a.part if world > 1 else None,
+                          "pml_elements_per_rank": [int((np.isin(m.elem_kind, (3, 4)) & (epart == r)).sum()) for r in range(world)] if world > 1 else None,
+                          "elements": int(m.n_elem), "dof": int(m.n_total),
                           "ms_per_step": float(ms.item()), "element_updates_per_s": m.n_elem / (float(ms.item()) * 1e-3),
                           "pml_iterations_per_step": (c["pml_iterations"] / c["pml_solves"]) if c["pml_solves"] else 0,
                           "pml_unknowns_rank0": c["n_pml_unknowns"], "launches_per_step_rank0": c["launches_per_step"],
