@@ -210,16 +210,6 @@ def mid_quad4_pml():
     return m
 
 
-def mid_pml3d():
-    """configs[2] shape: 14 x 14 x 12 lin3DHexa8 half-space + 3-cell PML3DHexa8 layer on 5 faces."""
-    m = M.make_pml_model((14, 14, 12), 3, 1.0, soil=(M.ELASTIC3DLINEAR, SOIL), nt=90, dt=PML_DT)
-    ns = m.n_soil_nodes
-    N1 = 15
-    m.rec_nodes = np.array([7 + N1 * 7 + N1 * N1 * 12, 7 + N1 * 7 + N1 * N1 * 6, 1 + N1 * 2 + N1 * N1 * 3, int(m.point_loads[0].nodes[0]), ns + 11, ns + 1500],
-                           dtype=np.int32)
-    return m
-
-
 def mid_j2():
     """configs[4] shape: 10 x 10 x 40 lin3DHexa8 + Plastic3DJ2 column, base shear + vertical load through the free surface,
     loaded into yield (checked by the GPU test against the elastic twin)."""
@@ -232,7 +222,9 @@ def mid_j2():
     return m
 
 
-MID_CASES = {f.__name__: f for f in (mid_quad4_pml, mid_pml3d, mid_j2)}
+MID_CASES = {f.__name__: f for f in (mid_quad4_pml, mid_j2)}
+# (a mid-size PML3DHexa8 golden is out of reach of the reference build in this image: the shim's envelope LDL^T of the ~46 000-dof
+# coupled system of a 14 x 14 x 12 + 3-cell model is near-dense -- it had not finished its first factorisation after 45 minutes)
 
 # cases whose goldens also hold `reaction` (and vel / accel where the support moves): tests/golden/make_golden.py
 REACTION_CASES = ("reaction_box", "reaction_area", "support_column", "support_area", "reaction_lysmer")
@@ -242,7 +234,7 @@ CASES = {f.__name__: f for f in (c1_column20, kat444, kat444_masses, hex8_distor
 # tolerance of |oracle - reference| and |device - oracle| per case (max_t|d| / max_t|ref| per dof)
 REACTION_CASE_FUNCS = {f.__name__: f for f in (reaction_box, reaction_area, support_column, support_area, reaction_lysmer)}
 TOL = {name: 1e-10 for name in list(CASES) + list(REACTION_CASE_FUNCS)}
-TOL.update({"mid_quad4_pml": 1e-9, "mid_pml3d": 1e-9, "mid_j2": 1e-8})
+TOL.update({"mid_quad4_pml": 1e-9, "mid_j2": 1e-8})
 TOL["j2ps_area"] = 1e-8
 TOL["j2_column"] = 1e-8        # plastic: looser bound (BASELINE.json north_star), stated in DESIGN.md
 TOL["pml2d"] = 1e-9            # PML: Keff is not diagonal -> iterative block solve (rtol 1e-14), see DESIGN.md

@@ -362,8 +362,8 @@ def test_gauss_point_strain_stress_at_the_current_state(oracle, name):
 
 @pytest.mark.parametrize("name", list(cases.MID_CASES))
 def test_device_matches_reference_golden_on_mid_size_config_shapes(name):
-    """BASELINE configs[1] / [2] / [4] shapes at the largest size the reference executable finishes in minutes (200 x 100 quad4 +
-    PML2D, 14 x 14 x 12 hex8 + PML3D, 10 x 10 x 40 J2): many tiles / chunks / classes instead of the toy meshes' one."""
+    """BASELINE configs[1] / [4] shapes at the largest size the reference executable finishes in minutes (200 x 100 quad4 +
+    PML2D, 10 x 10 x 40 J2): many tiles / chunks / classes instead of the toy meshes' one."""
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"{name}.npz")
     if not os.path.exists(path):
         pytest.skip(f"{name}.npz has not been generated (tests/golden/make_golden.py mid)")
