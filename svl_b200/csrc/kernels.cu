@@ -859,11 +859,28 @@ struct Shell3 {
 template <bool LOWREG>
 __global__ void __launch_bounds__(128, LOWREG ? 8 : 6) k_stencil3_shell(const Shell3 p) {
     __shared__ double T[kTbl3Stride];
+    __shared__ unsigned slot_mask;       // bit (s * 3 + dj) * 3 + di: the class couples to that neighbour at all
     {
         const double *Tg = p.tbl + (size_t)p.chunk_cls[blockIdx.x] * kTbl3Stride;
         for (int i = threadIdx.x; i < kTbl3Stride; i += 128) T[i] = Tg[i];
     }
     __syncthreads();
+    if (threadIdx.x < 32) {
+        // boundary classes have no neighbour on one or more sides (9 of 27 slots on a face, 15 on an edge, 19 at a corner):
+        // their blocks are exactly zero, so the CTA skips them -- indices, loads and DFMAs (adding 0 * u changes nothing)
+        bool nz = false;
+        if (threadIdx.x < 27) {
+            const int s = threadIdx.x / 9, dj = (threadIdx.x / 3) % 3, di = threadIdx.x % 3;
+#pragma unroll
+            for (int b = 0; b < 3; b++)
+#pragma unroll
+                for (int a = 0; a < 3; a++) nz = nz || T[((di * 3 + b) * 3 + dj) * 10 + s * 3 + a] != 0.0;
+        }
+        const unsigned mk = __ballot_sync(0xffffffffu, nz);
+        if (threadIdx.x == 0) slot_mask = mk;
+    }
+    __syncthreads();
+    const unsigned mask = slot_mask;
     int q[kShellNPT], ci[kShellNPT], cj[kShellNPT], ck[kShellNPT];
     double F[kShellNPT][3];
     // a class whose three dofs are restrained (1 / Keff == 0: e.g. the fixed base of a soil box) keeps its displacement:
@@ -888,8 +905,10 @@ __global__ void __launch_bounds__(128, LOWREG ? 8 : 6) k_stencil3_shell(const Sh
     }
     for (int s = 0; s < 3; s++) {
         for (int dj = 0; dj < 3; dj++) {
+            if (!((mask >> ((s * 3 + dj) * 3)) & 7u)) continue;
 #pragma unroll
             for (int di = 0; di < 3; di++) {
+                if (!((mask >> ((s * 3 + dj) * 3 + di)) & 1u)) continue;
                 const double *u[kShellNPT];
 #pragma unroll
                 for (int n = 0; n < kShellNPT; n++) {

@@ -238,6 +238,8 @@ struct PmlDev {
     double *d_sc = nullptr;          // [nc] column scaling 1 / sqrt|diag(Keff)|  (unknown y = x / sc)
     double *d_x = nullptr, *d_b = nullptr, *d_bext = nullptr, *d_r = nullptr, *d_rh = nullptr, *d_p = nullptr,
            *d_v = nullptr, *d_s = nullptr, *d_t = nullptr;
+    double *d_xp = nullptr;          // the increment of the step before the last one (starting guess: linear extrapolation)
+    bool extrapolate = true;
     int n_sc = 0;                    // dofs written back (unknown carriers + slaves)
     int32_t *d_sc_dof = nullptr, *d_sc_c = nullptr;
     double *d_part = nullptr;        // reduction partials

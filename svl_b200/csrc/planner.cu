@@ -1522,7 +1522,7 @@ static int plan_pml_nd(svlgpu_model *m, const std::vector<int32_t> &alias, const
     P.d_c_dof = dupload(m, c_dof); P.d_c_ptr = dupload(m, cnt); P.d_c_slot = dupload(m, slot); P.d_c_hf = dupload(m, c_hf);
     P.d_diag = dupload(m, dsoil); P.d_kms = dupload(m, kms); P.d_w = dupload(m, w);
     P.d_sc_dof = dupload(m, sc_dof); P.d_sc_c = dupload(m, sc_c);
-    double **vecs[] = {&P.d_x, &P.d_b, &P.d_bext, &P.d_r, &P.d_rh, &P.d_p, &P.d_v, &P.d_s, &P.d_t};
+    double **vecs[] = {&P.d_x, &P.d_b, &P.d_bext, &P.d_r, &P.d_rh, &P.d_p, &P.d_v, &P.d_s, &P.d_t, &P.d_xp};
     for (double **v : vecs) {
         *v = dalloc<double>(m, P.nc);
         if (!*v) { set_error("out of device memory (PML vectors)"); return 1; }
@@ -1533,6 +1533,7 @@ static int plan_pml_nd(svlgpu_model *m, const std::vector<int32_t> &alias, const
     CUDA_OK(cudaMallocHost(&P.h_scal, sizeof(double) * 8));
     const char *rt = getenv("SVLGPU_PML_RTOL");
     if (rt) P.rtol = atof(rt);
+    P.extrapolate = getenv("SVLGPU_PML_NO_EXTRAP") == nullptr;
     return 0;
 }
 static int plan_pml(svlgpu_model *m, const std::vector<int32_t> &alias, const std::vector<uint8_t> &node_is_pml,

@@ -470,6 +470,17 @@ static int post_exchange(svlgpu_model *m, int mode, double *out, const double *s
     }
 }
 
+// starting guess of the block solve: the increment extrapolated linearly from the last two steps, x0 = 2 x_n - x_{n-1}
+// (the increment of a resolved wave field is smooth in time: the residual of this guess is O((w dt)^2) of ||b|| instead of
+// O(w dt) for x_n alone, which saves BiCGStab iterations); element-wise, so replicas on several ranks stay bit-identical
+__global__ void k_pml_extrapolate(int n, double *x, double *xp) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const double xn = x[t];
+    x[t] = 2.0 * xn - xp[t];
+    xp[t] = xn;
+}
+
 int pml_step(svlgpu_model *m, const double *U, const double *Up, double *Un) {
     PmlDev &P = m->pml;
     const bool mg = P.multi;                              // several ranks: every rank runs the same sequence of collectives
@@ -485,7 +496,13 @@ int pml_step(svlgpu_model *m, const double *U, const double *Up, double *Un) {
                                                   U, Up, P.d_bext, P.d_w, P.d_b, P.d_part, raw);
     timer_end(m, 7);
     if (mg && post_exchange(m, -1, nullptr, nullptr, 0)) return 1;
-    // initial residual with the previous increment as the starting guess
+    // initial residual with the extrapolated (SVLGPU_PML_NO_EXTRAP: the previous) increment as the starting guess
+    if (P.extrapolate && P.solves >= 2 && P.nc) {
+        k_pml_extrapolate<<<(P.nc + 255) / 256, 256, 0, st>>>(P.nc, P.d_x, P.d_xp);
+        m->total_launches++;
+    } else if (P.extrapolate && P.nc) {
+        CUDA_OK(cudaMemcpyAsync(P.d_xp, P.d_x, sizeof(double) * P.nc, cudaMemcpyDeviceToDevice, st));
+    }
     elem_products(m, 0, P.d_ecd, P.d_A, P.d_x, nullptr, nullptr, P.d_sc, nullptr, 0, 0.0);
     int rr = S_RR0;
     timer_begin(m, 7);
