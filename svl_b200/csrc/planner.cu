@@ -1533,7 +1533,9 @@ static int plan_pml_nd(svlgpu_model *m, const std::vector<int32_t> &alias, const
     CUDA_OK(cudaMallocHost(&P.h_scal, sizeof(double) * 8));
     const char *rt = getenv("SVLGPU_PML_RTOL");
     if (rt) P.rtol = atof(rt);
-    P.extrapolate = getenv("SVLGPU_PML_NO_EXTRAP") == nullptr;
+    // measured neutral (profiles/r3m: 2.91 BiCGStab iterations per step either way at 120^3 + PML -- the count is set by the
+    // batch granularity of the convergence test, not by the starting residual): off unless asked for
+    P.extrapolate = getenv("SVLGPU_PML_EXTRAP") != nullptr;
     return 0;
 }
 static int plan_pml(svlgpu_model *m, const std::vector<int32_t> &alias, const std::vector<uint8_t> &node_is_pml,

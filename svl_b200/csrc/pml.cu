@@ -496,7 +496,7 @@ int pml_step(svlgpu_model *m, const double *U, const double *Up, double *Un) {
                                                   U, Up, P.d_bext, P.d_w, P.d_b, P.d_part, raw);
     timer_end(m, 7);
     if (mg && post_exchange(m, -1, nullptr, nullptr, 0)) return 1;
-    // initial residual with the extrapolated (SVLGPU_PML_NO_EXTRAP: the previous) increment as the starting guess
+    // initial residual with the previous increment (SVLGPU_PML_EXTRAP: the linearly extrapolated one) as the starting guess
     if (P.extrapolate && P.solves >= 2 && P.nc) {
         k_pml_extrapolate<<<(P.nc + 255) / 256, 256, 0, st>>>(P.nc, P.d_x, P.d_xp);
         m->total_launches++;
