@@ -266,9 +266,24 @@ class DeviceModel:
         self._ck(self.L.svlgpu_sync(self.h))
 
     def step_host(self, k, amplitudes, rec=0, row=None):
-        amp = np.ascontiguousarray(amplitudes, np.float64)
-        self._ck(self.L.svlgpu_step_host(self.h, k, _d(amp), len(amp), rec, _d(row) if row is not None else None,
-                                         len(row) if row is not None else 0))
+        # per-step call: keep the marshalling off the path (one persistent amplitude buffer, the row pointer cached per array)
+        n = len(amplitudes)
+        buf = getattr(self, "_amp_buf", None)
+        if buf is None or len(buf) < max(n, 1):
+            buf = self._amp_buf = np.zeros(max(n, 1))
+            self._amp_ptr = buf.ctypes.data_as(_dp)
+        if n:
+            buf[:n] = amplitudes
+        if row is None:
+            rp, rl = None, 0
+        else:
+            cached = getattr(self, "_row_cache", None)
+            if cached is None or cached[0] is not row:
+                assert row.dtype == np.float64 and row.flags.c_contiguous
+                cached = self._row_cache = (row, row.ctypes.data_as(_dp), len(row))
+            rp, rl = cached[1], cached[2]
+        if self.L.svlgpu_step_host(self.h, k, self._amp_ptr, n, rec, rp, rl):
+            raise SvlError(self._err())
 
     def run(self, nt=None):
         nt = nt or self.m.nt

@@ -1409,7 +1409,7 @@ struct NbrArgs {
     const long long *chunk_off;
     int stride, mode;
 };
-template <int ND>
+template <int ND, int UNR>
 __global__ void __launch_bounds__(128, 6) k_nbr_nodes(const NbrArgs p) {
     __shared__ double T[kNbrSlots * ND * ND + 2 * ND];
     const int c = p.chunk_cls[blockIdx.x];
@@ -1429,6 +1429,9 @@ __global__ void __launch_bounds__(128, 6) k_nbr_nodes(const NbrArgs p) {
         for (int a = 0; a < ND; a++) F[n][a] = 0.0;
     }
     const int32_t *nb = p.nbr + p.chunk_off[blockIdx.x] + threadIdx.x;
+    // UNR slots per trip: the index loads of the next slots go out before the displacement loads of this one return (the kernel
+    // is bound by gather latency, profiles/r3n: 25 % DRAM, 15 % FP64, L1 hit rate 86 %)
+#pragma unroll UNR
     for (int s = 0; s < nn; s++) {
         int idx[kNbrNPT];
 #pragma unroll
@@ -1648,6 +1651,66 @@ __global__ void __launch_bounds__(128) k_drm_pw(int n, const int32_t *ptr, const
     }
 #pragma unroll
     for (int r = 0; r < ND; r++) F[(long long)row * ND + r] = factor * f[r];
+}
+// The same, fused: wave value per ENTRY (about ten exp per row: cheaper than a kernel of its own with a buffer round trip),
+// row force, and its application in one launch -- phase 0: rows on interface nodes (hF -= F, before the exchange);
+// phase 1: all other rows (U_{n+1} += sign F / Keff).  The forces depend on the step index only, so evaluating them where
+// they are applied costs nothing extra; three launches and two buffers per step become one launch (the side-stream
+// prefetch never overlapped with the register-saturating stencil kernel anyway: DESIGN.md section 5).  Same arithmetic
+// and summation order as k_drm_field_pw + k_drm_pw + k_drm_apply: bit-identical forces.
+template <int ND>
+__global__ void __launch_bounds__(128) k_drm_pw_fused(int n, int phase, const int32_t *ptr, const int2 *cb, const uint8_t *ext, const double *sc,
+                                                     const double *wdict, double amp, double f0, double t0, double tnow, double factor,
+                                                     const int32_t *dof0, const int32_t *target, const double *rkinv, double sign,
+                                                     double *Un, double *hF) {
+    constexpr int NS = (ND == 3) ? 4 : 2;
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const int tg = target ? target[row] : -1;
+    if ((phase == 0) != (tg >= 0)) return;
+    double f[ND];
+#pragma unroll
+    for (int r = 0; r < ND; r++) f[r] = 0.0;
+    const int q1 = ptr[row + 1];
+    int q = ptr[row];
+    for (; q + 4 <= q1; q += 4) {
+        int2 e[4];
+#pragma unroll
+        for (int z = 0; z < 4; z++) e[z] = cb[q + z];
+        double sv[4];
+        double2 w2[4];
+        double w3[4];
+#pragma unroll
+        for (int z = 0; z < 4; z++) {
+            const double val = amp * ricker_disp(tnow - t0 - sc[e[z].x], f0);
+            sv[z] = ext[e[z].x] ? -val : val;
+            const double *w = wdict + (long long)e[z].y * NS;
+            w2[z] = *reinterpret_cast<const double2 *>(w);
+            if (ND == 3) w3[z] = w[2];
+        }
+#pragma unroll
+        for (int z = 0; z < 4; z++) {
+            f[0] += w2[z].x * sv[z];
+            f[1] += w2[z].y * sv[z];
+            if (ND == 3) f[2] += w3[z] * sv[z];
+        }
+    }
+    for (; q < q1; q++) {
+        const int2 e = cb[q];
+        const double val = amp * ricker_disp(tnow - t0 - sc[e.x], f0);
+        const double sv = ext[e.x] ? -val : val;
+        const double *w = wdict + (long long)e.y * NS;
+#pragma unroll
+        for (int r = 0; r < ND; r++) f[r] += w[r] * sv;
+    }
+    if (tg >= 0) {
+#pragma unroll
+        for (int r = 0; r < ND; r++) hF[tg + r] -= factor * f[r];
+        return;
+    }
+    const int d = dof0[row];
+#pragma unroll
+    for (int r = 0; r < ND; r++) Un[d + r] += sign * (rkinv ? rkinv[(long long)row * ND + r] : 1.0) * (factor * f[r]);
 }
 // phase 0: rows on interface nodes (hF -= F, before the exchange); phase 1: all other rows (U_{n+1} += F / Keff)
 __global__ void k_drm_apply(int n, int nd, int phase, const int32_t *dof0, const int32_t *target, const double *F,
@@ -1912,7 +1975,11 @@ static int launch_generic_elements(svlgpu_model *m, const double *U, int commit)
 static int launch_node_update(svlgpu_model *m, const double *U, const double *Up, double *Un, int mode) {
     if (upload_dom_tables(m)) return 1;
     bool shell_on_side = false;
-    if (m->overlap && !m->kernel_timing) {           // side stream 1 may start once U_n is final
+    // The shell classes run on side stream 1 beside the bulk kernel -- except in the per-step host call (svlgpu_step_host):
+    // there the fork / join costs four more API calls per step on the critical path of the host round trip and buys nothing
+    // measurable (the stencil kernel saturates the register file; measured e2e 5.54 -> 5.81e10 without the side streams)
+    const bool side_ok = m->overlap && !m->kernel_timing && !m->step_amp;
+    if (side_ok) {                                   // side stream 1 may start once U_n is final
         CUDA_OK(cudaEventRecord(m->ev_fork, m->stream));
         CUDA_OK(cudaStreamWaitEvent(m->side[1], m->ev_fork, 0));
     }
@@ -1950,7 +2017,7 @@ static int launch_node_update(svlgpu_model *m, const double *U, const double *Up
                 p.chunk_cls = mode == 0 ? b.d_shell_cls : b.d_shell_all_cls;
                 const int nchunks = mode == 0 ? b.n_shell_chunks : b.n_shell_all;
                 p.dof0 = b.dof0; p.nx = b.nx; p.ny = b.ny; p.nz = b.nz; p.mode = mode; p.target = nullptr; p.hF = nullptr;
-                cudaStream_t st = (m->overlap && !m->kernel_timing) ? m->side[1] : m->stream;
+                cudaStream_t st = side_ok ? m->side[1] : m->stream;
                 timer_begin(m, 4);
                 if (m->shell_lowreg) k_stencil3_shell<true><<<nchunks, 128, 0, st>>>(p);
                 else k_stencil3_shell<false><<<nchunks, 128, 0, st>>>(p);
@@ -1975,8 +2042,9 @@ static int launch_node_update(svlgpu_model *m, const double *U, const double *Up
         a.dof0 = m->nbr.d_dof0; a.nbr = m->nbr.d_nbr; a.chunk_off = (const long long *)m->nbr.d_chunk_off;
         a.stride = m->nbr.stride; a.mode = mode;
         timer_begin(m, 2);
-        if (m->ndim == 3) k_nbr_nodes<3><<<m->nbr.n_chunks, 128, 0, m->stream>>>(a);
-        else k_nbr_nodes<2><<<m->nbr.n_chunks, 128, 0, m->stream>>>(a);
+        static const int unr = getenv("SVLGPU_NBR_UNROLL") ? atoi(getenv("SVLGPU_NBR_UNROLL")) : 1;
+        if (m->ndim == 3) { if (unr == 3) k_nbr_nodes<3, 3><<<m->nbr.n_chunks, 128, 0, m->stream>>>(a); else k_nbr_nodes<3, 1><<<m->nbr.n_chunks, 128, 0, m->stream>>>(a); }
+        else { if (unr == 3) k_nbr_nodes<2, 3><<<m->nbr.n_chunks, 128, 0, m->stream>>>(a); else k_nbr_nodes<2, 1><<<m->nbr.n_chunks, 128, 0, m->stream>>>(a); }
         timer_end(m, 2);
         m->total_launches++;
     }
@@ -2155,6 +2223,7 @@ static int drm_compute(svlgpu_model *m, DrmDev &d, int k, cudaStream_t st) {
 static int drm_prefetch(svlgpu_model *m, int knext) {
     for (auto &d : m->drm_dev) {
         if (!d.n_nodes || (!d.analytic && knext >= d.nt)) continue;
+        if (d.fused && !m->graph_capturing) continue;          // evaluated where it is applied (k_drm_pw_fused)
         const int b = knext & 1;
         if (drm_compute(m, d, knext, m->side[0])) return 1;
         CUDA_OK(cudaEventRecord(d.ev_ready[b], m->side[0]));
@@ -2189,6 +2258,15 @@ static int launch_external(svlgpu_model *m, int k, const double *dev_amp, double
         if (!d.n_nodes) continue;
         const int b = k & 1;
         timer_begin(m, 5);
+        if (d.fused && !m->graph_capturing) {
+            const int32_t *tgt = halo ? d.d_target : nullptr;
+            const double *rk = kinv ? d.d_rkinv : nullptr;
+            if (m->ndim == 3) k_drm_pw_fused<3><<<(d.n_nodes + 127) / 128, 128, 0, m->stream>>>(d.n_nodes, phase, d.d_row_ptr, (const int2 *)d.d_col_blk, d.d_ext, d.d_sc, d.d_wdict, d.amp, d.f0, d.t0, k * m->dt, d.factor, d.d_node_dof0, tgt, rk, sign, Un, m->halo.d_hF);
+            else k_drm_pw_fused<2><<<(d.n_nodes + 127) / 128, 128, 0, m->stream>>>(d.n_nodes, phase, d.d_row_ptr, (const int2 *)d.d_col_blk, d.d_ext, d.d_sc, d.d_wdict, d.amp, d.f0, d.t0, k * m->dt, d.factor, d.d_node_dof0, tgt, rk, sign, Un, m->halo.d_hF);
+            timer_end(m, 5);
+            m->total_launches++;
+            continue;
+        }
         if (d.buf_k[b] != k) { if (drm_compute(m, d, k, m->stream)) return 1; }        // not precomputed: do it now
         else if (d.ev_valid[b]) cudaStreamWaitEvent(m->stream, d.ev_ready[b], 0);
         k_drm_apply<<<(d.n_nodes * m->ndim + 127) / 128, 128, 0, m->stream>>>(d.n_nodes, m->ndim, phase, d.d_node_dof0,
@@ -2207,7 +2285,10 @@ static int step_once(svlgpu_model *m, int k, const double *dev_amp) {
     const double *U = m->d_U[m->cur], *Up = m->d_U[m->prev];
     double *Un = m->d_U[m->next];
     m->k_of_step = k;
-    if (m->overlap && !m->drm_dev.empty() && !m->kernel_timing) {
+    m->step_amp = dev_amp;
+    bool drm_ahead = false;                                   // some DRM load still uses the two-step (field, force) kernels
+    for (auto &d : m->drm_dev) drm_ahead = drm_ahead || !(d.fused && !m->graph_capturing);
+    if (m->overlap && drm_ahead && !m->kernel_timing && !dev_amp) {
         // DRM forces of step k+1 are computed on side stream 0 while this step runs; its buffer was last read
         // by step k-1, which is complete on the main stream at this point.  They are enqueued BEFORE the bulk
         // kernels: enqueued after them they only get SM slots when the stencil drains and the step serialises

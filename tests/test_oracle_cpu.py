@@ -441,6 +441,9 @@ def test_bench_reads_the_hbm_peak_from_any_reasonable_measured_peaks_schema():
     assert b.pick_hbm_peak({"peaks": {"hbm_tb_s": 6.54, "bf16_tf_s": 1600}})[0] == pytest.approx(6540.0)
     assert b.pick_hbm_peak({"copy_bandwidth_GBps": 6600, "cublas_bf16_TFLOPs": 1700})[0] == 6600.0
     assert b.pick_hbm_peak({"bf16_tflops": 1700}) is None and b.pick_hbm_peak({}) is None
+    # a key that names HBM wins over an unrelated "*bandwidth*" one, and an out-of-range first candidate does not end the search
+    assert b.pick_hbm_peak({"l2_bandwidth_gbs": 9000.0, "hbm_gbs": 6551.0})[0] == 6551.0
+    assert b.pick_hbm_peak({"nvlink_bandwidth_gbs": 900.0, "dram_copy_gbs": 6500.0})[0] == 6500.0
 
 
 def test_interior_hex8_stencil_is_a_sum_of_tensor_products(oracle):
