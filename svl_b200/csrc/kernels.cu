@@ -1652,8 +1652,8 @@ __global__ void __launch_bounds__(128) k_drm_pw(int n, const int32_t *ptr, const
 #pragma unroll
     for (int r = 0; r < ND; r++) F[(long long)row * ND + r] = factor * f[r];
 }
-// The same, fused: wave value per ENTRY (about ten exp per row: cheaper than a kernel of its own with a buffer round trip),
-// row force, and its application in one launch -- phase 0: rows on interface nodes (hF -= F, before the exchange);
+// The same, fused (SVLGPU_DRM_FUSE; measured slower at 320^3 -- ten FP64 exp per row cost more than two launches and a buffer
+// round trip save -- so off by default): wave value per ENTRY, row force, and its application in one launch -- phase 0: rows on interface nodes (hF -= F, before the exchange);
 // phase 1: all other rows (U_{n+1} += sign F / Keff).  The forces depend on the step index only, so evaluating them where
 // they are applied costs nothing extra; three launches and two buffers per step become one launch (the side-stream
 // prefetch never overlapped with the register-saturating stencil kernel anyway: DESIGN.md section 5).  Same arithmetic
@@ -2042,7 +2042,8 @@ static int launch_node_update(svlgpu_model *m, const double *U, const double *Up
         a.dof0 = m->nbr.d_dof0; a.nbr = m->nbr.d_nbr; a.chunk_off = (const long long *)m->nbr.d_chunk_off;
         a.stride = m->nbr.stride; a.mode = mode;
         timer_begin(m, 2);
-        static const int unr = getenv("SVLGPU_NBR_UNROLL") ? atoi(getenv("SVLGPU_NBR_UNROLL")) : 1;
+        // 3 slots per trip: 0.409 -> 0.390 ms (160^3, lattice order) and 0.660 -> 0.569 ms (random numbering), profiles/r3o
+        static const int unr = getenv("SVLGPU_NBR_UNROLL") ? atoi(getenv("SVLGPU_NBR_UNROLL")) : 3;
         if (m->ndim == 3) { if (unr == 3) k_nbr_nodes<3, 3><<<m->nbr.n_chunks, 128, 0, m->stream>>>(a); else k_nbr_nodes<3, 1><<<m->nbr.n_chunks, 128, 0, m->stream>>>(a); }
         else { if (unr == 3) k_nbr_nodes<2, 3><<<m->nbr.n_chunks, 128, 0, m->stream>>>(a); else k_nbr_nodes<2, 1><<<m->nbr.n_chunks, 128, 0, m->stream>>>(a); }
         timer_end(m, 2);

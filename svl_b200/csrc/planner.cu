@@ -1209,7 +1209,9 @@ int plan_and_upload(svlgpu_model *m) {
                 }
                 dd.d_wdict = dupload(m, wd); dd.d_sc = dupload(m, sc);
                 dd.d_sval[0] = dalloc<double>(m, (size_t)nn + 2); dd.d_sval[1] = dalloc<double>(m, (size_t)nn + 2);
-                dd.fused = getenv("SVLGPU_DRM_NO_FUSE") == nullptr;
+                // one fused launch (wave value per entry + force + application) was measured SLOWER at 320^3: 0.110 vs 0.064 ms per
+                // step for the DRM layer -- ten FP64 exp per row instead of one per node (profiles/r3o); kept for small partitions
+                dd.fused = getenv("SVLGPU_DRM_FUSE") != nullptr;
             }
             for (int c = 0; c < 3; c++) { dd.dir[c] = dl.dir[c]; dd.pol[c] = dl.pol[c]; dd.xref[c] = dl.xref[c]; }
             dd.c = dl.c; dd.f0 = dl.f0; dd.t0 = dl.t0; dd.amp = dl.amp;
