@@ -605,12 +605,17 @@ def write_reference_partitions(m: Model, epart, nparts: int, directory: str, nam
             if L["name"] == "POINTLOAD":
                 lst = sorted(t for t in L["attributes"]["list"] if t in nset and t not in taken_load[l])
                 taken_load[l].update(lst)
+            elif L["name"] == "SUPPORTMOTION":          # every partition that holds the node moves it (SeismoVLAB.py:211-216)
+                lst = sorted(t for t in L["attributes"]["list"] if t in nset)
             else:
                 lst = sorted(t for t in L["attributes"]["list"] if t in eset)
             if lst:
                 loads[l] = {"name": L["name"], "attributes": dict(L["attributes"], list=lst)}
         if loads:
             K["Loads"] = loads
+        sup = {t: v for t, v in J.get("Supports", {}).items() if int(t) in nset}      # SeismoVLAB.py:124-128
+        if sup:
+            K["Supports"] = sup
         C = J["Combinations"]["1"]
         keep = [(l, f) for l, f in zip(C["attributes"]["load"], C["attributes"]["factor"]) if str(l) in loads]
         K["Combinations"] = {"1": {"name": C["name"], "attributes": (

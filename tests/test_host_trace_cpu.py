@@ -64,10 +64,10 @@ import numpy as np, cases
 from svl_b200 import capi, partition as P
 case, nparts, rank, how = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
 capi.LIB_PATH = {shim!r}                       # the recording stand-in instead of svl_b200/libsvlgpu.so (this test only)
-m = cases.CASES[case]()
+m = (cases.CASES.get(case) or cases.REACTION_CASE_FUNCS[case])()
 ep = eval(how)
 s = P.split_model(m, ep, nparts)[rank]
-d = capi.DeviceModel(s, comm=(rank, nparts, b"\x5a" * 128))
+d = capi.DeviceModel(s, comm=(rank, nparts, b"\x5a" * 128), fields=(0, 3) if case in cases.REACTION_CASE_FUNCS else (0,))
 d.close()
 """
 
@@ -100,8 +100,10 @@ def _canon(lines):
             out["recorders"].append((kv["field"], kv["nnodes"], kv["nodes"]))
         elif name == "add_drm_load":
             out["drm"] = kv
-        elif name == "set_option" and "pml_collective" in l:
+        elif name == "set_option" and ("pml_collective" in l or "reaction_collective" in l):
             out["options"].add(l)
+        elif name == "add_support_motion":
+            out.setdefault("supports", set()).add((kv["node"], kv["dof"], kv["nt"], kv["factor"], kv["series"]))
     return out
 
 
@@ -112,6 +114,9 @@ def _canon(lines):
     ("drm_box", 4, "P.block_epart((6, 6, 5), (2, 2, 1))"),
     ("pml3d", 2, "P.centroid_epart(m, (1, 1, 2))"),
     ("pml2d", 3, "np.random.default_rng(5).integers(0, 3, m.n_elem).astype(np.int32)"),
+    # moving supports on every partition that holds the node, REACTION recorders and the collective reaction pass
+    ("support_column", 2, "P.block_epart((3, 3, 6), (2, 1, 1))"),
+    ("reaction_box", 4, "P.block_epart((4, 3, 6), (2, 2, 1))"),
 ])
 def test_driver_on_reference_rank_files_matches_python_partitioner_at_the_c_abi(shim, tmp_path, case, nparts, how):
     """Several ranks.  Left: write_reference_partitions (global numbering, masters travel with slaves only, as createPartitions
@@ -119,13 +124,15 @@ def test_driver_on_reference_rank_files_matches_python_partitioner_at_the_c_abi(
     partition directory; svlgpu_comm_init).  Right: partition.split_model -> capi.DeviceModel, the pair the GPU multi-rank
     parity runs use.  Both must hand every rank the same nodes, numbering, elements, constraints, halo lists, loads,
     recorders, options and communicator arguments."""
-    m = cases.CASES[case]()
+    reac = case in cases.REACTION_CASE_FUNCS
+    m = (cases.CASES.get(case) or cases.REACTION_CASE_FUNCS[case])()
     ep = eval(how)
-    part = M.write_reference_partitions(m, ep, nparts, str(tmp_path), "Case", "Run")
+    resp = ("disp", "reaction") if reac else ("disp",)
+    part = M.write_reference_partitions(m, ep, nparts, str(tmp_path), "Case", "Run", resp=resp)
     left = run_driver(shim, part, "Case.1.$.json", str(tmp_path / "cpp.trace"), nparts)
     assert not [f for f in os.listdir(part) if f.startswith(".svlgpu_nccl_id")]          # rank 0 removed the id file
     # the same rank files with their tables in binary sidecars, written straight from the arrays: identical calls
-    M.write_reference_partitions(m, ep, nparts, str(tmp_path), "Case", "Run", binary=True)
+    M.write_reference_partitions(m, ep, nparts, str(tmp_path), "Case", "Run", resp=resp, binary=True)
     assert run_driver(shim, part, "Case.1.$.bin.json", str(tmp_path / "cppbin.trace"), nparts) == left
     for rank in range(nparts):
         env = dict(os.environ, SVLGPU_TRACE=str(tmp_path / "py.trace"), RANK=str(rank))
@@ -135,8 +142,13 @@ def test_driver_on_reference_rank_files_matches_python_partitioner_at_the_c_abi(
         right = open(str(tmp_path / "py.trace") + f".{rank}").read().splitlines()
         a, b = _canon(left[rank]), _canon(right)
         for key in ("create", "set_nodes", "finalize", "comm_init", "materials", "elements", "constraints", "halos", "loads",
-                    "options"):
+                    "options", "supports"):
             assert a.get(key) == b.get(key), (rank, key)
+        if reac:
+            assert any("reaction_collective" in o for o in a["options"])     # also on a rank that records no reaction itself
+            assert {r[0] for r in a["recorders"]} <= {"0", "3"}
+        if case == "support_column":
+            assert a["supports"]
         # recorders differ by design: the reference's files list a recorded node in EVERY partition that holds it
         # (SeismoVLAB.py:237-246), split_model hands it to its owner only
         assert sum(int(r[1]) for r in a["recorders"]) >= sum(int(r[1]) for r in b["recorders"])
@@ -161,14 +173,14 @@ d.close()
 
 
 @pytest.mark.parametrize("case", ["kat444", "kat444_masses", "pml2d", "pml3d", "lysmer_column", "hex8_layered_rayleigh", "j2ps_area",
-                                  "drm_box", "drm_area", "F06", "F11"])
+                                  "drm_box", "drm_area", "support_column", "support_area", "F06", "F11"])
 def test_cpp_driver_and_python_binding_hand_the_device_the_same_model(shim, tmp_path, case):
     """One partition file, two front ends: `SeismoVLAB_gpu.exe` (svl_host.cpp UpdateMesh + Initialize) and
     `model.read_reference_json` + `capi.DeviceModel` (what the GPU parity tests drive).  Nodes, numbering, materials, elements,
     constraints, Rayleigh groups, nodal masses, loads, recorder nodes and dt reach the C ABI identically -- also for the
     reference's own pre-processor output (fixtures F06: Rayleigh + dashpots under Newmark, F11: EQUAL ties)."""
-    if case in cases.CASES:
-        m = cases.CASES[case]()
+    if case in cases.CASES or case in cases.REACTION_CASE_FUNCS:
+        m = (cases.CASES.get(case) or cases.REACTION_CASE_FUNCS[case])()
         part = M.write_reference_json(m, str(tmp_path), "Case", "Run")
         jp, pattern = os.path.join(part, "Case.1.0.json"), "Case.1.$.json"
     else:
@@ -195,8 +207,10 @@ def test_cpp_driver_and_python_binding_hand_the_device_the_same_model(shim, tmp_
     assert r.returncode == 0, r.stdout + r.stderr
     a = _canon(open(str(tmp_path / "cpp.trace")).read().splitlines())
     b = _canon(open(str(tmp_path / "py.trace")).read().splitlines())
-    for key in ("create", "set_nodes", "finalize", "materials", "elements", "constraints", "rayleigh", "loads", "drm"):
+    for key in ("create", "set_nodes", "finalize", "materials", "elements", "constraints", "rayleigh", "loads", "drm", "supports"):
         assert a.get(key) == b.get(key), key
+    if case.startswith("support"):
+        assert len(a["supports"]) == len({(n, d) for n, d, _, _ in m.supports})      # Supports{} + SUPPORTMOTION load -> one call per dof
     assert a["recorders"][0] == b["recorders"][0]
     if case.startswith("drm"):
         assert a.get("drm")
