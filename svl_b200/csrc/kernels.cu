@@ -1652,6 +1652,52 @@ __global__ void __launch_bounds__(128) k_drm_pw(int n, const int32_t *ptr, const
 #pragma unroll
     for (int r = 0; r < ND; r++) F[(long long)row * ND + r] = factor * f[r];
 }
+// k_drm_pw with the application folded in (models without interface / PML rows): U_{n+1}[row dofs] += sign F / Keff straight
+// from the registers -- no F buffer round trip, no k_drm_apply launch, and no side-stream prefetch (which never overlapped
+// with the stencil kernel anyway).  Same products in the same order as k_drm_pw + k_drm_apply.
+template <int ND>
+__global__ void __launch_bounds__(128) k_drm_pw_apply(int n, const int32_t *ptr, const int2 *cb, const double *sval, const double *wdict,
+                                                     double factor, const int32_t *dof0, const double *rkinv, double sign, double *Un) {
+    constexpr int NS = (ND == 3) ? 4 : 2;
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    double f[ND];
+#pragma unroll
+    for (int r = 0; r < ND; r++) f[r] = 0.0;
+    const int q1 = ptr[row + 1];
+    int q = ptr[row];
+    for (; q + 4 <= q1; q += 4) {
+        int2 e[4];
+#pragma unroll
+        for (int z = 0; z < 4; z++) e[z] = cb[q + z];
+        double sv[4];
+        double2 w2[4];
+        double w3[4];
+#pragma unroll
+        for (int z = 0; z < 4; z++) {
+            sv[z] = sval[e[z].x];
+            const double *w = wdict + (long long)e[z].y * NS;
+            w2[z] = *reinterpret_cast<const double2 *>(w);
+            if (ND == 3) w3[z] = w[2];
+        }
+#pragma unroll
+        for (int z = 0; z < 4; z++) {
+            f[0] += w2[z].x * sv[z];
+            f[1] += w2[z].y * sv[z];
+            if (ND == 3) f[2] += w3[z] * sv[z];
+        }
+    }
+    for (; q < q1; q++) {
+        const int2 e = cb[q];
+        const double sv = sval[e.x];
+        const double *w = wdict + (long long)e.y * NS;
+#pragma unroll
+        for (int r = 0; r < ND; r++) f[r] += w[r] * sv;
+    }
+    const int d = dof0[row];
+#pragma unroll
+    for (int r = 0; r < ND; r++) Un[d + r] += sign * (rkinv ? rkinv[(long long)row * ND + r] : 1.0) * (factor * f[r]);
+}
 // The same, fused (SVLGPU_DRM_FUSE; measured slower at 320^3 -- ten FP64 exp per row cost more than two launches and a buffer
 // round trip save -- so off by default): wave value per ENTRY, row force, and its application in one launch -- phase 0: rows on interface nodes (hF -= F, before the exchange);
 // phase 1: all other rows (U_{n+1} += sign F / Keff).  The forces depend on the step index only, so evaluating them where
@@ -2225,6 +2271,7 @@ static int drm_prefetch(svlgpu_model *m, int knext) {
     for (auto &d : m->drm_dev) {
         if (!d.n_nodes || (!d.analytic && knext >= d.nt)) continue;
         if (d.fused && !m->graph_capturing) continue;          // evaluated where it is applied (k_drm_pw_fused)
+        if (d.inline_apply && !(m->halo.active || m->pml.present) && !m->graph_capturing) continue;   // k_drm_pw_apply
         const int b = knext & 1;
         if (drm_compute(m, d, knext, m->side[0])) return 1;
         CUDA_OK(cudaEventRecord(d.ev_ready[b], m->side[0]));
@@ -2268,6 +2315,16 @@ static int launch_external(svlgpu_model *m, int k, const double *dev_amp, double
             m->total_launches++;
             continue;
         }
+        if (d.inline_apply && !halo && !m->graph_capturing) {
+            // wave values of step k, then force + application in one kernel (k_drm_pw_apply); phase 0 has returned above (!halo)
+            k_drm_field_pw<<<(d.n_all + 255) / 256, 256, 0, m->stream>>>(d.n_all, d.d_ext, d.d_sc, d.amp, d.f0, d.t0, m->dt, k, nullptr, 0, d.d_sval[0]);
+            const double *rk = kinv ? d.d_rkinv : nullptr;
+            if (m->ndim == 3) k_drm_pw_apply<3><<<(d.n_nodes + 127) / 128, 128, 0, m->stream>>>(d.n_nodes, d.d_row_ptr, (const int2 *)d.d_col_blk, d.d_sval[0], d.d_wdict, d.factor, d.d_node_dof0, rk, sign, Un);
+            else k_drm_pw_apply<2><<<(d.n_nodes + 127) / 128, 128, 0, m->stream>>>(d.n_nodes, d.d_row_ptr, (const int2 *)d.d_col_blk, d.d_sval[0], d.d_wdict, d.factor, d.d_node_dof0, rk, sign, Un);
+            timer_end(m, 5);
+            m->total_launches += 2;
+            continue;
+        }
         if (d.buf_k[b] != k) { if (drm_compute(m, d, k, m->stream)) return 1; }        // not precomputed: do it now
         else if (d.ev_valid[b]) cudaStreamWaitEvent(m->stream, d.ev_ready[b], 0);
         k_drm_apply<<<(d.n_nodes * m->ndim + 127) / 128, 128, 0, m->stream>>>(d.n_nodes, m->ndim, phase, d.d_node_dof0,
@@ -2288,7 +2345,8 @@ static int step_once(svlgpu_model *m, int k, const double *dev_amp) {
     m->k_of_step = k;
     m->step_amp = dev_amp;
     bool drm_ahead = false;                                   // some DRM load still uses the two-step (field, force) kernels
-    for (auto &d : m->drm_dev) drm_ahead = drm_ahead || !(d.fused && !m->graph_capturing);
+    for (auto &d : m->drm_dev)
+        drm_ahead = drm_ahead || !((d.fused || (d.inline_apply && !(m->halo.active || m->pml.present))) && !m->graph_capturing);
     if (m->overlap && drm_ahead && !m->kernel_timing && !dev_amp) {
         // DRM forces of step k+1 are computed on side stream 0 while this step runs; its buffer was last read
         // by step k-1, which is complete on the main stream at this point.  They are enqueued BEFORE the bulk

@@ -165,6 +165,7 @@ struct DrmDev {
     double *d_wdict = nullptr;       // [nblk][4 | 2]  B . pol
     double *d_sc = nullptr;          // [n_all] (x - xref) . dir / c
     double *d_sval[2] = {nullptr, nullptr};   // [n_all] +-amp * ricker of step k in buffer k & 1
+    bool inline_apply = false;       // k_drm_pw_apply: force + application in one kernel on the main stream (no interface rows)
     bool fused = false;              // k_drm_pw_fused: wave value, row force and application in one launch (default for plane waves)
 };
 

@@ -1212,6 +1212,7 @@ int plan_and_upload(svlgpu_model *m) {
                 // one fused launch (wave value per entry + force + application) was measured SLOWER at 320^3: 0.110 vs 0.064 ms per
                 // step for the DRM layer -- ten FP64 exp per row instead of one per node (profiles/r3o); kept for small partitions
                 dd.fused = getenv("SVLGPU_DRM_FUSE") != nullptr;
+                dd.inline_apply = getenv("SVLGPU_DRM_NO_INLINE") == nullptr;
             }
             for (int c = 0; c < 3; c++) { dd.dir[c] = dl.dir[c]; dd.pol[c] = dl.pol[c]; dd.xref[c] = dl.xref[c]; }
             dd.c = dl.c; dd.f0 = dl.f0; dd.t0 = dl.t0; dd.amp = dl.amp;
