@@ -329,7 +329,9 @@ int svlgpu_step_host(svlgpu_model *m, int k, const double *amplitudes, int nload
         REQUIRE(row_len == r.width && r.rows < r.max_rows, "step_host: row length differs from the recorder width");
         m->mirror_rec = rec;
     }
+    m->host_step = true;
     const int rc = run_steps(m, k, k + 1, damp);
+    m->host_step = false;
     m->mirror_rec = -1;
     if (rc) return 1;
     cudaError_t e = cudaStreamSynchronize(m->stream);

@@ -2022,9 +2022,9 @@ static int launch_node_update(svlgpu_model *m, const double *U, const double *Up
     if (upload_dom_tables(m)) return 1;
     bool shell_on_side = false;
     // The shell classes run on side stream 1 beside the bulk kernel -- except in the per-step host call (svlgpu_step_host):
-    // there the fork / join costs four more API calls per step on the critical path of the host round trip and buys nothing
-    // measurable (the stencil kernel saturates the register file; measured e2e 5.54 -> 5.81e10 without the side streams)
-    const bool side_ok = m->overlap && !m->kernel_timing && !m->step_amp;
+    // there the fork / join costs four more API calls per step on the critical path of the host round trip (measured e2e
+    // 5.54 -> 5.81e10 without the side streams)
+    const bool side_ok = m->overlap && !m->kernel_timing && !m->host_step;
     if (side_ok) {                                   // side stream 1 may start once U_n is final
         CUDA_OK(cudaEventRecord(m->ev_fork, m->stream));
         CUDA_OK(cudaStreamWaitEvent(m->side[1], m->ev_fork, 0));
@@ -2271,7 +2271,7 @@ static int drm_prefetch(svlgpu_model *m, int knext) {
     for (auto &d : m->drm_dev) {
         if (!d.n_nodes || (!d.analytic && knext >= d.nt)) continue;
         if (d.fused && !m->graph_capturing) continue;          // evaluated where it is applied (k_drm_pw_fused)
-        if (d.inline_apply && !(m->halo.active || m->pml.present) && !m->graph_capturing) continue;   // k_drm_pw_apply
+        if (d.inline_apply && m->host_step && !(m->halo.active || m->pml.present) && !m->graph_capturing) continue;   // k_drm_pw_apply
         const int b = knext & 1;
         if (drm_compute(m, d, knext, m->side[0])) return 1;
         CUDA_OK(cudaEventRecord(d.ev_ready[b], m->side[0]));
@@ -2315,7 +2315,10 @@ static int launch_external(svlgpu_model *m, int k, const double *dev_amp, double
             m->total_launches++;
             continue;
         }
-        if (d.inline_apply && !halo && !m->graph_capturing) {
+        // Bulk stepping (svlgpu_step over many steps) keeps the two-kernel form prefetched on a side stream: part of it hides in
+        // the stencil kernel's tail (0.513 vs 0.528 ms per step).  The per-step host call takes the inline form: fewer launches
+        // and no stream fork on the critical path of the host round trip (e2e 6.00 -> 6.20e10), profiles/r3r.
+        if (d.inline_apply && m->host_step && !halo && !m->graph_capturing) {
             // wave values of step k, then force + application in one kernel (k_drm_pw_apply); phase 0 has returned above (!halo)
             k_drm_field_pw<<<(d.n_all + 255) / 256, 256, 0, m->stream>>>(d.n_all, d.d_ext, d.d_sc, d.amp, d.f0, d.t0, m->dt, k, nullptr, 0, d.d_sval[0]);
             const double *rk = kinv ? d.d_rkinv : nullptr;
@@ -2346,8 +2349,8 @@ static int step_once(svlgpu_model *m, int k, const double *dev_amp) {
     m->step_amp = dev_amp;
     bool drm_ahead = false;                                   // some DRM load still uses the two-step (field, force) kernels
     for (auto &d : m->drm_dev)
-        drm_ahead = drm_ahead || !((d.fused || (d.inline_apply && !(m->halo.active || m->pml.present))) && !m->graph_capturing);
-    if (m->overlap && drm_ahead && !m->kernel_timing && !dev_amp) {
+        drm_ahead = drm_ahead || !((d.fused || (d.inline_apply && m->host_step && !(m->halo.active || m->pml.present))) && !m->graph_capturing);
+    if (m->overlap && drm_ahead && !m->kernel_timing && !m->host_step) {
         // DRM forces of step k+1 are computed on side stream 0 while this step runs; its buffer was last read
         // by step k-1, which is complete on the main stream at this point.  They are enqueued BEFORE the bulk
         // kernels: enqueued after them they only get SM slots when the stencil drains and the step serialises

@@ -360,6 +360,7 @@ struct svlgpu_model {
     int h_row_len = 0;
     bool shell_lowreg = false;                      // SVLGPU_SHELL_LOWREG: 96-register shell kernel (co-resides with the stencil)
     int mirror_rec = -1;                            // recorder whose next row k_record also writes to h_row (step_host)
+    bool host_step = false;                         // inside svlgpu_step_host: one step per call, host round trip on the critical path
     const double *step_amp = nullptr;               // host-fed load amplitudes of the step being recorded (reaction pass)
 
     std::vector<svl::DrmDev> drm_dev;
