@@ -2188,13 +2188,13 @@ static int reaction_pass(svlgpu_model *m, int k, const double *dev_amp) {
     return 0;
 }
 
-void record_rows(svlgpu_model *m, bool devk) {
+int record_rows(svlgpu_model *m, bool devk) {
     int ri = -1;
     bool reaction_ready = false;
     const SupArgs sup = sup_args(m);
     if (m->opt_reaction_collective && m->halo.active && !m->halo_peers.empty()) {
         // some rank records reactions: the pass exchanges interface partial forces, so every rank runs it on every step
-        if (reaction_pass(m, m->k_of_step, m->step_amp)) return;
+        if (reaction_pass(m, m->k_of_step, m->step_amp)) return 1;
         reaction_ready = true;
     }
     for (auto &r : m->recorders) {
@@ -2220,8 +2220,9 @@ void record_rows(svlgpu_model *m, bool devk) {
                 r.d_cptr = (int32_t *)up(r.h_cptr.data(), sizeof(int32_t) * r.h_cptr.size());
                 r.d_cdof = (int32_t *)up(r.h_cdof.data(), sizeof(int32_t) * r.h_cdof.size());
                 r.d_ccoef = (double *)up(r.h_ccoef.data(), sizeof(double) * r.h_ccoef.size());
+                if (!r.d_rmass || !r.d_rcd || !r.d_fixed || !r.d_cptr || !r.d_cdof || !r.d_ccoef) { set_error("out of device memory (REACTION recorder tables)"); return 1; }
             }
-            if (!reaction_ready) { if (reaction_pass(m, m->k_of_step, m->step_amp)) return; reaction_ready = true; }
+            if (!reaction_ready) { if (reaction_pass(m, m->k_of_step, m->step_amp)) return 1; reaction_ready = true; }
             ReacArgs a;
             a.n = r.width; a.dofs = r.d_dofs; a.Fs = m->d_fscratch; a.Un = m->d_U[m->next]; a.U = m->d_U[m->cur]; a.Up = m->d_U[m->prev];
             a.mass = r.d_rmass; a.cd = r.d_rcd; a.ccoef = r.d_ccoef; a.fixed = r.d_fixed; a.cptr = r.d_cptr; a.cdof = r.d_cdof;
@@ -2237,6 +2238,7 @@ void record_rows(svlgpu_model *m, bool devk) {
         r.rows++;
         m->total_launches++;
     }
+    return 0;
 }
 
 // incident field + DRM row forces of step k into buffer k & 1, on stream st
@@ -2388,7 +2390,7 @@ static int step_once(svlgpu_model *m, int k, const double *dev_amp) {
         m->total_launches++;
     }
     m->step_amp = dev_amp;
-    record_rows(m, m->graph_capturing);
+    if (record_rows(m, m->graph_capturing)) return 1;
     if (m->use_graph) {                                       // the device-side step counter only serves graph replay
         k_advance<<<1, 1, 0, m->stream>>>(m->d_kctl);
         m->total_launches++;

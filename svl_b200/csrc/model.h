@@ -432,5 +432,5 @@ int external_forces_interface(svlgpu_model *m, int k, const double *dev_amp);   
 void newmark_destroy(svlgpu_model *m);
 int operator_K(svlgpu_model *m, const double *x, double *out);
 int external_forces_raw(svlgpu_model *m, int k, const double *dev_amp, double *b);
-void record_rows(svlgpu_model *m, bool devk);
+int record_rows(svlgpu_model *m, bool devk);
 }  // namespace svl

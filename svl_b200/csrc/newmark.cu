@@ -289,7 +289,7 @@ int newmark_step(svlgpu_model *m, int k, const double *dev_amp) {
     N.total_iters += it; N.solves++;
     k_nm_update<<<kNmBlocks, kNmThreads, 0, st>>>(n, dt, N.d_x, U, Un, N.d_V, N.d_A);
     m->total_launches++;
-    record_rows(m, false);
+    if (record_rows(m, false)) return 1;
     const int old_prev = m->prev;
     m->prev = m->cur; m->cur = m->next; m->next = old_prev;
     m->steps_done++;

@@ -23,6 +23,8 @@
 #include <map>
 #include <memory>
 #include <sstream>
+#include <stdexcept>
+#include <initializer_list>
 #include <string>
 #include <strings.h>
 #include <signal.h>
@@ -50,15 +52,33 @@ std::vector<std::pair<long, const JValue *>> by_tag(const JValue &o) {
 }
 
 // ---- Geometry module (01-Node ... 06-Mesh): plain data, the device owns the arithmetic ----------------------
+// Per-node / per-element lists are short and bounded (<= 9 dofs, <= 8 nodes, <= 10 attributes): kept inline instead of one
+// heap block each -- five std::vector per node were most of the 2.5 GB / 6 s the object graph cost at 4 M elements.
+template <class T, int N> struct Small {
+    T v[N]; unsigned char n = 0;
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    void clear() { n = 0; }
+    void push_back(const T &x) { if (n >= N) throw std::length_error("entity list longer than the path supports"); v[n++] = x; }
+    T &back() { return v[n - 1]; }
+    T &operator[](size_t i) { return v[i]; }
+    const T &operator[](size_t i) const { return v[i]; }
+    T *begin() { return v; }
+    T *end() { return v + n; }
+    const T *begin() const { return v; }
+    const T *end() const { return v + n; }
+    template <class It> void assign(It a, It b) { n = 0; for (; a != b; ++a) push_back(*a); }
+    Small &operator=(std::initializer_list<T> l) { n = 0; for (const T &x : l) push_back(x); return *this; }
+};
 struct Node {            // 01-Node/Node.cpp:3-21
     unsigned tag; int index; int ndof;
-    std::vector<int> total, free;        // as in the file: GLOBAL numbers when the model is partitioned
-    std::vector<int> ltotal, lfree;      // this partition's own compact numbering (several ranks only; else empty)
-    std::vector<double> coords;
+    Small<int, 9> total, free;           // as in the file: GLOBAL numbers when the model is partitioned
+    Small<int, 9> ltotal, lfree;         // this partition's own compact numbering (several ranks only; else empty)
+    Small<double, 3> coords;
 };
 struct Material { unsigned tag; int index; int kind; std::vector<double> par; };      // 02-Materials/Material.hpp
 struct Element {         // 04-Elements/Element.hpp:51-249
-    unsigned tag; int index; int kind; std::vector<unsigned> conn; unsigned material; std::vector<double> attr;
+    unsigned tag; int index; int kind; Small<unsigned, 8> conn; unsigned material; Small<double, 10> attr;
 };
 struct Load {            // 05-Loads/Load.cpp
     unsigned tag; bool drm = false, support = false;      // support: POINTLOAD_SUPPORT_MOTION (Driver.hpp:1725-1735)
@@ -465,7 +485,7 @@ class CentralDifference {
         for (auto &kv : mesh.Nodes) {
             const Node &n = kv.second;
             ndof.push_back(n.ndof);
-            const std::vector<int> &tt = n.ltotal.empty() ? n.total : n.ltotal, &ff = n.lfree.empty() ? n.free : n.lfree;
+            const Small<int, 9> &tt = n.ltotal.empty() ? n.total : n.ltotal, &ff = n.lfree.empty() ? n.free : n.lfree;
             total.insert(total.end(), tt.begin(), tt.end());
             freed.insert(freed.end(), ff.begin(), ff.end());
             for (int c = 0; c < mesh.ndim; c++) xyz.push_back(c < (int)n.coords.size() ? n.coords[c] : 0.0);

@@ -387,3 +387,45 @@ def test_rank_file_generator_tool_output_is_planned_by_the_driver(tmp_path):
     assert p.returncode == 0, p.stdout + p.stderr
     heads = [l for l in p.stdout.splitlines() if " nodes " in l]
     assert len(heads) == 4 and all("pml_collective 1" in l for l in heads)
+
+
+def test_weighted_bisection_balances_the_pml_shell_with_planar_cuts():
+    """partition.weighted_epart: recursive coordinate bisection with PML elements weighted 250x (what the block solve costs on the
+    device): every rank gets (nearly) the same number of PML elements, every element exactly one rank, and the cuts are planes
+    (all elements of one layer along the cut axis go to the same side) -- the geometric split leaves 37 % more PML on the bottom ranks."""
+    import cases as _c
+    from svl_b200 import model as M, partition as P
+    m = M.make_pml_model((24, 24, 24), 6, 1.0, soil=(M.ELASTIC3DLINEAR, _c.SOIL), nt=10)
+    pml = np.isin(m.elem_kind, (3, 4))
+    for grid in ((1, 1, 2), (1, 2, 2), (2, 2, 2)):
+        n = int(np.prod(grid))
+        ep = P.weighted_epart(m, grid)
+        assert ep.min() == 0 and ep.max() == n - 1 and len(ep) == m.n_elem
+        w = np.array([(pml & (ep == r)).sum() for r in range(n)])
+        g = np.array([(pml & (P.centroid_epart(m, grid) == r)).sum() for r in range(n)])
+        assert w.max() / w.min() < 1.08 < g.max() / g.min()
+        # planar cut along z: the z-slab index of an element is a function of its centroid height alone
+        cz = np.round(m.coords[m.elem_conn[:, :8]].mean(axis=1)[:, 2], 6)
+        slab = ep // (grid[0] * grid[1])
+        for z in np.unique(cz):
+            assert len(np.unique(slab[cz == z])) == 1
+        subs = P.split_model(m, ep, n)
+        assert sum(s.n_elem for s in subs) == m.n_elem
+        for r, s in enumerate(subs):
+            for p_, nodes in s.halos.items():
+                assert (s.global_nodes[nodes] == subs[p_].global_nodes[subs[p_].halos[r]]).all()
+
+
+def test_shuffled_numbering_is_the_same_model(oracle):
+    """model.shuffle_numbering (random node ids and element order: the input of the neighbour-list node classes and of the
+    planner's locality renumbering) describes the same physics: the oracle's histories agree to rounding."""
+    import cases as _c
+    from svl_b200 import model as M
+    for name in ("hex8_layered_rayleigh", "drm_box", "quad4_area", "lysmer_column", "kat444_masses"):
+        m = _c.CASES[name]()
+        s = M.shuffle_numbering(m, 3)
+        assert s.n_nodes == m.n_nodes and s.n_elem == m.n_elem and not s.blocks
+        assert not np.array_equal(s.elem_conn, m.elem_conn)
+        a, _ = oracle.run(m)
+        b, _ = oracle.run(s)
+        assert _c.rel_err(b, a) < 1e-11, name
