@@ -39,13 +39,24 @@ def test_oracle_history_matches_reference_executable(oracle, name):
 
 
 def test_oracle_matches_reference_executable_on_the_mid_size_j2_column(oracle):
-    """configs[4] shape (10 x 10 x 40 lin3DHexa8 + Plastic3DJ2, loaded into yield) against the reference executable.  (The two
-    mid-size PML goldens are device-only checks: the oracle's dense LDL^T of the coupled block would take an hour.)"""
+    """configs[4] shape (10 x 10 x 40 lin3DHexa8 + Plastic3DJ2, loaded into yield) against the reference executable.  (The
+    mid-size PML2D golden is checked against the oracle by the opt-in test below: 7 minutes of envelope LDL^T.)"""
     m = cases.mid_j2()
     g = gold("mid_j2")
     assert str(g["fingerprint"]) == cases.fingerprint(m)
     out, _ = oracle.run(m, nthreads=8)
     assert cases.rel_err(out, g["disp"]) < cases.TOL["mid_j2"]
+
+
+@pytest.mark.skipif(os.environ.get("SVL_SLOW_TESTS", "0") != "1", reason="7 minutes of envelope LDL^T on one core: SVL_SLOW_TESTS=1 "
+                    "(measured 2.8e-13 against the reference executable's golden, DESIGN.md section 4)")
+def test_oracle_matches_reference_executable_on_the_mid_size_quad4_pml_model(oracle):
+    """configs[1] shape (200 x 100 lin2DQuad4 + 5-cell PML2DQuad4 layer, 16 000 coupled unknowns) against the reference executable."""
+    m = cases.mid_quad4_pml()
+    g = gold("mid_quad4_pml")
+    assert str(g["fingerprint"]) == cases.fingerprint(m)
+    out, _ = oracle.run(m, nthreads=8)
+    assert cases.rel_err(out, g["disp"]) < cases.TOL["mid_quad4_pml"]
 
 
 @pytest.mark.parametrize("name", list(cases.REACTION_CASES))
